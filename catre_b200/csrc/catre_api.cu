@@ -1,0 +1,717 @@
+// libcatre_b200.so -- C ABI (include/catre_b200.h) and the host-side driver of the kernel chain.
+// One engine per device; all work is enqueued on the caller's stream.
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/catre_b200.h"
+#include "simt_kernels.cuh"
+#include "tc_kernels.cuh"
+
+using namespace catre;
+
+namespace {
+
+thread_local std::string g_create_error;
+
+struct WeightSpec {
+  const char* name;
+  int ndim;
+  long long shape[3];  // -1 in shape[1] of conv_p = n_obs + n_prior
+};
+
+// the 74 checkpoint tensors in checkpoint order
+const WeightSpec kWeights[] = {
+    {"pcl_net.stn.conv1.weight", 3, {64, 3, 1}},      {"pcl_net.stn.conv1.bias", 1, {64}},
+    {"pcl_net.stn.conv2.weight", 3, {128, 64, 1}},    {"pcl_net.stn.conv2.bias", 1, {128}},
+    {"pcl_net.stn.conv3.weight", 3, {1024, 128, 1}},  {"pcl_net.stn.conv3.bias", 1, {1024}},
+    {"pcl_net.stn.fc1.weight", 2, {512, 1024}},       {"pcl_net.stn.fc1.bias", 1, {512}},
+    {"pcl_net.stn.fc2.weight", 2, {256, 512}},        {"pcl_net.stn.fc2.bias", 1, {256}},
+    {"pcl_net.stn.fc3.weight", 2, {9, 256}},          {"pcl_net.stn.fc3.bias", 1, {9}},
+    {"pcl_net.conv1.weight", 3, {64, 3, 1}},          {"pcl_net.conv1.bias", 1, {64}},
+    {"pcl_net.conv2.weight", 3, {128, 64, 1}},        {"pcl_net.conv2.bias", 1, {128}},
+    {"pcl_net.conv3.weight", 3, {512, 128, 1}},       {"pcl_net.conv3.bias", 1, {512}},
+    {"pcl_net.conv4.weight", 3, {1024, 512, 1}},      {"pcl_net.conv4.bias", 1, {1024}},
+    {"pcl_net.fstn.conv1.weight", 3, {64, 64, 1}},    {"pcl_net.fstn.conv1.bias", 1, {64}},
+    {"pcl_net.fstn.conv2.weight", 3, {128, 64, 1}},   {"pcl_net.fstn.conv2.bias", 1, {128}},
+    {"pcl_net.fstn.conv3.weight", 3, {1024, 128, 1}}, {"pcl_net.fstn.conv3.bias", 1, {1024}},
+    {"pcl_net.fstn.fc1.weight", 2, {512, 1024}},      {"pcl_net.fstn.fc1.bias", 1, {512}},
+    {"pcl_net.fstn.fc2.weight", 2, {256, 512}},       {"pcl_net.fstn.fc2.bias", 1, {256}},
+    {"pcl_net.fstn.fc3.weight", 2, {4096, 256}},      {"pcl_net.fstn.fc3.bias", 1, {4096}},
+    {"rot_head.rot_head_x.norm.weight", 1, {256}},    {"rot_head.rot_head_x.norm.bias", 1, {256}},
+    {"rot_head.rot_head_x.layers.0.weight", 3, {256, 1088, 1}}, {"rot_head.rot_head_x.layers.0.bias", 1, {256}},
+    {"rot_head.rot_head_x.layers.1.weight", 1, {256}}, {"rot_head.rot_head_x.layers.1.bias", 1, {256}},
+    {"rot_head.rot_head_x.layers.3.weight", 3, {256, 256, 1}}, {"rot_head.rot_head_x.layers.3.bias", 1, {256}},
+    {"rot_head.rot_head_x.layers.4.weight", 1, {256}}, {"rot_head.rot_head_x.layers.4.bias", 1, {256}},
+    {"rot_head.rot_head_x.neck.0.weight", 3, {3, 256, 1}}, {"rot_head.rot_head_x.neck.0.bias", 1, {3}},
+    {"rot_head.rot_head_x.conv_p.weight", 3, {1, -1, 1}}, {"rot_head.rot_head_x.conv_p.bias", 1, {1}},
+    {"rot_head.rot_head_y.norm.weight", 1, {256}},    {"rot_head.rot_head_y.norm.bias", 1, {256}},
+    {"rot_head.rot_head_y.layers.0.weight", 3, {256, 1088, 1}}, {"rot_head.rot_head_y.layers.0.bias", 1, {256}},
+    {"rot_head.rot_head_y.layers.1.weight", 1, {256}}, {"rot_head.rot_head_y.layers.1.bias", 1, {256}},
+    {"rot_head.rot_head_y.layers.3.weight", 3, {256, 256, 1}}, {"rot_head.rot_head_y.layers.3.bias", 1, {256}},
+    {"rot_head.rot_head_y.layers.4.weight", 1, {256}}, {"rot_head.rot_head_y.layers.4.bias", 1, {256}},
+    {"rot_head.rot_head_y.neck.0.weight", 3, {3, 256, 1}}, {"rot_head.rot_head_y.neck.0.bias", 1, {3}},
+    {"rot_head.rot_head_y.conv_p.weight", 3, {1, -1, 1}}, {"rot_head.rot_head_y.conv_p.bias", 1, {1}},
+    {"ts_head.norm.weight", 1, {256}},                {"ts_head.norm.bias", 1, {256}},
+    {"ts_head.linears.0.weight", 2, {256, 1091}},     {"ts_head.linears.0.bias", 1, {256}},
+    {"ts_head.linears.1.weight", 1, {256}},           {"ts_head.linears.1.bias", 1, {256}},
+    {"ts_head.linears.3.weight", 2, {256, 256}},      {"ts_head.linears.3.bias", 1, {256}},
+    {"ts_head.linears.4.weight", 1, {256}},           {"ts_head.linears.4.bias", 1, {256}},
+    {"ts_head.fc_t.weight", 2, {3, 256}},             {"ts_head.fc_t.bias", 1, {3}},
+    {"ts_head.fc_s.weight", 2, {3, 256}},             {"ts_head.fc_s.bias", 1, {3}},
+};
+constexpr int kNumWeights = sizeof(kWeights) / sizeof(kWeights[0]);
+
+// kernel groups for launch accounting / per-group device timing
+enum Grp {
+  G_FILL, G_UPDATE_POINTS, G_FRONT3, G_STN_CONV2, G_STN_CONV3_MAX, G_TNET_FC, G_FSTN_CONV1, G_FSTN_CONV2,
+  G_FSTN_CONV3_MAX, G_FEAT_TRANSFORM, G_CONV2, G_CONV3, G_CONV4_MAX, G_ROT_GFEAT, G_ROT_LAYER0, G_GN_FINALIZE,
+  G_ROT_LAYER1, G_ROT_TAIL, G_TS_POSE, G_SPLIT, G_NUM
+};
+const char* kGrpNames[G_NUM] = {
+    "fill", "update_points", "front3", "stn_conv2", "stn_conv3_max", "tnet_fc", "fstn_conv1", "fstn_conv2",
+    "fstn_conv3_max", "feat_transform", "conv2", "conv3", "conv4_max", "rot_gfeat", "rot_layer0", "gn_finalize",
+    "rot_layer1", "rot_tail", "ts_pose", "split_bf16"};
+
+}  // namespace
+
+struct catre_engine {
+  catre_cfg cfg{};
+  std::string err;
+  int N = 0;          // points per set
+  int maxB = 0;
+  bool packed = false;
+  std::map<std::string, std::vector<float>> hw;  // host copies of the checkpoint tensors
+  std::vector<void*> dev_allocs;
+
+  // ---- device weights (fp32)
+  std::map<std::string, float*> dw;
+  float *stn_fc3_bI = nullptr, *fstn_fc3_bI = nullptr;
+  float *rot_w0g = nullptr, *rot_b0 = nullptr, *rot_w0p = nullptr;
+  float *rot_gn0_g = nullptr, *rot_gn0_b = nullptr, *rot_gn1_g = nullptr, *rot_gn1_b = nullptr;
+  float *rot_b1 = nullptr, *neck_w = nullptr, *neck_b = nullptr, *wp = nullptr, *convp_b = nullptr;
+  float *ts_w0t = nullptr, *ts_w1t = nullptr;
+  TcWeights tcw;  // bf16 hi/lo copies + tensor maps (tensor-core modes)
+
+  // ---- workspace
+  float *q = nullptr, *h64a = nullptr, *h64b = nullptr, *h128 = nullptr, *h512 = nullptr, *a0 = nullptr, *a1 = nullptr;
+  int *gmax_all = nullptr, *gmax_stn = nullptr, *gmax_fstn = nullptr, *gmax_g = nullptr, *gmax_pf = nullptr;
+  float *fc512 = nullptr, *fc256 = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
+  float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
+  TcWorkspace tcws;
+  size_t ws_bytes = 0;
+  // staging for catre_refine_host
+  float *st_pcl = nullptr, *st_prior = nullptr, *st_pose = nullptr, *st_scale = nullptr, *st_K = nullptr;
+  float *st_oposes = nullptr, *st_oscales = nullptr;
+  static constexpr int kMaxHostIter = 16;
+
+  // ---- accounting
+  int64_t launches = 0;
+  bool prof_on = false;
+  struct Ev { int grp; cudaEvent_t a, b; };
+  std::vector<Ev> ev_pending;
+  std::vector<cudaEvent_t> ev_pool;
+  double prof_ms[G_NUM] = {0};
+  int64_t prof_n[G_NUM] = {0};
+};
+
+namespace {
+
+int fail(catre_engine* e, int code, const char* fmt, ...) {
+  char buf[512];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  if (e) e->err = buf; else g_create_error = buf;
+  return code;
+}
+
+#define CU_TRY(e, call)                                                                           \
+  do {                                                                                            \
+    cudaError_t _st = (call);                                                                     \
+    if (_st != cudaSuccess)                                                                       \
+      return fail(e, CATRE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(_st), __FILE__, __LINE__); \
+  } while (0)
+
+template <typename T>
+int dalloc(catre_engine* e, T** p, size_t n) {
+  void* v = nullptr;
+  size_t bytes = n * sizeof(T);
+  if (bytes == 0) bytes = 16;
+  CU_TRY(e, cudaMalloc(&v, bytes));
+  e->dev_allocs.push_back(v);
+  e->ws_bytes += bytes;
+  *p = reinterpret_cast<T*>(v);
+  return 0;
+}
+
+int upload(catre_engine* e, float** p, const std::vector<float>& h) {
+  int rc = dalloc(e, p, h.size());
+  if (rc) return rc;
+  CU_TRY(e, cudaMemcpy(*p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice));
+  return 0;
+}
+
+// ---- launch bookkeeping ------------------------------------------------------------------------
+struct Launch {
+  catre_engine* e;
+  cudaStream_t s;
+  int grp;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Launch(catre_engine* e_, cudaStream_t s_, int g) : e(e_), s(s_), grp(g) {
+    e->launches++;
+    if (e->prof_on) {
+      auto get = [&]() {
+        cudaEvent_t ev;
+        if (!e->ev_pool.empty()) { ev = e->ev_pool.back(); e->ev_pool.pop_back(); }
+        else cudaEventCreate(&ev);
+        return ev;
+      };
+      a = get(); b = get();
+      cudaEventRecord(a, s);
+    }
+  }
+  ~Launch() {
+    if (e->prof_on) {
+      cudaEventRecord(b, s);
+      e->ev_pending.push_back({grp, a, b});
+    }
+  }
+};
+
+int check_launch(catre_engine* e, const char* what) {
+  cudaError_t st = cudaPeekAtLastError();
+  if (st != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e, CATRE_ERR_CUDA, "launch of %s failed: %s", what, cudaGetErrorString(st));
+  }
+  return 0;
+}
+
+GemmP gemm_args(const float* A, int lda, const float* W, int K, int C, const float* bias, float* out, int ldo,
+                long long R, int relu) {
+  GemmP p{};
+  p.A = A; p.lda = lda; p.W = W; p.wcs = K; p.wks = 1; p.w_set_stride = 0;
+  p.bias = bias; p.rowvec = nullptr; p.ldrv = 0; p.out = out; p.ldo = ldo; p.gmax = nullptr; p.stats = nullptr;
+  p.stats_ld = 0; p.stats_goff = 0;
+  p.gn_scale = p.gn_shift = nullptr; p.ldgn = 0;
+  p.R = (int)R; p.C = C; p.K = K; p.rows_per_set = 1; p.rows_per_obj = 1; p.relu = relu;
+  return p;
+}
+
+template <int BN, int AMODE>
+int run_gemm(catre_engine* e, cudaStream_t s, int grp, const GemmP& p) {
+  dim3 grid((p.C + BN - 1) / BN, (p.R + 127) / 128);
+  {
+    Launch l(e, s, grp);
+    pw_gemm_kernel<BN, AMODE><<<grid, 256, 0, s>>>(p);
+  }
+  return check_launch(e, kGrpNames[grp]);
+}
+
+int fill_i32(catre_engine* e, cudaStream_t s, int* p, long long n, int v) {
+  int blocks = (int)((n + 255) / 256);
+  if (blocks > 148 * 8) blocks = 148 * 8;
+  if (blocks < 1) blocks = 1;
+  {
+    Launch l(e, s, G_FILL);
+    fill_i32_kernel<<<blocks, 256, 0, s>>>(p, n, v);
+  }
+  return check_launch(e, "fill");
+}
+
+const float* W(catre_engine* e, const char* name) { return e->dw.at(name); }
+
+// T-Net FC chain: keys [S,1024] -> 512 -> 256 -> kk  (pointnets/pointnet.py:32-40, 66-77)
+int tnet_fc(catre_engine* e, cudaStream_t s, const int* keys, int S, const char* prefix, const float* fc3_bias_I,
+            int kk, float* out) {
+  std::string pf(prefix);
+  int rc;
+  GemmP p = gemm_args(reinterpret_cast<const float*>(keys), 1024, W(e, (pf + ".fc1.weight").c_str()), 1024, 512,
+                      W(e, (pf + ".fc1.bias").c_str()), e->fc512, 512, S, 1);
+  if ((rc = run_gemm<128, A_KEY>(e, s, G_TNET_FC, p))) return rc;
+  p = gemm_args(e->fc512, 512, W(e, (pf + ".fc2.weight").c_str()), 512, 256, W(e, (pf + ".fc2.bias").c_str()), e->fc256,
+                256, S, 1);
+  if ((rc = run_gemm<128, A_PLAIN>(e, s, G_TNET_FC, p))) return rc;
+  p = gemm_args(e->fc256, 256, W(e, (pf + ".fc3.weight").c_str()), 256, kk, fc3_bias_I, out, kk, S, 0);
+  if (kk <= 64) return run_gemm<64, A_PLAIN>(e, s, G_TNET_FC, p);
+  return run_gemm<128, A_PLAIN>(e, s, G_TNET_FC, p);
+}
+
+// One refinement iteration on a chunk of B objects whose points are already in e->q.
+int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, const float* scale_in, const float* K,
+              float* pose_out, float* scale_out) {
+  const int N = e->N, S = 2 * B, P = 2 * N;
+  const long long R = (long long)S * N;
+  int rc;
+  const bool tc = e->cfg.precision != CATRE_PREC_FP32_SIMT;
+
+  if ((rc = fill_i32(e, s, e->gmax_all, (long long)S * (1024 * 3 + 64), KEY_NEG_INF))) return rc;
+
+  // ---- E1: STN3d (pointnets/pointnet.py:24-41)
+  {
+    Launch l(e, s, G_FRONT3);
+    front3_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(e->q, nullptr, W(e, "pcl_net.stn.conv1.weight"),
+                                                                  W(e, "pcl_net.stn.conv1.bias"), e->h64a, R, N);
+  }
+  if ((rc = check_launch(e, "front3"))) return rc;
+  if (tc) {
+    if ((rc = tc_tnet_trunk(e->tcw, e->tcws, s, e->h64a, /*fstn=*/false, R, N, e->gmax_stn, e))) return rc;
+  } else {
+    GemmP p = gemm_args(e->h64a, 64, W(e, "pcl_net.stn.conv2.weight"), 64, 128, W(e, "pcl_net.stn.conv2.bias"), e->h128,
+                        128, R, 1);
+    if ((rc = run_gemm<128, A_PLAIN>(e, s, G_STN_CONV2, p))) return rc;
+    p = gemm_args(e->h128, 128, W(e, "pcl_net.stn.conv3.weight"), 128, 1024, W(e, "pcl_net.stn.conv3.bias"), nullptr, 0,
+                  R, 1);
+    p.gmax = e->gmax_stn; p.rows_per_set = N;
+    if ((rc = run_gemm<128, A_PLAIN>(e, s, G_STN_CONV3_MAX, p))) return rc;
+  }
+  if ((rc = tnet_fc(e, s, e->gmax_stn, S, "pcl_net.stn", e->stn_fc3_bI, 9, e->t3))) return rc;
+
+  // ---- E2: input transform + conv1 (pointnet.py:97-103)
+  {
+    Launch l(e, s, G_FRONT3);
+    front3_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(e->q, e->t3, W(e, "pcl_net.conv1.weight"),
+                                                                  W(e, "pcl_net.conv1.bias"), e->h64a, R, N);
+  }
+  if ((rc = check_launch(e, "front3"))) return rc;
+
+  // ---- E3: STNkd (pointnet.py:57-78)
+  if (tc) {
+    if ((rc = tc_tnet_trunk(e->tcw, e->tcws, s, e->h64a, /*fstn=*/true, R, N, e->gmax_fstn, e))) return rc;
+  } else {
+    GemmP p = gemm_args(e->h64a, 64, W(e, "pcl_net.fstn.conv1.weight"), 64, 64, W(e, "pcl_net.fstn.conv1.bias"), e->h64b,
+                        64, R, 1);
+    if ((rc = run_gemm<64, A_PLAIN>(e, s, G_FSTN_CONV1, p))) return rc;
+    p = gemm_args(e->h64b, 64, W(e, "pcl_net.fstn.conv2.weight"), 64, 128, W(e, "pcl_net.fstn.conv2.bias"), e->h128, 128,
+                  R, 1);
+    if ((rc = run_gemm<128, A_PLAIN>(e, s, G_FSTN_CONV2, p))) return rc;
+    p = gemm_args(e->h128, 128, W(e, "pcl_net.fstn.conv3.weight"), 128, 1024, W(e, "pcl_net.fstn.conv3.bias"), nullptr,
+                  0, R, 1);
+    p.gmax = e->gmax_fstn; p.rows_per_set = N;
+    if ((rc = run_gemm<128, A_PLAIN>(e, s, G_FSTN_CONV3_MAX, p))) return rc;
+  }
+  if ((rc = tnet_fc(e, s, e->gmax_fstn, S, "pcl_net.fstn", e->fstn_fc3_bI, 4096, e->t64))) return rc;
+
+  // ---- E4: feature transform pf = h1 . T64 (per set), trunk conv2-4, global max (pointnet.py:105-116)
+  {
+    GemmP p = gemm_args(e->h64a, 64, e->t64, 64, 64, nullptr, e->h64b, 64, R, 0);
+    p.wcs = 1; p.wks = 64; p.w_set_stride = 4096; p.rows_per_set = N;
+    p.gmax = e->gmax_pf;
+    if ((rc = run_gemm<64, A_PLAIN>(e, s, G_FEAT_TRANSFORM, p))) return rc;
+  }
+  if (tc) {
+    if ((rc = tc_trunk(e->tcw, e->tcws, s, e->h64b, R, N, e->gmax_g, e))) return rc;
+  } else {
+    GemmP p = gemm_args(e->h64b, 64, W(e, "pcl_net.conv2.weight"), 64, 128, W(e, "pcl_net.conv2.bias"), e->h128, 128, R, 1);
+    if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV2, p))) return rc;
+    p = gemm_args(e->h128, 128, W(e, "pcl_net.conv3.weight"), 128, 512, W(e, "pcl_net.conv3.bias"), e->h512, 512, R, 1);
+    if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV3, p))) return rc;
+    p = gemm_args(e->h512, 512, W(e, "pcl_net.conv4.weight"), 512, 1024, W(e, "pcl_net.conv4.bias"), nullptr, 0, R, 0);
+    p.gmax = e->gmax_g; p.rows_per_set = N;
+    if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV4_MAX, p))) return rc;
+  }
+
+  // ---- R1: rotation heads (heads/conv_out_per_rot_head.py:62-71,126-140) with the layer-0 split:
+  //      layers.0 . [g_set | pf_p] = W0[:, :1024] . g_set (once per set) + W0[:, 1024:] . pf_p
+  {
+    GemmP p = gemm_args(reinterpret_cast<const float*>(e->gmax_g), 1024, e->rot_w0g, 1024, 512, e->rot_b0, e->cset, 512, S, 0);
+    if ((rc = run_gemm<128, A_KEY>(e, s, G_ROT_GFEAT, p))) return rc;
+  }
+  if (tc) {
+    if ((rc = tc_rot_layers(e->tcw, e->tcws, s, e->h64b, e->cset, R, N, e->a0, e->a1, e->stats0, e->stats1, e->gn0,
+                            e->rot_gn0_g, e->rot_gn0_b, B, e))) return rc;
+  } else {
+    GemmP p = gemm_args(e->h64b, 64, e->rot_w0p, 64, 512, nullptr, e->a0, 512, R, 0);
+    p.rowvec = e->cset; p.ldrv = 512; p.rows_per_set = N; p.rows_per_obj = P;
+    p.stats = e->stats0; p.stats_ld = 64; p.stats_goff = 0;
+    if ((rc = run_gemm<128, A_PLAIN>(e, s, G_ROT_LAYER0, p))) return rc;
+    {
+      Launch l(e, s, G_GN_FINALIZE);
+      gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats0, e->rot_gn0_g, e->rot_gn0_b, e->gn0,
+                                                             e->gn0 + (size_t)e->maxB * 512, B, 512, P / 128, P);
+    }
+    if ((rc = check_launch(e, "gn_finalize"))) return rc;
+    for (int h = 0; h < 2; ++h) {
+      const char* wn = h == 0 ? "rot_head.rot_head_x.layers.3.weight" : "rot_head.rot_head_y.layers.3.weight";
+      GemmP p1 = gemm_args(e->a0 + h * 256, 512, W(e, wn), 256, 256, e->rot_b1 + h * 256, e->a1 + h * 256, 512, R, 0);
+      p1.rows_per_set = N; p1.rows_per_obj = P;
+      p1.gn_scale = e->gn0 + h * 256; p1.gn_shift = e->gn0 + (size_t)e->maxB * 512 + h * 256; p1.ldgn = 512;
+      p1.stats = e->stats1; p1.stats_ld = 64; p1.stats_goff = 32 * h;
+      if ((rc = run_gemm<128, A_GN_GELU>(e, s, G_ROT_LAYER1, p1))) return rc;
+    }
+  }
+  {
+    Launch l(e, s, G_GN_FINALIZE);
+    gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats1, e->rot_gn1_g, e->rot_gn1_b, e->gn1,
+                                                           e->gn1 + (size_t)e->maxB * 512, B, 512, P / 128, P);
+  }
+  if ((rc = check_launch(e, "gn_finalize"))) return rc;
+  {
+    Launch l(e, s, G_ROT_TAIL);
+    rot_tail_kernel<<<dim3(P / 128, B), 256, 0, s>>>(e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
+                                                    e->wp, e->rot_partial, P);
+  }
+  if ((rc = check_launch(e, "rot_tail"))) return rc;
+
+  // ---- H1 + G1 + G2
+  {
+    TsPoseP p{};
+    p.gmax_g = e->gmax_g; p.gmax_pf = e->gmax_pf;
+    p.w0t = e->ts_w0t; p.b0 = W(e, "ts_head.linears.0.bias"); p.g0 = W(e, "ts_head.linears.1.weight");
+    p.be0 = W(e, "ts_head.linears.1.bias");
+    p.w1t = e->ts_w1t; p.b1 = W(e, "ts_head.linears.3.bias"); p.g1 = W(e, "ts_head.linears.4.weight");
+    p.be1 = W(e, "ts_head.linears.4.bias");
+    p.wt = W(e, "ts_head.fc_t.weight"); p.bt = W(e, "ts_head.fc_t.bias");
+    p.ws = W(e, "ts_head.fc_s.weight"); p.bs = W(e, "ts_head.fc_s.bias");
+    p.rot_partial = e->rot_partial; p.rot_tiles = P / 128; p.convp_bias = e->convp_b;
+    p.pose_in = pose_in; p.scale_in = scale_in; p.K = K; p.pose_out = pose_out; p.scale_out = scale_out;
+    Launch l(e, s, G_TS_POSE);
+    ts_pose_kernel<<<B, 256, 0, s>>>(p);
+  }
+  return check_launch(e, "ts_pose");
+}
+
+int check_ready(catre_engine* e, int B) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  if (!e->packed) return fail(e, CATRE_ERR_NOT_PACKED, "catre_pack has not been called (or weights changed since)");
+  if (B < 0) return fail(e, CATRE_ERR_INVALID_ARG, "negative batch %d", B);
+  return 0;
+}
+
+}  // namespace
+
+// ================================================================================================
+extern "C" {
+
+const char* catre_version(void) { return "catre_b200 0.1 sm_100a (fp32 SIMT + tcgen05 bf16x3)"; }
+int32_t catre_num_weights(void) { return kNumWeights; }
+const char* catre_weight_name(int32_t i) { return (i >= 0 && i < kNumWeights) ? kWeights[i].name : nullptr; }
+int32_t catre_profile_num(void) { return G_NUM; }
+const char* catre_profile_name(int32_t i) { return (i >= 0 && i < G_NUM) ? kGrpNames[i] : nullptr; }
+
+const char* catre_last_error(const catre_engine* e) { return e ? e->err.c_str() : g_create_error.c_str(); }
+
+int catre_create(catre_engine** out, const catre_cfg* cfg) {
+  if (!out || !cfg) return fail(nullptr, CATRE_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  if (cfg->n_obs <= 0 || cfg->n_obs % 128 != 0)
+    return fail(nullptr, CATRE_ERR_UNSUPPORTED, "n_obs=%d must be a positive multiple of 128", cfg->n_obs);
+  if (cfg->n_prior != cfg->n_obs)
+    return fail(nullptr, CATRE_ERR_UNSUPPORTED, "n_prior=%d must equal n_obs=%d in this version", cfg->n_prior, cfg->n_obs);
+  if (cfg->max_batch < 1) return fail(nullptr, CATRE_ERR_INVALID_ARG, "max_batch=%d must be >= 1", cfg->max_batch);
+  if (cfg->precision < CATRE_PREC_FP32_SIMT || cfg->precision > CATRE_PREC_BF16)
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "unknown precision %d", cfg->precision);
+  if (cfg->precision != CATRE_PREC_FP32_SIMT && cfg->n_obs % 256 != 0)
+    return fail(nullptr, CATRE_ERR_UNSUPPORTED, "tensor-core modes need n_obs %% 256 == 0 (got %d)", cfg->n_obs);
+  int ndev = 0;
+  cudaError_t st = cudaGetDeviceCount(&ndev);
+  if (st != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(nullptr, CATRE_ERR_NO_DEVICE, "no CUDA device: %s", cudaGetErrorString(st));
+  }
+  if (cfg->device < 0 || cfg->device >= ndev) return fail(nullptr, CATRE_ERR_INVALID_ARG, "device %d out of range", cfg->device);
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, cfg->device) != cudaSuccess || prop.major != 10)
+    return fail(nullptr, CATRE_ERR_NO_DEVICE, "device %d is not an sm_100 (Blackwell) GPU", cfg->device);
+  if (cudaSetDevice(cfg->device) != cudaSuccess) return fail(nullptr, CATRE_ERR_CUDA, "cudaSetDevice failed");
+
+  catre_engine* e = new catre_engine();
+  e->cfg = *cfg;
+  e->N = cfg->n_obs;
+  e->maxB = cfg->max_batch;
+  const size_t B = e->maxB, S = 2 * B, N = e->N, R = S * N, P = 2 * N;
+  int rc = 0;
+  const bool tc = cfg->precision != CATRE_PREC_FP32_SIMT;
+  rc |= dalloc(e, &e->q, R * 3);
+  rc |= dalloc(e, &e->h64a, R * 64);
+  rc |= dalloc(e, &e->h64b, R * 64);
+  if (!tc) {
+    rc |= dalloc(e, &e->h128, R * 128);
+    rc |= dalloc(e, &e->h512, R * 512);
+  }
+  rc |= dalloc(e, &e->a0, R * 512);
+  rc |= dalloc(e, &e->a1, R * 512);
+  rc |= dalloc(e, &e->gmax_all, S * (1024 * 3 + 64));
+  e->gmax_stn = e->gmax_all;
+  e->gmax_fstn = e->gmax_all + S * 1024;
+  e->gmax_g = e->gmax_all + S * 2048;
+  e->gmax_pf = e->gmax_all + S * 3072;
+  rc |= dalloc(e, &e->fc512, S * 512);
+  rc |= dalloc(e, &e->fc256, S * 256);
+  rc |= dalloc(e, &e->t3, S * 9 + 7);
+  rc |= dalloc(e, &e->t64, S * 4096);
+  rc |= dalloc(e, &e->cset, S * 512);
+  rc |= dalloc(e, &e->stats0, (R / 128) * 64 * 2);
+  rc |= dalloc(e, &e->stats1, (R / 128) * 64 * 2);
+  rc |= dalloc(e, &e->gn0, B * 512 * 2);
+  rc |= dalloc(e, &e->gn1, B * 512 * 2);
+  rc |= dalloc(e, &e->rot_partial, B * (P / 128) * 6);
+  rc |= dalloc(e, &e->st_pcl, B * N * 3);
+  rc |= dalloc(e, &e->st_prior, B * N * 3);
+  rc |= dalloc(e, &e->st_pose, B * 12);
+  rc |= dalloc(e, &e->st_scale, B * 3);
+  rc |= dalloc(e, &e->st_K, B * 9);
+  rc |= dalloc(e, &e->st_oposes, B * 12 * (catre_engine::kMaxHostIter + 1));
+  rc |= dalloc(e, &e->st_oscales, B * 3 * (catre_engine::kMaxHostIter + 1));
+  if (!rc && tc) {
+    size_t bytes = 0;
+    rc = tc_workspace_alloc(e->tcws, R, e->dev_allocs, &bytes, e);
+    e->ws_bytes += bytes;
+  }
+  if (rc) {
+    g_create_error = e->err;
+    catre_destroy(e);
+    return CATRE_ERR_CUDA;
+  }
+  *out = e;
+  return CATRE_OK;
+}
+
+void catre_destroy(catre_engine* e) {
+  if (!e) return;
+  cudaSetDevice(e->cfg.device);
+  for (void* p : e->dev_allocs) cudaFree(p);
+  for (auto& ev : e->ev_pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
+  for (auto ev : e->ev_pool) cudaEventDestroy(ev);
+  delete e;
+}
+
+int catre_set_weight(catre_engine* e, const char* name, const float* data, const int64_t* shape, int32_t ndim) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  if (!name || !data || !shape) return fail(e, CATRE_ERR_INVALID_ARG, "null argument");
+  const WeightSpec* spec = nullptr;
+  for (int i = 0; i < kNumWeights; ++i)
+    if (strcmp(kWeights[i].name, name) == 0) spec = &kWeights[i];
+  if (!spec) return fail(e, CATRE_ERR_UNKNOWN_WEIGHT, "unknown weight '%s'", name);
+  if (ndim != spec->ndim) return fail(e, CATRE_ERR_SHAPE, "%s: expected %d dims, got %d", name, spec->ndim, ndim);
+  size_t n = 1;
+  for (int d = 0; d < ndim; ++d) {
+    long long want = spec->shape[d] == -1 ? (long long)(e->cfg.n_obs + e->cfg.n_prior) : spec->shape[d];
+    if (shape[d] != want)
+      return fail(e, CATRE_ERR_SHAPE, "%s: dim %d is %lld, expected %lld%s", name, d, (long long)shape[d], want,
+                  spec->shape[d] == -1 ? " (= n_obs + n_prior: conv_p is tied to the point count)" : "");
+    n *= (size_t)want;
+  }
+  std::vector<float>& h = e->hw[name];
+  h.resize(n);
+  CU_TRY(e, cudaMemcpy(h.data(), data, n * sizeof(float), cudaMemcpyDefault));
+  e->packed = false;
+  return CATRE_OK;
+}
+
+int catre_pack(catre_engine* e, void* stream) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  (void)stream;
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  for (int i = 0; i < kNumWeights; ++i)
+    if (!e->hw.count(kWeights[i].name))
+      return fail(e, CATRE_ERR_NOT_PACKED, "weight '%s' has not been set", kWeights[i].name);
+  // packed weights are re-created on every pack; previous device copies stay allocated until destroy
+  // only when shapes change (they cannot), so reuse buffers if present
+  int rc = 0;
+  auto up = [&](float** p, const std::vector<float>& h) {
+    if (*p == nullptr) rc |= upload(e, p, h);
+    else if (cudaMemcpy(*p, h.data(), h.size() * sizeof(float), cudaMemcpyHostToDevice) != cudaSuccess) rc |= 1;
+  };
+  for (int i = 0; i < kNumWeights; ++i) up(&e->dw[kWeights[i].name], e->hw[kWeights[i].name]);
+  auto H = [&](const char* n) -> const std::vector<float>& { return e->hw.at(n); };
+
+  std::vector<float> v;
+  v = H("pcl_net.stn.fc3.bias");  // + I3 (pointnet.py:37-40)
+  for (int i = 0; i < 3; ++i) v[i * 3 + i] += 1.0f;
+  up(&e->stn_fc3_bI, v);
+  v = H("pcl_net.fstn.fc3.bias");  // + I64 (pointnet.py:72-77)
+  for (int i = 0; i < 64; ++i) v[i * 64 + i] += 1.0f;
+  up(&e->fstn_fc3_bI, v);
+
+  const char* hx = "rot_head.rot_head_x.";
+  const char* hy = "rot_head.rot_head_y.";
+  const int P = e->cfg.n_obs + e->cfg.n_prior;
+  std::vector<float> w0g(512 * 1024), w0p(512 * 64), b0(512), g0(512), be0(512), b1(512), g1(512), be1(512),
+      nw(2 * 3 * 256), nb(6), wp(2 * (size_t)P), cb(2);
+  for (int h = 0; h < 2; ++h) {
+    std::string pre = h == 0 ? hx : hy;
+    const std::vector<float>& w0 = H((pre + "layers.0.weight").c_str());  // [256, 1088] = [global 1024 | pointfeat 64]
+    for (int c = 0; c < 256; ++c) {
+      memcpy(&w0g[(size_t)(h * 256 + c) * 1024], &w0[(size_t)c * 1088], 1024 * sizeof(float));
+      memcpy(&w0p[(size_t)(h * 256 + c) * 64], &w0[(size_t)c * 1088 + 1024], 64 * sizeof(float));
+    }
+    auto cp = [&](std::vector<float>& dst, const char* n, size_t off) {
+      const std::vector<float>& s = H((pre + n).c_str());
+      memcpy(&dst[off], s.data(), s.size() * sizeof(float));
+    };
+    cp(b0, "layers.0.bias", h * 256); cp(g0, "layers.1.weight", h * 256); cp(be0, "layers.1.bias", h * 256);
+    cp(b1, "layers.3.bias", h * 256); cp(g1, "layers.4.weight", h * 256); cp(be1, "layers.4.bias", h * 256);
+    cp(nw, "neck.0.weight", h * 768); cp(nb, "neck.0.bias", h * 3);
+    cp(wp, "conv_p.weight", (size_t)h * P); cp(cb, "conv_p.bias", h);
+  }
+  up(&e->rot_w0g, w0g); up(&e->rot_w0p, w0p); up(&e->rot_b0, b0);
+  up(&e->rot_gn0_g, g0); up(&e->rot_gn0_b, be0); up(&e->rot_b1, b1);
+  up(&e->rot_gn1_g, g1); up(&e->rot_gn1_b, be1);
+  up(&e->neck_w, nw); up(&e->neck_b, nb); up(&e->wp, wp); up(&e->convp_b, cb);
+
+  const std::vector<float>& t0 = H("ts_head.linears.0.weight");
+  std::vector<float> t0t(1091 * 256), t1t(256 * 256);
+  for (int c = 0; c < 256; ++c)
+    for (int k = 0; k < 1091; ++k) t0t[(size_t)k * 256 + c] = t0[(size_t)c * 1091 + k];
+  const std::vector<float>& t1 = H("ts_head.linears.3.weight");
+  for (int c = 0; c < 256; ++c)
+    for (int k = 0; k < 256; ++k) t1t[(size_t)k * 256 + c] = t1[(size_t)c * 256 + k];
+  up(&e->ts_w0t, t0t); up(&e->ts_w1t, t1t);
+  if (rc) return fail(e, CATRE_ERR_CUDA, "uploading packed weights failed: %s", cudaGetErrorString(cudaGetLastError()));
+
+  if (e->cfg.precision != CATRE_PREC_FP32_SIMT) {
+    rc = tc_pack_weights(e->tcw, e->hw, w0p, e->cfg.precision == CATRE_PREC_BF16, e->dev_allocs, e);
+    if (rc) return rc;
+  }
+  CU_TRY(e, cudaDeviceSynchronize());
+  e->packed = true;
+  return CATRE_OK;
+}
+
+size_t catre_workspace_bytes(const catre_engine* e, int32_t B) {
+  if (!e || B < 0) return 0;
+  // the workspace is allocated once for max_batch; report the share a launch of B objects touches
+  double frac = (double)(B > e->maxB ? e->maxB : B) / (double)e->maxB;
+  return (size_t)((double)e->ws_bytes * frac);
+}
+
+int catre_forward_once(catre_engine* e, const float* x_pm, const float* kps_pm, const float* pose, const float* scale,
+                       const float* K, int32_t B, float* out_pose, float* out_scale, void* stream) {
+  int rc = check_ready(e, B);
+  if (rc) return rc;
+  if (B == 0) { e->launches = 0; return CATRE_OK; }
+  if (!x_pm || !kps_pm || !pose || !scale || !K || !out_pose || !out_scale) return fail(e, CATRE_ERR_INVALID_ARG, "null tensor");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  e->launches = 0;
+  const int N = e->N;
+  for (int b0 = 0; b0 < B; b0 += e->maxB) {
+    int Bc = (B - b0 < e->maxB) ? B - b0 : e->maxB;
+    long long total = (long long)Bc * 2 * N;
+    {
+      Launch l(e, s, G_UPDATE_POINTS);
+      gather_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x_pm + (size_t)b0 * N * 3, kps_pm + (size_t)b0 * N * 3,
+                                                                          e->q, Bc, N);
+    }
+    if ((rc = check_launch(e, "gather_points"))) return rc;
+    if ((rc = iteration(e, s, Bc, pose + (size_t)b0 * 12, scale + (size_t)b0 * 3, K + (size_t)b0 * 9,
+                        out_pose + (size_t)b0 * 12, out_scale + (size_t)b0 * 3))) return rc;
+  }
+  return CATRE_OK;
+}
+
+int catre_refine(catre_engine* e, const float* pcl, const float* prior, const float* init_pose, const float* init_scale,
+                 const float* K, int32_t B, int32_t n_iter, float* out_poses, float* out_scales, void* stream) {
+  int rc = check_ready(e, B);
+  if (rc) return rc;
+  if (n_iter < 0) return fail(e, CATRE_ERR_INVALID_ARG, "negative n_iter %d", n_iter);
+  if (B == 0) { e->launches = 0; return CATRE_OK; }
+  if (!pcl || !prior || !init_pose || !init_scale || !K || !out_poses || !out_scales) return fail(e, CATRE_ERR_INVALID_ARG, "null tensor");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  e->launches = 0;
+  const int N = e->N;
+  CU_TRY(e, cudaMemcpyAsync(out_poses, init_pose, (size_t)B * 12 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  CU_TRY(e, cudaMemcpyAsync(out_scales, init_scale, (size_t)B * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  for (int b0 = 0; b0 < B; b0 += e->maxB) {
+    int Bc = (B - b0 < e->maxB) ? B - b0 : e->maxB;
+    long long total = (long long)Bc * 2 * N;
+    for (int it = 1; it <= n_iter; ++it) {
+      const float* pin = out_poses + ((size_t)(it - 1) * B + b0) * 12;
+      const float* sin = out_scales + ((size_t)(it - 1) * B + b0) * 3;
+      float* pout = out_poses + ((size_t)it * B + b0) * 12;
+      float* sout = out_scales + ((size_t)it * B + b0) * 3;
+      {
+        Launch l(e, s, G_UPDATE_POINTS);
+        update_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pcl + (size_t)b0 * N * 3, prior + (size_t)b0 * N * 3,
+                                                                            pin, sin, e->q, Bc, N);
+      }
+      if ((rc = check_launch(e, "update_points"))) return rc;
+      if ((rc = iteration(e, s, Bc, pin, sin, K + (size_t)b0 * 9, pout, sout))) return rc;
+    }
+  }
+  return CATRE_OK;
+}
+
+int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, const float* init_pose, const float* init_scale,
+                      const float* K, int32_t B, int32_t n_iter, float* out_poses, float* out_scales, void* stream) {
+  int rc = check_ready(e, B);
+  if (rc) return rc;
+  if (n_iter < 0 || n_iter > catre_engine::kMaxHostIter)
+    return fail(e, CATRE_ERR_INVALID_ARG, "n_iter %d outside [0, %d] for the host entry", n_iter, catre_engine::kMaxHostIter);
+  if (B == 0) { e->launches = 0; return CATRE_OK; }
+  if (!pcl || !prior || !init_pose || !init_scale || !K || !out_poses || !out_scales) return fail(e, CATRE_ERR_INVALID_ARG, "null tensor");
+  cudaStream_t s = (cudaStream_t)stream;
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  const int N = e->N;
+  int64_t launches = 0;
+  for (int b0 = 0; b0 < B; b0 += e->maxB) {
+    int Bc = (B - b0 < e->maxB) ? B - b0 : e->maxB;
+    CU_TRY(e, cudaMemcpyAsync(e->st_pcl, pcl + (size_t)b0 * N * 3, (size_t)Bc * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU_TRY(e, cudaMemcpyAsync(e->st_prior, prior + (size_t)b0 * N * 3, (size_t)Bc * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU_TRY(e, cudaMemcpyAsync(e->st_pose, init_pose + (size_t)b0 * 12, (size_t)Bc * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU_TRY(e, cudaMemcpyAsync(e->st_scale, init_scale + (size_t)b0 * 3, (size_t)Bc * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU_TRY(e, cudaMemcpyAsync(e->st_K, K + (size_t)b0 * 9, (size_t)Bc * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+    rc = catre_refine(e, e->st_pcl, e->st_prior, e->st_pose, e->st_scale, e->st_K, Bc, n_iter, e->st_oposes, e->st_oscales, s);
+    if (rc) return rc;
+    launches += e->launches;
+    for (int it = 0; it <= n_iter; ++it) {
+      CU_TRY(e, cudaMemcpyAsync(out_poses + ((size_t)it * B + b0) * 12, e->st_oposes + (size_t)it * Bc * 12,
+                                (size_t)Bc * 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+      CU_TRY(e, cudaMemcpyAsync(out_scales + ((size_t)it * B + b0) * 3, e->st_oscales + (size_t)it * Bc * 3,
+                                (size_t)Bc * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    }
+  }
+  CU_TRY(e, cudaStreamSynchronize(s));
+  e->launches = launches;
+  return CATRE_OK;
+}
+
+int64_t catre_last_launch_count(const catre_engine* e) { return e ? e->launches : 0; }
+
+int catre_profile_enable(catre_engine* e, int32_t on) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  e->prof_on = on != 0;
+  return CATRE_OK;
+}
+
+static int profile_drain(catre_engine* e) {
+  for (auto& ev : e->ev_pending) {
+    CU_TRY(e, cudaEventSynchronize(ev.b));
+    float ms = 0.f;
+    CU_TRY(e, cudaEventElapsedTime(&ms, ev.a, ev.b));
+    e->prof_ms[ev.grp] += ms;
+    e->prof_n[ev.grp] += 1;
+    e->ev_pool.push_back(ev.a);
+    e->ev_pool.push_back(ev.b);
+  }
+  e->ev_pending.clear();
+  return 0;
+}
+
+int catre_profile_reset(catre_engine* e) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  int rc = profile_drain(e);
+  for (int i = 0; i < G_NUM; ++i) { e->prof_ms[i] = 0; e->prof_n[i] = 0; }
+  return rc;
+}
+
+int catre_profile_get(catre_engine* e, int32_t which, double* total_ms, int64_t* launches) {
+  if (!e || which < 0 || which >= G_NUM || !total_ms || !launches) return CATRE_ERR_INVALID_ARG;
+  int rc = profile_drain(e);
+  if (rc) return rc;
+  *total_ms = e->prof_ms[which];
+  *launches = e->prof_n[which];
+  return CATRE_OK;
+}
+
+}  // extern "C"

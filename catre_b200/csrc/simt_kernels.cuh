@@ -1,0 +1,515 @@
+// fp32 CUDA-core kernels of the CATRE refinement path (precision mode CATRE_PREC_FP32_SIMT, and the
+// narrow / per-object stages of every mode).  Semantics follow SURVEY.md appendix A; each kernel cites
+// the reference lines it restates.  Written for sm_100a; no library calls.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace catre {
+
+// ----------------------------------------------------------------------------------------------
+// small helpers
+// ----------------------------------------------------------------------------------------------
+
+// order-preserving float <-> int key, so a column max over points can use atomicMax(int)
+__device__ __forceinline__ int f2key(float f) {
+  int i = __float_as_int(f);
+  return i >= 0 ? i : i ^ 0x7fffffff;
+}
+__device__ __forceinline__ float key2f(int k) { return __int_as_float(k >= 0 ? k : k ^ 0x7fffffff); }
+constexpr int KEY_NEG_INF = (int)0x807fffff;  // f2key(-inf)
+
+// exact GELU (nn.GELU default, lib/torch_utils/layers/layer_utils.py:61-95 "gelu")
+__device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
+
+__global__ void fill_i32_kernel(int* __restrict__ p, long long n, int v) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long stride = (long long)gridDim.x * blockDim.x;
+  for (; i < n; i += stride) p[i] = v;
+}
+
+// ----------------------------------------------------------------------------------------------
+// U1: per-iteration point update (core/catre/engine/batch_test.py:78-97,
+//     lib/pysixd/misc.py:1011-1026):  x = pcl - t ;  k = R (s * kps)
+// q layout: set 2b = observed points of object b, set 2b+1 = prior points; [2B, N, 3] point-major.
+// ----------------------------------------------------------------------------------------------
+__global__ void update_points_kernel(const float* __restrict__ pcl, const float* __restrict__ prior,
+                                     const float* __restrict__ pose, const float* __restrict__ scale,
+                                     float* __restrict__ q, int B, int N) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)B * 2 * N;
+  if (i >= total) return;
+  int b = (int)(i / (2 * N));
+  int r = (int)(i % (2 * N));
+  const float* P = pose + (long long)b * 12;
+  float o0, o1, o2;
+  if (r < N) {
+    const float* p = pcl + ((long long)b * N + r) * 3;
+    o0 = p[0] - P[3];
+    o1 = p[1] - P[7];
+    o2 = p[2] - P[11];
+  } else {
+    const float* p = prior + ((long long)b * N + (r - N)) * 3;
+    const float* s = scale + (long long)b * 3;
+    float k0 = p[0] * s[0], k1 = p[1] * s[1], k2 = p[2] * s[2];
+    o0 = P[0] * k0 + P[1] * k1 + P[2] * k2;
+    o1 = P[4] * k0 + P[5] * k1 + P[6] * k2;
+    o2 = P[8] * k0 + P[9] * k1 + P[10] * k2;
+  }
+  float* o = q + i * 3;
+  o[0] = o0; o[1] = o1; o[2] = o2;
+}
+
+// forward_once entry: x and tfd_kps arrive already transformed; interleave them into the q layout
+__global__ void gather_points_kernel(const float* __restrict__ x_pm, const float* __restrict__ kps_pm,
+                                     float* __restrict__ q, int B, int N) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long total = (long long)B * 2 * N;
+  if (i >= total) return;
+  int b = (int)(i / (2 * N));
+  int r = (int)(i % (2 * N));
+  const float* p = (r < N) ? x_pm + ((long long)b * N + r) * 3 : kps_pm + ((long long)b * N + (r - N)) * 3;
+  float* o = q + i * 3;
+  o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
+}
+
+// ----------------------------------------------------------------------------------------------
+// E1/E2 front layer: optional per-set 3x3 input transform, then 3 -> 64 point-wise conv + ReLU
+// (pointnets/pointnet.py:26 stn.conv1 ; :100-103 bmm with T3 then conv1).
+//   x'_j = sum_i x_i T3[set][i][j] ;  h[c] = relu(W[c][0..2] . x' + b[c])
+// One thread per (point, 4 channels); output [R, 64] fp32.
+// ----------------------------------------------------------------------------------------------
+__global__ void front3_kernel(const float* __restrict__ q, const float* __restrict__ t3 /*[S,9] or null*/,
+                              const float* __restrict__ W /*[64,3]*/, const float* __restrict__ bias,
+                              float* __restrict__ out, long long R, int N) {
+  __shared__ float sW[64 * 3];
+  __shared__ float sB[64];
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) sW[i] = W[i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) sB[i] = bias[i];
+  __syncthreads();
+  long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long r = gid >> 4;
+  int cg = (int)(gid & 15);
+  if (r >= R) return;
+  float x0 = q[r * 3 + 0], x1 = q[r * 3 + 1], x2 = q[r * 3 + 2];
+  if (t3 != nullptr) {
+    const float* T = t3 + (r / N) * 9;
+    float y0 = x0 * T[0] + x1 * T[3] + x2 * T[6];
+    float y1 = x0 * T[1] + x1 * T[4] + x2 * T[7];
+    float y2 = x0 * T[2] + x1 * T[5] + x2 * T[8];
+    x0 = y0; x1 = y1; x2 = y2;
+  }
+  float4 o;
+  float* po = reinterpret_cast<float*>(&o);
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {
+    int c = cg * 4 + j;
+    float v = sB[c] + sW[c * 3 + 0] * x0 + sW[c * 3 + 1] * x1 + sW[c * 3 + 2] * x2;
+    po[j] = fmaxf(v, 0.0f);
+  }
+  *reinterpret_cast<float4*>(out + r * 64 + cg * 4) = o;
+}
+
+// ----------------------------------------------------------------------------------------------
+// Generic fp32 point-wise layer:  out[r, c] = act( sum_k f(A[r, k]) * W[c, k] + bias[c] + rowvec[set(r), c] )
+// 128 x BN output tile, K chunks of 16, 256 threads, 8 x (BN/16) micro-tile.
+// ----------------------------------------------------------------------------------------------
+enum { A_PLAIN = 0, A_KEY = 1, A_GN_GELU = 2 };
+
+struct GemmP {
+  const float* A; int lda;
+  const float* W; int wcs, wks; long long w_set_stride;
+  const float* bias;
+  const float* rowvec; int ldrv;
+  float* out; int ldo;
+  int* gmax;       // [S, C] ordered-int keys (column max over the points of a set)
+  float* stats;    // [R/128, stats_ld, 2] per-row-tile GroupNorm partials (sum, sum of squares)
+  int stats_ld, stats_goff;  // groups per row tile in the stats buffer, first group of this launch
+  const float* gn_scale; const float* gn_shift; int ldgn;  // A_GN_GELU: per (object, k)
+  int R, C, K;
+  int rows_per_set, rows_per_obj;
+  int relu;
+};
+
+template <int BN, int AMODE>
+__global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
+  constexpr int BM = 128, BK = 16;
+  constexpr int TN = BN / 16;           // 8 or 4 columns per thread
+  constexpr int NCH = TN / 4;           // 4-column chunks per thread (2 or 1)
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Ws[BK][BN + 4];
+  __shared__ float red[16][BN];
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int r0 = blockIdx.y * BM, c0 = blockIdx.x * BN;
+  const int set = r0 / p.rows_per_set;
+  const int obj = r0 / p.rows_per_obj;
+  const float* Wb = p.W + (long long)set * p.w_set_stride;
+
+  float acc[8][TN];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
+
+  for (int k0 = 0; k0 < p.K; k0 += BK) {
+    // ---- A tile: 128 rows x 16 k, float4 along k
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      int e = tid + it * 256;  // 0..511
+      int row = e >> 2, kq = (e & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + row < p.R) {
+        const float* src = p.A + (long long)(r0 + row) * p.lda + k0 + kq;
+        if (AMODE == A_KEY) {
+          int4 kv = *reinterpret_cast<const int4*>(src);
+          v = make_float4(key2f(kv.x), key2f(kv.y), key2f(kv.z), key2f(kv.w));
+        } else {
+          v = *reinterpret_cast<const float4*>(src);
+          if (AMODE == A_GN_GELU) {
+            const float4 sc = *reinterpret_cast<const float4*>(p.gn_scale + (long long)obj * p.ldgn + k0 + kq);
+            const float4 sh = *reinterpret_cast<const float4*>(p.gn_shift + (long long)obj * p.ldgn + k0 + kq);
+            v.x = gelu_exact(v.x * sc.x + sh.x);
+            v.y = gelu_exact(v.y * sc.y + sh.y);
+            v.z = gelu_exact(v.z * sc.z + sh.z);
+            v.w = gelu_exact(v.w * sc.w + sh.w);
+          }
+        }
+      }
+      As[kq + 0][row] = v.x; As[kq + 1][row] = v.y; As[kq + 2][row] = v.z; As[kq + 3][row] = v.w;
+    }
+    // ---- W tile: BN channels x 16 k
+    if (p.wks == 1) {
+#pragma unroll
+      for (int it = 0; it < BN / 64; ++it) {
+        int e = tid + it * 256;
+        int col = e >> 2, kq = (e & 3) * 4;
+        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (c0 + col < p.C) v = *reinterpret_cast<const float4*>(Wb + (long long)(c0 + col) * p.wcs + k0 + kq);
+        Ws[kq + 0][col] = v.x; Ws[kq + 1][col] = v.y; Ws[kq + 2][col] = v.z; Ws[kq + 3][col] = v.w;
+      }
+    } else {
+#pragma unroll
+      for (int it = 0; it < BN / 16; ++it) {
+        int e = tid + it * 256;
+        int col = e % BN, kk = e / BN;
+        float v = 0.f;
+        if (c0 + col < p.C) v = Wb[(long long)(c0 + col) * p.wcs + (long long)(k0 + kk) * p.wks];
+        Ws[kk][col] = v;
+      }
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < BK; ++kk) {
+      float a[8], w[TN];
+      *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+      *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch)
+        *reinterpret_cast<float4*>(&w[ch * 4]) = *reinterpret_cast<const float4*>(&Ws[kk][ch * (BN / 2) + tx * 4]);
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < TN; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+
+  // ---- epilogue: bias / per-set vector / ReLU
+  // thread's rows: ty*4+i (i<4), 64+ty*4+(i-4); columns: chunk ch -> ch*(BN/2) + tx*4 + j
+#pragma unroll
+  for (int ch = 0; ch < NCH; ++ch) {
+    int cbase = c0 + ch * (BN / 2) + tx * 4;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      int c = cbase + j;
+      float add = 0.f;
+      if (c < p.C) {
+        if (p.bias) add += p.bias[c];
+        if (p.rowvec) add += p.rowvec[(long long)set * p.ldrv + c];
+      }
+#pragma unroll
+      for (int i = 0; i < 8; ++i) {
+        float v = acc[i][ch * 4 + j] + add;
+        if (p.relu) v = fmaxf(v, 0.f);
+        acc[i][ch * 4 + j] = v;
+      }
+    }
+  }
+  if (p.out) {
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int row = r0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      if (row >= p.R) continue;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        int cbase = c0 + ch * (BN / 2) + tx * 4;
+        if (cbase + 3 < p.C && (p.ldo & 3) == 0) {
+          *reinterpret_cast<float4*>(p.out + (long long)row * p.ldo + cbase) =
+              make_float4(acc[i][ch * 4 + 0], acc[i][ch * 4 + 1], acc[i][ch * 4 + 2], acc[i][ch * 4 + 3]);
+        } else {
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            if (cbase + j < p.C) p.out[(long long)row * p.ldo + cbase + j] = acc[i][ch * 4 + j];
+        }
+      }
+    }
+  }
+  if (p.gmax) {  // column max over the tile's rows (all rows of a tile belong to one set)
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch)
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        float m = acc[0][ch * 4 + j];
+#pragma unroll
+        for (int i = 1; i < 8; ++i) m = fmaxf(m, acc[i][ch * 4 + j]);
+        red[ty][ch * (BN / 2) + tx * 4 + j] = m;
+      }
+    __syncthreads();
+    if (tid < BN && c0 + tid < p.C) {
+      float m = red[0][tid];
+#pragma unroll
+      for (int i = 1; i < 16; ++i) m = fmaxf(m, red[i][tid]);
+      atomicMax(p.gmax + (long long)set * p.C + c0 + tid, f2key(m));
+    }
+    __syncthreads();
+  }
+  if (p.stats) {  // GroupNorm partial sums per 8-channel group over the tile's 128 rows
+    float* red2 = &As[0][0];  // reuse: needs 16 * (BN/4) * 2 floats <= 16*132
+#pragma unroll
+    for (int ch = 0; ch < NCH; ++ch) {
+      float s = 0.f, ss = 0.f;
+#pragma unroll
+      for (int i = 0; i < 8; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          float v = acc[i][ch * 4 + j];
+          s += v;
+          ss = fmaf(v, v, ss);
+        }
+      int chunk = ch * (BN / 8) + tx;  // 4-column chunk index within the tile
+      red2[(ty * (BN / 4) + chunk) * 2 + 0] = s;
+      red2[(ty * (BN / 4) + chunk) * 2 + 1] = ss;
+    }
+    __syncthreads();
+    if (tid < BN / 8) {  // one thread per group: chunks 2g, 2g+1, all 16 ty, fixed order
+      float s = 0.f, ss = 0.f;
+      for (int y = 0; y < 16; ++y)
+        for (int h = 0; h < 2; ++h) {
+          s += red2[(y * (BN / 4) + tid * 2 + h) * 2 + 0];
+          ss += red2[(y * (BN / 4) + tid * 2 + h) * 2 + 1];
+        }
+      long long o = ((long long)blockIdx.y * p.stats_ld + p.stats_goff + (c0 / 8 + tid)) * 2;
+      p.stats[o] = s;
+      p.stats[o + 1] = ss;
+    }
+  }
+}
+
+// GroupNorm(32 groups of 8 channels per head) statistics -> per (object, channel) affine
+//   y = x * scale + shift,  scale = rstd * gamma, shift = beta - mean * rstd * gamma, biased variance,
+//   eps = 1e-5 (torch.nn.GroupNorm; heads/conv_out_per_rot_head.py:100-104)
+__global__ void gn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                   const float* __restrict__ beta, float* __restrict__ scale,
+                                   float* __restrict__ shift, int B, int C, int tiles_per_obj, int rows_per_obj) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int G = C / 8;
+  if (i >= B * G) return;
+  int b = i / G, g = i % G;
+  double s = 0.0, ss = 0.0;
+  for (int t = 0; t < tiles_per_obj; ++t) {
+    long long o = (((long long)b * tiles_per_obj + t) * G + g) * 2;
+    s += (double)stats[o];
+    ss += (double)stats[o + 1];
+  }
+  double n = 8.0 * rows_per_obj;
+  double mean = s / n;
+  double var = ss / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  float rstd = (float)(1.0 / sqrt(var + 1e-5));
+  float fmean = (float)mean;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int c = g * 8 + j;
+    float sc = rstd * gamma[c];
+    scale[(long long)b * C + c] = sc;
+    shift[(long long)b * C + c] = beta[c] - fmean * sc;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// R1 tail: GN + GELU of the second rot layer, neck 256 -> 3, learned weighted sum over the point index
+// (heads/conv_out_per_rot_head.py:131-140).  a1 [R, 512] = [head x 256 | head y 256] raw layer-3 output.
+// Block = 128 rows of one object; warp per row; partial[b][tile][6] (deterministic two-level reduce).
+// ----------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__ a1, const float* __restrict__ gn_scale,
+                                                       const float* __restrict__ gn_shift,
+                                                       const float* __restrict__ neck_w /*[2][3][256]*/,
+                                                       const float* __restrict__ neck_b /*[2][3]*/,
+                                                       const float* __restrict__ wp /*[2][P]*/, float* __restrict__ partial,
+                                                       int P) {
+  const int b = blockIdx.y, tile = blockIdx.x, tiles = gridDim.x;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  __shared__ float s_part[8][6];
+  float accw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+  // lane owns channels lane*8 .. lane*8+7 of each head
+  float sc[2][8], sh[2][8], nw[2][3][8];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      int c = h * 256 + lane * 8 + j;
+      sc[h][j] = gn_scale[(long long)b * 512 + c];
+      sh[h][j] = gn_shift[(long long)b * 512 + c];
+#pragma unroll
+      for (int d = 0; d < 3; ++d) nw[h][d][j] = neck_w[(h * 3 + d) * 256 + lane * 8 + j];
+    }
+  for (int rr = warp; rr < 128; rr += 8) {
+    int pidx = tile * 128 + rr;
+    const float* row = a1 + ((long long)b * P + pidx) * 512;
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {
+      float4 v0 = *reinterpret_cast<const float4*>(row + h * 256 + lane * 8);
+      float4 v1 = *reinterpret_cast<const float4*>(row + h * 256 + lane * 8 + 4);
+      float u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) {
+        float g = gelu_exact(u[j] * sc[h][j] + sh[h][j]);
+        d0 = fmaf(nw[h][0][j], g, d0);
+        d1 = fmaf(nw[h][1][j], g, d1);
+        d2 = fmaf(nw[h][2][j], g, d2);
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
+        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
+        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
+      }
+      float w = wp[(long long)h * P + pidx];
+      accw[h * 3 + 0] = fmaf(w, d0 + neck_b[h * 3 + 0], accw[h * 3 + 0]);
+      accw[h * 3 + 1] = fmaf(w, d1 + neck_b[h * 3 + 1], accw[h * 3 + 1]);
+      accw[h * 3 + 2] = fmaf(w, d2 + neck_b[h * 3 + 2], accw[h * 3 + 2]);
+    }
+  }
+  if (lane == 0)
+#pragma unroll
+    for (int j = 0; j < 6; ++j) s_part[warp][j] = accw[j];
+  __syncthreads();
+  if (threadIdx.x < 6) {
+    float s = 0.f;
+    for (int w = 0; w < 8; ++w) s += s_part[w][threadIdx.x];
+    partial[((long long)b * tiles + tile) * 6 + threadIdx.x] = s;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------
+// H1 + G1 + G2: per object -- translation/size head (heads/fc_trans_size_head.py:61-70), rot6d
+// Gram-Schmidt (core/utils/rot_reps.py:34-55) and the pose update
+// (models/pose_scale_from_delta_init.py:47-95: image-space, K-aware, cosypose z, additive scale,
+// R' = dR R).  One block of 256 threads per object.
+//   w0t [1091, 256], w1t [256, 256]: transposed at pack time so threads read coalesced.
+// ----------------------------------------------------------------------------------------------
+struct TsPoseP {
+  const int* gmax_g;    // [2B, 1024] keys: global feature per set (obs set = 2b)
+  const int* gmax_pf;   // [2B, 64] keys: max over points of pointfeat
+  const float* w0t; const float* b0; const float* g0; const float* be0;
+  const float* w1t; const float* b1; const float* g1; const float* be1;
+  const float* wt; const float* bt; const float* ws; const float* bs;
+  const float* rot_partial; int rot_tiles;  // [B, tiles, 6]
+  const float* convp_bias;                  // [2]
+  const float* pose_in; const float* scale_in; const float* K;
+  float* pose_out; float* scale_out;
+};
+
+__device__ __forceinline__ float gn8_gelu(float v, float gamma, float beta) {
+  // GroupNorm over the 8 consecutive channels held by 8 consecutive lanes, then GELU
+  float s = v;
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  float mean = s * 0.125f;
+  float d = v - mean;
+  float q = d * d;
+  q += __shfl_xor_sync(0xffffffffu, q, 1);
+  q += __shfl_xor_sync(0xffffffffu, q, 2);
+  q += __shfl_xor_sync(0xffffffffu, q, 4);
+  float rstd = rsqrtf(q * 0.125f + 1e-5f);
+  return gelu_exact(d * rstd * gamma + beta);
+}
+
+__global__ void __launch_bounds__(256) ts_pose_kernel(TsPoseP p) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  __shared__ float feat[1091 + 5];
+  __shared__ float h[256];
+  __shared__ float outv[6];
+  const float* sc_in = p.scale_in + (long long)b * 3;
+  for (int i = t; i < 1024; i += 256) feat[i] = key2f(p.gmax_g[(long long)(2 * b) * 1024 + i]);
+  if (t < 64) feat[1024 + t] = key2f(p.gmax_pf[(long long)(2 * b) * 64 + t]);
+  if (t < 3) feat[1088 + t] = sc_in[t];
+  __syncthreads();
+  float a = p.b0[t];
+  for (int k = 0; k < 1091; ++k) a = fmaf(p.w0t[k * 256 + t], feat[k], a);
+  a = gn8_gelu(a, p.g0[t], p.be0[t]);
+  h[t] = a;
+  __syncthreads();
+  float a2 = p.b1[t];
+  for (int k = 0; k < 256; ++k) a2 = fmaf(p.w1t[k * 256 + t], h[k], a2);
+  a2 = gn8_gelu(a2, p.g1[t], p.be1[t]);
+  __syncthreads();
+  h[t] = a2;
+  __syncthreads();
+  // fc_t (3) and fc_s (3): warp w < 6 computes one output
+  int warp = t >> 5, lane = t & 31;
+  if (warp < 6) {
+    const float* w = (warp < 3) ? p.wt + warp * 256 : p.ws + (warp - 3) * 256;
+    float s = 0.f;
+    for (int k = lane; k < 256; k += 32) s = fmaf(w[k], h[k], s);
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) outv[warp] = s + ((warp < 3) ? p.bt[warp] : p.bs[warp - 3]);
+  }
+  __syncthreads();
+  if (t == 0) {
+    float r6[6];
+    for (int j = 0; j < 6; ++j) {
+      float s = 0.f;
+      for (int tl = 0; tl < p.rot_tiles; ++tl) s += p.rot_partial[((long long)b * p.rot_tiles + tl) * 6 + j];
+      r6[j] = s + p.convp_bias[j / 3];
+    }
+    // rot6d -> R (columns x, y, z)
+    float nx = sqrtf(r6[0] * r6[0] + r6[1] * r6[1] + r6[2] * r6[2]);
+    nx = fmaxf(nx, 1e-12f);
+    float x0 = r6[0] / nx, x1 = r6[1] / nx, x2 = r6[2] / nx;
+    float z0 = x1 * r6[5] - x2 * r6[4];
+    float z1 = x2 * r6[3] - x0 * r6[5];
+    float z2 = x0 * r6[4] - x1 * r6[3];
+    float nz = fmaxf(sqrtf(z0 * z0 + z1 * z1 + z2 * z2), 1e-12f);
+    z0 /= nz; z1 /= nz; z2 /= nz;
+    float y0 = z1 * x2 - z2 * x1;
+    float y1 = z2 * x0 - z0 * x2;
+    float y2 = z0 * x1 - z1 * x0;
+    float dR[9] = {x0, y0, z0, x1, y1, z1, x2, y2, z2};
+    const float* Pin = p.pose_in + (long long)b * 12;
+    float* Pout = p.pose_out + (long long)b * 12;
+    float Rin[9] = {Pin[0], Pin[1], Pin[2], Pin[4], Pin[5], Pin[6], Pin[8], Pin[9], Pin[10]};
+    float tin[3] = {Pin[3], Pin[7], Pin[11]};
+    float Ro[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) Ro[i * 3 + j] = dR[i * 3 + 0] * Rin[0 * 3 + j] + dR[i * 3 + 1] * Rin[1 * 3 + j] + dR[i * 3 + 2] * Rin[2 * 3 + j];
+    const float* Kb = p.K + (long long)b * 9;
+    float fx = Kb[0], fy = Kb[4];
+    float zt = outv[2] * tin[2];
+    float xt = zt * (outv[0] / fx + tin[0] / tin[2]);
+    float yt = zt * (outv[1] / fy + tin[1] / tin[2]);
+    Pout[0] = Ro[0]; Pout[1] = Ro[1]; Pout[2] = Ro[2]; Pout[3] = xt;
+    Pout[4] = Ro[3]; Pout[5] = Ro[4]; Pout[6] = Ro[5]; Pout[7] = yt;
+    Pout[8] = Ro[6]; Pout[9] = Ro[7]; Pout[10] = Ro[8]; Pout[11] = zt;
+    float* So = p.scale_out + (long long)b * 3;
+    So[0] = sc_in[0] + outv[3];
+    So[1] = sc_in[1] + outv[4];
+    So[2] = sc_in[2] + outv[5];
+  }
+}
+
+}  // namespace catre

@@ -1,0 +1,236 @@
+"""Drop-in replacement for the reference's model plugin ``core/catre/models/CATRE_disR_shared.py``.
+
+The reference resolves its model with ``eval(cfg.MODEL.CATRE.NAME).build_model_optimizer(cfg, is_test)``
+(core/catre/main_catre.py:138) and then calls, per refinement iteration,
+``model(x, tfd_kps, init_pose=..., init_scale=..., K_zoom=..., obj_class=..., mean_scales=...,
+do_loss=False, cur_iter=i)`` -> ``{"pose_i": [B,3,4], "scale_i": [B,3]}``
+(core/catre/engine/catre_evaluator.py:295-311, CATRE_disR_shared.py:40-124).
+
+This module exposes the same two names with the same meaning.  The module tree holds exactly the
+reference's 74 parameters under the reference's names (so ``MyCheckpointer(model).resume_or_load`` /
+``load_state_dict(strict=True)`` fill it: core/utils/my_checkpoint.py:48-84), but the arithmetic is the
+sm_100a kernel chain in libcatre_b200.so, reached through ``catre_b200.engine`` (ctypes, C ABI).  There
+is no PyTorch implementation of the forward in this package and no CPU path: inputs must be CUDA
+tensors, and a missing library or device raises.
+
+Additionally (not in the reference): ``CatreB200.refine(...)`` runs the evaluator's whole K-loop
+(batch_updater_test + forward, catre_evaluator.py:292-311, batch_test.py:63-97) in one call.
+
+Training (``do_loss=True``) is out of scope for this engine and raises.
+"""
+from __future__ import annotations
+
+from typing import Any, Dict, Optional, Tuple
+
+import torch
+import torch.nn as nn
+
+from . import engine as _engine
+
+# (name, shape); -1 = n_obs + n_prior (conv_p is tied to the point count,
+# core/catre/models/heads/conv_out_per_rot_head.py:112)
+_PARAM_SPECS = (
+    [("pcl_net.stn.conv1.weight", (64, 3, 1)), ("pcl_net.stn.conv1.bias", (64,)),
+     ("pcl_net.stn.conv2.weight", (128, 64, 1)), ("pcl_net.stn.conv2.bias", (128,)),
+     ("pcl_net.stn.conv3.weight", (1024, 128, 1)), ("pcl_net.stn.conv3.bias", (1024,)),
+     ("pcl_net.stn.fc1.weight", (512, 1024)), ("pcl_net.stn.fc1.bias", (512,)),
+     ("pcl_net.stn.fc2.weight", (256, 512)), ("pcl_net.stn.fc2.bias", (256,)),
+     ("pcl_net.stn.fc3.weight", (9, 256)), ("pcl_net.stn.fc3.bias", (9,)),
+     ("pcl_net.conv1.weight", (64, 3, 1)), ("pcl_net.conv1.bias", (64,)),
+     ("pcl_net.conv2.weight", (128, 64, 1)), ("pcl_net.conv2.bias", (128,)),
+     ("pcl_net.conv3.weight", (512, 128, 1)), ("pcl_net.conv3.bias", (512,)),
+     ("pcl_net.conv4.weight", (1024, 512, 1)), ("pcl_net.conv4.bias", (1024,)),
+     ("pcl_net.fstn.conv1.weight", (64, 64, 1)), ("pcl_net.fstn.conv1.bias", (64,)),
+     ("pcl_net.fstn.conv2.weight", (128, 64, 1)), ("pcl_net.fstn.conv2.bias", (128,)),
+     ("pcl_net.fstn.conv3.weight", (1024, 128, 1)), ("pcl_net.fstn.conv3.bias", (1024,)),
+     ("pcl_net.fstn.fc1.weight", (512, 1024)), ("pcl_net.fstn.fc1.bias", (512,)),
+     ("pcl_net.fstn.fc2.weight", (256, 512)), ("pcl_net.fstn.fc2.bias", (256,)),
+     ("pcl_net.fstn.fc3.weight", (4096, 256)), ("pcl_net.fstn.fc3.bias", (4096,))]
+    + [(f"rot_head.rot_head_{a}.{n}", s) for a in ("x", "y") for n, s in (
+        ("norm.weight", (256,)), ("norm.bias", (256,)),
+        ("layers.0.weight", (256, 1088, 1)), ("layers.0.bias", (256,)),
+        ("layers.1.weight", (256,)), ("layers.1.bias", (256,)),
+        ("layers.3.weight", (256, 256, 1)), ("layers.3.bias", (256,)),
+        ("layers.4.weight", (256,)), ("layers.4.bias", (256,)),
+        ("neck.0.weight", (3, 256, 1)), ("neck.0.bias", (3,)),
+        ("conv_p.weight", (1, -1, 1)), ("conv_p.bias", (1,)))]
+    + [("ts_head.norm.weight", (256,)), ("ts_head.norm.bias", (256,)),
+       ("ts_head.linears.0.weight", (256, 1091)), ("ts_head.linears.0.bias", (256,)),
+       ("ts_head.linears.1.weight", (256,)), ("ts_head.linears.1.bias", (256,)),
+       ("ts_head.linears.3.weight", (256, 256)), ("ts_head.linears.3.bias", (256,)),
+       ("ts_head.linears.4.weight", (256,)), ("ts_head.linears.4.bias", (256,)),
+       ("ts_head.fc_t.weight", (3, 256)), ("ts_head.fc_t.bias", (3,)),
+       ("ts_head.fc_s.weight", (3, 256)), ("ts_head.fc_s.bias", (3,))]
+)
+
+
+def param_specs(n_obs: int, n_prior: int):
+    return [(n, tuple((n_obs + n_prior) if d == -1 else d for d in s)) for n, s in _PARAM_SPECS]
+
+
+class _Holder(nn.Module):
+    """A parameter container node; leaves are registered as nn.Parameter under the reference's names."""
+
+
+def _cfg_get(cfg: Any, path: str, default: Any = None) -> Any:
+    cur = cfg
+    for key in path.split("."):
+        if cur is None:
+            return default
+        if isinstance(cur, dict):
+            cur = cur.get(key, None)
+        else:
+            cur = getattr(cur, key, None)
+    return default if cur is None else cur
+
+
+# cfg values the kernel chain is built for (SURVEY.md 5 "Config / flags"); anything else is refused.
+_REQUIRED_CFG = {
+    "MODEL.CATRE.PCLNET.INIT_CFG.type": "point_net",
+    "MODEL.CATRE.PCLNET.INIT_CFG.global_feat": False,
+    "MODEL.CATRE.PCLNET.INIT_CFG.feature_transform": True,
+    "MODEL.CATRE.PCLNET.INIT_CFG.out_dim": 1024,
+    "MODEL.CATRE.ROT_HEAD.ROT_TYPE": "ego_rot6d",
+    "MODEL.CATRE.ROT_HEAD.CLASS_AWARE": False,
+    "MODEL.CATRE.ROT_HEAD.DELTA_T_SPACE": "image",
+    "MODEL.CATRE.ROT_HEAD.DELTA_T_WEIGHT": 1.0,
+    "MODEL.CATRE.ROT_HEAD.T_TRANSFORM_K_AWARE": True,
+    "MODEL.CATRE.ROT_HEAD.DELTA_Z_STYLE": "cosypose",
+    "MODEL.CATRE.ROT_HEAD.SCLAE_TYPE": "iter_add",
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.type": "ConvOutPerRotHead",
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.num_layers": 2,
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.feat_dim": 256,
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.norm": "GN",
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.num_gn_groups": 32,
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.act": "gelu",
+    "MODEL.CATRE.TS_HEAD.WITH_KPS_FEATURE": False,
+    "MODEL.CATRE.TS_HEAD.WITH_INIT_SCALE": True,
+    "MODEL.CATRE.TS_HEAD.WITH_INIT_TRANS": False,
+    "MODEL.CATRE.TS_HEAD.INIT_CFG.type": "FC_TransSizeHead",
+    "MODEL.CATRE.TS_HEAD.INIT_CFG.num_layers": 2,
+    "MODEL.CATRE.TS_HEAD.INIT_CFG.feat_dim": 256,
+    "MODEL.CATRE.TS_HEAD.INIT_CFG.norm": "GN",
+    "MODEL.CATRE.TS_HEAD.INIT_CFG.act": "gelu",
+    "MODEL.REFINE_SCLAE": True,
+}
+
+
+def check_cfg(cfg: Any) -> Tuple[int, int]:
+    """Validate a reference config against what the engine implements; returns (n_obs, n_prior)."""
+    bad = []
+    for path, want in _REQUIRED_CFG.items():
+        got = _cfg_get(cfg, path, want)  # absent keys take the reference's base-config defaults
+        if got != want:
+            bad.append(f"{path}={got!r} (engine implements {want!r})")
+    if bad:
+        raise NotImplementedError("catre_b200 implements the shipped CATRE config only: " + "; ".join(bad))
+    n_obs = int(_cfg_get(cfg, "INPUT.NUM_PCL", 1024))
+    n_prior = int(_cfg_get(cfg, "INPUT.NUM_KPS", 1024))
+    n_rot = int(_cfg_get(cfg, "MODEL.CATRE.ROT_HEAD.INIT_CFG.num_points", n_obs + n_prior))
+    if n_rot != n_obs + n_prior:
+        raise NotImplementedError(f"ROT_HEAD num_points={n_rot} != NUM_PCL+NUM_KPS={n_obs + n_prior}")
+    return n_obs, n_prior
+
+
+class CatreB200(nn.Module):
+    """Same constructor-independent surface as the reference's ``CATRE_disR_shared`` nn.Module:
+    ``.to()``, ``.eval()``, ``.parameters()``, ``state_dict()`` with the checkpoint's keys, and
+    ``forward(...)`` for one refinement iteration."""
+
+    def __init__(self, n_obs: int = 1024, n_prior: int = 1024, precision: str = "bf16x3", max_batch: int = 256,
+                 cfg: Any = None):
+        super().__init__()
+        if n_obs != n_prior:
+            raise NotImplementedError("catre_b200 needs NUM_PCL == NUM_KPS")
+        self.cfg = cfg
+        self.n_obs, self.n_prior = int(n_obs), int(n_prior)
+        self.precision = precision
+        self.max_batch = int(max_batch)
+        g = torch.Generator().manual_seed(0)
+        for name, shape in param_specs(n_obs, n_prior):
+            parts = name.split(".")
+            node: nn.Module = self
+            for p in parts[:-1]:
+                if p not in node._modules:
+                    node.add_module(p, _Holder())
+                node = node._modules[p]
+            if parts[-1] == "bias":
+                init = torch.zeros(shape)
+            elif len(shape) == 1:
+                init = torch.ones(shape)  # norm scales
+            else:
+                init = torch.randn(shape, generator=g) * 0.01
+            node.register_parameter(parts[-1], nn.Parameter(init))
+        self._engine: Optional[_engine.Engine] = None
+        self._packed_key = None
+
+    # ---- engine plumbing -----------------------------------------------------------------------
+    def _weights_key(self):
+        return tuple((p._version, p.data_ptr()) for p in self.parameters())
+
+    def engine(self, device: torch.device) -> _engine.Engine:
+        """The engine for ``device`` with the module's current parameters packed (lazy; re-packs after
+        load_state_dict / any in-place parameter update)."""
+        if device.type != "cuda":
+            raise _engine.CatreError("catre_b200 runs on CUDA (sm_100a) only; there is no CPU path. "
+                                     f"Got tensors on {device}.")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self._engine is None or self._engine.device != idx:
+            if self._engine is not None:
+                self._engine.close()
+            self._engine = _engine.Engine(self.n_obs, self.max_batch, self.precision, idx)
+            self._packed_key = None
+        key = self._weights_key()
+        if key != self._packed_key:
+            self._engine.load_weights({k: v for k, v in self.state_dict().items()})
+            self._packed_key = key
+        return self._engine
+
+    # ---- the reference's forward (one iteration) ---------------------------------------------------
+    @torch.no_grad()
+    def forward(self, x, tfd_kps, init_pose, init_scale, K_zoom=None, obj_class=None, gt_ego_rot=None, gt_trans=None,
+                gt_scale=None, obj_kps=None, mean_scales=None, sym_info=None, do_loss=False, cur_iter=0):
+        """x [B,3,N_o] and tfd_kps [B,3,N_p] as the reference passes them (permuted views of point-major
+        tensors, core/catre/engine/batch_test.py:92-95).  Returns {f"pose_{cur_iter}", f"scale_{cur_iter}"}."""
+        if do_loss:
+            raise NotImplementedError("catre_b200 is a forward-only inference engine; the training forward "
+                                      "(do_loss=True) is out of scope (SURVEY.md 8(f) N4)")
+        if K_zoom is None:
+            raise ValueError("K_zoom is required (T_TRANSFORM_K_AWARE=True)")
+        eng = self.engine(x.device)
+        x_pm = x.transpose(1, 2).contiguous().float()
+        k_pm = tfd_kps.transpose(1, 2).contiguous().float()
+        pose, scale = eng.forward_once(x_pm, k_pm, init_pose.float().contiguous(), init_scale.float().contiguous(),
+                                       K_zoom.float().contiguous())
+        return {f"pose_{cur_iter}": pose, f"scale_{cur_iter}": scale}
+
+    # ---- fused K-loop (additive API) ------------------------------------------------------------------
+    @torch.no_grad()
+    def refine(self, pcl, prior, init_pose, init_scale, K, n_iter: int = 4):
+        """pcl [B,N_o,3] (batch["pcl"]), prior [B,N_p,3] (batch["obj_kps"]), init_pose [B,3,4],
+        init_scale [B,3], K [B,3,3] -> poses [n_iter+1,B,3,4], scales [n_iter+1,B,3] (entry 0 = init)."""
+        eng = self.engine(pcl.device)
+        return eng.refine(pcl.float(), prior.float(), init_pose.float(), init_scale.float(), K.float(), n_iter)
+
+    def refine_as_out_dict(self, pcl, prior, init_pose, init_scale, K, n_iter: int = 4) -> Dict[str, torch.Tensor]:
+        """The evaluator's out_dict for all iterations: {pose_0.., scale_0..} (catre_evaluator.py:292-311)."""
+        poses, scales = self.refine(pcl, prior, init_pose, init_scale, K, n_iter)
+        out = {}
+        for i in range(n_iter + 1):
+            out[f"pose_{i}"] = poses[i]
+            out[f"scale_{i}"] = scales[i]
+        return out
+
+
+def build_model_optimizer(cfg, is_test: bool = False, precision: str = "bf16x3", max_batch: int = 256):
+    """Same contract as the reference's build_model_optimizer (CATRE_disR_shared.py:291-350):
+    returns (model, optimizer).  ``optimizer`` is None for is_test=True, as in the reference."""
+    n_obs, n_prior = check_cfg(cfg)
+    if not is_test:
+        raise NotImplementedError("catre_b200 is an inference engine: build it with is_test=True "
+                                  "(--eval-only); training is out of scope (SURVEY.md 8(f) N4)")
+    model = CatreB200(n_obs, n_prior, precision=precision, max_batch=max_batch, cfg=cfg)
+    device = _cfg_get(cfg, "MODEL.DEVICE", "cuda")
+    model.to(torch.device(device))
+    model.eval()
+    return model, None

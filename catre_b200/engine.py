@@ -1,0 +1,218 @@
+"""ctypes binding of libcatre_b200.so (include/catre_b200.h) -- the only way the Python side reaches the
+CUDA kernels.  There is NO fallback: if the library is missing or there is no sm_100 device, every call
+raises.
+
+The reference has no FFI; this binding is what stands behind the drop-in model (catre_b200/dropin.py)
+that replaces core/catre/models/CATRE_disR_shared.py.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from typing import Dict, Optional, Tuple
+
+import torch
+
+from . import build as _build
+
+PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+
+
+class CatreCfg(ctypes.Structure):
+    _fields_ = [("n_obs", ctypes.c_int32), ("n_prior", ctypes.c_int32), ("max_batch", ctypes.c_int32),
+                ("precision", ctypes.c_int32), ("device", ctypes.c_int32), ("reserved", ctypes.c_int32 * 3)]
+
+
+# every symbol include/catre_b200.h declares: (restype, argtypes)
+_P = ctypes.c_void_p
+_F = ctypes.c_void_p  # float* passed as raw addresses (tensor.data_ptr())
+SYMBOLS = {
+    "catre_create": (ctypes.c_int, [ctypes.POINTER(_P), ctypes.POINTER(CatreCfg)]),
+    "catre_set_weight": (ctypes.c_int, [_P, ctypes.c_char_p, _F, ctypes.POINTER(ctypes.c_int64), ctypes.c_int32]),
+    "catre_num_weights": (ctypes.c_int32, []),
+    "catre_weight_name": (ctypes.c_char_p, [ctypes.c_int32]),
+    "catre_pack": (ctypes.c_int, [_P, _P]),
+    "catre_workspace_bytes": (ctypes.c_size_t, [_P, ctypes.c_int32]),
+    "catre_forward_once": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, _F, _F, _P]),
+    "catre_refine": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
+    "catre_refine_host": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
+    "catre_last_launch_count": (ctypes.c_int64, [_P]),
+    "catre_profile_enable": (ctypes.c_int, [_P, ctypes.c_int32]),
+    "catre_profile_reset": (ctypes.c_int, [_P]),
+    "catre_profile_num": (ctypes.c_int32, []),
+    "catre_profile_name": (ctypes.c_char_p, [ctypes.c_int32]),
+    "catre_profile_get": (ctypes.c_int, [_P, ctypes.c_int32, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_int64)]),
+    "catre_last_error": (ctypes.c_char_p, [_P]),
+    "catre_destroy": (None, [_P]),
+    "catre_version": (ctypes.c_char_p, []),
+}
+
+_LIB: Optional[ctypes.CDLL] = None
+
+
+def load_library(path: Optional[str] = None) -> ctypes.CDLL:
+    """dlopen the in-tree libcatre_b200.so (no compute, works without a GPU) and bind every symbol."""
+    global _LIB
+    if _LIB is not None and path is None:
+        return _LIB
+    p = path or _build.LIB_PATH
+    if not os.path.exists(p):
+        raise RuntimeError(f"{p} is missing: run `python -m catre_b200.build` (nvcc, sm_100a). "
+                           "catre_b200 has no CPU or PyTorch fallback.")
+    lib = ctypes.CDLL(p)
+    for name, (res, args) in SYMBOLS.items():
+        fn = getattr(lib, name)  # AttributeError if the header and the library disagree
+        fn.restype = res
+        fn.argtypes = args
+    if path is None:
+        _LIB = lib
+    return lib
+
+
+class CatreError(RuntimeError):
+    pass
+
+
+def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
+    return None if t is None else t.data_ptr()
+
+
+class Engine:
+    """One engine per device.  All tensors fp32; device entry points take CUDA tensors on the engine's
+    device and run on the current torch stream without host synchronisation."""
+
+    def __init__(self, n_pts: int, max_batch: int, precision: str = "bf16x3", device: int = 0):
+        self.lib = load_library()
+        self.n_pts, self.max_batch, self.device = int(n_pts), int(max_batch), int(device)
+        self.precision = precision
+        cfg = CatreCfg(n_obs=n_pts, n_prior=n_pts, max_batch=max_batch, precision=PRECISIONS[precision], device=device)
+        h = ctypes.c_void_p()
+        rc = self.lib.catre_create(ctypes.byref(h), ctypes.byref(cfg))
+        if rc != 0:
+            raise CatreError(f"catre_create failed ({rc}): {self.lib.catre_last_error(None).decode()}")
+        self._h = h
+        self._keep = []
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self.lib.catre_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _check(self, rc: int, what: str):
+        if rc != 0:
+            raise CatreError(f"{what} failed ({rc}): {self.lib.catre_last_error(self._h).decode()}")
+
+    # ---- weights ---------------------------------------------------------------------------------
+    @staticmethod
+    def weight_names():
+        lib = load_library()
+        return [lib.catre_weight_name(i).decode() for i in range(lib.catre_num_weights())]
+
+    def set_weight(self, name: str, t: torch.Tensor):
+        t = t.detach().to(torch.float32).contiguous()
+        shape = (ctypes.c_int64 * t.dim())(*t.shape)
+        self._check(self.lib.catre_set_weight(self._h, name.encode(), t.data_ptr(), shape, t.dim()), f"set_weight({name})")
+
+    def load_weights(self, state: Dict[str, torch.Tensor]):
+        """state: {checkpoint name: tensor} (CPU or CUDA).  Extra keys are an error, like a strict load."""
+        names = set(self.weight_names())
+        extra = sorted(set(state) - names)
+        missing = sorted(names - set(state))
+        if extra or missing:
+            raise CatreError(f"state dict mismatch: missing {missing[:4]}..., unexpected {extra[:4]}...")
+        for k, v in state.items():
+            self.set_weight(k, v)
+        self.pack()
+
+    def pack(self):
+        self._check(self.lib.catre_pack(self._h, self._stream()), "catre_pack")
+
+    # ---- compute ---------------------------------------------------------------------------------
+    def _stream(self):
+        return ctypes.c_void_p(torch.cuda.current_stream(self.device).cuda_stream)
+
+    def _dev(self, t: torch.Tensor, shape: Tuple[int, ...], name: str) -> torch.Tensor:
+        if not t.is_cuda or t.device.index != self.device:
+            raise CatreError(f"{name} must be a CUDA tensor on device {self.device} (got {t.device})")
+        if tuple(t.shape) != tuple(shape):
+            raise CatreError(f"{name} has shape {tuple(t.shape)}, expected {tuple(shape)}")
+        if t.dtype != torch.float32:
+            raise CatreError(f"{name} must be float32 (got {t.dtype})")
+        return t if t.is_contiguous() else t.contiguous()
+
+    def forward_once(self, x_pm, kps_pm, pose, scale, K):
+        """x_pm [B,N,3], kps_pm [B,N,3] point-major; returns (pose [B,3,4], scale [B,3])."""
+        B, N = x_pm.shape[0], self.n_pts
+        x_pm = self._dev(x_pm, (B, N, 3), "x")
+        kps_pm = self._dev(kps_pm, (B, N, 3), "tfd_kps")
+        pose = self._dev(pose, (B, 3, 4), "init_pose")
+        scale = self._dev(scale, (B, 3), "init_scale")
+        K = self._dev(K, (B, 3, 3), "K")
+        op = torch.empty((B, 3, 4), dtype=torch.float32, device=x_pm.device)
+        os_ = torch.empty((B, 3), dtype=torch.float32, device=x_pm.device)
+        self._check(self.lib.catre_forward_once(self._h, _ptr(x_pm), _ptr(kps_pm), _ptr(pose), _ptr(scale), _ptr(K), B,
+                                                _ptr(op), _ptr(os_), self._stream()), "catre_forward_once")
+        return op, os_
+
+    def refine(self, pcl, prior, init_pose, init_scale, K, n_iter: int, out=None):
+        """All K iterations on the device.  Returns poses [n_iter+1,B,3,4], scales [n_iter+1,B,3]."""
+        B, N = pcl.shape[0], self.n_pts
+        pcl = self._dev(pcl, (B, N, 3), "pcl")
+        prior = self._dev(prior, (B, N, 3), "prior")
+        init_pose = self._dev(init_pose, (B, 3, 4), "init_pose")
+        init_scale = self._dev(init_scale, (B, 3), "init_scale")
+        K = self._dev(K, (B, 3, 3), "K")
+        if out is None:
+            poses = torch.empty((n_iter + 1, B, 3, 4), dtype=torch.float32, device=pcl.device)
+            scales = torch.empty((n_iter + 1, B, 3), dtype=torch.float32, device=pcl.device)
+        else:
+            poses, scales = out
+        self._check(self.lib.catre_refine(self._h, _ptr(pcl), _ptr(prior), _ptr(init_pose), _ptr(init_scale), _ptr(K), B,
+                                          n_iter, _ptr(poses), _ptr(scales), self._stream()), "catre_refine")
+        return poses, scales
+
+    def refine_host(self, pcl, prior, init_pose, init_scale, K, n_iter: int, out=None):
+        """Host tensors in (pinned for async copies), host tensors out; copies are inside the call."""
+        B, N = pcl.shape[0], self.n_pts
+        for name, t, shp in (("pcl", pcl, (B, N, 3)), ("prior", prior, (B, N, 3)), ("init_pose", init_pose, (B, 3, 4)),
+                             ("init_scale", init_scale, (B, 3)), ("K", K, (B, 3, 3))):
+            if t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != shp or not t.is_contiguous():
+                raise CatreError(f"{name}: expected contiguous float32 host tensor of shape {shp}")
+        if out is None:
+            poses = torch.empty((n_iter + 1, B, 3, 4), dtype=torch.float32).pin_memory()
+            scales = torch.empty((n_iter + 1, B, 3), dtype=torch.float32).pin_memory()
+        else:
+            poses, scales = out
+        self._check(self.lib.catre_refine_host(self._h, _ptr(pcl), _ptr(prior), _ptr(init_pose), _ptr(init_scale), _ptr(K),
+                                               B, n_iter, _ptr(poses), _ptr(scales), self._stream()), "catre_refine_host")
+        return poses, scales
+
+    # ---- accounting ------------------------------------------------------------------------------
+    def last_launch_count(self) -> int:
+        return int(self.lib.catre_last_launch_count(self._h))
+
+    def workspace_bytes(self, B: int) -> int:
+        return int(self.lib.catre_workspace_bytes(self._h, B))
+
+    def profile_enable(self, on: bool):
+        self._check(self.lib.catre_profile_enable(self._h, 1 if on else 0), "profile_enable")
+
+    def profile_reset(self):
+        self._check(self.lib.catre_profile_reset(self._h), "profile_reset")
+
+    def profile(self) -> Dict[str, Tuple[float, int]]:
+        """{kernel group: (total device ms, launches)} since the last reset."""
+        out = {}
+        for i in range(self.lib.catre_profile_num()):
+            ms, n = ctypes.c_double(), ctypes.c_int64()
+            self._check(self.lib.catre_profile_get(self._h, i, ctypes.byref(ms), ctypes.byref(n)), "profile_get")
+            if n.value:
+                out[self.lib.catre_profile_name(i).decode()] = (ms.value, n.value)
+        return out

@@ -1,0 +1,133 @@
+/*
+ * catre_b200.h -- C ABI of libcatre_b200.so: the B200-native (sm_100a) engine for the CATRE
+ * iterative point-cloud pose-refinement forward.
+ *
+ * The reference (THU-DA-6D-Pose-Group/CATRE) is pure Python/PyTorch and has no FFI; this is the C
+ * surface a binding for its model-plugin boundary calls (ctypes: catre_b200/engine.py, shown in
+ * INTEGRATION.md).  Each entry point cites the reference interface it stands in for.
+ *
+ * Conventions
+ *   - every function returns 0 on success or a negative catre_status; nothing throws across the ABI;
+ *     catre_last_error() returns a human-readable message for the last failure on that engine.
+ *   - all tensors are fp32, contiguous, caller-owned.  "dev" pointers are device pointers on the
+ *     engine's device; "host" pointers are host memory (pinned for async copies).
+ *   - calls are stream-ordered on the cudaStream_t passed (void* here so the header needs no CUDA
+ *     include), never synchronise the host (except the *_host entry, which returns results), and are
+ *     CUDA-graph capturable.  One engine per device; calls on one engine are not re-entrant.
+ *   - objects are independent: B may be any value >= 0 (B == 0 is a no-op).  B larger than
+ *     cfg.max_batch is processed in chunks of max_batch.
+ */
+#ifndef CATRE_B200_H_
+#define CATRE_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct catre_engine catre_engine;
+
+typedef enum catre_status {
+  CATRE_OK = 0,
+  CATRE_ERR_INVALID_ARG = -1,   /* null pointer, negative size, unknown enum */
+  CATRE_ERR_SHAPE = -2,         /* weight / tensor shape does not match the configuration */
+  CATRE_ERR_UNKNOWN_WEIGHT = -3,/* name is not one of the 74 checkpoint tensors */
+  CATRE_ERR_NOT_PACKED = -4,    /* forward/refine before catre_pack, or weights missing at pack */
+  CATRE_ERR_CUDA = -5,          /* a CUDA runtime call failed (message has the cudaError string) */
+  CATRE_ERR_UNSUPPORTED = -6,   /* configuration outside the shipped CATRE config */
+  CATRE_ERR_NO_DEVICE = -7      /* no CUDA device / not an sm_100 device */
+} catre_status;
+
+/* arithmetic of the wide per-point contractions (everything else is always fp32 FMA) */
+typedef enum catre_precision {
+  CATRE_PREC_FP32_SIMT = 0,   /* fp32 FMA on CUDA cores everywhere (strict mode, validation) */
+  CATRE_PREC_BF16X3 = 1,      /* tcgen05 kind::f16, bf16 hi/lo split, 3 products, fp32 TMEM accumulate:
+                                 fp32-parity mode (<= 1e-4 on R,t,s vs the reference fp32 forward) */
+  CATRE_PREC_BF16 = 2         /* tcgen05 single-product bf16 (BASELINE.json config 3; looser tolerance) */
+} catre_precision;
+
+/* Replaces: the cfg.MODEL.CATRE / cfg.INPUT values the reference reads at model build time
+ * (core/catre/models/CATRE_disR_shared.py:291-350, configs/catre/NOCS_REAL/aug05_..._120e.py:29-30,73-114). */
+typedef struct catre_cfg {
+  int32_t n_obs;        /* INPUT.NUM_PCL: observed points per object (multiple of 128) */
+  int32_t n_prior;      /* INPUT.NUM_KPS: prior points per object (== n_obs in this version) */
+  int32_t max_batch;    /* workspace is sized for this many objects per launch (>= 1) */
+  int32_t precision;    /* catre_precision */
+  int32_t device;       /* CUDA device ordinal */
+  int32_t reserved[3];  /* must be 0 */
+} catre_cfg;
+
+/* Replaces: build_model_optimizer(cfg, is_test=True) -> model  (CATRE_disR_shared.py:291-350). */
+int catre_create(catre_engine** out, const catre_cfg* cfg);
+
+/* Replaces: MyCheckpointer(model).resume_or_load(cfg.MODEL.WEIGHTS) (core/catre/main_catre.py:151,
+ * core/utils/my_checkpoint.py:48-84).  `name` is the checkpoint key (e.g. "pcl_net.stn.conv1.weight");
+ * `data` may be a host or a device pointer (copied with cudaMemcpyDefault); shape is checked against
+ * the configuration.  All 74 tensors must be set before catre_pack. */
+int catre_set_weight(catre_engine* e, const char* name, const float* data, const int64_t* shape, int32_t ndim);
+
+/* Number of checkpoint tensors the engine expects, and the i-th expected name (for bindings/tests). */
+int32_t catre_num_weights(void);
+const char* catre_weight_name(int32_t i);
+
+/* Derive the engine's packed weights (stacked heads, folded identities, bf16 hi/lo splits). Must be
+ * called after the weights change and before forward/refine.  Stream-ordered. */
+int catre_pack(catre_engine* e, void* stream);
+
+/* Bytes of device workspace the engine holds for a launch of B objects (0 <= B <= max_batch). */
+size_t catre_workspace_bytes(const catre_engine* e, int32_t B);
+
+/* Replaces: CATRE_disR_shared.forward(x, tfd_kps, init_pose, init_scale, K_zoom, ..., do_loss=False)
+ * (CATRE_disR_shared.py:40-124) = ONE refinement iteration.
+ *   x_pm      [B, n_obs, 3]   zero-centred observed points, point-major (the memory behind the
+ *                             reference's permuted view batch["x"], core/catre/engine/batch_test.py:95)
+ *   kps_pm    [B, n_prior, 3] transformed prior points R(s*kps), point-major (batch_test.py:85-92)
+ *   pose      [B, 3, 4], scale [B, 3], K [B, 3, 3] (only K[0][0], K[1][1] are read)
+ *   out_pose  [B, 3, 4], out_scale [B, 3]          (= out_dict["pose_i"], out_dict["scale_i"]) */
+int catre_forward_once(catre_engine* e, const float* x_pm, const float* kps_pm, const float* pose,
+                       const float* scale, const float* K, int32_t B, float* out_pose, float* out_scale,
+                       void* stream);
+
+/* Replaces: the evaluator's K-loop, batch_updater_test + model.forward per iteration
+ * (core/catre/engine/catre_evaluator.py:292-311, core/catre/engine/batch_test.py:63-97).
+ *   pcl       [B, n_obs, 3]   observed cloud, camera frame (batch["pcl"])
+ *   prior     [B, n_prior, 3] normalised category prior per object (batch["obj_kps"])
+ *   out_poses [n_iter+1, B, 3, 4], out_scales [n_iter+1, B, 3]; entry 0 = the initial estimate, entry i =
+ *   out_dict["pose_i"/"scale_i"] (the evaluator consumes every iteration).  Points never leave the GPU. */
+int catre_refine(catre_engine* e, const float* pcl, const float* prior, const float* init_pose,
+                 const float* init_scale, const float* K, int32_t B, int32_t n_iter, float* out_poses,
+                 float* out_scales, void* stream);
+
+/* Same as catre_refine with HOST buffers (pinned or pageable): copies inputs host->device, refines,
+ * copies the poses device->host and synchronises the stream before returning.  This is the call the
+ * end-to-end (`e2e`) benchmark times. */
+int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, const float* init_pose,
+                      const float* init_scale, const float* K, int32_t B, int32_t n_iter, float* out_poses,
+                      float* out_scales, void* stream);
+
+/* Number of kernels the last forward/refine call launched (bench.py's `gpu_launches`). */
+int64_t catre_last_launch_count(const catre_engine* e);
+
+/* Average device time (ms, CUDA events on the launching stream) of the kernel group `which` over the
+ * calls since catre_profile_reset; `which` indexes catre_profile_name().  Profiling is off by default
+ * (events cost launches); enable with catre_profile_enable(e, 1).  Used by bench.py's roofline leg. */
+int catre_profile_enable(catre_engine* e, int32_t on);
+int catre_profile_reset(catre_engine* e);
+int32_t catre_profile_num(void);
+const char* catre_profile_name(int32_t which);
+int catre_profile_get(catre_engine* e, int32_t which, double* total_ms, int64_t* launches);
+
+/* Message for the last error on this engine (or for a failed catre_create when e == NULL). */
+const char* catre_last_error(const catre_engine* e);
+
+void catre_destroy(catre_engine* e);
+
+/* Library build info: "catre_b200 <version> sm_100a ..." */
+const char* catre_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* CATRE_B200_H_ */

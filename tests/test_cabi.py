@@ -1,0 +1,93 @@
+"""Host-side checks that need no GPU: the C-ABI library loads and exports every symbol the header
+declares, the weight registry equals the reference checkpoint, and the drop-in module has the
+reference's state_dict."""
+import ctypes
+import os
+import re
+
+import pytest
+import torch
+
+from catre_b200 import build, dropin, engine, synth
+
+REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def lib():
+    build.build()  # nvcc cross-compiles sm_100a without a GPU
+    return engine.load_library()
+
+
+def header_symbols():
+    src = open(os.path.join(REPO, "include", "catre_b200.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(catre_[a-z_0-9]+)\s*\(", src)))
+
+
+def test_library_exports_every_header_symbol(lib):
+    syms = header_symbols()
+    assert len(syms) >= 15
+    for s in syms:
+        assert hasattr(lib, s), f"libcatre_b200.so does not export {s}"
+    assert sorted(engine.SYMBOLS) == syms  # the ctypes binding covers the whole header
+
+
+def test_version_and_weight_registry(lib):
+    assert b"sm_100a" in lib.catre_version()
+    names = engine.Engine.weight_names()
+    w = synth.load_weights()
+    assert names == list(w.keys())  # same 74 names, checkpoint order
+
+
+def test_create_rejects_bad_config(lib):
+    h = ctypes.c_void_p()
+    for kw in (dict(n_obs=1000, n_prior=1000), dict(n_obs=1024, n_prior=512), dict(n_obs=1024, n_prior=1024, max_batch=0),
+               dict(n_obs=1024, n_prior=1024, precision=9)):
+        full = dict(n_obs=1024, n_prior=1024, max_batch=4, precision=0, device=0)
+        full.update(kw)
+        cfg = engine.CatreCfg(**full)
+        rc = lib.catre_create(ctypes.byref(h), ctypes.byref(cfg))
+        assert rc < 0 and not h.value
+        assert len(lib.catre_last_error(None)) > 0
+
+
+@pytest.mark.skipif(torch.cuda.is_available(), reason="checks the no-device error path")
+def test_no_device_fails_loudly(lib):
+    with pytest.raises(engine.CatreError):
+        engine.Engine(1024, 4, "fp32")
+
+
+def test_dropin_state_dict_matches_checkpoint():
+    w = synth.load_weights()
+    m = dropin.CatreB200(1024, 1024)
+    sd = m.state_dict()
+    assert list(sd.keys()) == list(w.keys())
+    for k in w:
+        assert tuple(sd[k].shape) == tuple(w[k].shape), k
+    res = m.load_state_dict(w, strict=True)
+    assert str(res) == "<All keys matched successfully>"
+    assert sum(p.numel() for p in m.parameters()) == 4298711
+
+
+def test_dropin_refuses_cpu_and_training():
+    m = dropin.CatreB200(1024, 1024)
+    b = synth.known_answer_inputs()
+    x = b.pcl.permute(0, 2, 1)
+    with pytest.raises(NotImplementedError):
+        m(x, x, b.init_pose, b.init_scale, K_zoom=b.K, do_loss=True)
+    with pytest.raises(engine.CatreError):  # no CPU path, no silent fallback
+        m(x, x, b.init_pose, b.init_scale, K_zoom=b.K)
+
+
+def test_check_cfg():
+    cfg = {"INPUT": {"NUM_PCL": 1024, "NUM_KPS": 1024},
+           "MODEL": {"REFINE_SCLAE": True, "CATRE": {"ROT_HEAD": {"ROT_TYPE": "ego_rot6d", "INIT_CFG": {"num_points": 2048}}}}}
+    assert dropin.check_cfg(cfg) == (1024, 1024)
+    cfg["MODEL"]["CATRE"]["ROT_HEAD"]["ROT_TYPE"] = "allo_rot6d"
+    with pytest.raises(NotImplementedError):
+        dropin.check_cfg(cfg)
+    with pytest.raises(NotImplementedError):
+        dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}}, is_test=False)
+    model, opt = dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}}, is_test=True)
+    assert opt is None and not model.training

@@ -1,0 +1,169 @@
+"""Parity of the CUDA path (through the C ABI) against the committed golden vectors of the unmodified
+reference and against the CPU oracle, plus size-independent properties at BASELINE.json's full sizes.
+
+Tolerance (BASELINE.json north_star): every (R, t, s) component within 1e-4 of the reference fp32 forward.
+"""
+import pytest
+import torch
+
+from catre_b200 import dropin, engine, synth
+from oracle import catre_oracle
+from tests import golden_util as gu
+
+pytestmark = pytest.mark.gpu
+
+TOL = gu.TOL  # 1e-4
+PRECS = ["fp32", "bf16x3"]
+
+
+@pytest.fixture(scope="module")
+def weights():
+    return synth.load_weights()
+
+
+_ENGINES = {}
+
+
+def get_engine(weights, n_pts, prec, max_batch=64):
+    key = (n_pts, prec, max_batch)
+    if key not in _ENGINES:
+        eng = engine.Engine(n_pts, max_batch, prec, 0)
+        eng.load_weights(catre_oracle.resize_conv_p(weights, n_pts))
+        _ENGINES[key] = eng
+    return _ENGINES[key]
+
+
+def run_refine(eng, b, n_iter):
+    d = b.to("cuda")
+    poses, scales = eng.refine(d.pcl, d.prior, d.init_pose, d.init_scale, d.K, n_iter)
+    torch.cuda.synchronize()
+    return poses.cpu(), scales.cpu()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", gu.case_names())
+def test_refine_matches_reference_golden(weights, name, prec):
+    case = gu.load_case(name)
+    eng = get_engine(weights, case.n_pts, prec)
+    poses, scales = run_refine(eng, case.batch, case.n_iter)
+    assert torch.equal(poses[0], case.batch.init_pose) and torch.equal(scales[0], case.batch.init_scale)
+    e_r, e_t, e_s = gu.max_abs_err(poses, scales, case.poses, case.scales)
+    assert max(e_r, e_t, e_s) <= TOL, (name, prec, e_r, e_t, e_s)
+    assert eng.last_launch_count() > 0
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_known_answer_vector(weights, prec):
+    """SURVEY.md 8(c) KAT recorded from the reference."""
+    b = synth.known_answer_inputs()
+    eng = get_engine(weights, 1024, prec)
+    poses, scales = run_refine(eng, b, 4)
+    t4 = torch.tensor((0.0179817, -0.0090819, 1.0235741))
+    s4 = torch.tensor((0.1317138, 0.0903642, 0.1021996))
+    r4 = torch.tensor((0.9763225, 0.1059966, 0.1885720, -0.1304222, 0.9838986, 0.1222041, -0.1725824, -0.1439046, 0.9744264))
+    assert (poses[4, 0, :, 3] - t4).abs().max() <= TOL
+    assert (scales[4, 0] - s4).abs().max() <= TOL
+    assert (poses[4, 0, :, :3].flatten() - r4).abs().max() <= TOL
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_forward_once_through_dropin_matches_oracle(weights, prec):
+    """The reference-facing call: model(x, tfd_kps, init_pose, init_scale, K_zoom=..., cur_iter=i) with the
+    permuted views batch_updater_test produces; checked against the CPU oracle's single iteration."""
+    b = synth.make_batch(5, 1024, seed=11)
+    model = dropin.CatreB200(1024, 1024, precision=prec, max_batch=8)
+    model.load_state_dict(weights, strict=True)
+    model = model.to("cuda").eval()
+    x, tfd = catre_oracle.update_points(b.pcl, b.prior, b.init_pose, b.init_scale)
+    ref_pose, ref_scale = catre_oracle.forward_once(weights, x, tfd, b.init_pose, b.init_scale, b.K)
+    out = model(x.cuda(), tfd.cuda(), init_pose=b.init_pose.cuda(), init_scale=b.init_scale.cuda(), K_zoom=b.K.cuda(),
+                obj_class=b.obj_cls.cuda(), do_loss=False, cur_iter=3)
+    assert set(out) == {"pose_3", "scale_3"} and out["pose_3"].is_cuda
+    assert (out["pose_3"].cpu() - ref_pose).abs().max() <= TOL
+    assert (out["scale_3"].cpu() - ref_scale).abs().max() <= TOL
+    od = model.refine_as_out_dict(b.pcl.cuda(), b.prior.cuda(), b.init_pose.cuda(), b.init_scale.cuda(), b.K.cuda(), 1)
+    assert (od["pose_1"].cpu() - ref_pose).abs().max() <= TOL
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_oracle_parity_seeded_n256(weights, prec):
+    """Fresh seeded inputs (not a committed fixture) at a size the oracle finishes in seconds."""
+    n = 256
+    b = synth.make_batch(6, n, seed=21)
+    w = catre_oracle.resize_conv_p(weights, n)
+    ref_p, ref_s = catre_oracle.refine(w, b.pcl, b.prior, b.init_pose, b.init_scale, b.K, 3)
+    eng = get_engine(weights, n, prec)
+    poses, scales = run_refine(eng, b, 3)
+    e = gu.max_abs_err(poses, scales, ref_p, ref_s)
+    assert max(e) <= TOL, e
+
+
+def test_empty_batch_and_zero_iters(weights):
+    eng = get_engine(weights, 1024, "fp32")
+    b = synth.make_batch(2, 1024, seed=3).to("cuda")
+    p, s = eng.refine(b.pcl[:0], b.prior[:0], b.init_pose[:0], b.init_scale[:0], b.K[:0], 4)
+    assert p.shape == (5, 0, 3, 4) and s.shape == (5, 0, 3)
+    p, s = eng.refine(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, 0)
+    torch.cuda.synchronize()
+    assert torch.equal(p[0], b.init_pose) and torch.equal(s[0], b.init_scale)
+
+
+def test_errors_are_reported_not_ub(weights):
+    eng = get_engine(weights, 1024, "fp32")
+    b = synth.make_batch(2, 1024, seed=3).to("cuda")
+    with pytest.raises(engine.CatreError):
+        eng.refine(b.pcl[:, :512], b.prior, b.init_pose, b.init_scale, b.K, 1)  # ragged point count
+    with pytest.raises(engine.CatreError):
+        eng.refine(b.pcl.cpu(), b.prior, b.init_pose, b.init_scale, b.K, 1)
+    e2 = engine.Engine(1024, 4, "fp32", 0)
+    with pytest.raises(engine.CatreError):  # not packed
+        e2.refine(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, 1)
+    with pytest.raises(engine.CatreError):  # conv_p tied to the point count
+        e2.set_weight("rot_head.rot_head_x.conv_p.weight", torch.zeros(1, 1024, 1))
+    with pytest.raises(engine.CatreError):
+        e2.set_weight("nope.weight", torch.zeros(3))
+    e2.close()
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_full_size_properties(weights, prec):
+    """BASELINE.json config 2 size (B=64, N=1024, K=4) through size-independent properties:
+    bit-exact repeatability, object independence (batch order / chunking does not change an object's
+    result), orthonormal R with det +1, host entry == device entry."""
+    B, N, K = 64, 1024, 4
+    b = synth.make_batch(B, N, seed=2)
+    eng = get_engine(weights, N, prec, max_batch=64)
+    p1, s1 = run_refine(eng, b, K)
+    p2, s2 = run_refine(eng, b, K)
+    assert torch.equal(p1, p2) and torch.equal(s1, s2)  # idempotent, deterministic reductions
+    # object independence: reversed batch order, and chunked execution (max_batch 24 -> 3 chunks)
+    perm = torch.arange(B - 1, -1, -1)
+    rb = synth.Batch(b.pcl[perm].contiguous(), b.prior[perm].contiguous(), b.init_pose[perm].contiguous(),
+                     b.init_scale[perm].contiguous(), b.K[perm].contiguous(), b.obj_cls[perm].contiguous())
+    p3, s3 = run_refine(eng, rb, K)
+    assert torch.equal(p3[:, perm], p1) and torch.equal(s3[:, perm], s1)
+    eng_small = get_engine(weights, N, prec, max_batch=24)
+    p4, s4 = run_refine(eng_small, b, K)
+    assert torch.equal(p4, p1) and torch.equal(s4, s1)
+    # rotations stay in SO(3)
+    r = p1[1:, :, :, :3].double()
+    eye = torch.eye(3, dtype=torch.float64)
+    assert (r @ r.transpose(-1, -2) - eye).abs().max() < 1e-5
+    assert (torch.linalg.det(r) - 1).abs().max() < 1e-5
+    # host entry (pinned buffers, copies inside) returns the same bytes
+    ph, sh = eng.refine_host(b.pcl.pin_memory(), b.prior.pin_memory(), b.init_pose.pin_memory(),
+                             b.init_scale.pin_memory(), b.K.pin_memory(), K)
+    assert torch.equal(ph, p1) and torch.equal(sh, s1)
+    # and it matches the reference golden for this exact batch
+    case = gu.load_case("c2_b64_n1024_k4")
+    e = gu.max_abs_err(p1, s1, case.poses, case.scales)
+    assert max(e) <= TOL, e
+
+
+def test_precision_modes_agree(weights):
+    """fp32 CUDA-core mode vs bf16x3 tensor-core mode on the same inputs (both within TOL of the
+    reference, so within 2*TOL of each other; typically ~1e-5)."""
+    b = synth.make_batch(16, 1024, seed=31)
+    pa, sa = run_refine(get_engine(weights, 1024, "fp32"), b, 4)
+    pb, sb = run_refine(get_engine(weights, 1024, "bf16x3"), b, 4)
+    assert (pa - pb).abs().max() <= 2 * TOL and (sa - sb).abs().max() <= 2 * TOL
