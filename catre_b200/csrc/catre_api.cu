@@ -253,6 +253,11 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   int rc;
   const bool tc = e->cfg.precision != CATRE_PREC_FP32_SIMT;
 
+  // column-max key buffers are laid out for the current S so one fill resets all of them
+  e->gmax_stn = e->gmax_all;
+  e->gmax_fstn = e->gmax_all + (size_t)S * 1024;
+  e->gmax_g = e->gmax_all + (size_t)S * 2048;
+  e->gmax_pf = e->gmax_all + (size_t)S * 3072;
   if ((rc = fill_i32(e, s, e->gmax_all, (long long)S * (1024 * 3 + 64), KEY_NEG_INF))) return rc;
 
   // ---- E1: STN3d (pointnets/pointnet.py:24-41)
@@ -677,6 +682,21 @@ int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, con
 }
 
 int64_t catre_last_launch_count(const catre_engine* e) { return e ? e->launches : 0; }
+
+int catre_debug_read(catre_engine* e, const char* name, void* dst_host, size_t bytes) {
+  if (!e || !name || !dst_host) return CATRE_ERR_INVALID_ARG;
+  std::map<std::string, const void*> m = {
+      {"q", e->q}, {"h64a", e->h64a}, {"h64b", e->h64b}, {"h128", e->h128}, {"h512", e->h512}, {"a0", e->a0}, {"a1", e->a1},
+      {"gmax_stn", e->gmax_stn}, {"gmax_fstn", e->gmax_fstn}, {"gmax_g", e->gmax_g}, {"gmax_pf", e->gmax_pf},
+      {"fc512", e->fc512}, {"fc256", e->fc256}, {"t3", e->t3}, {"t64", e->t64}, {"cset", e->cset},
+      {"stats0", e->stats0}, {"stats1", e->stats1}, {"gn0", e->gn0}, {"gn1", e->gn1}, {"rot_partial", e->rot_partial}};
+  tc_debug_buffers(e->tcws, m);
+  auto it = m.find(name);
+  if (it == m.end() || it->second == nullptr) return fail(e, CATRE_ERR_INVALID_ARG, "no debug buffer '%s'", name);
+  CU_TRY(e, cudaDeviceSynchronize());
+  CU_TRY(e, cudaMemcpy(dst_host, it->second, bytes, cudaMemcpyDeviceToHost));
+  return CATRE_OK;
+}
 
 int catre_profile_enable(catre_engine* e, int32_t on) {
   if (!e) return CATRE_ERR_INVALID_ARG;

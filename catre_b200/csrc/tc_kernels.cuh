@@ -9,6 +9,7 @@ namespace catre {
 struct TcWeights {};
 struct TcWorkspace {};
 inline int tc_unsupported() { return -6; }
+inline void tc_debug_buffers(TcWorkspace&, std::map<std::string, const void*>&) {}
 inline int tc_workspace_alloc(TcWorkspace&, size_t, std::vector<void*>&, size_t*, catre_engine*) { return 0; }
 inline int tc_pack_weights(TcWeights&, const std::map<std::string, std::vector<float>>&, const std::vector<float>&, bool,
                            std::vector<void*>&, catre_engine*) { return tc_unsupported(); }

@@ -38,6 +38,7 @@ SYMBOLS = {
     "catre_refine": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
     "catre_refine_host": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
     "catre_last_launch_count": (ctypes.c_int64, [_P]),
+    "catre_debug_read": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_size_t]),
     "catre_profile_enable": (ctypes.c_int, [_P, ctypes.c_int32]),
     "catre_profile_reset": (ctypes.c_int, [_P]),
     "catre_profile_num": (ctypes.c_int32, []),
@@ -197,6 +198,13 @@ class Engine:
     # ---- accounting ------------------------------------------------------------------------------
     def last_launch_count(self) -> int:
         return int(self.lib.catre_last_launch_count(self._h))
+
+    def debug_read(self, name: str, shape, dtype=torch.float32) -> torch.Tensor:
+        """Tests only: copy an internal workspace buffer of the last launch to a CPU tensor."""
+        out = torch.empty(shape, dtype=dtype)
+        self._check(self.lib.catre_debug_read(self._h, name.encode(), out.data_ptr(), out.numel() * out.element_size()),
+                    f"debug_read({name})")
+        return out
 
     def workspace_bytes(self, B: int) -> int:
         return int(self.lib.catre_workspace_bytes(self._h, B))

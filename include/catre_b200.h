@@ -110,6 +110,10 @@ int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, con
 /* Number of kernels the last forward/refine call launched (bench.py's `gpu_launches`). */
 int64_t catre_last_launch_count(const catre_engine* e);
 
+/* Debug tap (tests only): synchronise and copy `bytes` of the internal workspace buffer `name`
+ * ("t3", "t64", "gmax_g", "cset", ...) of the last launch to host memory. */
+int catre_debug_read(catre_engine* e, const char* name, void* dst_host, size_t bytes);
+
 /* Average device time (ms, CUDA events on the launching stream) of the kernel group `which` over the
  * calls since catre_profile_reset; `which` indexes catre_profile_name().  Profiling is off by default
  * (events cost launches); enable with catre_profile_enable(e, 1).  Used by bench.py's roofline leg. */

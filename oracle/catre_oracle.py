@@ -52,7 +52,7 @@ def tnet(w: Weights, prefix: str, x: torch.Tensor, k: int) -> torch.Tensor:
     h = F.relu(_fc(w, prefix + ".fc1", h))
     h = F.relu(_fc(w, prefix + ".fc2", h))
     h = _fc(w, prefix + ".fc3", h)
-    eye = torch.eye(k, dtype=h.dtype).reshape(1, k * k)
+    eye = torch.eye(k, dtype=h.dtype, device=h.device).reshape(1, k * k)
     return (h + eye).reshape(-1, k, k)
 
 
