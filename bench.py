@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""Benchmark of the CATRE pose-refinement hot path on B200 (contract: see README / DESIGN.md).
+
+  python bench.py --gpus N --steps K --warmup W            # this repo's engine (libcatre_b200.so)
+  python bench.py --impl reference --steps K --warmup W    # the reference algorithm on the host CPU cores
+
+A "step" is one pass of the hot path over one batch: `batch` objects per GPU, N points per set, K_iter
+refinement iterations (default = BASELINE.json configs[1]: batch 64, N 1024, K 4, fp32 parity mode).
+Metric = pose-refinements/sec = objects fully refined per second, whole job (all GPUs).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import sys
+import threading
+import time
+
+REPO = os.path.dirname(os.path.abspath(__file__))
+if REPO not in sys.path:
+    sys.path.insert(0, REPO)
+
+METRIC = "pose-refinements/sec"
+UNIT = "objects/s"
+
+
+def flops_per_object_iter(n_o: int, n_p: int) -> float:
+    """Algorithmic FLOPs of one reference forward per object (counted on the reference
+    model with torch FlopCounterMode): 3,149,598 (N_o+N_p) + 18 N_p + 10,139,190."""
+    return 3149598.0 * (n_o + n_p) + 18.0 * n_p + 10139190.0
+
+
+# algorithmic FLOPs per POINT of each wide layer (2 * C_in * C_out), for per-kernel rooflines
+LAYER_FLOPS_PER_POINT = {
+    "conv4_max": 2 * 512 * 1024, "stn_conv3_max": 2 * 128 * 1024, "fstn_conv3_max": 2 * 128 * 1024,
+    "conv3": 2 * 128 * 512, "rot_layer1": 2 * 256 * 256 * 2, "rot_layer0": 2 * 1088 * 256 * 2,
+    "stn_conv2": 2 * 64 * 128, "fstn_conv2": 2 * 64 * 128, "conv2": 2 * 64 * 128, "fstn_conv1": 2 * 64 * 64,
+}
+
+
+def measured_peaks():
+    p = os.path.join(REPO, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        with open(p) as f:
+            d = json.load(f)
+        return {"hbm_gbs": d["hbm_gbs"], "bf16_tflops": d["bf16_tflops"],
+                "bf16_tflops_sustained": d.get("bf16_tflops_sustained"), "source": "measured (MEASURED_PEAKS.json)"}
+    return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0,
+            "source": "fallback (B200_PROFILING.md)"}
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock / throttle reasons of one GPU through NVML while the timed region runs."""
+
+    def __init__(self, index: int, period: float = 0.02):
+        super().__init__(daemon=True)
+        self.index, self.period = index, period
+        self.samples, self.reasons, self.max_mhz = [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            self.ok = False
+
+    def run(self):
+        if not self.ok:
+            return
+        nv = self.nv
+        names = {
+            getattr(nv, "nvmlClocksThrottleReasonHwSlowdown", 0x8): "hw_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0x40): "hw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0x20): "sw_thermal_slowdown",
+            getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0x4): "sw_power_cap",
+            getattr(nv, "nvmlClocksThrottleReasonHwPowerBrakeSlowdown", 0x80): "hw_power_brake",
+        }
+        while not self._stop_evt.is_set():
+            try:
+                self.samples.append(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM))
+                try:
+                    mask = nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    mask = nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in names.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(self.period)
+
+    def stop(self):
+        self._stop_evt.set()
+        self.join(timeout=2)
+        s = sorted(self.samples)
+        return {"sm_mhz": (s[len(s) // 2] if s else None), "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons),
+                "samples": len(s)}
+
+
+def cpu_reference_run(batch: int, n_pts: int, n_iter: int, steps: int, warmup: int, threads: int):
+    """The reference algorithm on the host cores: the CPU oracle (a torch-CPU restatement of the reference,
+    pinned against the unmodified reference's golden vectors; the reference itself is pure Python and does
+    not travel to the GPU box).  Returns (objects/s, seconds per step)."""
+    import torch
+
+    from catre_b200 import synth
+    from oracle import catre_oracle  # the one place bench.py executes oracle/: the CPU baseline
+
+    torch.set_num_threads(threads)
+    w = catre_oracle.resize_conv_p(synth.load_weights(), n_pts)
+    b = synth.make_batch(batch, n_pts, seed=2)
+    for _ in range(warmup):
+        catre_oracle.refine(w, b.pcl, b.prior, b.init_pose, b.init_scale, b.K, n_iter)
+    t0 = time.perf_counter()
+    for _ in range(steps):
+        catre_oracle.refine(w, b.pcl, b.prior, b.init_pose, b.init_scale, b.K, n_iter)
+    dt = (time.perf_counter() - t0) / max(steps, 1)
+    return batch / dt, dt
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="catre_b200", choices=["catre_b200", "reference"])
+    ap.add_argument("--batch", type=int, default=64, help="objects per GPU per step (BASELINE configs[1])")
+    ap.add_argument("--n-pts", type=int, default=1024)
+    ap.add_argument("--n-iter", type=int, default=4)
+    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--cpu-sample", type=int, default=16, help="objects in the bounded CPU-baseline sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "catre_b200" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    workload = (f"batch={args.batch}/GPU, N={args.n_pts} pts per set (obs+prior), K={args.n_iter} iters, "
+                f"NOCS REAL275 aug05_kpsMS_r9d config (BASELINE.json configs[1])")
+
+    # ------------------------------------------------------------------ reference arm (CPU) -------------
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        threads = os.cpu_count() or 1
+        sample = min(args.cpu_sample, args.batch)
+        steps, warm = max(1, min(args.steps, 3)), min(args.warmup, 1)
+        val, dt = cpu_reference_run(sample, args.n_pts, args.n_iter, steps, warm, threads)
+        line = {
+            "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": steps, "warmup": warm,
+            "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
+            "data": "synthetic (seeded; shipped checkpoint weights)",
+            "config": {"workload": workload, "n_pts": args.n_pts, "n_iter": args.n_iter,
+                       "note": f"each step = a bounded sample of {sample} objects of the workload on the host CPU"},
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port",
+                             "sample": f"{sample} objects, N={args.n_pts}, K={args.n_iter}, {steps} step(s), torch CPU fp32"},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        }
+        print(json.dumps(line), flush=True)
+        return
+
+    # ------------------------------------------------------------------ this repo's engine --------------
+    import torch
+    import torch.distributed as dist
+
+    from catre_b200 import engine, shard, synth
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device (no CPU fallback exists)")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B, N, K = args.batch, args.n_pts, args.n_iter
+    total_B = B * world
+
+    eng = engine.Engine(N, B, args.precision, local_rank)
+    eng.load_weights(synth.resize_conv_p(synth.load_weights(), N))
+    # a few different resident batches, rotated between steps; rank r owns objects [r*B, (r+1)*B)
+    n_rot = 4
+    host = [synth.make_batch(B, N, seed=1000 * rank + i) for i in range(n_rot)]
+    devb = [b.to(dev) for b in host]
+    pinned = [synth.Batch(*(getattr(b, f).pin_memory() for f in ("pcl", "prior", "init_pose", "init_scale", "K", "obj_cls")))
+              for b in host]
+    out_dev = (torch.empty((K + 1, B, 3, 4), device=dev), torch.empty((K + 1, B, 3), device=dev))
+    out_pin = (torch.empty((K + 1, B, 3, 4)).pin_memory(), torch.empty((K + 1, B, 3)).pin_memory())
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)  # > 126 MB L2
+
+    def step_device(i):
+        b = devb[i % n_rot]
+        p, s = eng.refine(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, K, out=out_dev)
+        if world > 1:
+            shard.gather_poses(p[-1:], s[-1:], total_B)
+        return p
+
+    def step_host(i):
+        b = pinned[i % n_rot]
+        p, s = eng.refine_host(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, K, out=out_pin)
+        if world > 1:
+            shard.gather_poses(p[-1:].to(dev, non_blocking=True), s[-1:].to(dev, non_blocking=True), total_B)
+            torch.cuda.synchronize()
+        return p
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps, warmup, host_timed=False):
+        """W untimed warm-ups, then K steps; L2 flushed (untimed) before every step; device time by CUDA
+        events on the launching stream (host entry: wall clock around the synchronous call)."""
+        for i in range(warmup):
+            fn(i)
+        barrier()
+        total_ms = 0.0
+        for i in range(steps):
+            flush.fill_(i & 0xFF)
+            torch.cuda.synchronize()
+            if host_timed:
+                t0 = time.perf_counter()
+                fn(i)
+                torch.cuda.synchronize()
+                total_ms += (time.perf_counter() - t0) * 1e3
+            else:
+                a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                a.record()
+                fn(i)
+                b_.record()
+                torch.cuda.synchronize()
+                total_ms += a.elapsed_time(b_)
+        barrier()
+        t = torch.tensor([total_ms], device=dev, dtype=torch.float64)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return t.item()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    total_ms = timed(step_device, args.steps, args.warmup)
+    clocks = sampler.stop()
+    launches = eng.last_launch_count() * args.steps
+    ms_per_step = total_ms / args.steps
+    value = total_B / (ms_per_step * 1e-3)
+
+    e2e_ms = timed(step_host, args.steps, min(args.warmup, 3), host_timed=True) / args.steps
+    h2d = sum(getattr(pinned[0], f).numel() * 4 for f in ("pcl", "prior", "init_pose", "init_scale", "K"))
+    d2h = (out_pin[0].numel() + out_pin[1].numel()) * 4
+    e2e = {"value": total_B / (e2e_ms * 1e-3), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+           "ms_per_step": e2e_ms, "api": "catre_refine_host (C ABI, pinned host buffers, copies inside the call)"}
+
+    # ---- per-kernel roofline: same steps again with per-launch CUDA events on the launching stream
+    roofline = None
+    if rank == 0:
+        eng.profile_enable(True)
+        eng.profile_reset()
+        for i in range(args.steps):
+            flush.fill_(i & 0xFF)
+            step_device(i)
+        torch.cuda.synchronize()
+        prof = eng.profile()
+        eng.profile_enable(False)
+        peaks = measured_peaks()
+        tot = sum(v[0] for v in prof.values())
+        cand = {k: v for k, v in prof.items() if k in LAYER_FLOPS_PER_POINT}
+        top = max(cand, key=lambda k: cand[k][0])
+        ms_launch = cand[top][0] / cand[top][1]
+        launches_per_step_top = cand[top][1] / args.steps
+        pts_per_launch = 2 * B * N / max(1.0, launches_per_step_top / K)
+        fl = LAYER_FLOPS_PER_POINT[top] * pts_per_launch
+        ach = fl / (ms_launch * 1e-3) / 1e12
+        nprod = {"bf16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
+        roofline = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
+                    "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                    "ms_per_launch": ms_launch, "share_of_step": cand[top][0] / tot if tot else None,
+                    "mma_products_per_mac": nprod,
+                    "note": "achieved = algorithmic FLOPs (one fp32-equivalent product per MAC) / CUDA-event time; "
+                            f"the {args.precision} mode issues {nprod} bf16 MMA product(s) per MAC"
+                            + (" on CUDA cores (no tensor pipe)" if args.precision == "fp32" else ""),
+                    "whole_step_tflops": flops_per_object_iter(N, N) * B * K / (ms_per_step * 1e-3) / 1e12,
+                    "profile_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in
+                                            sorted(prof.items(), key=lambda kv: -kv[1][0])}}
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        threads = os.cpu_count() or 1
+        sample = min(args.cpu_sample, B)
+        v, dt = cpu_reference_run(sample, N, K, 1, 1, threads)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
+                        "sample": f"{sample} objects, N={N}, K={K}, 1 pass after 1 warm-up, torch CPU fp32 oracle"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": {"fp32": "f32", "bf16x3": "bf16x3->f32 (3 bf16 tcgen05 products per MAC, fp32 accumulate)",
+                      "bf16": "bf16 (fp32 accumulate)"}[args.precision],
+            "data": "synthetic (seeded, SURVEY.md 8(d)); weights = the reference's shipped checkpoint",
+            "config": {"workload": workload, "batch_per_gpu": B, "global_batch": total_B, "n_pts": N, "n_iter": K,
+                       "precision": args.precision, "parallelism": f"batch-sharded x{world}, final-pose all-gather",
+                       "l2": "flushed (256 MB write) before every timed step; inputs resident in HBM",
+                       "object_iterations_per_s": value * K},
+            "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -59,6 +59,27 @@ def load_weights(path: str = WEIGHTS_NPZ) -> Dict[str, torch.Tensor]:
     return {k: torch.from_numpy(z[k]) for k in z.files}
 
 
+def resize_conv_p(w: Dict[str, torch.Tensor], n_pts: int) -> Dict[str, torch.Tensor]:
+    """Fixture-defined weights for N != 1024 (SURVEY.md 8(d) "Weights per config"): the checkpoint with the
+    two conv_p.weight [1, 2*1024, 1] re-sized -- obs half and prior half each linearly re-sampled to n_pts
+    and scaled by 1024 / n_pts (conv_p is tied to the point count,
+    core/catre/models/heads/conv_out_per_rot_head.py:112)."""
+    import torch.nn.functional as F
+
+    out = dict(w)
+    for head in ("rot_head.rot_head_x", "rot_head.rot_head_y"):
+        cp = w[head + ".conv_p.weight"]
+        half = cp.shape[1] // 2
+        if half == n_pts:
+            continue
+        parts = []
+        for seg in (cp[:, :half, 0], cp[:, half:, 0]):
+            r = F.interpolate(seg.reshape(1, 1, half).double(), size=n_pts, mode="linear", align_corners=True)
+            parts.append(r.reshape(1, n_pts) * (float(half) / float(n_pts)))
+        out[head + ".conv_p.weight"] = torch.cat(parts, dim=1).reshape(1, 2 * n_pts, 1).to(cp.dtype).contiguous()
+    return out
+
+
 def resample_prior(prior: torch.Tensor, n_pts: int) -> torch.Tensor:
     """[..., 1024, 3] -> [..., n_pts, 3]: first-N when shrinking, tiling when growing."""
     n0 = prior.shape[-2]
