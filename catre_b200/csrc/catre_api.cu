@@ -97,14 +97,19 @@ struct catre_engine {
   float *rot_gn0_g = nullptr, *rot_gn0_b = nullptr, *rot_gn1_g = nullptr, *rot_gn1_b = nullptr;
   float *rot_b1 = nullptr, *neck_w = nullptr, *neck_b = nullptr, *wp = nullptr, *convp_b = nullptr;
   float *ts_w0t = nullptr, *ts_w1t = nullptr;
-  TcWeights tcw;  // bf16 hi/lo copies + tensor maps (tensor-core modes)
+  // bf16 hi/lo weight copies + tensor maps (tensor-core modes); "MA" maps have 128-row boxes (M side of
+  // the MMA), "NB" maps have BN-row boxes (N side)
+  TcPair tw_stn_c2, tw_stn_c3, tw_fstn_c1, tw_fstn_c2, tw_fstn_c3, tw_conv2, tw_conv3, tw_conv4, tw_rot0, tw_rot1[2];
+  int num_sms = 148;
 
   // ---- workspace
   float *q = nullptr, *h64a = nullptr, *h64b = nullptr, *h128 = nullptr, *h512 = nullptr, *a0 = nullptr, *a1 = nullptr;
   int *gmax_all = nullptr, *gmax_stn = nullptr, *gmax_fstn = nullptr, *gmax_g = nullptr, *gmax_pf = nullptr;
   float *fc512 = nullptr, *fc256 = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
   float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
-  TcWorkspace tcws;
+  // bf16 hi/lo activations of the tensor-core path and their tensor maps
+  TcPair x64, f64, a128, pf16, a512, u512;                 // .map_* = MA view (128-row boxes)
+  CUtensorMap a128_nb[2], pf_nb[2], a512_nb[2], u_nb[2][2];  // NB views (256-row boxes): [hi, lo]
   size_t ws_bytes = 0;
   // staging for catre_refine_host
   float *st_pcl = nullptr, *st_prior = nullptr, *st_pose = nullptr, *st_scale = nullptr, *st_K = nullptr;
@@ -229,6 +234,62 @@ int fill_i32(catre_engine* e, cudaStream_t s, int* p, long long n, int v) {
 
 const float* W(catre_engine* e, const char* name) { return e->dw.at(name); }
 
+// ---- tensor-core launch helpers ------------------------------------------------------------------
+template <int ORIENT, int EPI, int BN>
+int tc_run(catre_engine* e, cudaStream_t s, int grp, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo,
+           const CUtensorMap& nb_hi, const CUtensorMap& nb_lo, const TcGemmP& p) {
+  cudaError_t st;
+  {
+    Launch l(e, s, grp);
+    if (e->cfg.precision == CATRE_PREC_BF16) st = tc_launch<ORIENT, EPI, BN, 1>(ma_hi, ma_lo, nb_hi, nb_lo, p, e->num_sms, s);
+    else st = tc_launch<ORIENT, EPI, BN, 3>(ma_hi, ma_lo, nb_hi, nb_lo, p, e->num_sms, s);
+  }
+  if (st != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e, CATRE_ERR_CUDA, "launch of tc %s failed: %s", kGrpNames[grp], cudaGetErrorString(st));
+  }
+  return 0;
+}
+
+// point-wise layer, points on TMEM lanes: act [R,K] (hi/lo) x W [C,K] -> relu(. + bias) re-split to bf16 hi/lo [R,C]
+template <int BN>
+int tc_split_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& act, const TcPair& w, int K, int C,
+                   const float* bias, const TcPair& out, long long R) {
+  TcGemmP p{};
+  p.K = K; p.m_tiles = (int)(R / 128); p.n_tiles = C / BN;
+  p.bias = bias; p.relu = 1; p.out_hi = out.hi; p.out_lo = out.lo; p.ldo16 = C;
+  return tc_run<PT_ON_LANES, EPI_SPLIT, BN>(e, s, grp, act.map_hi, act.map_lo, w.map_hi, w.map_lo, p);
+}
+
+// point-wise layer + column max over the points of each set, channels on TMEM lanes
+int tc_max_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& w, const CUtensorMap* act_nb, int K, int C,
+                 const float* bias, int relu, int* gmax, long long R) {
+  TcGemmP p{};
+  p.K = K; p.m_tiles = C / 128; p.n_tiles = (int)(R / 256);
+  p.bias = bias; p.relu = relu; p.gmax = gmax; p.C = C; p.rows_per_set = e->N;
+  return tc_run<CH_ON_LANES, EPI_MAX, 256>(e, s, grp, w.map_hi, w.map_lo, act_nb[0], act_nb[1], p);
+}
+
+int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv, float* out32, long long R) {
+  std::string c(conv);
+  {
+    Launch l(e, s, G_FRONT3);
+    front3_split_kernel<<<(unsigned)((R * 8 + 255) / 256), 256, 0, s>>>(e->q, t3, e->dw.at(c + ".weight"), e->dw.at(c + ".bias"),
+                                                                       out32, e->x64.hi, e->x64.lo, R, e->N);
+  }
+  return check_launch(e, "front3_split");
+}
+
+int tc_split_f32(catre_engine* e, cudaStream_t s, const float* src, const TcPair& out, long long n, const float* gn_scale,
+                 const float* gn_shift, int ld, int rows_per_obj) {
+  long long n8 = n / 8;
+  {
+    Launch l(e, s, G_SPLIT);
+    split_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(src, out.hi, out.lo, n8, gn_scale, gn_shift, ld, rows_per_obj);
+  }
+  return check_launch(e, "split");
+}
+
 // T-Net FC chain: keys [S,1024] -> 512 -> 256 -> kk  (pointnets/pointnet.py:32-40, 66-77)
 int tnet_fc(catre_engine* e, cudaStream_t s, const int* keys, int S, const char* prefix, const float* fc3_bias_I,
             int kk, float* out) {
@@ -268,7 +329,9 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   }
   if ((rc = check_launch(e, "front3"))) return rc;
   if (tc) {
-    if ((rc = tc_tnet_trunk(e->tcw, e->tcws, s, e->h64a, /*fstn=*/false, R, N, e->gmax_stn, e))) return rc;
+    if ((rc = tc_front(e, s, nullptr, "pcl_net.stn.conv1", nullptr, R))) return rc;
+    if ((rc = tc_split_layer<128>(e, s, G_STN_CONV2, e->x64, e->tw_stn_c2, 64, 128, W(e, "pcl_net.stn.conv2.bias"), e->a128, R))) return rc;
+    if ((rc = tc_max_layer(e, s, G_STN_CONV3_MAX, e->tw_stn_c3, e->a128_nb, 128, 1024, W(e, "pcl_net.stn.conv3.bias"), 1, e->gmax_stn, R))) return rc;
   } else {
     GemmP p = gemm_args(e->h64a, 64, W(e, "pcl_net.stn.conv2.weight"), 64, 128, W(e, "pcl_net.stn.conv2.bias"), e->h128,
                         128, R, 1);
@@ -281,7 +344,9 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   if ((rc = tnet_fc(e, s, e->gmax_stn, S, "pcl_net.stn", e->stn_fc3_bI, 9, e->t3))) return rc;
 
   // ---- E2: input transform + conv1 (pointnet.py:97-103)
-  {
+  if (tc) {
+    if ((rc = tc_front(e, s, e->t3, "pcl_net.conv1", e->h64a, R))) return rc;
+  } else {
     Launch l(e, s, G_FRONT3);
     front3_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(e->q, e->t3, W(e, "pcl_net.conv1.weight"),
                                                                   W(e, "pcl_net.conv1.bias"), e->h64a, R, N);
@@ -290,7 +355,9 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
 
   // ---- E3: STNkd (pointnet.py:57-78)
   if (tc) {
-    if ((rc = tc_tnet_trunk(e->tcw, e->tcws, s, e->h64a, /*fstn=*/true, R, N, e->gmax_fstn, e))) return rc;
+    if ((rc = tc_split_layer<64>(e, s, G_FSTN_CONV1, e->x64, e->tw_fstn_c1, 64, 64, W(e, "pcl_net.fstn.conv1.bias"), e->f64, R))) return rc;
+    if ((rc = tc_split_layer<128>(e, s, G_FSTN_CONV2, e->f64, e->tw_fstn_c2, 64, 128, W(e, "pcl_net.fstn.conv2.bias"), e->a128, R))) return rc;
+    if ((rc = tc_max_layer(e, s, G_FSTN_CONV3_MAX, e->tw_fstn_c3, e->a128_nb, 128, 1024, W(e, "pcl_net.fstn.conv3.bias"), 1, e->gmax_fstn, R))) return rc;
   } else {
     GemmP p = gemm_args(e->h64a, 64, W(e, "pcl_net.fstn.conv1.weight"), 64, 64, W(e, "pcl_net.fstn.conv1.bias"), e->h64b,
                         64, R, 1);
@@ -313,7 +380,10 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = run_gemm<64, A_PLAIN>(e, s, G_FEAT_TRANSFORM, p))) return rc;
   }
   if (tc) {
-    if ((rc = tc_trunk(e->tcw, e->tcws, s, e->h64b, R, N, e->gmax_g, e))) return rc;
+    if ((rc = tc_split_f32(e, s, e->h64b, e->pf16, R * 64, nullptr, nullptr, 64, 1))) return rc;
+    if ((rc = tc_split_layer<128>(e, s, G_CONV2, e->pf16, e->tw_conv2, 64, 128, W(e, "pcl_net.conv2.bias"), e->a128, R))) return rc;
+    if ((rc = tc_split_layer<256>(e, s, G_CONV3, e->a128, e->tw_conv3, 128, 512, W(e, "pcl_net.conv3.bias"), e->a512, R))) return rc;
+    if ((rc = tc_max_layer(e, s, G_CONV4_MAX, e->tw_conv4, e->a512_nb, 512, 1024, W(e, "pcl_net.conv4.bias"), 0, e->gmax_g, R))) return rc;
   } else {
     GemmP p = gemm_args(e->h64b, 64, W(e, "pcl_net.conv2.weight"), 64, 128, W(e, "pcl_net.conv2.bias"), e->h128, 128, R, 1);
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV2, p))) return rc;
@@ -330,9 +400,28 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     GemmP p = gemm_args(reinterpret_cast<const float*>(e->gmax_g), 1024, e->rot_w0g, 1024, 512, e->rot_b0, e->cset, 512, S, 0);
     if ((rc = run_gemm<128, A_KEY>(e, s, G_ROT_GFEAT, p))) return rc;
   }
+  const int gn_tile = tc ? 256 : 128;  // rows per GroupNorm partial
   if (tc) {
-    if ((rc = tc_rot_layers(e->tcw, e->tcws, s, e->h64b, e->cset, R, N, e->a0, e->a1, e->stats0, e->stats1, e->gn0,
-                            e->rot_gn0_g, e->rot_gn0_b, B, e))) return rc;
+    TcGemmP p{};
+    p.K = 64; p.m_tiles = 4; p.n_tiles = (int)(R / 256);
+    p.rowvec = e->cset; p.ldrv = 512; p.rows_per_set = N; p.out = e->a0; p.ldo = 512;
+    p.stats = e->stats0; p.stats_ld = 64; p.stats_goff = 0;
+    if ((rc = tc_run<CH_ON_LANES, EPI_RAW_STATS, 256>(e, s, G_ROT_LAYER0, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->pf_nb[0], e->pf_nb[1], p))) return rc;
+    {
+      Launch l(e, s, G_GN_FINALIZE);
+      gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats0, e->rot_gn0_g, e->rot_gn0_b, e->gn0,
+                                                             e->gn0 + (size_t)e->maxB * 512, B, 512, P / 256, P);
+    }
+    if ((rc = check_launch(e, "gn_finalize"))) return rc;
+    if ((rc = tc_split_f32(e, s, e->a0, e->u512, R * 512, e->gn0, e->gn0 + (size_t)e->maxB * 512, 512, P))) return rc;
+    for (int h = 0; h < 2; ++h) {
+      TcGemmP p1{};
+      p1.K = 256; p1.m_tiles = 2; p1.n_tiles = (int)(R / 256);
+      p1.bias = e->rot_b1 + h * 256; p1.rows_per_set = N; p1.out = e->a1 + h * 256; p1.ldo = 512;
+      p1.stats = e->stats1; p1.stats_ld = 64; p1.stats_goff = 32 * h;
+      if ((rc = tc_run<CH_ON_LANES, EPI_RAW_STATS, 256>(e, s, G_ROT_LAYER1, e->tw_rot1[h].map_hi, e->tw_rot1[h].map_lo,
+                                                        e->u_nb[h][0], e->u_nb[h][1], p1))) return rc;
+    }
   } else {
     GemmP p = gemm_args(e->h64b, 64, e->rot_w0p, 64, 512, nullptr, e->a0, 512, R, 0);
     p.rowvec = e->cset; p.ldrv = 512; p.rows_per_set = N; p.rows_per_obj = P;
@@ -356,7 +445,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   {
     Launch l(e, s, G_GN_FINALIZE);
     gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats1, e->rot_gn1_g, e->rot_gn1_b, e->gn1,
-                                                           e->gn1 + (size_t)e->maxB * 512, B, 512, P / 128, P);
+                                                           e->gn1 + (size_t)e->maxB * 512, B, 512, P / gn_tile, P);
   }
   if ((rc = check_launch(e, "gn_finalize"))) return rc;
   {
@@ -466,10 +555,26 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   rc |= dalloc(e, &e->st_K, B * 9);
   rc |= dalloc(e, &e->st_oposes, B * 12 * (catre_engine::kMaxHostIter + 1));
   rc |= dalloc(e, &e->st_oscales, B * 3 * (catre_engine::kMaxHostIter + 1));
+  e->num_sms = prop.multiProcessorCount;
   if (!rc && tc) {
-    size_t bytes = 0;
-    rc = tc_workspace_alloc(e->tcws, R, e->dev_allocs, &bytes, e);
-    e->ws_bytes += bytes;
+    auto pair = [&](TcPair& t, size_t cols) {
+      rc |= dalloc(e, &t.hi, R * cols);
+      rc |= dalloc(e, &t.lo, R * cols);
+      if (rc) return;
+      if (!tc_make_map(&t.map_hi, t.hi, R, cols, cols, 128) || !tc_make_map(&t.map_lo, t.lo, R, cols, cols, 128)) rc |= 2;
+    };
+    pair(e->x64, 64); pair(e->f64, 64); pair(e->a128, 128); pair(e->pf16, 64); pair(e->a512, 512); pair(e->u512, 512);
+    if (!rc) {
+      bool ok = true;
+      ok &= tc_make_map(&e->a128_nb[0], e->a128.hi, R, 128, 128, 256) && tc_make_map(&e->a128_nb[1], e->a128.lo, R, 128, 128, 256);
+      ok &= tc_make_map(&e->pf_nb[0], e->pf16.hi, R, 64, 64, 256) && tc_make_map(&e->pf_nb[1], e->pf16.lo, R, 64, 64, 256);
+      ok &= tc_make_map(&e->a512_nb[0], e->a512.hi, R, 512, 512, 256) && tc_make_map(&e->a512_nb[1], e->a512.lo, R, 512, 512, 256);
+      for (int h = 0; h < 2; ++h)
+        ok &= tc_make_map(&e->u_nb[h][0], e->u512.hi + h * 256, R, 256, 512, 256) &&
+              tc_make_map(&e->u_nb[h][1], e->u512.lo + h * 256, R, 256, 512, 256);
+      if (!ok) rc |= 2;
+    }
+    if (rc & 2) e->err = "cuTensorMapEncodeTiled failed for an activation buffer";
   }
   if (rc) {
     g_create_error = e->err;
@@ -574,8 +679,35 @@ int catre_pack(catre_engine* e, void* stream) {
   if (rc) return fail(e, CATRE_ERR_CUDA, "uploading packed weights failed: %s", cudaGetErrorString(cudaGetLastError()));
 
   if (e->cfg.precision != CATRE_PREC_FP32_SIMT) {
-    rc = tc_pack_weights(e->tcw, e->hw, w0p, e->cfg.precision == CATRE_PREC_BF16, e->dev_allocs, e);
-    if (rc) return rc;
+    // bf16 hi/lo split of the wide layers' weights [C, K] + tensor maps (box rows = how the layer uses W)
+    auto wpair = [&](TcPair& t, const std::vector<float>& w, int C, int K, int box_rows) -> int {
+      std::vector<__nv_bfloat16> hi((size_t)C * K), lo((size_t)C * K);
+      for (size_t i = 0; i < hi.size(); ++i) {
+        hi[i] = __float2bfloat16_rn(w[i]);
+        lo[i] = __float2bfloat16_rn(w[i] - __bfloat162float(hi[i]));
+      }
+      if (!t.hi) {
+        if (dalloc(e, &t.hi, hi.size()) || dalloc(e, &t.lo, lo.size())) return CATRE_ERR_CUDA;
+      }
+      CU_TRY(e, cudaMemcpy(t.hi, hi.data(), hi.size() * 2, cudaMemcpyHostToDevice));
+      CU_TRY(e, cudaMemcpy(t.lo, lo.data(), lo.size() * 2, cudaMemcpyHostToDevice));
+      if (!tc_make_map(&t.map_hi, t.hi, C, K, K, box_rows) || !tc_make_map(&t.map_lo, t.lo, C, K, K, box_rows))
+        return fail(e, CATRE_ERR_CUDA, "cuTensorMapEncodeTiled failed for a %dx%d weight", C, K);
+      return 0;
+    };
+    int r2 = 0;
+    r2 = r2 ? r2 : wpair(e->tw_stn_c2, H("pcl_net.stn.conv2.weight"), 128, 64, 128);
+    r2 = r2 ? r2 : wpair(e->tw_stn_c3, H("pcl_net.stn.conv3.weight"), 1024, 128, 128);
+    r2 = r2 ? r2 : wpair(e->tw_fstn_c1, H("pcl_net.fstn.conv1.weight"), 64, 64, 64);
+    r2 = r2 ? r2 : wpair(e->tw_fstn_c2, H("pcl_net.fstn.conv2.weight"), 128, 64, 128);
+    r2 = r2 ? r2 : wpair(e->tw_fstn_c3, H("pcl_net.fstn.conv3.weight"), 1024, 128, 128);
+    r2 = r2 ? r2 : wpair(e->tw_conv2, H("pcl_net.conv2.weight"), 128, 64, 128);
+    r2 = r2 ? r2 : wpair(e->tw_conv3, H("pcl_net.conv3.weight"), 512, 128, 256);
+    r2 = r2 ? r2 : wpair(e->tw_conv4, H("pcl_net.conv4.weight"), 1024, 512, 128);
+    r2 = r2 ? r2 : wpair(e->tw_rot0, w0p, 512, 64, 128);
+    r2 = r2 ? r2 : wpair(e->tw_rot1[0], H("rot_head.rot_head_x.layers.3.weight"), 256, 256, 128);
+    r2 = r2 ? r2 : wpair(e->tw_rot1[1], H("rot_head.rot_head_y.layers.3.weight"), 256, 256, 128);
+    if (r2) return r2;
   }
   CU_TRY(e, cudaDeviceSynchronize());
   e->packed = true;
@@ -690,7 +822,9 @@ int catre_debug_read(catre_engine* e, const char* name, void* dst_host, size_t b
       {"gmax_stn", e->gmax_stn}, {"gmax_fstn", e->gmax_fstn}, {"gmax_g", e->gmax_g}, {"gmax_pf", e->gmax_pf},
       {"fc512", e->fc512}, {"fc256", e->fc256}, {"t3", e->t3}, {"t64", e->t64}, {"cset", e->cset},
       {"stats0", e->stats0}, {"stats1", e->stats1}, {"gn0", e->gn0}, {"gn1", e->gn1}, {"rot_partial", e->rot_partial}};
-  tc_debug_buffers(e->tcws, m);
+  m["x64_hi"] = e->x64.hi; m["x64_lo"] = e->x64.lo; m["f64_hi"] = e->f64.hi; m["f64_lo"] = e->f64.lo;
+  m["a128_hi"] = e->a128.hi; m["a128_lo"] = e->a128.lo; m["pf_hi"] = e->pf16.hi; m["pf_lo"] = e->pf16.lo;
+  m["a512_hi"] = e->a512.hi; m["a512_lo"] = e->a512.lo; m["u_hi"] = e->u512.hi; m["u_lo"] = e->u512.lo;
   auto it = m.find(name);
   if (it == m.end() || it->second == nullptr) return fail(e, CATRE_ERR_INVALID_ARG, "no debug buffer '%s'", name);
   CU_TRY(e, cudaDeviceSynchronize());

@@ -1,20 +1,484 @@
-// placeholder: tensor-core path (filled in below)
+// Tensor-core path (sm_100a): tcgen05.mma kind::f16 with bf16 hi/lo split operands ("bf16x3": three
+// products hi*hi + hi*lo + lo*hi accumulated in fp32 in TMEM), operands staged HBM/L2 -> shared memory by
+// TMA (cp.async.bulk.tensor, 128B swizzle), mbarrier producer/consumer pipeline, warp-specialised:
+//   warp 0 : TMA producer          warp 1 : TMEM allocator + MMA issuer (one elected thread)
+//   warps 2-5 : epilogue (tcgen05.ld -> registers -> fused bias/ReLU + column-max | GroupNorm partials |
+//               bf16 hi/lo re-split for the next layer)
+// One persistent CTA per SM loops over output tiles; the fp32 accumulator is double-buffered in TMEM so
+// the epilogue of tile i overlaps the MMAs of tile i+1.
+//
+// Every wide point-wise layer of the CATRE encoder/rot-head is a GEMM  D = W . A^T  over K = C_in with
+// both operands K-major; two orientations are used:
+//   CH_ON_LANES : M side (128 TMEM lanes) = output channels, N side (<=256 TMEM columns) = points.
+//                 A column max over points / GroupNorm sums over points are per-thread serial reductions.
+//   PT_ON_LANES : M side = points, N side = output channels.  Each thread owns one point's contiguous
+//                 channels, so the re-split bf16 activations are written with 16-byte vector stores.
 #pragma once
+#include <cuda.h>  // CUtensorMap (types only; cuTensorMapEncodeTiled is fetched through the runtime)
+#include <cuda_bf16.h>
 #include <cuda_runtime.h>
-#include <map>
-#include <string>
-#include <vector>
-struct catre_engine;
+#include <stdint.h>
+
+#include "simt_kernels.cuh"
+
 namespace catre {
-struct TcWeights {};
-struct TcWorkspace {};
-inline int tc_unsupported() { return -6; }
-inline void tc_debug_buffers(TcWorkspace&, std::map<std::string, const void*>&) {}
-inline int tc_workspace_alloc(TcWorkspace&, size_t, std::vector<void*>&, size_t*, catre_engine*) { return 0; }
-inline int tc_pack_weights(TcWeights&, const std::map<std::string, std::vector<float>>&, const std::vector<float>&, bool,
-                           std::vector<void*>&, catre_engine*) { return tc_unsupported(); }
-inline int tc_tnet_trunk(TcWeights&, TcWorkspace&, cudaStream_t, const float*, bool, long long, int, int*, catre_engine*) { return tc_unsupported(); }
-inline int tc_trunk(TcWeights&, TcWorkspace&, cudaStream_t, const float*, long long, int, int*, catre_engine*) { return tc_unsupported(); }
-inline int tc_rot_layers(TcWeights&, TcWorkspace&, cudaStream_t, const float*, const float*, long long, int, float*, float*,
-                         float*, float*, float*, const float*, const float*, int, catre_engine*) { return tc_unsupported(); }
+
+constexpr int TC_THREADS = 192;
+constexpr int TC_BK = 64;  // K slab = one 128-byte swizzle atom of bf16
+enum { CH_ON_LANES = 0, PT_ON_LANES = 1 };
+enum { EPI_MAX = 0, EPI_RAW_STATS = 1, EPI_SPLIT = 2 };
+
+// ------------------------------------------------------------------------------------------------
+// PTX wrappers
+// ------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint32_t bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+      "selp.u32 %0, 1, 0, p;\n\t}"
+      : "=r"(ok)
+      : "r"(bar), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+// Bounded wait: a pipeline bug must trap (launch error) instead of hanging the GPU.
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+  uint32_t spins = 0;
+  while (!mbar_try_wait(bar, parity)) {
+    if (++spins > (1u << 26)) __trap();
+  }
+}
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, int c0, int c1, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void prefetch_tmap(const CUtensorMap* map) {
+  asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tmem_alloc(uint32_t dst_smem, uint32_t ncols) {
+  asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(dst_smem), "r"(ncols) : "memory");
+  asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t taddr, uint32_t ncols) {
+  asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(taddr), "r"(ncols) : "memory");
+}
+// D[tmem] (+)= A[smem desc] . B[smem desc]^T, bf16 inputs, fp32 accumulate
+__device__ __forceinline__ void umma_bf16(uint32_t d_tmem, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// arrive on an mbarrier once all previously issued MMAs of this thread have completed
+__device__ __forceinline__ void umma_commit(uint32_t bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+        "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+        "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+
+// shared-memory matrix descriptor: K-major, 128B swizzle, rows 128 B apart, 8-row groups 1024 B apart
+// (cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48)=1 layout[61,64)=2)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((saddr & 0x3FFFFu) >> 4);
+  d |= (uint64_t)1 << 16;
+  d |= (uint64_t)(1024 >> 4) << 32;
+  d |= (uint64_t)1 << 46;
+  d |= (uint64_t)2 << 61;
+  return d;
+}
+// instruction descriptor kind::f16: D fp32 (bit 4), A/B bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
+__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
+  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+__device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// ------------------------------------------------------------------------------------------------
+// The GEMM kernel
+// ------------------------------------------------------------------------------------------------
+struct TcGemmP {
+  int K;                 // reduction length, multiple of 64
+  int m_tiles, n_tiles;  // tiles on the M side (128 rows each) / N side (BN rows each)
+  // epilogue
+  const float* bias;     // per output channel (or null)
+  int relu;
+  int* gmax; int C; int rows_per_set;           // EPI_MAX: keys [S, C]
+  float* out; int ldo;                          // EPI_RAW_STATS: fp32 [R, ldo]
+  const float* rowvec; int ldrv;                // EPI_RAW_STATS: per-set additive vector [S, ldrv]
+  float* stats; int stats_ld, stats_goff;       // EPI_RAW_STATS: [R/BN, stats_ld, 2]
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int ldo16;  // EPI_SPLIT: bf16 [R, ldo16]
+};
+
+template <int BN, int NPROD>
+struct TcCfg {
+  static constexpr int ARR = (NPROD == 3) ? 2 : 1;  // hi (+ lo) arrays per operand
+  static constexpr int MA_BYTES = 128 * 128;        // 128 rows x 64 bf16
+  static constexpr int NB_BYTES = BN * 128;
+  static constexpr int STAGE_BYTES = (MA_BYTES + NB_BYTES) * ARR;
+  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 4 ? 4 : (200 * 1024 / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;  // + barriers + 1024 B alignment slack
+};
+
+template <int ORIENT, int EPI, int BN, int NPROD>
+__global__ void __launch_bounds__(TC_THREADS, 1)
+tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant__ CUtensorMap ma_lo,
+               const __grid_constant__ CUtensorMap nb_hi, const __grid_constant__ CUtensorMap nb_lo, const TcGemmP p) {
+  using Cfg = TcCfg<BN, NPROD>;
+  constexpr int STAGES = Cfg::STAGES;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t tiles_base = (smem_base + 1024 + 1023) & ~1023u;  // barriers live in the first 1 KB
+  // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base pointer
+  const uint32_t bar_full = smem_base, bar_empty = smem_base + 8 * STAGES;
+  const uint32_t bar_tfull = smem_base + 16 * STAGES, bar_tempty = bar_tfull + 16;
+  const uint32_t tmem_slot = bar_tempty + 16;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int total_tiles = p.m_tiles * p.n_tiles;
+  const int k_slabs = p.K / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&ma_hi); prefetch_tmap(&nb_hi);
+    if (NPROD == 3) { prefetch_tmap(&ma_lo); prefetch_tmap(&nb_lo); }
+    for (int i = 0; i < STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  auto tile_coords = [&](int t, int& mi, int& ni) {
+    if (ORIENT == CH_ON_LANES) { mi = t % p.m_tiles; ni = t / p.m_tiles; }  // channel tile fastest
+    else { ni = t % p.n_tiles; mi = t / p.n_tiles; }
+  };
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        int mi, ni; tile_coords(t, mi, ni);
+        for (int ks = 0; ks < k_slabs; ++ks) {
+          mbar_wait(bar_empty + 8 * stage, phase ^ 1);
+          const uint32_t sb = tiles_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t full = bar_full + 8 * stage;
+          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          tma_load_2d(sb, &ma_hi, ks * TC_BK, mi * 128, full);
+          tma_load_2d(sb + Cfg::MA_BYTES * Cfg::ARR, &nb_hi, ks * TC_BK, ni * BN, full);
+          if (NPROD == 3) {
+            tma_load_2d(sb + Cfg::MA_BYTES, &ma_lo, ks * TC_BK, mi * 128, full);
+            tma_load_2d(sb + Cfg::MA_BYTES * 2 + Cfg::NB_BYTES, &nb_lo, ks * TC_BK, ni * BN, full);
+          }
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+        mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * BN);
+        for (int ks = 0; ks < k_slabs; ++ks) {
+          mbar_wait(bar_full + 8 * stage, phase);
+          tc_fence_after();
+          const uint32_t sb = tiles_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t a_hi = sb, a_lo = sb + Cfg::MA_BYTES;
+          const uint32_t b_hi = sb + Cfg::MA_BYTES * Cfg::ARR, b_lo = b_hi + Cfg::NB_BYTES;
+#pragma unroll
+          for (int kk = 0; kk < TC_BK / 16; ++kk) {
+            const uint32_t off = kk * 32;  // 16 bf16 = 32 bytes along K inside the swizzle atom
+            umma_bf16(d_tmem, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_hi + off), idesc, (ks | kk) != 0);
+            if (NPROD == 3) {
+              umma_bf16(d_tmem, umma_desc_sw128(a_hi + off), umma_desc_sw128(b_lo + off), idesc, 1);
+              umma_bf16(d_tmem, umma_desc_sw128(a_lo + off), umma_desc_sw128(b_hi + off), idesc, 1);
+            }
+          }
+          umma_commit(bar_empty + 8 * stage);  // frees the smem slot when these MMAs retire
+          if (++stage == STAGES) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(bar_tfull + 8 * acc);  // accumulator complete -> epilogue
+        if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+      }
+    }
+  } else {
+    // ===================== epilogue warps (TMEM lanes 32*(warp%4) ..) =====================
+    const int lane_row = (warp & 3) * 32 + lane;
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
+      int mi, ni; tile_coords(t, mi, ni);
+      mbar_wait(bar_tfull + 8 * acc, acc_phase);
+      tc_fence_after();
+      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * BN);
+      if (EPI == EPI_MAX) {
+        const int ch = mi * 128 + lane_row;
+        float m = -INFINITY;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 64) {
+          float v[64];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld32(taddr + c0 + 32, v + 32);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 64; ++j) m = fmaxf(m, v[j]);
+        }
+        if (p.bias) m += p.bias[ch];
+        if (p.relu) m = fmaxf(m, 0.f);
+        const int set = (ni * BN) / p.rows_per_set;
+        atomicMax(p.gmax + (long long)set * p.C + ch, f2key(m));
+      } else if (EPI == EPI_RAW_STATS) {
+        const int ch = mi * 128 + lane_row;
+        const long long p0 = (long long)ni * BN;
+        const int set = (int)(p0 / p.rows_per_set);
+        float add = p.bias ? p.bias[ch] : 0.f;
+        if (p.rowvec) add += p.rowvec[(long long)set * p.ldrv + ch];
+        float s = 0.f, ss = 0.f;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+#pragma unroll
+          for (int j = 0; j < 32; ++j) {
+            float x = v[j] + add;
+            p.out[(p0 + c0 + j) * p.ldo + ch] = x;  // 32 lanes -> 32 consecutive channels: 128 B
+            s += x;
+            ss = fmaf(x, x, ss);
+          }
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+        if ((lane & 7) == 0) {
+          long long o = ((long long)ni * p.stats_ld + p.stats_goff + (ch >> 3)) * 2;
+          p.stats[o] = s;
+          p.stats[o + 1] = ss;
+        }
+      } else {  // EPI_SPLIT: lane = point row, columns = channels
+        const long long row = (long long)mi * 128 + lane_row;
+        const int n0 = ni * BN;
+#pragma unroll 1
+        for (int c0 = 0; c0 < BN; c0 += 32) {
+          float v[32];
+          tmem_ld32(taddr + c0, v);
+          tmem_ld_wait();
+          uint32_t hi[16], lo[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            float x0 = v[j] + __ldg(p.bias + n0 + c0 + j);
+            float x1 = v[j + 1] + __ldg(p.bias + n0 + c0 + j + 1);
+            if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
+            __nv_bfloat16 h0, l0, h1, l1;
+            split_bf16(x0, h0, l0);
+            split_bf16(x1, h1, l1);
+            hi[j >> 1] = pack_bf16(h0, h1);
+            lo[j >> 1] = pack_bf16(l0, l1);
+          }
+          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row * p.ldo16 + n0 + c0);
+#pragma unroll
+          for (int q = 0; q < 4; ++q) dh[q] = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+          if (NPROD == 3) {
+            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row * p.ldo16 + n0 + c0);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+          }
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
+      if (++acc == 2) { acc = 0; acc_phase ^= 1; }
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// element-wise helpers of the tensor-core path
+// ------------------------------------------------------------------------------------------------
+
+// front layer (see front3_kernel) writing the bf16 hi/lo split (and optionally fp32) of the 64 channels
+__global__ void front3_split_kernel(const float* __restrict__ q, const float* __restrict__ t3, const float* __restrict__ W,
+                                    const float* __restrict__ bias, float* __restrict__ out32 /*or null*/,
+                                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long R, int N) {
+  __shared__ float sW[64 * 3];
+  __shared__ float sB[64];
+  for (int i = threadIdx.x; i < 192; i += blockDim.x) sW[i] = W[i];
+  for (int i = threadIdx.x; i < 64; i += blockDim.x) sB[i] = bias[i];
+  __syncthreads();
+  long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  long long r = gid >> 3;  // 8 threads per point, 8 channels each
+  int cg = (int)(gid & 7);
+  if (r >= R) return;
+  float x0 = q[r * 3 + 0], x1 = q[r * 3 + 1], x2 = q[r * 3 + 2];
+  if (t3 != nullptr) {
+    const float* T = t3 + (r / N) * 9;
+    float y0 = x0 * T[0] + x1 * T[3] + x2 * T[6];
+    float y1 = x0 * T[1] + x1 * T[4] + x2 * T[7];
+    float y2 = x0 * T[2] + x1 * T[5] + x2 * T[8];
+    x0 = y0; x1 = y1; x2 = y2;
+  }
+  float v[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int c = cg * 8 + j;
+    v[j] = fmaxf(sB[c] + sW[c * 3 + 0] * x0 + sW[c * 3 + 1] * x1 + sW[c * 3 + 2] * x2, 0.0f);
+  }
+  if (out32) {
+    *reinterpret_cast<float4*>(out32 + r * 64 + cg * 8) = make_float4(v[0], v[1], v[2], v[3]);
+    *reinterpret_cast<float4*>(out32 + r * 64 + cg * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[j], h0, l0);
+    split_bf16(v[j + 1], h1, l1);
+    hi[j >> 1] = pack_bf16(h0, h1);
+    lo[j >> 1] = pack_bf16(l0, l1);
+  }
+  *reinterpret_cast<uint4*>(out_hi + r * 64 + cg * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(out_lo + r * 64 + cg * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// fp32 [n] -> bf16 hi/lo [n] (n multiple of 8), optionally through GroupNorm affine + GELU:
+//   x' = gelu(x * scale[obj, c] + shift[obj, c]),  obj = row / rows_per_obj, c = column (ld columns per row)
+__global__ void split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                             long long n8, const float* __restrict__ gn_scale, const float* __restrict__ gn_shift, int ld,
+                             int rows_per_obj) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n8) return;
+  const float4 a = *reinterpret_cast<const float4*>(src + i * 8);
+  const float4 b = *reinterpret_cast<const float4*>(src + i * 8 + 4);
+  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+  if (gn_scale) {
+    long long e0 = i * 8;
+    long long row = e0 / ld;
+    int c = (int)(e0 % ld);
+    long long obj = row / rows_per_obj;
+    const float* sc = gn_scale + obj * ld + c;
+    const float* sh = gn_shift + obj * ld + c;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) v[j] = gelu_exact(v[j] * sc[j] + sh[j]);
+  }
+  uint32_t hi[4], lo[4];
+#pragma unroll
+  for (int j = 0; j < 8; j += 2) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(v[j], h0, l0);
+    split_bf16(v[j + 1], h1, l1);
+    hi[j >> 1] = pack_bf16(h0, h1);
+    lo[j >> 1] = pack_bf16(l0, l1);
+  }
+  *reinterpret_cast<uint4*>(out_hi + i * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+  *reinterpret_cast<uint4*>(out_lo + i * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+}
+
+// ------------------------------------------------------------------------------------------------
+// host side: tensor maps and launch
+// ------------------------------------------------------------------------------------------------
+struct TcPair {  // hi/lo bf16 arrays [rows, ld] and their tensor maps (box = 64 x box_rows, 128B swizzle)
+  __nv_bfloat16* hi = nullptr;
+  __nv_bfloat16* lo = nullptr;
+  CUtensorMap map_hi, map_lo;
+};
+
+typedef CUresult (*PFN_encodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                    const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                    CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+inline PFN_encodeTiled tc_encode_fn() {
+  static PFN_encodeTiled fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult qres;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &qres) == cudaSuccess &&
+        qres == cudaDriverEntryPointSuccess)
+      fn = reinterpret_cast<PFN_encodeTiled>(p);
+  }
+  return fn;
+}
+
+// bf16 [rows, kext] view with row pitch ld (elements); returns false on failure
+inline bool tc_make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_t kext, uint64_t ld, uint32_t box_rows) {
+  PFN_encodeTiled fn = tc_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {kext, rows};
+  cuuint64_t gstride[1] = {ld * 2};
+  cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+template <int ORIENT, int EPI, int BN, int NPROD>
+cudaError_t tc_launch(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& nb_hi, const CUtensorMap& nb_lo,
+                      const TcGemmP& p, int num_sms, cudaStream_t s) {
+  using Cfg = TcCfg<BN, NPROD>;
+  auto kern = tc_gemm_kernel<ORIENT, EPI, BN, NPROD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (st != cudaSuccess) return st;
+    configured = true;
+  }
+  int tiles = p.m_tiles * p.n_tiles;
+  int grid = tiles < num_sms ? tiles : num_sms;
+  if (grid < 1) return cudaSuccess;
+  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, nb_hi, nb_lo, p);
+  return cudaPeekAtLastError();
+}
+
 }  // namespace catre
