@@ -72,12 +72,12 @@ constexpr int kNumWeights = sizeof(kWeights) / sizeof(kWeights[0]);
 enum Grp {
   G_FILL, G_UPDATE_POINTS, G_FRONT3, G_STN_CONV2, G_STN_CONV3_MAX, G_TNET_FC, G_FSTN_CONV1, G_FSTN_CONV2,
   G_FSTN_CONV3_MAX, G_FEAT_TRANSFORM, G_CONV2, G_CONV3, G_CONV4_MAX, G_ROT_GFEAT, G_ROT_LAYER0, G_GN_FINALIZE,
-  G_ROT_LAYER1, G_ROT_TAIL, G_TS_POSE, G_SPLIT, G_NUM
+  G_ROT_LAYER1, G_ROT_TAIL, G_TS_POSE, G_SPLIT, G_SUM_PARTS, G_ROT_LAYER0_APPLY, G_NUM
 };
 const char* kGrpNames[G_NUM] = {
     "fill", "update_points", "front3", "stn_conv2", "stn_conv3_max", "tnet_fc", "fstn_conv1", "fstn_conv2",
     "fstn_conv3_max", "feat_transform", "conv2", "conv3", "conv4_max", "rot_gfeat", "rot_layer0", "gn_finalize",
-    "rot_layer1", "rot_tail", "ts_pose", "split_bf16"};
+    "rot_layer1", "rot_tail", "ts_pose", "split_bf16", "sum_parts", "rot_layer0_apply"};
 
 }  // namespace
 
@@ -100,12 +100,15 @@ struct catre_engine {
   // bf16 hi/lo weight copies + tensor maps (tensor-core modes); "MA" maps have 128-row boxes (M side of
   // the MMA), "NB" maps have BN-row boxes (N side)
   TcPair tw_stn_c2, tw_stn_c3, tw_fstn_c1, tw_fstn_c2, tw_fstn_c3, tw_conv2, tw_conv3, tw_conv4, tw_rot0, tw_rot1[2];
+  CUtensorMap tw_rot0_nb[2];  // rot layer-0 point-feature weights [512, 64] as an N-side operand (256-row boxes)
+  float *fstn_fc3_wT = nullptr;  // fstn.fc3 rows permuted so the FC emits T64^T (row j = output channel j of pf = h1 . T64)
   int num_sms = 148;
 
   // ---- workspace
   float *q = nullptr, *h64a = nullptr, *h64b = nullptr, *h128 = nullptr, *h512 = nullptr, *a0 = nullptr, *a1 = nullptr;
   int *gmax_all = nullptr, *gmax_stn = nullptr, *gmax_fstn = nullptr, *gmax_g = nullptr, *gmax_pf = nullptr;
-  float *fc512 = nullptr, *fc256 = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
+  float *fc512 = nullptr, *fc256 = nullptr, *fc3p = nullptr, *csetp = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
+  TcPair t64s;  // tensor-core modes: bf16 hi/lo of T64^T, [S*64, 64]
   float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
   // bf16 hi/lo activations of the tensor-core path and their tensor maps
   TcPair x64, f64, a128, pf16, a512, u512;                 // .map_* = MA view (128-row boxes)
@@ -208,12 +211,13 @@ GemmP gemm_args(const float* A, int lda, const float* W, int K, int C, const flo
   p.stats_ld = 0; p.stats_goff = 0;
   p.gn_scale = p.gn_shift = nullptr; p.ldgn = 0;
   p.R = (int)R; p.C = C; p.K = K; p.rows_per_set = 1; p.rows_per_obj = 1; p.relu = relu;
+  p.ksplit = 1; p.part_stride = 0; p.a_bias = nullptr; p.a_nparts = 0; p.a_part_stride = 0; p.a_relu = 0;
   return p;
 }
 
 template <int BN, int AMODE>
 int run_gemm(catre_engine* e, cudaStream_t s, int grp, const GemmP& p) {
-  dim3 grid((p.C + BN - 1) / BN, (p.R + 127) / 128);
+  dim3 grid((p.C + BN - 1) / BN, (p.R + 127) / 128, p.ksplit > 1 ? p.ksplit : 1);
   {
     Launch l(e, s, grp);
     pw_gemm_kernel<BN, AMODE><<<grid, 256, 0, s>>>(p);
@@ -233,6 +237,23 @@ int fill_i32(catre_engine* e, cudaStream_t s, int* p, long long n, int v) {
 }
 
 const float* W(catre_engine* e, const char* name) { return e->dw.at(name); }
+
+// out[r, c] = act(sum of split-K partials + bias[c]); optional bf16 hi/lo copy (tensor-core operand)
+int sum_parts(catre_engine* e, cudaStream_t s, const float* parts, int nparts, long long R, int C, const float* bias,
+              int relu, float* out32, const TcPair* out16) {
+  const long long n = R * C;
+  {
+    Launch l(e, s, G_SUM_PARTS);
+    if (C % 4 == 0) {
+      sum_parts_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(
+          parts, nparts, n, bias, C, relu, out32, out16 ? reinterpret_cast<unsigned short*>(out16->hi) : nullptr,
+          out16 ? reinterpret_cast<unsigned short*>(out16->lo) : nullptr, n / 4);
+    } else {
+      sum_parts_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(parts, nparts, n, bias, C, relu, out32, n);
+    }
+  }
+  return check_launch(e, "sum_parts");
+}
 
 // ---- tensor-core launch helpers ------------------------------------------------------------------
 template <int ORIENT, int EPI, int BN>
@@ -256,7 +277,7 @@ template <int BN>
 int tc_split_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& act, const TcPair& w, int K, int C,
                    const float* bias, const TcPair& out, long long R) {
   TcGemmP p{};
-  p.K = K; p.m_tiles = (int)(R / 128); p.n_tiles = C / BN;
+  p.K = K; p.m_tiles = (int)(R / 128); p.n_tiles = C / BN; p.rows_per_set = e->N;
   p.bias = bias; p.relu = 1; p.out_hi = out.hi; p.out_lo = out.lo; p.ldo16 = C;
   return tc_run<PT_ON_LANES, EPI_SPLIT, BN>(e, s, grp, act.map_hi, act.map_lo, w.map_hi, w.map_lo, p);
 }
@@ -270,40 +291,39 @@ int tc_max_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& w, cons
   return tc_run<CH_ON_LANES, EPI_MAX, 256>(e, s, grp, w.map_hi, w.map_lo, act_nb[0], act_nb[1], p);
 }
 
-int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv, float* out32, long long R) {
+int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv, long long R) {
   std::string c(conv);
   {
     Launch l(e, s, G_FRONT3);
     front3_split_kernel<<<(unsigned)((R * 8 + 255) / 256), 256, 0, s>>>(e->q, t3, e->dw.at(c + ".weight"), e->dw.at(c + ".bias"),
-                                                                       out32, e->x64.hi, e->x64.lo, R, e->N);
+                                                                       nullptr, e->x64.hi, e->x64.lo, R, e->N);
   }
   return check_launch(e, "front3_split");
 }
 
-int tc_split_f32(catre_engine* e, cudaStream_t s, const float* src, const TcPair& out, long long n, const float* gn_scale,
-                 const float* gn_shift, int ld, int rows_per_obj) {
-  long long n8 = n / 8;
-  {
-    Launch l(e, s, G_SPLIT);
-    split_kernel<<<(unsigned)((n8 + 255) / 256), 256, 0, s>>>(src, out.hi, out.lo, n8, gn_scale, gn_shift, ld, rows_per_obj);
-  }
-  return check_launch(e, "split");
-}
+// T-Net FC chain: keys [S,1024] -> 512 -> 256 -> kk  (pointnets/pointnet.py:32-40, 66-77).  M = S is
+// small, so every layer is split-K over many CTAs; partials are summed (fixed order) by the consumer.
+constexpr int KS_FC1 = 16, KS_FC2 = 8, KS_FC3 = 4;
 
-// T-Net FC chain: keys [S,1024] -> 512 -> 256 -> kk  (pointnets/pointnet.py:32-40, 66-77)
-int tnet_fc(catre_engine* e, cudaStream_t s, const int* keys, int S, const char* prefix, const float* fc3_bias_I,
-            int kk, float* out) {
+int tnet_fc(catre_engine* e, cudaStream_t s, const int* keys, int S, const char* prefix, const float* fc3_w,
+            const float* fc3_bias_I, int kk, float* out32, const TcPair* out16) {
   std::string pf(prefix);
   int rc;
-  GemmP p = gemm_args(reinterpret_cast<const float*>(keys), 1024, W(e, (pf + ".fc1.weight").c_str()), 1024, 512,
-                      W(e, (pf + ".fc1.bias").c_str()), e->fc512, 512, S, 1);
-  if ((rc = run_gemm<128, A_KEY>(e, s, G_TNET_FC, p))) return rc;
-  p = gemm_args(e->fc512, 512, W(e, (pf + ".fc2.weight").c_str()), 512, 256, W(e, (pf + ".fc2.bias").c_str()), e->fc256,
-                256, S, 1);
-  if ((rc = run_gemm<128, A_PLAIN>(e, s, G_TNET_FC, p))) return rc;
-  p = gemm_args(e->fc256, 256, W(e, (pf + ".fc3.weight").c_str()), 256, kk, fc3_bias_I, out, kk, S, 0);
-  if (kk <= 64) return run_gemm<64, A_PLAIN>(e, s, G_TNET_FC, p);
-  return run_gemm<128, A_PLAIN>(e, s, G_TNET_FC, p);
+  GemmP p = gemm_args(reinterpret_cast<const float*>(keys), 1024, W(e, (pf + ".fc1.weight").c_str()), 1024, 512, nullptr,
+                      e->fc512, 512, S, 0);
+  p.ksplit = KS_FC1; p.part_stride = (long long)S * 512;
+  if ((rc = run_gemm<64, A_KEY>(e, s, G_TNET_FC, p))) return rc;
+  p = gemm_args(e->fc512, 512, W(e, (pf + ".fc2.weight").c_str()), 512, 256, nullptr, e->fc256, 256, S, 0);
+  p.a_bias = W(e, (pf + ".fc1.bias").c_str()); p.a_nparts = KS_FC1; p.a_part_stride = (long long)S * 512; p.a_relu = 1;
+  p.ksplit = KS_FC2; p.part_stride = (long long)S * 256;
+  if ((rc = run_gemm<64, A_PARTIAL>(e, s, G_TNET_FC, p))) return rc;
+  p = gemm_args(e->fc256, 256, fc3_w, 256, kk, nullptr, e->fc3p, kk, S, 0);
+  p.a_bias = W(e, (pf + ".fc2.bias").c_str()); p.a_nparts = KS_FC2; p.a_part_stride = (long long)S * 256; p.a_relu = 1;
+  p.ksplit = KS_FC3; p.part_stride = (long long)S * kk;
+  if (kk <= 64) rc = run_gemm<64, A_PARTIAL>(e, s, G_TNET_FC, p);
+  else rc = run_gemm<128, A_PARTIAL>(e, s, G_TNET_FC, p);
+  if (rc) return rc;
+  return sum_parts(e, s, e->fc3p, KS_FC3, S, kk, fc3_bias_I, 0, out32, out16);
 }
 
 // One refinement iteration on a chunk of B objects whose points are already in e->q.
@@ -322,17 +342,17 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   if ((rc = fill_i32(e, s, e->gmax_all, (long long)S * (1024 * 3 + 64), KEY_NEG_INF))) return rc;
 
   // ---- E1: STN3d (pointnets/pointnet.py:24-41)
-  {
-    Launch l(e, s, G_FRONT3);
-    front3_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(e->q, nullptr, W(e, "pcl_net.stn.conv1.weight"),
-                                                                  W(e, "pcl_net.stn.conv1.bias"), e->h64a, R, N);
-  }
-  if ((rc = check_launch(e, "front3"))) return rc;
   if (tc) {
-    if ((rc = tc_front(e, s, nullptr, "pcl_net.stn.conv1", nullptr, R))) return rc;
+    if ((rc = tc_front(e, s, nullptr, "pcl_net.stn.conv1", R))) return rc;
     if ((rc = tc_split_layer<128>(e, s, G_STN_CONV2, e->x64, e->tw_stn_c2, 64, 128, W(e, "pcl_net.stn.conv2.bias"), e->a128, R))) return rc;
     if ((rc = tc_max_layer(e, s, G_STN_CONV3_MAX, e->tw_stn_c3, e->a128_nb, 128, 1024, W(e, "pcl_net.stn.conv3.bias"), 1, e->gmax_stn, R))) return rc;
   } else {
+    {
+      Launch l(e, s, G_FRONT3);
+      front3_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(e->q, nullptr, W(e, "pcl_net.stn.conv1.weight"),
+                                                                    W(e, "pcl_net.stn.conv1.bias"), e->h64a, R, N);
+    }
+    if ((rc = check_launch(e, "front3"))) return rc;
     GemmP p = gemm_args(e->h64a, 64, W(e, "pcl_net.stn.conv2.weight"), 64, 128, W(e, "pcl_net.stn.conv2.bias"), e->h128,
                         128, R, 1);
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_STN_CONV2, p))) return rc;
@@ -341,19 +361,21 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p.gmax = e->gmax_stn; p.rows_per_set = N;
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_STN_CONV3_MAX, p))) return rc;
   }
-  if ((rc = tnet_fc(e, s, e->gmax_stn, S, "pcl_net.stn", e->stn_fc3_bI, 9, e->t3))) return rc;
+  if ((rc = tnet_fc(e, s, e->gmax_stn, S, "pcl_net.stn", W(e, "pcl_net.stn.fc3.weight"), e->stn_fc3_bI, 9, e->t3, nullptr))) return rc;
 
   // ---- E2: input transform + conv1 (pointnet.py:97-103)
   if (tc) {
-    if ((rc = tc_front(e, s, e->t3, "pcl_net.conv1", e->h64a, R))) return rc;
+    if ((rc = tc_front(e, s, e->t3, "pcl_net.conv1", R))) return rc;
   } else {
-    Launch l(e, s, G_FRONT3);
-    front3_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(e->q, e->t3, W(e, "pcl_net.conv1.weight"),
-                                                                  W(e, "pcl_net.conv1.bias"), e->h64a, R, N);
+    {
+      Launch l(e, s, G_FRONT3);
+      front3_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(e->q, e->t3, W(e, "pcl_net.conv1.weight"),
+                                                                    W(e, "pcl_net.conv1.bias"), e->h64a, R, N);
+    }
+    if ((rc = check_launch(e, "front3"))) return rc;
   }
-  if ((rc = check_launch(e, "front3"))) return rc;
 
-  // ---- E3: STNkd (pointnet.py:57-78)
+  // ---- E3: STNkd (pointnet.py:57-78).  fc3's rows are permuted at pack time so it emits T64^T.
   if (tc) {
     if ((rc = tc_split_layer<64>(e, s, G_FSTN_CONV1, e->x64, e->tw_fstn_c1, 64, 64, W(e, "pcl_net.fstn.conv1.bias"), e->f64, R))) return rc;
     if ((rc = tc_split_layer<128>(e, s, G_FSTN_CONV2, e->f64, e->tw_fstn_c2, 64, 128, W(e, "pcl_net.fstn.conv2.bias"), e->a128, R))) return rc;
@@ -370,22 +392,25 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p.gmax = e->gmax_fstn; p.rows_per_set = N;
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_FSTN_CONV3_MAX, p))) return rc;
   }
-  if ((rc = tnet_fc(e, s, e->gmax_fstn, S, "pcl_net.fstn", e->fstn_fc3_bI, 4096, e->t64))) return rc;
+  if ((rc = tnet_fc(e, s, e->gmax_fstn, S, "pcl_net.fstn", e->fstn_fc3_wT, e->fstn_fc3_bI, 4096, tc ? nullptr : e->t64,
+                    tc ? &e->t64s : nullptr))) return rc;
 
   // ---- E4: feature transform pf = h1 . T64 (per set), trunk conv2-4, global max (pointnet.py:105-116)
-  {
-    GemmP p = gemm_args(e->h64a, 64, e->t64, 64, 64, nullptr, e->h64b, 64, R, 0);
-    p.wcs = 1; p.wks = 64; p.w_set_stride = 4096; p.rows_per_set = N;
-    p.gmax = e->gmax_pf;
-    if ((rc = run_gemm<64, A_PLAIN>(e, s, G_FEAT_TRANSFORM, p))) return rc;
-  }
   if (tc) {
-    if ((rc = tc_split_f32(e, s, e->h64b, e->pf16, R * 64, nullptr, nullptr, 64, 1))) return rc;
+    TcGemmP p{};
+    p.K = 64; p.m_tiles = (int)(R / 128); p.n_tiles = 1; p.rows_per_set = N; p.nb_per_set = 1;
+    p.out_hi = e->pf16.hi; p.out_lo = e->pf16.lo; p.ldo16 = 64; p.gmax = e->gmax_pf; p.C = 64;
+    if ((rc = tc_run<PT_ON_LANES, EPI_SPLIT_MAX, 64>(e, s, G_FEAT_TRANSFORM, e->x64.map_hi, e->x64.map_lo, e->t64s.map_hi,
+                                                      e->t64s.map_lo, p))) return rc;
     if ((rc = tc_split_layer<128>(e, s, G_CONV2, e->pf16, e->tw_conv2, 64, 128, W(e, "pcl_net.conv2.bias"), e->a128, R))) return rc;
     if ((rc = tc_split_layer<256>(e, s, G_CONV3, e->a128, e->tw_conv3, 128, 512, W(e, "pcl_net.conv3.bias"), e->a512, R))) return rc;
     if ((rc = tc_max_layer(e, s, G_CONV4_MAX, e->tw_conv4, e->a512_nb, 512, 1024, W(e, "pcl_net.conv4.bias"), 0, e->gmax_g, R))) return rc;
   } else {
-    GemmP p = gemm_args(e->h64b, 64, W(e, "pcl_net.conv2.weight"), 64, 128, W(e, "pcl_net.conv2.bias"), e->h128, 128, R, 1);
+    GemmP p = gemm_args(e->h64a, 64, e->t64, 64, 64, nullptr, e->h64b, 64, R, 0);
+    p.w_set_stride = 4096; p.rows_per_set = N;  // W[c][k] = T64^T[set][c][k]
+    p.gmax = e->gmax_pf;
+    if ((rc = run_gemm<64, A_PLAIN>(e, s, G_FEAT_TRANSFORM, p))) return rc;
+    p = gemm_args(e->h64b, 64, W(e, "pcl_net.conv2.weight"), 64, 128, W(e, "pcl_net.conv2.bias"), e->h128, 128, R, 1);
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV2, p))) return rc;
     p = gemm_args(e->h128, 128, W(e, "pcl_net.conv3.weight"), 128, 512, W(e, "pcl_net.conv3.bias"), e->h512, 512, R, 1);
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV3, p))) return rc;
@@ -397,23 +422,33 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   // ---- R1: rotation heads (heads/conv_out_per_rot_head.py:62-71,126-140) with the layer-0 split:
   //      layers.0 . [g_set | pf_p] = W0[:, :1024] . g_set (once per set) + W0[:, 1024:] . pf_p
   {
-    GemmP p = gemm_args(reinterpret_cast<const float*>(e->gmax_g), 1024, e->rot_w0g, 1024, 512, e->rot_b0, e->cset, 512, S, 0);
-    if ((rc = run_gemm<128, A_KEY>(e, s, G_ROT_GFEAT, p))) return rc;
+    GemmP p = gemm_args(reinterpret_cast<const float*>(e->gmax_g), 1024, e->rot_w0g, 1024, 512, nullptr, e->csetp, 512, S, 0);
+    p.ksplit = KS_FC1; p.part_stride = (long long)S * 512;
+    if ((rc = run_gemm<64, A_KEY>(e, s, G_ROT_GFEAT, p))) return rc;
+    if ((rc = sum_parts(e, s, e->csetp, KS_FC1, S, 512, e->rot_b0, 0, e->cset, nullptr))) return rc;
   }
-  const int gn_tile = tc ? 256 : 128;  // rows per GroupNorm partial
+  float* gn0_scale = e->gn0;
+  float* gn0_shift = e->gn0 + (size_t)e->maxB * 1024;
   if (tc) {
+    // pass 1: GroupNorm statistics of a0 = W0p . pf + cset (nothing stored; K = 64 makes the recompute cheap)
     TcGemmP p{};
-    p.K = 64; p.m_tiles = 4; p.n_tiles = (int)(R / 256);
-    p.rowvec = e->cset; p.ldrv = 512; p.rows_per_set = N; p.out = e->a0; p.ldo = 512;
+    p.K = 64; p.m_tiles = 4; p.n_tiles = (int)(R / 256); p.rows_per_set = N;
+    p.rowvec = e->cset; p.ldrv = 512;
     p.stats = e->stats0; p.stats_ld = 64; p.stats_goff = 0;
-    if ((rc = tc_run<CH_ON_LANES, EPI_RAW_STATS, 256>(e, s, G_ROT_LAYER0, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->pf_nb[0], e->pf_nb[1], p))) return rc;
+    if ((rc = tc_run<CH_ON_LANES, EPI_STATS, 256>(e, s, G_ROT_LAYER0, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->pf_nb[0], e->pf_nb[1], p))) return rc;
     {
       Launch l(e, s, G_GN_FINALIZE);
-      gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats0, e->rot_gn0_g, e->rot_gn0_b, e->gn0,
-                                                             e->gn0 + (size_t)e->maxB * 512, B, 512, P / 256, P);
+      gn_finalize_set_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats0, e->rot_gn0_g, e->rot_gn0_b, e->cset, gn0_scale,
+                                                                 gn0_shift, B, 512, P / 128, P);
     }
-    if ((rc = check_launch(e, "gn_finalize"))) return rc;
-    if ((rc = tc_split_f32(e, s, e->a0, e->u512, R * 512, e->gn0, e->gn0 + (size_t)e->maxB * 512, 512, P))) return rc;
+    if ((rc = check_launch(e, "gn_finalize_set"))) return rc;
+    // pass 2: recompute a0 and apply GroupNorm + GELU + bf16 hi/lo split in the epilogue -> operand of layer 1
+    TcGemmP pa{};
+    pa.K = 64; pa.m_tiles = (int)(R / 128); pa.n_tiles = 2; pa.rows_per_set = N;
+    pa.gn_scale = gn0_scale; pa.gn_shift = gn0_shift; pa.ldgn = 512;
+    pa.out_hi = e->u512.hi; pa.out_lo = e->u512.lo; pa.ldo16 = 512;
+    if ((rc = tc_run<PT_ON_LANES, EPI_GN_SPLIT, 256>(e, s, G_ROT_LAYER0_APPLY, e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0_nb[0],
+                                                     e->tw_rot0_nb[1], pa))) return rc;
     for (int h = 0; h < 2; ++h) {
       TcGemmP p1{};
       p1.K = 256; p1.m_tiles = 2; p1.n_tiles = (int)(R / 256);
@@ -429,15 +464,15 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_ROT_LAYER0, p))) return rc;
     {
       Launch l(e, s, G_GN_FINALIZE);
-      gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats0, e->rot_gn0_g, e->rot_gn0_b, e->gn0,
-                                                             e->gn0 + (size_t)e->maxB * 512, B, 512, P / 128, P);
+      gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats0, e->rot_gn0_g, e->rot_gn0_b, gn0_scale, gn0_shift, B,
+                                                             512, P / 128, P);
     }
     if ((rc = check_launch(e, "gn_finalize"))) return rc;
     for (int h = 0; h < 2; ++h) {
       const char* wn = h == 0 ? "rot_head.rot_head_x.layers.3.weight" : "rot_head.rot_head_y.layers.3.weight";
       GemmP p1 = gemm_args(e->a0 + h * 256, 512, W(e, wn), 256, 256, e->rot_b1 + h * 256, e->a1 + h * 256, 512, R, 0);
       p1.rows_per_set = N; p1.rows_per_obj = P;
-      p1.gn_scale = e->gn0 + h * 256; p1.gn_shift = e->gn0 + (size_t)e->maxB * 512 + h * 256; p1.ldgn = 512;
+      p1.gn_scale = gn0_scale + h * 256; p1.gn_shift = gn0_shift + h * 256; p1.ldgn = 512;
       p1.stats = e->stats1; p1.stats_ld = 64; p1.stats_goff = 32 * h;
       if ((rc = run_gemm<128, A_GN_GELU>(e, s, G_ROT_LAYER1, p1))) return rc;
     }
@@ -445,13 +480,17 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   {
     Launch l(e, s, G_GN_FINALIZE);
     gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats1, e->rot_gn1_g, e->rot_gn1_b, e->gn1,
-                                                           e->gn1 + (size_t)e->maxB * 512, B, 512, P / gn_tile, P);
+                                                           e->gn1 + (size_t)e->maxB * 512, B, 512, P / 128, P);
   }
   if ((rc = check_launch(e, "gn_finalize"))) return rc;
   {
     Launch l(e, s, G_ROT_TAIL);
-    rot_tail_kernel<<<dim3(P / 128, B), 256, 0, s>>>(e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
-                                                    e->wp, e->rot_partial, P);
+    if (tc)
+      rot_tail_kernel<1><<<dim3(P / 128, B), 256, 0, s>>>(e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
+                                                         e->wp, e->rot_partial, P);
+    else
+      rot_tail_kernel<0><<<dim3(P / 128, B), 256, 0, s>>>(e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
+                                                         e->wp, e->rot_partial, P);
   }
   if ((rc = check_launch(e, "rot_tail"))) return rc;
 
@@ -485,7 +524,7 @@ int check_ready(catre_engine* e, int B) {
 // ================================================================================================
 extern "C" {
 
-const char* catre_version(void) { return "catre_b200 0.1 sm_100a (fp32 SIMT + tcgen05 bf16x3)"; }
+const char* catre_version(void) { return "catre_b200 0.2 sm_100a (fp32 SIMT + tcgen05 bf16x3)"; }
 int32_t catre_num_weights(void) { return kNumWeights; }
 const char* catre_weight_name(int32_t i) { return (i >= 0 && i < kNumWeights) ? kWeights[i].name : nullptr; }
 int32_t catre_profile_num(void) { return G_NUM; }
@@ -525,27 +564,29 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   int rc = 0;
   const bool tc = cfg->precision != CATRE_PREC_FP32_SIMT;
   rc |= dalloc(e, &e->q, R * 3);
-  rc |= dalloc(e, &e->h64a, R * 64);
-  rc |= dalloc(e, &e->h64b, R * 64);
-  if (!tc) {
+  if (!tc) {  // fp32 activations of the CUDA-core mode; the tensor-core modes keep bf16 hi/lo operands only
+    rc |= dalloc(e, &e->h64a, R * 64);
+    rc |= dalloc(e, &e->h64b, R * 64);
     rc |= dalloc(e, &e->h128, R * 128);
     rc |= dalloc(e, &e->h512, R * 512);
+    rc |= dalloc(e, &e->a0, R * 512);
+    rc |= dalloc(e, &e->t64, S * 4096);
   }
-  rc |= dalloc(e, &e->a0, R * 512);
   rc |= dalloc(e, &e->a1, R * 512);
   rc |= dalloc(e, &e->gmax_all, S * (1024 * 3 + 64));
   e->gmax_stn = e->gmax_all;
   e->gmax_fstn = e->gmax_all + S * 1024;
   e->gmax_g = e->gmax_all + S * 2048;
   e->gmax_pf = e->gmax_all + S * 3072;
-  rc |= dalloc(e, &e->fc512, S * 512);
-  rc |= dalloc(e, &e->fc256, S * 256);
+  rc |= dalloc(e, &e->fc512, KS_FC1 * S * 512);  // split-K partials of the small-M FC layers
+  rc |= dalloc(e, &e->fc256, KS_FC2 * S * 256);
+  rc |= dalloc(e, &e->fc3p, KS_FC3 * S * 4096);
+  rc |= dalloc(e, &e->csetp, KS_FC1 * S * 512);
   rc |= dalloc(e, &e->t3, S * 9 + 7);
-  rc |= dalloc(e, &e->t64, S * 4096);
   rc |= dalloc(e, &e->cset, S * 512);
   rc |= dalloc(e, &e->stats0, (R / 128) * 64 * 2);
   rc |= dalloc(e, &e->stats1, (R / 128) * 64 * 2);
-  rc |= dalloc(e, &e->gn0, B * 512 * 2);
+  rc |= dalloc(e, &e->gn0, B * 2048);  // scale | shift, per set in the tensor-core modes
   rc |= dalloc(e, &e->gn1, B * 512 * 2);
   rc |= dalloc(e, &e->rot_partial, B * (P / 128) * 6);
   rc |= dalloc(e, &e->st_pcl, B * N * 3);
@@ -564,6 +605,12 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
       if (!tc_make_map(&t.map_hi, t.hi, R, cols, cols, 128) || !tc_make_map(&t.map_lo, t.lo, R, cols, cols, 128)) rc |= 2;
     };
     pair(e->x64, 64); pair(e->f64, 64); pair(e->a128, 128); pair(e->pf16, 64); pair(e->a512, 512); pair(e->u512, 512);
+    if (!rc) {  // T64^T per set, the N-side operand of the feature transform: [S*64, 64], 64-row boxes
+      rc |= dalloc(e, &e->t64s.hi, S * 4096);
+      rc |= dalloc(e, &e->t64s.lo, S * 4096);
+      if (!rc && (!tc_make_map(&e->t64s.map_hi, e->t64s.hi, S * 64, 64, 64, 64) ||
+                  !tc_make_map(&e->t64s.map_lo, e->t64s.lo, S * 64, 64, 64, 64))) rc |= 2;
+    }
     if (!rc) {
       bool ok = true;
       ok &= tc_make_map(&e->a128_nb[0], e->a128.hi, R, 128, 128, 256) && tc_make_map(&e->a128_nb[1], e->a128.lo, R, 128, 128, 256);
@@ -638,9 +685,18 @@ int catre_pack(catre_engine* e, void* stream) {
   v = H("pcl_net.stn.fc3.bias");  // + I3 (pointnet.py:37-40)
   for (int i = 0; i < 3; ++i) v[i * 3 + i] += 1.0f;
   up(&e->stn_fc3_bI, v);
-  v = H("pcl_net.fstn.fc3.bias");  // + I64 (pointnet.py:72-77)
-  for (int i = 0; i < 64; ++i) v[i * 64 + i] += 1.0f;
-  up(&e->fstn_fc3_bI, v);
+  {  // fstn.fc3 with output rows permuted (i*64+j -> j*64+i) so the FC emits T64^T, + I64 (pointnet.py:72-77)
+    const std::vector<float>& w3 = H("pcl_net.fstn.fc3.weight");
+    const std::vector<float>& b3 = H("pcl_net.fstn.fc3.bias");
+    std::vector<float> wT(w3.size()), bT(b3.size());
+    for (int i = 0; i < 64; ++i)
+      for (int j = 0; j < 64; ++j) {
+        memcpy(&wT[(size_t)(j * 64 + i) * 256], &w3[(size_t)(i * 64 + j) * 256], 256 * sizeof(float));
+        bT[j * 64 + i] = b3[i * 64 + j] + (i == j ? 1.0f : 0.0f);
+      }
+    up(&e->fstn_fc3_wT, wT);
+    up(&e->fstn_fc3_bI, bT);
+  }
 
   const char* hx = "rot_head.rot_head_x.";
   const char* hy = "rot_head.rot_head_y.";
@@ -705,6 +761,9 @@ int catre_pack(catre_engine* e, void* stream) {
     r2 = r2 ? r2 : wpair(e->tw_conv3, H("pcl_net.conv3.weight"), 512, 128, 256);
     r2 = r2 ? r2 : wpair(e->tw_conv4, H("pcl_net.conv4.weight"), 1024, 512, 128);
     r2 = r2 ? r2 : wpair(e->tw_rot0, w0p, 512, 64, 128);
+    if (!r2 && (!tc_make_map(&e->tw_rot0_nb[0], e->tw_rot0.hi, 512, 64, 64, 256) ||
+                !tc_make_map(&e->tw_rot0_nb[1], e->tw_rot0.lo, 512, 64, 64, 256)))
+      r2 = fail(e, CATRE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the rot layer-0 N-side view");
     r2 = r2 ? r2 : wpair(e->tw_rot1[0], H("rot_head.rot_head_x.layers.3.weight"), 256, 256, 128);
     r2 = r2 ? r2 : wpair(e->tw_rot1[1], H("rot_head.rot_head_y.layers.3.weight"), 256, 256, 128);
     if (r2) return r2;
@@ -821,6 +880,7 @@ int catre_debug_read(catre_engine* e, const char* name, void* dst_host, size_t b
       {"q", e->q}, {"h64a", e->h64a}, {"h64b", e->h64b}, {"h128", e->h128}, {"h512", e->h512}, {"a0", e->a0}, {"a1", e->a1},
       {"gmax_stn", e->gmax_stn}, {"gmax_fstn", e->gmax_fstn}, {"gmax_g", e->gmax_g}, {"gmax_pf", e->gmax_pf},
       {"fc512", e->fc512}, {"fc256", e->fc256}, {"t3", e->t3}, {"t64", e->t64}, {"cset", e->cset},
+      {"t64s_hi", e->t64s.hi}, {"t64s_lo", e->t64s.lo},
       {"stats0", e->stats0}, {"stats1", e->stats1}, {"gn0", e->gn0}, {"gn1", e->gn1}, {"rot_partial", e->rot_partial}};
   m["x64_hi"] = e->x64.hi; m["x64_lo"] = e->x64.lo; m["f64_hi"] = e->f64.hi; m["f64_lo"] = e->f64.lo;
   m["a128_hi"] = e->a128.hi; m["a128_lo"] = e->a128.lo; m["pf_hi"] = e->pf16.hi; m["pf_lo"] = e->pf16.lo;

@@ -22,6 +22,24 @@ constexpr int KEY_NEG_INF = (int)0x807fffff;  // f2key(-inf)
 // exact GELU (nn.GELU default, lib/torch_utils/layers/layer_utils.py:61-95 "gelu")
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
+// GELU through the Abramowitz-Stegun 7.1.26 erfc form (|err| of erf <= 1.5e-7; measured max |gelu err|
+// 4.2e-7 vs fp64 over [-12, 12], i.e. below the fp32 erff path's own 1.2e-6), branch-free, no
+// cancellation on the negative side:  1 + erf(x/sqrt2) = w (x < 0) | 2 - w (x >= 0),
+//   w = poly(t) exp(-x^2/2), t = 1 / (1 + p |x|/sqrt2).   Used by the tensor-core modes' fused epilogues.
+__device__ __forceinline__ float gelu_fast(float x) {
+  const float z = fabsf(x) * 0.70710678118654752440f;
+  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
+  float pl = fmaf(1.061405429f, t, -1.453152027f);
+  pl = fmaf(pl, t, 1.421413741f);
+  pl = fmaf(pl, t, -0.284496736f);
+  pl = fmaf(pl, t, 0.254829592f);
+  const float w = pl * t * __expf(-z * z);
+  const float phi2 = x < 0.0f ? w : 2.0f - w;
+  return 0.5f * x * phi2;
+}
+template <int FAST>
+__device__ __forceinline__ float gelu_sel(float x) { return FAST ? gelu_fast(x) : gelu_exact(x); }
+
 __global__ void fill_i32_kernel(int* __restrict__ p, long long n, int v) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
@@ -114,7 +132,8 @@ __global__ void front3_kernel(const float* __restrict__ q, const float* __restri
 // Generic fp32 point-wise layer:  out[r, c] = act( sum_k f(A[r, k]) * W[c, k] + bias[c] + rowvec[set(r), c] )
 // 128 x BN output tile, K chunks of 16, 256 threads, 8 x (BN/16) micro-tile.
 // ----------------------------------------------------------------------------------------------
-enum { A_PLAIN = 0, A_KEY = 1, A_GN_GELU = 2 };
+//   A_PARTIAL : A[r, k] = act(sum_z Apart[z][r, k] + a_bias[k])  -- consumes a split-K producer's partials
+enum { A_PLAIN = 0, A_KEY = 1, A_GN_GELU = 2, A_PARTIAL = 3 };
 
 struct GemmP {
   const float* A; int lda;
@@ -129,6 +148,11 @@ struct GemmP {
   int R, C, K;
   int rows_per_set, rows_per_obj;
   int relu;
+  // split-K (small-M FC layers): gridDim.z = ksplit CTAs each reduce K/ksplit and write RAW partial sums
+  // (no bias / activation) to out + z * part_stride; the consumer (A_PARTIAL or sum_parts_kernel) adds
+  // them in fixed z order, so results are deterministic.
+  int ksplit; long long part_stride;
+  const float* a_bias; int a_nparts; long long a_part_stride; int a_relu;  // A_PARTIAL
 };
 
 template <int BN, int AMODE>
@@ -152,7 +176,9 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
-  for (int k0 = 0; k0 < p.K; k0 += BK) {
+  const int kz = (p.ksplit > 1) ? p.K / p.ksplit : p.K;
+  const int k_begin = (p.ksplit > 1) ? blockIdx.z * kz : 0;
+  for (int k0 = k_begin; k0 < k_begin + kz; k0 += BK) {
     // ---- A tile: 128 rows x 16 k, float4 along k
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
@@ -164,6 +190,13 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
         if (AMODE == A_KEY) {
           int4 kv = *reinterpret_cast<const int4*>(src);
           v = make_float4(key2f(kv.x), key2f(kv.y), key2f(kv.z), key2f(kv.w));
+        } else if (AMODE == A_PARTIAL) {
+          v = *reinterpret_cast<const float4*>(p.a_bias + k0 + kq);
+          for (int z = 0; z < p.a_nparts; ++z) {
+            const float4 t = *reinterpret_cast<const float4*>(src + (long long)z * p.a_part_stride);
+            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+          }
+          if (p.a_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         } else {
           v = *reinterpret_cast<const float4*>(src);
           if (AMODE == A_GN_GELU) {
@@ -215,6 +248,22 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
     __syncthreads();
   }
 
+  if (p.ksplit > 1) {  // raw partial sums; bias / activation belong to the consumer
+    float* po = p.out + (long long)blockIdx.z * p.part_stride;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+      int row = r0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+      if (row >= p.R) continue;
+#pragma unroll
+      for (int ch = 0; ch < NCH; ++ch) {
+        int cbase = c0 + ch * (BN / 2) + tx * 4;
+#pragma unroll
+        for (int j = 0; j < 4; ++j)
+          if (cbase + j < p.C) po[(long long)row * p.ldo + cbase + j] = acc[i][ch * 4 + j];
+      }
+    }
+    return;
+  }
   // ---- epilogue: bias / per-set vector / ReLU
   // thread's rows: ty*4+i (i<4), 64+ty*4+(i-4); columns: chunk ch -> ch*(BN/2) + tx*4 + j
 #pragma unroll
@@ -337,11 +386,94 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, const float*
   }
 }
 
+// Fixed-order reduction of split-K partials:  out[r, c] = act(sum_z parts[z][r, c] + bias[c]).
+// Optionally also writes the bf16 hi/lo split of the result (operand of a tensor-core layer).
+__global__ void sum_parts_kernel(const float* __restrict__ parts, int nparts, long long part_stride,
+                                 const float* __restrict__ bias, int C, int relu, float* __restrict__ out32,
+                                 unsigned short* __restrict__ out_hi, unsigned short* __restrict__ out_lo, long long n4) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int c = (int)((i * 4) % C);
+  float4 v = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int z = 0; z < nparts; ++z) {
+    const float4 t = *reinterpret_cast<const float4*>(parts + (long long)z * part_stride + i * 4);
+    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+  }
+  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
+  if (out32) *reinterpret_cast<float4*>(out32 + i * 4) = v;
+  if (out_hi) {
+    const float f[4] = {v.x, v.y, v.z, v.w};
+    unsigned short h[4], l[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {  // round-to-nearest-even bf16 of f and of the residual
+      unsigned int u = __float_as_uint(f[j]);
+      unsigned int hr = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;
+      h[j] = (unsigned short)(hr >> 16);
+      unsigned int ul = __float_as_uint(f[j] - __uint_as_float(hr));
+      l[j] = (unsigned short)((ul + 0x7fffu + ((ul >> 16) & 1u)) >> 16);
+    }
+    *reinterpret_cast<uint2*>(out_hi + i * 4) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
+    *reinterpret_cast<uint2*>(out_lo + i * 4) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
+  }
+}
+
+// scalar variant for widths that are not a multiple of 4 (stn.fc3: C = 9)
+__global__ void sum_parts_scalar_kernel(const float* __restrict__ parts, int nparts, long long part_stride,
+                                        const float* __restrict__ bias, int C, int relu, float* __restrict__ out32,
+                                        long long n) {
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float v = bias ? bias[i % C] : 0.f;
+  for (int z = 0; z < nparts; ++z) v += parts[(long long)z * part_stride + i];
+  out32[i] = relu ? fmaxf(v, 0.f) : v;
+}
+
+// Tensor-core modes: GroupNorm statistics of rot layer 0 -> per (SET, channel) affine applied to the raw
+// MMA accumulator D = W0p . pf (the per-set constant cset = W0g . g_set + b0 is folded into the shift):
+//   gelu_in = (D + cset) * sc + sh  =  D * sc + (cset * sc + sh)
+__global__ void gn_finalize_set_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
+                                       const float* __restrict__ beta, const float* __restrict__ cset,
+                                       float* __restrict__ scale, float* __restrict__ shift, int B, int C,
+                                       int tiles_per_obj, int rows_per_obj) {
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  int G = C / 8;
+  if (i >= B * G) return;
+  int b = i / G, g = i % G;
+  double s = 0.0, ss = 0.0;
+  for (int t = 0; t < tiles_per_obj; ++t) {
+    long long o = (((long long)b * tiles_per_obj + t) * G + g) * 2;
+    s += (double)stats[o];
+    ss += (double)stats[o + 1];
+  }
+  double n = 8.0 * rows_per_obj;
+  double mean = s / n;
+  double var = ss / n - mean * mean;
+  if (var < 0.0) var = 0.0;
+  float rstd = (float)(1.0 / sqrt(var + 1e-5));
+  float fmean = (float)mean;
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    int c = g * 8 + j;
+    float sc = rstd * gamma[c];
+    float sh = beta[c] - fmean * sc;
+#pragma unroll
+    for (int q = 0; q < 2; ++q) {  // the two sets (observed, prior) of object b
+      long long o = ((long long)(2 * b + q)) * C + c;
+      scale[o] = sc;
+      shift[o] = fmaf(cset[o], sc, sh);
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // R1 tail: GN + GELU of the second rot layer, neck 256 -> 3, learned weighted sum over the point index
 // (heads/conv_out_per_rot_head.py:131-140).  a1 [R, 512] = [head x 256 | head y 256] raw layer-3 output.
 // Block = 128 rows of one object; warp per row; partial[b][tile][6] (deterministic two-level reduce).
 // ----------------------------------------------------------------------------------------------
+// By linearity  sum_p wp[p] (neck . g_p + nb) = neck . (sum_p wp[p] g_p) + nb sum_p wp[p]:  each lane
+// accumulates the wp-weighted GELU outputs of its 8 channels per head over the block's rows (no
+// per-row shuffles); the 256 -> 3 neck is applied once per warp at the end.
+template <int FAST_GELU>
 __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__ a1, const float* __restrict__ gn_scale,
                                                        const float* __restrict__ gn_shift,
                                                        const float* __restrict__ neck_w /*[2][3][256]*/,
@@ -351,9 +483,8 @@ __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__
   const int b = blockIdx.y, tile = blockIdx.x, tiles = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ float s_part[8][6];
-  float accw[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-  // lane owns channels lane*8 .. lane*8+7 of each head
-  float sc[2][8], sh[2][8], nw[2][3][8];
+  float sc[2][8], sh[2][8], acc[2][8];
+  float wsum[2] = {0.f, 0.f};
 #pragma unroll
   for (int h = 0; h < 2; ++h)
 #pragma unroll
@@ -361,40 +492,40 @@ __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__
       int c = h * 256 + lane * 8 + j;
       sc[h][j] = gn_scale[(long long)b * 512 + c];
       sh[h][j] = gn_shift[(long long)b * 512 + c];
-#pragma unroll
-      for (int d = 0; d < 3; ++d) nw[h][d][j] = neck_w[(h * 3 + d) * 256 + lane * 8 + j];
+      acc[h][j] = 0.f;
     }
+#pragma unroll 2
   for (int rr = warp; rr < 128; rr += 8) {
-    int pidx = tile * 128 + rr;
+    const int pidx = tile * 128 + rr;
     const float* row = a1 + ((long long)b * P + pidx) * 512;
 #pragma unroll
     for (int h = 0; h < 2; ++h) {
-      float4 v0 = *reinterpret_cast<const float4*>(row + h * 256 + lane * 8);
-      float4 v1 = *reinterpret_cast<const float4*>(row + h * 256 + lane * 8 + 4);
-      float u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
-      float d0 = 0.f, d1 = 0.f, d2 = 0.f;
+      const float4 v0 = *reinterpret_cast<const float4*>(row + h * 256 + lane * 8);
+      const float4 v1 = *reinterpret_cast<const float4*>(row + h * 256 + lane * 8 + 4);
+      const float u[8] = {v0.x, v0.y, v0.z, v0.w, v1.x, v1.y, v1.z, v1.w};
+      const float w = __ldg(wp + (long long)h * P + pidx);
+      wsum[h] += w;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        float g = gelu_exact(u[j] * sc[h][j] + sh[h][j]);
-        d0 = fmaf(nw[h][0][j], g, d0);
-        d1 = fmaf(nw[h][1][j], g, d1);
-        d2 = fmaf(nw[h][2][j], g, d2);
-      }
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) {
-        d0 += __shfl_xor_sync(0xffffffffu, d0, o);
-        d1 += __shfl_xor_sync(0xffffffffu, d1, o);
-        d2 += __shfl_xor_sync(0xffffffffu, d2, o);
-      }
-      float w = wp[(long long)h * P + pidx];
-      accw[h * 3 + 0] = fmaf(w, d0 + neck_b[h * 3 + 0], accw[h * 3 + 0]);
-      accw[h * 3 + 1] = fmaf(w, d1 + neck_b[h * 3 + 1], accw[h * 3 + 1]);
-      accw[h * 3 + 2] = fmaf(w, d2 + neck_b[h * 3 + 2], accw[h * 3 + 2]);
+      for (int j = 0; j < 8; ++j) acc[h][j] = fmaf(w, gelu_sel<FAST_GELU>(fmaf(u[j], sc[h][j], sh[h][j])), acc[h][j]);
     }
   }
+  float d[6];
+#pragma unroll
+  for (int h = 0; h < 2; ++h)
+#pragma unroll
+    for (int k = 0; k < 3; ++k) {
+      float t = 0.f;
+#pragma unroll
+      for (int j = 0; j < 8; ++j) t = fmaf(neck_w[(h * 3 + k) * 256 + lane * 8 + j], acc[h][j], t);
+      d[h * 3 + k] = t;
+    }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1)
+#pragma unroll
+    for (int k = 0; k < 6; ++k) d[k] += __shfl_xor_sync(0xffffffffu, d[k], o);
   if (lane == 0)
 #pragma unroll
-    for (int j = 0; j < 6; ++j) s_part[warp][j] = accw[j];
+    for (int k = 0; k < 6; ++k) s_part[warp][k] = fmaf(neck_b[k], wsum[k / 3], d[k]);
   __syncthreads();
   if (threadIdx.x < 6) {
     float s = 0.f;
@@ -448,13 +579,36 @@ __global__ void __launch_bounds__(256) ts_pose_kernel(TsPoseP p) {
   if (t < 64) feat[1024 + t] = key2f(p.gmax_pf[(long long)(2 * b) * 64 + t]);
   if (t < 3) feat[1088 + t] = sc_in[t];
   __syncthreads();
-  float a = p.b0[t];
-  for (int k = 0; k < 1091; ++k) a = fmaf(p.w0t[k * 256 + t], feat[k], a);
+  float a;
+  {
+    float a0 = p.b0[t], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 1088; k += 4) {
+      a0 = fmaf(p.w0t[(k + 0) * 256 + t], feat[k + 0], a0);
+      a1 = fmaf(p.w0t[(k + 1) * 256 + t], feat[k + 1], a1);
+      a2 = fmaf(p.w0t[(k + 2) * 256 + t], feat[k + 2], a2);
+      a3 = fmaf(p.w0t[(k + 3) * 256 + t], feat[k + 3], a3);
+    }
+    a0 = fmaf(p.w0t[1088 * 256 + t], feat[1088], a0);
+    a1 = fmaf(p.w0t[1089 * 256 + t], feat[1089], a1);
+    a2 = fmaf(p.w0t[1090 * 256 + t], feat[1090], a2);
+    a = (a0 + a1) + (a2 + a3);
+  }
   a = gn8_gelu(a, p.g0[t], p.be0[t]);
   h[t] = a;
   __syncthreads();
-  float a2 = p.b1[t];
-  for (int k = 0; k < 256; ++k) a2 = fmaf(p.w1t[k * 256 + t], h[k], a2);
+  float a2;
+  {
+    float c0 = p.b1[t], c1 = 0.f, c2 = 0.f, c3 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 256; k += 4) {
+      c0 = fmaf(p.w1t[(k + 0) * 256 + t], h[k + 0], c0);
+      c1 = fmaf(p.w1t[(k + 1) * 256 + t], h[k + 1], c1);
+      c2 = fmaf(p.w1t[(k + 2) * 256 + t], h[k + 2], c2);
+      c3 = fmaf(p.w1t[(k + 3) * 256 + t], h[k + 3], c3);
+    }
+    a2 = (c0 + c1) + (c2 + c3);
+  }
   a2 = gn8_gelu(a2, p.g1[t], p.be1[t]);
   __syncthreads();
   h[t] = a2;

@@ -23,10 +23,18 @@
 
 namespace catre {
 
-constexpr int TC_THREADS = 192;
+constexpr int TC_EPI_WARPS = 8;                    // two per TMEM lane quadrant: each takes half of the columns
+constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // + TMA warp + MMA warp
 constexpr int TC_BK = 64;  // K slab = one 128-byte swizzle atom of bf16
 enum { CH_ON_LANES = 0, PT_ON_LANES = 1 };
-enum { EPI_MAX = 0, EPI_RAW_STATS = 1, EPI_SPLIT = 2 };
+// epilogues:            orientation   what leaves the kernel
+//   EPI_MAX             CH_ON_LANES   column max over the tile's points of act(D + bias) -> atomicMax keys
+//   EPI_RAW_STATS       CH_ON_LANES   D + bias + rowvec[set] -> fp32 [R, ldo] and GroupNorm partial sums
+//   EPI_STATS           CH_ON_LANES   GroupNorm partial sums of D + rowvec[set] only (nothing stored)
+//   EPI_SPLIT           PT_ON_LANES   act(D + bias) -> bf16 hi/lo [R, ldo16] (operand of the next layer)
+//   EPI_GN_SPLIT        PT_ON_LANES   gelu(D * sc[set] + sh[set]) -> bf16 hi/lo (GroupNorm + GELU fused)
+//   EPI_SPLIT_MAX       PT_ON_LANES   D -> bf16 hi/lo, and column max over the tile's points -> atomicMax keys
+enum { EPI_MAX = 0, EPI_RAW_STATS = 1, EPI_SPLIT = 2, EPI_STATS = 3, EPI_GN_SPLIT = 4, EPI_SPLIT_MAX = 5 };
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -105,6 +113,37 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float* v) {
       : "memory");
 }
 __device__ __forceinline__ void tmem_ld_wait() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
+// wait for outstanding tcgen05.ld; the 32 destination registers pass through the statement so the
+// compiler cannot schedule their consumers above the wait
+__device__ __forceinline__ void tmem_ld_wait32(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]), "+r"(r[16]),
+                 "+r"(r[17]), "+r"(r[18]), "+r"(r[19]), "+r"(r[20]), "+r"(r[21]), "+r"(r[22]), "+r"(r[23]), "+r"(r[24]),
+                 "+r"(r[25]), "+r"(r[26]), "+r"(r[27]), "+r"(r[28]), "+r"(r[29]), "+r"(r[30]), "+r"(r[31])
+               :
+               : "memory");
+}
+// visit NCHUNK consecutive 32-column chunks of this warp's TMEM lanes; the load of chunk c+1 is in
+// flight while f(c, values) runs (two register buffers)
+template <int NCHUNK, typename F>
+__device__ __forceinline__ void tmem_foreach32(uint32_t taddr, F&& f) {
+  float va[32], vb[32];
+  tmem_ld32(taddr, va);
+#pragma unroll
+  for (int c = 0; c < NCHUNK; ++c) {
+    if (c & 1) {
+      tmem_ld_wait32(vb);
+      if (c + 1 < NCHUNK) tmem_ld32(taddr + (c + 1) * 32, va);
+      f(c, vb);
+    } else {
+      tmem_ld_wait32(va);
+      if (c + 1 < NCHUNK) tmem_ld32(taddr + (c + 1) * 32, vb);
+      f(c, va);
+    }
+  }
+}
 
 // shared-memory matrix descriptor: K-major, 128B swizzle, rows 128 B apart, 8-row groups 1024 B apart
 // (cute::UMMA::SmemDescriptor: start[0,14) lbo[16,30) sbo[32,46) version[46,48)=1 layout[61,64)=2)
@@ -136,14 +175,17 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
 struct TcGemmP {
   int K;                 // reduction length, multiple of 64
   int m_tiles, n_tiles;  // tiles on the M side (128 rows each) / N side (BN rows each)
+  int rows_per_set;      // points per set (a tile never straddles two sets)
+  int nb_per_set;        // PT_ON_LANES: the NB operand is per set (rows set*BN .. +BN): feature transform
   // epilogue
   const float* bias;     // per output channel (or null)
   int relu;
-  int* gmax; int C; int rows_per_set;           // EPI_MAX: keys [S, C]
+  int* gmax; int C;                             // EPI_MAX / EPI_SPLIT_MAX: keys [S, C]
   float* out; int ldo;                          // EPI_RAW_STATS: fp32 [R, ldo]
-  const float* rowvec; int ldrv;                // EPI_RAW_STATS: per-set additive vector [S, ldrv]
-  float* stats; int stats_ld, stats_goff;       // EPI_RAW_STATS: [R/BN, stats_ld, 2]
-  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int ldo16;  // EPI_SPLIT: bf16 [R, ldo16]
+  const float* rowvec; int ldrv;                // EPI_RAW_STATS / EPI_STATS: per-set additive vector [S, ldrv]
+  float* stats; int stats_ld, stats_goff;       // GroupNorm partials [R/(BN/2), stats_ld, 2]
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int ldo16;  // EPI_*SPLIT*: bf16 [R, ldo16]
+  const float* gn_scale; const float* gn_shift; int ldgn;   // EPI_GN_SPLIT: per (set, channel) affine
 };
 
 template <int BN, int NPROD>
@@ -156,13 +198,39 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;  // + barriers + 1024 B alignment slack
 };
 
+// 32 columns of one point row: fp32 -> bf16 hi/lo, 16-byte stores
+template <int NPROD>
+__device__ __forceinline__ void store_split32(const float* x, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo) {
+  uint32_t hi[16], lo[16];
+#pragma unroll
+  for (int j = 0; j < 32; j += 2) {
+    __nv_bfloat16 h0, l0, h1, l1;
+    split_bf16(x[j], h0, l0);
+    split_bf16(x[j + 1], h1, l1);
+    hi[j >> 1] = pack_bf16(h0, h1);
+    lo[j >> 1] = pack_bf16(l0, l1);
+  }
+  uint4* dh = reinterpret_cast<uint4*>(dst_hi);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) dh[q] = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+  if (NPROD == 3) {
+    uint4* dl = reinterpret_cast<uint4*>(dst_lo);
+#pragma unroll
+    for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+  }
+}
+
 template <int ORIENT, int EPI, int BN, int NPROD>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant__ CUtensorMap ma_lo,
                const __grid_constant__ CUtensorMap nb_hi, const __grid_constant__ CUtensorMap nb_lo, const TcGemmP p) {
   using Cfg = TcCfg<BN, NPROD>;
   constexpr int STAGES = Cfg::STAGES;
+  constexpr int HALF = BN / 2;       // columns per epilogue warp
+  constexpr int NCHUNK = HALF / 32;  // 32-column chunks per epilogue warp
+  static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128 or 256");
   extern __shared__ uint8_t smem_raw[];
+  __shared__ float s_bias[1024];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t tiles_base = (smem_base + 1024 + 1023) & ~1023u;  // barriers live in the first 1 KB
   // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base pointer
@@ -179,10 +247,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
     prefetch_tmap(&ma_hi); prefetch_tmap(&nb_hi);
     if (NPROD == 3) { prefetch_tmap(&ma_lo); prefetch_tmap(&nb_lo); }
     for (int i = 0; i < STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, TC_EPI_WARPS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
+  if (p.bias) {  // per-channel bias of the whole layer (<= 1024 channels) staged once
+    const int nbias = (ORIENT == CH_ON_LANES) ? p.m_tiles * 128 : p.n_tiles * BN;
+    for (int i = threadIdx.x; i < nbias; i += TC_THREADS) s_bias[i] = p.bias[i];
+  }
   tc_fence_before();
   __syncthreads();
   tc_fence_after();
@@ -199,16 +271,17 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
       int stage = 0; uint32_t phase = 0;
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int mi, ni; tile_coords(t, mi, ni);
+        const int nb_row = (ORIENT == PT_ON_LANES && p.nb_per_set) ? ((mi * 128) / p.rows_per_set) * BN : ni * BN;
         for (int ks = 0; ks < k_slabs; ++ks) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sb = tiles_base + stage * Cfg::STAGE_BYTES;
           const uint32_t full = bar_full + 8 * stage;
           mbar_expect_tx(full, Cfg::STAGE_BYTES);
           tma_load_2d(sb, &ma_hi, ks * TC_BK, mi * 128, full);
-          tma_load_2d(sb + Cfg::MA_BYTES * Cfg::ARR, &nb_hi, ks * TC_BK, ni * BN, full);
+          tma_load_2d(sb + Cfg::MA_BYTES * Cfg::ARR, &nb_hi, ks * TC_BK, nb_row, full);
           if (NPROD == 3) {
             tma_load_2d(sb + Cfg::MA_BYTES, &ma_lo, ks * TC_BK, mi * 128, full);
-            tma_load_2d(sb + Cfg::MA_BYTES * 2 + Cfg::NB_BYTES, &nb_lo, ks * TC_BK, ni * BN, full);
+            tma_load_2d(sb + Cfg::MA_BYTES * 2 + Cfg::NB_BYTES, &nb_lo, ks * TC_BK, nb_row, full);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -247,87 +320,95 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
       }
     }
   } else {
-    // ===================== epilogue warps (TMEM lanes 32*(warp%4) ..) =====================
-    const int lane_row = (warp & 3) * 32 + lane;
+    // ===================== epilogue warps =====================
+    // warp w may touch TMEM lanes 32*(w%4) .. +31; the two warps of a quadrant split the BN columns
+    const int quad = warp & 3, half = (warp - 2) >> 2;
+    const int lane_row = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
     for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
       int mi, ni; tile_coords(t, mi, ni);
       mbar_wait(bar_tfull + 8 * acc, acc_phase);
       tc_fence_after();
-      const uint32_t taddr = tmem_base + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)(acc * BN);
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(acc * BN + half * HALF);
       if (EPI == EPI_MAX) {
         const int ch = mi * 128 + lane_row;
         float m = -INFINITY;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 64) {
-          float v[64];
-          tmem_ld32(taddr + c0, v);
-          tmem_ld32(taddr + c0 + 32, v + 32);
-          tmem_ld_wait();
+        tmem_foreach32<NCHUNK>(taddr, [&](int, const float* v) {
 #pragma unroll
-          for (int j = 0; j < 64; ++j) m = fmaxf(m, v[j]);
-        }
-        if (p.bias) m += p.bias[ch];
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
+        });
+        if (p.bias) m += s_bias[ch];
         if (p.relu) m = fmaxf(m, 0.f);
         const int set = (ni * BN) / p.rows_per_set;
         atomicMax(p.gmax + (long long)set * p.C + ch, f2key(m));
-      } else if (EPI == EPI_RAW_STATS) {
+      } else if (EPI == EPI_RAW_STATS || EPI == EPI_STATS) {
         const int ch = mi * 128 + lane_row;
-        const long long p0 = (long long)ni * BN;
+        const long long p0 = (long long)ni * BN + half * HALF;
         const int set = (int)(p0 / p.rows_per_set);
-        float add = p.bias ? p.bias[ch] : 0.f;
+        float add = p.bias ? s_bias[ch] : 0.f;
         if (p.rowvec) add += p.rowvec[(long long)set * p.ldrv + ch];
         float s = 0.f, ss = 0.f;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          float v[32];
-          tmem_ld32(taddr + c0, v);
-          tmem_ld_wait();
+        tmem_foreach32<NCHUNK>(taddr, [&](int c, const float* v) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            float x = v[j] + add;
-            p.out[(p0 + c0 + j) * p.ldo + ch] = x;  // 32 lanes -> 32 consecutive channels: 128 B
+            const float x = v[j] + add;
+            if (EPI == EPI_RAW_STATS) p.out[(p0 + c * 32 + j) * p.ldo + ch] = x;  // 32 lanes -> 32 channels: 128 B
             s += x;
             ss = fmaf(x, x, ss);
           }
-        }
+        });
         s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
         s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
         if ((lane & 7) == 0) {
-          long long o = ((long long)ni * p.stats_ld + p.stats_goff + (ch >> 3)) * 2;
+          long long o = (((long long)ni * 2 + half) * p.stats_ld + p.stats_goff + (ch >> 3)) * 2;
           p.stats[o] = s;
           p.stats[o + 1] = ss;
         }
-      } else {  // EPI_SPLIT: lane = point row, columns = channels
+      } else {  // PT_ON_LANES epilogues: lane = point row, columns = channels
         const long long row = (long long)mi * 128 + lane_row;
-        const int n0 = ni * BN;
-#pragma unroll 1
-        for (int c0 = 0; c0 < BN; c0 += 32) {
-          float v[32];
-          tmem_ld32(taddr + c0, v);
-          tmem_ld_wait();
-          uint32_t hi[16], lo[16];
+        const int n0 = ni * BN + half * HALF;
+        const int set = (mi * 128) / p.rows_per_set;
+        tmem_foreach32<NCHUNK>(taddr, [&](int c, const float* v) {
+          const int col = n0 + c * 32;
+          float x[32];
+          if (EPI == EPI_GN_SPLIT) {
+            const float4* sc4 = reinterpret_cast<const float4*>(p.gn_scale + (long long)set * p.ldgn + col);
+            const float4* sh4 = reinterpret_cast<const float4*>(p.gn_shift + (long long)set * p.ldgn + col);
 #pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            float x0 = v[j] + __ldg(p.bias + n0 + c0 + j);
-            float x1 = v[j + 1] + __ldg(p.bias + n0 + c0 + j + 1);
-            if (p.relu) { x0 = fmaxf(x0, 0.f); x1 = fmaxf(x1, 0.f); }
-            __nv_bfloat16 h0, l0, h1, l1;
-            split_bf16(x0, h0, l0);
-            split_bf16(x1, h1, l1);
-            hi[j >> 1] = pack_bf16(h0, h1);
-            lo[j >> 1] = pack_bf16(l0, l1);
+            for (int j = 0; j < 8; ++j) {  // all lanes read the same address: one broadcast transaction
+              const float4 a = __ldg(sc4 + j), b = __ldg(sh4 + j);
+              x[4 * j + 0] = gelu_fast(fmaf(v[4 * j + 0], a.x, b.x));
+              x[4 * j + 1] = gelu_fast(fmaf(v[4 * j + 1], a.y, b.y));
+              x[4 * j + 2] = gelu_fast(fmaf(v[4 * j + 2], a.z, b.z));
+              x[4 * j + 3] = gelu_fast(fmaf(v[4 * j + 3], a.w, b.w));
+            }
+          } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) {
+              float y = v[j];
+              if (p.bias) y += s_bias[col + j];
+              if (p.relu) y = fmaxf(y, 0.f);
+              x[j] = y;
+            }
           }
-          uint4* dh = reinterpret_cast<uint4*>(p.out_hi + row * p.ldo16 + n0 + c0);
+          store_split32<NPROD>(x, p.out_hi + row * p.ldo16 + col, p.out_lo + row * p.ldo16 + col);
+          if (EPI == EPI_SPLIT_MAX) {
+            // column max over the warp's 32 rows: butterfly that halves the live columns each step;
+            // afterwards x[0] of lane l is the max of column col + l
 #pragma unroll
-          for (int q = 0; q < 4; ++q) dh[q] = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
-          if (NPROD == 3) {
-            uint4* dl = reinterpret_cast<uint4*>(p.out_lo + row * p.ldo16 + n0 + c0);
+            for (int w = 16; w >= 1; w >>= 1) {
+              const bool upper = (lane & w) != 0;
 #pragma unroll
-            for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+              for (int j = 0; j < w; ++j) {
+                const float mine = upper ? x[j + w] : x[j];
+                const float give = upper ? x[j] : x[j + w];
+                x[j] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, give, w));
+              }
+            }
+            atomicMax(p.gmax + (long long)set * p.C + col + lane, f2key(x[0]));
           }
-        }
+        });
       }
       tc_fence_before();
       __syncwarp();
