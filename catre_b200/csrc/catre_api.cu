@@ -206,7 +206,7 @@ int check_launch(catre_engine* e, const char* what) {
 GemmP gemm_args(const float* A, int lda, const float* W, int K, int C, const float* bias, float* out, int ldo,
                 long long R, int relu) {
   GemmP p{};
-  p.A = A; p.lda = lda; p.W = W; p.wcs = K; p.wks = 1; p.w_set_stride = 0;
+  p.A = A; p.lda = lda; p.W = W; p.wcs = K; p.w_set_stride = 0;
   p.bias = bias; p.rowvec = nullptr; p.ldrv = 0; p.out = out; p.ldo = ldo; p.gmax = nullptr; p.stats = nullptr;
   p.stats_ld = 0; p.stats_goff = 0;
   p.gn_scale = p.gn_shift = nullptr; p.ldgn = 0;
@@ -507,7 +507,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p.rot_partial = e->rot_partial; p.rot_tiles = P / 128; p.convp_bias = e->convp_b;
     p.pose_in = pose_in; p.scale_in = scale_in; p.K = K; p.pose_out = pose_out; p.scale_out = scale_out;
     Launch l(e, s, G_TS_POSE);
-    ts_pose_kernel<<<B, 256, 0, s>>>(p);
+    ts_pose_kernel<<<B, 1024, 0, s>>>(p);
   }
   return check_launch(e, "ts_pose");
 }

@@ -137,7 +137,7 @@ enum { A_PLAIN = 0, A_KEY = 1, A_GN_GELU = 2, A_PARTIAL = 3 };
 
 struct GemmP {
   const float* A; int lda;
-  const float* W; int wcs, wks; long long w_set_stride;
+  const float* W; int wcs; long long w_set_stride;  // W[c][k] at W[c * wcs + k] (+ set * w_set_stride)
   const float* bias;
   const float* rowvec; int ldrv;
   float* out; int ldo;
@@ -178,8 +178,12 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
 
   const int kz = (p.ksplit > 1) ? p.K / p.ksplit : p.K;
   const int k_begin = (p.ksplit > 1) ? blockIdx.z * kz : 0;
-  for (int k0 = k_begin; k0 < k_begin + kz; k0 += BK) {
-    // ---- A tile: 128 rows x 16 k, float4 along k
+  const int k_end = k_begin + kz;
+
+  // global -> registers for one K chunk (A: 128 rows x 16 k, W: BN channels x 16 k; float4 along k).  The
+  // loads of chunk i+1 are issued before the FMAs of chunk i, so their latency hides behind the math.
+  float4 areg[2], wreg[BN / 64];
+  auto load_chunk = [&](int k0) {
 #pragma unroll
     for (int it = 0; it < 2; ++it) {
       int e = tid + it * 256;  // 0..511
@@ -192,6 +196,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
           v = make_float4(key2f(kv.x), key2f(kv.y), key2f(kv.z), key2f(kv.w));
         } else if (AMODE == A_PARTIAL) {
           v = *reinterpret_cast<const float4*>(p.a_bias + k0 + kq);
+#pragma unroll 8
           for (int z = 0; z < p.a_nparts; ++z) {
             const float4 t = *reinterpret_cast<const float4*>(src + (long long)z * p.a_part_stride);
             v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
@@ -209,29 +214,34 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
           }
         }
       }
-      As[kq + 0][row] = v.x; As[kq + 1][row] = v.y; As[kq + 2][row] = v.z; As[kq + 3][row] = v.w;
+      areg[it] = v;
     }
-    // ---- W tile: BN channels x 16 k
-    if (p.wks == 1) {
 #pragma unroll
-      for (int it = 0; it < BN / 64; ++it) {
-        int e = tid + it * 256;
-        int col = e >> 2, kq = (e & 3) * 4;
-        float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-        if (c0 + col < p.C) v = *reinterpret_cast<const float4*>(Wb + (long long)(c0 + col) * p.wcs + k0 + kq);
-        Ws[kq + 0][col] = v.x; Ws[kq + 1][col] = v.y; Ws[kq + 2][col] = v.z; Ws[kq + 3][col] = v.w;
-      }
-    } else {
+    for (int it = 0; it < BN / 64; ++it) {
+      int e = tid + it * 256;
+      int col = e >> 2, kq = (e & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + col < p.C) v = *reinterpret_cast<const float4*>(Wb + (long long)(c0 + col) * p.wcs + k0 + kq);
+      wreg[it] = v;
+    }
+  };
+
+  load_chunk(k_begin);
+  for (int k0 = k_begin; k0 < k_end; k0 += BK) {
 #pragma unroll
-      for (int it = 0; it < BN / 16; ++it) {
-        int e = tid + it * 256;
-        int col = e % BN, kk = e / BN;
-        float v = 0.f;
-        if (c0 + col < p.C) v = Wb[(long long)(c0 + col) * p.wcs + (long long)(k0 + kk) * p.wks];
-        Ws[kk][col] = v;
-      }
+    for (int it = 0; it < 2; ++it) {
+      int e = tid + it * 256;
+      int row = e >> 2, kq = (e & 3) * 4;
+      As[kq + 0][row] = areg[it].x; As[kq + 1][row] = areg[it].y; As[kq + 2][row] = areg[it].z; As[kq + 3][row] = areg[it].w;
+    }
+#pragma unroll
+    for (int it = 0; it < BN / 64; ++it) {
+      int e = tid + it * 256;
+      int col = e >> 2, kq = (e & 3) * 4;
+      Ws[kq + 0][col] = wreg[it].x; Ws[kq + 1][col] = wreg[it].y; Ws[kq + 2][col] = wreg[it].z; Ws[kq + 3][col] = wreg[it].w;
     }
     __syncthreads();
+    if (k0 + BK < k_end) load_chunk(k0 + BK);
 #pragma unroll
     for (int kk = 0; kk < BK; ++kk) {
       float a[8], w[TN];
@@ -569,50 +579,62 @@ __device__ __forceinline__ float gn8_gelu(float v, float gamma, float beta) {
   return gelu_exact(d * rstd * gamma + beta);
 }
 
-__global__ void __launch_bounds__(256) ts_pose_kernel(TsPoseP p) {
-  const int b = blockIdx.x, t = threadIdx.x;
-  __shared__ float feat[1091 + 5];
+__global__ void __launch_bounds__(1024) ts_pose_kernel(TsPoseP p) {
+  // 1024 threads: thread (kq, t) accumulates output channel t over the kq-th quarter of K, so four times
+  // as many weight loads are in flight per SM; the quarters are summed through shared memory.
+  const int b = blockIdx.x, t = threadIdx.x & 255, kq = threadIdx.x >> 8;
+  __shared__ float feat[1092];
   __shared__ float h[256];
+  __shared__ float part[4][256];
   __shared__ float outv[6];
   const float* sc_in = p.scale_in + (long long)b * 3;
-  for (int i = t; i < 1024; i += 256) feat[i] = key2f(p.gmax_g[(long long)(2 * b) * 1024 + i]);
-  if (t < 64) feat[1024 + t] = key2f(p.gmax_pf[(long long)(2 * b) * 64 + t]);
-  if (t < 3) feat[1088 + t] = sc_in[t];
+  for (int i = threadIdx.x; i < 1024; i += 1024) feat[i] = key2f(p.gmax_g[(long long)(2 * b) * 1024 + i]);
+  if (threadIdx.x < 64) feat[1024 + threadIdx.x] = key2f(p.gmax_pf[(long long)(2 * b) * 64 + threadIdx.x]);
+  if (threadIdx.x >= 64 && threadIdx.x < 67) feat[1088 + threadIdx.x - 64] = sc_in[threadIdx.x - 64];
+  if (threadIdx.x == 67) feat[1091] = 0.f;
   __syncthreads();
-  float a;
   {
-    float a0 = p.b0[t], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-#pragma unroll 4
-    for (int k = 0; k < 1088; k += 4) {
+    const int kb = kq * 273, ke = kb + 273 < 1091 ? kb + 273 : 1091;  // 4 x 273 = 1092 >= 1091
+    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+    int k = kb;
+#pragma unroll 2
+    for (; k + 4 <= ke; k += 4) {
       a0 = fmaf(p.w0t[(k + 0) * 256 + t], feat[k + 0], a0);
       a1 = fmaf(p.w0t[(k + 1) * 256 + t], feat[k + 1], a1);
       a2 = fmaf(p.w0t[(k + 2) * 256 + t], feat[k + 2], a2);
       a3 = fmaf(p.w0t[(k + 3) * 256 + t], feat[k + 3], a3);
     }
-    a0 = fmaf(p.w0t[1088 * 256 + t], feat[1088], a0);
-    a1 = fmaf(p.w0t[1089 * 256 + t], feat[1089], a1);
-    a2 = fmaf(p.w0t[1090 * 256 + t], feat[1090], a2);
-    a = (a0 + a1) + (a2 + a3);
+    for (; k < ke; ++k) a0 = fmaf(p.w0t[k * 256 + t], feat[k], a0);
+    part[kq][t] = (a0 + a1) + (a2 + a3);
   }
-  a = gn8_gelu(a, p.g0[t], p.be0[t]);
-  h[t] = a;
   __syncthreads();
-  float a2;
+  if (kq == 0) {
+    float a = p.b0[t] + ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t]));
+    h[t] = gn8_gelu(a, p.g0[t], p.be0[t]);
+  }
+  __syncthreads();
   {
-    float c0 = p.b1[t], c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    const int kb = kq * 64;
+    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
 #pragma unroll 4
-    for (int k = 0; k < 256; k += 4) {
+    for (int k = kb; k < kb + 64; k += 4) {
       c0 = fmaf(p.w1t[(k + 0) * 256 + t], h[k + 0], c0);
       c1 = fmaf(p.w1t[(k + 1) * 256 + t], h[k + 1], c1);
       c2 = fmaf(p.w1t[(k + 2) * 256 + t], h[k + 2], c2);
       c3 = fmaf(p.w1t[(k + 3) * 256 + t], h[k + 3], c3);
     }
-    a2 = (c0 + c1) + (c2 + c3);
+    part[kq][t] = (c0 + c1) + (c2 + c3);
   }
-  a2 = gn8_gelu(a2, p.g1[t], p.be1[t]);
   __syncthreads();
-  h[t] = a2;
+  float a2 = 0.f;
+  if (kq == 0) {
+    a2 = p.b1[t] + ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t]));
+    a2 = gn8_gelu(a2, p.g1[t], p.be1[t]);
+  }
   __syncthreads();
+  if (kq == 0) h[t] = a2;
+  __syncthreads();
+  if (threadIdx.x >= 256) return;
   // fc_t (3) and fc_s (3): warp w < 6 computes one output
   int warp = t >> 5, lane = t & 31;
   if (warp < 6) {

@@ -23,8 +23,14 @@
 
 namespace catre {
 
-constexpr int TC_EPI_WARPS = 8;                    // two per TMEM lane quadrant: each takes half of the columns
-constexpr int TC_THREADS = 64 + 32 * TC_EPI_WARPS;  // + TMA warp + MMA warp
+// epilogue warps: EW / 4 per TMEM lane quadrant, each takes BN / (EW / 4) of the columns.  The
+// channel-on-lanes epilogues (MMA-bound layers) use 8; the point-on-lanes epilogues, which are pure
+// CUDA-core work (bias/ReLU or GroupNorm+GELU, bf16 split, stores), use 16 when the tile is wide enough.
+template <int ORIENT, int BN>
+struct TcEpi {
+  static constexpr int EW = (ORIENT == 1 && BN >= 128) ? 16 : 8;
+  static constexpr int THREADS = 64 + 32 * EW;  // + TMA warp + MMA warp
+};
 constexpr int TC_BK = 64;  // K slab = one 128-byte swizzle atom of bf16
 enum { CH_ON_LANES = 0, PT_ON_LANES = 1 };
 // epilogues:            orientation   what leaves the kernel
@@ -127,8 +133,18 @@ __device__ __forceinline__ void tmem_ld_wait32(float* v) {
 }
 // visit NCHUNK consecutive 32-column chunks of this warp's TMEM lanes; the load of chunk c+1 is in
 // flight while f(c, values) runs (two register buffers)
-template <int NCHUNK, typename F>
+template <int NCHUNK, bool PIPE, typename F>
 __device__ __forceinline__ void tmem_foreach32(uint32_t taddr, F&& f) {
+  if (!PIPE) {  // many resident warps hide the load latency; keep the register footprint small
+#pragma unroll
+    for (int c = 0; c < NCHUNK; ++c) {
+      float v[32];
+      tmem_ld32(taddr + c * 32, v);
+      tmem_ld_wait32(v);
+      f(c, v);
+    }
+    return;
+  }
   float va[32], vb[32];
   tmem_ld32(taddr, va);
 #pragma unroll
@@ -165,6 +181,18 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bflo
   hi = __float2bfloat16_rn(x);
   lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
+// two floats -> packed bf16 hi pair and packed bf16 residual pair (element 0 in the low half)
+__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(x1), "f"(x0));
+  const float r0 = x0 - __uint_as_float(hi2 << 16);
+  const float r1 = x1 - __uint_as_float(hi2 & 0xffff0000u);
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(r1), "f"(r0));
+}
+__device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* v) {
+  asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
+               "r"(v[3]), "r"(v[4]), "r"(v[5]), "r"(v[6]), "r"(v[7])
+               : "memory");
+}
 __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) {
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
@@ -198,39 +226,35 @@ struct TcCfg {
   static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;  // + barriers + 1024 B alignment slack
 };
 
-// 32 columns of one point row: fp32 -> bf16 hi/lo, 16-byte stores
+// 32 columns of one point row: fp32 -> bf16 hi/lo, written as full 32-byte sectors (st.global.v8)
 template <int NPROD>
 __device__ __forceinline__ void store_split32(const float* x, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo) {
   uint32_t hi[16], lo[16];
 #pragma unroll
-  for (int j = 0; j < 32; j += 2) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(x[j], h0, l0);
-    split_bf16(x[j + 1], h1, l1);
-    hi[j >> 1] = pack_bf16(h0, h1);
-    lo[j >> 1] = pack_bf16(l0, l1);
-  }
-  uint4* dh = reinterpret_cast<uint4*>(dst_hi);
-#pragma unroll
-  for (int q = 0; q < 4; ++q) dh[q] = make_uint4(hi[q * 4], hi[q * 4 + 1], hi[q * 4 + 2], hi[q * 4 + 3]);
+  for (int j = 0; j < 32; j += 2) split_bf16x2(x[j], x[j + 1], hi[j >> 1], lo[j >> 1]);
+  st_global_256(dst_hi, hi);
+  st_global_256(dst_hi + 16, hi + 8);
   if (NPROD == 3) {
-    uint4* dl = reinterpret_cast<uint4*>(dst_lo);
-#pragma unroll
-    for (int q = 0; q < 4; ++q) dl[q] = make_uint4(lo[q * 4], lo[q * 4 + 1], lo[q * 4 + 2], lo[q * 4 + 3]);
+    st_global_256(dst_lo, lo);
+    st_global_256(dst_lo + 16, lo + 8);
   }
 }
 
 template <int ORIENT, int EPI, int BN, int NPROD>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+__global__ void __launch_bounds__(TcEpi<ORIENT, BN>::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant__ CUtensorMap ma_lo,
                const __grid_constant__ CUtensorMap nb_hi, const __grid_constant__ CUtensorMap nb_lo, const TcGemmP p) {
   using Cfg = TcCfg<BN, NPROD>;
   constexpr int STAGES = Cfg::STAGES;
-  constexpr int HALF = BN / 2;       // columns per epilogue warp
-  constexpr int NCHUNK = HALF / 32;  // 32-column chunks per epilogue warp
+  constexpr int EW = TcEpi<ORIENT, BN>::EW, TC_THREADS = TcEpi<ORIENT, BN>::THREADS;
+  constexpr int PARTS = EW / 4;        // epilogue warps per TMEM lane quadrant
+  constexpr int HALF = BN / PARTS;     // columns per epilogue warp
+  constexpr int NCHUNK = HALF / 32;    // 32-column chunks per epilogue warp
+  constexpr bool PIPE = (EW == 8);
+  static_assert(HALF % 32 == 0, "each epilogue warp needs whole 32-column chunks");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128 or 256");
   extern __shared__ uint8_t smem_raw[];
-  __shared__ float s_bias[1024];
+  __shared__ __align__(16) float s_bias[1024];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t tiles_base = (smem_base + 1024 + 1023) & ~1023u;  // barriers live in the first 1 KB
   // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base pointer
@@ -247,7 +271,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
     prefetch_tmap(&ma_hi); prefetch_tmap(&nb_hi);
     if (NPROD == 3) { prefetch_tmap(&ma_lo); prefetch_tmap(&nb_lo); }
     for (int i = 0; i < STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, TC_EPI_WARPS); }
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, EW); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -333,7 +357,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
       if (EPI == EPI_MAX) {
         const int ch = mi * 128 + lane_row;
         float m = -INFINITY;
-        tmem_foreach32<NCHUNK>(taddr, [&](int, const float* v) {
+        tmem_foreach32<NCHUNK, PIPE>(taddr, [&](int, const float* v) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) m = fmaxf(m, v[j]);
         });
@@ -348,7 +372,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         float add = p.bias ? s_bias[ch] : 0.f;
         if (p.rowvec) add += p.rowvec[(long long)set * p.ldrv + ch];
         float s = 0.f, ss = 0.f;
-        tmem_foreach32<NCHUNK>(taddr, [&](int c, const float* v) {
+        tmem_foreach32<NCHUNK, PIPE>(taddr, [&](int c, const float* v) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
             const float x = v[j] + add;
@@ -361,7 +385,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
         s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
         if ((lane & 7) == 0) {
-          long long o = (((long long)ni * 2 + half) * p.stats_ld + p.stats_goff + (ch >> 3)) * 2;
+          long long o = (((long long)ni * PARTS + half) * p.stats_ld + p.stats_goff + (ch >> 3)) * 2;
           p.stats[o] = s;
           p.stats[o + 1] = ss;
         }
@@ -369,7 +393,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         const long long row = (long long)mi * 128 + lane_row;
         const int n0 = ni * BN + half * HALF;
         const int set = (mi * 128) / p.rows_per_set;
-        tmem_foreach32<NCHUNK>(taddr, [&](int c, const float* v) {
+        tmem_foreach32<NCHUNK, PIPE>(taddr, [&](int c, const float* v) {
           const int col = n0 + c * 32;
           float x[32];
           if (EPI == EPI_GN_SPLIT) {
@@ -385,11 +409,15 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
             }
           } else {
 #pragma unroll
-            for (int j = 0; j < 32; ++j) {
-              float y = v[j];
-              if (p.bias) y += s_bias[col + j];
-              if (p.relu) y = fmaxf(y, 0.f);
-              x[j] = y;
+            for (int j = 0; j < 32; j += 4) {
+              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (p.bias) b4 = *reinterpret_cast<const float4*>(s_bias + col + j);  // broadcast LDS.128
+              x[j + 0] = v[j + 0] + b4.x; x[j + 1] = v[j + 1] + b4.y;
+              x[j + 2] = v[j + 2] + b4.z; x[j + 3] = v[j + 3] + b4.w;
+            }
+            if (p.relu) {
+#pragma unroll
+              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
             }
           }
           store_split32<NPROD>(x, p.out_hi + row * p.ldo16 + col, p.out_lo + row * p.ldo16 + col);
@@ -558,7 +586,7 @@ cudaError_t tc_launch(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const 
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < num_sms ? tiles : num_sms;
   if (grid < 1) return cudaSuccess;
-  kern<<<grid, TC_THREADS, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, nb_hi, nb_lo, p);
+  kern<<<grid, TcEpi<ORIENT, BN>::THREADS, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, nb_hi, nb_lo, p);
   return cudaPeekAtLastError();
 }
 
