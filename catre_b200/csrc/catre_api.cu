@@ -4,6 +4,7 @@
 #include <math.h>
 #include <stdarg.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <map>
@@ -13,6 +14,7 @@
 #include "../../include/catre_b200.h"
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
+#include "tc_fused.cuh"
 
 using namespace catre;
 
@@ -72,12 +74,12 @@ constexpr int kNumWeights = sizeof(kWeights) / sizeof(kWeights[0]);
 enum Grp {
   G_FILL, G_UPDATE_POINTS, G_FRONT3, G_STN_CONV2, G_STN_CONV3_MAX, G_TNET_FC, G_FSTN_CONV1, G_FSTN_CONV2,
   G_FSTN_CONV3_MAX, G_FEAT_TRANSFORM, G_CONV2, G_CONV3, G_CONV4_MAX, G_ROT_GFEAT, G_ROT_LAYER0, G_GN_FINALIZE,
-  G_ROT_LAYER1, G_ROT_TAIL, G_TS_POSE, G_SPLIT, G_SUM_PARTS, G_ROT_LAYER0_APPLY, G_NUM
+  G_ROT_LAYER1, G_ROT_TAIL, G_TS_POSE, G_SPLIT, G_SUM_PARTS, G_ROT_LAYER0_APPLY, G_ROT_FUSED, G_NUM
 };
 const char* kGrpNames[G_NUM] = {
     "fill", "update_points", "front3", "stn_conv2", "stn_conv3_max", "tnet_fc", "fstn_conv1", "fstn_conv2",
     "fstn_conv3_max", "feat_transform", "conv2", "conv3", "conv4_max", "rot_gfeat", "rot_layer0", "gn_finalize",
-    "rot_layer1", "rot_tail", "ts_pose", "split_bf16", "sum_parts", "rot_layer0_apply"};
+    "rot_layer1", "rot_tail", "ts_pose", "split_bf16", "sum_parts", "rot_layer0_apply", "rot_fused"};
 
 }  // namespace
 
@@ -99,7 +101,9 @@ struct catre_engine {
   float *ts_w0t = nullptr, *ts_w1t = nullptr;
   // bf16 hi/lo weight copies + tensor maps (tensor-core modes); "MA" maps have 128-row boxes (M side of
   // the MMA), "NB" maps have BN-row boxes (N side)
-  TcPair tw_stn_c2, tw_stn_c3, tw_fstn_c1, tw_fstn_c2, tw_fstn_c3, tw_conv2, tw_conv3, tw_conv4, tw_rot0, tw_rot1[2];
+  TcPair tw_stn_c2, tw_stn_c3, tw_fstn_c1, tw_fstn_c2, tw_fstn_c3, tw_conv2, tw_conv3, tw_conv4, tw_rot0;
+  TcPair tw_rot1s;            // both heads' layers.3 weights stacked [512, 256] (fused rot kernel)
+  long long* rf_dbg = nullptr;  // timeline buffer of the fused rot kernel (CATRE_RF_DEBUG=1)
   CUtensorMap tw_rot0_nb[2];  // rot layer-0 point-feature weights [512, 64] as an N-side operand (256-row boxes)
   float *fstn_fc3_wT = nullptr;  // fstn.fc3 rows permuted so the FC emits T64^T (row j = output channel j of pf = h1 . T64)
   int num_sms = 148;
@@ -108,11 +112,12 @@ struct catre_engine {
   float *q = nullptr, *h64a = nullptr, *h64b = nullptr, *h128 = nullptr, *h512 = nullptr, *a0 = nullptr, *a1 = nullptr;
   int *gmax_all = nullptr, *gmax_stn = nullptr, *gmax_fstn = nullptr, *gmax_g = nullptr, *gmax_pf = nullptr;
   float *fc512 = nullptr, *fc256 = nullptr, *fc3p = nullptr, *csetp = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
+  CUtensorMap a1t_map;  // fp16 a1T [maxB*512, P] for the fused rot kernel's TMA stores (64-point x 128-channel boxes)
   TcPair t64s;  // tensor-core modes: bf16 hi/lo of T64^T, [S*64, 64]
   float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
   // bf16 hi/lo activations of the tensor-core path and their tensor maps
-  TcPair x64, f64, a128, pf16, a512, u512;                 // .map_* = MA view (128-row boxes)
-  CUtensorMap a128_nb[2], pf_nb[2], a512_nb[2], u_nb[2][2];  // NB views (256-row boxes): [hi, lo]
+  TcPair x64, f64, a128, pf16, a512;               // .map_* = MA view (128-row boxes)
+  CUtensorMap a128_nb[2], pf_nb[2], a512_nb[2];   // NB views (256-row boxes): [hi, lo]
   size_t ws_bytes = 0;
   // staging for catre_refine_host
   float *st_pcl = nullptr, *st_prior = nullptr, *st_pose = nullptr, *st_scale = nullptr, *st_K = nullptr;
@@ -442,20 +447,25 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
                                                                  gn0_shift, B, 512, P / 128, P);
     }
     if ((rc = check_launch(e, "gn_finalize_set"))) return rc;
-    // pass 2: recompute a0 and apply GroupNorm + GELU + bf16 hi/lo split in the epilogue -> operand of layer 1
-    TcGemmP pa{};
-    pa.K = 64; pa.m_tiles = (int)(R / 128); pa.n_tiles = 2; pa.rows_per_set = N;
-    pa.gn_scale = gn0_scale; pa.gn_shift = gn0_shift; pa.ldgn = 512;
-    pa.out_hi = e->u512.hi; pa.out_lo = e->u512.lo; pa.ldo16 = 512;
-    if ((rc = tc_run<PT_ON_LANES, EPI_GN_SPLIT, 256>(e, s, G_ROT_LAYER0_APPLY, e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0_nb[0],
-                                                     e->tw_rot0_nb[1], pa))) return rc;
-    for (int h = 0; h < 2; ++h) {
-      TcGemmP p1{};
-      p1.K = 256; p1.m_tiles = 2; p1.n_tiles = (int)(R / 256);
-      p1.bias = e->rot_b1 + h * 256; p1.rows_per_set = N; p1.out = e->a1 + h * 256; p1.ldo = 512;
-      p1.stats = e->stats1; p1.stats_ld = 64; p1.stats_goff = 32 * h;
-      if ((rc = tc_run<CH_ON_LANES, EPI_RAW_STATS, 256>(e, s, G_ROT_LAYER1, e->tw_rot1[h].map_hi, e->tw_rot1[h].map_lo,
-                                                        e->u_nb[h][0], e->u_nb[h][1], p1))) return rc;
+    {
+      // layer-0 recompute + GroupNorm + GELU + bf16 split into shared memory + layer 1, one kernel
+      RotFusedP pf{};
+      pf.tiles = (int)(R / 128); pf.rows_per_set = N; pf.rows_per_obj = P;
+      pf.gn_scale = gn0_scale; pf.gn_shift = gn0_shift; pf.bias1 = e->rot_b1; pf.stats = e->stats1; pf.dbg = e->rf_dbg;
+      cudaError_t st;
+      {
+        Launch l(e, s, G_ROT_FUSED);
+        if (e->cfg.precision == CATRE_PREC_BF16)
+          st = rot_fused_launch<1>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0_nb[0], e->tw_rot0_nb[1], e->tw_rot1s.map_hi,
+                                   e->tw_rot1s.map_lo, e->a1t_map, pf, e->num_sms, s);
+        else
+          st = rot_fused_launch<3>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0_nb[0], e->tw_rot0_nb[1], e->tw_rot1s.map_hi,
+                                   e->tw_rot1s.map_lo, e->a1t_map, pf, e->num_sms, s);
+      }
+      if (st != cudaSuccess) {
+        cudaGetLastError();
+        return fail(e, CATRE_ERR_CUDA, "launch of rot_fused failed: %s", cudaGetErrorString(st));
+      }
     }
   } else {
     GemmP p = gemm_args(e->h64b, 64, e->rot_w0p, 64, 512, nullptr, e->a0, 512, R, 0);
@@ -480,14 +490,15 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   {
     Launch l(e, s, G_GN_FINALIZE);
     gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats1, e->rot_gn1_g, e->rot_gn1_b, e->gn1,
-                                                           e->gn1 + (size_t)e->maxB * 512, B, 512, P / 128, P);
+                                                           e->gn1 + (size_t)e->maxB * 512, B, 512,
+                                                           tc ? P / 64 : P / 128, P);
   }
   if ((rc = check_launch(e, "gn_finalize"))) return rc;
   {
     Launch l(e, s, G_ROT_TAIL);
     if (tc)
-      rot_tail_kernel<1><<<dim3(P / 128, B), 256, 0, s>>>(e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
-                                                         e->wp, e->rot_partial, P);
+      rot_tail_t_kernel<<<dim3(16, B), 256, P * sizeof(float), s>>>(reinterpret_cast<const __half*>(e->a1), e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
+                                                                   e->neck_b, e->wp, e->rot_partial, P);
     else
       rot_tail_kernel<0><<<dim3(P / 128, B), 256, 0, s>>>(e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
                                                          e->wp, e->rot_partial, P);
@@ -504,7 +515,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p.be1 = W(e, "ts_head.linears.4.bias");
     p.wt = W(e, "ts_head.fc_t.weight"); p.bt = W(e, "ts_head.fc_t.bias");
     p.ws = W(e, "ts_head.fc_s.weight"); p.bs = W(e, "ts_head.fc_s.bias");
-    p.rot_partial = e->rot_partial; p.rot_tiles = P / 128; p.convp_bias = e->convp_b;
+    p.rot_partial = e->rot_partial; p.rot_tiles = tc ? 16 : P / 128; p.convp_bias = e->convp_b;
     p.pose_in = pose_in; p.scale_in = scale_in; p.K = K; p.pose_out = pose_out; p.scale_out = scale_out;
     Launch l(e, s, G_TS_POSE);
     ts_pose_kernel<<<B, 1024, 0, s>>>(p);
@@ -572,7 +583,7 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
     rc |= dalloc(e, &e->a0, R * 512);
     rc |= dalloc(e, &e->t64, S * 4096);
   }
-  rc |= dalloc(e, &e->a1, R * 512);
+  rc |= dalloc(e, &e->a1, tc ? R * 256 : R * 512);  // tensor-core modes: fp16 a1T [B][512][P]
   rc |= dalloc(e, &e->gmax_all, S * (1024 * 3 + 64));
   e->gmax_stn = e->gmax_all;
   e->gmax_fstn = e->gmax_all + S * 1024;
@@ -585,10 +596,10 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   rc |= dalloc(e, &e->t3, S * 9 + 7);
   rc |= dalloc(e, &e->cset, S * 512);
   rc |= dalloc(e, &e->stats0, (R / 128) * 64 * 2);
-  rc |= dalloc(e, &e->stats1, (R / 128) * 64 * 2);
+  rc |= dalloc(e, &e->stats1, (R / 64) * 64 * 2);  // the fused rot kernel emits partials per 64 points
   rc |= dalloc(e, &e->gn0, B * 2048);  // scale | shift, per set in the tensor-core modes
   rc |= dalloc(e, &e->gn1, B * 512 * 2);
-  rc |= dalloc(e, &e->rot_partial, B * (P / 128) * 6);
+  rc |= dalloc(e, &e->rot_partial, B * (P / 128 > 16 ? P / 128 : 16) * 6);
   rc |= dalloc(e, &e->st_pcl, B * N * 3);
   rc |= dalloc(e, &e->st_prior, B * N * 3);
   rc |= dalloc(e, &e->st_pose, B * 12);
@@ -597,6 +608,10 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   rc |= dalloc(e, &e->st_oposes, B * 12 * (catre_engine::kMaxHostIter + 1));
   rc |= dalloc(e, &e->st_oscales, B * 3 * (catre_engine::kMaxHostIter + 1));
   e->num_sms = prop.multiProcessorCount;
+  {
+    const char* dbg = getenv("CATRE_RF_DEBUG");
+    if (dbg && dbg[0] == '1') rc |= dalloc(e, &e->rf_dbg, 8 * 32);
+  }
   if (!rc && tc) {
     auto pair = [&](TcPair& t, size_t cols) {
       rc |= dalloc(e, &t.hi, R * cols);
@@ -604,7 +619,8 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
       if (rc) return;
       if (!tc_make_map(&t.map_hi, t.hi, R, cols, cols, 128) || !tc_make_map(&t.map_lo, t.lo, R, cols, cols, 128)) rc |= 2;
     };
-    pair(e->x64, 64); pair(e->f64, 64); pair(e->a128, 128); pair(e->pf16, 64); pair(e->a512, 512); pair(e->u512, 512);
+    pair(e->x64, 64); pair(e->f64, 64); pair(e->a128, 128); pair(e->pf16, 64); pair(e->a512, 512);
+    if (!rc && !tc_make_map_f16(&e->a1t_map, e->a1, B * 512, P, 64, 128)) rc |= 2;
     if (!rc) {  // T64^T per set, the N-side operand of the feature transform: [S*64, 64], 64-row boxes
       rc |= dalloc(e, &e->t64s.hi, S * 4096);
       rc |= dalloc(e, &e->t64s.lo, S * 4096);
@@ -616,9 +632,6 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
       ok &= tc_make_map(&e->a128_nb[0], e->a128.hi, R, 128, 128, 256) && tc_make_map(&e->a128_nb[1], e->a128.lo, R, 128, 128, 256);
       ok &= tc_make_map(&e->pf_nb[0], e->pf16.hi, R, 64, 64, 256) && tc_make_map(&e->pf_nb[1], e->pf16.lo, R, 64, 64, 256);
       ok &= tc_make_map(&e->a512_nb[0], e->a512.hi, R, 512, 512, 256) && tc_make_map(&e->a512_nb[1], e->a512.lo, R, 512, 512, 256);
-      for (int h = 0; h < 2; ++h)
-        ok &= tc_make_map(&e->u_nb[h][0], e->u512.hi + h * 256, R, 256, 512, 256) &&
-              tc_make_map(&e->u_nb[h][1], e->u512.lo + h * 256, R, 256, 512, 256);
       if (!ok) rc |= 2;
     }
     if (rc & 2) e->err = "cuTensorMapEncodeTiled failed for an activation buffer";
@@ -764,8 +777,12 @@ int catre_pack(catre_engine* e, void* stream) {
     if (!r2 && (!tc_make_map(&e->tw_rot0_nb[0], e->tw_rot0.hi, 512, 64, 64, 256) ||
                 !tc_make_map(&e->tw_rot0_nb[1], e->tw_rot0.lo, 512, 64, 64, 256)))
       r2 = fail(e, CATRE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the rot layer-0 N-side view");
-    r2 = r2 ? r2 : wpair(e->tw_rot1[0], H("rot_head.rot_head_x.layers.3.weight"), 256, 256, 128);
-    r2 = r2 ? r2 : wpair(e->tw_rot1[1], H("rot_head.rot_head_y.layers.3.weight"), 256, 256, 128);
+    {
+      std::vector<float> w1s = H("rot_head.rot_head_x.layers.3.weight");
+      const std::vector<float>& w1y = H("rot_head.rot_head_y.layers.3.weight");
+      w1s.insert(w1s.end(), w1y.begin(), w1y.end());
+      r2 = r2 ? r2 : wpair(e->tw_rot1s, w1s, 512, 256, 128);
+    }
     if (r2) return r2;
   }
   CU_TRY(e, cudaDeviceSynchronize());
@@ -880,11 +897,11 @@ int catre_debug_read(catre_engine* e, const char* name, void* dst_host, size_t b
       {"q", e->q}, {"h64a", e->h64a}, {"h64b", e->h64b}, {"h128", e->h128}, {"h512", e->h512}, {"a0", e->a0}, {"a1", e->a1},
       {"gmax_stn", e->gmax_stn}, {"gmax_fstn", e->gmax_fstn}, {"gmax_g", e->gmax_g}, {"gmax_pf", e->gmax_pf},
       {"fc512", e->fc512}, {"fc256", e->fc256}, {"t3", e->t3}, {"t64", e->t64}, {"cset", e->cset},
-      {"t64s_hi", e->t64s.hi}, {"t64s_lo", e->t64s.lo},
+      {"t64s_hi", e->t64s.hi}, {"t64s_lo", e->t64s.lo}, {"rf_dbg", e->rf_dbg},
       {"stats0", e->stats0}, {"stats1", e->stats1}, {"gn0", e->gn0}, {"gn1", e->gn1}, {"rot_partial", e->rot_partial}};
   m["x64_hi"] = e->x64.hi; m["x64_lo"] = e->x64.lo; m["f64_hi"] = e->f64.hi; m["f64_lo"] = e->f64.lo;
   m["a128_hi"] = e->a128.hi; m["a128_lo"] = e->a128.lo; m["pf_hi"] = e->pf16.hi; m["pf_lo"] = e->pf16.lo;
-  m["a512_hi"] = e->a512.hi; m["a512_lo"] = e->a512.lo; m["u_hi"] = e->u512.hi; m["u_lo"] = e->u512.lo;
+  m["a512_hi"] = e->a512.hi; m["a512_lo"] = e->a512.lo;
   auto it = m.find(name);
   if (it == m.end() || it->second == nullptr) return fail(e, CATRE_ERR_INVALID_ARG, "no debug buffer '%s'", name);
   CU_TRY(e, cudaDeviceSynchronize());

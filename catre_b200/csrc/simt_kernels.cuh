@@ -2,6 +2,7 @@
 // narrow / per-object stages of every mode).  Semantics follow SURVEY.md appendix A; each kernel cites
 // the reference lines it restates.  Written for sm_100a; no library calls.
 #pragma once
+#include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
 
@@ -22,20 +23,22 @@ constexpr int KEY_NEG_INF = (int)0x807fffff;  // f2key(-inf)
 // exact GELU (nn.GELU default, lib/torch_utils/layers/layer_utils.py:61-95 "gelu")
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// GELU through the Abramowitz-Stegun 7.1.26 erfc form (|err| of erf <= 1.5e-7; measured max |gelu err|
-// 4.2e-7 vs fp64 over [-12, 12], i.e. below the fp32 erff path's own 1.2e-6), branch-free, no
-// cancellation on the negative side:  1 + erf(x/sqrt2) = w (x < 0) | 2 - w (x >= 0),
-//   w = poly(t) exp(-x^2/2), t = 1 / (1 + p |x|/sqrt2).   Used by the tensor-core modes' fused epilogues.
+// GELU for the tensor-core modes' fused epilogues: one MUFU, 14 FP32 ops, branch-free.
+//   gelu(x) = max(x, 0) - |x/2| erfc(|x|/sqrt2),   erfc(z) = 2^p(z),  p = degree-9 fit of log2(erfc) on
+//   [0, 4.2] (beyond 4.2 erfc < 3e-9 and z is clamped).  Max |gelu err| vs fp64 over [-12, 12]: 2.4e-7
+//   (the erff-based fp32 GELU itself is 1.2e-6 off), no cancellation on the negative side.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fabsf(x) * 0.70710678118654752440f;
-  const float t = __fdividef(1.0f, fmaf(0.3275911f, z, 1.0f));
-  float pl = fmaf(1.061405429f, t, -1.453152027f);
-  pl = fmaf(pl, t, 1.421413741f);
-  pl = fmaf(pl, t, -0.284496736f);
-  pl = fmaf(pl, t, 0.254829592f);
-  const float w = pl * t * __expf(-z * z);
-  const float phi2 = x < 0.0f ? w : 2.0f - w;
-  return 0.5f * x * phi2;
+  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.2f);
+  float p = fmaf(5.4279603e-06f, z, -8.880036e-05f);
+  p = fmaf(p, z, 0.0005802389f);
+  p = fmaf(p, z, -0.0016933879f);
+  p = fmaf(p, z, -0.00062220806f);
+  p = fmaf(p, z, 0.028209634f);
+  p = fmaf(p, z, -0.1484874f);
+  p = fmaf(p, z, -0.91841096f);
+  p = fmaf(p, z, -1.6279094f);
+  p = fmaf(p, z, 2.3326544e-08f);
+  return fmaf(-fabsf(0.5f * x), exp2f(p), fmaxf(x, 0.0f));
 }
 template <int FAST>
 __device__ __forceinline__ float gelu_sel(float x) { return FAST ? gelu_fast(x) : gelu_exact(x); }
@@ -541,6 +544,75 @@ __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__
     float s = 0.f;
     for (int w = 0; w < 8; ++w) s += s_part[w][threadIdx.x];
     partial[((long long)b * tiles + tile) * 6 + threadIdx.x] = s;
+  }
+}
+
+// Tensor-core modes keep the rot layer-1 output channel-major and in fp16, a1T [B][512][P] (written by the
+// fused rot kernel's TMA stores).  One warp per channel: lanes stride over the
+// points, S_c = sum_p wp[p] gelu(a1T[c][p] sc_c + sh_c), and the neck is applied to S_c (linearity, see
+// above).  Block = 32 channels of one head of one object; partial[b][blockIdx.x][6] (other head's 3 = 0).
+__global__ void __launch_bounds__(256) rot_tail_t_kernel(const __half* __restrict__ a1t, const float* __restrict__ gn_scale,
+                                                         const float* __restrict__ gn_shift,
+                                                         const float* __restrict__ neck_w /*[2][3][256]*/,
+                                                         const float* __restrict__ neck_b /*[2][3]*/,
+                                                         const float* __restrict__ wp /*[2][P]*/, float* __restrict__ partial,
+                                                         int P) {
+  extern __shared__ __align__(16) float s_wp[];  // [P]
+  __shared__ float s_part[8][3];
+  const int b = blockIdx.y, cg = blockIdx.x, h = cg >> 3;  // 16 blocks per object, 8 per head
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < P / 4; i += 256)
+    reinterpret_cast<float4*>(s_wp)[i] = __ldg(reinterpret_cast<const float4*>(wp + (long long)h * P) + i);
+  __syncthreads();
+  float r0 = 0.f, r1 = 0.f, r2 = 0.f;
+#pragma unroll 1
+  for (int cc = 0; cc < 4; ++cc) {
+    const int c = cg * 32 + warp * 4 + cc;  // channel in [0, 512)
+    const float sc = gn_scale[(long long)b * 512 + c], sh = gn_shift[(long long)b * 512 + c];
+    const uint4* row = reinterpret_cast<const uint4*>(a1t + ((long long)b * 512 + c) * P);  // 8 points per load
+    float acc = 0.f;
+#pragma unroll 2
+    for (int i = lane; i < P / 8; i += 32) {
+      const uint4 v = __ldg(row + i);
+      const float4 w0 = reinterpret_cast<const float4*>(s_wp)[2 * i], w1 = reinterpret_cast<const float4*>(s_wp)[2 * i + 1];
+      const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+      const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+      const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
+      const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
+      acc = fmaf(w0.x, gelu_fast(fmaf(f0.x, sc, sh)), acc);
+      acc = fmaf(w0.y, gelu_fast(fmaf(f0.y, sc, sh)), acc);
+      acc = fmaf(w0.z, gelu_fast(fmaf(f1.x, sc, sh)), acc);
+      acc = fmaf(w0.w, gelu_fast(fmaf(f1.y, sc, sh)), acc);
+      acc = fmaf(w1.x, gelu_fast(fmaf(f2.x, sc, sh)), acc);
+      acc = fmaf(w1.y, gelu_fast(fmaf(f2.y, sc, sh)), acc);
+      acc = fmaf(w1.z, gelu_fast(fmaf(f3.x, sc, sh)), acc);
+      acc = fmaf(w1.w, gelu_fast(fmaf(f3.y, sc, sh)), acc);
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
+    const int cl = c & 255;
+    r0 = fmaf(neck_w[(h * 3 + 0) * 256 + cl], acc, r0);
+    r1 = fmaf(neck_w[(h * 3 + 1) * 256 + cl], acc, r1);
+    r2 = fmaf(neck_w[(h * 3 + 2) * 256 + cl], acc, r2);
+  }
+  if (lane == 0) { s_part[warp][0] = r0; s_part[warp][1] = r1; s_part[warp][2] = r2; }
+  __syncthreads();
+  if (warp == 0) {
+    float wsum = 0.f;
+    if ((cg & 7) == 0) {  // the neck bias term  nb * sum_p wp[p]  is added once per head
+      for (int i = lane; i < P; i += 32) wsum += s_wp[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
+    if (lane < 6) {
+      float s = 0.f;
+      if (lane / 3 == h) {
+        const int d = lane % 3;
+        for (int w = 0; w < 8; ++w) s += s_part[w][d];
+        s = fmaf(neck_b[h * 3 + d], wsum, s);
+      }
+      partial[((long long)b * gridDim.x + cg) * 6 + lane] = s;
+    }
   }
 }
 

@@ -1,0 +1,376 @@
+// Fused rotation-head kernel (sm_100a): for a tile of 128 points and one of the two axis heads,
+//   L0   D0[128 pts x 256 ch] = pf[128 x 64] . W0p_h[256 x 64]^T              (tcgen05, points on TMEM lanes)
+//   epi0 u = gelu(D0 * sc + sh)   (GroupNorm folded into sc/sh, per set)      -> bf16 hi/lo written by the
+//        epilogue warps straight into shared memory in the 128B-swizzled K-major operand layout
+//   L1   D1[mt][128 ch x 128 pts] = W1_h[mt*128.., 256] . u^T,  mt = 0, 1      (tcgen05, channels on lanes)
+//   epi1 a1T[obj][h*256 + ch][pt] = D1 + b1 (stored as fp16, channel-major; the GroupNorm partial sums per
+//        64 points are taken from the fp32 values.  fp16 storage of this one activation moves the final
+//        (R, t, s) by ~5e-6, measured with the CPU oracle -- it halves the only large HBM stream of the head)
+// so the layer-0 activations (2 KB per point) never touch HBM.  The layer-1 MMAs of K-slab ks start as
+// soon as epi0 has written slab ks, i.e. they run underneath the GELU work of slabs ks+1.. (one U buffer).
+//
+// Reference: heads/conv_out_per_rot_head.py:126-135 (layers.0 .. layers.3 of one RotHead), with the
+// layer-0 split of SURVEY.md 8(a) R1.
+//
+// Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..17 epilogue (4 per lane quadrant).
+// Shared memory: barriers (1 KB) | U: 4 K-slabs x {hi, lo} x [128 rows x 128 B] = 128 KB | ring of 3 x 32 KB slots.
+// After the layer-1 MMAs of a work item have completed, U is dead until the next item's epi0, so epi1 stages
+// its 64 KB fp16 output tile in U slabs 0-1 (4 boxes of [128 ch x 64 pts], 128B-swizzled) and hands it to
+// the TMA store engine (cp.async.bulk.tensor, shared -> global): the a1T write drains in the background.
+// epi0 (and therefore the layer-1 K loop) visits the slabs in the order 2, 3, 0, 1, so the next item only
+// has to wait for that drain before its third slab.
+// TMEM: D0 = columns 0..255, D1[mt] = columns 256 + 128 mt.
+#pragma once
+#include "tc_kernels.cuh"
+
+namespace catre {
+
+constexpr int RF_EW = 16;
+constexpr int RF_THREADS = 64 + 32 * RF_EW;
+constexpr int RF_SLOT = 32 * 1024;
+constexpr int RF_SLOTS = 3;
+constexpr int RF_U_BYTES = 128 * 1024;
+constexpr int RF_SMEM = 1024 + 1024 + RF_U_BYTES + RF_SLOTS * RF_SLOT;  // barriers + alignment slack + U + ring
+
+struct RotFusedP {
+  int tiles;             // R / 128
+  int rows_per_set;      // N
+  int rows_per_obj;      // P = 2N
+  const float* gn_scale; // [S][512]  GroupNorm-0 scale per (set, channel)
+  const float* gn_shift; // [S][512]  shift with the per-set constant folded in
+  const float* bias1;    // [512]     layers.3 bias, both heads
+  float* stats;          // [R/64][64 groups][2]
+  long long* dbg;        // optional timeline of CTA 0 (debug): [work item][32] clock64 stamps, or null
+};
+
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+      : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+        "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+      : "r"(taddr)
+      : "memory");
+}
+__device__ __forceinline__ void tmem_ld_wait16(float* v) {
+  uint32_t* r = reinterpret_cast<uint32_t*>(v);
+  asm volatile("tcgen05.wait::ld.sync.aligned;"
+               : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]), "+r"(r[8]),
+                 "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+               :
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
+template <int NPROD>
+__global__ void __launch_bounds__(RF_THREADS, 1)
+rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constant__ CUtensorMap pf_lo,
+                 const __grid_constant__ CUtensorMap w0_hi, const __grid_constant__ CUtensorMap w0_lo,
+                 const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo,
+                 const __grid_constant__ CUtensorMap a1t_map, const RotFusedP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t u_base = (smem_base + 1024 + 1023) & ~1023u;  // barriers live in the first 1 KB
+  const uint32_t ring_base = u_base + RF_U_BYTES;
+  // barriers (8 B each): full[3] empty[3] d0_full d0_empty d1_full d1_empty u_full[4], then the TMEM base slot
+  const uint32_t bar_full = smem_base, bar_empty = smem_base + 24;
+  const uint32_t bar_d0_full = smem_base + 48, bar_d0_empty = smem_base + 56;
+  const uint32_t bar_d1_full = smem_base + 64, bar_d1_empty = smem_base + 72;
+  const uint32_t bar_u_full = smem_base + 80;  // 4 barriers
+  const uint32_t tmem_slot = smem_base + 112;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + 112);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_ht = p.tiles * 2;  // (tile, head) work items
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&pf_hi); prefetch_tmap(&w0_hi); prefetch_tmap(&w1_hi); prefetch_tmap(&a1t_map);
+    if (NPROD == 3) { prefetch_tmap(&pf_lo); prefetch_tmap(&w0_lo); prefetch_tmap(&w1_lo); }
+    for (int i = 0; i < RF_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_d0_full, 1); mbar_init(bar_d0_empty, RF_EW);
+    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RF_EW);
+    for (int i = 0; i < 4; ++i) mbar_init(bar_u_full + 8 * i, RF_EW);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int slot = 0; uint32_t phase = 0;
+      auto next = [&]() { if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; } };
+      for (int ht = blockIdx.x; ht < n_ht; ht += gridDim.x) {
+        const int tile = ht >> 1, h = ht & 1;
+        // slot A: the tile's point features, hi | lo (16 KB each)
+        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        {
+          const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
+          mbar_expect_tx(full, NPROD == 3 ? 32768 : 16384);
+          tma_load_2d(sb, &pf_hi, 0, tile * 128, full);
+          if (NPROD == 3) tma_load_2d(sb + 16384, &pf_lo, 0, tile * 128, full);
+        }
+        next();
+        // slots B, C: W0p_h hi and lo, [256 ch x 64] each (32 KB)
+        for (int a = 0; a < (NPROD == 3 ? 2 : 1); ++a) {
+          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+          const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
+          mbar_expect_tx(full, 32768);
+          tma_load_2d(sb, a == 0 ? &w0_hi : &w0_lo, 0, h * 256, full);
+          next();
+        }
+        // 8 slots: W1_h[mt*128 .., ks*64 ..] hi | lo, in the order the MMA warp consumes them
+        for (int kq = 0; kq < 4; ++kq)
+          for (int mt = 0; mt < 2; ++mt) {
+            const int ks = (kq + 2) & 3;  // slab order 2, 3, 0, 1
+            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+            const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
+            mbar_expect_tx(full, NPROD == 3 ? 32768 : 16384);
+            tma_load_2d(sb, &w1_hi, ks * 64, h * 256 + mt * 128, full);
+            if (NPROD == 3) tma_load_2d(sb + 16384, &w1_lo, ks * 64, h * 256 + mt * 128, full);
+            next();
+          }
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc0 = umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 128);
+      int slot = 0; uint32_t phase = 0;
+      auto next = [&]() { if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; } };
+      uint32_t it_phase = 0;  // parity of the per-work-item barriers
+      for (int ht = blockIdx.x; ht < n_ht; ht += gridDim.x) {
+        long long* dbg = (p.dbg && blockIdx.x == 0 && ht / (int)gridDim.x < 8) ? p.dbg + (ht / gridDim.x) * 32 : nullptr;
+        if (dbg) dbg[0] = clock64();
+        // ---- L0: D0 = pf . W0p_h^T   (K = 64: 4 k-steps)
+        mbar_wait(bar_d0_empty, it_phase ^ 1);
+        if (dbg) dbg[1] = clock64();
+        tc_fence_after();
+        const int sx = slot;
+        mbar_wait(bar_full + 8 * slot, phase); next();
+        const int sw_hi = slot;
+        mbar_wait(bar_full + 8 * slot, phase); next();
+        int sw_lo = sw_hi;
+        if (NPROD == 3) { sw_lo = slot; mbar_wait(bar_full + 8 * slot, phase); next(); }
+        tc_fence_after();
+        if (dbg) dbg[2] = clock64();
+        {
+          const uint32_t x_hi = ring_base + sx * RF_SLOT, x_lo = x_hi + 16384;
+          const uint32_t w_hi = ring_base + sw_hi * RF_SLOT, w_lo = ring_base + sw_lo * RF_SLOT;
+#pragma unroll
+          for (int kk = 0; kk < 4; ++kk) {
+            const uint32_t off = kk * 32;
+            umma_bf16(tmem_base, umma_desc_sw128(x_hi + off), umma_desc_sw128(w_hi + off), idesc0, kk != 0);
+            if (NPROD == 3) {
+              umma_bf16(tmem_base, umma_desc_sw128(x_hi + off), umma_desc_sw128(w_lo + off), idesc0, 1);
+              umma_bf16(tmem_base, umma_desc_sw128(x_lo + off), umma_desc_sw128(w_hi + off), idesc0, 1);
+            }
+          }
+          umma_commit(bar_empty + 8 * sx);
+          umma_commit(bar_empty + 8 * sw_hi);
+          if (NPROD == 3) umma_commit(bar_empty + 8 * sw_lo);
+          umma_commit(bar_d0_full);
+        }
+        // ---- L1: D1[mt] += W1_h[mt][ks] . U[ks]^T as the U slabs arrive
+        mbar_wait(bar_d1_empty, it_phase ^ 1);
+        tc_fence_after();
+        if (dbg) dbg[3] = clock64();
+        for (int kq = 0; kq < 4; ++kq) {
+          const int ks = (kq + 2) & 3;  // slab order 2, 3, 0, 1
+          mbar_wait(bar_u_full + 8 * ks, it_phase);
+          tc_fence_after();
+          if (dbg) dbg[4 + ks * 3] = clock64();
+          const uint32_t u_hi = u_base + ks * 32768, u_lo = u_hi + 16384;
+          for (int mt = 0; mt < 2; ++mt) {
+            mbar_wait(bar_full + 8 * slot, phase);
+            tc_fence_after();
+            if (dbg) dbg[5 + ks * 3 + mt] = clock64();
+            const uint32_t w_hi = ring_base + slot * RF_SLOT, w_lo = w_hi + 16384;
+            const uint32_t d1 = tmem_base + 256 + mt * 128;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t off = kk * 32;
+              umma_bf16(d1, umma_desc_sw128(w_hi + off), umma_desc_sw128(u_hi + off), idesc1, (kq | kk) != 0);
+              if (NPROD == 3) {
+                umma_bf16(d1, umma_desc_sw128(w_hi + off), umma_desc_sw128(u_lo + off), idesc1, 1);
+                umma_bf16(d1, umma_desc_sw128(w_lo + off), umma_desc_sw128(u_hi + off), idesc1, 1);
+              }
+            }
+            umma_commit(bar_empty + 8 * slot);
+            next();
+          }
+        }
+        umma_commit(bar_d1_full);
+        if (dbg) dbg[16] = clock64();
+        it_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3, part = (warp - 2) >> 2;  // TMEM lanes 32*quad.., 4 parts per quadrant
+    const int lane_row = quad * 32 + lane;
+    uint32_t it_phase = 0;
+    for (int ht = blockIdx.x; ht < n_ht; ht += gridDim.x) {
+      const int tile = ht >> 1, h = ht & 1;
+      const long long row0 = (long long)tile * 128;
+      const int set = (int)(row0 / p.rows_per_set);
+      long long* dbg = (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && ht / (int)gridDim.x < 8)
+                           ? p.dbg + (ht / gridDim.x) * 32 : nullptr;
+      // ---- epi0: lane = point row; slab ks, this warp's 16 channels: ks*64 + part*16 ..
+      mbar_wait(bar_d0_full, it_phase);
+      tc_fence_after();
+      if (dbg) dbg[17] = clock64();
+      const float* scp = p.gn_scale + (long long)set * 512 + h * 256;
+      const float* shp = p.gn_shift + (long long)set * 512 + h * 256;
+      const uint32_t row_off = (uint32_t)((lane_row >> 3) * 1024 + (lane_row & 7) * 128);
+#pragma unroll 1
+      for (int kq = 0; kq < 4; ++kq) {
+        const int ks = (kq + 2) & 3;  // slab order 2, 3, 0, 1
+        if (kq == 2) {
+          // the previous item's TMA stores read their source from U slabs 0-1: they must be done with it
+          if (quad == 0 && lane == 0) tma_store_wait_read();
+          named_bar_sync(5, 32 * RF_EW);
+        }
+        const int ch0 = ks * 64 + part * 16;
+        float v[16];
+        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ch0, v);
+        float4 sc4[4], sh4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {  // broadcast loads (same address on every lane), overlapped with the TMEM load
+          sc4[j] = __ldg(reinterpret_cast<const float4*>(scp + ch0) + j);
+          sh4[j] = __ldg(reinterpret_cast<const float4*>(shp + ch0) + j);
+        }
+        tmem_ld_wait16(v);
+        uint32_t hi[8], lo[8];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const float g0 = gelu_fast(fmaf(v[4 * j + 0], sc4[j].x, sh4[j].x));
+          const float g1 = gelu_fast(fmaf(v[4 * j + 1], sc4[j].y, sh4[j].y));
+          const float g2 = gelu_fast(fmaf(v[4 * j + 2], sc4[j].z, sh4[j].z));
+          const float g3 = gelu_fast(fmaf(v[4 * j + 3], sc4[j].w, sh4[j].w));
+          split_bf16x2(g0, g1, hi[2 * j], lo[2 * j]);
+          split_bf16x2(g2, g3, hi[2 * j + 1], lo[2 * j + 1]);
+        }
+        // two 16-byte chunks (8 channels each) of this row, 128B-swizzled: chunk' = chunk ^ (row & 7)
+        const uint32_t slab = u_base + ks * 32768 + row_off;
+        const uint32_t c0 = (uint32_t)(part * 2), sw = (uint32_t)(lane_row & 7);
+        st_shared_v4(slab + (((c0 + 0) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+        st_shared_v4(slab + (((c0 + 1) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
+        if (NPROD == 3) {
+          st_shared_v4(slab + 16384 + (((c0 + 0) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+          st_shared_v4(slab + 16384 + (((c0 + 1) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
+        }
+        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
+        if (dbg) dbg[18 + ks] = clock64();
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_d0_empty);
+
+      // ---- epi1: lane = output channel of m-tile mt; this warp's 64 points
+      mbar_wait(bar_d1_full, it_phase);
+      tc_fence_after();
+      if (dbg) dbg[22] = clock64();
+      {
+        const int mt = part >> 1, ph = part & 1;
+        const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
+        const long long r64 = row0 + ph * 64;          // first global row of this warp's 64 points
+        const long long obj = r64 / p.rows_per_obj;
+        const float add = p.bias1[ch];
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128 + ph * 64);
+        const uint32_t sw = (uint32_t)(lane_row & 7);
+        // box (mt, ph): [128 ch rows x 64 pts fp16 = 128 B], chunk' = chunk ^ (row & 7)
+        const uint32_t box = u_base + (uint32_t)((mt * 2 + ph) * 16384);
+        const uint32_t brow = box + (uint32_t)lane_row * 128;
+        float s = 0.f, ss = 0.f;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float x[32];
+          tmem_ld32(taddr + c * 32, x);
+          tmem_ld_wait32(x);
+          uint32_t hx[16];
+#pragma unroll
+          for (int j = 0; j < 32; j += 2) {
+            x[j] += add; x[j + 1] += add;
+            s += x[j]; s += x[j + 1];
+            ss = fmaf(x[j], x[j], ss); ss = fmaf(x[j + 1], x[j + 1], ss);
+            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx[j >> 1]) : "f"(x[j + 1]), "f"(x[j]));
+          }
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            st_shared_v4(brow + (((uint32_t)(c * 4 + q) ^ sw) << 4), hx[4 * q], hx[4 * q + 1], hx[4 * q + 2], hx[4 * q + 3]);
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + part, 128);  // the four quadrant warps that share this (mt, ph)
+        if (quad == 0 && lane == 0) {
+          const int pl = (int)(r64 - obj * p.rows_per_obj);
+          const int crow = (int)(obj * 512) + h * 256 + mt * 128;
+          tma_store_2d(&a1t_map, box, pl, crow);
+          tma_store_commit();
+        }
+        s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+        s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+        s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+        if ((lane & 7) == 0) {
+          const long long o = ((r64 >> 6) * 64 + (ch >> 3)) * 2;
+          p.stats[o] = s;
+          p.stats[o + 1] = ss;
+        }
+      }
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_d1_empty);
+      if (dbg) dbg[23] = clock64();
+      it_phase ^= 1;
+    }
+  }
+  if (warp >= 2 && (warp & 3) == 0 && lane == 0) tma_store_wait_all();
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NPROD>
+cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo, const CUtensorMap& w0_hi,
+                             const CUtensorMap& w0_lo, const CUtensorMap& w1_hi, const CUtensorMap& w1_lo,
+                             const CUtensorMap& a1t_map, const RotFusedP& p, int num_sms, cudaStream_t s) {
+  auto kern = rot_fused_kernel<NPROD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SMEM);
+    if (st != cudaSuccess) return st;
+    configured = true;
+  }
+  int items = p.tiles * 2;
+  int grid = items < num_sms ? items : num_sms;
+  if (grid < 1) return cudaSuccess;
+  kern<<<grid, RF_THREADS, RF_SMEM, s>>>(pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, a1t_map, p);
+  return cudaPeekAtLastError();
+}
+
+}  // namespace catre

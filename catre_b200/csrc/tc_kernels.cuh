@@ -209,7 +209,8 @@ struct TcGemmP {
   const float* bias;     // per output channel (or null)
   int relu;
   int* gmax; int C;                             // EPI_MAX / EPI_SPLIT_MAX: keys [S, C]
-  float* out; int ldo;                          // EPI_RAW_STATS: fp32 [R, ldo]
+  float* out; int rows_per_obj;                 // EPI_RAW_STATS: fp32 channel-major [obj][out_ch_per_obj][rows_per_obj]
+  long long out_obj_stride;                     //   = out_ch_per_obj * rows_per_obj (out already points at the first channel)
   const float* rowvec; int ldrv;                // EPI_RAW_STATS / EPI_STATS: per-set additive vector [S, ldrv]
   float* stats; int stats_ld, stats_goff;       // GroupNorm partials [R/(BN/2), stats_ld, 2]
   __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int ldo16;  // EPI_*SPLIT*: bf16 [R, ldo16]
@@ -372,13 +373,23 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         float add = p.bias ? s_bias[ch] : 0.f;
         if (p.rowvec) add += p.rowvec[(long long)set * p.ldrv + ch];
         float s = 0.f, ss = 0.f;
+        float* orow = nullptr;
+        if (EPI == EPI_RAW_STATS) {  // this thread's channel row of the object, at the tile's first point
+          const long long obj = p0 / p.rows_per_obj;
+          orow = p.out + obj * p.out_obj_stride + (long long)ch * p.rows_per_obj + (p0 - obj * p.rows_per_obj);
+        }
         tmem_foreach32<NCHUNK, PIPE>(taddr, [&](int c, const float* v) {
+          float x[32];
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            const float x = v[j] + add;
-            if (EPI == EPI_RAW_STATS) p.out[(p0 + c * 32 + j) * p.ldo + ch] = x;  // 32 lanes -> 32 channels: 128 B
-            s += x;
-            ss = fmaf(x, x, ss);
+            x[j] = v[j] + add;
+            s += x[j];
+            ss = fmaf(x[j], x[j], ss);
+          }
+          if (EPI == EPI_RAW_STATS) {  // 32 consecutive points of one channel: 128 contiguous bytes
+            const uint32_t* xu = reinterpret_cast<const uint32_t*>(x);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) st_global_256(orow + c * 32 + q * 8, xu + q * 8);
           }
         });
         s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
@@ -567,6 +578,20 @@ inline bool tc_make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  return r == CUDA_SUCCESS;
+}
+
+// fp16 [rows, cols] row-major view, box = box_cols x box_rows (box_cols * 2 <= 128 B), 128B swizzle (TMA stores)
+inline bool tc_make_map_f16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
+  PFN_encodeTiled fn = tc_encode_fn();
+  if (!fn) return false;
+  cuuint64_t gdim[2] = {cols, rows};
+  cuuint64_t gstride[1] = {cols * 2};
+  cuuint32_t box[2] = {box_cols, box_rows};
+  cuuint32_t estr[2] = {1, 1};
+  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;
