@@ -98,7 +98,7 @@ struct catre_engine {
   float *rot_w0g = nullptr, *rot_b0 = nullptr, *rot_w0p = nullptr;
   float *rot_gn0_g = nullptr, *rot_gn0_b = nullptr, *rot_gn1_g = nullptr, *rot_gn1_b = nullptr;
   float *rot_b1 = nullptr, *neck_w = nullptr, *neck_b = nullptr, *wp = nullptr, *convp_b = nullptr;
-  float *ts_w0t = nullptr, *ts_w1t = nullptr;
+  float *ts_w0t = nullptr, *ts_w1t = nullptr, *ts_w0g = nullptr;
   // bf16 hi/lo weight copies + tensor maps (tensor-core modes); "MA" maps have 128-row boxes (M side of
   // the MMA), "NB" maps have BN-row boxes (N side)
   TcPair tw_stn_c2, tw_stn_c3, tw_fstn_c1, tw_fstn_c2, tw_fstn_c3, tw_conv2, tw_conv3, tw_conv4, tw_rot0;
@@ -111,7 +111,7 @@ struct catre_engine {
   // ---- workspace
   float *q = nullptr, *h64a = nullptr, *h64b = nullptr, *h128 = nullptr, *h512 = nullptr, *a0 = nullptr, *a1 = nullptr;
   int *gmax_all = nullptr, *gmax_stn = nullptr, *gmax_fstn = nullptr, *gmax_g = nullptr, *gmax_pf = nullptr;
-  float *fc512 = nullptr, *fc256 = nullptr, *fc3p = nullptr, *csetp = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
+  float *fc512 = nullptr, *fc256 = nullptr, *ts0 = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
   CUtensorMap a1t_map;  // fp16 a1T [maxB*512, P] for the fused rot kernel's TMA stores (64-point x 128-channel boxes)
   TcPair t64s;  // tensor-core modes: bf16 hi/lo of T64^T, [S*64, 64]
   float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
@@ -243,23 +243,6 @@ int fill_i32(catre_engine* e, cudaStream_t s, int* p, long long n, int v) {
 
 const float* W(catre_engine* e, const char* name) { return e->dw.at(name); }
 
-// out[r, c] = act(sum of split-K partials + bias[c]); optional bf16 hi/lo copy (tensor-core operand)
-int sum_parts(catre_engine* e, cudaStream_t s, const float* parts, int nparts, long long R, int C, const float* bias,
-              int relu, float* out32, const TcPair* out16) {
-  const long long n = R * C;
-  {
-    Launch l(e, s, G_SUM_PARTS);
-    if (C % 4 == 0) {
-      sum_parts_kernel<<<(unsigned)((n / 4 + 255) / 256), 256, 0, s>>>(
-          parts, nparts, n, bias, C, relu, out32, out16 ? reinterpret_cast<unsigned short*>(out16->hi) : nullptr,
-          out16 ? reinterpret_cast<unsigned short*>(out16->lo) : nullptr, n / 4);
-    } else {
-      sum_parts_scalar_kernel<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(parts, nparts, n, bias, C, relu, out32, n);
-    }
-  }
-  return check_launch(e, "sum_parts");
-}
-
 // ---- tensor-core launch helpers ------------------------------------------------------------------
 template <int ORIENT, int EPI, int BN>
 int tc_run(catre_engine* e, cudaStream_t s, int grp, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo,
@@ -306,29 +289,33 @@ int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv,
   return check_launch(e, "front3_split");
 }
 
-// T-Net FC chain: keys [S,1024] -> 512 -> 256 -> kk  (pointnets/pointnet.py:32-40, 66-77).  M = S is
-// small, so every layer is split-K over many CTAs; partials are summed (fixed order) by the consumer.
-constexpr int KS_FC1 = 16, KS_FC2 = 8, KS_FC3 = 4;
+// small-M fully-connected layer on a cluster of FC_KSPLIT CTAs (see fc_cluster_kernel)
+template <int AMODE>
+int run_fc(catre_engine* e, cudaStream_t s, int grp, const float* A, int lda, const float* Wt, int ldw, const float* bias,
+           int R, int C, int K, int relu, float* out32, const TcPair* out16) {
+  FcP p{};
+  p.A = A; p.lda = lda; p.W = Wt; p.ldw = ldw; p.bias = bias; p.out32 = out32;
+  p.out_hi = out16 ? reinterpret_cast<unsigned short*>(out16->hi) : nullptr;
+  p.out_lo = out16 ? reinterpret_cast<unsigned short*>(out16->lo) : nullptr;
+  p.R = R; p.C = C; p.K = K; p.relu = relu;
+  dim3 grid((C + 63) / 64, (R + 127) / 128, FC_KSPLIT);
+  {
+    Launch l(e, s, grp);
+    fc_cluster_kernel<AMODE><<<grid, 256, 0, s>>>(p);
+  }
+  return check_launch(e, kGrpNames[grp]);
+}
 
+// T-Net FC chain: keys [S,1024] -> 512 -> 256 -> kk  (pointnets/pointnet.py:32-40, 66-77)
 int tnet_fc(catre_engine* e, cudaStream_t s, const int* keys, int S, const char* prefix, const float* fc3_w,
             const float* fc3_bias_I, int kk, float* out32, const TcPair* out16) {
   std::string pf(prefix);
   int rc;
-  GemmP p = gemm_args(reinterpret_cast<const float*>(keys), 1024, W(e, (pf + ".fc1.weight").c_str()), 1024, 512, nullptr,
-                      e->fc512, 512, S, 0);
-  p.ksplit = KS_FC1; p.part_stride = (long long)S * 512;
-  if ((rc = run_gemm<64, A_KEY>(e, s, G_TNET_FC, p))) return rc;
-  p = gemm_args(e->fc512, 512, W(e, (pf + ".fc2.weight").c_str()), 512, 256, nullptr, e->fc256, 256, S, 0);
-  p.a_bias = W(e, (pf + ".fc1.bias").c_str()); p.a_nparts = KS_FC1; p.a_part_stride = (long long)S * 512; p.a_relu = 1;
-  p.ksplit = KS_FC2; p.part_stride = (long long)S * 256;
-  if ((rc = run_gemm<64, A_PARTIAL>(e, s, G_TNET_FC, p))) return rc;
-  p = gemm_args(e->fc256, 256, fc3_w, 256, kk, nullptr, e->fc3p, kk, S, 0);
-  p.a_bias = W(e, (pf + ".fc2.bias").c_str()); p.a_nparts = KS_FC2; p.a_part_stride = (long long)S * 256; p.a_relu = 1;
-  p.ksplit = KS_FC3; p.part_stride = (long long)S * kk;
-  if (kk <= 64) rc = run_gemm<64, A_PARTIAL>(e, s, G_TNET_FC, p);
-  else rc = run_gemm<128, A_PARTIAL>(e, s, G_TNET_FC, p);
-  if (rc) return rc;
-  return sum_parts(e, s, e->fc3p, KS_FC3, S, kk, fc3_bias_I, 0, out32, out16);
+  if ((rc = run_fc<A_KEY>(e, s, G_TNET_FC, reinterpret_cast<const float*>(keys), 1024, W(e, (pf + ".fc1.weight").c_str()), 1024,
+                          W(e, (pf + ".fc1.bias").c_str()), S, 512, 1024, 1, e->fc512, nullptr))) return rc;
+  if ((rc = run_fc<A_PLAIN>(e, s, G_TNET_FC, e->fc512, 512, W(e, (pf + ".fc2.weight").c_str()), 512,
+                            W(e, (pf + ".fc2.bias").c_str()), S, 256, 512, 1, e->fc256, nullptr))) return rc;
+  return run_fc<A_PLAIN>(e, s, G_TNET_FC, e->fc256, 256, fc3_w, 256, fc3_bias_I, S, kk, 256, 0, out32, out16);
 }
 
 // One refinement iteration on a chunk of B objects whose points are already in e->q.
@@ -427,10 +414,8 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   // ---- R1: rotation heads (heads/conv_out_per_rot_head.py:62-71,126-140) with the layer-0 split:
   //      layers.0 . [g_set | pf_p] = W0[:, :1024] . g_set (once per set) + W0[:, 1024:] . pf_p
   {
-    GemmP p = gemm_args(reinterpret_cast<const float*>(e->gmax_g), 1024, e->rot_w0g, 1024, 512, nullptr, e->csetp, 512, S, 0);
-    p.ksplit = KS_FC1; p.part_stride = (long long)S * 512;
-    if ((rc = run_gemm<64, A_KEY>(e, s, G_ROT_GFEAT, p))) return rc;
-    if ((rc = sum_parts(e, s, e->csetp, KS_FC1, S, 512, e->rot_b0, 0, e->cset, nullptr))) return rc;
+    if ((rc = run_fc<A_KEY>(e, s, G_ROT_GFEAT, reinterpret_cast<const float*>(e->gmax_g), 1024, e->rot_w0g, 1024, e->rot_b0, S, 512,
+                            1024, 0, e->cset, nullptr))) return rc;
   }
   float* gn0_scale = e->gn0;
   float* gn0_shift = e->gn0 + (size_t)e->maxB * 1024;
@@ -505,11 +490,14 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   }
   if ((rc = check_launch(e, "rot_tail"))) return rc;
 
-  // ---- H1 + G1 + G2
+  // ---- H1 + G1 + G2.  ts-head layer 0 over the 1024 global-feature inputs of the OBSERVED set (row b -> set 2b)
+  //      runs as a cluster FC; the remaining 67 inputs (pointfeat max, init scale) are added in ts_pose.
+  if ((rc = run_fc<A_KEY>(e, s, G_TS_POSE, reinterpret_cast<const float*>(e->gmax_g), 2048, e->ts_w0g, 1024,
+                          W(e, "ts_head.linears.0.bias"), B, 256, 1024, 0, e->ts0, nullptr))) return rc;
   {
     TsPoseP p{};
-    p.gmax_g = e->gmax_g; p.gmax_pf = e->gmax_pf;
-    p.w0t = e->ts_w0t; p.b0 = W(e, "ts_head.linears.0.bias"); p.g0 = W(e, "ts_head.linears.1.weight");
+    p.ts0 = e->ts0; p.gmax_pf = e->gmax_pf;
+    p.w0t = e->ts_w0t; p.g0 = W(e, "ts_head.linears.1.weight");
     p.be0 = W(e, "ts_head.linears.1.bias");
     p.w1t = e->ts_w1t; p.b1 = W(e, "ts_head.linears.3.bias"); p.g1 = W(e, "ts_head.linears.4.weight");
     p.be1 = W(e, "ts_head.linears.4.bias");
@@ -518,7 +506,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p.rot_partial = e->rot_partial; p.rot_tiles = tc ? 16 : P / 128; p.convp_bias = e->convp_b;
     p.pose_in = pose_in; p.scale_in = scale_in; p.K = K; p.pose_out = pose_out; p.scale_out = scale_out;
     Launch l(e, s, G_TS_POSE);
-    ts_pose_kernel<<<B, 1024, 0, s>>>(p);
+    ts_pose_kernel<<<B, 256, 0, s>>>(p);
   }
   return check_launch(e, "ts_pose");
 }
@@ -589,10 +577,9 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   e->gmax_fstn = e->gmax_all + S * 1024;
   e->gmax_g = e->gmax_all + S * 2048;
   e->gmax_pf = e->gmax_all + S * 3072;
-  rc |= dalloc(e, &e->fc512, KS_FC1 * S * 512);  // split-K partials of the small-M FC layers
-  rc |= dalloc(e, &e->fc256, KS_FC2 * S * 256);
-  rc |= dalloc(e, &e->fc3p, KS_FC3 * S * 4096);
-  rc |= dalloc(e, &e->csetp, KS_FC1 * S * 512);
+  rc |= dalloc(e, &e->fc512, S * 512);
+  rc |= dalloc(e, &e->fc256, S * 256);
+  rc |= dalloc(e, &e->ts0, B * 256);
   rc |= dalloc(e, &e->t3, S * 9 + 7);
   rc |= dalloc(e, &e->cset, S * 512);
   rc |= dalloc(e, &e->stats0, (R / 128) * 64 * 2);
@@ -745,6 +732,11 @@ int catre_pack(catre_engine* e, void* stream) {
   for (int c = 0; c < 256; ++c)
     for (int k = 0; k < 256; ++k) t1t[(size_t)k * 256 + c] = t1[(size_t)c * 256 + k];
   up(&e->ts_w0t, t0t); up(&e->ts_w1t, t1t);
+  {  // ts layer-0 weights over the global feature, [256, 1024] contiguous (operand of the cluster FC)
+    std::vector<float> t0g(256 * 1024);
+    for (int c = 0; c < 256; ++c) memcpy(&t0g[(size_t)c * 1024], &t0[(size_t)c * 1091], 1024 * sizeof(float));
+    up(&e->ts_w0g, t0g);
+  }
   if (rc) return fail(e, CATRE_ERR_CUDA, "uploading packed weights failed: %s", cudaGetErrorString(cudaGetLastError()));
 
   if (e->cfg.precision != CATRE_PREC_FP32_SIMT) {

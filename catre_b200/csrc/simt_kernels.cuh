@@ -2,6 +2,7 @@
 // narrow / per-object stages of every mode).  Semantics follow SURVEY.md appendix A; each kernel cites
 // the reference lines it restates.  Written for sm_100a; no library calls.
 #pragma once
+#include <cooperative_groups.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -399,6 +400,145 @@ __global__ void gn_finalize_kernel(const float* __restrict__ stats, const float*
   }
 }
 
+// ----------------------------------------------------------------------------------------------
+// Small-M fully-connected layer (T-Net FCs, rot g-feature GEMV, ts-head layer 0):
+//   out[r, c] = act(sum_k f(A[r, k]) W[c, k] + bias[c]),   R = number of sets (or objects), a few hundred.
+// There is too little work per output tile to hide memory latency and too few tiles to fill 148 SMs, so
+// K is split over a thread-block CLUSTER of FC_KSPLIT CTAs (grid.z): each CTA reduces K / FC_KSPLIT
+// for one 128 x 64 output tile (register-tiled FMA, all of its global loads issued up front in groups of
+// 4 chunks), parks its partial tile in its own shared memory, and after a cluster barrier every CTA sums
+// 1/FC_KSPLIT of the tile over the cluster's shared memories (DSMEM) in fixed rank order -- deterministic,
+// no global scratch, no atomics -- and writes the finished values (+ optional bf16 hi/lo copy).
+// ----------------------------------------------------------------------------------------------
+constexpr int FC_KSPLIT = 8;
+
+struct FcP {
+  const float* A; int lda;      // [R, K] (A_KEY: ordered-int keys of a column max)
+  const float* W; int ldw;      // [C, K]
+  const float* bias;            // [C] or null
+  float* out32;                 // [R, C] or null
+  unsigned short* out_hi; unsigned short* out_lo;  // bf16 hi/lo of the result [R, C], or null
+  int R, C, K;                  // K multiple of 16 * FC_KSPLIT
+  int relu;
+};
+
+template <int AMODE>
+__global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(256) fc_cluster_kernel(FcP p) {
+  namespace cg = cooperative_groups;
+  constexpr int BM = 128, BN = 64, BK = 16, DEPTH = 4;
+  __shared__ __align__(16) float As[BK][BM + 4];
+  __shared__ __align__(16) float Ws[BK][BN + 4];
+  __shared__ __align__(16) float part[BM][BN];
+  cg::cluster_group cluster = cg::this_cluster();
+  const int rank = (int)cluster.block_rank();  // == blockIdx.z (cluster spans grid.z)
+
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int r0 = blockIdx.y * BM, c0 = blockIdx.x * BN;
+  const int kz = p.K / FC_KSPLIT, k_begin = rank * kz, nsteps = kz / BK;
+
+  float acc[8][4];
+#pragma unroll
+  for (int i = 0; i < 8; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+
+  float4 areg[DEPTH][2], wreg[DEPTH];
+  auto load_chunk = [&](int slot, int k0) {
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int e = tid + it * 256, row = e >> 2, kq = (e & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + row < p.R) {
+        const float* src = p.A + (long long)(r0 + row) * p.lda + k0 + kq;
+        if (AMODE == A_KEY) {
+          const int4 kv = *reinterpret_cast<const int4*>(src);
+          v = make_float4(key2f(kv.x), key2f(kv.y), key2f(kv.z), key2f(kv.w));
+        } else {
+          v = *reinterpret_cast<const float4*>(src);
+        }
+      }
+      areg[slot][it] = v;
+    }
+    {
+      const int col = tid >> 2, kq = (tid & 3) * 4;
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + col < p.C) v = *reinterpret_cast<const float4*>(p.W + (long long)(c0 + col) * p.ldw + k0 + kq);
+      wreg[slot] = v;
+    }
+  };
+
+  for (int s0 = 0; s0 < nsteps; s0 += DEPTH) {
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d)
+      if (s0 + d < nsteps) load_chunk(d, k_begin + (s0 + d) * BK);
+#pragma unroll
+    for (int d = 0; d < DEPTH; ++d) {
+      if (s0 + d < nsteps) {
+#pragma unroll
+        for (int it = 0; it < 2; ++it) {
+          const int e = tid + it * 256, row = e >> 2, kq = (e & 3) * 4;
+          As[kq + 0][row] = areg[d][it].x; As[kq + 1][row] = areg[d][it].y;
+          As[kq + 2][row] = areg[d][it].z; As[kq + 3][row] = areg[d][it].w;
+        }
+        {
+          const int col = tid >> 2, kq = (tid & 3) * 4;
+          Ws[kq + 0][col] = wreg[d].x; Ws[kq + 1][col] = wreg[d].y; Ws[kq + 2][col] = wreg[d].z; Ws[kq + 3][col] = wreg[d].w;
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < BK; ++kk) {
+          float a[8], w[4];
+          *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
+          *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+          *reinterpret_cast<float4*>(&w[0]) = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+#pragma unroll
+            for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+        }
+        __syncthreads();
+      }
+    }
+  }
+  // park the partial tile: thread's rows ty*4+i (i<4), 64+ty*4+(i-4); columns tx*4 ..
+#pragma unroll
+  for (int i = 0; i < 8; ++i) {
+    const int row = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
+    *reinterpret_cast<float4*>(&part[row][tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
+  }
+  cluster.sync();
+  // CTA `rank` finishes rows rank*16 .. +15 of the tile: 16 x 64 values = one float4 per thread
+  {
+    const int row = rank * (BM / FC_KSPLIT) + (tid >> 4), col = (tid & 15) * 4;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int z = 0; z < FC_KSPLIT; ++z) {
+      const float4 t = *reinterpret_cast<const float4*>(cluster.map_shared_rank(&part[row][col], z));
+      v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
+    }
+    const int gr = r0 + row, gc = c0 + col;
+    if (gr < p.R) {
+      float f[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+      for (int j = 0; j < 4; ++j)
+        if (gc + j < p.C) {
+          float y = f[j] + (p.bias ? p.bias[gc + j] : 0.f);
+          if (p.relu) y = fmaxf(y, 0.f);
+          const long long o = (long long)gr * p.C + gc + j;
+          if (p.out32) p.out32[o] = y;
+          if (p.out_hi) {  // round-to-nearest-even bf16 of y and of the residual
+            const unsigned int u = __float_as_uint(y);
+            const unsigned int hr = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;
+            const unsigned int ul = __float_as_uint(y - __uint_as_float(hr));
+            p.out_hi[o] = (unsigned short)(hr >> 16);
+            p.out_lo[o] = (unsigned short)((ul + 0x7fffu + ((ul >> 16) & 1u)) >> 16);
+          }
+        }
+    }
+  }
+  cluster.sync();  // no CTA may exit while its shared memory is still being read by the others
+}
+
 // Fixed-order reduction of split-K partials:  out[r, c] = act(sum_z parts[z][r, c] + bias[c]).
 // Optionally also writes the bf16 hi/lo split of the result (operand of a tensor-core layer).
 __global__ void sum_parts_kernel(const float* __restrict__ parts, int nparts, long long part_stride,
@@ -624,9 +764,9 @@ __global__ void __launch_bounds__(256) rot_tail_t_kernel(const __half* __restric
 //   w0t [1091, 256], w1t [256, 256]: transposed at pack time so threads read coalesced.
 // ----------------------------------------------------------------------------------------------
 struct TsPoseP {
-  const int* gmax_g;    // [2B, 1024] keys: global feature per set (obs set = 2b)
+  const float* ts0;     // [B, 256] ts layer 0 over the 1024 global-feature inputs (+ bias), from the cluster FC
   const int* gmax_pf;   // [2B, 64] keys: max over points of pointfeat
-  const float* w0t; const float* b0; const float* g0; const float* be0;
+  const float* w0t; const float* g0; const float* be0;  // w0t [1091, 256] transposed layer-0 weights
   const float* w1t; const float* b1; const float* g1; const float* be1;
   const float* wt; const float* bt; const float* ws; const float* bs;
   const float* rot_partial; int rot_tiles;  // [B, tiles, 6]
@@ -651,62 +791,49 @@ __device__ __forceinline__ float gn8_gelu(float v, float gamma, float beta) {
   return gelu_exact(d * rstd * gamma + beta);
 }
 
-__global__ void __launch_bounds__(1024) ts_pose_kernel(TsPoseP p) {
-  // 1024 threads: thread (kq, t) accumulates output channel t over the kq-th quarter of K, so four times
-  // as many weight loads are in flight per SM; the quarters are summed through shared memory.
-  const int b = blockIdx.x, t = threadIdx.x & 255, kq = threadIdx.x >> 8;
-  __shared__ float feat[1092];
+__global__ void __launch_bounds__(256) ts_pose_kernel(TsPoseP p) {
+  const int b = blockIdx.x, t = threadIdx.x;
+  __shared__ float feat2[68];  // pointfeat max (64) | init scale (3)
   __shared__ float h[256];
-  __shared__ float part[4][256];
   __shared__ float outv[6];
   const float* sc_in = p.scale_in + (long long)b * 3;
-  for (int i = threadIdx.x; i < 1024; i += 1024) feat[i] = key2f(p.gmax_g[(long long)(2 * b) * 1024 + i]);
-  if (threadIdx.x < 64) feat[1024 + threadIdx.x] = key2f(p.gmax_pf[(long long)(2 * b) * 64 + threadIdx.x]);
-  if (threadIdx.x >= 64 && threadIdx.x < 67) feat[1088 + threadIdx.x - 64] = sc_in[threadIdx.x - 64];
-  if (threadIdx.x == 67) feat[1091] = 0.f;
+  if (t < 64) feat2[t] = key2f(p.gmax_pf[(long long)(2 * b) * 64 + t]);
+  if (t >= 64 && t < 67) feat2[t] = sc_in[t - 64];
   __syncthreads();
   {
-    const int kb = kq * 273, ke = kb + 273 < 1091 ? kb + 273 : 1091;  // 4 x 273 = 1092 >= 1091
-    float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
-    int k = kb;
-#pragma unroll 2
-    for (; k + 4 <= ke; k += 4) {
-      a0 = fmaf(p.w0t[(k + 0) * 256 + t], feat[k + 0], a0);
-      a1 = fmaf(p.w0t[(k + 1) * 256 + t], feat[k + 1], a1);
-      a2 = fmaf(p.w0t[(k + 2) * 256 + t], feat[k + 2], a2);
-      a3 = fmaf(p.w0t[(k + 3) * 256 + t], feat[k + 3], a3);
-    }
-    for (; k < ke; ++k) a0 = fmaf(p.w0t[k * 256 + t], feat[k], a0);
-    part[kq][t] = (a0 + a1) + (a2 + a3);
-  }
-  __syncthreads();
-  if (kq == 0) {
-    float a = p.b0[t] + ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t]));
-    h[t] = gn8_gelu(a, p.g0[t], p.be0[t]);
-  }
-  __syncthreads();
-  {
-    const int kb = kq * 64;
-    float c0 = 0.f, c1 = 0.f, c2 = 0.f, c3 = 0.f;
+    float a0 = p.ts0[(long long)b * 256 + t], a1 = 0.f, a2 = 0.f, a3 = 0.f;
 #pragma unroll 4
-    for (int k = kb; k < kb + 64; k += 4) {
+    for (int k = 0; k < 64; k += 4) {
+      a0 = fmaf(p.w0t[(1024 + k + 0) * 256 + t], feat2[k + 0], a0);
+      a1 = fmaf(p.w0t[(1024 + k + 1) * 256 + t], feat2[k + 1], a1);
+      a2 = fmaf(p.w0t[(1024 + k + 2) * 256 + t], feat2[k + 2], a2);
+      a3 = fmaf(p.w0t[(1024 + k + 3) * 256 + t], feat2[k + 3], a3);
+    }
+    a0 = fmaf(p.w0t[1088 * 256 + t], feat2[64], a0);
+    a1 = fmaf(p.w0t[1089 * 256 + t], feat2[65], a1);
+    a2 = fmaf(p.w0t[1090 * 256 + t], feat2[66], a2);
+    h[t] = gn8_gelu((a0 + a1) + (a2 + a3), p.g0[t], p.be0[t]);
+  }
+  __syncthreads();
+  float a2;
+  {
+    float c0 = p.b1[t], c1 = 0.f, c2 = 0.f, c3 = 0.f, c4 = 0.f, c5 = 0.f, c6 = 0.f, c7 = 0.f;
+#pragma unroll 4
+    for (int k = 0; k < 256; k += 8) {
       c0 = fmaf(p.w1t[(k + 0) * 256 + t], h[k + 0], c0);
       c1 = fmaf(p.w1t[(k + 1) * 256 + t], h[k + 1], c1);
       c2 = fmaf(p.w1t[(k + 2) * 256 + t], h[k + 2], c2);
       c3 = fmaf(p.w1t[(k + 3) * 256 + t], h[k + 3], c3);
+      c4 = fmaf(p.w1t[(k + 4) * 256 + t], h[k + 4], c4);
+      c5 = fmaf(p.w1t[(k + 5) * 256 + t], h[k + 5], c5);
+      c6 = fmaf(p.w1t[(k + 6) * 256 + t], h[k + 6], c6);
+      c7 = fmaf(p.w1t[(k + 7) * 256 + t], h[k + 7], c7);
     }
-    part[kq][t] = (c0 + c1) + (c2 + c3);
+    a2 = gn8_gelu(((c0 + c1) + (c2 + c3)) + ((c4 + c5) + (c6 + c7)), p.g1[t], p.be1[t]);
   }
   __syncthreads();
-  float a2 = 0.f;
-  if (kq == 0) {
-    a2 = p.b1[t] + ((part[0][t] + part[1][t]) + (part[2][t] + part[3][t]));
-    a2 = gn8_gelu(a2, p.g1[t], p.be1[t]);
-  }
+  h[t] = a2;
   __syncthreads();
-  if (kq == 0) h[t] = a2;
-  __syncthreads();
-  if (threadIdx.x >= 256) return;
   // fc_t (3) and fc_s (3): warp w < 6 computes one output
   int warp = t >> 5, lane = t & 31;
   if (warp < 6) {
@@ -718,13 +845,19 @@ __global__ void __launch_bounds__(1024) ts_pose_kernel(TsPoseP p) {
     if (lane == 0) outv[warp] = s + ((warp < 3) ? p.bt[warp] : p.bs[warp - 3]);
   }
   __syncthreads();
+  // rot-head partial sums [tiles][6]: warp j < 6 adds column j (lanes stride over the tiles, fixed order)
+  __shared__ float r6s[6];
+  if (warp < 6) {
+    float s = 0.f;
+    for (int tl = lane; tl < p.rot_tiles; tl += 32) s += p.rot_partial[((long long)b * p.rot_tiles + tl) * 6 + warp];
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
+    if (lane == 0) r6s[warp] = s + p.convp_bias[warp / 3];
+  }
+  __syncthreads();
   if (t == 0) {
     float r6[6];
-    for (int j = 0; j < 6; ++j) {
-      float s = 0.f;
-      for (int tl = 0; tl < p.rot_tiles; ++tl) s += p.rot_partial[((long long)b * p.rot_tiles + tl) * 6 + j];
-      r6[j] = s + p.convp_bias[j / 3];
-    }
+    for (int j = 0; j < 6; ++j) r6[j] = r6s[j];
     // rot6d -> R (columns x, y, z)
     float nx = sqrtf(r6[0] * r6[0] + r6[1] * r6[1] + r6[2] * r6[2]);
     nx = fmaxf(nx, 1e-12f);
