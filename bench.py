@@ -34,9 +34,21 @@ def flops_per_object_iter(n_o: int, n_p: int) -> float:
 # algorithmic FLOPs per POINT of each wide layer (2 * C_in * C_out), for per-kernel rooflines
 LAYER_FLOPS_PER_POINT = {
     "conv4_max": 2 * 512 * 1024, "stn_conv3_max": 2 * 128 * 1024, "fstn_conv3_max": 2 * 128 * 1024,
-    "conv3": 2 * 128 * 512, "rot_layer1": 2 * 256 * 256 * 2, "rot_layer0": 2 * 1088 * 256 * 2,
+    "conv3": 2 * 128 * 512, "rot_fused": 2 * 64 * 512 + 2 * 256 * 256 * 2, "rot_layer0": 2 * 64 * 512,
     "stn_conv2": 2 * 64 * 128, "fstn_conv2": 2 * 64 * 128, "conv2": 2 * 64 * 128, "fstn_conv1": 2 * 64 * 64,
 }
+
+
+def ncu_traffic(kernel: str, batch: int):
+    """DRAM bytes (read + write) per launch of `kernel` from the committed `ncu --set full` capture of this
+    workload (profiles/ncu_traffic.json, written by tools/ncu_raw.py --traffic), or None if not captured."""
+    p = os.path.join(REPO, "profiles", "ncu_traffic.json")
+    try:
+        with open(p) as f:
+            return json.load(f).get(kernel, {}).get(str(batch))
+    except Exception:
+        return None
+
 
 
 def measured_peaks():
@@ -277,7 +289,7 @@ def main():
         ach = fl / (ms_launch * 1e-3) / 1e12
         nprod = {"bf16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
         roofline = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
-                    "frac": ach / peaks["bf16_tflops"], "traffic": None, "peak_source": peaks["source"],
+                    "frac": ach / peaks["bf16_tflops"], "traffic": ncu_traffic(top, B), "peak_source": peaks["source"],
                     "ms_per_launch": ms_launch, "share_of_step": cand[top][0] / tot if tot else None,
                     "mma_products_per_mac": nprod,
                     "note": "achieved = algorithmic FLOPs (one fp32-equivalent product per MAC) / CUDA-event time; "

@@ -205,6 +205,7 @@ struct TcGemmP {
   int m_tiles, n_tiles;  // tiles on the M side (128 rows each) / N side (BN rows each)
   int rows_per_set;      // points per set (a tile never straddles two sets)
   int nb_per_set;        // PT_ON_LANES: the NB operand is per set (rows set*BN .. +BN): feature transform
+  int res_stages;        // resident-weight layers: activation stages in the ring (set by tc_launch)
   // epilogue
   const float* bias;     // per output channel (or null)
   int relu;
@@ -224,8 +225,23 @@ struct TcCfg {
   static constexpr int NB_BYTES = BN * 128;
   static constexpr int STAGE_BYTES = (MA_BYTES + NB_BYTES) * ARR;
   static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 4 ? 4 : (200 * 1024 / STAGE_BYTES);
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2048;  // + barriers + 1024 B alignment slack
+  static constexpr int BIAS_BYTES = 4096;                          // per-channel bias of the layer (<= 1024 channels)
+  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BIAS_BYTES;  // barriers | stages | bias
+  // resident-weight variant (point-on-lanes layers with a fixed weight operand): all K slabs of the CTA's
+  // BN weight rows stay in shared memory for the whole kernel; only the activation tiles stream.
+  static constexpr int RES_STAGE_BYTES = MA_BYTES * ARR;
+  static constexpr int MAX_SMEM = 227 * 1024;
+  static constexpr int RES_BIAS_BYTES = 2048;  // point-on-lanes layers have <= 512 output channels
+  static int res_bytes(int K) { return (K / 64) * NB_BYTES * ARR; }
+  static int res_stages(int K) {
+    int st = (MAX_SMEM - 1024 - RES_BIAS_BYTES - res_bytes(K)) / RES_STAGE_BYTES;
+    return st > 4 ? 4 : st;
+  }
+  static int res_smem(int K) { return 1024 + res_bytes(K) + res_stages(K) * RES_STAGE_BYTES + RES_BIAS_BYTES; }
 };
+// weights stay resident for the plain point-on-lanes layers (bias/ReLU/split epilogue)
+template <int ORIENT, int EPI>
+struct TcRes { static constexpr bool value = (ORIENT == 1 && EPI == 2); };
 
 // 32 columns of one point row: fp32 -> bf16 hi/lo, written as full 32-byte sectors (st.global.v8)
 template <int NPROD>
@@ -246,7 +262,9 @@ __global__ void __launch_bounds__(TcEpi<ORIENT, BN>::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant__ CUtensorMap ma_lo,
                const __grid_constant__ CUtensorMap nb_hi, const __grid_constant__ CUtensorMap nb_lo, const TcGemmP p) {
   using Cfg = TcCfg<BN, NPROD>;
-  constexpr int STAGES = Cfg::STAGES;
+  constexpr bool RESW = TcRes<ORIENT, EPI>::value;
+  const int STAGES = RESW ? p.res_stages : Cfg::STAGES;
+  constexpr int STAGE_BYTES = RESW ? Cfg::RES_STAGE_BYTES : Cfg::STAGE_BYTES;
   constexpr int EW = TcEpi<ORIENT, BN>::EW, TC_THREADS = TcEpi<ORIENT, BN>::THREADS;
   constexpr int PARTS = EW / 4;        // epilogue warps per TMEM lane quadrant
   constexpr int HALF = BN / PARTS;     // columns per epilogue warp
@@ -254,14 +272,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
   constexpr bool PIPE = (EW == 8);
   static_assert(HALF % 32 == 0, "each epilogue warp needs whole 32-column chunks");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128 or 256");
-  extern __shared__ uint8_t smem_raw[];
-  __shared__ __align__(16) float s_bias[1024];
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
-  const uint32_t tiles_base = (smem_base + 1024 + 1023) & ~1023u;  // barriers live in the first 1 KB
-  // barrier block: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], tmem base pointer
-  const uint32_t bar_full = smem_base, bar_empty = smem_base + 8 * STAGES;
-  const uint32_t bar_tfull = smem_base + 16 * STAGES, bar_tempty = bar_tfull + 16;
-  const uint32_t tmem_slot = bar_tempty + 16;
+  if (smem_base & 1023u) __trap();                 // the 128B-swizzled tiles need a 1 KB aligned base
+  const uint32_t tiles_base = smem_base + 1024;    // barriers live in the first 1 KB
+  // barrier block: full[4], empty[4], tmem_full[2], tmem_empty[2], resident-weights barrier, tmem base pointer
+  const uint32_t bar_full = smem_base, bar_empty = smem_base + 32;
+  const uint32_t bar_tfull = smem_base + 64, bar_tempty = bar_tfull + 16;
+  const uint32_t bar_res = bar_tempty + 16;
+  const uint32_t tmem_slot = bar_res + 8;
+  // resident weights (RESW): [k slab][hi | lo][BN rows x 128 B] right after the barrier block, then the stage ring
+  const uint32_t res_base = tiles_base;
+  const uint32_t ring_base = RESW ? tiles_base + (uint32_t)((p.K / TC_BK) * Cfg::NB_BYTES * Cfg::ARR) : tiles_base;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (ring_base - smem_base) + (uint32_t)STAGES * STAGE_BYTES);  // tail
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -273,6 +296,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
     if (NPROD == 3) { prefetch_tmap(&ma_lo); prefetch_tmap(&nb_lo); }
     for (int i = 0; i < STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, EW); }
+    mbar_init(bar_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -285,6 +309,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
 
+  // tile t of this CTA's sequence: blockIdx.x, blockIdx.x + gridDim.x, ...  With resident weights the grid is
+  // a multiple of n_tiles, so t % n_tiles (the weight tile) is the same for every tile of a CTA.
   auto tile_coords = [&](int t, int& mi, int& ni) {
     if (ORIENT == CH_ON_LANES) { mi = t % p.m_tiles; ni = t / p.m_tiles; }  // channel tile fastest
     else { ni = t % p.n_tiles; mi = t / p.n_tiles; }
@@ -294,19 +320,28 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
     // ===================== TMA producer =====================
     if (lane == 0) {
       int stage = 0; uint32_t phase = 0;
+      if (RESW && blockIdx.x < total_tiles) {  // the CTA's weight tile, all K slabs, once
+        const int ni0 = blockIdx.x % p.n_tiles;
+        mbar_expect_tx(bar_res, (uint32_t)(k_slabs * Cfg::NB_BYTES * Cfg::ARR));
+        for (int ks = 0; ks < k_slabs; ++ks) {
+          const uint32_t rb = res_base + (uint32_t)(ks * Cfg::NB_BYTES * Cfg::ARR);
+          tma_load_2d(rb, &nb_hi, ks * TC_BK, ni0 * BN, bar_res);
+          if (NPROD == 3) tma_load_2d(rb + Cfg::NB_BYTES, &nb_lo, ks * TC_BK, ni0 * BN, bar_res);
+        }
+      }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int mi, ni; tile_coords(t, mi, ni);
         const int nb_row = (ORIENT == PT_ON_LANES && p.nb_per_set) ? ((mi * 128) / p.rows_per_set) * BN : ni * BN;
         for (int ks = 0; ks < k_slabs; ++ks) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
-          const uint32_t sb = tiles_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = ring_base + stage * STAGE_BYTES;
           const uint32_t full = bar_full + 8 * stage;
-          mbar_expect_tx(full, Cfg::STAGE_BYTES);
+          mbar_expect_tx(full, STAGE_BYTES);
           tma_load_2d(sb, &ma_hi, ks * TC_BK, mi * 128, full);
-          tma_load_2d(sb + Cfg::MA_BYTES * Cfg::ARR, &nb_hi, ks * TC_BK, nb_row, full);
+          if (!RESW) tma_load_2d(sb + Cfg::MA_BYTES * Cfg::ARR, &nb_hi, ks * TC_BK, nb_row, full);
           if (NPROD == 3) {
             tma_load_2d(sb + Cfg::MA_BYTES, &ma_lo, ks * TC_BK, mi * 128, full);
-            tma_load_2d(sb + Cfg::MA_BYTES * 2 + Cfg::NB_BYTES, &nb_lo, ks * TC_BK, nb_row, full);
+            if (!RESW) tma_load_2d(sb + Cfg::MA_BYTES * 2 + Cfg::NB_BYTES, &nb_lo, ks * TC_BK, nb_row, full);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -318,6 +353,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
       constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
+      if (RESW && blockIdx.x < total_tiles) mbar_wait(bar_res, 0);
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         mbar_wait(bar_tempty + 8 * acc, acc_phase ^ 1);
         tc_fence_after();
@@ -325,9 +361,10 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         for (int ks = 0; ks < k_slabs; ++ks) {
           mbar_wait(bar_full + 8 * stage, phase);
           tc_fence_after();
-          const uint32_t sb = tiles_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = ring_base + stage * STAGE_BYTES;
           const uint32_t a_hi = sb, a_lo = sb + Cfg::MA_BYTES;
-          const uint32_t b_hi = sb + Cfg::MA_BYTES * Cfg::ARR, b_lo = b_hi + Cfg::NB_BYTES;
+          const uint32_t b_hi = RESW ? res_base + (uint32_t)(ks * Cfg::NB_BYTES * Cfg::ARR) : sb + Cfg::MA_BYTES * Cfg::ARR;
+          const uint32_t b_lo = b_hi + Cfg::NB_BYTES;
 #pragma unroll
           for (int kk = 0; kk < TC_BK / 16; ++kk) {
             const uint32_t off = kk * 32;  // 16 bf16 = 32 bytes along K inside the swizzle atom
@@ -601,17 +638,27 @@ template <int ORIENT, int EPI, int BN, int NPROD>
 cudaError_t tc_launch(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& nb_hi, const CUtensorMap& nb_lo,
                       const TcGemmP& p, int num_sms, cudaStream_t s) {
   using Cfg = TcCfg<BN, NPROD>;
+  constexpr bool RESW = TcRes<ORIENT, EPI>::value;
   auto kern = tc_gemm_kernel<ORIENT, EPI, BN, NPROD>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                          RESW ? Cfg::MAX_SMEM : Cfg::SMEM_BYTES);
     if (st != cudaSuccess) return st;
     configured = true;
   }
+  TcGemmP q = p;
+  int smem = Cfg::SMEM_BYTES;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < num_sms ? tiles : num_sms;
+  if (RESW) {
+    q.res_stages = Cfg::res_stages(p.K);
+    if (q.res_stages < 2) return cudaErrorInvalidConfiguration;
+    smem = Cfg::res_smem(p.K);
+    grid -= grid % p.n_tiles;  // every CTA keeps one weight tile: t % n_tiles must not change along its sequence
+  }
   if (grid < 1) return cudaSuccess;
-  kern<<<grid, TcEpi<ORIENT, BN>::THREADS, Cfg::SMEM_BYTES, s>>>(ma_hi, ma_lo, nb_hi, nb_lo, p);
+  kern<<<grid, TcEpi<ORIENT, BN>::THREADS, smem, s>>>(ma_hi, ma_lo, nb_hi, nb_lo, q);
   return cudaPeekAtLastError();
 }
 
