@@ -246,12 +246,15 @@ const float* W(catre_engine* e, const char* name) { return e->dw.at(name); }
 // ---- tensor-core launch helpers ------------------------------------------------------------------
 template <int ORIENT, int EPI, int BN>
 int tc_run(catre_engine* e, cudaStream_t s, int grp, const CUtensorMap& ma_hi, const CUtensorMap& ma_lo,
-           const CUtensorMap& nb_hi, const CUtensorMap& nb_lo, const TcGemmP& p) {
+           const CUtensorMap& nb_hi, const CUtensorMap& nb_lo, const TcGemmP& p, const TcPair* out = nullptr) {
   cudaError_t st;
+  // point-on-lanes layers TMA-store their bf16 hi/lo output through the destination's [64 x 128-row] maps
+  const CUtensorMap& oh = out ? out->map_hi : ma_hi;
+  const CUtensorMap& ol = out ? out->map_lo : ma_lo;
   {
     Launch l(e, s, grp);
-    if (e->cfg.precision == CATRE_PREC_BF16) st = tc_launch<ORIENT, EPI, BN, 1>(ma_hi, ma_lo, nb_hi, nb_lo, p, e->num_sms, s);
-    else st = tc_launch<ORIENT, EPI, BN, 3>(ma_hi, ma_lo, nb_hi, nb_lo, p, e->num_sms, s);
+    if (e->cfg.precision == CATRE_PREC_BF16) st = tc_launch<ORIENT, EPI, BN, 1>(ma_hi, ma_lo, nb_hi, nb_lo, oh, ol, p, e->num_sms, s);
+    else st = tc_launch<ORIENT, EPI, BN, 3>(ma_hi, ma_lo, nb_hi, nb_lo, oh, ol, p, e->num_sms, s);
   }
   if (st != cudaSuccess) {
     cudaGetLastError();
@@ -266,8 +269,8 @@ int tc_split_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& act, 
                    const float* bias, const TcPair& out, long long R) {
   TcGemmP p{};
   p.K = K; p.m_tiles = (int)(R / 128); p.n_tiles = C / BN; p.rows_per_set = e->N;
-  p.bias = bias; p.relu = 1; p.out_hi = out.hi; p.out_lo = out.lo; p.ldo16 = C;
-  return tc_run<PT_ON_LANES, EPI_SPLIT, BN>(e, s, grp, act.map_hi, act.map_lo, w.map_hi, w.map_lo, p);
+  p.bias = bias; p.relu = 1;
+  return tc_run<PT_ON_LANES, EPI_SPLIT, BN>(e, s, grp, act.map_hi, act.map_lo, w.map_hi, w.map_lo, p, &out);
 }
 
 // point-wise layer + column max over the points of each set, channels on TMEM lanes
@@ -391,11 +394,11 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   if (tc) {
     TcGemmP p{};
     p.K = 64; p.m_tiles = (int)(R / 128); p.n_tiles = 1; p.rows_per_set = N; p.nb_per_set = 1;
-    p.out_hi = e->pf16.hi; p.out_lo = e->pf16.lo; p.ldo16 = 64; p.gmax = e->gmax_pf; p.C = 64;
+    p.gmax = e->gmax_pf; p.C = 64;
     if ((rc = tc_run<PT_ON_LANES, EPI_SPLIT_MAX, 64>(e, s, G_FEAT_TRANSFORM, e->x64.map_hi, e->x64.map_lo, e->t64s.map_hi,
-                                                      e->t64s.map_lo, p))) return rc;
+                                                      e->t64s.map_lo, p, &e->pf16))) return rc;
     if ((rc = tc_split_layer<128>(e, s, G_CONV2, e->pf16, e->tw_conv2, 64, 128, W(e, "pcl_net.conv2.bias"), e->a128, R))) return rc;
-    if ((rc = tc_split_layer<256>(e, s, G_CONV3, e->a128, e->tw_conv3, 128, 512, W(e, "pcl_net.conv3.bias"), e->a512, R))) return rc;
+    if ((rc = tc_split_layer<128>(e, s, G_CONV3, e->a128, e->tw_conv3, 128, 512, W(e, "pcl_net.conv3.bias"), e->a512, R))) return rc;
     if ((rc = tc_max_layer(e, s, G_CONV4_MAX, e->tw_conv4, e->a512_nb, 512, 1024, W(e, "pcl_net.conv4.bias"), 0, e->gmax_g, R))) return rc;
   } else {
     GemmP p = gemm_args(e->h64a, 64, e->t64, 64, 64, nullptr, e->h64b, 64, R, 0);
@@ -763,7 +766,7 @@ int catre_pack(catre_engine* e, void* stream) {
     r2 = r2 ? r2 : wpair(e->tw_fstn_c2, H("pcl_net.fstn.conv2.weight"), 128, 64, 128);
     r2 = r2 ? r2 : wpair(e->tw_fstn_c3, H("pcl_net.fstn.conv3.weight"), 1024, 128, 128);
     r2 = r2 ? r2 : wpair(e->tw_conv2, H("pcl_net.conv2.weight"), 128, 64, 128);
-    r2 = r2 ? r2 : wpair(e->tw_conv3, H("pcl_net.conv3.weight"), 512, 128, 256);
+    r2 = r2 ? r2 : wpair(e->tw_conv3, H("pcl_net.conv3.weight"), 512, 128, 128);
     r2 = r2 ? r2 : wpair(e->tw_conv4, H("pcl_net.conv4.weight"), 1024, 512, 128);
     r2 = r2 ? r2 : wpair(e->tw_rot0, w0p, 512, 64, 128);
     if (!r2 && (!tc_make_map(&e->tw_rot0_nb[0], e->tw_rot0.hi, 512, 64, 64, 256) ||

@@ -35,10 +35,8 @@ constexpr int TC_BK = 64;  // K slab = one 128-byte swizzle atom of bf16
 enum { CH_ON_LANES = 0, PT_ON_LANES = 1 };
 // epilogues:            orientation   what leaves the kernel
 //   EPI_MAX             CH_ON_LANES   column max over the tile's points of act(D + bias) -> atomicMax keys
-//   EPI_RAW_STATS       CH_ON_LANES   D + bias + rowvec[set] -> fp32 [R, ldo] and GroupNorm partial sums
 //   EPI_STATS           CH_ON_LANES   GroupNorm partial sums of D + rowvec[set] only (nothing stored)
-//   EPI_SPLIT           PT_ON_LANES   act(D + bias) -> bf16 hi/lo [R, ldo16] (operand of the next layer)
-//   EPI_GN_SPLIT        PT_ON_LANES   gelu(D * sc[set] + sh[set]) -> bf16 hi/lo (GroupNorm + GELU fused)
+//   EPI_SPLIT           PT_ON_LANES   act(D + bias) -> bf16 hi/lo [R, C] (operand of the next layer), TMA-stored
 //   EPI_SPLIT_MAX       PT_ON_LANES   D -> bf16 hi/lo, and column max over the tile's points -> atomicMax keys
 enum { EPI_MAX = 0, EPI_RAW_STATS = 1, EPI_SPLIT = 2, EPI_STATS = 3, EPI_GN_SPLIT = 4, EPI_SPLIT_MAX = 5 };
 
@@ -197,6 +195,22 @@ __device__ __forceinline__ uint32_t pack_bf16(__nv_bfloat16 a, __nv_bfloat16 b) 
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+__device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];" ::"l"(map), "r"(src), "r"(c0),
+               "r"(c1)
+               : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+
 // ------------------------------------------------------------------------------------------------
 // The GEMM kernel
 // ------------------------------------------------------------------------------------------------
@@ -210,58 +224,45 @@ struct TcGemmP {
   const float* bias;     // per output channel (or null)
   int relu;
   int* gmax; int C;                             // EPI_MAX / EPI_SPLIT_MAX: keys [S, C]
-  float* out; int rows_per_obj;                 // EPI_RAW_STATS: fp32 channel-major [obj][out_ch_per_obj][rows_per_obj]
-  long long out_obj_stride;                     //   = out_ch_per_obj * rows_per_obj (out already points at the first channel)
-  const float* rowvec; int ldrv;                // EPI_RAW_STATS / EPI_STATS: per-set additive vector [S, ldrv]
-  float* stats; int stats_ld, stats_goff;       // GroupNorm partials [R/(BN/2), stats_ld, 2]
-  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo; int ldo16;  // EPI_*SPLIT*: bf16 [R, ldo16]
-  const float* gn_scale; const float* gn_shift; int ldgn;   // EPI_GN_SPLIT: per (set, channel) affine
+  const float* rowvec; int ldrv;                // EPI_STATS: per-set additive vector [S, ldrv]
+  float* stats; int stats_ld, stats_goff;       // EPI_STATS: GroupNorm partials [R/(BN/2), stats_ld, 2]
 };
 
-template <int BN, int NPROD>
+template <int ORIENT, int BN, int NPROD>
 struct TcCfg {
   static constexpr int ARR = (NPROD == 3) ? 2 : 1;  // hi (+ lo) arrays per operand
   static constexpr int MA_BYTES = 128 * 128;        // 128 rows x 64 bf16
   static constexpr int NB_BYTES = BN * 128;
+  static constexpr int MAX_SMEM = 227 * 1024;
+  static constexpr int BIAS_BYTES = (ORIENT == 1) ? 2048 : 4096;  // <= 512 (points on lanes) / 1024 channels
+  // point-on-lanes layers stage their bf16 hi/lo output tile in shared memory for the TMA store engine:
+  // BN/64 boxes of [128 rows x 64 channels] per array
+  static constexpr int OUT_BYTES = (ORIENT == 1) ? (BN / 64) * 16384 * ARR : 0;
+  static constexpr int FIXED = 1024 + BIAS_BYTES + OUT_BYTES;  // barriers | ... | output staging | bias
+  // streaming both operands
   static constexpr int STAGE_BYTES = (MA_BYTES + NB_BYTES) * ARR;
-  static constexpr int STAGES = (200 * 1024 / STAGE_BYTES) > 4 ? 4 : (200 * 1024 / STAGE_BYTES);
-  static constexpr int BIAS_BYTES = 4096;                          // per-channel bias of the layer (<= 1024 channels)
-  static constexpr int SMEM_BYTES = 1024 + STAGES * STAGE_BYTES + BIAS_BYTES;  // barriers | stages | bias
+  static constexpr int STAGES = ((MAX_SMEM - FIXED) / STAGE_BYTES) > 4 ? 4 : ((MAX_SMEM - FIXED) / STAGE_BYTES);
+  static constexpr int SMEM_BYTES = FIXED + STAGES * STAGE_BYTES;
   // resident-weight variant (point-on-lanes layers with a fixed weight operand): all K slabs of the CTA's
   // BN weight rows stay in shared memory for the whole kernel; only the activation tiles stream.
   static constexpr int RES_STAGE_BYTES = MA_BYTES * ARR;
-  static constexpr int MAX_SMEM = 227 * 1024;
-  static constexpr int RES_BIAS_BYTES = 2048;  // point-on-lanes layers have <= 512 output channels
   static int res_bytes(int K) { return (K / 64) * NB_BYTES * ARR; }
   static int res_stages(int K) {
-    int st = (MAX_SMEM - 1024 - RES_BIAS_BYTES - res_bytes(K)) / RES_STAGE_BYTES;
+    int st = (MAX_SMEM - FIXED - res_bytes(K)) / RES_STAGE_BYTES;
     return st > 4 ? 4 : st;
   }
-  static int res_smem(int K) { return 1024 + res_bytes(K) + res_stages(K) * RES_STAGE_BYTES + RES_BIAS_BYTES; }
+  static int res_smem(int K) { return FIXED + res_bytes(K) + res_stages(K) * RES_STAGE_BYTES; }
 };
 // weights stay resident for the plain point-on-lanes layers (bias/ReLU/split epilogue)
 template <int ORIENT, int EPI>
 struct TcRes { static constexpr bool value = (ORIENT == 1 && EPI == 2); };
 
-// 32 columns of one point row: fp32 -> bf16 hi/lo, written as full 32-byte sectors (st.global.v8)
-template <int NPROD>
-__device__ __forceinline__ void store_split32(const float* x, __nv_bfloat16* dst_hi, __nv_bfloat16* dst_lo) {
-  uint32_t hi[16], lo[16];
-#pragma unroll
-  for (int j = 0; j < 32; j += 2) split_bf16x2(x[j], x[j + 1], hi[j >> 1], lo[j >> 1]);
-  st_global_256(dst_hi, hi);
-  st_global_256(dst_hi + 16, hi + 8);
-  if (NPROD == 3) {
-    st_global_256(dst_lo, lo);
-    st_global_256(dst_lo + 16, lo + 8);
-  }
-}
-
 template <int ORIENT, int EPI, int BN, int NPROD>
 __global__ void __launch_bounds__(TcEpi<ORIENT, BN>::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant__ CUtensorMap ma_lo,
-               const __grid_constant__ CUtensorMap nb_hi, const __grid_constant__ CUtensorMap nb_lo, const TcGemmP p) {
-  using Cfg = TcCfg<BN, NPROD>;
+               const __grid_constant__ CUtensorMap nb_hi, const __grid_constant__ CUtensorMap nb_lo,
+               const __grid_constant__ CUtensorMap out_hi, const __grid_constant__ CUtensorMap out_lo, const TcGemmP p) {
+  using Cfg = TcCfg<ORIENT, BN, NPROD>;
   constexpr bool RESW = TcRes<ORIENT, EPI>::value;
   const int STAGES = RESW ? p.res_stages : Cfg::STAGES;
   constexpr int STAGE_BYTES = RESW ? Cfg::RES_STAGE_BYTES : Cfg::STAGE_BYTES;
@@ -270,8 +271,9 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
   constexpr int HALF = BN / PARTS;     // columns per epilogue warp
   constexpr int NCHUNK = HALF / 32;    // 32-column chunks per epilogue warp
   constexpr bool PIPE = (EW == 8);
-  static_assert(HALF % 32 == 0, "each epilogue warp needs whole 32-column chunks");
   static_assert(BN % 64 == 0 && BN <= 256, "BN must be 64, 128 or 256");
+  static_assert(HALF % 32 == 0, "each epilogue warp needs whole 32-column chunks");
+  static_assert(ORIENT == CH_ON_LANES || HALF == 32, "point-on-lanes epilogues handle one 32-column chunk per warp");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   if (smem_base & 1023u) __trap();                 // the 128B-swizzled tiles need a 1 KB aligned base
@@ -281,10 +283,11 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
   const uint32_t bar_tfull = smem_base + 64, bar_tempty = bar_tfull + 16;
   const uint32_t bar_res = bar_tempty + 16;
   const uint32_t tmem_slot = bar_res + 8;
-  // resident weights (RESW): [k slab][hi | lo][BN rows x 128 B] right after the barrier block, then the stage ring
+  // layout after the barrier block: [resident weights (RESW)] [stage ring] [output staging (PT)] [bias]
   const uint32_t res_base = tiles_base;
   const uint32_t ring_base = RESW ? tiles_base + (uint32_t)((p.K / TC_BK) * Cfg::NB_BYTES * Cfg::ARR) : tiles_base;
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (ring_base - smem_base) + (uint32_t)STAGES * STAGE_BYTES);  // tail
+  const uint32_t ostage_base = ring_base + (uint32_t)STAGES * STAGE_BYTES;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (ostage_base - smem_base) + Cfg::OUT_BYTES);
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -294,13 +297,14 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&ma_hi); prefetch_tmap(&nb_hi);
     if (NPROD == 3) { prefetch_tmap(&ma_lo); prefetch_tmap(&nb_lo); }
+    if (ORIENT == PT_ON_LANES) { prefetch_tmap(&out_hi); if (NPROD == 3) prefetch_tmap(&out_lo); }
     for (int i = 0; i < STAGES; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_tfull + 8 * i, 1); mbar_init(bar_tempty + 8 * i, EW); }
     mbar_init(bar_res, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (p.bias) {  // per-channel bias of the whole layer (<= 1024 channels) staged once
+  if (p.bias) {  // per-channel bias of the whole layer staged once
     const int nbias = (ORIENT == CH_ON_LANES) ? p.m_tiles * 128 : p.n_tiles * BN;
     for (int i = threadIdx.x; i < nbias; i += TC_THREADS) s_bias[i] = p.bias[i];
   }
@@ -383,7 +387,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
     }
   } else {
     // ===================== epilogue warps =====================
-    // warp w may touch TMEM lanes 32*(w%4) .. +31; the two warps of a quadrant split the BN columns
+    // warp w may touch TMEM lanes 32*(w%4) .. +31; the PARTS warps of a quadrant split the BN columns
     const int quad = warp & 3, half = (warp - 2) >> 2;
     const int lane_row = quad * 32 + lane;
     int acc = 0; uint32_t acc_phase = 0;
@@ -403,30 +407,19 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         if (p.relu) m = fmaxf(m, 0.f);
         const int set = (ni * BN) / p.rows_per_set;
         atomicMax(p.gmax + (long long)set * p.C + ch, f2key(m));
-      } else if (EPI == EPI_RAW_STATS || EPI == EPI_STATS) {
+      } else if (EPI == EPI_STATS) {
         const int ch = mi * 128 + lane_row;
         const long long p0 = (long long)ni * BN + half * HALF;
         const int set = (int)(p0 / p.rows_per_set);
         float add = p.bias ? s_bias[ch] : 0.f;
         if (p.rowvec) add += p.rowvec[(long long)set * p.ldrv + ch];
         float s = 0.f, ss = 0.f;
-        float* orow = nullptr;
-        if (EPI == EPI_RAW_STATS) {  // this thread's channel row of the object, at the tile's first point
-          const long long obj = p0 / p.rows_per_obj;
-          orow = p.out + obj * p.out_obj_stride + (long long)ch * p.rows_per_obj + (p0 - obj * p.rows_per_obj);
-        }
-        tmem_foreach32<NCHUNK, PIPE>(taddr, [&](int c, const float* v) {
-          float x[32];
+        tmem_foreach32<NCHUNK, PIPE>(taddr, [&](int, const float* v) {
 #pragma unroll
           for (int j = 0; j < 32; ++j) {
-            x[j] = v[j] + add;
-            s += x[j];
-            ss = fmaf(x[j], x[j], ss);
-          }
-          if (EPI == EPI_RAW_STATS) {  // 32 consecutive points of one channel: 128 contiguous bytes
-            const uint32_t* xu = reinterpret_cast<const uint32_t*>(x);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) st_global_256(orow + c * 32 + q * 8, xu + q * 8);
+            const float x = v[j] + add;
+            s += x;
+            ss = fmaf(x, x, ss);
           }
         });
         s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
@@ -437,60 +430,81 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
           p.stats[o] = s;
           p.stats[o + 1] = ss;
         }
-      } else {  // PT_ON_LANES epilogues: lane = point row, columns = channels
-        const long long row = (long long)mi * 128 + lane_row;
-        const int n0 = ni * BN + half * HALF;
+      } else {
+        // PT_ON_LANES epilogues: lane = point row, this warp's 32 channels n0 .. n0+31.  The bf16 hi/lo
+        // tile is staged in shared memory as 128B-swizzled [128 rows x 64 channels] boxes and written by
+        // the TMA store engine (coalesced, asynchronous).  The GW warps that share a 64-channel box form
+        // a group with its own named barrier; one of its threads issues and tracks the group's stores.
+        constexpr int GW = (64 / HALF) * 4;               // warps per 64-channel box
+        const int box = (half * HALF) / 64;                // box index within the tile
+        const bool issuer = (quad == 0) && ((half * HALF) % 64 == 0) && (lane == 0);
+        const int n0 = half * HALF;                        // first channel of this warp within the tile
         const int set = (mi * 128) / p.rows_per_set;
-        tmem_foreach32<NCHUNK, PIPE>(taddr, [&](int c, const float* v) {
-          const int col = n0 + c * 32;
-          float x[32];
-          if (EPI == EPI_GN_SPLIT) {
-            const float4* sc4 = reinterpret_cast<const float4*>(p.gn_scale + (long long)set * p.ldgn + col);
-            const float4* sh4 = reinterpret_cast<const float4*>(p.gn_shift + (long long)set * p.ldgn + col);
+        float x[32];
+        {
+          float v[32];
+          tmem_ld32(taddr, v);
+          tmem_ld_wait32(v);
 #pragma unroll
-            for (int j = 0; j < 8; ++j) {  // all lanes read the same address: one broadcast transaction
-              const float4 a = __ldg(sc4 + j), b = __ldg(sh4 + j);
-              x[4 * j + 0] = gelu_fast(fmaf(v[4 * j + 0], a.x, b.x));
-              x[4 * j + 1] = gelu_fast(fmaf(v[4 * j + 1], a.y, b.y));
-              x[4 * j + 2] = gelu_fast(fmaf(v[4 * j + 2], a.z, b.z));
-              x[4 * j + 3] = gelu_fast(fmaf(v[4 * j + 3], a.w, b.w));
-            }
-          } else {
+          for (int j = 0; j < 32; j += 4) {
+            float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (p.bias) b4 = *reinterpret_cast<const float4*>(s_bias + ni * BN + n0 + j);  // broadcast LDS.128
+            x[j + 0] = v[j + 0] + b4.x; x[j + 1] = v[j + 1] + b4.y;
+            x[j + 2] = v[j + 2] + b4.z; x[j + 3] = v[j + 3] + b4.w;
+          }
+          if (p.relu) {
 #pragma unroll
-            for (int j = 0; j < 32; j += 4) {
-              float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (p.bias) b4 = *reinterpret_cast<const float4*>(s_bias + col + j);  // broadcast LDS.128
-              x[j + 0] = v[j + 0] + b4.x; x[j + 1] = v[j + 1] + b4.y;
-              x[j + 2] = v[j + 2] + b4.z; x[j + 3] = v[j + 3] + b4.w;
-            }
-            if (p.relu) {
+            for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
+        }
+        uint32_t hi[16], lo[16];
 #pragma unroll
-              for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+        for (int j = 0; j < 32; j += 2) split_bf16x2(x[j], x[j + 1], hi[j >> 1], lo[j >> 1]);
+        // the group's previous stores must have finished reading the staging box
+        if (issuer) tma_store_wait_read();
+        named_bar_sync(1 + box, GW * 32);
+        {
+          const uint32_t bhi = ostage_base + (uint32_t)(box * 16384 * Cfg::ARR) + (uint32_t)lane_row * 128;
+          const uint32_t c0 = (uint32_t)((n0 % 64) / 8), sw = (uint32_t)(lane_row & 7);
+#pragma unroll
+          for (int q = 0; q < 4; ++q)
+            st_shared_v4(bhi + (((c0 + q) ^ sw) << 4), hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+          if (NPROD == 3) {
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+              st_shared_v4(bhi + 16384 + (((c0 + q) ^ sw) << 4), lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+          }
+        }
+        fence_proxy_async_smem();
+        named_bar_sync(1 + box, GW * 32);
+        if (issuer) {
+          const uint32_t src = ostage_base + (uint32_t)(box * 16384 * Cfg::ARR);
+          tma_store_2d(&out_hi, src, ni * BN + box * 64, mi * 128);
+          if (NPROD == 3) tma_store_2d(&out_lo, src + 16384, ni * BN + box * 64, mi * 128);
+          tma_store_commit();
+        }
+        if (EPI == EPI_SPLIT_MAX) {
+          // column max over the warp's 32 rows: butterfly that halves the live columns each step;
+          // afterwards x[0] of lane l is the max of channel n0 + l
+#pragma unroll
+          for (int w = 16; w >= 1; w >>= 1) {
+            const bool upper = (lane & w) != 0;
+#pragma unroll
+            for (int j = 0; j < w; ++j) {
+              const float mine = upper ? x[j + w] : x[j];
+              const float give = upper ? x[j] : x[j + w];
+              x[j] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, give, w));
             }
           }
-          store_split32<NPROD>(x, p.out_hi + row * p.ldo16 + col, p.out_lo + row * p.ldo16 + col);
-          if (EPI == EPI_SPLIT_MAX) {
-            // column max over the warp's 32 rows: butterfly that halves the live columns each step;
-            // afterwards x[0] of lane l is the max of column col + l
-#pragma unroll
-            for (int w = 16; w >= 1; w >>= 1) {
-              const bool upper = (lane & w) != 0;
-#pragma unroll
-              for (int j = 0; j < w; ++j) {
-                const float mine = upper ? x[j + w] : x[j];
-                const float give = upper ? x[j] : x[j + w];
-                x[j] = fmaxf(mine, __shfl_xor_sync(0xffffffffu, give, w));
-              }
-            }
-            atomicMax(p.gmax + (long long)set * p.C + col + lane, f2key(x[0]));
-          }
-        });
+          atomicMax(p.gmax + (long long)set * p.C + ni * BN + n0 + lane, f2key(x[0]));
+        }
       }
       tc_fence_before();
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_tempty + 8 * acc);
       if (++acc == 2) { acc = 0; acc_phase ^= 1; }
     }
+    if (ORIENT == PT_ON_LANES && quad == 0 && ((half * HALF) % 64 == 0) && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -636,8 +650,8 @@ inline bool tc_make_map_f16(CUtensorMap* m, const void* base, uint64_t rows, uin
 
 template <int ORIENT, int EPI, int BN, int NPROD>
 cudaError_t tc_launch(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const CUtensorMap& nb_hi, const CUtensorMap& nb_lo,
-                      const TcGemmP& p, int num_sms, cudaStream_t s) {
-  using Cfg = TcCfg<BN, NPROD>;
+                      const CUtensorMap& out_hi, const CUtensorMap& out_lo, const TcGemmP& p, int num_sms, cudaStream_t s) {
+  using Cfg = TcCfg<ORIENT, BN, NPROD>;
   constexpr bool RESW = TcRes<ORIENT, EPI>::value;
   auto kern = tc_gemm_kernel<ORIENT, EPI, BN, NPROD>;
   static bool configured = false;
@@ -658,7 +672,7 @@ cudaError_t tc_launch(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const 
     grid -= grid % p.n_tiles;  // every CTA keeps one weight tile: t % n_tiles must not change along its sequence
   }
   if (grid < 1) return cudaSuccess;
-  kern<<<grid, TcEpi<ORIENT, BN>::THREADS, smem, s>>>(ma_hi, ma_lo, nb_hi, nb_lo, q);
+  kern<<<grid, TcEpi<ORIENT, BN>::THREADS, smem, s>>>(ma_hi, ma_lo, nb_hi, nb_lo, out_hi, out_lo, q);
   return cudaPeekAtLastError();
 }
 
