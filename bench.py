@@ -189,7 +189,9 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=dev)
+        import datetime
+
+        dist.init_process_group("nccl", device_id=dev, timeout=datetime.timedelta(seconds=180))
     B, N, K = args.batch, args.n_pts, args.n_iter
     total_B = B * world
 
@@ -272,9 +274,10 @@ def main():
     if rank == 0:
         eng.profile_enable(True)
         eng.profile_reset()
-        for i in range(args.steps):
+        for i in range(args.steps):  # rank-0 only: no collective in here
             flush.fill_(i & 0xFF)
-            step_device(i)
+            b = devb[i % n_rot]
+            eng.refine(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, K, out=out_dev)
         torch.cuda.synchronize()
         prof = eng.profile()
         eng.profile_enable(False)
