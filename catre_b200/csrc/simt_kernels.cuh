@@ -24,22 +24,25 @@ constexpr int KEY_NEG_INF = (int)0x807fffff;  // f2key(-inf)
 // exact GELU (nn.GELU default, lib/torch_utils/layers/layer_utils.py:61-95 "gelu")
 __device__ __forceinline__ float gelu_exact(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752440f)); }
 
-// GELU for the tensor-core modes' fused epilogues: one MUFU, 14 FP32 ops, branch-free.
-//   gelu(x) = max(x, 0) - |x/2| erfc(|x|/sqrt2),   erfc(z) = 2^p(z),  p = degree-9 fit of log2(erfc) on
-//   [0, 4.2] (beyond 4.2 erfc < 3e-9 and z is clamped).  Max |gelu err| vs fp64 over [-12, 12]: 2.4e-7
-//   (the erff-based fp32 GELU itself is 1.2e-6 off), no cancellation on the negative side.
+// GELU for the tensor-core modes' fused epilogues: one MUFU, 12 FP32 ops, branch-free.
+//   gelu(x) = max(x, 0) - |x| * (erfc(|x|/sqrt2) / 2),   erfc(z)/2 = 2^p(|x|),  p = degree-9 fit of
+//   log2(erfc(z)) on z in [0, 4.2] re-expressed in |x| = z sqrt2 with the -1 (the 1/2) folded into c0; beyond
+//   |x| = 5.94 erfc < 3e-9 and |x| is clamped.  Max |gelu err| vs fp64 over [-12, 12]: 2.4e-7 (the
+//   erff-based fp32 GELU itself is 1.2e-6 off), no cancellation on the negative side.
 __device__ __forceinline__ float gelu_fast(float x) {
-  const float z = fminf(fabsf(x) * 0.70710678118654752440f, 4.2f);
-  float p = fmaf(5.4279603e-06f, z, -8.880036e-05f);
-  p = fmaf(p, z, 0.0005802389f);
-  p = fmaf(p, z, -0.0016933879f);
-  p = fmaf(p, z, -0.00062220806f);
-  p = fmaf(p, z, 0.028209634f);
-  p = fmaf(p, z, -0.1484874f);
-  p = fmaf(p, z, -0.91841096f);
-  p = fmaf(p, z, -1.6279094f);
-  p = fmaf(p, z, 2.3326544e-08f);
-  return fmaf(-fabsf(0.5f * x), exp2f(p), fmaxf(x, 0.0f));
+  const float z = fminf(fabsf(x), 5.939697f);
+  float p = fmaf(2.3988423e-07f, z, -5.5500227e-06f);
+  p = fmaf(p, z, 5.128636e-05f);
+  p = fmaf(p, z, -0.00021167348f);
+  p = fmaf(p, z, -0.00010999188f);
+  p = fmaf(p, z, 0.0070524085f);
+  p = fmaf(p, z, -0.052498225f);
+  p = fmaf(p, z, -0.45920548f);
+  p = fmaf(p, z, -1.1511058f);
+  p = fmaf(p, z, -1.0f);
+  float e;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));  // p in [-28, -1]: no range fix-up needed
+  return fmaf(-fabsf(x), e, fmaxf(x, 0.0f));
 }
 template <int FAST>
 __device__ __forceinline__ float gelu_sel(float x) { return FAST ? gelu_fast(x) : gelu_exact(x); }
