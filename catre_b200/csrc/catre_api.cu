@@ -301,10 +301,15 @@ int run_fc(catre_engine* e, cudaStream_t s, int grp, const float* A, int lda, co
   p.out_hi = out16 ? reinterpret_cast<unsigned short*>(out16->hi) : nullptr;
   p.out_lo = out16 ? reinterpret_cast<unsigned short*>(out16->lo) : nullptr;
   p.R = R; p.C = C; p.K = K; p.relu = relu;
-  dim3 grid((C + 63) / 64, (R + 127) / 128, FC_KSPLIT);
   {
     Launch l(e, s, grp);
-    fc_cluster_kernel<AMODE><<<grid, 256, 0, s>>>(p);
+    if ((long long)((C + 63) / 64) * ((R + 127) / 128) >= 32) {  // enough 128 x 64 tiles to fill the GPU with 8-CTA clusters
+      dim3 grid((C + 63) / 64, (R + 127) / 128, FC_KSPLIT);
+      fc_cluster_kernel<AMODE, 128, 64, 256><<<grid, 256, 0, s>>>(p);
+    } else {
+      dim3 grid((C + 31) / 32, (R + 63) / 64, FC_KSPLIT);
+      fc_cluster_kernel<AMODE, 64, 32, 128><<<grid, 128, 0, s>>>(p);
+    }
   }
   return check_launch(e, kGrpNames[grp]);
 }

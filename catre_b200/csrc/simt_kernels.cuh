@@ -425,31 +425,40 @@ struct FcP {
   int relu;
 };
 
-template <int AMODE>
-__global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(256) fc_cluster_kernel(FcP p) {
+// Tile shapes: 128 x 64 outputs on 256 threads (8 x 4 per thread) when there are many rows, 64 x 32 on 128
+// threads (4 x 4 per thread) when R is small, so that a layer still spreads over >= 128 CTAs.
+template <int AMODE, int BM, int BN, int NT>
+__global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(NT) fc_cluster_kernel(FcP p) {
   namespace cg = cooperative_groups;
-  constexpr int BM = 128, BN = 64, BK = 16, DEPTH = 4;
+  constexpr int BK = 16, DEPTH = 4;
+  constexpr int TM = BM * BN / NT / 4;     // rows per thread (8 or 4); 4 columns per thread
+  constexpr int TXN = BN / 4;              // threads along the columns
+  constexpr int A_IT = BM * BK / 4 / NT;   // float4 loads of the A chunk per thread
+  constexpr int W_IT = (BN * BK / 4 + NT - 1) / NT;
+  static_assert(TM == 8 || TM == 4, "unsupported tile");
+  static_assert(BM * BK / 4 % NT == 0 && NT / TXN * (TM == 8 ? 8 : 4) == BM, "tile / thread mismatch");
   __shared__ __align__(16) float As[BK][BM + 4];
   __shared__ __align__(16) float Ws[BK][BN + 4];
   __shared__ __align__(16) float part[BM][BN];
   cg::cluster_group cluster = cg::this_cluster();
   const int rank = (int)cluster.block_rank();  // == blockIdx.z (cluster spans grid.z)
 
-  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int tid = threadIdx.x, tx = tid % TXN, ty = tid / TXN;
   const int r0 = blockIdx.y * BM, c0 = blockIdx.x * BN;
   const int kz = p.K / FC_KSPLIT, k_begin = rank * kz, nsteps = kz / BK;
+  auto row_of = [&](int i) { return (TM == 8) ? ((i < 4) ? ty * 4 + i : BM / 2 + ty * 4 + (i - 4)) : ty * 4 + i; };
 
-  float acc[8][4];
+  float acc[TM][4];
 #pragma unroll
-  for (int i = 0; i < 8; ++i)
+  for (int i = 0; i < TM; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
 
-  float4 areg[DEPTH][2], wreg[DEPTH];
+  float4 areg[DEPTH][A_IT], wreg[DEPTH][W_IT];
   auto load_chunk = [&](int slot, int k0) {
 #pragma unroll
-    for (int it = 0; it < 2; ++it) {
-      const int e = tid + it * 256, row = e >> 2, kq = (e & 3) * 4;
+    for (int it = 0; it < A_IT; ++it) {
+      const int e = tid + it * NT, row = e >> 2, kq = (e & 3) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (r0 + row < p.R) {
         const float* src = p.A + (long long)(r0 + row) * p.lda + k0 + kq;
@@ -462,11 +471,12 @@ __global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(256) fc_clus
       }
       areg[slot][it] = v;
     }
-    {
-      const int col = tid >> 2, kq = (tid & 3) * 4;
+#pragma unroll
+    for (int it = 0; it < W_IT; ++it) {
+      const int e = tid + it * NT, col = e >> 2, kq = (e & 3) * 4;
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
-      if (c0 + col < p.C) v = *reinterpret_cast<const float4*>(p.W + (long long)(c0 + col) * p.ldw + k0 + kq);
-      wreg[slot] = v;
+      if (col < BN && c0 + col < p.C) v = *reinterpret_cast<const float4*>(p.W + (long long)(c0 + col) * p.ldw + k0 + kq);
+      wreg[slot][it] = v;
     }
   };
 
@@ -478,24 +488,28 @@ __global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(256) fc_clus
     for (int d = 0; d < DEPTH; ++d) {
       if (s0 + d < nsteps) {
 #pragma unroll
-        for (int it = 0; it < 2; ++it) {
-          const int e = tid + it * 256, row = e >> 2, kq = (e & 3) * 4;
+        for (int it = 0; it < A_IT; ++it) {
+          const int e = tid + it * NT, row = e >> 2, kq = (e & 3) * 4;
           As[kq + 0][row] = areg[d][it].x; As[kq + 1][row] = areg[d][it].y;
           As[kq + 2][row] = areg[d][it].z; As[kq + 3][row] = areg[d][it].w;
         }
-        {
-          const int col = tid >> 2, kq = (tid & 3) * 4;
-          Ws[kq + 0][col] = wreg[d].x; Ws[kq + 1][col] = wreg[d].y; Ws[kq + 2][col] = wreg[d].z; Ws[kq + 3][col] = wreg[d].w;
+#pragma unroll
+        for (int it = 0; it < W_IT; ++it) {
+          const int e = tid + it * NT, col = e >> 2, kq = (e & 3) * 4;
+          if (col < BN) {
+            Ws[kq + 0][col] = wreg[d][it].x; Ws[kq + 1][col] = wreg[d][it].y;
+            Ws[kq + 2][col] = wreg[d][it].z; Ws[kq + 3][col] = wreg[d][it].w;
+          }
         }
         __syncthreads();
 #pragma unroll
         for (int kk = 0; kk < BK; ++kk) {
-          float a[8], w[4];
+          float a[TM], w[4];
           *reinterpret_cast<float4*>(&a[0]) = *reinterpret_cast<const float4*>(&As[kk][ty * 4]);
-          *reinterpret_cast<float4*>(&a[4]) = *reinterpret_cast<const float4*>(&As[kk][64 + ty * 4]);
+          if (TM == 8) *reinterpret_cast<float4*>(&a[TM - 4]) = *reinterpret_cast<const float4*>(&As[kk][BM / 2 + ty * 4]);
           *reinterpret_cast<float4*>(&w[0]) = *reinterpret_cast<const float4*>(&Ws[kk][tx * 4]);
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int i = 0; i < TM; ++i)
 #pragma unroll
             for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
         }
@@ -503,16 +517,15 @@ __global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(256) fc_clus
       }
     }
   }
-  // park the partial tile: thread's rows ty*4+i (i<4), 64+ty*4+(i-4); columns tx*4 ..
+  // park the partial tile
 #pragma unroll
-  for (int i = 0; i < 8; ++i) {
-    const int row = (i < 4) ? ty * 4 + i : 64 + ty * 4 + (i - 4);
-    *reinterpret_cast<float4*>(&part[row][tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
-  }
+  for (int i = 0; i < TM; ++i)
+    *reinterpret_cast<float4*>(&part[row_of(i)][tx * 4]) = make_float4(acc[i][0], acc[i][1], acc[i][2], acc[i][3]);
   cluster.sync();
-  // CTA `rank` finishes rows rank*16 .. +15 of the tile: 16 x 64 values = one float4 per thread
-  {
-    const int row = rank * (BM / FC_KSPLIT) + (tid >> 4), col = (tid & 15) * 4;
+  // CTA `rank` finishes rows rank*BM/8 .. of the tile: (BM/8) x BN values, one float4 per thread
+  constexpr int RROWS = BM / FC_KSPLIT, RV = RROWS * BN / 4;
+  if (tid < RV) {
+    const int row = rank * RROWS + tid / (BN / 4), col = (tid % (BN / 4)) * 4;
     float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
     for (int z = 0; z < FC_KSPLIT; ++z) {
