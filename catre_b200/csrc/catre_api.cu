@@ -103,6 +103,9 @@ struct catre_engine {
   // the MMA), "NB" maps have BN-row boxes (N side)
   TcPair tw_stn_c2, tw_stn_c3, tw_fstn_c1, tw_fstn_c2, tw_fstn_c3, tw_conv2, tw_conv3, tw_conv4, tw_rot0;
   TcPair tw_rot1s;            // both heads' layers.3 weights stacked [512, 256] (fused rot kernel)
+  cudaStream_t side = nullptr;           // the ts head runs here, underneath the rot-head kernels
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  float* dts = nullptr;                  // [B, 6] raw ts-head outputs
   long long* rf_dbg = nullptr;  // timeline buffer of the fused rot kernel (CATRE_RF_DEBUG=1)
   CUtensorMap tw_rot0_nb[2];  // rot layer-0 point-feature weights [512, 64] as an N-side operand (256-row boxes)
   float *fstn_fc3_wT = nullptr;  // fstn.fc3 rows permuted so the FC emits T64^T (row j = output channel j of pf = h1 . T64)
@@ -419,6 +422,31 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV4_MAX, p))) return rc;
   }
 
+  // ---- H1 on the side stream (needs only the max-pooled features; independent of the rot head).  ts-head
+  //      layer 0 over the 1024 global-feature inputs of the OBSERVED set (row b -> set 2b) is a cluster FC;
+  //      the remaining 67 inputs (pointfeat max, init scale) are added in ts_head_kernel.
+  TsPoseP tsp{};
+  {
+    tsp.ts0 = e->ts0; tsp.gmax_pf = e->gmax_pf; tsp.dts = e->dts;
+    tsp.w0t = e->ts_w0t; tsp.g0 = W(e, "ts_head.linears.1.weight"); tsp.be0 = W(e, "ts_head.linears.1.bias");
+    tsp.w1t = e->ts_w1t; tsp.b1 = W(e, "ts_head.linears.3.bias"); tsp.g1 = W(e, "ts_head.linears.4.weight");
+    tsp.be1 = W(e, "ts_head.linears.4.bias");
+    tsp.wt = W(e, "ts_head.fc_t.weight"); tsp.bt = W(e, "ts_head.fc_t.bias");
+    tsp.ws = W(e, "ts_head.fc_s.weight"); tsp.bs = W(e, "ts_head.fc_s.bias");
+    tsp.rot_partial = e->rot_partial; tsp.rot_tiles = tc ? 16 : P / 128; tsp.convp_bias = e->convp_b;
+    tsp.pose_in = pose_in; tsp.scale_in = scale_in; tsp.K = K; tsp.pose_out = pose_out; tsp.scale_out = scale_out;
+    CU_TRY(e, cudaEventRecord(e->ev_fork, s));
+    CU_TRY(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
+    if ((rc = run_fc<A_KEY>(e, e->side, G_TS_POSE, reinterpret_cast<const float*>(e->gmax_g), 2048, e->ts_w0g, 1024,
+                            W(e, "ts_head.linears.0.bias"), B, 256, 1024, 0, e->ts0, nullptr))) return rc;
+    {
+      Launch l(e, e->side, G_TS_POSE);
+      ts_head_kernel<<<B, 256, 0, e->side>>>(tsp);
+    }
+    if ((rc = check_launch(e, "ts_head"))) return rc;
+    CU_TRY(e, cudaEventRecord(e->ev_join, e->side));
+  }
+
   // ---- R1: rotation heads (heads/conv_out_per_rot_head.py:62-71,126-140) with the layer-0 split:
   //      layers.0 . [g_set | pf_p] = W0[:, :1024] . g_set (once per set) + W0[:, 1024:] . pf_p
   {
@@ -498,25 +526,13 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   }
   if ((rc = check_launch(e, "rot_tail"))) return rc;
 
-  // ---- H1 + G1 + G2.  ts-head layer 0 over the 1024 global-feature inputs of the OBSERVED set (row b -> set 2b)
-  //      runs as a cluster FC; the remaining 67 inputs (pointfeat max, init scale) are added in ts_pose.
-  if ((rc = run_fc<A_KEY>(e, s, G_TS_POSE, reinterpret_cast<const float*>(e->gmax_g), 2048, e->ts_w0g, 1024,
-                          W(e, "ts_head.linears.0.bias"), B, 256, 1024, 0, e->ts0, nullptr))) return rc;
+  // ---- G1 + G2 after both heads: join the side stream, then rot6d Gram-Schmidt + pose update
+  CU_TRY(e, cudaStreamWaitEvent(s, e->ev_join, 0));
   {
-    TsPoseP p{};
-    p.ts0 = e->ts0; p.gmax_pf = e->gmax_pf;
-    p.w0t = e->ts_w0t; p.g0 = W(e, "ts_head.linears.1.weight");
-    p.be0 = W(e, "ts_head.linears.1.bias");
-    p.w1t = e->ts_w1t; p.b1 = W(e, "ts_head.linears.3.bias"); p.g1 = W(e, "ts_head.linears.4.weight");
-    p.be1 = W(e, "ts_head.linears.4.bias");
-    p.wt = W(e, "ts_head.fc_t.weight"); p.bt = W(e, "ts_head.fc_t.bias");
-    p.ws = W(e, "ts_head.fc_s.weight"); p.bs = W(e, "ts_head.fc_s.bias");
-    p.rot_partial = e->rot_partial; p.rot_tiles = tc ? 16 : P / 128; p.convp_bias = e->convp_b;
-    p.pose_in = pose_in; p.scale_in = scale_in; p.K = K; p.pose_out = pose_out; p.scale_out = scale_out;
     Launch l(e, s, G_TS_POSE);
-    ts_pose_kernel<<<B, 256, 0, s>>>(p);
+    pose_update_kernel<<<(B + 7) / 8, 256, 0, s>>>(tsp, B);
   }
-  return check_launch(e, "ts_pose");
+  return check_launch(e, "pose_update");
 }
 
 int check_ready(catre_engine* e, int B) {
@@ -588,6 +604,7 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   rc |= dalloc(e, &e->fc512, S * 512);
   rc |= dalloc(e, &e->fc256, S * 256);
   rc |= dalloc(e, &e->ts0, B * 256);
+  rc |= dalloc(e, &e->dts, B * 6);
   rc |= dalloc(e, &e->t3, S * 9 + 7);
   rc |= dalloc(e, &e->cset, S * 512);
   rc |= dalloc(e, &e->stats0, (R / 128) * 64 * 2);
@@ -603,6 +620,9 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   rc |= dalloc(e, &e->st_oposes, B * 12 * (catre_engine::kMaxHostIter + 1));
   rc |= dalloc(e, &e->st_oscales, B * 3 * (catre_engine::kMaxHostIter + 1));
   e->num_sms = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) rc |= 1;
   {
     const char* dbg = getenv("CATRE_RF_DEBUG");
     if (dbg && dbg[0] == '1') rc |= dalloc(e, &e->rf_dbg, 8 * 32);
@@ -644,6 +664,9 @@ void catre_destroy(catre_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   for (void* p : e->dev_allocs) cudaFree(p);
+  if (e->side) cudaStreamDestroy(e->side);
+  if (e->ev_fork) cudaEventDestroy(e->ev_fork);
+  if (e->ev_join) cudaEventDestroy(e->ev_join);
   for (auto& ev : e->ev_pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
   for (auto ev : e->ev_pool) cudaEventDestroy(ev);
   delete e;

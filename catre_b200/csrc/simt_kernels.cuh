@@ -789,6 +789,7 @@ struct TsPoseP {
   const float* convp_bias;                  // [2]
   const float* pose_in; const float* scale_in; const float* K;
   float* pose_out; float* scale_out;
+  float* dts;           // [B, 6] raw head outputs (dt 3 | ds 3): written by ts_head, read by pose_update
 };
 
 __device__ __forceinline__ float gn8_gelu(float v, float gamma, float beta) {
@@ -807,7 +808,9 @@ __device__ __forceinline__ float gn8_gelu(float v, float gamma, float beta) {
   return gelu_exact(d * rstd * gamma + beta);
 }
 
-__global__ void __launch_bounds__(256) ts_pose_kernel(TsPoseP p) {
+// ts_head_kernel: H1 (independent of the rotation head, so the host runs it on a side stream underneath the
+// rot kernels).  pose_update_kernel: G1 + G2, one warp per object, after both heads are done.
+__global__ void __launch_bounds__(256) ts_head_kernel(TsPoseP p) {
   const int b = blockIdx.x, t = threadIdx.x;
   __shared__ float feat2[68];  // pointfeat max (64) | init scale (3)
   __shared__ float h[256];
@@ -861,19 +864,26 @@ __global__ void __launch_bounds__(256) ts_pose_kernel(TsPoseP p) {
     if (lane == 0) outv[warp] = s + ((warp < 3) ? p.bt[warp] : p.bs[warp - 3]);
   }
   __syncthreads();
-  // rot-head partial sums [tiles][6]: warp j < 6 adds column j (lanes stride over the tiles, fixed order)
-  __shared__ float r6s[6];
-  if (warp < 6) {
+  if (t < 6) p.dts[(long long)b * 6 + t] = outv[t];
+}
+
+__global__ void __launch_bounds__(256) pose_update_kernel(TsPoseP p, int B) {
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= B) return;
+  // rot-head partial sums [tiles][6]: lanes stride over the tiles (fixed order), butterfly sum
+  float r6[6];
+#pragma unroll
+  for (int j = 0; j < 6; ++j) {
     float s = 0.f;
-    for (int tl = lane; tl < p.rot_tiles; tl += 32) s += p.rot_partial[((long long)b * p.rot_tiles + tl) * 6 + warp];
+    for (int tl = lane; tl < p.rot_tiles; tl += 32) s += p.rot_partial[((long long)b * p.rot_tiles + tl) * 6 + j];
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-    if (lane == 0) r6s[warp] = s + p.convp_bias[warp / 3];
+    r6[j] = s + p.convp_bias[j / 3];
   }
-  __syncthreads();
-  if (t == 0) {
-    float r6[6];
-    for (int j = 0; j < 6; ++j) r6[j] = r6s[j];
+  if (lane == 0) {
+    const float* outv = p.dts + (long long)b * 6;
+    const float* sc_in = p.scale_in + (long long)b * 3;
     // rot6d -> R (columns x, y, z)
     float nx = sqrtf(r6[0] * r6[0] + r6[1] * r6[1] + r6[2] * r6[2]);
     nx = fmaxf(nx, 1e-12f);
