@@ -74,12 +74,12 @@ constexpr int kNumWeights = sizeof(kWeights) / sizeof(kWeights[0]);
 enum Grp {
   G_FILL, G_UPDATE_POINTS, G_FRONT3, G_STN_CONV2, G_STN_CONV3_MAX, G_TNET_FC, G_FSTN_CONV1, G_FSTN_CONV2,
   G_FSTN_CONV3_MAX, G_FEAT_TRANSFORM, G_CONV2, G_CONV3, G_CONV4_MAX, G_ROT_GFEAT, G_ROT_LAYER0, G_GN_FINALIZE,
-  G_ROT_LAYER1, G_ROT_TAIL, G_TS_POSE, G_SPLIT, G_SUM_PARTS, G_ROT_LAYER0_APPLY, G_ROT_FUSED, G_NUM
+  G_ROT_LAYER1, G_ROT_TAIL, G_TS_POSE, G_ROT_FUSED, G_NUM
 };
 const char* kGrpNames[G_NUM] = {
     "fill", "update_points", "front3", "stn_conv2", "stn_conv3_max", "tnet_fc", "fstn_conv1", "fstn_conv2",
     "fstn_conv3_max", "feat_transform", "conv2", "conv3", "conv4_max", "rot_gfeat", "rot_layer0", "gn_finalize",
-    "rot_layer1", "rot_tail", "ts_pose", "split_bf16", "sum_parts", "rot_layer0_apply", "rot_fused"};
+    "rot_layer1", "rot_tail", "ts_pose", "rot_fused"};
 
 }  // namespace
 
@@ -219,13 +219,12 @@ GemmP gemm_args(const float* A, int lda, const float* W, int K, int C, const flo
   p.stats_ld = 0; p.stats_goff = 0;
   p.gn_scale = p.gn_shift = nullptr; p.ldgn = 0;
   p.R = (int)R; p.C = C; p.K = K; p.rows_per_set = 1; p.rows_per_obj = 1; p.relu = relu;
-  p.ksplit = 1; p.part_stride = 0; p.a_bias = nullptr; p.a_nparts = 0; p.a_part_stride = 0; p.a_relu = 0;
   return p;
 }
 
 template <int BN, int AMODE>
 int run_gemm(catre_engine* e, cudaStream_t s, int grp, const GemmP& p) {
-  dim3 grid((p.C + BN - 1) / BN, (p.R + 127) / 128, p.ksplit > 1 ? p.ksplit : 1);
+  dim3 grid((p.C + BN - 1) / BN, (p.R + 127) / 128);
   {
     Launch l(e, s, grp);
     pw_gemm_kernel<BN, AMODE><<<grid, 256, 0, s>>>(p);
@@ -521,7 +520,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
       rot_tail_t_kernel<<<dim3(16, B), 256, P * sizeof(float), s>>>(reinterpret_cast<const __half*>(e->a1), e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
                                                                    e->neck_b, e->wp, e->rot_partial, P);
     else
-      rot_tail_kernel<0><<<dim3(P / 128, B), 256, 0, s>>>(e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
+      rot_tail_kernel<<<dim3(P / 128, B), 256, 0, s>>>(e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
                                                          e->wp, e->rot_partial, P);
   }
   if ((rc = check_launch(e, "rot_tail"))) return rc;

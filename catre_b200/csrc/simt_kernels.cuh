@@ -44,8 +44,6 @@ __device__ __forceinline__ float gelu_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(e) : "f"(p));  // p in [-28, -1]: no range fix-up needed
   return fmaf(-fabsf(x), e, fmaxf(x, 0.0f));
 }
-template <int FAST>
-__device__ __forceinline__ float gelu_sel(float x) { return FAST ? gelu_fast(x) : gelu_exact(x); }
 
 __global__ void fill_i32_kernel(int* __restrict__ p, long long n, int v) {
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
@@ -139,8 +137,7 @@ __global__ void front3_kernel(const float* __restrict__ q, const float* __restri
 // Generic fp32 point-wise layer:  out[r, c] = act( sum_k f(A[r, k]) * W[c, k] + bias[c] + rowvec[set(r), c] )
 // 128 x BN output tile, K chunks of 16, 256 threads, 8 x (BN/16) micro-tile.
 // ----------------------------------------------------------------------------------------------
-//   A_PARTIAL : A[r, k] = act(sum_z Apart[z][r, k] + a_bias[k])  -- consumes a split-K producer's partials
-enum { A_PLAIN = 0, A_KEY = 1, A_GN_GELU = 2, A_PARTIAL = 3 };
+enum { A_PLAIN = 0, A_KEY = 1, A_GN_GELU = 2 };
 
 struct GemmP {
   const float* A; int lda;
@@ -155,11 +152,6 @@ struct GemmP {
   int R, C, K;
   int rows_per_set, rows_per_obj;
   int relu;
-  // split-K (small-M FC layers): gridDim.z = ksplit CTAs each reduce K/ksplit and write RAW partial sums
-  // (no bias / activation) to out + z * part_stride; the consumer (A_PARTIAL or sum_parts_kernel) adds
-  // them in fixed z order, so results are deterministic.
-  int ksplit; long long part_stride;
-  const float* a_bias; int a_nparts; long long a_part_stride; int a_relu;  // A_PARTIAL
 };
 
 template <int BN, int AMODE>
@@ -183,9 +175,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
 #pragma unroll
     for (int j = 0; j < TN; ++j) acc[i][j] = 0.0f;
 
-  const int kz = (p.ksplit > 1) ? p.K / p.ksplit : p.K;
-  const int k_begin = (p.ksplit > 1) ? blockIdx.z * kz : 0;
-  const int k_end = k_begin + kz;
+  const int k_begin = 0, k_end = p.K;
 
   // global -> registers for one K chunk (A: 128 rows x 16 k, W: BN channels x 16 k; float4 along k).  The
   // loads of chunk i+1 are issued before the FMAs of chunk i, so their latency hides behind the math.
@@ -201,14 +191,6 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
         if (AMODE == A_KEY) {
           int4 kv = *reinterpret_cast<const int4*>(src);
           v = make_float4(key2f(kv.x), key2f(kv.y), key2f(kv.z), key2f(kv.w));
-        } else if (AMODE == A_PARTIAL) {
-          v = *reinterpret_cast<const float4*>(p.a_bias + k0 + kq);
-#pragma unroll 8
-          for (int z = 0; z < p.a_nparts; ++z) {
-            const float4 t = *reinterpret_cast<const float4*>(src + (long long)z * p.a_part_stride);
-            v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-          }
-          if (p.a_relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
         } else {
           v = *reinterpret_cast<const float4*>(src);
           if (AMODE == A_GN_GELU) {
@@ -265,22 +247,6 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
     __syncthreads();
   }
 
-  if (p.ksplit > 1) {  // raw partial sums; bias / activation belong to the consumer
-    float* po = p.out + (long long)blockIdx.z * p.part_stride;
-#pragma unroll
-    for (int i = 0; i < 8; ++i) {
-      int row = r0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
-      if (row >= p.R) continue;
-#pragma unroll
-      for (int ch = 0; ch < NCH; ++ch) {
-        int cbase = c0 + ch * (BN / 2) + tx * 4;
-#pragma unroll
-        for (int j = 0; j < 4; ++j)
-          if (cbase + j < p.C) po[(long long)row * p.ldo + cbase + j] = acc[i][ch * 4 + j];
-      }
-    }
-    return;
-  }
   // ---- epilogue: bias / per-set vector / ReLU
   // thread's rows: ty*4+i (i<4), 64+ty*4+(i-4); columns: chunk ch -> ch*(BN/2) + tx*4 + j
 #pragma unroll
@@ -555,48 +521,6 @@ __global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(NT) fc_clust
   cluster.sync();  // no CTA may exit while its shared memory is still being read by the others
 }
 
-// Fixed-order reduction of split-K partials:  out[r, c] = act(sum_z parts[z][r, c] + bias[c]).
-// Optionally also writes the bf16 hi/lo split of the result (operand of a tensor-core layer).
-__global__ void sum_parts_kernel(const float* __restrict__ parts, int nparts, long long part_stride,
-                                 const float* __restrict__ bias, int C, int relu, float* __restrict__ out32,
-                                 unsigned short* __restrict__ out_hi, unsigned short* __restrict__ out_lo, long long n4) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n4) return;
-  const int c = (int)((i * 4) % C);
-  float4 v = bias ? *reinterpret_cast<const float4*>(bias + c) : make_float4(0.f, 0.f, 0.f, 0.f);
-  for (int z = 0; z < nparts; ++z) {
-    const float4 t = *reinterpret_cast<const float4*>(parts + (long long)z * part_stride + i * 4);
-    v.x += t.x; v.y += t.y; v.z += t.z; v.w += t.w;
-  }
-  if (relu) { v.x = fmaxf(v.x, 0.f); v.y = fmaxf(v.y, 0.f); v.z = fmaxf(v.z, 0.f); v.w = fmaxf(v.w, 0.f); }
-  if (out32) *reinterpret_cast<float4*>(out32 + i * 4) = v;
-  if (out_hi) {
-    const float f[4] = {v.x, v.y, v.z, v.w};
-    unsigned short h[4], l[4];
-#pragma unroll
-    for (int j = 0; j < 4; ++j) {  // round-to-nearest-even bf16 of f and of the residual
-      unsigned int u = __float_as_uint(f[j]);
-      unsigned int hr = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;
-      h[j] = (unsigned short)(hr >> 16);
-      unsigned int ul = __float_as_uint(f[j] - __uint_as_float(hr));
-      l[j] = (unsigned short)((ul + 0x7fffu + ((ul >> 16) & 1u)) >> 16);
-    }
-    *reinterpret_cast<uint2*>(out_hi + i * 4) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
-    *reinterpret_cast<uint2*>(out_lo + i * 4) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
-  }
-}
-
-// scalar variant for widths that are not a multiple of 4 (stn.fc3: C = 9)
-__global__ void sum_parts_scalar_kernel(const float* __restrict__ parts, int nparts, long long part_stride,
-                                        const float* __restrict__ bias, int C, int relu, float* __restrict__ out32,
-                                        long long n) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n) return;
-  float v = bias ? bias[i % C] : 0.f;
-  for (int z = 0; z < nparts; ++z) v += parts[(long long)z * part_stride + i];
-  out32[i] = relu ? fmaxf(v, 0.f) : v;
-}
-
 // Tensor-core modes: GroupNorm statistics of rot layer 0 -> per (SET, channel) affine applied to the raw
 // MMA accumulator D = W0p . pf (the per-set constant cset = W0g . g_set + b0 is folded into the shift):
 //   gelu_in = (D + cset) * sc + sh  =  D * sc + (cset * sc + sh)
@@ -642,7 +566,6 @@ __global__ void gn_finalize_set_kernel(const float* __restrict__ stats, const fl
 // By linearity  sum_p wp[p] (neck . g_p + nb) = neck . (sum_p wp[p] g_p) + nb sum_p wp[p]:  each lane
 // accumulates the wp-weighted GELU outputs of its 8 channels per head over the block's rows (no
 // per-row shuffles); the 256 -> 3 neck is applied once per warp at the end.
-template <int FAST_GELU>
 __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__ a1, const float* __restrict__ gn_scale,
                                                        const float* __restrict__ gn_shift,
                                                        const float* __restrict__ neck_w /*[2][3][256]*/,
@@ -675,7 +598,7 @@ __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__
       const float w = __ldg(wp + (long long)h * P + pidx);
       wsum[h] += w;
 #pragma unroll
-      for (int j = 0; j < 8; ++j) acc[h][j] = fmaf(w, gelu_sel<FAST_GELU>(fmaf(u[j], sc[h][j], sh[h][j])), acc[h][j]);
+      for (int j = 0; j < 8; ++j) acc[h][j] = fmaf(w, gelu_exact(fmaf(u[j], sc[h][j], sh[h][j])), acc[h][j]);
     }
   }
   float d[6];

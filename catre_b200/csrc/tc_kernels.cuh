@@ -38,7 +38,7 @@ enum { CH_ON_LANES = 0, PT_ON_LANES = 1 };
 //   EPI_STATS           CH_ON_LANES   GroupNorm partial sums of D + rowvec[set] only (nothing stored)
 //   EPI_SPLIT           PT_ON_LANES   act(D + bias) -> bf16 hi/lo [R, C] (operand of the next layer), TMA-stored
 //   EPI_SPLIT_MAX       PT_ON_LANES   D -> bf16 hi/lo, and column max over the tile's points -> atomicMax keys
-enum { EPI_MAX = 0, EPI_RAW_STATS = 1, EPI_SPLIT = 2, EPI_STATS = 3, EPI_GN_SPLIT = 4, EPI_SPLIT_MAX = 5 };
+enum { EPI_MAX = 0, EPI_SPLIT = 2, EPI_STATS = 3, EPI_SPLIT_MAX = 5 };
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -560,39 +560,6 @@ __global__ void front3_split_kernel(const float* __restrict__ q, const float* __
   }
   *reinterpret_cast<uint4*>(out_hi + r * 64 + cg * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
   *reinterpret_cast<uint4*>(out_lo + r * 64 + cg * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
-}
-
-// fp32 [n] -> bf16 hi/lo [n] (n multiple of 8), optionally through GroupNorm affine + GELU:
-//   x' = gelu(x * scale[obj, c] + shift[obj, c]),  obj = row / rows_per_obj, c = column (ld columns per row)
-__global__ void split_kernel(const float* __restrict__ src, __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                             long long n8, const float* __restrict__ gn_scale, const float* __restrict__ gn_shift, int ld,
-                             int rows_per_obj) {
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  if (i >= n8) return;
-  const float4 a = *reinterpret_cast<const float4*>(src + i * 8);
-  const float4 b = *reinterpret_cast<const float4*>(src + i * 8 + 4);
-  float v[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-  if (gn_scale) {
-    long long e0 = i * 8;
-    long long row = e0 / ld;
-    int c = (int)(e0 % ld);
-    long long obj = row / rows_per_obj;
-    const float* sc = gn_scale + obj * ld + c;
-    const float* sh = gn_shift + obj * ld + c;
-#pragma unroll
-    for (int j = 0; j < 8; ++j) v[j] = gelu_exact(v[j] * sc[j] + sh[j]);
-  }
-  uint32_t hi[4], lo[4];
-#pragma unroll
-  for (int j = 0; j < 8; j += 2) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v[j], h0, l0);
-    split_bf16(v[j + 1], h1, l1);
-    hi[j >> 1] = pack_bf16(h0, h1);
-    lo[j >> 1] = pack_bf16(l0, l1);
-  }
-  *reinterpret_cast<uint4*>(out_hi + i * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(out_lo + i * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // ------------------------------------------------------------------------------------------------

@@ -167,3 +167,38 @@ def test_precision_modes_agree(weights):
     pa, sa = run_refine(get_engine(weights, 1024, "fp32"), b, 4)
     pb, sb = run_refine(get_engine(weights, 1024, "bf16x3"), b, 4)
     assert (pa - pb).abs().max() <= 2 * TOL and (sa - sb).abs().max() <= 2 * TOL
+
+
+def test_refine_is_cuda_graph_capturable(weights):
+    """include/catre_b200.h promises stream-ordered, sync-free, graph-capturable calls (the engine forks its
+    ts head onto an internal side stream and joins it again inside the call)."""
+    b = synth.make_batch(8, 1024, seed=41).to("cuda")
+    eng = get_engine(weights, 1024, "bf16x3")
+    out = (torch.empty((5, 8, 3, 4), device="cuda"), torch.empty((5, 8, 3), device="cuda"))
+    eng.refine(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, 4, out=out)  # warm-up: one-time kernel attributes
+    torch.cuda.synchronize()
+    ref = (out[0].clone(), out[1].clone())
+    g = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        with torch.cuda.graph(g, stream=side):
+            eng.refine(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, 4, out=out)
+    torch.cuda.current_stream().wait_stream(side)
+    for _ in range(3):
+        out[0].zero_(); out[1].zero_()
+        g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(out[0], ref[0]) and torch.equal(out[1], ref[1])
+
+
+def test_bf16_single_product_mode(weights):
+    """BASELINE.json config 3's arithmetic: one bf16 MMA product on the wide layers.  NOT an fp32-parity mode:
+    tolerance 2e-2 on R and 5e-3 on t, s versus the reference fp32 forward (from the
+    6.2e-3 / 1.3e-3 rounding probe x3)."""
+    case = gu.load_case("c5s_b12_n1024_k4_mixed")
+    eng = get_engine(weights, 1024, "bf16")
+    poses, scales = run_refine(eng, case.batch, case.n_iter)
+    e_r, e_t, e_s = gu.max_abs_err(poses, scales, case.poses, case.scales)
+    assert e_r <= 2e-2 and e_t <= 5e-3 and e_s <= 5e-3, (e_r, e_t, e_s)
+    assert e_r > 0  # and it really is a different arithmetic from the parity mode

@@ -18,8 +18,8 @@ def keys2f(k):
 
 
 def main():
-    prec = sys.argv[1] if len(sys.argv) > 1 else "fp32"
-    B = int(sys.argv[2]) if len(sys.argv) > 2 else 2
+    prec = "fp32"  # the tensor-core modes keep only bf16 hi/lo operands; the fp32 taps below exist in fp32 mode
+    B = int(sys.argv[1]) if len(sys.argv) > 1 else 2
     N = 1024
     w = synth.load_weights()
     b = synth.make_batch(B, N, seed=5)
@@ -48,7 +48,7 @@ def main():
     h1 = F.relu(O._pw(w, "pcl_net.conv1", xq))
     rep("h1", eng.debug_read("h64a", (S, N, 64)), h1.permute(0, 2, 1))
     t64 = O.tnet(w, "pcl_net.fstn", h1, 64)
-    rep("t64", eng.debug_read("t64", (S, 4096)), t64.reshape(S, 4096))
+    rep("t64", eng.debug_read("t64", (S, 4096)), t64.transpose(1, 2).reshape(S, 4096))  # the engine keeps T64^T
     pf = torch.bmm(h1.transpose(2, 1), t64).transpose(2, 1)
     rep("pf", eng.debug_read("h64b", (S, N, 64)), pf.permute(0, 2, 1))
     rep("gmax_pf", keys2f(eng.debug_read("gmax_pf", (S, 64), torch.int32)), pf.max(2)[0])
