@@ -288,8 +288,8 @@ int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv,
   std::string c(conv);
   {
     Launch l(e, s, G_FRONT3);
-    front3_split_kernel<<<(unsigned)((R * 8 + 255) / 256), 256, 0, s>>>(e->q, t3, e->dw.at(c + ".weight"), e->dw.at(c + ".bias"),
-                                                                       nullptr, e->x64.hi, e->x64.lo, R, e->N);
+    front3_split_kernel<<<(unsigned)((R + FRONT_PTS - 1) / FRONT_PTS), 256, 0, s>>>(e->q, t3, e->dw.at(c + ".weight"), e->dw.at(c + ".bias"),
+                                                                 e->x64.hi, e->x64.lo, (int)R, e->N);
   }
   return check_launch(e, "front3_split");
 }
@@ -459,7 +459,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     TcGemmP p{};
     p.K = 64; p.m_tiles = 4; p.n_tiles = (int)(R / 256); p.rows_per_set = N;
     p.rowvec = e->cset; p.ldrv = 512;
-    p.stats = e->stats0; p.stats_ld = 64; p.stats_goff = 0;
+    p.stats = e->stats0; p.stats_ld = 64; p.stats_goff = 0;  // partials per 128 points (BN = 256, two column halves)
     if ((rc = tc_run<CH_ON_LANES, EPI_STATS, 256>(e, s, G_ROT_LAYER0, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->pf_nb[0], e->pf_nb[1], p))) return rc;
     {
       Launch l(e, s, G_GN_FINALIZE);
@@ -606,7 +606,7 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   rc |= dalloc(e, &e->dts, B * 6);
   rc |= dalloc(e, &e->t3, S * 9 + 7);
   rc |= dalloc(e, &e->cset, S * 512);
-  rc |= dalloc(e, &e->stats0, (R / 128) * 64 * 2);
+  rc |= dalloc(e, &e->stats0, (R / 64) * 64 * 2);
   rc |= dalloc(e, &e->stats1, (R / 64) * 64 * 2);  // the fused rot kernel emits partials per 64 points
   rc |= dalloc(e, &e->gn0, B * 2048);  // scale | shift, per set in the tensor-core modes
   rc |= dalloc(e, &e->gn1, B * 512 * 2);

@@ -203,6 +203,7 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 }
 __device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_read() { asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory"); }
+__device__ __forceinline__ void tma_store_wait_read1() { asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory"); }
 __device__ __forceinline__ void tma_store_wait_all() { asm volatile("cp.async.bulk.wait_group 0;" ::: "memory"); }
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
@@ -220,6 +221,7 @@ struct TcGemmP {
   int rows_per_set;      // points per set (a tile never straddles two sets)
   int nb_per_set;        // PT_ON_LANES: the NB operand is per set (rows set*BN .. +BN): feature transform
   int res_stages;        // resident-weight layers: activation stages in the ring (set by tc_launch)
+  int out_bufs;          // point-on-lanes layers: output staging buffers (1 or 2, set by tc_launch)
   // epilogue
   const float* bias;     // per output channel (or null)
   int relu;
@@ -238,25 +240,29 @@ struct TcCfg {
   // point-on-lanes layers stage their bf16 hi/lo output tile in shared memory for the TMA store engine:
   // BN/64 boxes of [128 rows x 64 channels] per array
   static constexpr int OUT_BYTES = (ORIENT == 1) ? (BN / 64) * 16384 * ARR : 0;
-  static constexpr int FIXED = 1024 + BIAS_BYTES + OUT_BYTES;  // barriers | ... | output staging | bias
-  // streaming both operands
+  // streaming both operands: as many stages as fit (<= 4); the output staging is double-buffered when >= 3
+  // stages remain
   static constexpr int STAGE_BYTES = (MA_BYTES + NB_BYTES) * ARR;
+  static constexpr int FIXED1 = 1024 + BIAS_BYTES + OUT_BYTES, FIXED2 = FIXED1 + OUT_BYTES;
+  static constexpr int OUT_BUFS = (ORIENT == 1 && (MAX_SMEM - FIXED2) / STAGE_BYTES >= 3) ? 2 : 1;
+  static constexpr int FIXED = (OUT_BUFS == 2) ? FIXED2 : FIXED1;  // barriers | ... | output staging | bias
   static constexpr int STAGES = ((MAX_SMEM - FIXED) / STAGE_BYTES) > 4 ? 4 : ((MAX_SMEM - FIXED) / STAGE_BYTES);
   static constexpr int SMEM_BYTES = FIXED + STAGES * STAGE_BYTES;
   // resident-weight variant (point-on-lanes layers with a fixed weight operand): all K slabs of the CTA's
   // BN weight rows stay in shared memory for the whole kernel; only the activation tiles stream.
   static constexpr int RES_STAGE_BYTES = MA_BYTES * ARR;
   static int res_bytes(int K) { return (K / 64) * NB_BYTES * ARR; }
+  static int res_out_bufs(int K) { return (MAX_SMEM - FIXED2 - res_bytes(K)) / RES_STAGE_BYTES >= 2 ? 2 : 1; }
+  static int res_fixed(int K) { return res_out_bufs(K) == 2 ? FIXED2 : FIXED1; }
   static int res_stages(int K) {
-    int st = (MAX_SMEM - FIXED - res_bytes(K)) / RES_STAGE_BYTES;
+    int st = (MAX_SMEM - res_fixed(K) - res_bytes(K)) / RES_STAGE_BYTES;
     return st > 4 ? 4 : st;
   }
-  static int res_smem(int K) { return FIXED + res_bytes(K) + res_stages(K) * RES_STAGE_BYTES; }
+  static int res_smem(int K) { return res_fixed(K) + res_bytes(K) + res_stages(K) * RES_STAGE_BYTES; }
 };
 // weights stay resident for the plain point-on-lanes layers (bias/ReLU/split epilogue)
 template <int ORIENT, int EPI>
 struct TcRes { static constexpr bool value = (ORIENT == 1 && EPI == 2); };
-
 template <int ORIENT, int EPI, int BN, int NPROD>
 __global__ void __launch_bounds__(TcEpi<ORIENT, BN>::THREADS, 1)
 tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant__ CUtensorMap ma_lo,
@@ -287,7 +293,8 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
   const uint32_t res_base = tiles_base;
   const uint32_t ring_base = RESW ? tiles_base + (uint32_t)((p.K / TC_BK) * Cfg::NB_BYTES * Cfg::ARR) : tiles_base;
   const uint32_t ostage_base = ring_base + (uint32_t)STAGES * STAGE_BYTES;
-  float* s_bias = reinterpret_cast<float*>(smem_raw + (ostage_base - smem_base) + Cfg::OUT_BYTES);
+  const int out_bufs = (ORIENT == PT_ON_LANES) ? p.out_bufs : 0;
+  float* s_bias = reinterpret_cast<float*>(smem_raw + (ostage_base - smem_base) + (uint32_t)(Cfg::OUT_BYTES * out_bufs));
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_base));
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -460,11 +467,13 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         uint32_t hi[16], lo[16];
 #pragma unroll
         for (int j = 0; j < 32; j += 2) split_bf16x2(x[j], x[j + 1], hi[j >> 1], lo[j >> 1]);
-        // the group's previous stores must have finished reading the staging box
-        if (issuer) tma_store_wait_read();
+        // the stores that last read this staging buffer must be done with it (with two buffers: the group
+        // committed two tiles ago, i.e. all but the most recent one)
+        const uint32_t obuf = ostage_base + (uint32_t)((out_bufs == 2 ? acc : 0) * Cfg::OUT_BYTES);
+        if (issuer) { if (out_bufs == 2) tma_store_wait_read1(); else tma_store_wait_read(); }
         named_bar_sync(1 + box, GW * 32);
         {
-          const uint32_t bhi = ostage_base + (uint32_t)(box * 16384 * Cfg::ARR) + (uint32_t)lane_row * 128;
+          const uint32_t bhi = obuf + (uint32_t)(box * 16384 * Cfg::ARR) + (uint32_t)lane_row * 128;
           const uint32_t c0 = (uint32_t)((n0 % 64) / 8), sw = (uint32_t)(lane_row & 7);
 #pragma unroll
           for (int q = 0; q < 4; ++q)
@@ -478,7 +487,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         fence_proxy_async_smem();
         named_bar_sync(1 + box, GW * 32);
         if (issuer) {
-          const uint32_t src = ostage_base + (uint32_t)(box * 16384 * Cfg::ARR);
+          const uint32_t src = obuf + (uint32_t)(box * 16384 * Cfg::ARR);
           tma_store_2d(&out_hi, src, ni * BN + box * 64, mi * 128);
           if (NPROD == 3) tma_store_2d(&out_lo, src + 16384, ni * BN + box * 64, mi * 128);
           tma_store_commit();
@@ -518,48 +527,49 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
 // element-wise helpers of the tensor-core path
 // ------------------------------------------------------------------------------------------------
 
-// front layer (see front3_kernel) writing the bf16 hi/lo split (and optionally fp32) of the 64 channels
-__global__ void front3_split_kernel(const float* __restrict__ q, const float* __restrict__ t3, const float* __restrict__ W,
-                                    const float* __restrict__ bias, float* __restrict__ out32 /*or null*/,
-                                    __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo, long long R, int N) {
+// front layer (see front3_kernel) writing the bf16 hi/lo split of the 64 channels.  One block = 128 consecutive
+// points (never straddling two sets: N is a multiple of 128); 256 threads = 32 point slots x 8 channel groups,
+// four points per thread, so weights / transform / points are staged once per 128 points.
+constexpr int FRONT_PTS = 128;
+__global__ void __launch_bounds__(256) front3_split_kernel(const float* __restrict__ q, const float* __restrict__ t3,
+                                                           const float* __restrict__ W, const float* __restrict__ bias,
+                                                           __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
+                                                           int R, int N) {
   __shared__ float sW[64 * 3];
   __shared__ float sB[64];
-  for (int i = threadIdx.x; i < 192; i += blockDim.x) sW[i] = W[i];
-  for (int i = threadIdx.x; i < 64; i += blockDim.x) sB[i] = bias[i];
+  __shared__ float sT[9];
+  __shared__ float sQ[FRONT_PTS * 3];
+  const int r0 = blockIdx.x * FRONT_PTS;  // first point of the block
+  if (threadIdx.x < 192) sW[threadIdx.x] = W[threadIdx.x];
+  if (threadIdx.x >= 192) sB[threadIdx.x - 192] = bias[threadIdx.x - 192];
+  if (threadIdx.x < 9) sT[threadIdx.x] = t3 ? t3[(r0 / N) * 9 + threadIdx.x] : ((threadIdx.x % 4 == 0) ? 1.0f : 0.0f);
+  for (int i = threadIdx.x; i < FRONT_PTS * 3; i += 256) sQ[i] = (r0 * 3 + i < R * 3) ? q[(size_t)r0 * 3 + i] : 0.0f;
   __syncthreads();
-  long long gid = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long r = gid >> 3;  // 8 threads per point, 8 channels each
-  int cg = (int)(gid & 7);
-  if (r >= R) return;
-  float x0 = q[r * 3 + 0], x1 = q[r * 3 + 1], x2 = q[r * 3 + 2];
-  if (t3 != nullptr) {
-    const float* T = t3 + (r / N) * 9;
-    float y0 = x0 * T[0] + x1 * T[3] + x2 * T[6];
-    float y1 = x0 * T[1] + x1 * T[4] + x2 * T[7];
-    float y2 = x0 * T[2] + x1 * T[5] + x2 * T[8];
-    x0 = y0; x1 = y1; x2 = y2;
-  }
-  float v[8];
+  const int cg = threadIdx.x & 7;  // channel group (8 channels)
+  float w[8][3], bb[8];
 #pragma unroll
   for (int j = 0; j < 8; ++j) {
-    int c = cg * 8 + j;
-    v[j] = fmaxf(sB[c] + sW[c * 3 + 0] * x0 + sW[c * 3 + 1] * x1 + sW[c * 3 + 2] * x2, 0.0f);
+    bb[j] = sB[cg * 8 + j];
+    w[j][0] = sW[(cg * 8 + j) * 3 + 0]; w[j][1] = sW[(cg * 8 + j) * 3 + 1]; w[j][2] = sW[(cg * 8 + j) * 3 + 2];
   }
-  if (out32) {
-    *reinterpret_cast<float4*>(out32 + r * 64 + cg * 8) = make_float4(v[0], v[1], v[2], v[3]);
-    *reinterpret_cast<float4*>(out32 + r * 64 + cg * 8 + 4) = make_float4(v[4], v[5], v[6], v[7]);
-  }
-  uint32_t hi[4], lo[4];
 #pragma unroll
-  for (int j = 0; j < 8; j += 2) {
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v[j], h0, l0);
-    split_bf16(v[j + 1], h1, l1);
-    hi[j >> 1] = pack_bf16(h0, h1);
-    lo[j >> 1] = pack_bf16(l0, l1);
+  for (int it = 0; it < FRONT_PTS / 32; ++it) {
+    const int pl = it * 32 + (threadIdx.x >> 3), r = r0 + pl;
+    if (r >= R) break;
+    const float q0 = sQ[pl * 3 + 0], q1 = sQ[pl * 3 + 1], q2 = sQ[pl * 3 + 2];
+    const float x0 = q0 * sT[0] + q1 * sT[3] + q2 * sT[6];
+    const float x1 = q0 * sT[1] + q1 * sT[4] + q2 * sT[7];
+    const float x2 = q0 * sT[2] + q1 * sT[5] + q2 * sT[8];
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float v0 = fmaxf(bb[j] + w[j][0] * x0 + w[j][1] * x1 + w[j][2] * x2, 0.0f);
+      const float v1 = fmaxf(bb[j + 1] + w[j + 1][0] * x0 + w[j + 1][1] * x1 + w[j + 1][2] * x2, 0.0f);
+      split_bf16x2(v0, v1, hi[j >> 1], lo[j >> 1]);
+    }
+    *reinterpret_cast<uint4*>(out_hi + (size_t)r * 64 + cg * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(out_lo + (size_t)r * 64 + cg * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
   }
-  *reinterpret_cast<uint4*>(out_hi + r * 64 + cg * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
-  *reinterpret_cast<uint4*>(out_lo + r * 64 + cg * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -629,11 +639,13 @@ cudaError_t tc_launch(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const 
     configured = true;
   }
   TcGemmP q = p;
+  q.out_bufs = Cfg::OUT_BUFS;
   int smem = Cfg::SMEM_BYTES;
   int tiles = p.m_tiles * p.n_tiles;
   int grid = tiles < num_sms ? tiles : num_sms;
   if (RESW) {
     q.res_stages = Cfg::res_stages(p.K);
+    q.out_bufs = Cfg::res_out_bufs(p.K);
     if (q.res_stages < 2) return cudaErrorInvalidConfiguration;
     smem = Cfg::res_smem(p.K);
     grid -= grid % p.n_tiles;  // every CTA keeps one weight tile: t % n_tiles must not change along its sequence
