@@ -33,7 +33,7 @@ def flops_per_object_iter(n_o: int, n_p: int) -> float:
 
 # algorithmic FLOPs per POINT of each wide layer (2 * C_in * C_out), for per-kernel rooflines
 LAYER_FLOPS_PER_POINT = {
-    "conv4_max": 2 * 512 * 1024, "stn_conv3_max": 2 * 128 * 1024, "fstn_conv3_max": 2 * 128 * 1024,
+    "conv4_max": 2 * 512 * 1024, "stn_conv3_max": 2 * 128 * 1024 + 2 * 64 * 128, "fstn_conv3_max": 2 * 128 * 1024 + 2 * 64 * 128,
     "conv3": 2 * 128 * 512, "rot_fused": 2 * 64 * 512 + 2 * 256 * 256 * 2, "rot_layer0": 2 * 64 * 512,
     "stn_conv2": 2 * 64 * 128, "fstn_conv2": 2 * 64 * 128, "conv2": 2 * 64 * 128, "fstn_conv1": 2 * 64 * 64,
 }

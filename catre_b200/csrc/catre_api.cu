@@ -284,6 +284,26 @@ int tc_max_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& w, cons
   return tc_run<CH_ON_LANES, EPI_MAX, 256>(e, s, grp, w.map_hi, w.map_lo, act_nb[0], act_nb[1], p);
 }
 
+// fused 64 -> 128 -> 1024 + column max of a T-Net (see enc_fused_kernel)
+int tc_tnet_trunk(catre_engine* e, cudaStream_t s, int grp, const TcPair& act, const TcPair& w2, const float* b2, const TcPair& w3,
+                  const float* b3, int* gmax, long long R) {
+  EncFusedP p{};
+  p.tiles = (int)(R / 256); p.rows_per_set = e->N; p.bias2 = b2; p.bias3 = b3; p.gmax = gmax;
+  cudaError_t st;
+  {
+    Launch l(e, s, grp);
+    if (e->cfg.precision == CATRE_PREC_BF16)
+      st = enc_fused_launch<1>(act.map_hi, act.map_lo, w2.map_hi, w2.map_lo, w3.map_hi, w3.map_lo, p, e->num_sms, s);
+    else
+      st = enc_fused_launch<3>(act.map_hi, act.map_lo, w2.map_hi, w2.map_lo, w3.map_hi, w3.map_lo, p, e->num_sms, s);
+  }
+  if (st != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e, CATRE_ERR_CUDA, "launch of %s failed: %s", kGrpNames[grp], cudaGetErrorString(st));
+  }
+  return 0;
+}
+
 int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv, long long R) {
   std::string c(conv);
   {
@@ -346,8 +366,8 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   // ---- E1: STN3d (pointnets/pointnet.py:24-41)
   if (tc) {
     if ((rc = tc_front(e, s, nullptr, "pcl_net.stn.conv1", R))) return rc;
-    if ((rc = tc_split_layer<128>(e, s, G_STN_CONV2, e->x64, e->tw_stn_c2, 64, 128, W(e, "pcl_net.stn.conv2.bias"), e->a128, R))) return rc;
-    if ((rc = tc_max_layer(e, s, G_STN_CONV3_MAX, e->tw_stn_c3, e->a128_nb, 128, 1024, W(e, "pcl_net.stn.conv3.bias"), 1, e->gmax_stn, R))) return rc;
+    if ((rc = tc_tnet_trunk(e, s, G_STN_CONV3_MAX, e->x64, e->tw_stn_c2, W(e, "pcl_net.stn.conv2.bias"), e->tw_stn_c3,
+                            W(e, "pcl_net.stn.conv3.bias"), e->gmax_stn, R))) return rc;
   } else {
     {
       Launch l(e, s, G_FRONT3);
@@ -380,8 +400,8 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   // ---- E3: STNkd (pointnet.py:57-78).  fc3's rows are permuted at pack time so it emits T64^T.
   if (tc) {
     if ((rc = tc_split_layer<64>(e, s, G_FSTN_CONV1, e->x64, e->tw_fstn_c1, 64, 64, W(e, "pcl_net.fstn.conv1.bias"), e->f64, R))) return rc;
-    if ((rc = tc_split_layer<128>(e, s, G_FSTN_CONV2, e->f64, e->tw_fstn_c2, 64, 128, W(e, "pcl_net.fstn.conv2.bias"), e->a128, R))) return rc;
-    if ((rc = tc_max_layer(e, s, G_FSTN_CONV3_MAX, e->tw_fstn_c3, e->a128_nb, 128, 1024, W(e, "pcl_net.fstn.conv3.bias"), 1, e->gmax_fstn, R))) return rc;
+    if ((rc = tc_tnet_trunk(e, s, G_FSTN_CONV3_MAX, e->f64, e->tw_fstn_c2, W(e, "pcl_net.fstn.conv2.bias"), e->tw_fstn_c3,
+                            W(e, "pcl_net.fstn.conv3.bias"), e->gmax_fstn, R))) return rc;
   } else {
     GemmP p = gemm_args(e->h64a, 64, W(e, "pcl_net.fstn.conv1.weight"), 64, 64, W(e, "pcl_net.fstn.conv1.bias"), e->h64b,
                         64, R, 1);

@@ -356,4 +356,250 @@ cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo,
   return cudaPeekAtLastError();
 }
 
+
+// =================================================================================================
+// Fused T-Net trunk (sm_100a):  128-wide layer + 1024-wide layer + column max, for one tile of 256 points:
+//   L0   D0[sub][128 pts x 128 ch] = X[sub][128 x 64] . W2[128 x 64]^T, sub = 0, 1   (points on TMEM lanes)
+//   epi0 u = relu(D0 + b2) -> bf16 hi/lo straight into shared memory (swizzled K-major operand, 256 rows)
+//   L1   D1[128 ch x 256 pts] = W3[mt*128.., 128] . u^T for the 8 channel tiles mt     (channels on lanes)
+//   epi1 gmax[set][ch] = max over the tile's points of relu(D1 + b3)                   (atomicMax of keys)
+// i.e. stn.conv2 + stn.conv3 + max (pointnets/pointnet.py:27-29) or fstn.conv2 + fstn.conv3 + max (:60-62).
+// The CTA owns its point tile for all 8 channel tiles, so the 128-wide activations never leave the SM
+// and only the 1024 x 128 weights stream (512 KB per 256 points, ~21 B/clk/SM under the layer-1 MMAs).
+// TMEM: D0 = columns 0..255; D1 double-buffered in columns 256..511 (even mt) and 0..255 (odd mt: by then epi0
+// has drained D0, which the u_full barriers of mt 0 guarantee).  Shared memory and warp roles as in
+// rot_fused_kernel.
+// =================================================================================================
+struct EncFusedP {
+  int tiles;             // R / 256
+  int rows_per_set;      // N
+  const float* bias2;    // [128]
+  const float* bias3;    // [1024]
+  int* gmax;             // [S][1024] ordered-int keys
+};
+
+template <int NPROD>
+__global__ void __launch_bounds__(RF_THREADS, 1)
+enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant__ CUtensorMap x_lo,
+                 const __grid_constant__ CUtensorMap w2_hi, const __grid_constant__ CUtensorMap w2_lo,
+                 const __grid_constant__ CUtensorMap w3_hi, const __grid_constant__ CUtensorMap w3_lo, const EncFusedP p) {
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = smem_u32(smem_raw);
+  const uint32_t u_base = (smem_base + 1024 + 1023) & ~1023u;
+  const uint32_t ring_base = u_base + RF_U_BYTES;
+  // barriers: full[3] empty[3] d0_full u_full[2] d1_full[2] d1_empty[2], then the TMEM base slot
+  const uint32_t bar_full = smem_base, bar_empty = smem_base + 24;
+  const uint32_t bar_d0_full = smem_base + 48;
+  const uint32_t bar_u_full = smem_base + 56;    // 2
+  const uint32_t bar_d1_full = smem_base + 72;   // 2
+  const uint32_t bar_d1_empty = smem_base + 88;  // 2
+  const uint32_t tmem_slot = smem_base + 112;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + 112);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&x_hi); prefetch_tmap(&w2_hi); prefetch_tmap(&w3_hi);
+    if (NPROD == 3) { prefetch_tmap(&x_lo); prefetch_tmap(&w2_lo); prefetch_tmap(&w3_lo); }
+    for (int i = 0; i < RF_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    mbar_init(bar_d0_full, 1);
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(bar_u_full + 8 * i, RF_EW);
+      mbar_init(bar_d1_full + 8 * i, 1);
+      mbar_init(bar_d1_empty + 8 * i, RF_EW);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 512);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot_ptr;
+  constexpr uint32_t SLOT_TX = (NPROD == 3) ? 32768 : 16384;
+
+  if (warp == 0) {
+    // ===================== TMA producer =====================
+    if (lane == 0) {
+      int slot = 0; uint32_t phase = 0;
+      auto load2 = [&](const CUtensorMap* hi, const CUtensorMap* lo, int c0, int c1) {  // one slot: hi | lo, 16 KB each
+        mbar_wait(bar_empty + 8 * slot, phase ^ 1);
+        const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
+        mbar_expect_tx(full, SLOT_TX);
+        tma_load_2d(sb, hi, c0, c1, full);
+        if (NPROD == 3) tma_load_2d(sb + 16384, lo, c0, c1, full);
+        if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; }
+      };
+      for (int it = blockIdx.x; it < p.tiles; it += gridDim.x) {
+        load2(&x_hi, &x_lo, 0, it * 256);
+        load2(&x_hi, &x_lo, 0, it * 256 + 128);
+        load2(&w2_hi, &w2_lo, 0, 0);
+        for (int mt = 0; mt < 8; ++mt)
+          for (int ks = 0; ks < 2; ++ks) load2(&w3_hi, &w3_lo, ks * 64, mt * 128);
+      }
+    }
+  } else if (warp == 1) {
+    // ===================== MMA issuer =====================
+    if (lane == 0) {
+      constexpr uint32_t idesc0 = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 256);
+      int slot = 0; uint32_t phase = 0;
+      auto next = [&]() { if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; } };
+      uint32_t it_phase = 0;         // per-item barriers (d0_full, u_full)
+      uint32_t use[2] = {0, 0};      // uses of each D1 buffer so far (parity of its full / empty barriers)
+      for (int it = blockIdx.x; it < p.tiles; it += gridDim.x) {
+        // ---- L0 into columns 0..255 (= D1 buffer 1): wait until its last reader (epi1 of the previous mt 7) is done
+        mbar_wait(bar_d1_empty + 8 * 1, (use[1] & 1) ^ 1);
+        tc_fence_after();
+        const int sx0 = slot; mbar_wait(bar_full + 8 * slot, phase); next();
+        const int sx1 = slot; mbar_wait(bar_full + 8 * slot, phase); next();
+        const int sw = slot;  mbar_wait(bar_full + 8 * slot, phase); next();
+        tc_fence_after();
+        {
+          const uint32_t w_hi = ring_base + sw * RF_SLOT, w_lo = w_hi + 16384;
+#pragma unroll
+          for (int sub = 0; sub < 2; ++sub) {
+            const uint32_t x_hi_a = ring_base + (sub ? sx1 : sx0) * RF_SLOT, x_lo_a = x_hi_a + 16384;
+            const uint32_t d0 = tmem_base + sub * 128;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t off = kk * 32;
+              umma_bf16(d0, umma_desc_sw128(x_hi_a + off), umma_desc_sw128(w_hi + off), idesc0, kk != 0);
+              if (NPROD == 3) {
+                umma_bf16(d0, umma_desc_sw128(x_hi_a + off), umma_desc_sw128(w_lo + off), idesc0, 1);
+                umma_bf16(d0, umma_desc_sw128(x_lo_a + off), umma_desc_sw128(w_hi + off), idesc0, 1);
+              }
+            }
+          }
+          umma_commit(bar_empty + 8 * sx0);
+          umma_commit(bar_empty + 8 * sx1);
+          umma_commit(bar_empty + 8 * sw);
+          umma_commit(bar_d0_full);
+        }
+        // ---- L1: 8 channel tiles; even mt -> buffer 0 (columns 256..511), odd mt -> buffer 1 (columns 0..255)
+        for (int mt = 0; mt < 8; ++mt) {
+          const int buf = mt & 1;
+          if (mt != 1) {  // mt 1 is the first writer of buffer 1 after L0: covered by the wait above + u_full
+            mbar_wait(bar_d1_empty + 8 * buf, (use[buf] & 1) ^ 1);
+            tc_fence_after();
+          }
+          const uint32_t d1 = tmem_base + (buf ? 0u : 256u);
+          for (int ks = 0; ks < 2; ++ks) {
+            if (mt == 0) { mbar_wait(bar_u_full + 8 * ks, it_phase); tc_fence_after(); }
+            mbar_wait(bar_full + 8 * slot, phase);
+            tc_fence_after();
+            const uint32_t w_hi = ring_base + slot * RF_SLOT, w_lo = w_hi + 16384;
+            const uint32_t u_hi = u_base + ks * 65536, u_lo = u_hi + 32768;
+#pragma unroll
+            for (int kk = 0; kk < 4; ++kk) {
+              const uint32_t off = kk * 32;
+              umma_bf16(d1, umma_desc_sw128(w_hi + off), umma_desc_sw128(u_hi + off), idesc1, (ks | kk) != 0);
+              if (NPROD == 3) {
+                umma_bf16(d1, umma_desc_sw128(w_hi + off), umma_desc_sw128(u_lo + off), idesc1, 1);
+                umma_bf16(d1, umma_desc_sw128(w_lo + off), umma_desc_sw128(u_hi + off), idesc1, 1);
+              }
+            }
+            umma_commit(bar_empty + 8 * slot);
+            next();
+          }
+          umma_commit(bar_d1_full + 8 * buf);
+          use[buf]++;
+        }
+        it_phase ^= 1;
+      }
+    }
+  } else {
+    // ===================== epilogue warps =====================
+    const int quad = warp & 3, part = (warp - 2) >> 2;
+    const int lane_row = quad * 32 + lane;
+    uint32_t it_phase = 0;
+    uint32_t use[2] = {0, 0};
+    for (int it = blockIdx.x; it < p.tiles; it += gridDim.x) {
+      const int set = (int)(((long long)it * 256) / p.rows_per_set);
+      // ---- epi0: lane = point row of sub-tile `sub`; this warp's 16 channels of slab ks
+      mbar_wait(bar_d0_full, it_phase);
+      tc_fence_after();
+#pragma unroll 1
+      for (int ks = 0; ks < 2; ++ks) {
+        const int ch0 = ks * 64 + part * 16;
+        float4 b4[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) b4[j] = __ldg(reinterpret_cast<const float4*>(p.bias2 + ch0) + j);
+#pragma unroll
+        for (int sub = 0; sub < 2; ++sub) {
+          float v[16];
+          tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(sub * 128 + ch0), v);
+          tmem_ld_wait16(v);
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int j = 0; j < 4; ++j) {
+            const float g0 = fmaxf(v[4 * j + 0] + b4[j].x, 0.f), g1 = fmaxf(v[4 * j + 1] + b4[j].y, 0.f);
+            const float g2 = fmaxf(v[4 * j + 2] + b4[j].z, 0.f), g3 = fmaxf(v[4 * j + 3] + b4[j].w, 0.f);
+            split_bf16x2(g0, g1, hi[2 * j], lo[2 * j]);
+            split_bf16x2(g2, g3, hi[2 * j + 1], lo[2 * j + 1]);
+          }
+          const int row = sub * 128 + lane_row;  // row of the 256-row operand slab
+          const uint32_t slab = u_base + ks * 65536 + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);
+          const uint32_t c0 = (uint32_t)(part * 2), sw = (uint32_t)(row & 7);
+          st_shared_v4(slab + (((c0 + 0) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+          st_shared_v4(slab + (((c0 + 1) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
+          if (NPROD == 3) {
+            st_shared_v4(slab + 32768 + (((c0 + 0) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+            st_shared_v4(slab + 32768 + (((c0 + 1) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
+          }
+        }
+        fence_proxy_async_smem();
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
+      }
+      // ---- epi1: lane = output channel of tile mt; this warp's 64 of the 256 points
+      for (int mt = 0; mt < 8; ++mt) {
+        const int buf = mt & 1;
+        mbar_wait(bar_d1_full + 8 * buf, use[buf] & 1);
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (buf ? 0u : 256u) + (uint32_t)(part * 64);
+        float m = -INFINITY;
+#pragma unroll
+        for (int c = 0; c < 2; ++c) {
+          float x[32];
+          tmem_ld32(taddr + c * 32, x);
+          tmem_ld_wait32(x);
+#pragma unroll
+          for (int j = 0; j < 32; ++j) m = fmaxf(m, x[j]);
+        }
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_d1_empty + 8 * buf);
+        use[buf]++;
+        const int ch = mt * 128 + lane_row;
+        m = fmaxf(m + __ldg(p.bias3 + ch), 0.f);
+        atomicMax(p.gmax + (long long)set * 1024 + ch, f2key(m));
+      }
+      it_phase ^= 1;
+    }
+  }
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, 512);
+  }
+}
+
+template <int NPROD>
+cudaError_t enc_fused_launch(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& w2_hi, const CUtensorMap& w2_lo,
+                             const CUtensorMap& w3_hi, const CUtensorMap& w3_lo, const EncFusedP& p, int num_sms, cudaStream_t s) {
+  auto kern = enc_fused_kernel<NPROD>;
+  static bool configured = false;
+  if (!configured) {
+    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SMEM);
+    if (st != cudaSuccess) return st;
+    configured = true;
+  }
+  int grid = p.tiles < num_sms ? p.tiles : num_sms;
+  if (grid < 1) return cudaSuccess;
+  kern<<<grid, RF_THREADS, RF_SMEM, s>>>(x_hi, x_lo, w2_hi, w2_lo, w3_hi, w3_lo, p);
+  return cudaPeekAtLastError();
+}
+
 }  // namespace catre
