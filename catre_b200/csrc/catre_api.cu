@@ -496,10 +496,10 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
       {
         Launch l(e, s, G_ROT_FUSED);
         if (e->cfg.precision == CATRE_PREC_BF16)
-          st = rot_fused_launch<1>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0_nb[0], e->tw_rot0_nb[1], e->tw_rot1s.map_hi,
+          st = rot_fused_launch<1>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
                                    e->tw_rot1s.map_lo, e->a1t_map, pf, e->num_sms, s);
         else
-          st = rot_fused_launch<3>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0_nb[0], e->tw_rot0_nb[1], e->tw_rot1s.map_hi,
+          st = rot_fused_launch<3>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
                                    e->tw_rot1s.map_lo, e->a1t_map, pf, e->num_sms, s);
       }
       if (st != cudaSuccess) {

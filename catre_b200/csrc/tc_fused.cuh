@@ -61,6 +61,12 @@ __device__ __forceinline__ void tmem_ld_wait16(float* v) {
                :
                : "memory");
 }
+// Schedule (software-pipelined over the CTA's work items j; half A = layer-0 channels 0..127 = U slabs 0-1,
+// half B = channels 128..255 = slabs 2-3; D0a / D0b = TMEM columns 0..127 / 128..255):
+//   MMA warp      L0(0,A) L0(0,B) | L1(j,A) L0(j+1,A) L1(j,B) L0(j+1,B) | ...
+//   epilogue      E0(0,s0..s3)    | E0(j+1,s0) E1(j) E0(j+1,s1) [store drain] E0(j+1,s2) E0(j+1,s3) | ...
+// so the GELU work of item j+1 runs underneath the layer-1 MMAs of item j and the CUDA cores never wait for
+// the tensor pipe.  E1(j) stages its fp16 tile in slabs 2-3 (free between L1(j,B) and E0(j+1,s2)).
 template <int NPROD>
 __global__ void __launch_bounds__(RF_THREADS, 1)
 rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constant__ CUtensorMap pf_lo,
@@ -71,22 +77,24 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t u_base = (smem_base + 1024 + 1023) & ~1023u;  // barriers live in the first 1 KB
   const uint32_t ring_base = u_base + RF_U_BYTES;
-  // barriers (8 B each): full[3] empty[3] d0_full d0_empty d1_full d1_empty u_full[4], then the TMEM base slot
+  // barriers (8 B each): full[3] empty[3] d0_full[2] d0_empty[2] d1_full d1_empty u_full[4], then the TMEM base slot
   const uint32_t bar_full = smem_base, bar_empty = smem_base + 24;
-  const uint32_t bar_d0_full = smem_base + 48, bar_d0_empty = smem_base + 56;
-  const uint32_t bar_d1_full = smem_base + 64, bar_d1_empty = smem_base + 72;
-  const uint32_t bar_u_full = smem_base + 80;  // 4 barriers
-  const uint32_t tmem_slot = smem_base + 112;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + 112);
+  const uint32_t bar_d0_full = smem_base + 48, bar_d0_empty = smem_base + 64;
+  const uint32_t bar_d1_full = smem_base + 80, bar_d1_empty = smem_base + 88;
+  const uint32_t bar_u_full = smem_base + 96;  // 4 barriers
+  const uint32_t tmem_slot = smem_base + 128;
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + 128);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_ht = p.tiles * 2;  // (tile, head) work items
+  const int n_items = (n_ht > (int)blockIdx.x) ? (n_ht - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x : 0;
+  auto item_ht = [&](int j) { return (int)blockIdx.x + j * (int)gridDim.x; };
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&pf_hi); prefetch_tmap(&w0_hi); prefetch_tmap(&w1_hi); prefetch_tmap(&a1t_map);
     if (NPROD == 3) { prefetch_tmap(&pf_lo); prefetch_tmap(&w0_lo); prefetch_tmap(&w1_lo); }
     for (int i = 0; i < RF_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
-    mbar_init(bar_d0_full, 1); mbar_init(bar_d0_empty, RF_EW);
+    for (int i = 0; i < 2; ++i) { mbar_init(bar_d0_full + 8 * i, 1); mbar_init(bar_d0_empty + 8 * i, RF_EW); }
     mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RF_EW);
     for (int i = 0; i < 4; ++i) mbar_init(bar_u_full + 8 * i, RF_EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -96,240 +104,233 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  constexpr uint32_t SLOT_TX = (NPROD == 3) ? 32768 : 16384;
 
   if (warp == 0) {
-    // ===================== TMA producer =====================
-    if (lane == 0) {
+    // ===================== TMA producer (same order as the MMA warp consumes) =====================
+    if (lane == 0 && n_items > 0) {
       int slot = 0; uint32_t phase = 0;
-      auto next = [&]() { if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; } };
-      for (int ht = blockIdx.x; ht < n_ht; ht += gridDim.x) {
-        const int tile = ht >> 1, h = ht & 1;
-        // slot A: the tile's point features, hi | lo (16 KB each)
+      auto load2 = [&](const CUtensorMap* hi, const CUtensorMap* lo, int c0, int c1) {  // one slot: hi | lo, 16 KB each
         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-        {
-          const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
-          mbar_expect_tx(full, NPROD == 3 ? 32768 : 16384);
-          tma_load_2d(sb, &pf_hi, 0, tile * 128, full);
-          if (NPROD == 3) tma_load_2d(sb + 16384, &pf_lo, 0, tile * 128, full);
-        }
-        next();
-        // slots B, C: W0p_h hi and lo, [256 ch x 64] each (32 KB)
-        for (int a = 0; a < (NPROD == 3 ? 2 : 1); ++a) {
-          mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-          const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
-          mbar_expect_tx(full, 32768);
-          tma_load_2d(sb, a == 0 ? &w0_hi : &w0_lo, 0, h * 256, full);
-          next();
-        }
-        // 8 slots: W1_h[mt*128 .., ks*64 ..] hi | lo, in the order the MMA warp consumes them
-        for (int kq = 0; kq < 4; ++kq)
-          for (int mt = 0; mt < 2; ++mt) {
-            const int ks = (kq + 2) & 3;  // slab order 2, 3, 0, 1
-            mbar_wait(bar_empty + 8 * slot, phase ^ 1);
-            const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
-            mbar_expect_tx(full, NPROD == 3 ? 32768 : 16384);
-            tma_load_2d(sb, &w1_hi, ks * 64, h * 256 + mt * 128, full);
-            if (NPROD == 3) tma_load_2d(sb + 16384, &w1_lo, ks * 64, h * 256 + mt * 128, full);
-            next();
-          }
+        const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
+        mbar_expect_tx(full, SLOT_TX);
+        tma_load_2d(sb, hi, c0, c1, full);
+        if (NPROD == 3) tma_load_2d(sb + 16384, lo, c0, c1, full);
+        if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; }
+      };
+      auto load_l0 = [&](int j, int half) {  // point features of the tile + 128 rows of W0p_h
+        const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
+        load2(&pf_hi, &pf_lo, 0, tile * 128);
+        load2(&w0_hi, &w0_lo, 0, h * 256 + half * 128);
+      };
+      auto load_l1 = [&](int j, int half) {  // W1_h[mt*128.., ks*64..] for the half's two K slabs
+        const int h = item_ht(j) & 1;
+        for (int ks = half * 2; ks < half * 2 + 2; ++ks)
+          for (int mt = 0; mt < 2; ++mt) load2(&w1_hi, &w1_lo, ks * 64, h * 256 + mt * 128);
+      };
+      load_l0(0, 0); load_l0(0, 1);
+      for (int j = 0; j < n_items; ++j) {
+        load_l1(j, 0);
+        if (j + 1 < n_items) load_l0(j + 1, 0);
+        load_l1(j, 1);
+        if (j + 1 < n_items) load_l0(j + 1, 1);
       }
     }
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
-    if (lane == 0) {
-      constexpr uint32_t idesc0 = umma_idesc_bf16(128, 256);
-      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 128);
+    if (lane == 0 && n_items > 0) {
+      constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
       int slot = 0; uint32_t phase = 0;
       auto next = [&]() { if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; } };
-      uint32_t it_phase = 0;  // parity of the per-work-item barriers
-      for (int ht = blockIdx.x; ht < n_ht; ht += gridDim.x) {
-        long long* dbg = (p.dbg && blockIdx.x == 0 && ht / (int)gridDim.x < 8) ? p.dbg + (ht / gridDim.x) * 32 : nullptr;
-        if (dbg) dbg[0] = clock64();
-        // ---- L0: D0 = pf . W0p_h^T   (K = 64: 4 k-steps)
-        mbar_wait(bar_d0_empty, it_phase ^ 1);
-        if (dbg) dbg[1] = clock64();
+      // L0(j, half): D0[half] = pf . W0p_h[half*128 ..]^T   (K = 64: 4 k-steps, N = 128)
+      auto L0 = [&](int j, int half) {
+        mbar_wait(bar_d0_empty + 8 * half, ((uint32_t)j & 1) ^ 1);  // E0(j-1) has drained this half of D0
         tc_fence_after();
-        const int sx = slot;
-        mbar_wait(bar_full + 8 * slot, phase); next();
-        const int sw_hi = slot;
-        mbar_wait(bar_full + 8 * slot, phase); next();
-        int sw_lo = sw_hi;
-        if (NPROD == 3) { sw_lo = slot; mbar_wait(bar_full + 8 * slot, phase); next(); }
+        const int sx = slot; mbar_wait(bar_full + 8 * slot, phase); next();
+        const int sw = slot; mbar_wait(bar_full + 8 * slot, phase); next();
         tc_fence_after();
-        if (dbg) dbg[2] = clock64();
-        {
-          const uint32_t x_hi = ring_base + sx * RF_SLOT, x_lo = x_hi + 16384;
-          const uint32_t w_hi = ring_base + sw_hi * RF_SLOT, w_lo = ring_base + sw_lo * RF_SLOT;
+        const uint32_t x_hi = ring_base + sx * RF_SLOT, x_lo = x_hi + 16384;
+        const uint32_t w_hi = ring_base + sw * RF_SLOT, w_lo = w_hi + 16384;
+        const uint32_t d0 = tmem_base + (uint32_t)(half * 128);
 #pragma unroll
-          for (int kk = 0; kk < 4; ++kk) {
-            const uint32_t off = kk * 32;
-            umma_bf16(tmem_base, umma_desc_sw128(x_hi + off), umma_desc_sw128(w_hi + off), idesc0, kk != 0);
-            if (NPROD == 3) {
-              umma_bf16(tmem_base, umma_desc_sw128(x_hi + off), umma_desc_sw128(w_lo + off), idesc0, 1);
-              umma_bf16(tmem_base, umma_desc_sw128(x_lo + off), umma_desc_sw128(w_hi + off), idesc0, 1);
-            }
+        for (int kk = 0; kk < 4; ++kk) {
+          const uint32_t off = kk * 32;
+          umma_bf16(d0, umma_desc_sw128(x_hi + off), umma_desc_sw128(w_hi + off), idesc, kk != 0);
+          if (NPROD == 3) {
+            umma_bf16(d0, umma_desc_sw128(x_hi + off), umma_desc_sw128(w_lo + off), idesc, 1);
+            umma_bf16(d0, umma_desc_sw128(x_lo + off), umma_desc_sw128(w_hi + off), idesc, 1);
           }
-          umma_commit(bar_empty + 8 * sx);
-          umma_commit(bar_empty + 8 * sw_hi);
-          if (NPROD == 3) umma_commit(bar_empty + 8 * sw_lo);
-          umma_commit(bar_d0_full);
         }
-        // ---- L1: D1[mt] += W1_h[mt][ks] . U[ks]^T as the U slabs arrive
-        mbar_wait(bar_d1_empty, it_phase ^ 1);
-        tc_fence_after();
-        if (dbg) dbg[3] = clock64();
-        for (int kq = 0; kq < 4; ++kq) {
-          const int ks = (kq + 2) & 3;  // slab order 2, 3, 0, 1
-          mbar_wait(bar_u_full + 8 * ks, it_phase);
+        umma_commit(bar_empty + 8 * sx);
+        umma_commit(bar_empty + 8 * sw);
+        umma_commit(bar_d0_full + 8 * half);
+      };
+      // L1(j, half): D1[mt] (+)= W1_h[mt][ks] . U[ks]^T for the half's two K slabs, as the slabs arrive
+      auto L1 = [&](int j, int half) {
+        const uint32_t par = (uint32_t)j & 1;
+        if (half == 0) {  // first write of D1 for this item: E1(j-1) must have drained it
+          mbar_wait(bar_d1_empty, par ^ 1);
           tc_fence_after();
-          if (dbg) dbg[4 + ks * 3] = clock64();
+        }
+        for (int ks = half * 2; ks < half * 2 + 2; ++ks) {
+          mbar_wait(bar_u_full + 8 * ks, par);
+          tc_fence_after();
           const uint32_t u_hi = u_base + ks * 32768, u_lo = u_hi + 16384;
           for (int mt = 0; mt < 2; ++mt) {
             mbar_wait(bar_full + 8 * slot, phase);
             tc_fence_after();
-            if (dbg) dbg[5 + ks * 3 + mt] = clock64();
             const uint32_t w_hi = ring_base + slot * RF_SLOT, w_lo = w_hi + 16384;
             const uint32_t d1 = tmem_base + 256 + mt * 128;
 #pragma unroll
             for (int kk = 0; kk < 4; ++kk) {
               const uint32_t off = kk * 32;
-              umma_bf16(d1, umma_desc_sw128(w_hi + off), umma_desc_sw128(u_hi + off), idesc1, (kq | kk) != 0);
+              umma_bf16(d1, umma_desc_sw128(w_hi + off), umma_desc_sw128(u_hi + off), idesc, (ks | kk) != 0);
               if (NPROD == 3) {
-                umma_bf16(d1, umma_desc_sw128(w_hi + off), umma_desc_sw128(u_lo + off), idesc1, 1);
-                umma_bf16(d1, umma_desc_sw128(w_lo + off), umma_desc_sw128(u_hi + off), idesc1, 1);
+                umma_bf16(d1, umma_desc_sw128(w_hi + off), umma_desc_sw128(u_lo + off), idesc, 1);
+                umma_bf16(d1, umma_desc_sw128(w_lo + off), umma_desc_sw128(u_hi + off), idesc, 1);
               }
             }
             umma_commit(bar_empty + 8 * slot);
             next();
           }
         }
-        umma_commit(bar_d1_full);
-        if (dbg) dbg[16] = clock64();
-        it_phase ^= 1;
+        if (half == 1) umma_commit(bar_d1_full);
+      };
+      L0(0, 0); L0(0, 1);
+      for (int j = 0; j < n_items; ++j) {
+        L1(j, 0);
+        if (j + 1 < n_items) L0(j + 1, 0);
+        L1(j, 1);
+        if (j + 1 < n_items) L0(j + 1, 1);
       }
     }
   } else {
     // ===================== epilogue warps =====================
     const int quad = warp & 3, part = (warp - 2) >> 2;  // TMEM lanes 32*quad.., 4 parts per quadrant
     const int lane_row = quad * 32 + lane;
-    uint32_t it_phase = 0;
-    for (int ht = blockIdx.x; ht < n_ht; ht += gridDim.x) {
-      const int tile = ht >> 1, h = ht & 1;
-      const long long row0 = (long long)tile * 128;
-      const int set = (int)(row0 / p.rows_per_set);
-      long long* dbg = (p.dbg && blockIdx.x == 0 && warp == 2 && lane == 0 && ht / (int)gridDim.x < 8)
-                           ? p.dbg + (ht / gridDim.x) * 32 : nullptr;
-      // ---- epi0: lane = point row; slab ks, this warp's 16 channels: ks*64 + part*16 ..
-      mbar_wait(bar_d0_full, it_phase);
-      tc_fence_after();
-      if (dbg) dbg[17] = clock64();
+    const uint32_t row_off = (uint32_t)((lane_row >> 3) * 1024 + (lane_row & 7) * 128);
+    // E0(j, s): lane = point row; slab s (layer-0 channels s*64 .. +63), this warp's 16 channels
+    auto E0 = [&](int j, int ks) {
+      const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
+      const int set = (int)(((long long)tile * 128) / p.rows_per_set);
+      const int half = ks >> 1;
+      if ((ks & 1) == 0) {
+        mbar_wait(bar_d0_full + 8 * half, (uint32_t)j & 1);
+        tc_fence_after();
+      }
       const float* scp = p.gn_scale + (long long)set * 512 + h * 256;
       const float* shp = p.gn_shift + (long long)set * 512 + h * 256;
-      const uint32_t row_off = (uint32_t)((lane_row >> 3) * 1024 + (lane_row & 7) * 128);
-#pragma unroll 1
-      for (int kq = 0; kq < 4; ++kq) {
-        const int ks = (kq + 2) & 3;  // slab order 2, 3, 0, 1
-        if (kq == 2) {
-          // the previous item's TMA stores read their source from U slabs 0-1: they must be done with it
+      const int ch0 = ks * 64 + part * 16;
+      float v[16];
+      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ch0, v);
+      float4 sc4[4], sh4[4];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {  // broadcast loads (same address on every lane), overlapped with the TMEM load
+        sc4[q] = __ldg(reinterpret_cast<const float4*>(scp + ch0) + q);
+        sh4[q] = __ldg(reinterpret_cast<const float4*>(shp + ch0) + q);
+      }
+      tmem_ld_wait16(v);
+      if (ks & 1) {  // this half of D0 is drained: the next item's L0 may overwrite it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_d0_empty + 8 * half);
+      }
+      uint32_t hi[8], lo[8];
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float g0 = gelu_fast(fmaf(v[4 * q + 0], sc4[q].x, sh4[q].x));
+        const float g1 = gelu_fast(fmaf(v[4 * q + 1], sc4[q].y, sh4[q].y));
+        const float g2 = gelu_fast(fmaf(v[4 * q + 2], sc4[q].z, sh4[q].z));
+        const float g3 = gelu_fast(fmaf(v[4 * q + 3], sc4[q].w, sh4[q].w));
+        split_bf16x2(g0, g1, hi[2 * q], lo[2 * q]);
+        split_bf16x2(g2, g3, hi[2 * q + 1], lo[2 * q + 1]);
+      }
+      // two 16-byte chunks (8 channels each) of this row, 128B-swizzled: chunk' = chunk ^ (row & 7)
+      const uint32_t slab = u_base + ks * 32768 + row_off;
+      const uint32_t c0 = (uint32_t)(part * 2), sw = (uint32_t)(lane_row & 7);
+      st_shared_v4(slab + (((c0 + 0) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+      st_shared_v4(slab + (((c0 + 1) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
+      if (NPROD == 3) {
+        st_shared_v4(slab + 16384 + (((c0 + 0) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+        st_shared_v4(slab + 16384 + (((c0 + 1) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
+      }
+      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+      __syncwarp();
+      if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
+    };
+    // E1(j): lane = output channel of m-tile mt; this warp's 64 points; fp16 tile staged in slabs 2-3
+    auto E1 = [&](int j) {
+      const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
+      const long long row0 = (long long)tile * 128;
+      mbar_wait(bar_d1_full, (uint32_t)j & 1);
+      tc_fence_after();
+      const int mt = part >> 1, ph = part & 1;
+      const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
+      const long long r64 = row0 + ph * 64;          // first global row of this warp's 64 points
+      const long long obj = r64 / p.rows_per_obj;
+      const float add = p.bias1[ch];
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128 + ph * 64);
+      const uint32_t sw = (uint32_t)(lane_row & 7);
+      // box (mt, ph): [128 ch rows x 64 pts fp16 = 128 B], chunk' = chunk ^ (row & 7)
+      const uint32_t box = u_base + 65536 + (uint32_t)((mt * 2 + ph) * 16384);
+      const uint32_t brow = box + (uint32_t)lane_row * 128;
+      float s = 0.f, ss = 0.f;
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        float x[32];
+        tmem_ld32(taddr + c * 32, x);
+        tmem_ld_wait32(x);
+        if (c == 1) {  // D1 drained: the next item's layer-1 MMAs may overwrite it
+          tc_fence_before();
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_d1_empty);
+        }
+        uint32_t hx[16];
+#pragma unroll
+        for (int q = 0; q < 32; q += 2) {
+          x[q] += add; x[q + 1] += add;
+          s += x[q]; s += x[q + 1];
+          ss = fmaf(x[q], x[q], ss); ss = fmaf(x[q + 1], x[q + 1], ss);
+          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx[q >> 1]) : "f"(x[q + 1]), "f"(x[q]));
+        }
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+          st_shared_v4(brow + (((uint32_t)(c * 4 + q) ^ sw) << 4), hx[4 * q], hx[4 * q + 1], hx[4 * q + 2], hx[4 * q + 3]);
+      }
+      fence_proxy_async_smem();
+      named_bar_sync(1 + part, 128);  // the four quadrant warps that share this (mt, ph)
+      if (quad == 0 && lane == 0) {
+        const int pl = (int)(r64 - obj * p.rows_per_obj);
+        const int crow = (int)(obj * 512) + h * 256 + mt * 128;
+        tma_store_2d(&a1t_map, box, pl, crow);
+        tma_store_commit();
+      }
+      s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+      s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+      s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+      if ((lane & 7) == 0) {
+        const long long o = ((r64 >> 6) * 64 + (ch >> 3)) * 2;
+        p.stats[o] = s;
+        p.stats[o + 1] = ss;
+      }
+    };
+    if (n_items > 0) {
+      E0(0, 0); E0(0, 1); E0(0, 2); E0(0, 3);
+      for (int j = 0; j < n_items; ++j) {
+        const bool more = j + 1 < n_items;
+        if (more) E0(j + 1, 0);
+        E1(j);
+        if (more) {
+          E0(j + 1, 1);
+          // E1(j)'s TMA stores read their source from slabs 2-3: they must be done before those are rewritten
           if (quad == 0 && lane == 0) tma_store_wait_read();
           named_bar_sync(5, 32 * RF_EW);
-        }
-        const int ch0 = ks * 64 + part * 16;
-        float v[16];
-        tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ch0, v);
-        float4 sc4[4], sh4[4];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {  // broadcast loads (same address on every lane), overlapped with the TMEM load
-          sc4[j] = __ldg(reinterpret_cast<const float4*>(scp + ch0) + j);
-          sh4[j] = __ldg(reinterpret_cast<const float4*>(shp + ch0) + j);
-        }
-        tmem_ld_wait16(v);
-        uint32_t hi[8], lo[8];
-#pragma unroll
-        for (int j = 0; j < 4; ++j) {
-          const float g0 = gelu_fast(fmaf(v[4 * j + 0], sc4[j].x, sh4[j].x));
-          const float g1 = gelu_fast(fmaf(v[4 * j + 1], sc4[j].y, sh4[j].y));
-          const float g2 = gelu_fast(fmaf(v[4 * j + 2], sc4[j].z, sh4[j].z));
-          const float g3 = gelu_fast(fmaf(v[4 * j + 3], sc4[j].w, sh4[j].w));
-          split_bf16x2(g0, g1, hi[2 * j], lo[2 * j]);
-          split_bf16x2(g2, g3, hi[2 * j + 1], lo[2 * j + 1]);
-        }
-        // two 16-byte chunks (8 channels each) of this row, 128B-swizzled: chunk' = chunk ^ (row & 7)
-        const uint32_t slab = u_base + ks * 32768 + row_off;
-        const uint32_t c0 = (uint32_t)(part * 2), sw = (uint32_t)(lane_row & 7);
-        st_shared_v4(slab + (((c0 + 0) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
-        st_shared_v4(slab + (((c0 + 1) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
-        if (NPROD == 3) {
-          st_shared_v4(slab + 16384 + (((c0 + 0) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
-          st_shared_v4(slab + 16384 + (((c0 + 1) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
-        }
-        fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
-        if (dbg) dbg[18 + ks] = clock64();
-      }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_d0_empty);
-
-      // ---- epi1: lane = output channel of m-tile mt; this warp's 64 points
-      mbar_wait(bar_d1_full, it_phase);
-      tc_fence_after();
-      if (dbg) dbg[22] = clock64();
-      {
-        const int mt = part >> 1, ph = part & 1;
-        const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
-        const long long r64 = row0 + ph * 64;          // first global row of this warp's 64 points
-        const long long obj = r64 / p.rows_per_obj;
-        const float add = p.bias1[ch];
-        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128 + ph * 64);
-        const uint32_t sw = (uint32_t)(lane_row & 7);
-        // box (mt, ph): [128 ch rows x 64 pts fp16 = 128 B], chunk' = chunk ^ (row & 7)
-        const uint32_t box = u_base + (uint32_t)((mt * 2 + ph) * 16384);
-        const uint32_t brow = box + (uint32_t)lane_row * 128;
-        float s = 0.f, ss = 0.f;
-#pragma unroll
-        for (int c = 0; c < 2; ++c) {
-          float x[32];
-          tmem_ld32(taddr + c * 32, x);
-          tmem_ld_wait32(x);
-          uint32_t hx[16];
-#pragma unroll
-          for (int j = 0; j < 32; j += 2) {
-            x[j] += add; x[j + 1] += add;
-            s += x[j]; s += x[j + 1];
-            ss = fmaf(x[j], x[j], ss); ss = fmaf(x[j + 1], x[j + 1], ss);
-            asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx[j >> 1]) : "f"(x[j + 1]), "f"(x[j]));
-          }
-#pragma unroll
-          for (int q = 0; q < 4; ++q)
-            st_shared_v4(brow + (((uint32_t)(c * 4 + q) ^ sw) << 4), hx[4 * q], hx[4 * q + 1], hx[4 * q + 2], hx[4 * q + 3]);
-        }
-        fence_proxy_async_smem();
-        named_bar_sync(1 + part, 128);  // the four quadrant warps that share this (mt, ph)
-        if (quad == 0 && lane == 0) {
-          const int pl = (int)(r64 - obj * p.rows_per_obj);
-          const int crow = (int)(obj * 512) + h * 256 + mt * 128;
-          tma_store_2d(&a1t_map, box, pl, crow);
-          tma_store_commit();
-        }
-        s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-        s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-        s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-        if ((lane & 7) == 0) {
-          const long long o = ((r64 >> 6) * 64 + (ch >> 3)) * 2;
-          p.stats[o] = s;
-          p.stats[o + 1] = ss;
+          E0(j + 1, 2); E0(j + 1, 3);
         }
       }
-      tc_fence_before();
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_d1_empty);
-      if (dbg) dbg[23] = clock64();
-      it_phase ^= 1;
     }
+    if (quad == 0 && lane == 0) tma_store_wait_all();
   }
-  if (warp >= 2 && (warp & 3) == 0 && lane == 0) tma_store_wait_all();
   tc_fence_before();
   __syncthreads();
   if (warp == 1) {
