@@ -108,14 +108,14 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
 
   if (warp == 0) {
     // ===================== TMA producer (same order as the MMA warp consumes) =====================
-    if (lane == 0 && n_items > 0) {
+    // lane 0 issues the hi box (+ expect_tx), lane 1 the lo box: one thread alone sustains only ~30 B/clk/SM
+    if (lane < (NPROD == 3 ? 2 : 1) && n_items > 0) {
       int slot = 0; uint32_t phase = 0;
       auto load2 = [&](const CUtensorMap* hi, const CUtensorMap* lo, int c0, int c1) {  // one slot: hi | lo, 16 KB each
         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
         const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
-        mbar_expect_tx(full, SLOT_TX);
-        tma_load_2d(sb, hi, c0, c1, full);
-        if (NPROD == 3) tma_load_2d(sb + 16384, lo, c0, c1, full);
+        if (lane == 0) { mbar_expect_tx(full, SLOT_TX); tma_load_2d(sb, hi, c0, c1, full); }
+        else tma_load_2d(sb + 16384, lo, c0, c1, full);
         if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; }
       };
       auto load_l0 = [&](int j, int half) {  // point features of the tile + 128 rows of W0p_h
@@ -420,14 +420,13 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    if (lane < (NPROD == 3 ? 2 : 1)) {  // lane 0: hi box (+ expect_tx), lane 1: lo box, issued in parallel
       int slot = 0; uint32_t phase = 0;
       auto load2 = [&](const CUtensorMap* hi, const CUtensorMap* lo, int c0, int c1) {  // one slot: hi | lo, 16 KB each
         mbar_wait(bar_empty + 8 * slot, phase ^ 1);
         const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
-        mbar_expect_tx(full, SLOT_TX);
-        tma_load_2d(sb, hi, c0, c1, full);
-        if (NPROD == 3) tma_load_2d(sb + 16384, lo, c0, c1, full);
+        if (lane == 0) { mbar_expect_tx(full, SLOT_TX); tma_load_2d(sb, hi, c0, c1, full); }
+        else tma_load_2d(sb + 16384, lo, c0, c1, full);
         if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; }
       };
       for (int it = blockIdx.x; it < p.tiles; it += gridDim.x) {

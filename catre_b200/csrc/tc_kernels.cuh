@@ -329,16 +329,21 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
 
   if (warp == 0) {
     // ===================== TMA producer =====================
-    if (lane == 0) {
+    // A single thread can only keep ~30 B/clk/SM of TMA traffic in flight (tools/micro/tma_probe.cu: the
+    // issue path serialises per thread), so the up to four boxes of a stage are issued by four lanes in
+    // parallel: lane 0 = M-side hi (+ expect_tx), 1 = N-side hi, 2 = M-side lo, 3 = N-side lo.
+    if (lane < 4) {
       int stage = 0; uint32_t phase = 0;
-      if (RESW && blockIdx.x < total_tiles) {  // the CTA's weight tile, all K slabs, once
+      const bool is_lo = lane >= 2, is_nb = (lane & 1) != 0;
+      const bool active = (NPROD == 3 || !is_lo) && !(RESW && is_nb);
+      if (RESW && blockIdx.x < total_tiles && lane < 2) {  // the CTA's weight tile, all K slabs, once (lane 0 hi, lane 1 lo)
         const int ni0 = blockIdx.x % p.n_tiles;
-        mbar_expect_tx(bar_res, (uint32_t)(k_slabs * Cfg::NB_BYTES * Cfg::ARR));
-        for (int ks = 0; ks < k_slabs; ++ks) {
-          const uint32_t rb = res_base + (uint32_t)(ks * Cfg::NB_BYTES * Cfg::ARR);
-          tma_load_2d(rb, &nb_hi, ks * TC_BK, ni0 * BN, bar_res);
-          if (NPROD == 3) tma_load_2d(rb + Cfg::NB_BYTES, &nb_lo, ks * TC_BK, ni0 * BN, bar_res);
-        }
+        if (lane == 0) mbar_expect_tx(bar_res, (uint32_t)(k_slabs * Cfg::NB_BYTES * Cfg::ARR));
+        if (lane == 0 || NPROD == 3)
+          for (int ks = 0; ks < k_slabs; ++ks) {
+            const uint32_t rb = res_base + (uint32_t)(ks * Cfg::NB_BYTES * Cfg::ARR) + (lane ? Cfg::NB_BYTES : 0);
+            tma_load_2d(rb, lane ? &nb_lo : &nb_hi, ks * TC_BK, ni0 * BN, bar_res);
+          }
       }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int mi, ni; tile_coords(t, mi, ni);
@@ -347,12 +352,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sb = ring_base + stage * STAGE_BYTES;
           const uint32_t full = bar_full + 8 * stage;
-          mbar_expect_tx(full, STAGE_BYTES);
-          tma_load_2d(sb, &ma_hi, ks * TC_BK, mi * 128, full);
-          if (!RESW) tma_load_2d(sb + Cfg::MA_BYTES * Cfg::ARR, &nb_hi, ks * TC_BK, nb_row, full);
-          if (NPROD == 3) {
-            tma_load_2d(sb + Cfg::MA_BYTES, &ma_lo, ks * TC_BK, mi * 128, full);
-            if (!RESW) tma_load_2d(sb + Cfg::MA_BYTES * 2 + Cfg::NB_BYTES, &nb_lo, ks * TC_BK, nb_row, full);
+          if (lane == 0) mbar_expect_tx(full, STAGE_BYTES);
+          if (active) {
+            // stage layout: [M hi][M lo (x3)] then (streamed weights only) [N hi][N lo (x3)]
+            const uint32_t dst = sb + (is_nb ? Cfg::MA_BYTES * Cfg::ARR + (is_lo ? Cfg::NB_BYTES : 0) : (is_lo ? Cfg::MA_BYTES : 0));
+            const CUtensorMap* map = is_nb ? (is_lo ? &nb_lo : &nb_hi) : (is_lo ? &ma_lo : &ma_hi);
+            tma_load_2d(dst, map, ks * TC_BK, is_nb ? nb_row : mi * 128, full);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
