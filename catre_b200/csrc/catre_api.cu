@@ -227,7 +227,7 @@ int run_gemm(catre_engine* e, cudaStream_t s, int grp, const GemmP& p) {
   dim3 grid((p.C + BN - 1) / BN, (p.R + 127) / 128);
   {
     Launch l(e, s, grp);
-    pw_gemm_kernel<BN, AMODE><<<grid, 256, 0, s>>>(p);
+    launch_pdl(pw_gemm_kernel<BN, AMODE>, dim3(grid), dim3(256), (size_t)(0), s, p);
   }
   return check_launch(e, kGrpNames[grp]);
 }
@@ -238,7 +238,7 @@ int fill_i32(catre_engine* e, cudaStream_t s, int* p, long long n, int v) {
   if (blocks < 1) blocks = 1;
   {
     Launch l(e, s, G_FILL);
-    fill_i32_kernel<<<blocks, 256, 0, s>>>(p, n, v);
+    launch_pdl(fill_i32_kernel, dim3(blocks), dim3(256), (size_t)(0), s, p, n, v);
   }
   return check_launch(e, "fill");
 }
@@ -308,7 +308,7 @@ int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv,
   std::string c(conv);
   {
     Launch l(e, s, G_FRONT3);
-    front3_split_kernel<<<(unsigned)((R + FRONT_PTS - 1) / FRONT_PTS), 256, 0, s>>>(e->q, t3, e->dw.at(c + ".weight"), e->dw.at(c + ".bias"),
+    launch_pdl(front3_split_kernel, dim3((unsigned)((R + FRONT_PTS - 1) / FRONT_PTS)), dim3(256), (size_t)(0), s, e->q, t3, e->dw.at(c + ".weight"), e->dw.at(c + ".bias"),
                                                                  e->x64.hi, e->x64.lo, (int)R, e->N);
   }
   return check_launch(e, "front3_split");
@@ -327,10 +327,10 @@ int run_fc(catre_engine* e, cudaStream_t s, int grp, const float* A, int lda, co
     Launch l(e, s, grp);
     if ((long long)((C + 63) / 64) * ((R + 127) / 128) >= 32) {  // enough 128 x 64 tiles to fill the GPU with 8-CTA clusters
       dim3 grid((C + 63) / 64, (R + 127) / 128, FC_KSPLIT);
-      fc_cluster_kernel<AMODE, 128, 64, 256><<<grid, 256, 0, s>>>(p);
+      launch_pdl(fc_cluster_kernel<AMODE, 128, 64, 256>, dim3(grid), dim3(256), (size_t)(0), s, p);
     } else {
       dim3 grid((C + 31) / 32, (R + 63) / 64, FC_KSPLIT);
-      fc_cluster_kernel<AMODE, 64, 32, 128><<<grid, 128, 0, s>>>(p);
+      launch_pdl(fc_cluster_kernel<AMODE, 64, 32, 128>, dim3(grid), dim3(128), (size_t)(0), s, p);
     }
   }
   return check_launch(e, kGrpNames[grp]);
@@ -371,7 +371,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   } else {
     {
       Launch l(e, s, G_FRONT3);
-      front3_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(e->q, nullptr, W(e, "pcl_net.stn.conv1.weight"),
+      launch_pdl(front3_kernel, dim3((unsigned)((R * 16 + 255) / 256)), dim3(256), (size_t)(0), s, e->q, nullptr, W(e, "pcl_net.stn.conv1.weight"),
                                                                     W(e, "pcl_net.stn.conv1.bias"), e->h64a, R, N);
     }
     if ((rc = check_launch(e, "front3"))) return rc;
@@ -391,7 +391,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   } else {
     {
       Launch l(e, s, G_FRONT3);
-      front3_kernel<<<(unsigned)((R * 16 + 255) / 256), 256, 0, s>>>(e->q, e->t3, W(e, "pcl_net.conv1.weight"),
+      launch_pdl(front3_kernel, dim3((unsigned)((R * 16 + 255) / 256)), dim3(256), (size_t)(0), s, e->q, e->t3, W(e, "pcl_net.conv1.weight"),
                                                                     W(e, "pcl_net.conv1.bias"), e->h64a, R, N);
     }
     if ((rc = check_launch(e, "front3"))) return rc;
@@ -460,7 +460,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
                             W(e, "ts_head.linears.0.bias"), B, 256, 1024, 0, e->ts0, nullptr))) return rc;
     {
       Launch l(e, e->side, G_TS_POSE);
-      ts_head_kernel<<<B, 256, 0, e->side>>>(tsp);
+      launch_pdl(ts_head_kernel, dim3(B), dim3(256), (size_t)(0), e->side, tsp);
     }
     if ((rc = check_launch(e, "ts_head"))) return rc;
     CU_TRY(e, cudaEventRecord(e->ev_join, e->side));
@@ -483,7 +483,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = tc_run<CH_ON_LANES, EPI_STATS, 256>(e, s, G_ROT_LAYER0, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->pf_nb[0], e->pf_nb[1], p))) return rc;
     {
       Launch l(e, s, G_GN_FINALIZE);
-      gn_finalize_set_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats0, e->rot_gn0_g, e->rot_gn0_b, e->cset, gn0_scale,
+      launch_pdl(gn_finalize_set_kernel, dim3((B * 64 + 127) / 128), dim3(128), (size_t)(0), s, e->stats0, e->rot_gn0_g, e->rot_gn0_b, e->cset, gn0_scale,
                                                                  gn0_shift, B, 512, P / 128, P);
     }
     if ((rc = check_launch(e, "gn_finalize_set"))) return rc;
@@ -514,7 +514,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_ROT_LAYER0, p))) return rc;
     {
       Launch l(e, s, G_GN_FINALIZE);
-      gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats0, e->rot_gn0_g, e->rot_gn0_b, gn0_scale, gn0_shift, B,
+      launch_pdl(gn_finalize_kernel, dim3((B * 64 + 127) / 128), dim3(128), (size_t)(0), s, e->stats0, e->rot_gn0_g, e->rot_gn0_b, gn0_scale, gn0_shift, B,
                                                              512, P / 128, P);
     }
     if ((rc = check_launch(e, "gn_finalize"))) return rc;
@@ -529,7 +529,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   }
   {
     Launch l(e, s, G_GN_FINALIZE);
-    gn_finalize_kernel<<<(B * 64 + 127) / 128, 128, 0, s>>>(e->stats1, e->rot_gn1_g, e->rot_gn1_b, e->gn1,
+    launch_pdl(gn_finalize_kernel, dim3((B * 64 + 127) / 128), dim3(128), (size_t)(0), s, e->stats1, e->rot_gn1_g, e->rot_gn1_b, e->gn1,
                                                            e->gn1 + (size_t)e->maxB * 512, B, 512,
                                                            tc ? P / 64 : P / 128, P);
   }
@@ -537,10 +537,10 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   {
     Launch l(e, s, G_ROT_TAIL);
     if (tc)
-      rot_tail_t_kernel<<<dim3(16, B), 256, P * sizeof(float), s>>>(reinterpret_cast<const __half*>(e->a1), e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
+      launch_pdl(rot_tail_t_kernel, dim3(dim3(16, B)), dim3(256), (size_t)(P * sizeof(float)), s, reinterpret_cast<const __half*>(e->a1), e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
                                                                    e->neck_b, e->wp, e->rot_partial, P);
     else
-      rot_tail_kernel<<<dim3(P / 128, B), 256, 0, s>>>(e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
+      launch_pdl(rot_tail_kernel, dim3(dim3(P / 128, B)), dim3(256), (size_t)(0), s, e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
                                                          e->wp, e->rot_partial, P);
   }
   if ((rc = check_launch(e, "rot_tail"))) return rc;
@@ -549,7 +549,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   CU_TRY(e, cudaStreamWaitEvent(s, e->ev_join, 0));
   {
     Launch l(e, s, G_TS_POSE);
-    pose_update_kernel<<<(B + 7) / 8, 256, 0, s>>>(tsp, B);
+    launch_pdl(pose_update_kernel, dim3((B + 7) / 8), dim3(256), (size_t)(0), s, tsp, B);
   }
   return check_launch(e, "pose_update");
 }
@@ -854,7 +854,7 @@ int catre_forward_once(catre_engine* e, const float* x_pm, const float* kps_pm, 
     long long total = (long long)Bc * 2 * N;
     {
       Launch l(e, s, G_UPDATE_POINTS);
-      gather_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(x_pm + (size_t)b0 * N * 3, kps_pm + (size_t)b0 * N * 3,
+      launch_pdl(gather_points_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, x_pm + (size_t)b0 * N * 3, kps_pm + (size_t)b0 * N * 3,
                                                                           e->q, Bc, N);
     }
     if ((rc = check_launch(e, "gather_points"))) return rc;
@@ -887,7 +887,7 @@ int catre_refine(catre_engine* e, const float* pcl, const float* prior, const fl
       float* sout = out_scales + ((size_t)it * B + b0) * 3;
       {
         Launch l(e, s, G_UPDATE_POINTS);
-        update_points_kernel<<<(unsigned)((total + 255) / 256), 256, 0, s>>>(pcl + (size_t)b0 * N * 3, prior + (size_t)b0 * N * 3,
+        launch_pdl(update_points_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, pcl + (size_t)b0 * N * 3, prior + (size_t)b0 * N * 3,
                                                                             pin, sin, e->q, Bc, N);
       }
       if ((rc = check_launch(e, "update_points"))) return rc;

@@ -13,6 +13,23 @@ namespace catre {
 // small helpers
 // ----------------------------------------------------------------------------------------------
 
+// Programmatic dependent launch: every kernel of the chain is launched with the programmatic-stream-
+// serialization attribute, so its CTAs may be scheduled (and run their prologue: barrier init, TMEM allocation,
+// tensor-map prefetch, weight staging) while the previous kernel drains; pdl_wait() blocks until that kernel
+// has completed and its writes are visible, and must precede the first access to upstream data.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
 // order-preserving float <-> int key, so a column max over points can use atomicMax(int)
 __device__ __forceinline__ int f2key(float f) {
   int i = __float_as_int(f);
@@ -46,6 +63,7 @@ __device__ __forceinline__ float gelu_fast(float x) {
 }
 
 __global__ void fill_i32_kernel(int* __restrict__ p, long long n, int v) {
+  pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long stride = (long long)gridDim.x * blockDim.x;
   for (; i < n; i += stride) p[i] = v;
@@ -59,6 +77,7 @@ __global__ void fill_i32_kernel(int* __restrict__ p, long long n, int v) {
 __global__ void update_points_kernel(const float* __restrict__ pcl, const float* __restrict__ prior,
                                      const float* __restrict__ pose, const float* __restrict__ scale,
                                      float* __restrict__ q, int B, int N) {
+  pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)B * 2 * N;
   if (i >= total) return;
@@ -86,6 +105,7 @@ __global__ void update_points_kernel(const float* __restrict__ pcl, const float*
 // forward_once entry: x and tfd_kps arrive already transformed; interleave them into the q layout
 __global__ void gather_points_kernel(const float* __restrict__ x_pm, const float* __restrict__ kps_pm,
                                      float* __restrict__ q, int B, int N) {
+  pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)B * 2 * N;
   if (i >= total) return;
@@ -105,6 +125,7 @@ __global__ void gather_points_kernel(const float* __restrict__ x_pm, const float
 __global__ void front3_kernel(const float* __restrict__ q, const float* __restrict__ t3 /*[S,9] or null*/,
                               const float* __restrict__ W /*[64,3]*/, const float* __restrict__ bias,
                               float* __restrict__ out, long long R, int N) {
+  pdl_wait();
   __shared__ float sW[64 * 3];
   __shared__ float sB[64];
   for (int i = threadIdx.x; i < 192; i += blockDim.x) sW[i] = W[i];
@@ -156,6 +177,7 @@ struct GemmP {
 
 template <int BN, int AMODE>
 __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
+  pdl_wait();
   constexpr int BM = 128, BK = 16;
   constexpr int TN = BN / 16;           // 8 or 4 columns per thread
   constexpr int NCH = TN / 4;           // 4-column chunks per thread (2 or 1)
@@ -344,6 +366,7 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
 __global__ void gn_finalize_kernel(const float* __restrict__ stats, const float* __restrict__ gamma,
                                    const float* __restrict__ beta, float* __restrict__ scale,
                                    float* __restrict__ shift, int B, int C, int tiles_per_obj, int rows_per_obj) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int G = C / 8;
   if (i >= B * G) return;
@@ -395,6 +418,7 @@ struct FcP {
 // threads (4 x 4 per thread) when R is small, so that a layer still spreads over >= 128 CTAs.
 template <int AMODE, int BM, int BN, int NT>
 __global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(NT) fc_cluster_kernel(FcP p) {
+  pdl_wait();
   namespace cg = cooperative_groups;
   constexpr int BK = 16, DEPTH = 4;
   constexpr int TM = BM * BN / NT / 4;     // rows per thread (8 or 4); 4 columns per thread
@@ -528,6 +552,7 @@ __global__ void gn_finalize_set_kernel(const float* __restrict__ stats, const fl
                                        const float* __restrict__ beta, const float* __restrict__ cset,
                                        float* __restrict__ scale, float* __restrict__ shift, int B, int C,
                                        int tiles_per_obj, int rows_per_obj) {
+  pdl_wait();
   int i = blockIdx.x * blockDim.x + threadIdx.x;
   int G = C / 8;
   if (i >= B * G) return;
@@ -572,6 +597,7 @@ __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__
                                                        const float* __restrict__ neck_b /*[2][3]*/,
                                                        const float* __restrict__ wp /*[2][P]*/, float* __restrict__ partial,
                                                        int P) {
+  pdl_wait();
   const int b = blockIdx.y, tile = blockIdx.x, tiles = gridDim.x;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   __shared__ float s_part[8][6];
@@ -636,6 +662,7 @@ __global__ void __launch_bounds__(256) rot_tail_t_kernel(const __half* __restric
                                                          const float* __restrict__ neck_b /*[2][3]*/,
                                                          const float* __restrict__ wp /*[2][P]*/, float* __restrict__ partial,
                                                          int P) {
+  pdl_wait();
   extern __shared__ __align__(16) float s_wp[];  // [P]
   __shared__ float s_part[8][3];
   const int b = blockIdx.y, cg = blockIdx.x, h = cg >> 3;  // 16 blocks per object, 8 per head
@@ -734,6 +761,7 @@ __device__ __forceinline__ float gn8_gelu(float v, float gamma, float beta) {
 // ts_head_kernel: H1 (independent of the rotation head, so the host runs it on a side stream underneath the
 // rot kernels).  pose_update_kernel: G1 + G2, one warp per object, after both heads are done.
 __global__ void __launch_bounds__(256) ts_head_kernel(TsPoseP p) {
+  pdl_wait();
   const int b = blockIdx.x, t = threadIdx.x;
   __shared__ float feat2[68];  // pointfeat max (64) | init scale (3)
   __shared__ float h[256];
@@ -791,6 +819,7 @@ __global__ void __launch_bounds__(256) ts_head_kernel(TsPoseP p) {
 }
 
 __global__ void __launch_bounds__(256) pose_update_kernel(TsPoseP p, int B) {
+  pdl_wait();
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.x * 8 + warp;
   if (b >= B) return;

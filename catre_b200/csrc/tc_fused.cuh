@@ -105,6 +105,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   constexpr uint32_t SLOT_TX = (NPROD == 3) ? 32768 : 16384;
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer (same order as the MMA warp consumes) =====================
@@ -353,8 +354,7 @@ cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo,
   int items = p.tiles * 2;
   int grid = items < num_sms ? items : num_sms;
   if (grid < 1) return cudaSuccess;
-  kern<<<grid, RF_THREADS, RF_SMEM, s>>>(pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, a1t_map, p);
-  return cudaPeekAtLastError();
+  return launch_pdl(kern, dim3(grid), dim3(RF_THREADS), (size_t)RF_SMEM, s, pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, a1t_map, p);
 }
 
 
@@ -417,6 +417,7 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
   constexpr uint32_t SLOT_TX = (NPROD == 3) ? 32768 : 16384;
+  pdl_wait();  // the prologue above overlapped the previous kernel's tail
 
   if (warp == 0) {
     // ===================== TMA producer =====================
@@ -598,8 +599,7 @@ cudaError_t enc_fused_launch(const CUtensorMap& x_hi, const CUtensorMap& x_lo, c
   }
   int grid = p.tiles < num_sms ? p.tiles : num_sms;
   if (grid < 1) return cudaSuccess;
-  kern<<<grid, RF_THREADS, RF_SMEM, s>>>(x_hi, x_lo, w2_hi, w2_lo, w3_hi, w3_lo, p);
-  return cudaPeekAtLastError();
+  return launch_pdl(kern, dim3(grid), dim3(RF_THREADS), (size_t)RF_SMEM, s, x_hi, x_lo, w2_hi, w2_lo, w3_hi, w3_lo, p);
 }
 
 }  // namespace catre

@@ -319,6 +319,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
   __syncthreads();
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot_ptr;
+  pdl_wait();  // everything above overlapped the previous kernel's tail; upstream data is touched only below
 
   // tile t of this CTA's sequence: blockIdx.x, blockIdx.x + gridDim.x, ...  With resident weights the grid is
   // a multiple of n_tiles, so t % n_tiles (the weight tile) is the same for every tile of a CTA.
@@ -547,6 +548,7 @@ __global__ void __launch_bounds__(256) front3_split_kernel(const float* __restri
   const int r0 = blockIdx.x * FRONT_PTS;  // first point of the block
   if (threadIdx.x < 192) sW[threadIdx.x] = W[threadIdx.x];
   if (threadIdx.x >= 192) sB[threadIdx.x - 192] = bias[threadIdx.x - 192];
+  pdl_wait();  // weights above are constants; the transform and the points come from upstream kernels
   if (threadIdx.x < 9) sT[threadIdx.x] = t3 ? t3[(r0 / N) * 9 + threadIdx.x] : ((threadIdx.x % 4 == 0) ? 1.0f : 0.0f);
   for (int i = threadIdx.x; i < FRONT_PTS * 3; i += 256) sQ[i] = (r0 * 3 + i < R * 3) ? q[(size_t)r0 * 3 + i] : 0.0f;
   __syncthreads();
@@ -656,8 +658,7 @@ cudaError_t tc_launch(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const 
     grid -= grid % p.n_tiles;  // every CTA keeps one weight tile: t % n_tiles must not change along its sequence
   }
   if (grid < 1) return cudaSuccess;
-  kern<<<grid, TcEpi<ORIENT, BN>::THREADS, smem, s>>>(ma_hi, ma_lo, nb_hi, nb_lo, out_hi, out_lo, q);
-  return cudaPeekAtLastError();
+  return launch_pdl(kern, dim3(grid), dim3(TcEpi<ORIENT, BN>::THREADS), (size_t)smem, s, ma_hi, ma_lo, nb_hi, nb_lo, out_hi, out_lo, q);
 }
 
 }  // namespace catre
