@@ -72,12 +72,12 @@ constexpr int kNumWeights = sizeof(kWeights) / sizeof(kWeights[0]);
 
 // kernel groups for launch accounting / per-group device timing
 enum Grp {
-  G_FILL, G_UPDATE_POINTS, G_FRONT3, G_STN_CONV2, G_STN_CONV3_MAX, G_TNET_FC, G_FSTN_CONV1, G_FSTN_CONV2,
+  G_UPDATE_POINTS, G_FRONT3, G_STN_CONV2, G_STN_CONV3_MAX, G_TNET_FC, G_FSTN_CONV1, G_FSTN_CONV2,
   G_FSTN_CONV3_MAX, G_FEAT_TRANSFORM, G_CONV2, G_CONV3, G_CONV4_MAX, G_ROT_GFEAT, G_ROT_LAYER0, G_GN_FINALIZE,
   G_ROT_LAYER1, G_ROT_TAIL, G_TS_POSE, G_ROT_FUSED, G_NUM
 };
 const char* kGrpNames[G_NUM] = {
-    "fill", "update_points", "front3", "stn_conv2", "stn_conv3_max", "tnet_fc", "fstn_conv1", "fstn_conv2",
+    "update_points", "front3", "stn_conv2", "stn_conv3_max", "tnet_fc", "fstn_conv1", "fstn_conv2",
     "fstn_conv3_max", "feat_transform", "conv2", "conv3", "conv4_max", "rot_gfeat", "rot_layer0", "gn_finalize",
     "rot_layer1", "rot_tail", "ts_pose", "rot_fused"};
 
@@ -106,7 +106,6 @@ struct catre_engine {
   cudaStream_t side = nullptr;           // the ts head runs here, underneath the rot-head kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
   float* dts = nullptr;                  // [B, 6] raw ts-head outputs
-  long long* rf_dbg = nullptr;  // timeline buffer of the fused rot kernel (CATRE_RF_DEBUG=1)
   CUtensorMap tw_rot0_nb[2];  // rot layer-0 point-feature weights [512, 64] as an N-side operand (256-row boxes)
   float *fstn_fc3_wT = nullptr;  // fstn.fc3 rows permuted so the FC emits T64^T (row j = output channel j of pf = h1 . T64)
   int num_sms = 148;
@@ -232,17 +231,6 @@ int run_gemm(catre_engine* e, cudaStream_t s, int grp, const GemmP& p) {
   return check_launch(e, kGrpNames[grp]);
 }
 
-int fill_i32(catre_engine* e, cudaStream_t s, int* p, long long n, int v) {
-  int blocks = (int)((n + 255) / 256);
-  if (blocks > 148 * 8) blocks = 148 * 8;
-  if (blocks < 1) blocks = 1;
-  {
-    Launch l(e, s, G_FILL);
-    launch_pdl(fill_i32_kernel, dim3(blocks), dim3(256), (size_t)(0), s, p, n, v);
-  }
-  return check_launch(e, "fill");
-}
-
 const float* W(catre_engine* e, const char* name) { return e->dw.at(name); }
 
 // ---- tensor-core launch helpers ------------------------------------------------------------------
@@ -356,12 +344,11 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   int rc;
   const bool tc = e->cfg.precision != CATRE_PREC_FP32_SIMT;
 
-  // column-max key buffers are laid out for the current S so one fill resets all of them
+  // column-max key buffers are laid out for the current S; the point kernel that filled e->q has reset them
   e->gmax_stn = e->gmax_all;
   e->gmax_fstn = e->gmax_all + (size_t)S * 1024;
   e->gmax_g = e->gmax_all + (size_t)S * 2048;
   e->gmax_pf = e->gmax_all + (size_t)S * 3072;
-  if ((rc = fill_i32(e, s, e->gmax_all, (long long)S * (1024 * 3 + 64), KEY_NEG_INF))) return rc;
 
   // ---- E1: STN3d (pointnets/pointnet.py:24-41)
   if (tc) {
@@ -491,7 +478,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
       // layer-0 recompute + GroupNorm + GELU + bf16 split into shared memory + layer 1, one kernel
       RotFusedP pf{};
       pf.tiles = (int)(R / 128); pf.rows_per_set = N; pf.rows_per_obj = P;
-      pf.gn_scale = gn0_scale; pf.gn_shift = gn0_shift; pf.bias1 = e->rot_b1; pf.stats = e->stats1; pf.dbg = e->rf_dbg;
+      pf.gn_scale = gn0_scale; pf.gn_shift = gn0_shift; pf.bias1 = e->rot_b1; pf.stats = e->stats1;
       cudaError_t st;
       {
         Launch l(e, s, G_ROT_FUSED);
@@ -527,21 +514,20 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
       if ((rc = run_gemm<128, A_GN_GELU>(e, s, G_ROT_LAYER1, p1))) return rc;
     }
   }
-  {
+  if (!tc) {
     Launch l(e, s, G_GN_FINALIZE);
     launch_pdl(gn_finalize_kernel, dim3((B * 64 + 127) / 128), dim3(128), (size_t)(0), s, e->stats1, e->rot_gn1_g, e->rot_gn1_b, e->gn1,
-                                                           e->gn1 + (size_t)e->maxB * 512, B, 512,
-                                                           tc ? P / 64 : P / 128, P);
+               e->gn1 + (size_t)e->maxB * 512, B, 512, P / 128, P);
   }
   if ((rc = check_launch(e, "gn_finalize"))) return rc;
   {
     Launch l(e, s, G_ROT_TAIL);
-    if (tc)
-      launch_pdl(rot_tail_t_kernel, dim3(dim3(16, B)), dim3(256), (size_t)(P * sizeof(float)), s, reinterpret_cast<const __half*>(e->a1), e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
-                                                                   e->neck_b, e->wp, e->rot_partial, P);
+    if (tc)  // finalises the GroupNorm-1 statistics itself (partials per 64 points from the fused rot kernel)
+      launch_pdl(rot_tail_t_kernel, dim3(16, B), dim3(256), (size_t)(P * sizeof(float)), s, reinterpret_cast<const __half*>(e->a1),
+                 e->stats1, e->rot_gn1_g, e->rot_gn1_b, P / 64, e->neck_w, e->neck_b, e->wp, e->rot_partial, P);
     else
-      launch_pdl(rot_tail_kernel, dim3(dim3(P / 128, B)), dim3(256), (size_t)(0), s, e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w, e->neck_b,
-                                                         e->wp, e->rot_partial, P);
+      launch_pdl(rot_tail_kernel, dim3(P / 128, B), dim3(256), (size_t)(0), s, e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
+                 e->neck_b, e->wp, e->rot_partial, P);
   }
   if ((rc = check_launch(e, "rot_tail"))) return rc;
 
@@ -642,10 +628,6 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) rc |= 1;
-  {
-    const char* dbg = getenv("CATRE_RF_DEBUG");
-    if (dbg && dbg[0] == '1') rc |= dalloc(e, &e->rf_dbg, 8 * 32);
-  }
   if (!rc && tc) {
     auto pair = [&](TcPair& t, size_t cols) {
       rc |= dalloc(e, &t.hi, R * cols);
@@ -855,7 +837,7 @@ int catre_forward_once(catre_engine* e, const float* x_pm, const float* kps_pm, 
     {
       Launch l(e, s, G_UPDATE_POINTS);
       launch_pdl(gather_points_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, x_pm + (size_t)b0 * N * 3, kps_pm + (size_t)b0 * N * 3,
-                                                                          e->q, Bc, N);
+                 e->q, Bc, N, e->gmax_all, (long long)(2 * Bc) * (1024 * 3 + 64));
     }
     if ((rc = check_launch(e, "gather_points"))) return rc;
     if ((rc = iteration(e, s, Bc, pose + (size_t)b0 * 12, scale + (size_t)b0 * 3, K + (size_t)b0 * 9,
@@ -888,7 +870,7 @@ int catre_refine(catre_engine* e, const float* pcl, const float* prior, const fl
       {
         Launch l(e, s, G_UPDATE_POINTS);
         launch_pdl(update_points_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, pcl + (size_t)b0 * N * 3, prior + (size_t)b0 * N * 3,
-                                                                            pin, sin, e->q, Bc, N);
+                   pin, sin, e->q, Bc, N, e->gmax_all, (long long)(2 * Bc) * (1024 * 3 + 64));
       }
       if ((rc = check_launch(e, "update_points"))) return rc;
       if ((rc = iteration(e, s, Bc, pin, sin, K + (size_t)b0 * 9, pout, sout))) return rc;
@@ -939,7 +921,7 @@ int catre_debug_read(catre_engine* e, const char* name, void* dst_host, size_t b
       {"q", e->q}, {"h64a", e->h64a}, {"h64b", e->h64b}, {"h128", e->h128}, {"h512", e->h512}, {"a0", e->a0}, {"a1", e->a1},
       {"gmax_stn", e->gmax_stn}, {"gmax_fstn", e->gmax_fstn}, {"gmax_g", e->gmax_g}, {"gmax_pf", e->gmax_pf},
       {"fc512", e->fc512}, {"fc256", e->fc256}, {"t3", e->t3}, {"t64", e->t64}, {"cset", e->cset},
-      {"t64s_hi", e->t64s.hi}, {"t64s_lo", e->t64s.lo}, {"rf_dbg", e->rf_dbg},
+      {"t64s_hi", e->t64s.hi}, {"t64s_lo", e->t64s.lo},
       {"stats0", e->stats0}, {"stats1", e->stats1}, {"gn0", e->gn0}, {"gn1", e->gn1}, {"rot_partial", e->rot_partial}};
   m["x64_hi"] = e->x64.hi; m["x64_lo"] = e->x64.lo; m["f64_hi"] = e->f64.hi; m["f64_lo"] = e->f64.lo;
   m["a128_hi"] = e->a128.hi; m["a128_lo"] = e->a128.lo; m["pf_hi"] = e->pf16.hi; m["pf_lo"] = e->pf16.lo;

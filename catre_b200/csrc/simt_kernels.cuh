@@ -62,24 +62,19 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(-fabsf(x), e, fmaxf(x, 0.0f));
 }
 
-__global__ void fill_i32_kernel(int* __restrict__ p, long long n, int v) {
-  pdl_wait();
-  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long stride = (long long)gridDim.x * blockDim.x;
-  for (; i < n; i += stride) p[i] = v;
-}
-
 // ----------------------------------------------------------------------------------------------
 // U1: per-iteration point update (core/catre/engine/batch_test.py:78-97,
 //     lib/pysixd/misc.py:1011-1026):  x = pcl - t ;  k = R (s * kps)
 // q layout: set 2b = observed points of object b, set 2b+1 = prior points; [2B, N, 3] point-major.
 // ----------------------------------------------------------------------------------------------
+// Both point kernels also reset the iteration's column-max keys (gmax, n_keys ints) to -inf.
 __global__ void update_points_kernel(const float* __restrict__ pcl, const float* __restrict__ prior,
                                      const float* __restrict__ pose, const float* __restrict__ scale,
-                                     float* __restrict__ q, int B, int N) {
+                                     float* __restrict__ q, int B, int N, int* __restrict__ gmax, long long n_keys) {
   pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)B * 2 * N;
+  for (long long k = i; k < n_keys; k += (long long)gridDim.x * blockDim.x) gmax[k] = KEY_NEG_INF;
   if (i >= total) return;
   int b = (int)(i / (2 * N));
   int r = (int)(i % (2 * N));
@@ -104,10 +99,11 @@ __global__ void update_points_kernel(const float* __restrict__ pcl, const float*
 
 // forward_once entry: x and tfd_kps arrive already transformed; interleave them into the q layout
 __global__ void gather_points_kernel(const float* __restrict__ x_pm, const float* __restrict__ kps_pm,
-                                     float* __restrict__ q, int B, int N) {
+                                     float* __restrict__ q, int B, int N, int* __restrict__ gmax, long long n_keys) {
   pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)B * 2 * N;
+  for (long long k = i; k < n_keys; k += (long long)gridDim.x * blockDim.x) gmax[k] = KEY_NEG_INF;
   if (i >= total) return;
   int b = (int)(i / (2 * N));
   int r = (int)(i % (2 * N));
@@ -656,25 +652,50 @@ __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__
 // fused rot kernel's TMA stores).  One warp per channel: lanes stride over the
 // points, S_c = sum_p wp[p] gelu(a1T[c][p] sc_c + sh_c), and the neck is applied to S_c (linearity, see
 // above).  Block = 32 channels of one head of one object; partial[b][blockIdx.x][6] (other head's 3 = 0).
-__global__ void __launch_bounds__(256) rot_tail_t_kernel(const __half* __restrict__ a1t, const float* __restrict__ gn_scale,
-                                                         const float* __restrict__ gn_shift,
+// The GroupNorm-1 statistics are finalised here as well (fp64 sum of the block's 4 groups x tiles_per_obj
+// partials written by the fused rot kernel), so no separate finalize launch is needed.
+__global__ void __launch_bounds__(256) rot_tail_t_kernel(const __half* __restrict__ a1t, const float* __restrict__ stats /*[R/64][64][2]*/,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta /*[512]*/,
+                                                         int tiles_per_obj,
                                                          const float* __restrict__ neck_w /*[2][3][256]*/,
                                                          const float* __restrict__ neck_b /*[2][3]*/,
                                                          const float* __restrict__ wp /*[2][P]*/, float* __restrict__ partial,
                                                          int P) {
-  pdl_wait();
   extern __shared__ __align__(16) float s_wp[];  // [P]
   __shared__ float s_part[8][3];
+  __shared__ float s_sc[32], s_sh[32];
   const int b = blockIdx.y, cg = blockIdx.x, h = cg >> 3;  // 16 blocks per object, 8 per head
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  for (int i = threadIdx.x; i < P / 4; i += 256)
+  for (int i = threadIdx.x; i < P / 4; i += 256)  // weights: constants, staged before the dependency wait
     reinterpret_cast<float4*>(s_wp)[i] = __ldg(reinterpret_cast<const float4*>(wp + (long long)h * P) + i);
+  pdl_wait();
+  if (warp < 4) {  // GroupNorm(32 groups of 8 channels per head): group cg*4 + warp of the object's 64
+    const int g = cg * 4 + warp;
+    double s = 0.0, ss = 0.0;
+    for (int t = lane; t < tiles_per_obj; t += 32) {
+      const long long o = (((long long)b * tiles_per_obj + t) * 64 + g) * 2;
+      s += (double)stats[o];
+      ss += (double)stats[o + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    const double n = 8.0 * P, mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5)), fmean = (float)mean;
+    if (lane < 8) {
+      const int c = g * 8 + lane;
+      const float sc = rstd * gamma[c];
+      s_sc[warp * 8 + lane] = sc;
+      s_sh[warp * 8 + lane] = beta[c] - fmean * sc;
+    }
+  }
   __syncthreads();
   float r0 = 0.f, r1 = 0.f, r2 = 0.f;
 #pragma unroll 1
   for (int cc = 0; cc < 4; ++cc) {
     const int c = cg * 32 + warp * 4 + cc;  // channel in [0, 512)
-    const float sc = gn_scale[(long long)b * 512 + c], sh = gn_shift[(long long)b * 512 + c];
+    const float sc = s_sc[warp * 4 + cc], sh = s_sh[warp * 4 + cc];
     const uint4* row = reinterpret_cast<const uint4*>(a1t + ((long long)b * 512 + c) * P);  // 8 points per load
     float acc = 0.f;
 #pragma unroll 2

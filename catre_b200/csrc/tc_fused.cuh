@@ -40,7 +40,6 @@ struct RotFusedP {
   const float* gn_shift; // [S][512]  shift with the per-set constant folded in
   const float* bias1;    // [512]     layers.3 bias, both heads
   float* stats;          // [R/64][64 groups][2]
-  long long* dbg;        // optional timeline of CTA 0 (debug): [work item][32] clock64 stamps, or null
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
