@@ -294,7 +294,8 @@ def main():
         roofline = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_tflops"], "traffic": ncu_traffic(top, B), "peak_source": peaks["source"],
                     "ms_per_launch": ms_launch, "share_of_step": cand[top][0] / tot if tot else None,
-                    "mma_products_per_mac": nprod,
+                    "mma_products_per_mac": nprod, "issued_mma_tflops": ach * nprod,
+                    "issued_mma_frac_of_peak": ach * nprod / peaks["bf16_tflops"],
                     "note": "achieved = algorithmic FLOPs (one fp32-equivalent product per MAC) / CUDA-event time; "
                             f"the {args.precision} mode issues {nprod} bf16 MMA product(s) per MAC"
                             + (" on CUDA cores (no tensor pipe)" if args.precision == "fp32" else ""),

@@ -416,7 +416,7 @@ template <int AMODE, int BM, int BN, int NT>
 __global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(NT) fc_cluster_kernel(FcP p) {
   pdl_wait();
   namespace cg = cooperative_groups;
-  constexpr int BK = 16, DEPTH = 4;
+  constexpr int BK = 16, DEPTH = (NT == 128) ? 8 : 4;  // chunks of global loads in flight per thread
   constexpr int TM = BM * BN / NT / 4;     // rows per thread (8 or 4); 4 columns per thread
   constexpr int TXN = BN / 4;              // threads along the columns
   constexpr int A_IT = BM * BK / 4 / NT;   // float4 loads of the A chunk per thread
