@@ -115,6 +115,9 @@ struct catre_engine {
   int *gmax_all = nullptr, *gmax_stn = nullptr, *gmax_fstn = nullptr, *gmax_g = nullptr, *gmax_pf = nullptr;
   float *fc512 = nullptr, *fc256 = nullptr, *ts0 = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
   CUtensorMap a1t_map;  // fp16 a1T [maxB*512, P] for the fused rot kernel's TMA stores (64-point x 128-channel boxes)
+  // tensor-core FC path of the T-Nets / rot g-feature: operands [Spad, K] (Spad = S rounded up to 128 rows)
+  TcPair g16, fc1o, fc2o, t64s_out;  // t64s_out: the t64s memory viewed as [Spad, 4096] for the FC's TMA stores
+  TcPair tw_fc1[2], tw_fc2[2], tw_fstn_fc3, tw_rot_w0g;  // [0] = stn, [1] = fstn
   TcPair t64s;  // tensor-core modes: bf16 hi/lo of T64^T, [S*64, 64]
   float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
   // bf16 hi/lo activations of the tensor-core path and their tensor maps
@@ -161,6 +164,7 @@ int dalloc(catre_engine* e, T** p, size_t n) {
   size_t bytes = n * sizeof(T);
   if (bytes == 0) bytes = 16;
   CU_TRY(e, cudaMalloc(&v, bytes));
+  CU_TRY(e, cudaMemset(v, 0, bytes));  // padded operand rows (beyond the live sets) must hold finite values
   e->dev_allocs.push_back(v);
   e->ws_bytes += bytes;
   *p = reinterpret_cast<T*>(v);
@@ -336,6 +340,39 @@ int tnet_fc(catre_engine* e, cudaStream_t s, const int* keys, int S, const char*
   return run_fc<A_PLAIN>(e, s, G_TNET_FC, e->fc256, 256, fc3_w, 256, fc3_bias_I, S, kk, 256, 0, out32, out16);
 }
 
+// ---- tensor-core small-M FC layers (tensor-core modes): out[S, C] = act(in[S, K] . W[C, K]^T + b) with the
+//      sets on the TMEM lanes (one or a few 128-row tiles), weights streamed, bf16x3 like every wide layer
+int tc_keys_split(catre_engine* e, cudaStream_t s, int grp, const int* keys, int S, const TcPair& out) {
+  const long long n4 = (long long)S * 1024 / 4;
+  {
+    Launch l(e, s, grp);
+    launch_pdl(keys_split_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), (size_t)0, s, keys,
+               reinterpret_cast<unsigned short*>(out.hi), reinterpret_cast<unsigned short*>(out.lo), n4);
+  }
+  return check_launch(e, "keys_split");
+}
+
+int tc_fc(catre_engine* e, cudaStream_t s, int grp, const TcPair& in, const TcPair& w, int S, int C, int K, const float* bias,
+          int relu, const TcPair& out16, float* out32) {
+  TcGemmP p{};
+  p.K = K; p.m_tiles = (S + 127) / 128; p.n_tiles = C / 64; p.rows_per_set = 1 << 30;
+  p.bias = bias; p.relu = relu; p.out32 = out32; p.ldo32 = C; p.rows32 = S;
+  return tc_run<PT_ON_LANES, EPI_SPLIT_STREAM, 64>(e, s, grp, in.map_hi, in.map_lo, w.map_hi, w.map_lo, p, &out16);
+}
+
+// T-Net FC chain on the tensor cores: which = 0 (stn, kk = 9: last layer stays a fp32 cluster FC) or 1 (fstn, kk = 4096)
+int tnet_fc_tc(catre_engine* e, cudaStream_t s, const int* keys, int S, int which) {
+  const char* pre = which ? "pcl_net.fstn" : "pcl_net.stn";
+  std::string pf(pre);
+  int rc;
+  if ((rc = tc_keys_split(e, s, G_TNET_FC, keys, S, e->g16))) return rc;
+  if ((rc = tc_fc(e, s, G_TNET_FC, e->g16, e->tw_fc1[which], S, 512, 1024, W(e, (pf + ".fc1.bias").c_str()), 1, e->fc1o, nullptr))) return rc;
+  if ((rc = tc_fc(e, s, G_TNET_FC, e->fc1o, e->tw_fc2[which], S, 256, 512, W(e, (pf + ".fc2.bias").c_str()), 1, e->fc2o,
+                  which ? nullptr : e->fc256))) return rc;
+  if (which) return tc_fc(e, s, G_TNET_FC, e->fc2o, e->tw_fstn_fc3, S, 4096, 256, e->fstn_fc3_bI, 0, e->t64s_out, nullptr);
+  return run_fc<A_PLAIN>(e, s, G_TNET_FC, e->fc256, 256, W(e, "pcl_net.stn.fc3.weight"), 256, e->stn_fc3_bI, S, 9, 256, 0, e->t3, nullptr);
+}
+
 // One refinement iteration on a chunk of B objects whose points are already in e->q.
 int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, const float* scale_in, const float* K,
               float* pose_out, float* scale_out) {
@@ -343,6 +380,9 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   const long long R = (long long)S * N;
   int rc;
   const bool tc = e->cfg.precision != CATRE_PREC_FP32_SIMT;
+  // small-M FC layers: tensor cores when there are at least two 128-row tiles of sets (measured: B=256 -0.33 ms),
+  // split-K cluster FMA kernels otherwise (with one tile only 4-8 CTAs would stream all of K: B=64 +0.05 ms)
+  const bool tc_fcs = tc && S >= 256;
 
   // column-max key buffers are laid out for the current S; the point kernel that filled e->q has reset them
   e->gmax_stn = e->gmax_all;
@@ -370,7 +410,9 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p.gmax = e->gmax_stn; p.rows_per_set = N;
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_STN_CONV3_MAX, p))) return rc;
   }
-  if ((rc = tnet_fc(e, s, e->gmax_stn, S, "pcl_net.stn", W(e, "pcl_net.stn.fc3.weight"), e->stn_fc3_bI, 9, e->t3, nullptr))) return rc;
+  if (tc_fcs) {
+    if ((rc = tnet_fc_tc(e, s, e->gmax_stn, S, 0))) return rc;
+  } else if ((rc = tnet_fc(e, s, e->gmax_stn, S, "pcl_net.stn", W(e, "pcl_net.stn.fc3.weight"), e->stn_fc3_bI, 9, e->t3, nullptr))) return rc;
 
   // ---- E2: input transform + conv1 (pointnet.py:97-103)
   if (tc) {
@@ -401,8 +443,10 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p.gmax = e->gmax_fstn; p.rows_per_set = N;
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_FSTN_CONV3_MAX, p))) return rc;
   }
-  if ((rc = tnet_fc(e, s, e->gmax_fstn, S, "pcl_net.fstn", e->fstn_fc3_wT, e->fstn_fc3_bI, 4096, tc ? nullptr : e->t64,
-                    tc ? &e->t64s : nullptr))) return rc;
+  if (tc_fcs) {
+    if ((rc = tnet_fc_tc(e, s, e->gmax_fstn, S, 1))) return rc;
+  } else if ((rc = tnet_fc(e, s, e->gmax_fstn, S, "pcl_net.fstn", e->fstn_fc3_wT, e->fstn_fc3_bI, 4096, tc ? nullptr : e->t64,
+                           tc ? &e->t64s : nullptr))) return rc;
 
   // ---- E4: feature transform pf = h1 . T64 (per set), trunk conv2-4, global max (pointnet.py:105-116)
   if (tc) {
@@ -456,8 +500,11 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   // ---- R1: rotation heads (heads/conv_out_per_rot_head.py:62-71,126-140) with the layer-0 split:
   //      layers.0 . [g_set | pf_p] = W0[:, :1024] . g_set (once per set) + W0[:, 1024:] . pf_p
   {
-    if ((rc = run_fc<A_KEY>(e, s, G_ROT_GFEAT, reinterpret_cast<const float*>(e->gmax_g), 1024, e->rot_w0g, 1024, e->rot_b0, S, 512,
-                            1024, 0, e->cset, nullptr))) return rc;
+    if (tc_fcs) {  // cset = W0g . g_set + b0 on the tensor cores (fp32 copy is what the consumers read; fc1o is a scratch sink)
+      if ((rc = tc_keys_split(e, s, G_ROT_GFEAT, e->gmax_g, S, e->g16))) return rc;
+      if ((rc = tc_fc(e, s, G_ROT_GFEAT, e->g16, e->tw_rot_w0g, S, 512, 1024, e->rot_b0, 0, e->fc1o, e->cset))) return rc;
+    } else if ((rc = run_fc<A_KEY>(e, s, G_ROT_GFEAT, reinterpret_cast<const float*>(e->gmax_g), 1024, e->rot_w0g, 1024, e->rot_b0, S, 512,
+                                   1024, 0, e->cset, nullptr))) return rc;
   }
   float* gn0_scale = e->gn0;
   float* gn0_shift = e->gn0 + (size_t)e->maxB * 1024;
@@ -637,12 +684,23 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
     };
     pair(e->x64, 64); pair(e->f64, 64); pair(e->a128, 128); pair(e->pf16, 64); pair(e->a512, 512);
     if (!rc && !tc_make_map_f16(&e->a1t_map, e->a1, B * 512, P, 64, 128)) rc |= 2;
+    const size_t Spad = (S + 127) / 128 * 128;
     if (!rc) {  // T64^T per set, the N-side operand of the feature transform: [S*64, 64], 64-row boxes
-      rc |= dalloc(e, &e->t64s.hi, S * 4096);
-      rc |= dalloc(e, &e->t64s.lo, S * 4096);
+      rc |= dalloc(e, &e->t64s.hi, Spad * 4096);
+      rc |= dalloc(e, &e->t64s.lo, Spad * 4096);
       if (!rc && (!tc_make_map(&e->t64s.map_hi, e->t64s.hi, S * 64, 64, 64, 64) ||
                   !tc_make_map(&e->t64s.map_lo, e->t64s.lo, S * 64, 64, 64, 64))) rc |= 2;
+      e->t64s_out.hi = e->t64s.hi; e->t64s_out.lo = e->t64s.lo;
+      if (!rc && (!tc_make_map(&e->t64s_out.map_hi, e->t64s.hi, Spad, 4096, 4096, 128) ||
+                  !tc_make_map(&e->t64s_out.map_lo, e->t64s.lo, Spad, 4096, 4096, 128))) rc |= 2;
     }
+    auto pair_rows = [&](TcPair& t, size_t rows, size_t cols) {
+      rc |= dalloc(e, &t.hi, rows * cols);
+      rc |= dalloc(e, &t.lo, rows * cols);
+      if (rc) return;
+      if (!tc_make_map(&t.map_hi, t.hi, rows, cols, cols, 128) || !tc_make_map(&t.map_lo, t.lo, rows, cols, cols, 128)) rc |= 2;
+    };
+    if (!rc) { pair_rows(e->g16, Spad, 1024); pair_rows(e->fc1o, Spad, 512); pair_rows(e->fc2o, Spad, 256); }
     if (!rc) {
       bool ok = true;
       ok &= tc_make_map(&e->a128_nb[0], e->a128.hi, R, 128, 128, 256) && tc_make_map(&e->a128_nb[1], e->a128.lo, R, 128, 128, 256);
@@ -713,14 +771,16 @@ int catre_pack(catre_engine* e, void* stream) {
   for (int i = 0; i < kNumWeights; ++i) up(&e->dw[kWeights[i].name], e->hw[kWeights[i].name]);
   auto H = [&](const char* n) -> const std::vector<float>& { return e->hw.at(n); };
 
-  std::vector<float> v;
+  std::vector<float> v, fstn_fc3_wT_host;
   v = H("pcl_net.stn.fc3.bias");  // + I3 (pointnet.py:37-40)
   for (int i = 0; i < 3; ++i) v[i * 3 + i] += 1.0f;
   up(&e->stn_fc3_bI, v);
   {  // fstn.fc3 with output rows permuted (i*64+j -> j*64+i) so the FC emits T64^T, + I64 (pointnet.py:72-77)
     const std::vector<float>& w3 = H("pcl_net.fstn.fc3.weight");
     const std::vector<float>& b3 = H("pcl_net.fstn.fc3.bias");
-    std::vector<float> wT(w3.size()), bT(b3.size());
+    std::vector<float>& wT = fstn_fc3_wT_host;
+    wT.resize(w3.size());
+    std::vector<float> bT(b3.size());
     for (int i = 0; i < 64; ++i)
       for (int j = 0; j < 64; ++j) {
         memcpy(&wT[(size_t)(j * 64 + i) * 256], &w3[(size_t)(i * 64 + j) * 256], 256 * sizeof(float));
@@ -798,6 +858,12 @@ int catre_pack(catre_engine* e, void* stream) {
     r2 = r2 ? r2 : wpair(e->tw_conv3, H("pcl_net.conv3.weight"), 512, 128, 128);
     r2 = r2 ? r2 : wpair(e->tw_conv4, H("pcl_net.conv4.weight"), 1024, 512, 128);
     r2 = r2 ? r2 : wpair(e->tw_rot0, w0p, 512, 64, 128);
+    r2 = r2 ? r2 : wpair(e->tw_fc1[0], H("pcl_net.stn.fc1.weight"), 512, 1024, 64);
+    r2 = r2 ? r2 : wpair(e->tw_fc1[1], H("pcl_net.fstn.fc1.weight"), 512, 1024, 64);
+    r2 = r2 ? r2 : wpair(e->tw_fc2[0], H("pcl_net.stn.fc2.weight"), 256, 512, 64);
+    r2 = r2 ? r2 : wpair(e->tw_fc2[1], H("pcl_net.fstn.fc2.weight"), 256, 512, 64);
+    r2 = r2 ? r2 : wpair(e->tw_fstn_fc3, fstn_fc3_wT_host, 4096, 256, 64);
+    r2 = r2 ? r2 : wpair(e->tw_rot_w0g, w0g, 512, 1024, 64);
     if (!r2 && (!tc_make_map(&e->tw_rot0_nb[0], e->tw_rot0.hi, 512, 64, 64, 256) ||
                 !tc_make_map(&e->tw_rot0_nb[1], e->tw_rot0.lo, 512, 64, 64, 256)))
       r2 = fail(e, CATRE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the rot layer-0 N-side view");

@@ -541,6 +541,27 @@ __global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(NT) fc_clust
   cluster.sync();  // no CTA may exit while its shared memory is still being read by the others
 }
 
+// ordered-int max keys [n] -> bf16 hi/lo split of the float values (operand of the tensor-core FC layers)
+__global__ void keys_split_kernel(const int* __restrict__ keys, unsigned short* __restrict__ out_hi,
+                                  unsigned short* __restrict__ out_lo, long long n4) {
+  pdl_wait();
+  long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int4 k = *reinterpret_cast<const int4*>(keys + i * 4);
+  const float f[4] = {key2f(k.x), key2f(k.y), key2f(k.z), key2f(k.w)};
+  unsigned short h[4], l[4];
+#pragma unroll
+  for (int j = 0; j < 4; ++j) {  // round-to-nearest-even bf16 of f and of the residual
+    const unsigned int u = __float_as_uint(f[j]);
+    const unsigned int hr = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;
+    const unsigned int ul = __float_as_uint(f[j] - __uint_as_float(hr));
+    h[j] = (unsigned short)(hr >> 16);
+    l[j] = (unsigned short)((ul + 0x7fffu + ((ul >> 16) & 1u)) >> 16);
+  }
+  *reinterpret_cast<uint2*>(out_hi + i * 4) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
+  *reinterpret_cast<uint2*>(out_lo + i * 4) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
+}
+
 // Tensor-core modes: GroupNorm statistics of rot layer 0 -> per (SET, channel) affine applied to the raw
 // MMA accumulator D = W0p . pf (the per-set constant cset = W0g . g_set + b0 is folded into the shift):
 //   gelu_in = (D + cset) * sc + sh  =  D * sc + (cset * sc + sh)

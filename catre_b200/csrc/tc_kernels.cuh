@@ -38,7 +38,9 @@ enum { CH_ON_LANES = 0, PT_ON_LANES = 1 };
 //   EPI_STATS           CH_ON_LANES   GroupNorm partial sums of D + rowvec[set] only (nothing stored)
 //   EPI_SPLIT           PT_ON_LANES   act(D + bias) -> bf16 hi/lo [R, C] (operand of the next layer), TMA-stored
 //   EPI_SPLIT_MAX       PT_ON_LANES   D -> bf16 hi/lo, and column max over the tile's points -> atomicMax keys
-enum { EPI_MAX = 0, EPI_SPLIT = 2, EPI_STATS = 3, EPI_SPLIT_MAX = 5 };
+//   EPI_SPLIT_STREAM    PT_ON_LANES   as EPI_SPLIT (+ optional fp32 copy) but with the weights streamed, not resident:
+//                                     the small-M FC layers of the T-Nets, whose K is up to 1024
+enum { EPI_MAX = 0, EPI_SPLIT = 2, EPI_STATS = 3, EPI_SPLIT_MAX = 5, EPI_SPLIT_STREAM = 6 };
 
 // ------------------------------------------------------------------------------------------------
 // PTX wrappers
@@ -228,6 +230,7 @@ struct TcGemmP {
   int* gmax; int C;                             // EPI_MAX / EPI_SPLIT_MAX: keys [S, C]
   const float* rowvec; int ldrv;                // EPI_STATS: per-set additive vector [S, ldrv]
   float* stats; int stats_ld, stats_goff;       // EPI_STATS: GroupNorm partials [R/(BN/2), stats_ld, 2]
+  float* out32; int ldo32; int rows32;          // EPI_SPLIT_STREAM: optional fp32 copy [rows32, ldo32]
 };
 
 template <int ORIENT, int BN, int NPROD>
@@ -311,7 +314,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
-  if (p.bias) {  // per-channel bias of the whole layer staged once
+  if (p.bias && EPI != EPI_SPLIT_STREAM) {  // per-channel bias of the whole layer staged once (FC layers read it directly)
     const int nbias = (ORIENT == CH_ON_LANES) ? p.m_tiles * 128 : p.n_tiles * BN;
     for (int i = threadIdx.x; i < nbias; i += TC_THREADS) s_bias[i] = p.bias[i];
   }
@@ -461,13 +464,24 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
 #pragma unroll
           for (int j = 0; j < 32; j += 4) {
             float4 b4 = make_float4(0.f, 0.f, 0.f, 0.f);
-            if (p.bias) b4 = *reinterpret_cast<const float4*>(s_bias + ni * BN + n0 + j);  // broadcast LDS.128
+            if (p.bias) {
+              if (EPI == EPI_SPLIT_STREAM) b4 = __ldg(reinterpret_cast<const float4*>(p.bias + ni * BN + n0 + j));  // up to 4096 channels
+              else b4 = *reinterpret_cast<const float4*>(s_bias + ni * BN + n0 + j);  // broadcast LDS.128
+            }
             x[j + 0] = v[j + 0] + b4.x; x[j + 1] = v[j + 1] + b4.y;
             x[j + 2] = v[j + 2] + b4.z; x[j + 3] = v[j + 3] + b4.w;
           }
           if (p.relu) {
 #pragma unroll
             for (int j = 0; j < 32; ++j) x[j] = fmaxf(x[j], 0.f);
+          }
+          if (EPI == EPI_SPLIT_STREAM && p.out32 != nullptr) {
+            const int grow = mi * 128 + lane_row;
+            if (grow < p.rows32) {
+              float4* o4 = reinterpret_cast<float4*>(p.out32 + (long long)grow * p.ldo32 + ni * BN + n0);
+#pragma unroll
+              for (int j = 0; j < 8; ++j) o4[j] = make_float4(x[4 * j], x[4 * j + 1], x[4 * j + 2], x[4 * j + 3]);
+            }
           }
         }
         uint32_t hi[16], lo[16];

@@ -202,3 +202,20 @@ def test_bf16_single_product_mode(weights):
     e_r, e_t, e_s = gu.max_abs_err(poses, scales, case.poses, case.scales)
     assert e_r <= 2e-2 and e_t <= 5e-3 and e_s <= 5e-3, (e_r, e_t, e_s)
     assert e_r > 0  # and it really is a different arithmetic from the parity mode
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_oracle_parity_large_batch(weights, prec):
+    """B = 128 objects (256 sets): from two 128-row tiles of sets on, the tensor-core modes run the T-Net FC
+    chain and the rot g-feature layer on the tensor cores instead of the split-K cluster kernels."""
+    n, B, K = 256, 128, 2
+    b = synth.make_batch(B, n, seed=51)
+    w = catre_oracle.resize_conv_p(weights, n)
+    ref_p, ref_s = catre_oracle.refine(w, b.pcl, b.prior, b.init_pose, b.init_scale, b.K, K)
+    eng = get_engine(weights, n, prec, max_batch=B)
+    poses, scales = run_refine(eng, b, K)
+    e = gu.max_abs_err(poses, scales, ref_p, ref_s)
+    assert max(e) <= TOL, e
+    # chunked execution through a smaller engine (64 objects per chunk -> the cluster-kernel FC path) agrees
+    p2, s2 = run_refine(get_engine(weights, n, prec, max_batch=64), b, K)
+    assert (p2 - poses).abs().max() <= TOL and (s2 - scales).abs().max() <= TOL
