@@ -378,6 +378,21 @@ struct EncFusedP {
   int* gmax;             // [S][1024] ordered-int keys
 };
 
+// Work units of a CTA: unit k = global unit blockIdx.x + k * gridDim.x.  Full rounds are whole items (all 8
+// channel tiles of a 256-point tile); when the last round would be at most half full, its items are split
+// into two half-units of 4 channel tiles each (the cheap 64->128 layer is recomputed) so the tail spreads
+// over twice as many CTAs: 512 items on 148 CTAs take 3 + ~0.55 rounds instead of 4.
+struct EncUnit { int item, mt0, mtn; };
+__device__ __forceinline__ bool enc_unit(int k, int items, EncUnit& u) {
+  const int G = (int)gridDim.x, g = (int)blockIdx.x + k * G;
+  const int full = (items / G) * G, rem = items - full;
+  const bool split = rem > 0 && 2 * rem <= G;
+  if (g < full || !split) { u.item = g; u.mt0 = 0; u.mtn = 8; return g < items; }
+  const int v = g - full;
+  u.item = full + (v >> 1); u.mt0 = (v & 1) * 4; u.mtn = 4;
+  return v < 2 * rem;
+}
+
 template <int NPROD>
 __global__ void __launch_bounds__(RF_THREADS, 1)
 enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant__ CUtensorMap x_lo,
@@ -429,11 +444,12 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
         else tma_load_2d(sb + 16384, lo, c0, c1, full);
         if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; }
       };
-      for (int it = blockIdx.x; it < p.tiles; it += gridDim.x) {
-        load2(&x_hi, &x_lo, 0, it * 256);
-        load2(&x_hi, &x_lo, 0, it * 256 + 128);
+      EncUnit un;
+      for (int k = 0; enc_unit(k, p.tiles, un); ++k) {
+        load2(&x_hi, &x_lo, 0, un.item * 256);
+        load2(&x_hi, &x_lo, 0, un.item * 256 + 128);
         load2(&w2_hi, &w2_lo, 0, 0);
-        for (int mt = 0; mt < 8; ++mt)
+        for (int mt = un.mt0; mt < un.mt0 + un.mtn; ++mt)
           for (int ks = 0; ks < 2; ++ks) load2(&w3_hi, &w3_lo, ks * 64, mt * 128);
       }
     }
@@ -446,8 +462,9 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
       auto next = [&]() { if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; } };
       uint32_t it_phase = 0;         // per-item barriers (d0_full, u_full)
       uint32_t use[2] = {0, 0};      // uses of each D1 buffer so far (parity of its full / empty barriers)
-      for (int it = blockIdx.x; it < p.tiles; it += gridDim.x) {
-        // ---- L0 into columns 0..255 (= D1 buffer 1): wait until its last reader (epi1 of the previous mt 7) is done
+      EncUnit un;
+      for (int k = 0; enc_unit(k, p.tiles, un); ++k) {
+        // ---- L0 into columns 0..255 (= D1 buffer 1): wait until its last reader (epi1 of the previous unit's last odd tile) is done
         mbar_wait(bar_d1_empty + 8 * 1, (use[1] & 1) ^ 1);
         tc_fence_after();
         const int sx0 = slot; mbar_wait(bar_full + 8 * slot, phase); next();
@@ -476,7 +493,7 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
           umma_commit(bar_d0_full);
         }
         // ---- L1: 8 channel tiles; even mt -> buffer 0 (columns 256..511), odd mt -> buffer 1 (columns 0..255)
-        for (int mt = 0; mt < 8; ++mt) {
+        for (int mt = 0; mt < un.mtn; ++mt) {  // mt = index within the unit; channel tile un.mt0 + mt
           const int buf = mt & 1;
           if (mt != 1) {  // mt 1 is the first writer of buffer 1 after L0: covered by the wait above + u_full
             mbar_wait(bar_d1_empty + 8 * buf, (use[buf] & 1) ^ 1);
@@ -513,8 +530,9 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
     const int lane_row = quad * 32 + lane;
     uint32_t it_phase = 0;
     uint32_t use[2] = {0, 0};
-    for (int it = blockIdx.x; it < p.tiles; it += gridDim.x) {
-      const int set = (int)(((long long)it * 256) / p.rows_per_set);
+    EncUnit un;
+    for (int k = 0; enc_unit(k, p.tiles, un); ++k) {
+      const int set = (int)(((long long)un.item * 256) / p.rows_per_set);
       // ---- epi0: lane = point row of sub-tile `sub`; this warp's 16 channels of slab ks
       mbar_wait(bar_d0_full, it_phase);
       tc_fence_after();
@@ -553,7 +571,7 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
         if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
       }
       // ---- epi1: lane = output channel of tile mt; this warp's 64 of the 256 points
-      for (int mt = 0; mt < 8; ++mt) {
+      for (int mt = 0; mt < un.mtn; ++mt) {
         const int buf = mt & 1;
         mbar_wait(bar_d1_full + 8 * buf, use[buf] & 1);
         tc_fence_after();
@@ -571,7 +589,7 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
         __syncwarp();
         if (lane == 0) mbar_arrive(bar_d1_empty + 8 * buf);
         use[buf]++;
-        const int ch = mt * 128 + lane_row;
+        const int ch = (un.mt0 + mt) * 128 + lane_row;
         m = fmaxf(m + __ldg(p.bias3 + ch), 0.f);
         atomicMax(p.gmax + (long long)set * 1024 + ch, f2key(m));
       }
