@@ -967,11 +967,16 @@ int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, con
     rc = catre_refine(e, e->st_pcl, e->st_prior, e->st_pose, e->st_scale, e->st_K, Bc, n_iter, e->st_oposes, e->st_oscales, s);
     if (rc) return rc;
     launches += e->launches;
-    for (int it = 0; it <= n_iter; ++it) {
-      CU_TRY(e, cudaMemcpyAsync(out_poses + ((size_t)it * B + b0) * 12, e->st_oposes + (size_t)it * Bc * 12,
-                                (size_t)Bc * 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
-      CU_TRY(e, cudaMemcpyAsync(out_scales + ((size_t)it * B + b0) * 3, e->st_oscales + (size_t)it * Bc * 3,
-                                (size_t)Bc * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    if (Bc == B) {  // single chunk: the staging layout [n_iter+1, B, .] is the output layout
+      CU_TRY(e, cudaMemcpyAsync(out_poses, e->st_oposes, (size_t)(n_iter + 1) * B * 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+      CU_TRY(e, cudaMemcpyAsync(out_scales, e->st_oscales, (size_t)(n_iter + 1) * B * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+    } else {
+      for (int it = 0; it <= n_iter; ++it) {
+        CU_TRY(e, cudaMemcpyAsync(out_poses + ((size_t)it * B + b0) * 12, e->st_oposes + (size_t)it * Bc * 12,
+                                  (size_t)Bc * 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
+        CU_TRY(e, cudaMemcpyAsync(out_scales + ((size_t)it * B + b0) * 3, e->st_oscales + (size_t)it * Bc * 3,
+                                  (size_t)Bc * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
+      }
     }
   }
   CU_TRY(e, cudaStreamSynchronize(s));
