@@ -127,6 +127,8 @@ struct catre_engine {
   // staging for catre_refine_host
   float *st_pcl = nullptr, *st_prior = nullptr, *st_pose = nullptr, *st_scale = nullptr, *st_K = nullptr;
   float *st_oposes = nullptr, *st_oscales = nullptr;
+  int32_t* st_cls = nullptr;
+  int st_prior_rows = 0;  // rows ([N,3] each) st_prior holds: max(max_batch, 16), so a small class table always fits
   static constexpr int kMaxHostIter = 16;
 
   // ---- accounting
@@ -375,7 +377,7 @@ int tnet_fc_tc(catre_engine* e, cudaStream_t s, const int* keys, int S, int whic
 
 // One refinement iteration on a chunk of B objects whose points are already in e->q.
 int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, const float* scale_in, const float* K,
-              float* pose_out, float* scale_out) {
+              float* pose_out, float* scale_out, const int* prior_cls = nullptr, int n_cls = 0) {
   const int N = e->N, S = 2 * B, P = 2 * N;
   const long long R = (long long)S * N;
   int rc;
@@ -485,6 +487,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     tsp.ws = W(e, "ts_head.fc_s.weight"); tsp.bs = W(e, "ts_head.fc_s.bias");
     tsp.rot_partial = e->rot_partial; tsp.rot_tiles = tc ? 16 : P / 128; tsp.convp_bias = e->convp_b;
     tsp.pose_in = pose_in; tsp.scale_in = scale_in; tsp.K = K; tsp.pose_out = pose_out; tsp.scale_out = scale_out;
+    tsp.cls = prior_cls; tsp.n_cls = n_cls;
     CU_TRY(e, cudaEventRecord(e->ev_fork, s));
     CU_TRY(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
     if ((rc = run_fc<A_KEY>(e, e->side, G_TS_POSE, reinterpret_cast<const float*>(e->gmax_g), 2048, e->ts_w0g, 1024,
@@ -665,7 +668,9 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   rc |= dalloc(e, &e->gn1, B * 512 * 2);
   rc |= dalloc(e, &e->rot_partial, B * (P / 128 > 16 ? P / 128 : 16) * 6);
   rc |= dalloc(e, &e->st_pcl, B * N * 3);
-  rc |= dalloc(e, &e->st_prior, B * N * 3);
+  e->st_prior_rows = e->maxB > 16 ? e->maxB : 16;
+  rc |= dalloc(e, &e->st_prior, (size_t)e->st_prior_rows * N * 3);
+  rc |= dalloc(e, &e->st_cls, B);
   rc |= dalloc(e, &e->st_pose, B * 12);
   rc |= dalloc(e, &e->st_scale, B * 3);
   rc |= dalloc(e, &e->st_K, B * 9);
@@ -912,8 +917,10 @@ int catre_forward_once(catre_engine* e, const float* x_pm, const float* kps_pm, 
   return CATRE_OK;
 }
 
-int catre_refine(catre_engine* e, const float* pcl, const float* prior, const float* init_pose, const float* init_scale,
-                 const float* K, int32_t B, int32_t n_iter, float* out_poses, float* out_scales, void* stream) {
+// prior_cls == nullptr: `prior` is [B, N, 3]; otherwise `prior` is the table [n_cls, N, 3] indexed by prior_cls[b]
+static int refine_impl(catre_engine* e, const float* pcl, const float* prior, const int32_t* prior_cls, int32_t n_cls,
+                       const float* init_pose, const float* init_scale, const float* K, int32_t B, int32_t n_iter,
+                       float* out_poses, float* out_scales, void* stream) {
   int rc = check_ready(e, B);
   if (rc) return rc;
   if (n_iter < 0) return fail(e, CATRE_ERR_INVALID_ARG, "negative n_iter %d", n_iter);
@@ -928,6 +935,7 @@ int catre_refine(catre_engine* e, const float* pcl, const float* prior, const fl
   for (int b0 = 0; b0 < B; b0 += e->maxB) {
     int Bc = (B - b0 < e->maxB) ? B - b0 : e->maxB;
     long long total = (long long)Bc * 2 * N;
+    const int* pc_chunk = prior_cls ? (const int*)prior_cls + b0 : (const int*)nullptr;
     for (int it = 1; it <= n_iter; ++it) {
       const float* pin = out_poses + ((size_t)(it - 1) * B + b0) * 12;
       const float* sin = out_scales + ((size_t)(it - 1) * B + b0) * 3;
@@ -935,18 +943,32 @@ int catre_refine(catre_engine* e, const float* pcl, const float* prior, const fl
       float* sout = out_scales + ((size_t)it * B + b0) * 3;
       {
         Launch l(e, s, G_UPDATE_POINTS);
-        launch_pdl(update_points_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, pcl + (size_t)b0 * N * 3, prior + (size_t)b0 * N * 3,
-                   pin, sin, e->q, Bc, N, e->gmax_all, (long long)(2 * Bc) * (1024 * 3 + 64));
+        const float* pr = prior_cls ? prior : prior + (size_t)b0 * N * 3;
+        launch_pdl(update_points_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, pcl + (size_t)b0 * N * 3, pr,
+                   pin, sin, e->q, Bc, N, e->gmax_all, (long long)(2 * Bc) * (1024 * 3 + 64), pc_chunk, (int)n_cls);
       }
       if ((rc = check_launch(e, "update_points"))) return rc;
-      if ((rc = iteration(e, s, Bc, pin, sin, K + (size_t)b0 * 9, pout, sout))) return rc;
+      if ((rc = iteration(e, s, Bc, pin, sin, K + (size_t)b0 * 9, pout, sout, pc_chunk, (int)n_cls))) return rc;
     }
   }
   return CATRE_OK;
 }
 
-int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, const float* init_pose, const float* init_scale,
-                      const float* K, int32_t B, int32_t n_iter, float* out_poses, float* out_scales, void* stream) {
+int catre_refine(catre_engine* e, const float* pcl, const float* prior, const float* init_pose, const float* init_scale,
+                 const float* K, int32_t B, int32_t n_iter, float* out_poses, float* out_scales, void* stream) {
+  return refine_impl(e, pcl, prior, nullptr, 0, init_pose, init_scale, K, B, n_iter, out_poses, out_scales, stream);
+}
+
+int catre_refine_table(catre_engine* e, const float* pcl, const float* prior_table, const int32_t* prior_cls, int32_t n_cls,
+                       const float* init_pose, const float* init_scale, const float* K, int32_t B, int32_t n_iter,
+                       float* out_poses, float* out_scales, void* stream) {
+  if (e && (n_cls < 1 || (!prior_cls && B > 0))) return fail(e, CATRE_ERR_INVALID_ARG, "prior table needs n_cls >= 1 and class ids");
+  return refine_impl(e, pcl, prior_table, prior_cls, n_cls, init_pose, init_scale, K, B, n_iter, out_poses, out_scales, stream);
+}
+
+static int refine_host_impl(catre_engine* e, const float* pcl, const float* prior, const int32_t* prior_cls, int32_t n_cls,
+                            const float* init_pose, const float* init_scale, const float* K, int32_t B, int32_t n_iter,
+                            float* out_poses, float* out_scales, void* stream) {
   int rc = check_ready(e, B);
   if (rc) return rc;
   if (n_iter < 0 || n_iter > catre_engine::kMaxHostIter)
@@ -957,14 +979,24 @@ int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, con
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   const int N = e->N;
   int64_t launches = 0;
+  if (prior_cls) {  // the table travels once per call, the class ids per chunk
+    if (n_cls < 1 || n_cls > e->st_prior_rows)
+      return fail(e, CATRE_ERR_INVALID_ARG, "n_cls %d outside [1, %d] for the host entry", n_cls, e->st_prior_rows);
+    for (int b = 0; b < B; ++b)
+      if (prior_cls[b] < 0 || prior_cls[b] >= n_cls)
+        return fail(e, CATRE_ERR_INVALID_ARG, "prior_cls[%d] = %d outside [0, %d)", b, prior_cls[b], n_cls);
+    CU_TRY(e, cudaMemcpyAsync(e->st_prior, prior, (size_t)n_cls * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+  }
   for (int b0 = 0; b0 < B; b0 += e->maxB) {
     int Bc = (B - b0 < e->maxB) ? B - b0 : e->maxB;
     CU_TRY(e, cudaMemcpyAsync(e->st_pcl, pcl + (size_t)b0 * N * 3, (size_t)Bc * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
-    CU_TRY(e, cudaMemcpyAsync(e->st_prior, prior + (size_t)b0 * N * 3, (size_t)Bc * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    if (prior_cls) CU_TRY(e, cudaMemcpyAsync(e->st_cls, prior_cls + b0, (size_t)Bc * sizeof(int32_t), cudaMemcpyHostToDevice, s));
+    else CU_TRY(e, cudaMemcpyAsync(e->st_prior, prior + (size_t)b0 * N * 3, (size_t)Bc * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     CU_TRY(e, cudaMemcpyAsync(e->st_pose, init_pose + (size_t)b0 * 12, (size_t)Bc * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     CU_TRY(e, cudaMemcpyAsync(e->st_scale, init_scale + (size_t)b0 * 3, (size_t)Bc * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     CU_TRY(e, cudaMemcpyAsync(e->st_K, K + (size_t)b0 * 9, (size_t)Bc * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
-    rc = catre_refine(e, e->st_pcl, e->st_prior, e->st_pose, e->st_scale, e->st_K, Bc, n_iter, e->st_oposes, e->st_oscales, s);
+    rc = refine_impl(e, e->st_pcl, e->st_prior, prior_cls ? e->st_cls : nullptr, n_cls, e->st_pose, e->st_scale, e->st_K, Bc, n_iter,
+                     e->st_oposes, e->st_oscales, s);
     if (rc) return rc;
     launches += e->launches;
     if (Bc == B) {  // single chunk: the staging layout [n_iter+1, B, .] is the output layout
@@ -982,6 +1014,18 @@ int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, con
   CU_TRY(e, cudaStreamSynchronize(s));
   e->launches = launches;
   return CATRE_OK;
+}
+
+int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, const float* init_pose, const float* init_scale,
+                      const float* K, int32_t B, int32_t n_iter, float* out_poses, float* out_scales, void* stream) {
+  return refine_host_impl(e, pcl, prior, nullptr, 0, init_pose, init_scale, K, B, n_iter, out_poses, out_scales, stream);
+}
+
+int catre_refine_table_host(catre_engine* e, const float* pcl, const float* prior_table, const int32_t* prior_cls, int32_t n_cls,
+                            const float* init_pose, const float* init_scale, const float* K, int32_t B, int32_t n_iter,
+                            float* out_poses, float* out_scales, void* stream) {
+  if (e && (n_cls < 1 || (!prior_cls && B > 0))) return fail(e, CATRE_ERR_INVALID_ARG, "prior table needs n_cls >= 1 and class ids");
+  return refine_host_impl(e, pcl, prior_table, prior_cls, n_cls, init_pose, init_scale, K, B, n_iter, out_poses, out_scales, stream);
 }
 
 int64_t catre_last_launch_count(const catre_engine* e) { return e ? e->launches : 0; }

@@ -68,9 +68,13 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // q layout: set 2b = observed points of object b, set 2b+1 = prior points; [2B, N, 3] point-major.
 // ----------------------------------------------------------------------------------------------
 // Both point kernels also reset the iteration's column-max keys (gmax, n_keys ints) to -inf.
+// cls == nullptr: prior is [B, N, 3] (one prior per object).  Otherwise prior is a table [n_cls, N, 3] and
+// object b uses row cls[b] (batch["obj_kps"] = the category's mean shape, engine_utils.py:17-24); a class id
+// outside [0, n_cls) reads row 0 here and pose_update_kernel overwrites that object's result with NaN.
 __global__ void update_points_kernel(const float* __restrict__ pcl, const float* __restrict__ prior,
                                      const float* __restrict__ pose, const float* __restrict__ scale,
-                                     float* __restrict__ q, int B, int N, int* __restrict__ gmax, long long n_keys) {
+                                     float* __restrict__ q, int B, int N, int* __restrict__ gmax, long long n_keys,
+                                     const int* __restrict__ cls, int n_cls) {
   pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   long long total = (long long)B * 2 * N;
@@ -86,7 +90,12 @@ __global__ void update_points_kernel(const float* __restrict__ pcl, const float*
     o1 = p[1] - P[7];
     o2 = p[2] - P[11];
   } else {
-    const float* p = prior + ((long long)b * N + (r - N)) * 3;
+    int row = b;
+    if (cls != nullptr) {
+      row = cls[b];
+      if (row < 0 || row >= n_cls) row = 0;
+    }
+    const float* p = prior + ((long long)row * N + (r - N)) * 3;
     const float* s = scale + (long long)b * 3;
     float k0 = p[0] * s[0], k1 = p[1] * s[1], k2 = p[2] * s[2];
     o0 = P[0] * k0 + P[1] * k1 + P[2] * k2;
@@ -782,6 +791,7 @@ struct TsPoseP {
   const float* pose_in; const float* scale_in; const float* K;
   float* pose_out; float* scale_out;
   float* dts;           // [B, 6] raw head outputs (dt 3 | ds 3): written by ts_head, read by pose_update
+  const int* cls; int n_cls;  // prior-table entries: an object whose class id is outside [0, n_cls) gets a NaN pose
 };
 
 __device__ __forceinline__ float gn8_gelu(float v, float gamma, float beta) {
@@ -910,6 +920,11 @@ __global__ void __launch_bounds__(256) pose_update_kernel(TsPoseP p, int B) {
     So[0] = sc_in[0] + outv[3];
     So[1] = sc_in[1] + outv[4];
     So[2] = sc_in[2] + outv[5];
+    if (p.cls != nullptr && (p.cls[b] < 0 || p.cls[b] >= p.n_cls)) {  // bad class id: make it visible, not plausible
+      const float qnan = __int_as_float(0x7fc00000);
+      for (int i = 0; i < 12; ++i) Pout[i] = qnan;
+      So[0] = So[1] = So[2] = qnan;
+    }
   }
 }
 

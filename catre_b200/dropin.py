@@ -212,6 +212,14 @@ class CatreB200(nn.Module):
         eng = self.engine(pcl.device)
         return eng.refine(pcl.float(), prior.float(), init_pose.float(), init_scale.float(), K.float(), n_iter)
 
+    @torch.no_grad()
+    def refine_table(self, pcl, prior_table, obj_cls, init_pose, init_scale, K, n_iter: int = 4):
+        """refine() with the priors as a category table [C,N_p,3] and batch["obj_cls"] [B] (any integer
+        dtype): object b uses prior_table[obj_cls[b]] (core/catre/engine/engine_utils.py:17-24)."""
+        eng = self.engine(pcl.device)
+        return eng.refine_table(pcl.float(), prior_table.float(), obj_cls.to(torch.int32), init_pose.float(),
+                                init_scale.float(), K.float(), n_iter)
+
     def refine_as_out_dict(self, pcl, prior, init_pose, init_scale, K, n_iter: int = 4) -> Dict[str, torch.Tensor]:
         """The evaluator's out_dict for all iterations: {pose_0.., scale_0..} (catre_evaluator.py:292-311)."""
         poses, scales = self.refine(pcl, prior, init_pose, init_scale, K, n_iter)

@@ -37,6 +37,8 @@ SYMBOLS = {
     "catre_forward_once": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, _F, _F, _P]),
     "catre_refine": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
     "catre_refine_host": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
+    "catre_refine_table": (ctypes.c_int, [_P, _F, _F, _F, ctypes.c_int32, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
+    "catre_refine_table_host": (ctypes.c_int, [_P, _F, _F, _F, ctypes.c_int32, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
     "catre_last_launch_count": (ctypes.c_int64, [_P]),
     "catre_debug_read": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_size_t]),
     "catre_profile_enable": (ctypes.c_int, [_P, ctypes.c_int32]),
@@ -193,6 +195,48 @@ class Engine:
             poses, scales = out
         self._check(self.lib.catre_refine_host(self._h, _ptr(pcl), _ptr(prior), _ptr(init_pose), _ptr(init_scale), _ptr(K),
                                                B, n_iter, _ptr(poses), _ptr(scales), self._stream()), "catre_refine_host")
+        return poses, scales
+
+    def refine_table(self, pcl, prior_table, prior_cls, init_pose, init_scale, K, n_iter: int, out=None):
+        """catre_refine with a category table: prior_table [C,N,3] fp32, prior_cls [B] int32 (object b uses
+        prior_table[prior_cls[b]]).  Device tensors; an out-of-range class id yields a NaN pose for that object."""
+        B, N = pcl.shape[0], self.n_pts
+        C = prior_table.shape[0]
+        pcl = self._dev(pcl, (B, N, 3), "pcl")
+        prior_table = self._dev(prior_table, (C, N, 3), "prior_table")
+        if not prior_cls.is_cuda or prior_cls.dtype != torch.int32 or tuple(prior_cls.shape) != (B,):
+            raise CatreError(f"prior_cls must be a CUDA int32 tensor of shape ({B},)")
+        prior_cls = prior_cls.contiguous()
+        init_pose = self._dev(init_pose, (B, 3, 4), "init_pose")
+        init_scale = self._dev(init_scale, (B, 3), "init_scale")
+        K = self._dev(K, (B, 3, 3), "K")
+        if out is None:
+            poses = torch.empty((n_iter + 1, B, 3, 4), dtype=torch.float32, device=pcl.device)
+            scales = torch.empty((n_iter + 1, B, 3), dtype=torch.float32, device=pcl.device)
+        else:
+            poses, scales = out
+        self._check(self.lib.catre_refine_table(self._h, _ptr(pcl), _ptr(prior_table), _ptr(prior_cls), C, _ptr(init_pose),
+                                                _ptr(init_scale), _ptr(K), B, n_iter, _ptr(poses), _ptr(scales),
+                                                self._stream()), "catre_refine_table")
+        return poses, scales
+
+    def refine_table_host(self, pcl, prior_table, prior_cls, init_pose, init_scale, K, n_iter: int, out=None):
+        """Host-buffer form of refine_table (class ids are validated on the host)."""
+        B, N = pcl.shape[0], self.n_pts
+        C = prior_table.shape[0]
+        for name, t, shp, dt in (("pcl", pcl, (B, N, 3), torch.float32), ("prior_table", prior_table, (C, N, 3), torch.float32),
+                                 ("prior_cls", prior_cls, (B,), torch.int32), ("init_pose", init_pose, (B, 3, 4), torch.float32),
+                                 ("init_scale", init_scale, (B, 3), torch.float32), ("K", K, (B, 3, 3), torch.float32)):
+            if t.is_cuda or t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous():
+                raise CatreError(f"{name}: expected contiguous {dt} host tensor of shape {shp}")
+        if out is None:
+            poses = torch.empty((n_iter + 1, B, 3, 4), dtype=torch.float32).pin_memory()
+            scales = torch.empty((n_iter + 1, B, 3), dtype=torch.float32).pin_memory()
+        else:
+            poses, scales = out
+        self._check(self.lib.catre_refine_table_host(self._h, _ptr(pcl), _ptr(prior_table), _ptr(prior_cls), C,
+                                                     _ptr(init_pose), _ptr(init_scale), _ptr(K), B, n_iter, _ptr(poses),
+                                                     _ptr(scales), self._stream()), "catre_refine_table_host")
         return poses, scales
 
     # ---- accounting ------------------------------------------------------------------------------

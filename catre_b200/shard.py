@@ -52,3 +52,40 @@ def gather_poses(poses: torch.Tensor, scales: torch.Tensor, total: int,
     dist.all_gather_into_tensor(out, local, group=group)
     full = out.reshape(world, k1, per, 15).permute(1, 0, 2, 3).reshape(k1, world * per, 15)[:, :total].contiguous()
     return unpack_poses(full)
+
+
+def world_size() -> int:
+    return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
+
+
+def rank() -> int:
+    return dist.get_rank() if dist.is_available() and dist.is_initialized() else 0
+
+
+def gather_rows(rows: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """All-gather a ragged set of rows: rank r holds [n_r, D]; every rank gets [sum n_r, D] in rank order.
+    One size exchange + one padded ``all_gather_into_tensor`` (the tensor replacement for the reference's
+    pickled ``all_gather(self._predictions)``, core/catre/engine/catre_evaluator.py:172-177)."""
+    if world_size() == 1:
+        return rows
+    world = dist.get_world_size(group)
+    n = torch.tensor([rows.shape[0]], dtype=torch.int64, device=rows.device)
+    sizes = torch.empty(world, dtype=torch.int64, device=rows.device)
+    dist.all_gather_into_tensor(sizes, n, group=group)
+    sizes = sizes.tolist()
+    per = max(max(sizes), 1)
+    d = rows.shape[1]
+    local = rows.new_zeros((per, d))
+    local[: rows.shape[0]] = rows
+    out = rows.new_empty((world * per, d))
+    dist.all_gather_into_tensor(out, local.contiguous(), group=group)
+    return torch.cat([out[r * per: r * per + sizes[r]] for r in range(world)], dim=0)
+
+
+def gather_vocab(words, group: Optional[dist.ProcessGroup] = None):
+    """Union (rank order, first occurrence first) of each rank's small list of strings (scene ids)."""
+    if world_size() == 1:
+        return list(dict.fromkeys(words))
+    lists = [None] * dist.get_world_size(group)
+    dist.all_gather_object(lists, list(dict.fromkeys(words)), group=group)
+    return list(dict.fromkeys(w for l in lists for w in l))

@@ -107,6 +107,21 @@ int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, con
                       const float* init_scale, const float* K, int32_t B, int32_t n_iter, float* out_poses,
                       float* out_scales, void* stream);
 
+/* catre_refine with the priors given as a category table instead of one copy per object: object b uses
+ * prior_table[prior_cls[b]].  Replaces the same K-loop; the table is what get_normed_kps builds once per
+ * dataset (core/catre/engine/engine_utils.py:17-24: batch["obj_kps"] = the category's mean shape from
+ * cr_normed_mean_model_points_spd.pkl, selected by batch["obj_cls"]), so a caller need not expand it to
+ * [B, n_prior, 3] (halves the input bytes of the path).
+ *   prior_table [n_cls, n_prior, 3] fp32, prior_cls [B] int32 in [0, n_cls).
+ * Device entry: an out-of-range class id cannot be reported without a host sync; that object's pose comes
+ * back NaN.  Host entry: class ids are validated (CATRE_ERR_INVALID_ARG) and n_cls <= max(max_batch, 16). */
+int catre_refine_table(catre_engine* e, const float* pcl, const float* prior_table, const int32_t* prior_cls,
+                       int32_t n_cls, const float* init_pose, const float* init_scale, const float* K, int32_t B,
+                       int32_t n_iter, float* out_poses, float* out_scales, void* stream);
+int catre_refine_table_host(catre_engine* e, const float* pcl, const float* prior_table, const int32_t* prior_cls,
+                            int32_t n_cls, const float* init_pose, const float* init_scale, const float* K,
+                            int32_t B, int32_t n_iter, float* out_poses, float* out_scales, void* stream);
+
 /* Number of kernels the last forward/refine call launched (bench.py's `gpu_launches`). */
 int64_t catre_last_launch_count(const catre_engine* e);
 

@@ -219,3 +219,55 @@ def test_oracle_parity_large_batch(weights, prec):
     # chunked execution through a smaller engine (64 objects per chunk -> the cluster-kernel FC path) agrees
     p2, s2 = run_refine(get_engine(weights, n, prec, max_batch=64), b, K)
     assert (p2 - poses).abs().max() <= TOL and (s2 - scales).abs().max() <= TOL
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_refine_table_mixed_categories(weights, prec):
+    """BASELINE.json config 5 (mixed 6-category batch, per-category prior shapes) through the category-table
+    entry: prior_table [6,N,3] + class ids must give the same BYTES as the expanded [B,N,3] priors, and match
+    the reference golden of the mixed case; host entry == device entry."""
+    case = gu.load_case("c5s_b12_n1024_k4_mixed")
+    b = case.batch
+    table = synth.resample_prior(synth.load_fixtures().priors, case.n_pts).float().contiguous()  # [6, N, 3]
+    assert torch.equal(table[b.obj_cls], b.prior)
+    eng = get_engine(weights, case.n_pts, prec)
+    p_ref, s_ref = run_refine(eng, b, case.n_iter)
+    d = b.to("cuda")
+    cls32 = d.obj_cls.to(torch.int32)
+    p, s = eng.refine_table(d.pcl, table.cuda(), cls32, d.init_pose, d.init_scale, d.K, case.n_iter)
+    torch.cuda.synchronize()
+    assert torch.equal(p.cpu(), p_ref) and torch.equal(s.cpu(), s_ref)
+    e = gu.max_abs_err(p, s, case.poses, case.scales)
+    assert max(e) <= TOL, e
+    ph, sh = eng.refine_table_host(b.pcl.pin_memory(), table.pin_memory(), b.obj_cls.to(torch.int32), b.init_pose,
+                                   b.init_scale, b.K, case.n_iter)
+    assert torch.equal(ph, p_ref) and torch.equal(sh, s_ref)
+    # chunked (max_batch 5 -> 3 chunks, class ids offset per chunk)
+    eng5 = get_engine(weights, case.n_pts, prec, max_batch=5)
+    p5, s5 = eng5.refine_table(d.pcl, table.cuda(), cls32, d.init_pose, d.init_scale, d.K, case.n_iter)
+    torch.cuda.synchronize()
+    assert torch.equal(p5.cpu(), p_ref) and torch.equal(s5.cpu(), s_ref)
+    ph5, sh5 = eng5.refine_table_host(b.pcl, table, b.obj_cls.to(torch.int32), b.init_pose, b.init_scale, b.K, case.n_iter)
+    assert torch.equal(ph5, p_ref) and torch.equal(sh5, s_ref)
+
+
+def test_refine_table_bad_class_ids(weights):
+    eng = get_engine(weights, 1024, "fp32")
+    b = synth.make_batch(3, 1024, seed=7)
+    table = synth.load_fixtures().priors.float().contiguous()
+    cls = b.obj_cls.to(torch.int32).clone()
+    good_p, good_s = eng.refine_table_host(b.pcl, table, cls, b.init_pose, b.init_scale, b.K, 1)
+    good_p, good_s = good_p.clone(), good_s.clone()
+    cls[1] = 6
+    with pytest.raises(engine.CatreError):  # host entry validates
+        eng.refine_table_host(b.pcl, table, cls, b.init_pose, b.init_scale, b.K, 1)
+    d = b.to("cuda")
+    # device entry: no host sync, so the bad object comes back NaN and the others are untouched
+    p, s = eng.refine_table(d.pcl, table.cuda(), cls.cuda(), d.init_pose, d.init_scale, d.K, 1)
+    torch.cuda.synchronize()
+    p, s = p.cpu(), s.cpu()
+    assert torch.isnan(p[1, 1, :, :3]).any()
+    assert torch.equal(p[1, 0], good_p[1, 0]) and torch.equal(p[1, 2], good_p[1, 2])
+    assert torch.equal(s[1, 0], good_s[1, 0]) and torch.equal(s[1, 2], good_s[1, 2])
+    with pytest.raises(engine.CatreError):
+        eng.refine_table(d.pcl, table.cuda(), cls.cuda().long(), d.init_pose, d.init_scale, d.K, 1)  # dtype
