@@ -145,7 +145,7 @@ def main():
     ap.add_argument("--batch", type=int, default=64, help="objects per GPU per step (BASELINE configs[1])")
     ap.add_argument("--n-pts", type=int, default=1024)
     ap.add_argument("--n-iter", type=int, default=4)
-    ap.add_argument("--precision", default="bf16x3", choices=["fp32", "bf16x3", "bf16"])
+    ap.add_argument("--precision", default="f16x3", choices=["fp32", "f16x3", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=16, help="objects in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -290,14 +290,14 @@ def main():
         pts_per_launch = 2 * B * N / max(1.0, launches_per_step_top / K)
         fl = LAYER_FLOPS_PER_POINT[top] * pts_per_launch
         ach = fl / (ms_launch * 1e-3) / 1e12
-        nprod = {"bf16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
+        nprod = {"f16x3": 3, "bf16": 1, "fp32": 1}[args.precision]
         roofline = {"bound": "tensor", "kernel": top, "achieved": ach, "peak": peaks["bf16_tflops"], "unit": "TFLOP/s",
                     "frac": ach / peaks["bf16_tflops"], "traffic": ncu_traffic(top, B), "peak_source": peaks["source"],
                     "ms_per_launch": ms_launch, "share_of_step": cand[top][0] / tot if tot else None,
                     "mma_products_per_mac": nprod, "issued_mma_tflops": ach * nprod,
                     "issued_mma_frac_of_peak": ach * nprod / peaks["bf16_tflops"],
                     "note": "achieved = algorithmic FLOPs (one fp32-equivalent product per MAC) / CUDA-event time; "
-                            f"the {args.precision} mode issues {nprod} bf16 MMA product(s) per MAC"
+                            f"the {args.precision} mode issues {nprod} 16-bit (kind::f16) MMA product(s) per MAC; fp16 and bf16 MMAs share one peak"
                             + (" on CUDA cores (no tensor pipe)" if args.precision == "fp32" else ""),
                     "whole_step_tflops": flops_per_object_iter(N, N) * B * K / (ms_per_step * 1e-3) / 1e12,
                     "profile_ms_per_step": {k: round(v[0] / args.steps, 4) for k, v in
@@ -315,7 +315,7 @@ def main():
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": {"fp32": "f32", "bf16x3": "bf16x3->f32 (3 bf16 tcgen05 products per MAC, fp32 accumulate)",
+            "dtype": {"fp32": "f32", "f16x3": "f16x3->f32 (operands split into fp16 hi+lo, 3 tcgen05 kind::f16 products per MAC, fp32 accumulate)",
                       "bf16": "bf16 (fp32 accumulate)"}[args.precision],
             "data": "synthetic (seeded, SURVEY.md 8(d)); weights = the reference's shipped checkpoint",
             "config": {"workload": workload, "batch_per_gpu": B, "global_batch": total_B, "n_pts": N, "n_iter": K,

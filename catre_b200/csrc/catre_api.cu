@@ -114,7 +114,6 @@ struct catre_engine {
   float *q = nullptr, *h64a = nullptr, *h64b = nullptr, *h128 = nullptr, *h512 = nullptr, *a0 = nullptr, *a1 = nullptr;
   int *gmax_all = nullptr, *gmax_stn = nullptr, *gmax_fstn = nullptr, *gmax_g = nullptr, *gmax_pf = nullptr;
   float *fc512 = nullptr, *fc256 = nullptr, *ts0 = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
-  CUtensorMap a1t_map;  // fp16 a1T [maxB*512, P] for the fused rot kernel's TMA stores (64-point x 128-channel boxes)
   // tensor-core FC path of the T-Nets / rot g-feature: operands [Spad, K] (Spad = S rounded up to 128 rows)
   TcPair g16, fc1o, fc2o, t64s_out;  // t64s_out: the t64s memory viewed as [Spad, 4096] for the FC's TMA stores
   TcPair tw_fc1[2], tw_fc2[2], tw_fstn_fc3, tw_rot_w0g;  // [0] = stn, [1] = fstn
@@ -302,7 +301,7 @@ int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv,
   std::string c(conv);
   {
     Launch l(e, s, G_FRONT3);
-    launch_pdl(front3_split_kernel, dim3((unsigned)((R + FRONT_PTS - 1) / FRONT_PTS)), dim3(256), (size_t)(0), s, e->q, t3, e->dw.at(c + ".weight"), e->dw.at(c + ".bias"),
+    launch_pdl(e->cfg.precision == CATRE_PREC_F16X3 ? front3_split_kernel<true> : front3_split_kernel<false>, dim3((unsigned)((R + FRONT_PTS - 1) / FRONT_PTS)), dim3(256), (size_t)(0), s, e->q, t3, e->dw.at(c + ".weight"), e->dw.at(c + ".bias"),
                                                                  e->x64.hi, e->x64.lo, (int)R, e->N);
   }
   return check_launch(e, "front3_split");
@@ -316,6 +315,7 @@ int run_fc(catre_engine* e, cudaStream_t s, int grp, const float* A, int lda, co
   p.A = A; p.lda = lda; p.W = Wt; p.ldw = ldw; p.bias = bias; p.out32 = out32;
   p.out_hi = out16 ? reinterpret_cast<unsigned short*>(out16->hi) : nullptr;
   p.out_lo = out16 ? reinterpret_cast<unsigned short*>(out16->lo) : nullptr;
+  p.out_f16 = e->cfg.precision == CATRE_PREC_F16X3;
   p.R = R; p.C = C; p.K = K; p.relu = relu;
   {
     Launch l(e, s, grp);
@@ -343,13 +343,14 @@ int tnet_fc(catre_engine* e, cudaStream_t s, const int* keys, int S, const char*
 }
 
 // ---- tensor-core small-M FC layers (tensor-core modes): out[S, C] = act(in[S, K] . W[C, K]^T + b) with the
-//      sets on the TMEM lanes (one or a few 128-row tiles), weights streamed, bf16x3 like every wide layer
+//      sets on the TMEM lanes (one or a few 128-row tiles), weights streamed, f16x3 (or bf16) like every wide layer
 int tc_keys_split(catre_engine* e, cudaStream_t s, int grp, const int* keys, int S, const TcPair& out) {
   const long long n4 = (long long)S * 1024 / 4;
   {
     Launch l(e, s, grp);
     launch_pdl(keys_split_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), (size_t)0, s, keys,
-               reinterpret_cast<unsigned short*>(out.hi), reinterpret_cast<unsigned short*>(out.lo), n4);
+               reinterpret_cast<unsigned short*>(out.hi), reinterpret_cast<unsigned short*>(out.lo), n4,
+               (int)(e->cfg.precision == CATRE_PREC_F16X3));
   }
   return check_launch(e, "keys_split");
 }
@@ -528,16 +529,16 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
       // layer-0 recompute + GroupNorm + GELU + bf16 split into shared memory + layer 1, one kernel
       RotFusedP pf{};
       pf.tiles = (int)(R / 128); pf.rows_per_set = N; pf.rows_per_obj = P;
-      pf.gn_scale = gn0_scale; pf.gn_shift = gn0_shift; pf.bias1 = e->rot_b1; pf.stats = e->stats1;
+      pf.gn_scale = gn0_scale; pf.gn_shift = gn0_shift; pf.bias1 = e->rot_b1; pf.stats = e->stats1; pf.a1t = e->a1;
       cudaError_t st;
       {
         Launch l(e, s, G_ROT_FUSED);
         if (e->cfg.precision == CATRE_PREC_BF16)
           st = rot_fused_launch<1>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
-                                   e->tw_rot1s.map_lo, e->a1t_map, pf, e->num_sms, s);
+                                   e->tw_rot1s.map_lo, pf, e->num_sms, s);
         else
           st = rot_fused_launch<3>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
-                                   e->tw_rot1s.map_lo, e->a1t_map, pf, e->num_sms, s);
+                                   e->tw_rot1s.map_lo, pf, e->num_sms, s);
       }
       if (st != cudaSuccess) {
         cudaGetLastError();
@@ -573,7 +574,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   {
     Launch l(e, s, G_ROT_TAIL);
     if (tc)  // finalises the GroupNorm-1 statistics itself (partials per 64 points from the fused rot kernel)
-      launch_pdl(rot_tail_t_kernel, dim3(16, B), dim3(256), (size_t)(P * sizeof(float)), s, reinterpret_cast<const __half*>(e->a1),
+      launch_pdl(rot_tail_t_kernel, dim3(16, B), dim3(256), (size_t)(P * sizeof(float)), s, e->a1,
                  e->stats1, e->rot_gn1_g, e->rot_gn1_b, P / 64, e->neck_w, e->neck_b, e->wp, e->rot_partial, P);
     else
       launch_pdl(rot_tail_kernel, dim3(P / 128, B), dim3(256), (size_t)(0), s, e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
@@ -602,7 +603,7 @@ int check_ready(catre_engine* e, int B) {
 // ================================================================================================
 extern "C" {
 
-const char* catre_version(void) { return "catre_b200 0.2 sm_100a (fp32 SIMT + tcgen05 bf16x3)"; }
+const char* catre_version(void) { return "catre_b200 0.2 sm_100a (fp32 SIMT + tcgen05 f16x3 | bf16)"; }
 int32_t catre_num_weights(void) { return kNumWeights; }
 const char* catre_weight_name(int32_t i) { return (i >= 0 && i < kNumWeights) ? kWeights[i].name : nullptr; }
 int32_t catre_profile_num(void) { return G_NUM; }
@@ -650,7 +651,7 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
     rc |= dalloc(e, &e->a0, R * 512);
     rc |= dalloc(e, &e->t64, S * 4096);
   }
-  rc |= dalloc(e, &e->a1, tc ? R * 256 : R * 512);  // tensor-core modes: fp16 a1T [B][512][P]
+  rc |= dalloc(e, &e->a1, R * 512);  // fp32 mode: a1 [R][512]; tensor-core modes: a1T [B][P/4][512][4], fp32 as well
   rc |= dalloc(e, &e->gmax_all, S * (1024 * 3 + 64));
   e->gmax_stn = e->gmax_all;
   e->gmax_fstn = e->gmax_all + S * 1024;
@@ -688,7 +689,6 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
       if (!tc_make_map(&t.map_hi, t.hi, R, cols, cols, 128) || !tc_make_map(&t.map_lo, t.lo, R, cols, cols, 128)) rc |= 2;
     };
     pair(e->x64, 64); pair(e->f64, 64); pair(e->a128, 128); pair(e->pf16, 64); pair(e->a512, 512);
-    if (!rc && !tc_make_map_f16(&e->a1t_map, e->a1, B * 512, P, 64, 128)) rc |= 2;
     const size_t Spad = (S + 127) / 128 * 128;
     if (!rc) {  // T64^T per set, the N-side operand of the feature transform: [S*64, 64], 64-row boxes
       rc |= dalloc(e, &e->t64s.hi, Spad * 4096);
@@ -839,10 +839,18 @@ int catre_pack(catre_engine* e, void* stream) {
   if (e->cfg.precision != CATRE_PREC_FP32_SIMT) {
     // bf16 hi/lo split of the wide layers' weights [C, K] + tensor maps (box rows = how the layer uses W)
     auto wpair = [&](TcPair& t, const std::vector<float>& w, int C, int K, int box_rows) -> int {
-      std::vector<__nv_bfloat16> hi((size_t)C * K), lo((size_t)C * K);
+      std::vector<__nv_bfloat16> hi((size_t)C * K), lo((size_t)C * K);  // 16-bit storage; fp16 patterns in the f16x3 mode
+      const bool f16 = e->cfg.precision == CATRE_PREC_F16X3;
       for (size_t i = 0; i < hi.size(); ++i) {
-        hi[i] = __float2bfloat16_rn(w[i]);
-        lo[i] = __float2bfloat16_rn(w[i] - __bfloat162float(hi[i]));
+        if (f16) {
+          const __half h = __float2half_rn(w[i]);
+          const __half l = __float2half_rn(w[i] - __half2float(h));
+          hi[i] = __ushort_as_bfloat16(__half_as_ushort(h));
+          lo[i] = __ushort_as_bfloat16(__half_as_ushort(l));
+        } else {
+          hi[i] = __float2bfloat16_rn(w[i]);
+          lo[i] = __float2bfloat16_rn(w[i] - __bfloat162float(hi[i]));
+        }
       }
       if (!t.hi) {
         if (dalloc(e, &t.hi, hi.size()) || dalloc(e, &t.lo, lo.size())) return CATRE_ERR_CUDA;

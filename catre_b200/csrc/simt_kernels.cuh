@@ -3,6 +3,7 @@
 // the reference lines it restates.  Written for sm_100a; no library calls.
 #pragma once
 #include <cooperative_groups.h>
+#include <cuda_bf16.h>
 #include <cuda_fp16.h>
 #include <cuda_runtime.h>
 #include <stdint.h>
@@ -28,6 +29,21 @@ inline cudaError_t launch_pdl(void (*kern)(KArgs...), dim3 grid, dim3 block, siz
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = 1;
   return cudaLaunchKernelEx(&cfg, kern, static_cast<KArgs>(args)...);
+}
+
+// 16-bit hi / residual split of an fp32 value for the tensor-core operands (see TcOperand in tc_kernels.cuh):
+// fp16 pair in the 3-product mode, bf16 pair otherwise.
+__device__ __forceinline__ void split16(float x, bool f16, unsigned short& hi, unsigned short& lo) {
+  if (f16) {
+    const float xs = fminf(fmaxf(x, -65504.0f), 65504.0f);
+    const __half h = __float2half_rn(xs);
+    hi = __half_as_ushort(h);
+    lo = __half_as_ushort(__float2half_rn(x - __half2float(h)));
+  } else {
+    const __nv_bfloat16 h = __float2bfloat16_rn(x);
+    hi = __bfloat16_as_ushort(h);
+    lo = __bfloat16_as_ushort(__float2bfloat16_rn(x - __bfloat162float(h)));
+  }
 }
 
 // order-preserving float <-> int key, so a column max over points can use atomicMax(int)
@@ -414,7 +430,8 @@ struct FcP {
   const float* W; int ldw;      // [C, K]
   const float* bias;            // [C] or null
   float* out32;                 // [R, C] or null
-  unsigned short* out_hi; unsigned short* out_lo;  // bf16 hi/lo of the result [R, C], or null
+  unsigned short* out_hi; unsigned short* out_lo;  // 16-bit hi/lo split of the result [R, C], or null
+  int out_f16;                                     // split type: 1 = fp16 pair, 0 = bf16 pair
   int R, C, K;                  // K multiple of 16 * FC_KSPLIT
   int relu;
 };
@@ -537,22 +554,16 @@ __global__ void __cluster_dims__(1, 1, FC_KSPLIT) __launch_bounds__(NT) fc_clust
           if (p.relu) y = fmaxf(y, 0.f);
           const long long o = (long long)gr * p.C + gc + j;
           if (p.out32) p.out32[o] = y;
-          if (p.out_hi) {  // round-to-nearest-even bf16 of y and of the residual
-            const unsigned int u = __float_as_uint(y);
-            const unsigned int hr = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;
-            const unsigned int ul = __float_as_uint(y - __uint_as_float(hr));
-            p.out_hi[o] = (unsigned short)(hr >> 16);
-            p.out_lo[o] = (unsigned short)((ul + 0x7fffu + ((ul >> 16) & 1u)) >> 16);
-          }
+          if (p.out_hi) split16(y, p.out_f16 != 0, p.out_hi[o], p.out_lo[o]);
         }
     }
   }
   cluster.sync();  // no CTA may exit while its shared memory is still being read by the others
 }
 
-// ordered-int max keys [n] -> bf16 hi/lo split of the float values (operand of the tensor-core FC layers)
+// ordered-int max keys [n] -> 16-bit hi/lo split of the float values (operand of the tensor-core FC layers)
 __global__ void keys_split_kernel(const int* __restrict__ keys, unsigned short* __restrict__ out_hi,
-                                  unsigned short* __restrict__ out_lo, long long n4) {
+                                  unsigned short* __restrict__ out_lo, long long n4, int f16) {
   pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
   if (i >= n4) return;
@@ -560,13 +571,7 @@ __global__ void keys_split_kernel(const int* __restrict__ keys, unsigned short* 
   const float f[4] = {key2f(k.x), key2f(k.y), key2f(k.z), key2f(k.w)};
   unsigned short h[4], l[4];
 #pragma unroll
-  for (int j = 0; j < 4; ++j) {  // round-to-nearest-even bf16 of f and of the residual
-    const unsigned int u = __float_as_uint(f[j]);
-    const unsigned int hr = (u + 0x7fffu + ((u >> 16) & 1u)) & 0xffff0000u;
-    const unsigned int ul = __float_as_uint(f[j] - __uint_as_float(hr));
-    h[j] = (unsigned short)(hr >> 16);
-    l[j] = (unsigned short)((ul + 0x7fffu + ((ul >> 16) & 1u)) >> 16);
-  }
+  for (int j = 0; j < 4; ++j) split16(f[j], f16 != 0, h[j], l[j]);
   *reinterpret_cast<uint2*>(out_hi + i * 4) = make_uint2(h[0] | ((unsigned)h[1] << 16), h[2] | ((unsigned)h[3] << 16));
   *reinterpret_cast<uint2*>(out_lo + i * 4) = make_uint2(l[0] | ((unsigned)l[1] << 16), l[2] | ((unsigned)l[3] << 16));
 }
@@ -678,13 +683,15 @@ __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__
   }
 }
 
-// Tensor-core modes keep the rot layer-1 output channel-major and in fp16, a1T [B][512][P] (written by the
-// fused rot kernel's TMA stores).  One warp per channel: lanes stride over the
-// points, S_c = sum_p wp[p] gelu(a1T[c][p] sc_c + sh_c), and the neck is applied to S_c (linearity, see
-// above).  Block = 32 channels of one head of one object; partial[b][blockIdx.x][6] (other head's 3 = 0).
-// The GroupNorm-1 statistics are finalised here as well (fp64 sum of the block's 4 groups x tiles_per_obj
-// partials written by the fused rot kernel), so no separate finalize launch is needed.
-__global__ void __launch_bounds__(256) rot_tail_t_kernel(const __half* __restrict__ a1t, const float* __restrict__ stats /*[R/64][64][2]*/,
+// Tensor-core modes keep the rot layer-1 output in fp32 as a1T [B][P/4][512][4]: groups of 4 consecutive points,
+// channel-major inside a group, so that the fused rot kernel (lane = channel, 64 points per thread) and this
+// kernel (lane = channel too) both move 512 contiguous bytes per warp instruction.  Block = 32 channels
+// (one per lane) of one head of one object, the 8 warps split the P points;  S_c = sum_p wp[p] gelu(a1[c][p] sc_c
+// + sh_c) is accumulated per lane and the neck is applied to S_c (linearity, see above);
+// partial[b][blockIdx.x][6] (other head's 3 = 0).  The GroupNorm-1 statistics are finalised here as well (fp64
+// sum of the block's 4 groups x tiles_per_obj partials written by the fused rot kernel), so no separate finalize
+// launch is needed.
+__global__ void __launch_bounds__(256) rot_tail_t_kernel(const float* __restrict__ a1t, const float* __restrict__ stats /*[R/64][64][2]*/,
                                                          const float* __restrict__ gamma, const float* __restrict__ beta /*[512]*/,
                                                          int tiles_per_obj,
                                                          const float* __restrict__ neck_w /*[2][3][256]*/,
@@ -721,36 +728,30 @@ __global__ void __launch_bounds__(256) rot_tail_t_kernel(const __half* __restric
     }
   }
   __syncthreads();
-  float r0 = 0.f, r1 = 0.f, r2 = 0.f;
-#pragma unroll 1
-  for (int cc = 0; cc < 4; ++cc) {
-    const int c = cg * 32 + warp * 4 + cc;  // channel in [0, 512)
-    const float sc = s_sc[warp * 4 + cc], sh = s_sh[warp * 4 + cc];
-    const uint4* row = reinterpret_cast<const uint4*>(a1t + ((long long)b * 512 + c) * P);  // 8 points per load
-    float acc = 0.f;
-#pragma unroll 2
-    for (int i = lane; i < P / 8; i += 32) {
-      const uint4 v = __ldg(row + i);
-      const float4 w0 = reinterpret_cast<const float4*>(s_wp)[2 * i], w1 = reinterpret_cast<const float4*>(s_wp)[2 * i + 1];
-      const float2 f0 = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
-      const float2 f1 = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
-      const float2 f2 = __half22float2(*reinterpret_cast<const __half2*>(&v.z));
-      const float2 f3 = __half22float2(*reinterpret_cast<const __half2*>(&v.w));
-      acc = fmaf(w0.x, gelu_fast(fmaf(f0.x, sc, sh)), acc);
-      acc = fmaf(w0.y, gelu_fast(fmaf(f0.y, sc, sh)), acc);
-      acc = fmaf(w0.z, gelu_fast(fmaf(f1.x, sc, sh)), acc);
-      acc = fmaf(w0.w, gelu_fast(fmaf(f1.y, sc, sh)), acc);
-      acc = fmaf(w1.x, gelu_fast(fmaf(f2.x, sc, sh)), acc);
-      acc = fmaf(w1.y, gelu_fast(fmaf(f2.y, sc, sh)), acc);
-      acc = fmaf(w1.z, gelu_fast(fmaf(f3.x, sc, sh)), acc);
-      acc = fmaf(w1.w, gelu_fast(fmaf(f3.y, sc, sh)), acc);
-    }
+  const int c = cg * 32 + lane;  // this lane's channel in [0, 512)
+  const float sc = s_sc[lane], sh = s_sh[lane];
+  const int quads = P / 4, per_warp = quads / 8;  // P is a multiple of 256
+  const float4* src = reinterpret_cast<const float4*>(a1t) + ((long long)b * quads + warp * per_warp) * 512 + c;
+  const float4* wq = reinterpret_cast<const float4*>(s_wp) + warp * per_warp;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < per_warp; ++i) {
+    const float4 f = __ldcs(src + (long long)i * 512);  // read once: streaming
+    const float4 w = wq[i];  // same address on every lane: shared-memory broadcast
+    acc = fmaf(w.x, gelu_fast(fmaf(f.x, sc, sh)), acc);
+    acc = fmaf(w.y, gelu_fast(fmaf(f.y, sc, sh)), acc);
+    acc = fmaf(w.z, gelu_fast(fmaf(f.z, sc, sh)), acc);
+    acc = fmaf(w.w, gelu_fast(fmaf(f.w, sc, sh)), acc);
+  }
+  const int cl = c & 255;
+  float r0 = neck_w[(h * 3 + 0) * 256 + cl] * acc;
+  float r1 = neck_w[(h * 3 + 1) * 256 + cl] * acc;
+  float r2 = neck_w[(h * 3 + 2) * 256 + cl] * acc;
 #pragma unroll
-    for (int o = 16; o > 0; o >>= 1) acc += __shfl_xor_sync(0xffffffffu, acc, o);
-    const int cl = c & 255;
-    r0 = fmaf(neck_w[(h * 3 + 0) * 256 + cl], acc, r0);
-    r1 = fmaf(neck_w[(h * 3 + 1) * 256 + cl], acc, r1);
-    r2 = fmaf(neck_w[(h * 3 + 2) * 256 + cl], acc, r2);
+  for (int o = 16; o > 0; o >>= 1) {
+    r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+    r2 += __shfl_xor_sync(0xffffffffu, r2, o);
   }
   if (lane == 0) { s_part[warp][0] = r0; s_part[warp][1] = r1; s_part[warp][2] = r2; }
   __syncthreads();

@@ -40,6 +40,7 @@ struct RotFusedP {
   const float* gn_shift; // [S][512]  shift with the per-set constant folded in
   const float* bias1;    // [512]     layers.3 bias, both heads
   float* stats;          // [R/64][64 groups][2]
+  float* a1t;            // [B][P/4][512][4] fp32: layer-1 output (+ bias) for the rot tail (see rot_tail_t_kernel)
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -63,15 +64,14 @@ __device__ __forceinline__ void tmem_ld_wait16(float* v) {
 // Schedule (software-pipelined over the CTA's work items j; half A = layer-0 channels 0..127 = U slabs 0-1,
 // half B = channels 128..255 = slabs 2-3; D0a / D0b = TMEM columns 0..127 / 128..255):
 //   MMA warp      L0(0,A) L0(0,B) | L1(j,A) L0(j+1,A) L1(j,B) L0(j+1,B) | ...
-//   epilogue      E0(0,s0..s3)    | E0(j+1,s0) E1(j) E0(j+1,s1) [store drain] E0(j+1,s2) E0(j+1,s3) | ...
+//   epilogue      E0(0,s0..s3)    | E0(j+1,s0) E1(j,0) E0(j+1,s1) E1(j,1) E0(j+1,s2) E0(j+1,s3) | ...
 // so the GELU work of item j+1 runs underneath the layer-1 MMAs of item j and the CUDA cores never wait for
-// the tensor pipe.  E1(j) stages its fp16 tile in slabs 2-3 (free between L1(j,B) and E0(j+1,s2)).
+// the tensor pipe.  E1(j, c) writes 32 of the item's 64 points per thread straight to global memory (fp32).
 template <int NPROD>
 __global__ void __launch_bounds__(RF_THREADS, 1)
 rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constant__ CUtensorMap pf_lo,
                  const __grid_constant__ CUtensorMap w0_hi, const __grid_constant__ CUtensorMap w0_lo,
-                 const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo,
-                 const __grid_constant__ CUtensorMap a1t_map, const RotFusedP p) {
+                 const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo, const RotFusedP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t u_base = (smem_base + 1024 + 1023) & ~1023u;  // barriers live in the first 1 KB
@@ -90,7 +90,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   auto item_ht = [&](int j) { return (int)blockIdx.x + j * (int)gridDim.x; };
 
   if (warp == 0 && lane == 0) {
-    prefetch_tmap(&pf_hi); prefetch_tmap(&w0_hi); prefetch_tmap(&w1_hi); prefetch_tmap(&a1t_map);
+    prefetch_tmap(&pf_hi); prefetch_tmap(&w0_hi); prefetch_tmap(&w1_hi);
     if (NPROD == 3) { prefetch_tmap(&pf_lo); prefetch_tmap(&w0_lo); prefetch_tmap(&w1_lo); }
     for (int i = 0; i < RF_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(bar_d0_full + 8 * i, 1); mbar_init(bar_d0_empty + 8 * i, RF_EW); }
@@ -139,7 +139,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0 && n_items > 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, 128);
+      constexpr uint32_t idesc = umma_idesc<TcOperand<NPROD>::F16>(128, 128);
       int slot = 0; uint32_t phase = 0;
       auto next = [&]() { if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; } };
       // L0(j, half): D0[half] = pf . W0p_h[half*128 ..]^T   (K = 64: 4 k-steps, N = 128)
@@ -242,8 +242,8 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
         const float g1 = gelu_fast(fmaf(v[4 * q + 1], sc4[q].y, sh4[q].y));
         const float g2 = gelu_fast(fmaf(v[4 * q + 2], sc4[q].z, sh4[q].z));
         const float g3 = gelu_fast(fmaf(v[4 * q + 3], sc4[q].w, sh4[q].w));
-        split_bf16x2(g0, g1, hi[2 * q], lo[2 * q]);
-        split_bf16x2(g2, g3, hi[2 * q + 1], lo[2 * q + 1]);
+        split16x2<TcOperand<NPROD>::F16>(g0, g1, hi[2 * q], lo[2 * q]);
+        split16x2<TcOperand<NPROD>::F16>(g2, g3, hi[2 * q + 1], lo[2 * q + 1]);
       }
       // two 16-byte chunks (8 channels each) of this row, 128B-swizzled: chunk' = chunk ^ (row & 7)
       const uint32_t slab = u_base + ks * 32768 + row_off;
@@ -258,53 +258,47 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
       __syncwarp();
       if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
     };
-    // E1(j): lane = output channel of m-tile mt; this warp's 64 points; fp16 tile staged in slabs 2-3
-    auto E1 = [&](int j) {
+    // E1(j): lane = output channel of m-tile mt; this warp's 64 points.  The fp32 values (+ bias) go straight from
+    // the registers to a1T [B][P/4][512][4]: 4 consecutive points of a channel are one 16-byte store, and the 32
+    // lanes (consecutive channels) of a warp write 512 contiguous bytes per instruction.  Keeping this activation
+    // in fp32 matters for parity: rounding it to fp16 was the largest single error of the tensor-core path
+    // (up to 3e-5 on R).
+    // Split in two halves of 32 points (E1(j, 0) and E1(j, 1)) that the schedule below places between E0 slabs,
+    // so each 64 KB burst of stores drains underneath the next slab's GELU work.
+    float e1_s = 0.f, e1_ss = 0.f;
+    auto E1 = [&](int j, int c) {
       const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
       const long long row0 = (long long)tile * 128;
-      mbar_wait(bar_d1_full, (uint32_t)j & 1);
-      tc_fence_after();
+      if (c == 0) {
+        mbar_wait(bar_d1_full, (uint32_t)j & 1);
+        tc_fence_after();
+        e1_s = 0.f; e1_ss = 0.f;
+      }
       const int mt = part >> 1, ph = part & 1;
       const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
       const long long r64 = row0 + ph * 64;          // first global row of this warp's 64 points
-      const long long obj = r64 / p.rows_per_obj;
       const float add = p.bias1[ch];
       const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128 + ph * 64);
-      const uint32_t sw = (uint32_t)(lane_row & 7);
-      // box (mt, ph): [128 ch rows x 64 pts fp16 = 128 B], chunk' = chunk ^ (row & 7)
-      const uint32_t box = u_base + 65536 + (uint32_t)((mt * 2 + ph) * 16384);
-      const uint32_t brow = box + (uint32_t)lane_row * 128;
-      float s = 0.f, ss = 0.f;
-#pragma unroll
-      for (int c = 0; c < 2; ++c) {
-        float x[32];
-        tmem_ld32(taddr + c * 32, x);
-        tmem_ld_wait32(x);
-        if (c == 1) {  // D1 drained: the next item's layer-1 MMAs may overwrite it
-          tc_fence_before();
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_d1_empty);
-        }
-        uint32_t hx[16];
-#pragma unroll
-        for (int q = 0; q < 32; q += 2) {
-          x[q] += add; x[q + 1] += add;
-          s += x[q]; s += x[q + 1];
-          ss = fmaf(x[q], x[q], ss); ss = fmaf(x[q + 1], x[q + 1], ss);
-          asm("cvt.rn.f16x2.f32 %0, %1, %2;" : "=r"(hx[q >> 1]) : "f"(x[q + 1]), "f"(x[q]));
-        }
-#pragma unroll
-        for (int q = 0; q < 4; ++q)
-          st_shared_v4(brow + (((uint32_t)(c * 4 + q) ^ sw) << 4), hx[4 * q], hx[4 * q + 1], hx[4 * q + 2], hx[4 * q + 3]);
+      float4* dst = reinterpret_cast<float4*>(p.a1t) + ((r64 >> 2) + c * 8) * 512 + ch;
+      float x[32];
+      tmem_ld32(taddr + c * 32, x);
+      tmem_ld_wait32(x);
+      if (c == 1) {  // D1 drained: the next item's layer-1 MMAs may overwrite it
+        tc_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(bar_d1_empty);
       }
-      fence_proxy_async_smem();
-      named_bar_sync(1 + part, 128);  // the four quadrant warps that share this (mt, ph)
-      if (quad == 0 && lane == 0) {
-        const int pl = (int)(r64 - obj * p.rows_per_obj);
-        const int crow = (int)(obj * 512) + h * 256 + mt * 128;
-        tma_store_2d(&a1t_map, box, pl, crow);
-        tma_store_commit();
+      float s = e1_s, ss = e1_ss;
+#pragma unroll
+      for (int q = 0; q < 32; q += 2) {
+        x[q] += add; x[q + 1] += add;
+        s += x[q]; s += x[q + 1];
+        ss = fmaf(x[q], x[q], ss); ss = fmaf(x[q + 1], x[q + 1], ss);
       }
+#pragma unroll
+      for (int q = 0; q < 8; ++q)  // streaming stores: a1T is read once, by the next kernel; keep the weights in L2
+        __stcs(dst + q * 512, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+      if (c == 0) { e1_s = s; e1_ss = ss; return; }
       s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
       s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
       s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
@@ -319,17 +313,12 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
       for (int j = 0; j < n_items; ++j) {
         const bool more = j + 1 < n_items;
         if (more) E0(j + 1, 0);
-        E1(j);
-        if (more) {
-          E0(j + 1, 1);
-          // E1(j)'s TMA stores read their source from slabs 2-3: they must be done before those are rewritten
-          if (quad == 0 && lane == 0) tma_store_wait_read();
-          named_bar_sync(5, 32 * RF_EW);
-          E0(j + 1, 2); E0(j + 1, 3);
-        }
+        E1(j, 0);
+        if (more) E0(j + 1, 1);
+        E1(j, 1);
+        if (more) { E0(j + 1, 2); E0(j + 1, 3); }
       }
     }
-    if (quad == 0 && lane == 0) tma_store_wait_all();
   }
   tc_fence_before();
   __syncthreads();
@@ -342,7 +331,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
 template <int NPROD>
 cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo, const CUtensorMap& w0_hi,
                              const CUtensorMap& w0_lo, const CUtensorMap& w1_hi, const CUtensorMap& w1_lo,
-                             const CUtensorMap& a1t_map, const RotFusedP& p, int num_sms, cudaStream_t s) {
+                             const RotFusedP& p, int num_sms, cudaStream_t s) {
   auto kern = rot_fused_kernel<NPROD>;
   static bool configured = false;
   if (!configured) {
@@ -353,7 +342,7 @@ cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo,
   int items = p.tiles * 2;
   int grid = items < num_sms ? items : num_sms;
   if (grid < 1) return cudaSuccess;
-  return launch_pdl(kern, dim3(grid), dim3(RF_THREADS), (size_t)RF_SMEM, s, pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, a1t_map, p);
+  return launch_pdl(kern, dim3(grid), dim3(RF_THREADS), (size_t)RF_SMEM, s, pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p);
 }
 
 
@@ -456,8 +445,8 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc0 = umma_idesc_bf16(128, 128);
-      constexpr uint32_t idesc1 = umma_idesc_bf16(128, 256);
+      constexpr uint32_t idesc0 = umma_idesc<TcOperand<NPROD>::F16>(128, 128);
+      constexpr uint32_t idesc1 = umma_idesc<TcOperand<NPROD>::F16>(128, 256);
       int slot = 0; uint32_t phase = 0;
       auto next = [&]() { if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; } };
       uint32_t it_phase = 0;         // per-item barriers (d0_full, u_full)
@@ -552,8 +541,8 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
           for (int j = 0; j < 4; ++j) {
             const float g0 = fmaxf(v[4 * j + 0] + b4[j].x, 0.f), g1 = fmaxf(v[4 * j + 1] + b4[j].y, 0.f);
             const float g2 = fmaxf(v[4 * j + 2] + b4[j].z, 0.f), g3 = fmaxf(v[4 * j + 3] + b4[j].w, 0.f);
-            split_bf16x2(g0, g1, hi[2 * j], lo[2 * j]);
-            split_bf16x2(g2, g3, hi[2 * j + 1], lo[2 * j + 1]);
+            split16x2<TcOperand<NPROD>::F16>(g0, g1, hi[2 * j], lo[2 * j]);
+            split16x2<TcOperand<NPROD>::F16>(g2, g3, hi[2 * j + 1], lo[2 * j + 1]);
           }
           const int row = sub * 128 + lane_row;  // row of the 256-row operand slab
           const uint32_t slab = u_base + ks * 65536 + (uint32_t)((row >> 3) * 1024 + (row & 7) * 128);

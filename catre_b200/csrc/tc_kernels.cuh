@@ -1,5 +1,5 @@
-// Tensor-core path (sm_100a): tcgen05.mma kind::f16 with bf16 hi/lo split operands ("bf16x3": three
-// products hi*hi + hi*lo + lo*hi accumulated in fp32 in TMEM), operands staged HBM/L2 -> shared memory by
+// Tensor-core path (sm_100a): tcgen05.mma kind::f16 with 16-bit hi/lo split operands ("f16x3": fp16 hi + fp16
+// residual, three products hi*hi + hi*lo + lo*hi accumulated in fp32 in TMEM; single-product mode: bf16), operands staged HBM/L2 -> shared memory by
 // TMA (cp.async.bulk.tensor, 128B swizzle), mbarrier producer/consumer pipeline, warp-specialised:
 //   warp 0 : TMA producer          warp 1 : TMEM allocator + MMA issuer (one elected thread)
 //   warps 2-5 : epilogue (tcgen05.ld -> registers -> fused bias/ReLU + column-max | GroupNorm partials |
@@ -172,21 +172,36 @@ __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t saddr) {
   d |= (uint64_t)2 << 61;
   return d;
 }
-// instruction descriptor kind::f16: D fp32 (bit 4), A/B bf16 (bits 7, 10), K-major both, N>>3 at 17, M>>4 at 24
-__host__ __device__ constexpr uint32_t umma_idesc_bf16(int M, int N) {
-  return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+// The 16-bit operand type of a tensor-core mode.  3-product (fp32-parity) mode: fp16 hi + fp16 residual, i.e.
+// 22 significand bits per operand (the dropped lo*lo term is 2^-22 relative) -- 4x closer to fp32 than a
+// bf16 hi/lo split (16 bits) at the same MMA cost; the path's activations and weights are O(10) at most, far
+// inside fp16's range, and the conversions saturate instead of overflowing.  Single-product mode: bf16
+// (BASELINE.json config 3).
+template <int NPROD>
+struct TcOperand { static constexpr bool F16 = (NPROD == 3); };
+
+// instruction descriptor kind::f16: D fp32 (bit 4), A/B format at bits 7 / 10 (0 = f16, 1 = bf16), K-major both,
+// N>>3 at 17, M>>4 at 24
+template <bool F16>
+__host__ __device__ constexpr uint32_t umma_idesc(int M, int N) {
+  return (1u << 4) | (F16 ? 0u : ((1u << 7) | (1u << 10))) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
-__device__ __forceinline__ void split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
-  hi = __float2bfloat16_rn(x);
-  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
-}
-// two floats -> packed bf16 hi pair and packed bf16 residual pair (element 0 in the low half)
-__device__ __forceinline__ void split_bf16x2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(x1), "f"(x0));
-  const float r0 = x0 - __uint_as_float(hi2 << 16);
-  const float r1 = x1 - __uint_as_float(hi2 & 0xffff0000u);
-  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(r1), "f"(r0));
+// two floats -> packed 16-bit hi pair and packed 16-bit residual pair (element 0 in the low half)
+template <bool F16>
+__device__ __forceinline__ void split16x2(float x0, float x1, uint32_t& hi2, uint32_t& lo2) {
+  if (F16) {
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(x1), "f"(x0));
+    const float2 h = __half22float2(*reinterpret_cast<const __half2*>(&hi2));
+    const float r0 = x0 - h.x;
+    const float r1 = x1 - h.y;
+    asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(r1), "f"(r0));
+  } else {
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(hi2) : "f"(x1), "f"(x0));
+    const float r0 = x0 - __uint_as_float(hi2 << 16);
+    const float r1 = x1 - __uint_as_float(hi2 & 0xffff0000u);
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(lo2) : "f"(r1), "f"(r0));
+  }
 }
 __device__ __forceinline__ void st_global_256(void* ptr, const uint32_t* v) {
   asm volatile("st.global.v8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"l"(ptr), "r"(v[0]), "r"(v[1]), "r"(v[2]),
@@ -370,7 +385,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
   } else if (warp == 1) {
     // ===================== MMA issuer =====================
     if (lane == 0) {
-      constexpr uint32_t idesc = umma_idesc_bf16(128, BN);
+      constexpr uint32_t idesc = umma_idesc<TcOperand<NPROD>::F16>(128, BN);
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       if (RESW && blockIdx.x < total_tiles) mbar_wait(bar_res, 0);
@@ -486,7 +501,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         }
         uint32_t hi[16], lo[16];
 #pragma unroll
-        for (int j = 0; j < 32; j += 2) split_bf16x2(x[j], x[j + 1], hi[j >> 1], lo[j >> 1]);
+        for (int j = 0; j < 32; j += 2) split16x2<TcOperand<NPROD>::F16>(x[j], x[j + 1], hi[j >> 1], lo[j >> 1]);
         // the stores that last read this staging buffer must be done with it (with two buffers: the group
         // committed two tiles ago, i.e. all but the most recent one)
         const uint32_t obuf = ostage_base + (uint32_t)((out_bufs == 2 ? acc : 0) * Cfg::OUT_BYTES);
@@ -551,6 +566,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
 // points (never straddling two sets: N is a multiple of 128); 256 threads = 32 point slots x 8 channel groups,
 // four points per thread, so weights / transform / points are staged once per 128 points.
 constexpr int FRONT_PTS = 128;
+template <bool F16>
 __global__ void __launch_bounds__(256) front3_split_kernel(const float* __restrict__ q, const float* __restrict__ t3,
                                                            const float* __restrict__ W, const float* __restrict__ bias,
                                                            __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
@@ -586,7 +602,7 @@ __global__ void __launch_bounds__(256) front3_split_kernel(const float* __restri
     for (int j = 0; j < 8; j += 2) {
       const float v0 = fmaxf(bb[j] + w[j][0] * x0 + w[j][1] * x1 + w[j][2] * x2, 0.0f);
       const float v1 = fmaxf(bb[j + 1] + w[j + 1][0] * x0 + w[j + 1][1] * x1 + w[j + 1][2] * x2, 0.0f);
-      split_bf16x2(v0, v1, hi[j >> 1], lo[j >> 1]);
+      split16x2<F16>(v0, v1, hi[j >> 1], lo[j >> 1]);
     }
     *reinterpret_cast<uint4*>(out_hi + (size_t)r * 64 + cg * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
     *reinterpret_cast<uint4*>(out_lo + (size_t)r * 64 + cg * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
@@ -627,20 +643,6 @@ inline bool tc_make_map(CUtensorMap* m, const void* base, uint64_t rows, uint64_
   cuuint32_t box[2] = {(cuuint32_t)TC_BK, box_rows};
   cuuint32_t estr[2] = {1, 1};
   CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
-                  CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                  CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  return r == CUDA_SUCCESS;
-}
-
-// fp16 [rows, cols] row-major view, box = box_cols x box_rows (box_cols * 2 <= 128 B), 128B swizzle (TMA stores)
-inline bool tc_make_map_f16(CUtensorMap* m, const void* base, uint64_t rows, uint64_t cols, uint32_t box_cols, uint32_t box_rows) {
-  PFN_encodeTiled fn = tc_encode_fn();
-  if (!fn) return false;
-  cuuint64_t gdim[2] = {cols, rows};
-  cuuint64_t gstride[1] = {cols * 2};
-  cuuint32_t box[2] = {box_cols, box_rows};
-  cuuint32_t estr[2] = {1, 1};
-  CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   return r == CUDA_SUCCESS;

@@ -137,7 +137,7 @@ class CatreB200(nn.Module):
     ``.to()``, ``.eval()``, ``.parameters()``, ``state_dict()`` with the checkpoint's keys, and
     ``forward(...)`` for one refinement iteration."""
 
-    def __init__(self, n_obs: int = 1024, n_prior: int = 1024, precision: str = "bf16x3", max_batch: int = 256,
+    def __init__(self, n_obs: int = 1024, n_prior: int = 1024, precision: str = "f16x3", max_batch: int = 256,
                  cfg: Any = None):
         super().__init__()
         if n_obs != n_prior:
@@ -230,7 +230,7 @@ class CatreB200(nn.Module):
         return out
 
 
-def build_model_optimizer(cfg, is_test: bool = False, precision: str = "bf16x3", max_batch: int = 256):
+def build_model_optimizer(cfg, is_test: bool = False, precision: str = "f16x3", max_batch: int = 256):
     """Same contract as the reference's build_model_optimizer (CATRE_disR_shared.py:291-350):
     returns (model, optimizer).  ``optimizer`` is None for is_test=True, as in the reference."""
     n_obs, n_prior = check_cfg(cfg)

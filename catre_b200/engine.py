@@ -15,8 +15,8 @@ import torch
 
 from . import build as _build
 
-PREC_FP32_SIMT, PREC_BF16X3, PREC_BF16 = 0, 1, 2
-PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "bf16x3": PREC_BF16X3, "bf16": PREC_BF16}
+PREC_FP32_SIMT, PREC_F16X3, PREC_BF16 = 0, 1, 2
+PRECISIONS = {"fp32": PREC_FP32_SIMT, "fp32_simt": PREC_FP32_SIMT, "f16x3": PREC_F16X3, "bf16": PREC_BF16}
 
 
 class CatreCfg(ctypes.Structure):
@@ -85,7 +85,7 @@ class Engine:
     """One engine per device.  All tensors fp32; device entry points take CUDA tensors on the engine's
     device and run on the current torch stream without host synchronisation."""
 
-    def __init__(self, n_pts: int, max_batch: int, precision: str = "bf16x3", device: int = 0):
+    def __init__(self, n_pts: int, max_batch: int, precision: str = "f16x3", device: int = 0):
         self.lib = load_library()
         self.n_pts, self.max_batch, self.device = int(n_pts), int(max_batch), int(device)
         self.precision = precision

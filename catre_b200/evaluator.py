@@ -135,8 +135,26 @@ def _filter_labels(evaluator: Any, batch: Dict[str, Any], device: str) -> bool:
     return True
 
 
+@dataclass
+class _Launch:
+    items: List[_Pending]
+    n_obj: int
+    poses_h: torch.Tensor   # [K+1, n, 3, 4] host (pinned on the CUDA path)
+    scales_h: torch.Tensor  # [K+1, n, 3]
+    ev_start: Any
+    ev_end: Any
+    host_s: float           # host time spent staging + enqueueing this launch
+
+
 class CrossImageRefiner:
-    """Queue loader items, refine ``objects_per_launch`` objects per engine call, hand results back per item."""
+    """Queue loader items, refine ``objects_per_launch`` objects per engine call, hand results back per item.
+
+    The launch is asynchronous: flush() stages the pending objects into one of two pinned host buffers, enqueues
+    H2D copies + the engine's K-loop + the D2H copy of every iteration's pose, and returns; the PREVIOUS launch is
+    then finished (event wait, evaluator.process per loader item), so collation and result collection of one launch
+    run on the host underneath the device work of the next."""
+
+    _KEYS = (("pcl", "pcl"), ("obj_kps", "prior"), ("obj_pose_est", "pose"), ("obj_scale_est", "scale"), ("K", "K"))
 
     def __init__(self, cfg: Any, model: Any, evaluator: Any, n_iter: int, objects_per_launch: int = 256,
                  device: str = "cuda"):
@@ -147,15 +165,20 @@ class CrossImageRefiner:
         self.n_iter = int(n_iter)
         self.objects_per_launch = max(1, int(objects_per_launch))
         self.device = device
+        self.on_gpu = str(device).startswith("cuda")
         self.pending: List[_Pending] = []
         self.pending_objs = 0
         self.stats = InferenceStats()
+        self._stage: List[Optional[Dict[str, torch.Tensor]]] = [None, None]
+        self._cur = 0
+        self._inflight: Optional[_Launch] = None
 
     def add(self, inputs: Sequence[Dict[str, Any]]) -> None:
         t0 = time.perf_counter()
-        batch = batch_data_test(self.cfg, inputs, device=self.device)
+        # collate on the host: the objects cross to the device once per launch (flush), not once per image
+        batch = batch_data_test(self.cfg, inputs, device="cpu")
         self.stats.images += len(inputs)
-        if int(batch["obj_cls"].shape[0]) == 0 or not _filter_labels(self.evaluator, batch, self.device):
+        if int(batch["obj_cls"].shape[0]) == 0 or not _filter_labels(self.evaluator, batch, "cpu"):
             return  # nothing to refine for this item (the reference `continue`s)
         n_obj = int(batch["obj_cls"].shape[0])
         self.pending.append(_Pending(inputs, batch, n_obj, time.perf_counter() - t0))
@@ -163,31 +186,72 @@ class CrossImageRefiner:
         if self.pending_objs >= self.objects_per_launch:
             self.flush()
 
+    def _staging(self, n: int, items: List[_Pending]) -> Dict[str, torch.Tensor]:
+        st = self._stage[self._cur]
+        if st is None or st["cap"] < n:
+            cap = max(n, self.objects_per_launch + 64)
+            st = {"cap": cap}
+            for key, name in self._KEYS:
+                shape = (cap,) + tuple(items[0].batch[key].shape[1:])
+                st[name] = torch.empty(shape, dtype=torch.float32, pin_memory=self.on_gpu)
+            st["out_pose"] = torch.empty((self.n_iter + 1) * cap * 12, dtype=torch.float32, pin_memory=self.on_gpu)
+            st["out_scale"] = torch.empty((self.n_iter + 1) * cap * 3, dtype=torch.float32, pin_memory=self.on_gpu)
+            self._stage[self._cur] = st
+        return st
+
     def flush(self) -> None:
-        if not self.pending:
-            return
-        items, self.pending = self.pending, []
-        n_total, self.pending_objs = self.pending_objs, 0
-        t0 = time.perf_counter()
+        """Launch everything that is pending; finish the launch before it."""
+        if self.pending:
+            items, self.pending = self.pending, []
+            n, self.pending_objs = self.pending_objs, 0
+            t0 = time.perf_counter()
+            st = self._staging(n, items)
+            args = []
+            for key, name in self._KEYS:
+                torch.cat([it.batch[key] for it in items], dim=0, out=st[name][:n])
+                args.append(st[name][:n].to(self.device, non_blocking=True) if self.on_gpu else st[name][:n])
+            k1 = self.n_iter + 1
+            poses_h = st["out_pose"][: k1 * n * 12].view(k1, n, 3, 4)
+            scales_h = st["out_scale"][: k1 * n * 3].view(k1, n, 3)
+            ev_start = ev_end = None
+            if self.on_gpu:
+                ev_start, ev_end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                ev_start.record()
+            poses, scales = self.model.refine(*args, self.n_iter)
+            # ONE device->host copy for every iteration's pose of every object of the launch; the evaluator's own
+            # .detach().cpu().numpy() calls (catre_evaluator.py:96-100) then cost nothing
+            poses_h.copy_(poses, non_blocking=True)
+            scales_h.copy_(scales, non_blocking=True)
+            if self.on_gpu:
+                ev_end.record()
+            launch = _Launch(items, n, poses_h, scales_h, ev_start, ev_end, time.perf_counter() - t0)
+            self.stats.launches += 1
+            self.stats.objects += n
+            self.stats.objects_per_launch.append(n)
+            self._cur ^= 1
+            prev, self._inflight = self._inflight, launch
+        else:
+            prev, self._inflight = self._inflight, None
+        if prev is not None:
+            self._finish(prev)
 
-        def cat(key):
-            return torch.cat([it.batch[key] for it in items], dim=0) if len(items) > 1 else items[0].batch[key]
+    def drain(self) -> None:
+        """Launch what is pending and finish every launch in flight (end of the loader)."""
+        self.flush()
+        if self._inflight is not None:
+            last, self._inflight = self._inflight, None
+            self._finish(last)
 
-        poses, scales = self.model.refine(cat("pcl"), cat("obj_kps"), cat("obj_pose_est"), cat("obj_scale_est"), cat("K"),
-                                          self.n_iter)
-        # one device->host copy for every iteration's pose of every object of the launch; the evaluator's own
-        # .detach().cpu().numpy() calls (catre_evaluator.py:96-100) then cost nothing
-        poses_h = poses.to("cpu", non_blocking=False)
-        scales_h = scales.to("cpu", non_blocking=False)
-        dt = time.perf_counter() - t0
-        self.stats.compute_s += dt + sum(it.t_collate for it in items)
-        self.stats.launches += 1
-        self.stats.objects += n_total
-        self.stats.objects_per_launch.append(n_total)
-
+    def _finish(self, l: _Launch) -> None:
+        dt = l.host_s
+        if l.ev_end is not None:
+            l.ev_end.synchronize()
+            dt = max(dt, l.ev_start.elapsed_time(l.ev_end) * 1e-3)  # device time of H2D + K-loop + D2H
+        self.stats.compute_s += dt + sum(it.t_collate for it in l.items)
         t1 = time.perf_counter()
+        poses_h, scales_h = l.poses_h.clone(), l.scales_h.clone()  # the pinned buffer is reused two launches later
         o0 = 0
-        for it in items:
+        for it in l.items:
             sl = slice(o0, o0 + it.n_obj)
             o0 += it.n_obj
             out_dict = {}
@@ -195,12 +259,9 @@ class CrossImageRefiner:
                 out_dict[f"pose_{i}"] = poses_h[i, sl]
                 out_dict[f"scale_{i}"] = scales_h[i, sl]
             # the reference leaves the last iteration's estimate in the batch (batch_test.py:73-77)
-            it.batch["obj_pose_est"] = poses[self.n_iter, sl]
-            it.batch["obj_scale_est"] = scales[self.n_iter, sl]
-            # the evaluator only reads ids / labels from the batch; give it host copies so it does not sync
-            for k in ("im_id", "inst_id", "obj_cls"):
-                it.batch[k] = it.batch[k].cpu()
-            share = it.t_collate + dt * (it.n_obj / float(n_total))  # this item's share of the launch
+            it.batch["obj_pose_est"] = poses_h[self.n_iter, sl]
+            it.batch["obj_scale_est"] = scales_h[self.n_iter, sl]
+            share = it.t_collate + dt * (it.n_obj / float(l.n_obj))  # this item's share of the launch
             outputs = [{"time": share} for _ in range(len(it.inputs))]
             self.evaluator.process(it.inputs, it.batch, outputs, out_dict)
         self.stats.process_s += time.perf_counter() - t1
@@ -243,7 +304,7 @@ def catre_inference_on_dataset(cfg, model, data_loader, evaluator, amp_test: boo
     with torch.no_grad():
         for inputs in data_loader:
             runner.add(inputs)
-        runner.flush()
+        runner.drain()
     if torch.cuda.is_available():
         torch.cuda.synchronize()
     st = runner.stats
@@ -309,8 +370,7 @@ class PosePredictionCollector:
         inst_ids = batch["inst_id"].detach().cpu().numpy().tolist()
         labels = batch["obj_cls"].detach().cpu().numpy().tolist()
         names = self.train_objs if self.train_objs is not None else self.obj_names
-        meta = torch.zeros((n, self._META), dtype=torch.float64)
-        order = []
+        meta_rows, order = [], []
         for im_i, (inp, output) in enumerate(zip(inputs, outputs)):  # records are emitted image by image
             scene_id, im_id = inp["scene_im_id"].split("/")
             if scene_id not in self._scenes:
@@ -322,12 +382,14 @@ class PosePredictionCollector:
                 inst_id = int(inst_ids[out_i])
                 score = float(inst.obj_scores[inst_id]) if inst is not None and hasattr(inst, "obj_scores") else 1.0
                 handle = float(inst.mug_handle[inst_id]) if inst is not None and hasattr(inst, "mug_handle") else 1.0
-                meta[out_i] = torch.tensor([self._scenes.index(scene_id), int(im_id), self.obj2id[names[labels[out_i]]],
-                                            score, handle, output["time"]], dtype=torch.float64)
+                meta_rows.append([self._scenes.index(scene_id), int(im_id), self.obj2id[names[labels[out_i]]], score, handle,
+                                  output["time"]])
                 order.append(out_i)
+        if not order:
+            return
         idx = torch.tensor(order, dtype=torch.long)
         body = torch.cat((poses.reshape(n, k1, 12), scales.reshape(n, k1, 3)), dim=2).reshape(n, k1 * 15)
-        self._rows.append(torch.cat((meta, body), dim=1)[idx])
+        self._rows.append(torch.cat((torch.tensor(meta_rows, dtype=torch.float64), body[idx]), dim=1))
 
     def rows(self) -> torch.Tensor:
         width = self._META + (self.n_iter_test + 1) * 15
@@ -347,14 +409,15 @@ class PosePredictionCollector:
                 return None
         k1 = self.n_iter_test + 1
         out: Dict[str, List[Dict[str, Any]]] = {f"iter{i}": [] for i in range(k1)}
-        body = rows[:, self._META:].reshape(-1, k1, 15)
-        for r in range(rows.shape[0]):
-            m = rows[r]
+        body = rows[:, self._META:].reshape(-1, k1, 3 + 12)
+        pose = body[:, :, :12].reshape(-1, k1, 3, 4)
+        rot = pose[..., :3].reshape(-1, k1, 9).tolist()  # one conversion for all records, not one per record
+        trans = (1000.0 * pose[..., 3]).tolist()
+        scale = body[:, :, 12:].tolist()
+        meta = rows[:, : self._META].tolist()
+        for r, m in enumerate(meta):
+            scene, im_id, obj_id, handle = scenes[int(m[0])], int(m[1]), int(m[2]), int(m[4])
             for i in range(k1):
-                v = body[r, i]
-                out[f"iter{i}"].append({
-                    "scene_id": scenes[int(m[0])], "im_id": int(m[1]), "obj_id": int(m[2]), "score": float(m[3]),
-                    "R": v[:12].reshape(3, 4)[:, :3].flatten().tolist(), "t": (1000.0 * v[:12].reshape(3, 4)[:, 3]).tolist(),
-                    "scale": v[12:].tolist(), "mug_handle": int(m[4]), "time": float(m[5]),
-                })
+                out[f"iter{i}"].append({"scene_id": scene, "im_id": im_id, "obj_id": obj_id, "score": m[3], "R": rot[r][i],
+                                        "t": trans[r][i], "scale": scale[r][i], "mug_handle": handle, "time": m[5]})
         return out

@@ -43,8 +43,9 @@ typedef enum catre_status {
 /* arithmetic of the wide per-point contractions (everything else is always fp32 FMA) */
 typedef enum catre_precision {
   CATRE_PREC_FP32_SIMT = 0,   /* fp32 FMA on CUDA cores everywhere (strict mode, validation) */
-  CATRE_PREC_BF16X3 = 1,      /* tcgen05 kind::f16, bf16 hi/lo split, 3 products, fp32 TMEM accumulate:
-                                 fp32-parity mode (<= 1e-4 on R,t,s vs the reference fp32 forward) */
+  CATRE_PREC_F16X3 = 1,       /* tcgen05 kind::f16, operands split x = hi + lo (fp16 each, 22 significand bits),
+                                 3 products hi*hi + hi*lo + lo*hi, fp32 TMEM accumulate: the fp32-parity mode
+                                 (<= 1e-4 on R,t,s vs the reference fp32 forward; measured ~1e-5) */
   CATRE_PREC_BF16 = 2         /* tcgen05 single-product bf16 (BASELINE.json config 3; looser tolerance) */
 } catre_precision;
 

@@ -269,7 +269,7 @@ def test_cross_image_refinement_on_the_engine_is_bit_exact_and_matches_golden():
     assert sum(sizes) == 64
     loader = make_loader(b, sizes)
     cfg = {"INPUT": {"KPS_TYPE": "mean_shape"}, "MODEL": {"CATRE": {"N_ITER_TEST": case.n_iter}}}
-    model = dropin.CatreB200(1024, 1024, precision="bf16x3", max_batch=32)
+    model = dropin.CatreB200(1024, 1024, precision="f16x3", max_batch=32)
     model.load_state_dict(synth.load_weights(), strict=True)
     model = model.to("cuda").eval()
     rec = Recorder()

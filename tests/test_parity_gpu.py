@@ -13,7 +13,7 @@ from tests import golden_util as gu
 pytestmark = pytest.mark.gpu
 
 TOL = gu.TOL  # 1e-4
-PRECS = ["fp32", "bf16x3"]
+PRECS = ["fp32", "f16x3"]
 
 
 @pytest.fixture(scope="module")
@@ -161,11 +161,11 @@ def test_full_size_properties(weights, prec):
 
 
 def test_precision_modes_agree(weights):
-    """fp32 CUDA-core mode vs bf16x3 tensor-core mode on the same inputs (both within TOL of the
+    """fp32 CUDA-core mode vs f16x3 tensor-core mode on the same inputs (both within TOL of the
     reference, so within 2*TOL of each other; typically ~1e-5)."""
     b = synth.make_batch(16, 1024, seed=31)
     pa, sa = run_refine(get_engine(weights, 1024, "fp32"), b, 4)
-    pb, sb = run_refine(get_engine(weights, 1024, "bf16x3"), b, 4)
+    pb, sb = run_refine(get_engine(weights, 1024, "f16x3"), b, 4)
     assert (pa - pb).abs().max() <= 2 * TOL and (sa - sb).abs().max() <= 2 * TOL
 
 
@@ -173,7 +173,7 @@ def test_refine_is_cuda_graph_capturable(weights):
     """include/catre_b200.h promises stream-ordered, sync-free, graph-capturable calls (the engine forks its
     ts head onto an internal side stream and joins it again inside the call)."""
     b = synth.make_batch(8, 1024, seed=41).to("cuda")
-    eng = get_engine(weights, 1024, "bf16x3")
+    eng = get_engine(weights, 1024, "f16x3")
     out = (torch.empty((5, 8, 3, 4), device="cuda"), torch.empty((5, 8, 3), device="cuda"))
     eng.refine(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, 4, out=out)  # warm-up: one-time kernel attributes
     torch.cuda.synchronize()

@@ -1,0 +1,59 @@
+"""Measure the evaluator K-loop on the GPU: REAL275-like loader items (one image, a few
+objects each, CPU tensors as a data loader yields them) through catre_b200.evaluator.catre_inference_on_dataset
+ (a) with the reference's grouping -- one launch chain per image (objects_per_launch=1 flushes every item) -- and
+ (b) with cross-image batching (256 objects per launch),
+both on the same engine, collecting every iteration's pose into the reference's record format.
+Prints one JSON line.  Usage: python tools/bench_evaluator.py [--images 400]"""
+import argparse
+import json
+import os
+import sys
+import time
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import torch  # noqa: E402
+
+from catre_b200 import dropin, evaluator as ev, synth  # noqa: E402
+from tests.test_evaluator import OBJ2ID, OBJ_NAMES, make_loader  # noqa: E402  (fake Instances / loader items)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--images", type=int, default=400)
+    ap.add_argument("--n-iter", type=int, default=4)
+    a = ap.parse_args()
+    g = torch.Generator().manual_seed(0)
+    sizes = torch.randint(3, 9, (a.images,), generator=g).tolist()  # REAL275: 15374 objects / 2754 images = 5.6
+    total = sum(sizes)
+    b = synth.make_batch(total, 1024, seed=9)
+    loader = make_loader(b, sizes)
+    cfg = {"INPUT": {"KPS_TYPE": "mean_shape"}, "MODEL": {"CATRE": {"N_ITER_TEST": a.n_iter}}}
+    model = dropin.CatreB200(1024, 1024, precision="f16x3", max_batch=256)
+    model.load_state_dict(synth.load_weights(), strict=True)
+    model = model.to("cuda").eval()
+    out = {"images": a.images, "objects": total, "n_iter": a.n_iter}
+    results = {}
+    for name, opl in (("per_image", 1), ("cross_image_256", 256)):
+        col = ev.PosePredictionCollector(OBJ_NAMES, OBJ2ID, a.n_iter)
+        ev.catre_inference_on_dataset(cfg, model, loader[:20], col, objects_per_launch=opl)  # warm-up
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        res, st = ev.catre_inference_on_dataset(cfg, model, loader, col, objects_per_launch=opl, return_stats=True)
+        dt = time.perf_counter() - t0
+        results[name] = res
+        out[name] = {"seconds": round(dt, 4), "objects_per_s": round(total / dt, 1), "images_per_s": round(a.images / dt, 1),
+                     "launches": st.launches, "compute_s": round(st.compute_s, 4), "collect_s": round(st.process_s, 4)}
+    # the two groupings agree to rounding, not to the bit, once a launch holds >= 128 objects: from there the engine
+    # runs the T-Net FC chain on the tensor cores (f16x3) instead of the fp32 cluster kernels
+    last = f"iter{a.n_iter}"
+    diff = 0.0
+    for x, y in zip(results["per_image"][last], results["cross_image_256"][last]):
+        for f, unit in (("R", 1.0), ("t", 1e-3), ("scale", 1.0)):
+            diff = max(diff, max(abs(p - q) for p, q in zip(x[f], y[f])) * unit)
+    out["max_abs_diff_between_groupings"] = diff
+    out["speedup"] = round(out["per_image"]["seconds"] / out["cross_image_256"]["seconds"], 2)
+    print(json.dumps(out))
+
+
+if __name__ == "__main__":
+    main()

@@ -34,7 +34,7 @@ def main():
     ap.add_argument("--batch", type=int, default=256)
     ap.add_argument("--n", type=int, default=1024)
     ap.add_argument("--k", type=int, default=4)
-    ap.add_argument("--prec", default="fp32,bf16x3")
+    ap.add_argument("--prec", default="fp32,f16x3")
     ap.add_argument("--ref", type=int, default=1)
     ap.add_argument("--out", default="gpurun_out/probe.json")
     args = ap.parse_args()

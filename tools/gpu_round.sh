@@ -10,5 +10,5 @@ python bench.py --impl reference --steps 2 --warmup 1 > gpurun_out/bench_ref.jso
 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file gpurun_out/launches.csv \
     python bench.py --steps 2 --warmup 1 --no-cpu-baseline > gpurun_out/ncu_bench.log 2>&1
 ncu --set full --clock-control none --import-source on -k regex:tc_gemm -s 12 -c 12 -o gpurun_out/prof_tc \
-    python tools/ncu_target.py bf16x3 64 > gpurun_out/ncu_full.log 2>&1
+    python tools/ncu_target.py f16x3 64 > gpurun_out/ncu_full.log 2>&1
 ls -la gpurun_out

@@ -7,7 +7,7 @@ import torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from catre_b200 import engine, synth  # noqa: E402
 
-prec = sys.argv[1] if len(sys.argv) > 1 else "bf16x3"
+prec = sys.argv[1] if len(sys.argv) > 1 else "f16x3"
 B = int(sys.argv[2]) if len(sys.argv) > 2 else 64
 eng = engine.Engine(1024, B, prec, 0)
 eng.load_weights(synth.load_weights())

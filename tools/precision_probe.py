@@ -44,6 +44,15 @@ def make_pw(plan):
             xh, xl = split_bf16(x)
             wh, wl = split_bf16(wt)
             return F.conv1d(xh, wh, b) + F.conv1d(xh, wl) + F.conv1d(xl, wh)
+        if fmt == "f16x3":
+            xh = x.half().float(); xl = (x - xh).half().float()
+            wh = wt.half().float(); wl = (wt - wh).half().float()
+            return F.conv1d(xh, wh, b) + F.conv1d(xh, wl) + F.conv1d(xl, wh)
+        if fmt == "f16x3s":  # weights scaled by 2^8 before the split (their fp16 residuals leave the subnormal range)
+            xh = x.half().float(); xl = (x - xh).half().float()
+            ws = wt * 256.0
+            wh = ws.half().float(); wl = (ws - wh).half().float()
+            return (F.conv1d(xh, wh) + F.conv1d(xh, wl) + F.conv1d(xl, wh)) * (1.0 / 256.0) + b.reshape(1, -1, 1)
         if fmt == "f16":
             return F.conv1d(x.half().float(), wt.half().float(), b)
         if fmt == "bf16":
