@@ -271,3 +271,18 @@ def test_refine_table_bad_class_ids(weights):
     assert torch.equal(s[1, 0], good_s[1, 0]) and torch.equal(s[1, 2], good_s[1, 2])
     with pytest.raises(engine.CatreError):
         eng.refine_table(d.pcl, table.cuda(), cls.cuda().long(), d.init_pose, d.init_scale, d.K, 1)  # dtype
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_oracle_parity_k8_symmetric_categories(weights, prec):
+    """BASELINE.json config 4's iteration count (K = 8) at N = 1024 on the categories that are rotationally
+    symmetric (bottle, bowl, can): their rotation about the symmetry axis is unconstrained, the refinement keeps
+    turning them every iteration and any rounding difference grows ~1.4x per iteration -- the
+    hardest case for the 1e-4 bar."""
+    b = synth.make_batch(24, 1024, seed=61, round_robin_cls=True)
+    keep = torch.nonzero((b.obj_cls == 0) | (b.obj_cls == 1) | (b.obj_cls == 3)).flatten()
+    sub = synth.Batch(*(getattr(b, f)[keep].contiguous() for f in ("pcl", "prior", "init_pose", "init_scale", "K", "obj_cls")))
+    ref_p, ref_s = catre_oracle.refine(weights, sub.pcl, sub.prior, sub.init_pose, sub.init_scale, sub.K, 8)
+    poses, scales = run_refine(get_engine(weights, 1024, prec), sub, 8)
+    e = gu.max_abs_err(poses, scales, ref_p, ref_s)
+    assert max(e) <= TOL, e
