@@ -1,0 +1,107 @@
+"""Observed-cloud producer on the GPU: ``instances.pcl`` for all objects of one image.
+
+Stands in for the per-object CPU loop of the reference's test data loader
+(core/catre/datasets/data_loader.py:773-799 under the shipped config SAMPLE_DEPTH_FROM_BALL=True,
+DEPTH_SAMPLE_BALL_RATIO=0.6, FPS_SAMPLE=False, OCCLUDE_MASK_TEST=False):
+``depth_bp = backproject_th(depth, K)`` (lib/pysixd/misc.py:360-378) followed per object by
+``crop_ball_from_depth_image(image, depth_bp, mask, pose, scale, ratio, K, num_points=NUM_PCL)``
+(core/utils/cat_data_utils.py:380-400).  The per-pixel work (back-projection, mask & depth test, distances, radius
+growth, ordered compaction, final gather) runs in libcatre_b200.so (csrc/cloud_kernels.cuh) for all objects at
+once; the random draw is ``torch.randperm`` on the global CPU generator, called once per object in instance order
+exactly as the reference does, so ``torch.manual_seed(s)`` reproduces the reference's cloud bit for bit.
+
+No CPU fallback: needs the CUDA library and a device.
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Tuple
+
+import torch
+
+from . import engine as _engine
+
+N_RADII = 10  # crop_ball_from_pts tries the initial radius and up to 9 enlargements (cat_data_utils.py:286-291)
+
+
+def ball_radii(poses: torch.Tensor, scales: torch.Tensor, ratio: float) -> torch.Tensor:
+    """[B, 10] fp32: the radii the reference would try for each object.  r0 = max(ratio * |R s|, 0.05)
+    (cat_data_utils.py:386, :285), then r *= 1.10 per retry.  The reference keeps r as an fp32 tensor when the
+    object term wins (fp32 multiplies) and as a Python float when the 0.05 floor wins (double multiplies, rounded
+    to fp32 only in the comparison); both roundings are reproduced."""
+    out = torch.empty((poses.shape[0], N_RADII), dtype=torch.float32)
+    for b in range(poses.shape[0]):
+        pose, scale = poses[b].detach().cpu().float(), scales[b].detach().cpu().float()
+        r = ratio * torch.norm(pose[:, :3] @ scale)
+        if float(r) > 0.05:
+            for i in range(N_RADII):
+                out[b, i] = r
+                r = r * torch.tensor(1.10)  # fp32 tensor *= python float -> fp32 multiply
+        else:
+            rf = 0.05
+            for i in range(N_RADII):
+                out[b, i] = rf  # double -> fp32 on assignment, as in `distance <= radius`
+                rf *= 1.10
+    return out
+
+
+def _intr(K) -> "ctypes.Array":
+    Kt = torch.as_tensor(K).detach().cpu().float()
+    return (ctypes.c_float * 4)(float(Kt[0, 0]), float(Kt[1, 1]), float(Kt[0, 2]), float(Kt[1, 2]))
+
+
+def select_ball_points(depth: torch.Tensor, K, masks: torch.Tensor, poses: torch.Tensor, scales: torch.Tensor,
+                       ratio: float = 0.6) -> Tuple[torch.Tensor, torch.Tensor]:
+    """Device part 1: per object the ordered pixel ids inside the chosen ball.  depth [H,W] fp32 and masks [B,H,W]
+    bool/uint8 may live on the CPU or the GPU; poses [B,3,4], scales [B,3].  Returns (sel_pix [B, H*W] int32 CUDA,
+    n_sel [B] int32 CUDA); only the first n_sel[b] entries of row b are meaningful."""
+    lib = _engine.load_library()
+    if not torch.cuda.is_available():
+        raise _engine.CatreError("catre_b200.cloud runs on CUDA only; there is no CPU path")
+    dev = depth.device if depth.is_cuda else torch.device("cuda", torch.cuda.current_device())
+    depth_d = depth.to(dev, torch.float32).contiguous()
+    H, W = depth_d.shape
+    masks_d = masks.to(dev).to(torch.uint8).contiguous()
+    B = masks_d.shape[0]
+    if tuple(masks_d.shape) != (B, H, W) or tuple(poses.shape) != (B, 3, 4) or tuple(scales.shape) != (B, 3):
+        raise _engine.CatreError("shape mismatch between depth, masks, poses and scales")
+    centers = poses[:, :, 3].detach().float().contiguous().to(dev)
+    radii = ball_radii(poses, scales, ratio).to(dev)
+    sel_pix = torch.empty((B, H * W), dtype=torch.int32, device=dev)
+    n_sel = torch.zeros((B,), dtype=torch.int32, device=dev)
+    scratch = torch.empty((lib.catre_cloud_scratch_bytes(B, H, W),), dtype=torch.uint8, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    rc = lib.catre_cloud_select(depth_d.data_ptr(), masks_d.data_ptr(), _intr(K), centers.data_ptr(), radii.data_ptr(), N_RADII,
+                                B, H, W, sel_pix.data_ptr(), n_sel.data_ptr(), scratch.data_ptr(), stream)
+    if rc != 0:
+        raise _engine.CatreError(f"catre_cloud_select failed ({rc}): {lib.catre_last_error(None).decode()}")
+    return sel_pix, n_sel
+
+
+def sample_object_clouds(depth: torch.Tensor, K, masks: torch.Tensor, poses: torch.Tensor, scales: torch.Tensor,
+                         num_points: int = 1024, ratio: float = 0.6,
+                         generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """``test_insts.pcl`` for one image: [B, num_points, 3] fp32 on the GPU (data_loader.py:773-799)."""
+    lib = _engine.load_library()
+    sel_pix, n_sel = select_ball_points(depth, K, masks, poses, scales, ratio)
+    dev = sel_pix.device
+    B = int(n_sel.shape[0])
+    H, W = depth.shape
+    counts = n_sel.cpu().tolist()  # the one host sync: the draw below depends on the counts
+    sample = torch.empty((B, num_points), dtype=torch.int64)
+    for b, n in enumerate(counts):  # instance order, one randperm per object: the reference's RNG call sequence
+        if n == 0:
+            raise ValueError(f"object {b} has no valid depth pixel under its mask")
+        length = n
+        while length < num_points:  # `while len(idx) < num_points: idx = cat([idx, idx])` (cat_data_utils.py:297-298)
+            length *= 2
+        sample[b] = torch.randperm(length, generator=generator)[:num_points]
+    sample_d = sample.pin_memory().to(dev, non_blocking=True)
+    depth_d = depth.to(dev, torch.float32).contiguous()
+    pcl = torch.empty((B, num_points, 3), dtype=torch.float32, device=dev)
+    stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+    rc = lib.catre_cloud_gather(depth_d.data_ptr(), _intr(K), sel_pix.data_ptr(), n_sel.data_ptr(), sample_d.data_ptr(), B, H, W,
+                                num_points, pcl.data_ptr(), stream)
+    if rc != 0:
+        raise _engine.CatreError(f"catre_cloud_gather failed ({rc}): {lib.catre_last_error(None).decode()}")
+    return pcl

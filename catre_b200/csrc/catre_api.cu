@@ -15,6 +15,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc_fused.cuh"
+#include "cloud_kernels.cuh"
 
 using namespace catre;
 
@@ -1034,6 +1035,61 @@ int catre_refine_table_host(catre_engine* e, const float* pcl, const float* prio
                             float* out_poses, float* out_scales, void* stream) {
   if (e && (n_cls < 1 || (!prior_cls && B > 0))) return fail(e, CATRE_ERR_INVALID_ARG, "prior table needs n_cls >= 1 and class ids");
   return refine_host_impl(e, pcl, prior_table, prior_cls, n_cls, init_pose, init_scale, K, B, n_iter, out_poses, out_scales, stream);
+}
+
+// ---- observed-cloud producer (cloud_kernels.cuh): engine-independent, errors go to catre_last_error(NULL) ----
+namespace {
+struct CloudScratch { int* hist; int* chunk_off; int* kstar; };
+inline int cloud_chunks(long long hw) { return (int)((hw + CLOUD_CHUNK - 1) / CLOUD_CHUNK); }
+inline CloudScratch cloud_scratch(void* scratch, int B, int n_chunks) {
+  CloudScratch c;
+  c.hist = reinterpret_cast<int*>(scratch);
+  c.chunk_off = c.hist + (size_t)B * n_chunks * CLOUD_BINS;
+  c.kstar = c.chunk_off + (size_t)B * n_chunks;
+  return c;
+}
+}  // namespace
+
+size_t catre_cloud_scratch_bytes(int32_t B, int32_t H, int32_t W) {
+  if (B < 0 || H <= 0 || W <= 0) return 0;
+  const size_t nc = (size_t)cloud_chunks((long long)H * W);
+  return ((size_t)B * nc * (CLOUD_BINS + 1) + (size_t)B + 16) * sizeof(int);
+}
+
+int catre_cloud_select(const float* depth, const uint8_t* masks, const float* intr, const float* centers, const float* radii,
+                       int32_t n_radii, int32_t B, int32_t H, int32_t W, int32_t* sel_pix, int32_t* n_sel, void* scratch,
+                       void* stream) {
+  if (B == 0) return CATRE_OK;
+  if (!depth || !masks || !intr || !centers || !radii || !sel_pix || !n_sel || !scratch)
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_cloud_select: null argument");
+  if (B < 0 || H <= 0 || W <= 0 || (long long)H * W > (1ll << 30))
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_cloud_select: bad sizes B=%d H=%d W=%d", B, H, W);
+  if (n_radii < 1 || n_radii > CLOUD_MAX_RADII)
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_cloud_select: n_radii=%d outside [1, %d]", n_radii, CLOUD_MAX_RADII);
+  cudaStream_t s = (cudaStream_t)stream;
+  const int HW = H * W, nc = cloud_chunks(HW);
+  const CloudIntr k{intr[0], intr[1], intr[2], intr[3]};
+  const CloudScratch c = cloud_scratch(scratch, B, nc);
+  cloud_hist_kernel<<<dim3(nc, B), CLOUD_THREADS, 0, s>>>(depth, masks, k, centers, radii, n_radii, HW, W, nc, c.hist);
+  cloud_select_kernel<<<B, 32, 0, s>>>(c.hist, nc, n_radii, c.kstar, n_sel, c.chunk_off);
+  cloud_compact_kernel<<<dim3(nc, B), CLOUD_THREADS, 0, s>>>(depth, masks, k, centers, radii, n_radii, HW, W, nc, c.kstar,
+                                                               c.chunk_off, sel_pix);
+  CU_TRY(nullptr, cudaGetLastError());
+  return CATRE_OK;
+}
+
+int catre_cloud_gather(const float* depth, const float* intr, const int32_t* sel_pix, const int32_t* n_sel, const int64_t* sample_idx,
+                       int32_t B, int32_t H, int32_t W, int32_t n_pts, float* pcl, void* stream) {
+  if (B == 0 || n_pts == 0) return CATRE_OK;
+  if (!depth || !intr || !sel_pix || !n_sel || !sample_idx || !pcl)
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_cloud_gather: null argument");
+  if (B < 0 || H <= 0 || W <= 0 || n_pts < 0)
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_cloud_gather: bad sizes B=%d H=%d W=%d n_pts=%d", B, H, W, n_pts);
+  const CloudIntr k{intr[0], intr[1], intr[2], intr[3]};
+  cloud_gather_kernel<<<dim3((n_pts + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(
+      depth, k, sel_pix, n_sel, reinterpret_cast<const long long*>(sample_idx), H * W, W, n_pts, pcl);
+  CU_TRY(nullptr, cudaGetLastError());
+  return CATRE_OK;
 }
 
 int64_t catre_last_launch_count(const catre_engine* e) { return e ? e->launches : 0; }

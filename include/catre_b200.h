@@ -123,6 +123,29 @@ int catre_refine_table_host(catre_engine* e, const float* pcl, const float* prio
                             int32_t n_cls, const float* init_pose, const float* init_scale, const float* K,
                             int32_t B, int32_t n_iter, float* out_poses, float* out_scales, void* stream);
 
+/* ---- Observed-cloud producer (the step before the path) ------------------------------
+ * Replaces, for all objects of one image, the per-object CPU loop of the reference's test data loader
+ * (core/catre/datasets/data_loader.py:773-799): misc.backproject_th (lib/pysixd/misc.py:360-378) +
+ * crop_ball_from_depth_image / sample_bp_depth / crop_ball_from_pts (core/utils/cat_data_utils.py:209-226,
+ * 283-318, 380-400) with SAMPLE_DEPTH_FROM_BALL=True, FPS_SAMPLE=False.  Engine-independent; errors are reported
+ * through catre_last_error(NULL).  All pointers are device pointers except `intr` (host: fx, fy, cx, cy).
+ *
+ * catre_cloud_select: candidates of object b = pixels with masks[b] != 0 and depth > 0, in row-major order; they are
+ *   cropped to the first of the n_radii (<= 16, non-decreasing) balls |p - centers[b]| <= radii[b][i] that holds
+ *   >= 10 of them, to the last ball otherwise, and to all candidates when that ball is empty.  Writes the selected
+ *   pixel ids in order to sel_pix[b][0 .. n_sel[b]) (sel_pix is [B, H*W]) and their count to n_sel[b].
+ *   depth [H*W] fp32 metres, masks [B, H*W] uint8, centers [B,3] (the initial translation), radii [B, n_radii]
+ *   (the caller applies the reference's max(ratio*|R s|, 0.05) * 1.1^i rule); scratch >= catre_cloud_scratch_bytes.
+ * catre_cloud_gather: pcl[b][j] = back-projection of selected pixel (sample_idx[b][j] mod n_sel[b]); sample_idx
+ *   [B, n_pts] int64 is the caller's torch.randperm draw over the repeated index list (the random draw stays on
+ *   the host generator so a seed reproduces the reference's cloud bit for bit).  An object with n_sel == 0 gets NaN. */
+size_t catre_cloud_scratch_bytes(int32_t B, int32_t H, int32_t W);
+int catre_cloud_select(const float* depth, const uint8_t* masks, const float* intr, const float* centers, const float* radii,
+                       int32_t n_radii, int32_t B, int32_t H, int32_t W, int32_t* sel_pix, int32_t* n_sel, void* scratch,
+                       void* stream);
+int catre_cloud_gather(const float* depth, const float* intr, const int32_t* sel_pix, const int32_t* n_sel,
+                       const int64_t* sample_idx, int32_t B, int32_t H, int32_t W, int32_t n_pts, float* pcl, void* stream);
+
 /* Number of kernels the last forward/refine call launched (bench.py's `gpu_launches`). */
 int64_t catre_last_launch_count(const catre_engine* e);
 
