@@ -21,6 +21,7 @@ import torch
 
 from . import engine as _engine
 
+_SCRATCH: dict = {}
 N_RADII = 10  # crop_ball_from_pts tries the initial radius and up to 9 enlargements (cat_data_utils.py:286-291)
 
 
@@ -29,19 +30,20 @@ def ball_radii(poses: torch.Tensor, scales: torch.Tensor, ratio: float) -> torch
     (cat_data_utils.py:386, :285), then r *= 1.10 per retry.  The reference keeps r as an fp32 tensor when the
     object term wins (fp32 multiplies) and as a Python float when the 0.05 floor wins (double multiplies, rounded
     to fp32 only in the comparison); both roundings are reproduced."""
-    out = torch.empty((poses.shape[0], N_RADII), dtype=torch.float32)
-    for b in range(poses.shape[0]):
-        pose, scale = poses[b].detach().cpu().float(), scales[b].detach().cpu().float()
-        r = ratio * torch.norm(pose[:, :3] @ scale)
-        if float(r) > 0.05:
-            for i in range(N_RADII):
-                out[b, i] = r
-                r = r * torch.tensor(1.10)  # fp32 tensor *= python float -> fp32 multiply
-        else:
-            rf = 0.05
-            for i in range(N_RADII):
-                out[b, i] = rf  # double -> fp32 on assignment, as in `distance <= radius`
-                rf *= 1.10
+    P, S = poses.detach().cpu().float(), scales.detach().cpu().float()
+    # one mv + norm per object (the reference's own ops, so the fp32 rounding is the same), the x1.10 chain vectorised
+    r0 = torch.stack([ratio * torch.norm(P[b, :, :3] @ S[b]) for b in range(P.shape[0])]) if P.shape[0] else torch.empty(0)
+    cols = [r0]
+    for _ in range(N_RADII - 1):
+        cols.append(cols[-1] * 1.10)  # fp32 tensor times Python float: an fp32 multiply, like `radius *= 1.10`
+    out = torch.stack(cols, dim=1)
+    floor = r0 < 0.05  # Python's max(radius, 0.05) takes the float exactly when `0.05 > radius`
+    if bool(floor.any()):
+        chain, rf = [], 0.05
+        for _ in range(N_RADII):
+            chain.append(rf)  # double arithmetic, rounded to fp32 only below (as in `distance <= radius`)
+            rf *= 1.10
+        out[floor] = torch.tensor(chain, dtype=torch.float32)
     return out
 
 
@@ -69,7 +71,10 @@ def select_ball_points(depth: torch.Tensor, K, masks: torch.Tensor, poses: torch
     radii = ball_radii(poses, scales, ratio).to(dev)
     sel_pix = torch.empty((B, H * W), dtype=torch.int32, device=dev)
     n_sel = torch.zeros((B,), dtype=torch.int32, device=dev)
-    scratch = torch.empty((lib.catre_cloud_scratch_bytes(B, H, W),), dtype=torch.uint8, device=dev)
+    key = (B, H, W, str(dev))
+    scratch = _SCRATCH.get(key)
+    if scratch is None:  # reused across calls (stream-ordered, so back-to-back calls on one stream are safe)
+        scratch = _SCRATCH[key] = torch.empty((lib.catre_cloud_scratch_bytes(B, H, W),), dtype=torch.uint8, device=dev)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
     rc = lib.catre_cloud_select(depth_d.data_ptr(), masks_d.data_ptr(), _intr(K), centers.data_ptr(), radii.data_ptr(), N_RADII,
                                 B, H, W, sel_pix.data_ptr(), n_sel.data_ptr(), scratch.data_ptr(), stream)
