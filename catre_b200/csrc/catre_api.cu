@@ -16,6 +16,7 @@
 #include "tc_kernels.cuh"
 #include "tc_fused.cuh"
 #include "cloud_kernels.cuh"
+#include "metrics_kernels.cuh"
 
 using namespace catre;
 
@@ -1088,6 +1089,22 @@ int catre_cloud_gather(const float* depth, const float* intr, const int32_t* sel
   const CloudIntr k{intr[0], intr[1], intr[2], intr[3]};
   cloud_gather_kernel<<<dim3((n_pts + 255) / 256, B), 256, 0, (cudaStream_t)stream>>>(
       depth, k, sel_pix, n_sel, reinterpret_cast<const long long*>(sample_idx), H * W, W, n_pts, pcl);
+  CU_TRY(nullptr, cudaGetLastError());
+  return CATRE_OK;
+}
+
+// ---- pairwise NOCS pose metrics (metrics_kernels.cuh): engine-independent ----
+int catre_pair_metrics(const double* pred_RT, const double* pred_scale, const int32_t* pred_cls, const double* gt_RT,
+                       const double* gt_scale, const int32_t* gt_cls, const int32_t* gt_handle, const int32_t* pair_pred,
+                       const int32_t* pair_gt, int32_t n_pairs, uint32_t sym_class_mask, uint32_t flip_class_mask,
+                       int32_t mug_class, float* iou, float* deg_shift, void* stream) {
+  if (n_pairs == 0) return CATRE_OK;
+  if (n_pairs < 0) return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_pair_metrics: negative n_pairs %d", n_pairs);
+  if (!pred_RT || !pred_scale || !pred_cls || !gt_RT || !gt_scale || !gt_cls || !gt_handle || !pair_pred || !pair_gt || !iou || !deg_shift)
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_pair_metrics: null argument");
+  PairMetricsP p{pred_RT, pred_scale, pred_cls, gt_RT, gt_scale, gt_cls, gt_handle, pair_pred, pair_gt, n_pairs,
+                 sym_class_mask, flip_class_mask, mug_class, iou, deg_shift};
+  pair_metrics_kernel<<<(n_pairs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
   CU_TRY(nullptr, cudaGetLastError());
   return CATRE_OK;
 }

@@ -44,6 +44,8 @@ SYMBOLS = {
                                           ctypes.c_int32, _F, _F, _P, _P]),
     "catre_cloud_gather": (ctypes.c_int, [_F, ctypes.POINTER(ctypes.c_float), _F, _F, _F, ctypes.c_int32, ctypes.c_int32,
                                           ctypes.c_int32, ctypes.c_int32, _F, _P]),
+    "catre_pair_metrics": (ctypes.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32,
+                                          ctypes.c_int32, _F, _F, _P]),
     "catre_last_launch_count": (ctypes.c_int64, [_P]),
     "catre_debug_read": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_size_t]),
     "catre_profile_enable": (ctypes.c_int, [_P, ctypes.c_int32]),

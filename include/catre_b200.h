@@ -146,6 +146,22 @@ int catre_cloud_select(const float* depth, const uint8_t* masks, const float* in
 int catre_cloud_gather(const float* depth, const float* intr, const int32_t* sel_pix, const int32_t* n_sel,
                        const int64_t* sample_idx, int32_t B, int32_t H, int32_t W, int32_t n_pts, float* pcl, void* stream);
 
+/* ---- Pairwise NOCS pose metrics (the step after the path) ------------------------------
+ * Replaces the two nested Python loops of compute_combination_3d_matches (core/catre/engine/test_utils.py:331-352):
+ * for pair t = (pair_pred[t], pair_gt[t]) computes, in fp64 and stored as fp32 like the reference's arrays,
+ *   iou[t]            = compute_3d_iou_new(pred_RT, gt_RT, pred_scale, gt_scale, gt_handle, class names)  (:140-205)
+ *   deg_shift[t][0/1] = compute_combination_RT_degree_cm_symmetry(pred_RT, gt_RT, cbrt(det(gt_RT[:3,:3])), gt class,
+ *                       gt_handle)                                                                       (:208-277)
+ * for any number of images per call (the pair lists are flat).  RTs are row-major 4x4 fp64 [n,16], scales [n,3] fp64,
+ * class ids / handle visibility int32.  Class rules are passed as bit masks over class ids: sym_class_mask = classes
+ * symmetric about y (bottle, bowl, can), flip_class_mask = classes symmetric under a 180-degree y flip (phone,
+ * eggbox, glue; empty for NOCS), mug_class = id of "mug" (symmetric when its handle is not visible), -1 for none.
+ * All pointers are device pointers; engine-independent; errors through catre_last_error(NULL). */
+int catre_pair_metrics(const double* pred_RT, const double* pred_scale, const int32_t* pred_cls, const double* gt_RT,
+                       const double* gt_scale, const int32_t* gt_cls, const int32_t* gt_handle, const int32_t* pair_pred,
+                       const int32_t* pair_gt, int32_t n_pairs, uint32_t sym_class_mask, uint32_t flip_class_mask,
+                       int32_t mug_class, float* iou, float* deg_shift, void* stream);
+
 /* Number of kernels the last forward/refine call launched (bench.py's `gpu_launches`). */
 int64_t catre_last_launch_count(const catre_engine* e);
 

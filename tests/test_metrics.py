@@ -1,0 +1,83 @@
+"""Pairwise NOCS pose metrics: the numpy oracle against golden vectors made by the unmodified
+reference functions (tests/golden/make_golden_metrics.py), the product's host matching against the reference's
+matches, and -- on the GPU -- the CUDA pair kernel against the goldens.
+
+Tolerances: the reference computes in fp64 and stores fp32.  The oracle reproduces the stored values exactly; the
+CUDA kernel's fp64 trig / summation order differs in the last bits, so its fp32 results are compared at 2e-6
+relative (a couple of fp32 ulps) -- and the MATCHES they induce must equal the reference's exactly."""
+import os
+
+import numpy as np
+import pytest
+
+from catre_b200 import metrics
+from oracle import metrics_oracle as mo
+
+GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_metrics.npz")
+SYNSET = ["BG", "bottle", "bowl", "camera", "can", "laptop", "mug"]
+IOU_T, DEG_T, SHIFT_T = [0.25, 0.5, 0.75], [5, 10, 360], [2, 5, 100]
+KEYS = ("gt_cls", "gt_RTs", "gt_scales", "gt_handle", "pred_cls", "pred_RTs", "pred_scales", "pred_scores", "pred_boxes")
+
+
+def images():
+    z = np.load(GOLDEN)
+    out = []
+    for k in range(int(z["n_img"])):
+        im = {n: z[f"{n}_{k}"] for n in KEYS}
+        im.update(overlaps=z[f"overlaps_{k}"], rt=z[f"rt_{k}"], gt_matches=z[f"gt_matches_{k}"],
+                  pred_matches=z[f"pred_matches_{k}"], indices=z[f"indices_{k}"])
+        out.append(im)
+    return out
+
+
+def test_oracle_pair_metrics_match_reference_golden():
+    n_sym = 0
+    for im in images():
+        ov, rt = mo.pair_metrics(im["pred_RTs"], im["pred_scales"], im["pred_cls"], im["gt_RTs"], im["gt_scales"], im["gt_cls"],
+                                 im["gt_handle"], SYNSET)
+        assert np.array_equal(ov, im["overlaps"]) and np.array_equal(rt, im["rt"], equal_nan=True)
+        n_sym += sum(1 for i in im["pred_cls"] for j in im["gt_cls"] if i == j and SYNSET[i] in mo.SYM_Y)
+    assert n_sym > 10  # the symmetric branch is exercised
+
+
+def test_host_matching_equals_reference():
+    """metrics.greedy_matches (product host logic) fed with the reference's own pair metrics must reproduce the
+    reference's gt_matches / pred_matches; so must the oracle's restatement."""
+    seen_match = False
+    for im in images():
+        idx = im["indices"].astype(np.int64)
+        ov, rt = im["overlaps"][idx], im["rt"][idx]
+        for fn in (metrics.greedy_matches, mo.greedy_matches):
+            gm, pm = fn(ov, rt, im["pred_cls"][idx], im["gt_cls"], IOU_T, DEG_T, SHIFT_T)
+            assert np.array_equal(gm, im["gt_matches"]) and np.array_equal(pm, im["pred_matches"])
+        seen_match |= bool((im["pred_matches"] > -1).any())
+    assert seen_match
+    assert metrics.class_rules(SYNSET) == ((1 << 1) | (1 << 2) | (1 << 4), 0, 6)
+
+
+@pytest.mark.gpu
+def test_cuda_pair_metrics_match_reference_golden():
+    ims = images()
+    res = metrics.pair_metrics_batch(ims, SYNSET)  # one launch for all 24 images
+    for im, (ov, rt) in zip(ims, res):
+        assert ov.shape == im["overlaps"].shape and ov.dtype == np.float32
+        assert np.allclose(ov, im["overlaps"], rtol=2e-6, atol=1e-7)
+        assert np.array_equal(np.isnan(rt), np.isnan(im["rt"]))
+        assert np.allclose(rt, im["rt"], rtol=2e-6, atol=2e-5, equal_nan=True)  # theta in degrees: acos near 0 amplifies ulps
+
+
+@pytest.mark.gpu
+def test_cuda_matches_equal_reference():
+    ims = images()
+    for im in ims:  # the reference-signature entry, one image at a time
+        gm, pm, idx = metrics.compute_combination_3d_matches(
+            im["gt_cls"], im["gt_RTs"], im["gt_scales"], im["gt_handle"], SYNSET, im["pred_boxes"], im["pred_cls"],
+            im["pred_scores"], im["pred_RTs"], im["pred_scales"], IOU_T, DEG_T, SHIFT_T)
+        assert np.array_equal(gm, im["gt_matches"]) and np.array_equal(pm, im["pred_matches"])
+        assert np.array_equal(np.asarray(idx, np.int64), im["indices"])
+    batch = [dict(gt_class_ids=im["gt_cls"], gt_RTs=im["gt_RTs"], gt_scales=im["gt_scales"], gt_handle_visibility=im["gt_handle"],
+                  pred_class_ids=im["pred_cls"], pred_scores=im["pred_scores"], pred_RTs=im["pred_RTs"],
+                  pred_scales=im["pred_scales"]) for im in ims]
+    for im, (gm, pm, idx) in zip(ims, metrics.match_images(batch, SYNSET, IOU_T, DEG_T, SHIFT_T)):
+        assert np.array_equal(gm, im["gt_matches"]) and np.array_equal(pm, im["pred_matches"])
+    assert metrics.pair_metrics_batch([], SYNSET) == []
