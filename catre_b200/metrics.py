@@ -135,7 +135,8 @@ def compute_combination_3d_matches(gt_class_ids, gt_RTs, gt_scales, gt_handle_vi
     return gt_m, pred_m, indices
 
 
-def match_images(results: List[Dict[str, np.ndarray]], synset_names, iou_3d_thresholds, degree_thesholds, shift_thesholds):
+def match_images(results: List[Dict[str, np.ndarray]], synset_names, iou_3d_thresholds, degree_thesholds, shift_thesholds,
+                 pair_metrics_fn=None):
     """Batched form: ``results[k]`` has the keys of one entry of the reference's ``final_results`` that the matcher
     reads (gt_class_ids, gt_RTs, gt_scales, gt_handle_visibility, pred_class_ids, pred_scores, pred_RTs, pred_scales).
     One GPU launch for all images, then the per-image host matching.  Returns [(gt_matches, pred_matches, indices)]."""
@@ -145,9 +146,86 @@ def match_images(results: List[Dict[str, np.ndarray]], synset_names, iou_3d_thre
                                 r["pred_scores"], r["pred_RTs"], r["pred_scales"])
         ims.append(im)
         idxs.append(ind)
-    pm = pair_metrics_batch(ims, synset_names)
+    pm = (pair_metrics_fn or pair_metrics_batch)(ims, synset_names)
     out = []
     for im, ind, (ov, rt) in zip(ims, idxs, pm):
         gt_m, pred_m = greedy_matches(ov, rt, im["pred_cls"], im["gt_cls"], iou_3d_thresholds, degree_thesholds, shift_thesholds)
         out.append((gt_m, pred_m, ind))
     return out
+
+
+def compute_ap_from_matches_scores(pred_match, pred_scores, gt_match) -> float:
+    """VOC-style AP of one class / threshold triple (test_utils.py:112-137): predictions by descending score,
+    precision made monotone from the right, summed over the recall steps."""
+    assert pred_match.shape[0] == pred_scores.shape[0]
+    order = np.argsort(pred_scores)[::-1]
+    hit = pred_match[order] > -1
+    precisions = np.cumsum(hit) / (np.arange(len(hit)) + 1)
+    recalls = np.cumsum(hit).astype(np.float32) / len(gt_match)
+    precisions = np.concatenate([[0], precisions, [0]])
+    recalls = np.concatenate([[0], recalls, [1]])
+    for i in range(len(precisions) - 2, -1, -1):
+        precisions[i] = np.maximum(precisions[i], precisions[i + 1])
+    steps = np.where(recalls[:-1] != recalls[1:])[0] + 1
+    return np.sum((recalls[steps] - recalls[steps - 1]) * precisions[steps])
+
+
+def compute_combination_mAP(final_results, synset_names=("BG", "bottle", "bowl", "camera", "can", "laptop", "mug"),
+                            degree_thresholds=(5, 10, 15), shift_thresholds=(0.1, 0.2), iou_3d_thresholds=(0.1,),
+                            pair_metrics_fn=None):
+    """Same contract as the reference's compute_combination_mAP (test_utils.py:392-520), without its printing:
+    returns aps [num_classes + 1, len(degree)+1, len(shift)+1, len(iou)] (last class row = mean over classes
+    1..num_classes-1).  The reference calls the matcher once per (image, class) from Python; here all those
+    sub-problems go through ONE pair-metrics launch (``pair_metrics_fn`` is the pair stage, the CUDA one by
+    default; tests inject the CPU oracle to check the host logic without a GPU)."""
+    synset_names = list(synset_names)
+    num_classes = len(synset_names)
+    deg_list = list(degree_thresholds) + [360]
+    shift_list = list(shift_thresholds) + [100]
+    iou_list = list(iou_3d_thresholds)
+    nd, nt, ns = len(deg_list), len(shift_list), len(iou_list)
+    subs, sub_cls = [], []
+    for result in final_results:
+        gt_class_ids = np.asarray(result["gt_class_ids"]).astype(np.int32)
+        gt_RTs, gt_scales = np.array(result["gt_RTs"]), np.array(result["gt_scales"])
+        gt_handle = np.asarray(result["gt_handle_visibility"])
+        pred_class_ids, pred_scales = np.asarray(result["pred_class_ids"]), np.asarray(result["pred_scales"])
+        pred_scores, pred_RTs = np.asarray(result["pred_scores"]), np.array(result["pred_RTs"])
+        if len(gt_class_ids) == 0 and len(pred_class_ids) == 0:
+            continue
+        for cls_id in range(1, num_classes):  # only same-class predictions / ground truths meet (test_utils.py:431-441)
+            g = gt_class_ids == cls_id if len(gt_class_ids) else np.zeros(0, bool)
+            q = pred_class_ids == cls_id if len(pred_class_ids) else np.zeros(0, bool)
+            n_g = int(g.sum())
+            if synset_names[cls_id] != "mug":
+                handle = np.ones(n_g, dtype=np.int32)  # handle visibility only matters for mugs (:443-448)
+            else:
+                handle = gt_handle[g] if len(gt_class_ids) else np.ones(0)
+            subs.append(dict(gt_class_ids=gt_class_ids[g] if len(gt_class_ids) else np.zeros(0, np.int32),
+                             gt_RTs=gt_RTs[g] if len(gt_class_ids) else np.zeros((0, 4, 4)),
+                             gt_scales=gt_scales[g] if len(gt_class_ids) else np.zeros((0, 3)), gt_handle_visibility=handle,
+                             pred_class_ids=pred_class_ids[q] if len(pred_class_ids) else np.zeros(0, np.int32),
+                             pred_scores=pred_scores[q] if len(pred_class_ids) else np.zeros(0),
+                             pred_RTs=pred_RTs[q] if len(pred_class_ids) else np.zeros((0, 4, 4)),
+                             pred_scales=pred_scales[q] if len(pred_class_ids) else np.zeros((0, 3))))
+            sub_cls.append(cls_id)
+    matched = match_images(subs, synset_names, iou_list, deg_list, shift_list, pair_metrics_fn=pair_metrics_fn)
+    pred_m = [[np.zeros((nd, nt, ns, 0))] for _ in range(num_classes)]
+    gt_m = [[np.zeros((nd, nt, ns, 0))] for _ in range(num_classes)]
+    scores = [[np.zeros((nd, nt, ns, 0))] for _ in range(num_classes)]
+    for sub, cls_id, (gm, pm, ind) in zip(subs, sub_cls, matched):
+        sc = np.asarray(sub["pred_scores"])
+        if len(ind):
+            sc = sc[ind]
+        pred_m[cls_id].append(pm)
+        scores[cls_id].append(np.tile(sc, (nd, nt, ns, 1)))
+        gt_m[cls_id].append(gm)
+    aps = np.zeros((num_classes + 1, nd, nt, ns))
+    for cls_id in range(1, num_classes):
+        pm_all, sc_all, gm_all = (np.concatenate(x[cls_id], axis=-1) for x in (pred_m, scores, gt_m))
+        for s in range(ns):
+            for d in range(nd):
+                for t in range(nt):
+                    aps[cls_id, d, t, s] = compute_ap_from_matches_scores(pm_all[d, t, s, :], sc_all[d, t, s, :], gm_all[d, t, s, :])
+    aps[-1] = np.mean(aps[1:-1], axis=0)
+    return aps

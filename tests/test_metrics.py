@@ -16,6 +16,7 @@ from oracle import metrics_oracle as mo
 GOLDEN = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "golden_metrics.npz")
 SYNSET = ["BG", "bottle", "bowl", "camera", "can", "laptop", "mug"]
 IOU_T, DEG_T, SHIFT_T = [0.25, 0.5, 0.75], [5, 10, 360], [2, 5, 100]
+MAP_DEG, MAP_SHIFT, MAP_IOU = [5, 10, 15], [0.05, 0.10, 0.20], [0.25, 0.5, 0.75]
 KEYS = ("gt_cls", "gt_RTs", "gt_scales", "gt_handle", "pred_cls", "pred_RTs", "pred_scales", "pred_scores", "pred_boxes")
 
 
@@ -81,3 +82,33 @@ def test_cuda_matches_equal_reference():
     for im, (gm, pm, idx) in zip(ims, metrics.match_images(batch, SYNSET, IOU_T, DEG_T, SHIFT_T)):
         assert np.array_equal(gm, im["gt_matches"]) and np.array_equal(pm, im["pred_matches"])
     assert metrics.pair_metrics_batch([], SYNSET) == []
+
+
+def final_results():
+    return [dict(gt_class_ids=im["gt_cls"], gt_RTs=im["gt_RTs"], gt_scales=im["gt_scales"], gt_handle_visibility=im["gt_handle"],
+                 pred_bboxes=im["pred_boxes"], pred_class_ids=im["pred_cls"], pred_scales=im["pred_scales"],
+                 pred_scores=im["pred_scores"], pred_RTs=im["pred_RTs"]) for im in images()]
+
+
+def _oracle_pairs(ims, synset_names):
+    """Test-only pair stage: the CPU oracle in place of the CUDA launch, to check the host logic around it."""
+    return [mo.pair_metrics(im["pred_RTs"], im["pred_scales"], im["pred_cls"], im["gt_RTs"], im["gt_scales"], im["gt_cls"],
+                            im["gt_handle"], synset_names) for im in ims]
+
+
+def test_map_accumulation_equals_reference_host_logic():
+    """compute_combination_mAP's class splitting, score bookkeeping and AP integration, with the pair stage injected
+    from the oracle (no GPU): equals the aps the unmodified reference function returned."""
+    want = np.load(GOLDEN)["aps"]
+    with np.errstate(invalid="ignore"):
+        got = metrics.compute_combination_mAP(final_results(), SYNSET, MAP_DEG, MAP_SHIFT, MAP_IOU, pair_metrics_fn=_oracle_pairs)
+    assert got.shape == want.shape == (8, 4, 4, 3)
+    assert np.array_equal(got, want)
+    assert want[-1].max() > 0.05  # the synthetic images produce non-trivial APs
+
+
+@pytest.mark.gpu
+def test_cuda_map_equals_reference():
+    want = np.load(GOLDEN)["aps"]
+    got = metrics.compute_combination_mAP(final_results(), SYNSET, MAP_DEG, MAP_SHIFT, MAP_IOU)
+    assert np.array_equal(got, want)
