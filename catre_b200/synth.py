@@ -118,6 +118,32 @@ def make_batch(batch: int, n_pts: int, seed: int, round_robin_cls: bool = False,
                fixtures: Optional[Fixtures] = None) -> Batch:
     """SURVEY.md 8(d) "Synthetic inputs".  Everything is drawn from one seeded CPU generator in
     float64 and cast to fp32 at the end."""
+    return _draw(batch, n_pts, seed, round_robin_cls, fixtures)[0]
+
+
+@dataclass
+class TrainTargets:
+    """Ground truth of a synthetic batch (the pose the observed cloud was rendered from), as the training
+    forward takes it (reference: core/catre/engine/engine.py:305-318)."""
+    gt_pose: torch.Tensor  # [B, 3, 4] fp32 = batch["obj_pose"]
+    gt_scale: torch.Tensor  # [B, 3] fp32 = batch["obj_scale"]
+    sym_y: torch.Tensor  # [B] bool: category symmetric about y (reference: ref/nocs.py:138-158, mug handle visible)
+
+
+SYM_Y_CATEGORIES = ("bottle", "bowl", "can")
+
+
+def make_train_batch(batch: int, n_pts: int, seed: int, round_robin_cls: bool = False,
+                     fixtures: Optional[Fixtures] = None):
+    """make_batch plus the ground truth it was rendered from: (Batch, TrainTargets).  Same random stream as
+    make_batch, so the inputs are identical for a given seed."""
+    b, rot_true, t_true, s_true = _draw(batch, n_pts, seed, round_robin_cls, fixtures)
+    sym = torch.tensor([CATEGORIES[int(c)] in SYM_Y_CATEGORIES for c in b.obj_cls], dtype=torch.bool)
+    gt_pose = torch.cat((rot_true, t_true.unsqueeze(2)), dim=2).float().contiguous()
+    return b, TrainTargets(gt_pose=gt_pose, gt_scale=s_true.float().contiguous(), sym_y=sym)
+
+
+def _draw(batch: int, n_pts: int, seed: int, round_robin_cls: bool, fixtures: Optional[Fixtures]):
     fx = fixtures or load_fixtures()
     g = torch.Generator().manual_seed(seed)
     n_inst = fx.init_pose.shape[0]
@@ -156,7 +182,7 @@ def make_batch(batch: int, n_pts: int, seed: int, round_robin_cls: bool = False,
         pcl[b] = cloud[b, sel]
     pcl = pcl + 0.002 * torch.randn(batch, n_pts, 3, generator=g, dtype=torch.float64)
 
-    return Batch(
+    out = Batch(
         pcl=pcl.float().contiguous(),
         prior=resample_prior(prior_full, n_pts).float().contiguous(),
         init_pose=pose0.float().contiguous(),
@@ -164,6 +190,7 @@ def make_batch(batch: int, n_pts: int, seed: int, round_robin_cls: bool = False,
         K=torch.from_numpy(NOCS_REAL_K).expand(batch, 3, 3).contiguous(),
         obj_cls=cls.contiguous(),
     )
+    return out, rot_true, t_true, s_true
 
 
 def known_answer_inputs(fixtures: Optional[Fixtures] = None) -> Batch:
