@@ -68,3 +68,19 @@ def test_losses_and_gradients_match_reference(golden, inputs):
         assert np.allclose(got, z[f"it{it}_loss_values"], rtol=2e-5, atol=1e-7), (got, z[f"it{it}_loss_values"])
         assert np.abs(pose.numpy() - z[f"it{it}_pose"]).max() < 2e-6 and np.abs(scale.numpy() - z[f"it{it}_scale"]).max() < 2e-6
         check_grads(z, it, grads, rtol=2e-4, atol_frac=2e-3)
+
+
+def test_manual_backward_equals_autograd(inputs):
+    """The stage-by-stage backward the CUDA chain follows == autograd, in fp64 (algebra check, all 68 tensors)."""
+    batch, tgt, sym_info = inputs
+    w = {k: v.double() for k, v in synth.load_weights().items()}
+    args = [t.double() for t in (batch.pcl[:4], batch.prior[:4], batch.init_pose[:4], batch.init_scale[:4], batch.K[:4],
+                                 tgt.gt_pose[:4], tgt.gt_scale[:4])]
+    sym = [None if s is None else s.astype(np.float64) for s in sym_info[:4]]
+    pose, scale, losses, grads = to.train_step(w, *args, sym)
+    sv, mgr = to.manual_train_step(w, *args, sym)
+    assert (sv["rot"] - pose[:, :3, :3]).abs().max() < 1e-12 and (sv["s"] - scale).abs().max() < 1e-12
+    assert set(mgr.keys()) == set(grads.keys())
+    for k, g in grads.items():
+        assert mgr[k].shape == g.shape, k
+        assert (mgr[k] - g).abs().max() <= 1e-9 * max(g.abs().max().item(), 1e-6), (k, (mgr[k] - g).abs().max().item(), g.abs().max().item())
