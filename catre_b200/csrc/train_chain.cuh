@@ -1,0 +1,301 @@
+// Host orchestration of the training step: forward with saved activations, losses, backward.
+// Mirrors oracle/train_oracle.py::manual_forward / loss_backward / pose_backward / manual_backward line by line.
+// Written against the small `Ops` interface so the same code drives CUDA launches in libcatre_b200.so and plain
+// loops in the CPU emulation build used by tests/ (CATRE_HOST_EMU; see train_kernels.cuh).
+#pragma once
+#include <stddef.h>
+#include <string.h>
+
+#include "train_kernels.cuh"
+
+namespace catre_train {
+
+// checkpoint order of the 74 tensors (catre_api.cu kWeights)
+enum : int {
+  W_STN = 0, W_CONV1 = 12, W_CONV2 = 14, W_CONV3 = 16, W_CONV4 = 18, W_FSTN = 20, W_ROT_X = 32, W_ROT_Y = 46, W_TS = 60,
+  W_COUNT = 74
+};
+// offsets inside a T-Net block (weight; bias = +1)
+enum : int { T_CONV1 = 0, T_CONV2 = 2, T_CONV3 = 4, T_FC1 = 6, T_FC2 = 8, T_FC3 = 10 };
+// offsets inside a rotation-head block
+enum : int { R_L0 = 2, R_GN0 = 4, R_L3 = 6, R_GN1 = 8, R_NECK = 10, R_CONVP = 12 };
+// offsets inside the ts-head block (base 60)
+enum : int { S_L0 = 2, S_GN0 = 4, S_L3 = 6, S_GN1 = 8, S_FCT = 10, S_FCS = 12 };
+
+// number of elements of checkpoint tensor i for N points per set
+inline size_t weight_numel(int i, int N) {
+  static const int kStn[12] = {64 * 3, 64, 128 * 64, 128, 1024 * 128, 1024, 512 * 1024, 512, 256 * 512, 256, 9 * 256, 9};
+  static const int kFstn[12] = {64 * 64, 64, 128 * 64, 128, 1024 * 128, 1024, 512 * 1024, 512, 256 * 512, 256, 4096 * 256, 4096};
+  static const int kTrunk[8] = {64 * 3, 64, 128 * 64, 128, 512 * 128, 512, 1024 * 512, 1024};
+  static const int kRot[14] = {256, 256, 256 * 1088, 256, 256, 256, 256 * 256, 256, 256, 256, 3 * 256, 3, -1, 1};
+  static const int kTs[14] = {256, 256, 256 * 1091, 256, 256, 256, 256 * 256, 256, 256, 256, 3 * 256, 3, 3 * 256, 3};
+  if (i < 12) return kStn[i];
+  if (i < 20) return kTrunk[i - 12];
+  if (i < 32) return kFstn[i - 20];
+  if (i < 60) { const int v = kRot[(i - 32) % 14]; return v < 0 ? (size_t)2 * N : (size_t)v; }
+  return kTs[i - 60];
+}
+
+struct TrainWs {
+  int maxB = 0, N = 0;
+  // forward, saved
+  float *q, *s64, *s128, *zbuf, *smax, *sfc1, *sfc2, *t3, *qp, *h1, *f64, *f128, *fmax, *ffc1, *ffc2, *t64, *pf, *a128, *a512, *g,
+      *pfmax;
+  int *sarg, *farg, *garg, *pfarg;
+  float *ts_in, *ts_y0, *ts_u0, *ts_y1, *ts_u1, *ts_st0, *ts_st1, *dts;
+  float *cset[2], *ry0[2], *ru0[2], *ry1[2], *rst0[2], *rst1[2], *wsum[2], *ru1, *r6;
+  // loss / backward
+  float *lossp, *losses, *dpose, *d_r6, *d_dts, *tsd_u, *tsd_u0, *ts_din, *gn_m, *gnp_g, *gnp_b;
+  float *dg, *dpfmax, *dpf, *e, *du, *du0, *dcset, *d512, *d128, *d64, *dh1, *dt64, *dfc2, *dfc1, *dmax, *dqp, *dt3;
+  float *partial, *cs_partial;
+  unsigned char* is_sym;
+  float* sym_rots;
+  float* G[W_COUNT];  // gradient arena, checkpoint order
+  size_t grad_floats = 0;
+  static constexpr size_t kPartialFloats = (size_t)4 << 20;
+  static constexpr int kMaxSymRots = 1024;
+};
+
+// Assigns every workspace pointer from `base` (256-byte aligned slices) and returns the bytes needed; with
+// base == nullptr only the size is computed.
+inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base) {
+  size_t off = 0;
+  auto take = [&](size_t bytes) -> char* {
+    char* p = base ? base + off : nullptr;
+    off += (bytes + 255) & ~(size_t)255;
+    return p;
+  };
+  auto F = [&](float*& p, size_t n) { p = reinterpret_cast<float*>(take(n * sizeof(float))); };
+  auto I = [&](int*& p, size_t n) { p = reinterpret_cast<int*>(take(n * sizeof(int))); };
+  const size_t B = maxB, S = 2 * B, R = S * N;
+  w.maxB = maxB; w.N = N;
+  F(w.q, R * 3); F(w.s64, R * 64); F(w.s128, R * 128); F(w.zbuf, R * 1024); F(w.smax, S * 1024); I(w.sarg, S * 1024);
+  F(w.sfc1, S * 512); F(w.sfc2, S * 256); F(w.t3, S * 9); F(w.qp, R * 3); F(w.h1, R * 64); F(w.f64, R * 64); F(w.f128, R * 128);
+  F(w.fmax, S * 1024); I(w.farg, S * 1024); F(w.ffc1, S * 512); F(w.ffc2, S * 256); F(w.t64, S * 4096); F(w.pf, R * 64);
+  F(w.a128, R * 128); F(w.a512, R * 512); F(w.g, S * 1024); I(w.garg, S * 1024); F(w.pfmax, S * 64); I(w.pfarg, S * 64);
+  F(w.ts_in, B * 1091); F(w.ts_y0, B * 256); F(w.ts_u0, B * 256); F(w.ts_y1, B * 256); F(w.ts_u1, B * 256);
+  F(w.ts_st0, B * 64); F(w.ts_st1, B * 64); F(w.dts, B * 6);
+  for (int h = 0; h < 2; ++h) {
+    F(w.cset[h], S * 256); F(w.ry0[h], R * 256); F(w.ru0[h], R * 256); F(w.ry1[h], R * 256); F(w.rst0[h], B * 64);
+    F(w.rst1[h], B * 64); F(w.wsum[h], B * 256);
+  }
+  F(w.ru1, R * 256); F(w.r6, B * 6);
+  F(w.lossp, B * 6); F(w.losses, 8); F(w.dpose, B * 15); F(w.d_r6, B * 6); F(w.d_dts, B * 6); F(w.tsd_u, B * 256);
+  F(w.tsd_u0, B * 256); F(w.ts_din, B * 1091); F(w.gn_m, B * 64); F(w.gnp_g, B * 256); F(w.gnp_b, B * 256);
+  F(w.dg, S * 1024); F(w.dpfmax, S * 64); F(w.dpf, R * 64); F(w.e, B * 256); F(w.du, R * 256); F(w.du0, R * 256);
+  F(w.dcset, S * 256); F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
+  F(w.dfc2, S * 256); F(w.dfc1, S * 512); F(w.dmax, S * 1024); F(w.dqp, R * 3); F(w.dt3, S * 9);
+  F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, (size_t)64 * 4096);
+  w.is_sym = reinterpret_cast<unsigned char*>(take(B));
+  F(w.sym_rots, (size_t)TrainWs::kMaxSymRots * 9);
+  const size_t g0 = off;
+  for (int i = 0; i < W_COUNT; ++i) F(w.G[i], weight_numel(i, N));
+  w.grad_floats = (off - g0) / sizeof(float);
+  return off;
+}
+
+struct TrainIn {
+  const float *pcl, *kps, *pose, *scale, *K, *gt_pose, *gt_scale;  // device (or host in the emulation)
+  int B, n_rots, n_sym, n_nosym;                                    // is_sym / sym_rots already staged in the workspace
+  float *pose_out, *scale_out;
+};
+
+template <class Ops>
+struct Chain {
+  Ops& o;
+  TrainWs& w;
+  const float* const* W;  // the 74 checkpoint tensors
+  int N;
+
+  static unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
+
+  void gemm(const float* A, long long sam, long long sak, const float* Bm, long long sbk, long long sbn, float* C, long long scm,
+            long long scn, int M, int Nn, int K, const float* bias, int relu, int acc, int batch = 1, long long sab = 0,
+            long long sbb = 0, long long scb = 0, long long sbias_b = 0) {
+    GemmP p{};
+    p.A = A; p.sam = sam; p.sak = sak; p.sab = sab; p.B = Bm; p.sbk = sbk; p.sbn = sbn; p.sbb = sbb;
+    p.C = C; p.scm = scm; p.scn = scn; p.scb = scb; p.bias = bias; p.sbias_b = sbias_b;
+    p.M = M; p.N = Nn; p.K = K; p.relu = relu; p.accumulate = acc; p.splits = 1; p.k_per = K; p.partial = w.partial;
+    if (batch == 1 && !bias && !relu && K >= 4096) {  // weight gradients: reduce over many rows -> split K
+      int splits = K / 1024 < 32 ? K / 1024 : 32;
+      while (splits > 1 && (size_t)splits * M * Nn > TrainWs::kPartialFloats) --splits;
+      if (splits > 1) {
+        p.splits = splits;
+        p.k_per = ((K + splits - 1) / splits + 15) & ~15;
+        o.gemm(p, splits);
+        o.run(KSplitReduce{w.partial, C, scm, scn, M, Nn, splits, acc}, cdiv((long long)M * Nn, 256), 1, 1, 256);
+        return;
+      }
+    }
+    o.gemm(p, batch);
+  }
+  // out[rows, C] = act(x[rows, K] W^T + b), W = checkpoint tensor wi [C, K] (+ bias wi+1)
+  void layer(const float* x, int K, int wi, int C, float* out, long long rows, int relu) {
+    gemm(x, K, 1, W[wi], 1, K, out, C, 1, (int)rows, C, K, W[wi + 1], relu, 0);
+  }
+  void colsum(const float* d, long long rows, int C, long long ld, float* out, int acc) {
+    if (rows > 2048) {
+      const long long per = (rows + 63) / 64;
+      o.run(KColSum{d, w.cs_partial, rows, C, per, 0, ld}, cdiv(C, 256), 64, 1, 256);
+      o.run(KColSum{w.cs_partial, out, 64, C, 64, acc, C}, cdiv(C, 256), 1, 1, 256);
+    } else {
+      o.run(KColSum{d, out, rows, C, rows, acc, ld}, cdiv(C, 256), 1, 1, 256);
+    }
+  }
+  // backward of y = x W^T + b for checkpoint tensor wi viewed as [C, ldw] with the K input columns at woff:
+  // dW += dy^T x, db += colsum(dy) (when with_bias), dx (=|+=) dy W.
+  void lin_bwd(int wi, const float* x, int K, const float* dy, int C, long long ldy, long long rows, float* dx, int dx_acc,
+               int ldw = 0, int woff = 0, bool with_bias = true) {
+    if (ldw == 0) ldw = K;
+    gemm(dy, 1, ldy, x, K, 1, w.G[wi] + woff, ldw, 1, C, K, (int)rows, nullptr, 0, 1);
+    if (with_bias) colsum(dy, rows, C, ldy, w.G[wi + 1], 1);
+    if (dx) gemm(dy, ldy, 1, W[wi] + woff, ldw, 1, dx, K, 1, (int)rows, K, C, nullptr, 0, dx_acc);
+  }
+  void relu_mask(float* d, const float* act, long long n) { o.run(KReluMask{d, act, n}, cdiv(n, 256), 1, 1, 256); }
+  void gn_fwd(const float* y, float* st, const float* ga, const float* be, float* u, int B, int P) {
+    o.run(KGnStats{y, st, P}, B, 1, 1, 32);
+    const long long n = (long long)B * P * 256;
+    o.run(KGnGeluFwd{y, st, ga, be, u, P, n}, cdiv(n, 256), 1, 1, 256);
+  }
+  // du -> dy in place; gamma / beta gradients accumulated into G[gi], G[gi + 1]
+  void gn_bwd(float* du, const float* y, const float* st, int gi, int B, int P) {
+    o.run(KGnBwdSums{du, y, st, W[gi], W[gi + 1], w.gn_m, w.gnp_g, w.gnp_b, P}, B, 1, 1, 32);
+    colsum(w.gnp_g, B, 256, 256, w.G[gi], 1);
+    colsum(w.gnp_b, B, 256, 256, w.G[gi + 1], 1);
+    const long long n = (long long)B * P * 256;
+    o.run(KGnBwdApply{du, y, st, W[gi], W[gi + 1], w.gn_m, P, n}, cdiv(n, 256), 1, 1, 256);
+  }
+
+  // T-Net forward (pointnets/pointnet.py:24-41, 57-78)
+  void tnet_fwd(const float* x, int Kin, int wb, int k, float* c64, float* c128, float* vmax, int* arg, float* fc1, float* fc2,
+                float* tout, int S) {
+    const long long R = (long long)S * N;
+    layer(x, Kin, wb + T_CONV1, 64, c64, R, 1);
+    layer(c64, 64, wb + T_CONV2, 128, c128, R, 1);
+    layer(c128, 128, wb + T_CONV3, 1024, w.zbuf, R, 1);
+    o.run(KColMaxArg{w.zbuf, vmax, arg, N, 1024}, cdiv(1024, 256), S, 1, 256);
+    layer(vmax, 1024, wb + T_FC1, 512, fc1, S, 1);
+    layer(fc1, 512, wb + T_FC2, 256, fc2, S, 1);
+    layer(fc2, 256, wb + T_FC3, k * k, tout, S, 0);
+    o.run(KAddEye{tout, k}, cdiv(k, 64), S, 1, 64);
+  }
+  // T-Net backward from d(T) [S, k*k]; d(x) is accumulated into dx_out when given (oracle: tnet_bwd)
+  void tnet_bwd(const float* x, int Kin, int wb, int k, const float* c64, const float* c128, const float* vmax, const int* arg,
+                const float* fc1, const float* fc2, const float* dT, float* dx_out, int S) {
+    const long long R = (long long)S * N;
+    lin_bwd(wb + T_FC3, fc2, 256, dT, k * k, k * k, S, w.dfc2, 0);
+    relu_mask(w.dfc2, fc2, (long long)S * 256);
+    lin_bwd(wb + T_FC2, fc1, 512, w.dfc2, 256, 256, S, w.dfc1, 0);
+    relu_mask(w.dfc1, fc1, (long long)S * 512);
+    lin_bwd(wb + T_FC1, vmax, 1024, w.dfc1, 512, 512, S, w.dmax, 0);
+    o.zero(w.d128, (size_t)R * 128 * sizeof(float));
+    o.run(KMaxBwdDx{w.dmax, vmax, W[wb + T_CONV3], arg, w.d128, N, 1024, 128}, cdiv(128, 128), S, 1, 128);
+    o.run(KMaxBwdDw{w.dmax, vmax, c128, arg, w.G[wb + T_CONV3], w.G[wb + T_CONV3 + 1], S, N, 1024, 128}, cdiv(128, 128), 1024, 1, 128);
+    relu_mask(w.d128, c128, R * 128);
+    lin_bwd(wb + T_CONV2, c64, 64, w.d128, 128, 128, R, w.d64, 0);
+    relu_mask(w.d64, c64, R * 64);
+    lin_bwd(wb + T_CONV1, x, Kin, w.d64, 64, 64, R, dx_out, 1);
+  }
+
+  void forward(const TrainIn& in) {
+    const int B = in.B, S = 2 * B, P = 2 * N;
+    const long long R = (long long)S * N;
+    o.run(KUpdatePoints{in.pcl, in.kps, in.pose, in.scale, w.q, N}, cdiv(N, 256), B, 1, 256);
+    // encoder (pointnets/pointnet.py:97-116), all 2B sets at once
+    tnet_fwd(w.q, 3, W_STN, 3, w.s64, w.s128, w.smax, w.sarg, w.sfc1, w.sfc2, w.t3, S);
+    gemm(w.q, 3, 1, w.t3, 3, 1, w.qp, 3, 1, N, 3, 3, nullptr, 0, 0, S, (long long)N * 3, 9, (long long)N * 3);  // q' = q . T3
+    layer(w.qp, 3, W_CONV1, 64, w.h1, R, 1);
+    tnet_fwd(w.h1, 64, W_FSTN, 64, w.f64, w.f128, w.fmax, w.farg, w.ffc1, w.ffc2, w.t64, S);
+    gemm(w.h1, 64, 1, w.t64, 64, 1, w.pf, 64, 1, N, 64, 64, nullptr, 0, 0, S, (long long)N * 64, 4096, (long long)N * 64);  // pf = h1 . T64
+    layer(w.pf, 64, W_CONV2, 128, w.a128, R, 1);
+    layer(w.a128, 128, W_CONV3, 512, w.a512, R, 1);
+    layer(w.a512, 512, W_CONV4, 1024, w.zbuf, R, 0);  // no ReLU after conv4 (pointnet.py:114)
+    o.run(KColMaxArg{w.zbuf, w.g, w.garg, N, 1024}, cdiv(1024, 256), S, 1, 256);
+    o.run(KColMaxArg{w.pf, w.pfmax, w.pfarg, N, 64}, 1, S, 1, 64);
+    // translation / size head (heads/fc_trans_size_head.py:61-70)
+    o.run(KTsGather{w.g, w.pfmax, in.scale, w.ts_in}, cdiv(1091, 256), B, 1, 256);
+    layer(w.ts_in, 1091, W_TS + S_L0, 256, w.ts_y0, B, 0);
+    gn_fwd(w.ts_y0, w.ts_st0, W[W_TS + S_GN0], W[W_TS + S_GN0 + 1], w.ts_u0, B, 1);
+    layer(w.ts_u0, 256, W_TS + S_L3, 256, w.ts_y1, B, 0);
+    gn_fwd(w.ts_y1, w.ts_st1, W[W_TS + S_GN1], W[W_TS + S_GN1 + 1], w.ts_u1, B, 1);
+    gemm(w.ts_u1, 256, 1, W[W_TS + S_FCT], 1, 256, w.dts, 6, 1, B, 3, 256, W[W_TS + S_FCT + 1], 0, 0);
+    gemm(w.ts_u1, 256, 1, W[W_TS + S_FCS], 1, 256, w.dts + 3, 6, 1, B, 3, 256, W[W_TS + S_FCS + 1], 0, 0);
+    // rotation heads (heads/conv_out_per_rot_head.py:126-140) with the layer-0 split
+    for (int h = 0; h < 2; ++h) {
+      const int rb = h ? W_ROT_Y : W_ROT_X;
+      gemm(w.g, 1024, 1, W[rb + R_L0], 1, 1088, w.cset[h], 256, 1, S, 256, 1024, W[rb + R_L0 + 1], 0, 0);
+      gemm(w.pf, 64, 1, W[rb + R_L0] + 1024, 1, 1088, w.ry0[h], 256, 1, N, 256, 64, w.cset[h], 0, 0, S, (long long)N * 64, 0,
+           (long long)N * 256, 256);
+      gn_fwd(w.ry0[h], w.rst0[h], W[rb + R_GN0], W[rb + R_GN0 + 1], w.ru0[h], B, P);
+      layer(w.ru0[h], 256, rb + R_L3, 256, w.ry1[h], R, 0);
+      gn_fwd(w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1, B, P);
+      o.run(KRotWsum{w.ru1, W[rb + R_CONVP], w.wsum[h], P}, B, 1, 1, 256);
+      o.run(KRotOut{w.wsum[h], W[rb + R_NECK], W[rb + R_NECK + 1], W[rb + R_CONVP], W[rb + R_CONVP + 1], w.r6, P, h}, B, 1, 1, 32);
+    }
+    o.run(KPoseFwd{w.r6, w.dts, in.pose, in.scale, in.K, in.pose_out, in.scale_out, B}, cdiv(B, 64), 1, 1, 64);
+  }
+
+  void loss(const TrainIn& in) {
+    o.run(KLoss{in.pose_out, in.scale_out, in.gt_pose, in.gt_scale, in.kps, w.sym_rots, w.is_sym, w.lossp, w.dpose, in.B, N,
+                in.n_rots, in.n_sym, in.n_nosym}, cdiv(in.B, 32), 1, 1, 32);
+    o.run(KLossSum{w.lossp, w.losses, in.B}, 1, 1, 1, 32);
+  }
+
+  void backward(const TrainIn& in) {
+    const int B = in.B, S = 2 * B, P = 2 * N;
+    const long long R = (long long)S * N;
+    o.zero(w.G[0], w.grad_floats * sizeof(float));
+    o.zero(w.dg, (size_t)S * 1024 * sizeof(float));
+    o.zero(w.dpfmax, (size_t)S * 64 * sizeof(float));
+    o.zero(w.dpf, (size_t)R * 64 * sizeof(float));
+    o.run(KPoseBwd{w.dpose, w.r6, w.dts, in.pose, in.K, w.d_r6, w.d_dts, B}, cdiv(B, 64), 1, 1, 64);
+    // ---- ts head
+    lin_bwd(W_TS + S_FCT, w.ts_u1, 256, w.d_dts, 3, 6, B, w.tsd_u, 0);
+    lin_bwd(W_TS + S_FCS, w.ts_u1, 256, w.d_dts + 3, 3, 6, B, w.tsd_u, 1);
+    gn_bwd(w.tsd_u, w.ts_y1, w.ts_st1, W_TS + S_GN1, B, 1);
+    lin_bwd(W_TS + S_L3, w.ts_u0, 256, w.tsd_u, 256, 256, B, w.tsd_u0, 0);
+    gn_bwd(w.tsd_u0, w.ts_y0, w.ts_st0, W_TS + S_GN0, B, 1);
+    lin_bwd(W_TS + S_L0, w.ts_in, 1091, w.tsd_u0, 256, 256, B, w.ts_din, 0);
+    o.run(KTsScatter{w.ts_din, w.dg, w.dpfmax}, cdiv(1088, 256), B, 1, 256);
+    // ---- rotation heads
+    for (int h = 0; h < 2; ++h) {
+      const int rb = h ? W_ROT_Y : W_ROT_X;
+      const float* wp = W[rb + R_CONVP];
+      o.run(KRotTailBwd{w.d_r6, w.wsum[h], W[rb + R_NECK], wp, w.e, w.G[rb + R_NECK], w.G[rb + R_NECK + 1], w.G[rb + R_CONVP + 1], B, P, h},
+            1, 1, 1, 256);
+      const long long n = (long long)B * P * 256;
+      o.run(KGnGeluFwd{w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1, P, n}, cdiv(n, 256), 1, 1, 256);  // recompute u1
+      o.run(KRotDwp{w.ru1, w.e, w.d_r6, W[rb + R_NECK + 1], w.G[rb + R_CONVP], B, P, h}, cdiv(P, 128), 1, 1, 128);
+      o.run(KRotDu1{wp, w.e, w.du, P, n}, cdiv(n, 256), 1, 1, 256);
+      gn_bwd(w.du, w.ry1[h], w.rst1[h], rb + R_GN1, B, P);
+      lin_bwd(rb + R_L3, w.ru0[h], 256, w.du, 256, 256, R, w.du0, 0);
+      gn_bwd(w.du0, w.ry0[h], w.rst0[h], rb + R_GN0, B, P);
+      // layer 0: point-feature columns per point, global-feature columns once per set
+      o.run(KColSum{w.du0, w.dcset, R, 256, N, 0, 256}, 1, S, 1, 256);  // dcset[s] = sum over the set's points
+      gemm(w.dcset, 1, 256, w.g, 1024, 1, w.G[rb + R_L0], 1088, 1, 256, 1024, S, nullptr, 0, 1);
+      gemm(w.du0, 1, 256, w.pf, 64, 1, w.G[rb + R_L0] + 1024, 1088, 1, 256, 64, (int)R, nullptr, 0, 1);
+      colsum(w.dcset, S, 256, 256, w.G[rb + R_L0 + 1], 1);
+      gemm(w.dcset, 256, 1, W[rb + R_L0], 1088, 1, w.dg, 1024, 1, S, 1024, 256, nullptr, 0, 1);
+      gemm(w.du0, 256, 1, W[rb + R_L0] + 1024, 1088, 1, w.dpf, 64, 1, (int)R, 64, 256, nullptr, 0, 1);
+    }
+    // ---- encoder
+    o.run(KScatterMax{w.dpfmax, w.pfarg, w.dpf, N, 64}, 1, S, 1, 64);
+    o.zero(w.d512, (size_t)R * 512 * sizeof(float));
+    o.run(KMaxBwdDx{w.dg, nullptr, W[W_CONV4], w.garg, w.d512, N, 1024, 512}, cdiv(512, 128), S, 1, 128);
+    o.run(KMaxBwdDw{w.dg, nullptr, w.a512, w.garg, w.G[W_CONV4], w.G[W_CONV4 + 1], S, N, 1024, 512}, cdiv(512, 128), 1024, 1, 128);
+    relu_mask(w.d512, w.a512, R * 512);
+    lin_bwd(W_CONV3, w.a128, 128, w.d512, 512, 512, R, w.d128, 0);
+    relu_mask(w.d128, w.a128, R * 128);
+    lin_bwd(W_CONV2, w.pf, 64, w.d128, 128, 128, R, w.dpf, 1);
+    // pf = h1 . T64 per set:  dh1 = dpf . T64^T,  dT64 = h1^T . dpf
+    gemm(w.dpf, 64, 1, w.t64, 1, 64, w.dh1, 64, 1, N, 64, 64, nullptr, 0, 0, S, (long long)N * 64, 4096, (long long)N * 64);
+    gemm(w.h1, 1, 64, w.dpf, 64, 1, w.dt64, 64, 1, 64, 64, N, nullptr, 0, 0, S, (long long)N * 64, (long long)N * 64, 4096);
+    tnet_bwd(w.h1, 64, W_FSTN, 64, w.f64, w.f128, w.fmax, w.farg, w.ffc1, w.ffc2, w.dt64, w.dh1, S);
+    relu_mask(w.dh1, w.h1, R * 64);
+    lin_bwd(W_CONV1, w.qp, 3, w.dh1, 64, 64, R, w.dqp, 0);
+    gemm(w.q, 1, 3, w.dqp, 3, 1, w.dt3, 3, 1, 3, 3, N, nullptr, 0, 0, S, (long long)N * 3, (long long)N * 3, 9);  // dT3 = q^T . dq'
+    tnet_bwd(w.q, 3, W_STN, 3, w.s64, w.s128, w.smax, w.sarg, w.sfc1, w.sfc2, w.dt3, nullptr, S);
+  }
+};
+
+}  // namespace catre_train

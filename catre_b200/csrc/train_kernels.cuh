@@ -1,0 +1,604 @@
+// Training step of the CATRE refiner: kernels of the forward-with-saved-activations, the
+// loss and the backward chain.  All fp32 FMA on CUDA cores, row-major point-major [rows, channels] buffers; the
+// stage-by-stage algebra is the one of oracle/train_oracle.py::manual_forward / manual_backward (verified there
+// against autograd).
+//
+// Every kernel except the shared-memory GEMM is a functor whose operator() is the work of ONE thread with no
+// inter-thread communication (Idx carries the block / thread coordinates).  On the GPU the generic
+// `tk_run<K><<<grid, block>>>(k)` wrapper calls it with blockIdx / threadIdx; with CATRE_HOST_EMU defined the same
+// source compiles with a plain C++ compiler and tests/emu runs the grid as nested loops, so indexing and the host
+// orchestration (train_chain.cuh) are checked on the CPU against the oracle.  The emulation build is test
+// infrastructure; the product library never contains it.
+#pragma once
+#include <math.h>
+#include <stdint.h>
+
+#ifdef CATRE_HOST_EMU
+#define TK_HD inline
+#else
+#define TK_HD __host__ __device__ __forceinline__
+#endif
+
+namespace catre_train {
+
+struct Idx {
+  int bx, by, bz, tx;  // block coordinates, thread in block
+  int nt;              // threads per block
+};
+
+TK_HD float tk_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.70710678118654752f)); }
+TK_HD float tk_gelu_grad(float x) {
+  return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * expf(-0.5f * x * x) * 0.39894228040143268f;
+}
+TK_HD float tk_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
+
+// ---- re-posed points (core/catre/engine/batching.py:127-140 / batch_test.py:78-97): set 2b = pcl_b - t_b,
+//      set 2b+1 = R_b (s_b * kps_b).  grid (ceil(N / nt), B)
+struct KUpdatePoints {
+  const float *pcl, *kps, *pose, *scale;
+  float* q;
+  int N;
+  TK_HD void operator()(const Idx& i) const {
+    const int n = i.bx * i.nt + i.tx, b = i.by;
+    if (n >= N) return;
+    const float* P = pose + (size_t)b * 12;
+    const float* s = scale + (size_t)b * 3;
+    const float* x = pcl + ((size_t)b * N + n) * 3;
+    const float* k = kps + ((size_t)b * N + n) * 3;
+    float* qo = q + ((size_t)(2 * b) * N + n) * 3;
+    float* qk = q + ((size_t)(2 * b + 1) * N + n) * 3;
+    const float k0 = k[0] * s[0], k1 = k[1] * s[1], k2 = k[2] * s[2];
+    for (int r = 0; r < 3; ++r) {
+      qo[r] = x[r] - P[r * 4 + 3];
+      qk[r] = P[r * 4 + 0] * k0 + P[r * 4 + 1] * k1 + P[r * 4 + 2] * k2;
+    }
+  }
+};
+
+// ---- generic strided, batched GEMM: C(m,n,z) = act(sum_k A(m,k,z) B(k,n,z) + bias(n,z)) [+ C].  One thread per
+//      output element.  grid (ceil(M / (nt / 64)), ceil(N / 64), batch * splits); nt a multiple of 64.
+//      With splits > 1 (batch must be 1) block z sums k in [z * k_per, (z+1) * k_per) into partial[z][m][n].
+struct GemmP {
+  const float* A; long long sam, sak, sab;
+  const float* B; long long sbk, sbn, sbb;
+  float* C; long long scm, scn, scb;
+  const float* bias; long long sbias_b;  // bias[n + z * sbias_b] or nullptr
+  int M, N, K;
+  int relu, accumulate;
+  int splits; int k_per; float* partial;
+};
+struct KGemmNaive {
+  GemmP p;
+  TK_HD void operator()(const Idx& i) const {
+    const int n = i.by * 64 + (i.tx & 63);
+    const int m = i.bx * (i.nt >> 6) + (i.tx >> 6);
+    if (m >= p.M || n >= p.N) return;
+    int z = i.bz, k0 = 0, k1 = p.K;
+    if (p.splits > 1) { k0 = z * p.k_per; k1 = k0 + p.k_per < p.K ? k0 + p.k_per : p.K; z = 0; }
+    const float* a = p.A + (long long)z * p.sab + (long long)m * p.sam;
+    const float* b = p.B + (long long)z * p.sbb + (long long)n * p.sbn;
+    float acc = 0.0f;
+    for (int k = k0; k < k1; ++k) acc = fmaf(a[(long long)k * p.sak], b[(long long)k * p.sbk], acc);
+    if (p.splits > 1) { p.partial[((size_t)i.bz * p.M + m) * p.N + n] = acc; return; }
+    if (p.bias) acc += p.bias[n + (long long)z * p.sbias_b];
+    if (p.relu) acc = acc > 0.0f ? acc : 0.0f;
+    float* c = p.C + (long long)z * p.scb + (long long)m * p.scm + (long long)n * p.scn;
+    *c = p.accumulate ? *c + acc : acc;
+  }
+};
+// fixed-order sum of the split-K partials.  grid (ceil(M * N / nt))
+struct KSplitReduce {
+  const float* partial; float* C; long long scm, scn; int M, N, splits, accumulate;
+  TK_HD void operator()(const Idx& i) const {
+    const long long e = (long long)i.bx * i.nt + i.tx;
+    if (e >= (long long)M * N) return;
+    float acc = 0.0f;
+    for (int z = 0; z < splits; ++z) acc += partial[(size_t)z * M * N + e];
+    float* c = C + (e / N) * scm + (e % N) * scn;
+    *c = accumulate ? *c + acc : acc;
+  }
+};
+
+// ---- column max + arg-max over the N points of each set (first index wins ties, like torch.max on the CPU).
+//      z [S, N, C] -> vmax [S, C], arg [S, C].  grid (ceil(C / nt), S)
+struct KColMaxArg {
+  const float* z; float* vmax; int* arg; int N, C;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.bx * i.nt + i.tx, s = i.by;
+    if (c >= C) return;
+    const float* p = z + (size_t)s * N * C + c;
+    float best = p[0]; int bi = 0;
+    for (int n = 1; n < N; ++n) { const float v = p[(size_t)n * C]; if (v > best) { best = v; bi = n; } }
+    vmax[(size_t)s * C + c] = best; arg[(size_t)s * C + c] = bi;
+  }
+};
+
+// t[s, :] += I_k   (pointnets/pointnet.py:37-40, 72-77).  grid (ceil(k / nt), S)
+struct KAddEye {
+  float* t; int k;
+  TK_HD void operator()(const Idx& i) const {
+    const int d = i.bx * i.nt + i.tx;
+    if (d < k) t[(size_t)i.by * k * k + (size_t)d * k + d] += 1.0f;
+  }
+};
+
+// d[e] = act[e] > 0 ? d[e] : 0   (ReLU backward).  grid (ceil(n / nt))
+struct KReluMask {
+  float* d; const float* act; long long n;
+  TK_HD void operator()(const Idx& i) const {
+    const long long e = (long long)i.bx * i.nt + i.tx;
+    if (e < n && !(act[e] > 0.0f)) d[e] = 0.0f;
+  }
+};
+
+// out[chunk, c] = sum over the rows of the chunk of d[r, c]  (bias gradients; two stages keep it deterministic).
+// grid (ceil(C / nt), chunks); rows_per = rows per chunk.  With accumulate the result is added to out.
+struct KColSum {
+  const float* d; float* out; long long rows; int C; long long rows_per; int accumulate; long long ld;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.bx * i.nt + i.tx;
+    if (c >= C) return;
+    const long long r0 = (long long)i.by * rows_per;
+    const long long r1 = r0 + rows_per < rows ? r0 + rows_per : rows;
+    float acc = 0.0f;
+    for (long long r = r0; r < r1; ++r) acc += d[r * ld + c];
+    float* o = out + (size_t)i.by * C + c;
+    *o = accumulate ? *o + acc : acc;
+  }
+};
+
+// ---- sparse backward of `max over points of [relu](x W^T + b)` (oracle: max_layer_bwd).  Only the arg-max row of
+//      each (set, channel) receives a gradient.
+// dx[(s, arg[s,c]), k] += d[s,c] W[c,k] for c = 0..C-1 in order; thread (s, k) owns column k of set s, so there are
+// no races and the order is fixed.  dx must be zero on entry.  grid (ceil(K / nt), S)
+struct KMaxBwdDx {
+  const float *dmax, *relu_max, *W; const int* arg; float* dx; int N, C, K;
+  TK_HD void operator()(const Idx& i) const {
+    const int k = i.bx * i.nt + i.tx, s = i.by;
+    if (k >= K) return;
+    for (int c = 0; c < C; ++c) {
+      float d = dmax[(size_t)s * C + c];
+      if (relu_max && !(relu_max[(size_t)s * C + c] > 0.0f)) d = 0.0f;
+      if (d == 0.0f) continue;
+      float* o = dx + ((size_t)s * N + arg[(size_t)s * C + c]) * K + k;
+      *o = fmaf(d, W[(size_t)c * K + k], *o);
+    }
+  }
+};
+// dW[c, k] += sum_s d[s,c] x[(s, arg[s,c]), k];  db[c] += sum_s d[s,c].  grid (ceil(K / nt), C)
+struct KMaxBwdDw {
+  const float *dmax, *relu_max, *x; const int* arg; float *dW, *db; int S, N, C, K;
+  TK_HD void operator()(const Idx& i) const {
+    const int k = i.bx * i.nt + i.tx, c = i.by;
+    if (k >= K) return;
+    float acc = 0.0f, accb = 0.0f;
+    for (int s = 0; s < S; ++s) {
+      float d = dmax[(size_t)s * C + c];
+      if (relu_max && !(relu_max[(size_t)s * C + c] > 0.0f)) d = 0.0f;
+      acc = fmaf(d, x[((size_t)s * N + arg[(size_t)s * C + c]) * K + k], acc);
+      accb += d;
+    }
+    dW[(size_t)c * K + k] += acc;
+    if (k == 0) db[c] += accb;
+  }
+};
+// dpf[(s, arg[s,c]), c] += dpfmax[s, c]  (max_n pointfeat of the ts-head input).  grid (ceil(C / nt), S)
+struct KScatterMax {
+  const float* dmax; const int* arg; float* dx; int N, C;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.bx * i.nt + i.tx, s = i.by;
+    if (c < C) dx[((size_t)s * N + arg[(size_t)s * C + c]) * C + c] += dmax[(size_t)s * C + c];
+  }
+};
+
+// ---- GroupNorm (32 groups of 8 channels over the P points of an object; P = 1 for the ts head), eps 1e-5,
+//      biased variance, fp64 accumulation.  y [B, P, 256] -> st [B, 32, 2] = (mean, rstd).  grid (B), nt = 32
+struct KGnStats {
+  const float* y; float* st; int P;
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx, g = i.tx;
+    if (g >= 32) return;
+    const float* p = y + (size_t)b * P * 256 + g * 8;
+    double s = 0.0, ss = 0.0;
+    for (int n = 0; n < P; ++n)
+      for (int j = 0; j < 8; ++j) { const double v = p[(size_t)n * 256 + j]; s += v; ss += v * v; }
+    const double cnt = 8.0 * P, mu = s / cnt;
+    double var = ss / cnt - mu * mu;
+    if (var < 0.0) var = 0.0;
+    st[((size_t)b * 32 + g) * 2 + 0] = (float)mu;
+    st[((size_t)b * 32 + g) * 2 + 1] = (float)(1.0 / sqrt(var + 1e-5));
+  }
+};
+// u = gelu(gamma (y - mu) rstd + beta).  grid (ceil(B * P * 256 / nt))
+struct KGnGeluFwd {
+  const float *y, *st, *gamma, *beta; float* u; int P; long long n;
+  TK_HD void operator()(const Idx& i) const {
+    const long long e = (long long)i.bx * i.nt + i.tx;
+    if (e >= n) return;
+    const int c = (int)(e & 255);
+    const long long b = e / ((long long)P * 256);
+    const float* s = st + ((size_t)b * 32 + (c >> 3)) * 2;
+    u[e] = tk_gelu(gamma[c] * ((y[e] - s[0]) * s[1]) + beta[c]);
+  }
+};
+// backward, pass 1 (oracle: _gn_gelu_backward): with xhat = (y - mu) rstd, dn = du gelu'(gamma xhat + beta),
+// g = dn gamma:  m [B, 32, 2] = group means of (g, g xhat);  dgam [B, 256] = sum_p dn xhat, dbet [B, 256] = sum_p dn.
+// grid (B), nt = 32
+struct KGnBwdSums {
+  const float *du, *y, *st, *gamma, *beta; float *m, *dgam, *dbet; int P;
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx, g = i.tx;
+    if (g >= 32) return;
+    const float mu = st[((size_t)b * 32 + g) * 2], rstd = st[((size_t)b * 32 + g) * 2 + 1];
+    double s1 = 0.0, s2 = 0.0, dga[8], dbe[8];
+    for (int j = 0; j < 8; ++j) dga[j] = dbe[j] = 0.0;
+    const size_t base = (size_t)b * P * 256 + g * 8;
+    for (int n = 0; n < P; ++n)
+      for (int j = 0; j < 8; ++j) {
+        const size_t e = base + (size_t)n * 256 + j;
+        const float xh = (y[e] - mu) * rstd, ga = gamma[g * 8 + j];
+        const float dn = du[e] * tk_gelu_grad(ga * xh + beta[g * 8 + j]);
+        s1 += (double)(dn * ga); s2 += (double)(dn * ga) * xh;
+        dga[j] += (double)dn * xh; dbe[j] += dn;
+      }
+    m[((size_t)b * 32 + g) * 2 + 0] = (float)(s1 / (8.0 * P));
+    m[((size_t)b * 32 + g) * 2 + 1] = (float)(s2 / (8.0 * P));
+    for (int j = 0; j < 8; ++j) { dgam[(size_t)b * 256 + g * 8 + j] = (float)dga[j]; dbet[(size_t)b * 256 + g * 8 + j] = (float)dbe[j]; }
+  }
+};
+// pass 2: dy = rstd (g - m1 - xhat m2), written over du.  grid (ceil(B * P * 256 / nt))
+struct KGnBwdApply {
+  float* du; const float *y, *st, *gamma, *beta, *m; int P; long long n;
+  TK_HD void operator()(const Idx& i) const {
+    const long long e = (long long)i.bx * i.nt + i.tx;
+    if (e >= n) return;
+    const int c = (int)(e & 255);
+    const long long b = e / ((long long)P * 256);
+    const size_t gi = ((size_t)b * 32 + (c >> 3)) * 2;
+    const float xh = (y[e] - st[gi]) * st[gi + 1];
+    const float g = du[e] * tk_gelu_grad(gamma[c] * xh + beta[c]) * gamma[c];
+    du[e] = st[gi + 1] * (g - m[gi] - xh * m[gi + 1]);
+  }
+};
+
+// ---- rotation-head tail (conv_out_per_rot_head.py:136-139 by linearity): wsum[b, c] = sum_p wp[p] u1[b, p, c].
+//      grid (B), nt = 256
+struct KRotWsum {
+  const float *u1, *wp; float* wsum; int P;
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx, c = i.tx;
+    if (c >= 256) return;
+    const float* u = u1 + (size_t)b * P * 256 + c;
+    float acc = 0.0f;
+    for (int p = 0; p < P; ++p) acc = fmaf(wp[p], u[(size_t)p * 256], acc);
+    wsum[(size_t)b * 256 + c] = acc;
+  }
+};
+// r6[b, 3h + j] = Wn[j, :] . wsum[b, :] + bn[j] sum_p wp[p] + bp.  grid (B), nt >= 3
+struct KRotOut {
+  const float *wsum, *wn, *bn, *wp, *bp; float* r6; int P, h;
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx, j = i.tx;
+    if (j >= 3) return;
+    float acc = 0.0f, sw = 0.0f;
+    for (int c = 0; c < 256; ++c) acc = fmaf(wn[j * 256 + c], wsum[(size_t)b * 256 + c], acc);
+    for (int p = 0; p < P; ++p) sw += wp[p];
+    r6[(size_t)b * 6 + 3 * h + j] = acc + bn[j] * sw + bp[0];
+  }
+};
+// small gradients of the tail (oracle: manual_backward, "conv_p / neck"): e[b, c] = sum_j Wn[j, c] dr[b, j];
+// dWn[j, c] += sum_b dr[b, j] wsum[b, c]; dbn[j] += sum_b dr[b, j] sum_p wp; dbp += sum_{b, j} dr[b, j].
+// grid (1), nt = 256 (thread = channel c)
+struct KRotTailBwd {
+  const float *d_r6, *wsum, *wn, *wp; float *e, *dwn, *dbn, *dbp; int B, P, h;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.tx;
+    if (c >= 256) return;
+    float gw[3] = {0.0f, 0.0f, 0.0f};
+    for (int b = 0; b < B; ++b) {
+      const float* dr = d_r6 + (size_t)b * 6 + 3 * h;
+      e[(size_t)b * 256 + c] = wn[c] * dr[0] + wn[256 + c] * dr[1] + wn[512 + c] * dr[2];
+      for (int j = 0; j < 3; ++j) gw[j] = fmaf(dr[j], wsum[(size_t)b * 256 + c], gw[j]);
+    }
+    for (int j = 0; j < 3; ++j) dwn[j * 256 + c] += gw[j];
+    if (c < 3) {
+      float sw = 0.0f, sd = 0.0f;
+      for (int p = 0; p < P; ++p) sw += wp[p];
+      for (int b = 0; b < B; ++b) sd += d_r6[(size_t)b * 6 + 3 * h + c];
+      dbn[c] += sd * sw;
+    }
+    if (c == 3) {
+      float sd = 0.0f;
+      for (int b = 0; b < B; ++b) for (int j = 0; j < 3; ++j) sd += d_r6[(size_t)b * 6 + 3 * h + j];
+      dbp[0] += sd;
+    }
+  }
+};
+// du1[b, p, c] = wp[p] e[b, c]  (rank one).  grid (ceil(B * P * 256 / nt))
+struct KRotDu1 {
+  const float *wp, *e; float* du; int P; long long n;
+  TK_HD void operator()(const Idx& i) const {
+    const long long x = (long long)i.bx * i.nt + i.tx;
+    if (x >= n) return;
+    const int c = (int)(x & 255);
+    const long long bp = x >> 8;
+    du[x] = wp[bp % P] * e[(size_t)(bp / P) * 256 + c];
+  }
+};
+// dwp[p] += sum_b (u1[b, p, :] . e[b, :] + dr[b, :] . bn).  grid (ceil(P / nt))
+struct KRotDwp {
+  const float *u1, *e, *d_r6, *bn; float* dwp; int B, P, h;
+  TK_HD void operator()(const Idx& i) const {
+    const int p = i.bx * i.nt + i.tx;
+    if (p >= P) return;
+    float acc = 0.0f;
+    for (int b = 0; b < B; ++b) {
+      const float* u = u1 + ((size_t)b * P + p) * 256;
+      const float* eb = e + (size_t)b * 256;
+      float a = 0.0f;
+      for (int c = 0; c < 256; ++c) a = fmaf(u[c], eb[c], a);
+      const float* dr = d_r6 + (size_t)b * 6 + 3 * h;
+      acc += a + dr[0] * bn[0] + dr[1] * bn[1] + dr[2] * bn[2];
+    }
+    dwp[p] += acc;
+  }
+};
+
+// ---- ts-head input gather / gradient scatter (CATRE_disR_shared.py:66-82): ts_in[b] = [g(2b) | pfmax(2b) | s_b]
+//      grid (ceil(1091 / nt), B)
+struct KTsGather {
+  const float *g, *pfmax, *scale; float* ts_in;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.bx * i.nt + i.tx, b = i.by;
+    if (c >= 1091) return;
+    float v;
+    if (c < 1024) v = g[(size_t)(2 * b) * 1024 + c];
+    else if (c < 1088) v = pfmax[(size_t)(2 * b) * 64 + (c - 1024)];
+    else v = scale[(size_t)b * 3 + (c - 1088)];
+    ts_in[(size_t)b * 1091 + c] = v;
+  }
+};
+// dg[2b, :] = din[b, :1024], dpfmax[2b, :] = din[b, 1024:1088] (the prior sets' rows stay zero; the initial scale is
+// detached).  grid (ceil(1088 / nt), B)
+struct KTsScatter {
+  const float* din; float *dg, *dpfmax;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.bx * i.nt + i.tx, b = i.by;
+    if (c >= 1088) return;
+    const float v = din[(size_t)b * 1091 + c];
+    if (c < 1024) dg[(size_t)(2 * b) * 1024 + c] = v;
+    else dpfmax[(size_t)(2 * b) * 64 + (c - 1024)] = v;
+  }
+};
+
+// ---- rot6d Gram-Schmidt + pose update (core/utils/rot_reps.py:34-55, pose_scale_from_delta_init.py:47-95).
+//      grid (ceil(B / nt))
+struct KPoseFwd {
+  const float *r6, *dts, *pose_in, *scale_in, *K; float *pose_out, *scale_out; int B;
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx * i.nt + i.tx;
+    if (b >= B) return;
+    const float* r = r6 + (size_t)b * 6;
+    const float* P = pose_in + (size_t)b * 12;
+    const float* d = dts + (size_t)b * 6;
+    float na = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); na = na > 1e-12f ? na : 1e-12f;
+    const float x[3] = {r[0] / na, r[1] / na, r[2] / na};
+    float c[3] = {x[1] * r[5] - x[2] * r[4], x[2] * r[3] - x[0] * r[5], x[0] * r[4] - x[1] * r[3]};
+    float nc = sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]); nc = nc > 1e-12f ? nc : 1e-12f;
+    const float z[3] = {c[0] / nc, c[1] / nc, c[2] / nc};
+    const float y[3] = {z[1] * x[2] - z[2] * x[1], z[2] * x[0] - z[0] * x[2], z[0] * x[1] - z[1] * x[0]};
+    float* O = pose_out + (size_t)b * 12;
+    for (int r_ = 0; r_ < 3; ++r_)
+      for (int cc = 0; cc < 3; ++cc)  // R' = dR . R, dR = [x y z] as columns
+        O[r_ * 4 + cc] = x[r_] * P[0 * 4 + cc] + y[r_] * P[1 * 4 + cc] + z[r_] * P[2 * 4 + cc];
+    const float fx = K[(size_t)b * 9 + 0], fy = K[(size_t)b * 9 + 4];
+    const float tz = P[2 * 4 + 3], zn = d[2] * tz;
+    O[0 * 4 + 3] = zn * (d[0] / fx + P[0 * 4 + 3] / tz);
+    O[1 * 4 + 3] = zn * (d[1] / fy + P[1 * 4 + 3] / tz);
+    O[2 * 4 + 3] = zn;
+    for (int j = 0; j < 3; ++j) scale_out[(size_t)b * 3 + j] = scale_in[(size_t)b * 3 + j] + d[3 + j];
+  }
+};
+
+// ---- losses of the shipped LOSS_CFG and their gradients w.r.t. the predicted (R, t, s)
+//      (CATRE_disR_shared.py:168-288, core/catre/losses/pm_loss.py:110-130, rot_loss.py:45-58,
+//      core/utils/pose_utils.py:472-528; oracle: catre_loss / loss_backward).  One thread per object.
+//      lossp [B, 6] = this object's share of (PM_R, rot, yaxis_rot, trans_xy, trans_z, scale);
+//      dpose [B, 15] = d/d(R' row-major 9, t' 3, s' 3).  grid (ceil(B / nt))
+struct KLoss {
+  const float *pose, *scale, *gt_pose, *gt_scale, *kps, *sym_rots; const unsigned char* is_sym;
+  float *lossp, *dpose; int B, N, n_rots, n_sym, n_nosym;
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx * i.nt + i.tx;
+    if (b >= B) return;
+    const float* Pp = pose + (size_t)b * 12;
+    const float* Gp = gt_pose + (size_t)b * 12;
+    float R[9], G[9], Gs[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { R[r * 3 + c] = Pp[r * 4 + c]; G[r * 3 + c] = Gp[r * 4 + c]; Gs[r * 3 + c] = G[r * 3 + c]; }
+    const bool sym = is_sym[b] != 0;
+    if (sym) {  // closest symmetric ground truth: largest clamped cosine of the rotation error, strict improvement only
+      float tr = 0.0f;
+      for (int e = 0; e < 9; ++e) tr += R[e] * G[e];
+      float best = fminf(1.0f, fmaxf(-1.0f, 0.5f * ((tr <= 3.0f ? tr : 3.0f) - 1.0f)));
+      for (int k = 0; k < n_rots; ++k) {
+        const float* S = sym_rots + (size_t)k * 9;
+        float C[9];
+        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C[r * 3 + c] = G[r * 3] * S[c] + G[r * 3 + 1] * S[3 + c] + G[r * 3 + 2] * S[6 + c];
+        float t2 = 0.0f;
+        for (int e = 0; e < 9; ++e) t2 += R[e] * C[e];
+        const float cs = fminf(1.0f, fmaxf(-1.0f, 0.5f * ((t2 <= 3.0f ? t2 : 3.0f) - 1.0f)));
+        if (cs > best) { best = cs; for (int e = 0; e < 9; ++e) Gs[e] = C[e]; }
+      }
+    }
+    const float* s = scale + (size_t)b * 3;
+    const float* sg = gt_scale + (size_t)b * 3;
+    float dR[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ds[3] = {0, 0, 0};
+    double pm = 0.0;
+    const float inv_bn = 1.0f / ((float)B * (float)N);
+    for (int n = 0; n < N; ++n) {
+      const float* k = kps + ((size_t)b * N + n) * 3;
+      const float sk[3] = {k[0] * s[0], k[1] * s[1], k[2] * s[2]};
+      const float gk[3] = {k[0] * sg[0], k[1] * sg[1], k[2] * sg[2]};
+      float de[3];
+      for (int r = 0; r < 3; ++r) {
+        const float diff = (R[r * 3] * sk[0] + R[r * 3 + 1] * sk[1] + R[r * 3 + 2] * sk[2]) -
+                           (Gs[r * 3] * gk[0] + Gs[r * 3 + 1] * gk[1] + Gs[r * 3 + 2] * gk[2]);
+        pm += fabsf(diff);
+        de[r] = tk_sign(diff) * inv_bn;
+        for (int c = 0; c < 3; ++c) dR[r * 3 + c] += de[r] * sk[c];
+      }
+      for (int c = 0; c < 3; ++c) ds[c] += (R[c] * de[0] + R[3 + c] * de[1] + R[6 + c] * de[2]) * k[c];
+    }
+    float* L = lossp + (size_t)b * 6;
+    L[0] = (float)(pm / ((double)B * N));  // 3 * mean over B*N*3
+    L[1] = L[2] = 0.0f;
+    if (sym) {
+      float a = 0.0f;
+      for (int r = 0; r < 3; ++r) { const float d = R[r * 3 + 1] - G[r * 3 + 1]; a += fabsf(d); dR[r * 3 + 1] += tk_sign(d) / (3.0f * n_sym); }
+      L[2] = a / (3.0f * n_sym);
+    } else {
+      float tr = 0.0f;
+      for (int e = 0; e < 9; ++e) { tr += R[e] * G[e]; dR[e] += -G[e] / (4.0f * n_nosym); }
+      L[1] = (3.0f - tr) * 0.25f / n_nosym;
+    }
+    float* D = dpose + (size_t)b * 15;
+    for (int e = 0; e < 9; ++e) D[e] = dR[e];
+    const float dx = Pp[3] - Gp[3], dy = Pp[7] - Gp[7], dz = Pp[11] - Gp[11];
+    L[3] = (fabsf(dx) + fabsf(dy)) / (2.0f * B);
+    L[4] = fabsf(dz) / (float)B;
+    D[9] = tk_sign(dx) / (2.0f * B); D[10] = tk_sign(dy) / (2.0f * B); D[11] = tk_sign(dz) / (float)B;
+    float ls = 0.0f;
+    for (int c = 0; c < 3; ++c) { const float d = s[c] - sg[c]; ls += fabsf(d); D[12 + c] = ds[c] + tk_sign(d) / (3.0f * B); }
+    L[5] = ls / (3.0f * B);
+  }
+};
+// losses[j] = sum_b lossp[b, j] in object order.  grid (1), nt >= 6
+struct KLossSum {
+  const float* lossp; float* losses; int B;
+  TK_HD void operator()(const Idx& i) const {
+    if (i.tx >= 6) return;
+    float a = 0.0f;
+    for (int b = 0; b < B; ++b) a += lossp[(size_t)b * 6 + i.tx];
+    losses[i.tx] = a;
+  }
+};
+
+// ---- backward of the pose update and the Gram-Schmidt (oracle: pose_backward): dpose [B, 15] -> d_r6 [B, 6],
+//      d_dts [B, 6] = (d Delta_t, d Delta_s).  grid (ceil(B / nt))
+struct KPoseBwd {
+  const float *dpose, *r6, *dts, *pose_in, *K; float *d_r6, *d_dts; int B;
+  TK_HD static void cross(const float* a, const float* b, float* o) {
+    o[0] = a[1] * b[2] - a[2] * b[1]; o[1] = a[2] * b[0] - a[0] * b[2]; o[2] = a[0] * b[1] - a[1] * b[0];
+  }
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx * i.nt + i.tx;
+    if (b >= B) return;
+    const float* D = dpose + (size_t)b * 15;
+    const float* P = pose_in + (size_t)b * 12;
+    const float* d = dts + (size_t)b * 6;
+    const float* r = r6 + (size_t)b * 6;
+    // d(dR) = dR' . R^T  (R' = dR . R); columns gx, gy, gz of d(dR)
+    float g[9];
+    for (int rr = 0; rr < 3; ++rr)
+      for (int cc = 0; cc < 3; ++cc) g[rr * 3 + cc] = D[rr * 3] * P[cc * 4] + D[rr * 3 + 1] * P[cc * 4 + 1] + D[rr * 3 + 2] * P[cc * 4 + 2];
+    float gx[3] = {g[0], g[3], g[6]}, gy[3] = {g[1], g[4], g[7]}, gz[3] = {g[2], g[5], g[8]};
+    float na = sqrtf(r[0] * r[0] + r[1] * r[1] + r[2] * r[2]); na = na > 1e-12f ? na : 1e-12f;
+    const float x[3] = {r[0] / na, r[1] / na, r[2] / na};
+    const float bv[3] = {r[3], r[4], r[5]};
+    float c[3]; cross(x, bv, c);
+    float nc = sqrtf(c[0] * c[0] + c[1] * c[1] + c[2] * c[2]); nc = nc > 1e-12f ? nc : 1e-12f;
+    const float z[3] = {c[0] / nc, c[1] / nc, c[2] / nc};
+    float t[3];
+    cross(x, gy, t); for (int j = 0; j < 3; ++j) gz[j] += t[j];   // y = z x x
+    cross(gy, z, t); for (int j = 0; j < 3; ++j) gx[j] += t[j];
+    const float zg = z[0] * gz[0] + z[1] * gz[1] + z[2] * gz[2];
+    float gc[3]; for (int j = 0; j < 3; ++j) gc[j] = (gz[j] - z[j] * zg) / nc;
+    cross(bv, gc, t); for (int j = 0; j < 3; ++j) gx[j] += t[j];  // c = x x b
+    float gb[3]; cross(gc, x, gb);
+    const float xg = x[0] * gx[0] + x[1] * gx[1] + x[2] * gx[2];
+    float* o = d_r6 + (size_t)b * 6;
+    for (int j = 0; j < 3; ++j) { o[j] = (gx[j] - x[j] * xg) / na; o[3 + j] = gb[j]; }
+    const float fx = K[(size_t)b * 9], fy = K[(size_t)b * 9 + 4];
+    const float tx = P[3], ty = P[7], tz = P[11], zn = d[2] * tz;
+    const float dzt = D[11] + D[9] * (d[0] / fx + tx / tz) + D[10] * (d[1] / fy + ty / tz);
+    float* q = d_dts + (size_t)b * 6;
+    q[0] = D[9] * zn / fx; q[1] = D[10] * zn / fy; q[2] = dzt * tz;
+    q[3] = D[12]; q[4] = D[13]; q[5] = D[14];
+  }
+};
+
+}  // namespace catre_train
+
+#ifndef CATRE_HOST_EMU
+namespace catre_train {
+template <class KF>
+__global__ void tk_run(KF k) {
+  k(Idx{(int)blockIdx.x, (int)blockIdx.y, (int)blockIdx.z, (int)threadIdx.x, (int)blockDim.x});
+}
+
+// Shared-memory tiled version of KGemmNaive (same parameters and results up to summation order): 64 x 64 output
+// tile, 16-deep k slabs, 256 threads with a 4 x 4 register tile each.  grid (ceil(M/64), ceil(N/64), batch * splits)
+__global__ void __launch_bounds__(256) tk_gemm_tiled(GemmP p) {
+  __shared__ float As[16][64 + 4];
+  __shared__ float Bs[16][64 + 4];
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
+  const int m0 = blockIdx.x * 64, n0 = blockIdx.y * 64;
+  int z = blockIdx.z, k0 = 0, k1 = p.K;
+  if (p.splits > 1) { k0 = z * p.k_per; k1 = min(k0 + p.k_per, p.K); z = 0; }
+  const float* A = p.A + (long long)z * p.sab;
+  const float* Bm = p.B + (long long)z * p.sbb;
+  float acc[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
+  const bool a_kfast = p.sak == 1, b_nfast = p.sbn == 1;
+  for (int kb = k0; kb < k1; kb += 16) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int idx = tid + l * 256;
+      int m, k;
+      if (a_kfast) { m = idx >> 4; k = idx & 15; } else { m = idx & 63; k = idx >> 6; }
+      float v = 0.0f;
+      if (m0 + m < p.M && kb + k < k1) v = A[(long long)(m0 + m) * p.sam + (long long)(kb + k) * p.sak];
+      As[k][m] = v;
+      int n, k2;
+      if (b_nfast) { k2 = idx >> 6; n = idx & 63; } else { k2 = idx & 15; n = idx >> 4; }
+      v = 0.0f;
+      if (n0 + n < p.N && kb + k2 < k1) v = Bm[(long long)(kb + k2) * p.sbk + (long long)(n0 + n) * p.sbn];
+      Bs[k2][n] = v;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int kk = 0; kk < 16; ++kk) {
+      float a[4], b[4];
+#pragma unroll
+      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty * 4 + i];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx * 4 + j];
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+    }
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int m = m0 + ty * 4 + i;
+    if (m >= p.M) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int n = n0 + tx * 4 + j;
+      if (n >= p.N) continue;
+      float v = acc[i][j];
+      if (p.splits > 1) { p.partial[((size_t)blockIdx.z * p.M + m) * p.N + n] = v; continue; }
+      if (p.bias) v += p.bias[n + (long long)z * p.sbias_b];
+      if (p.relu) v = fmaxf(v, 0.0f);
+      float* c = p.C + (long long)z * p.scb + (long long)m * p.scm + (long long)n * p.scn;
+      *c = p.accumulate ? *c + v : v;
+    }
+  }
+}
+}  // namespace catre_train
+#endif

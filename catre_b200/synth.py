@@ -150,7 +150,7 @@ def _draw(batch: int, n_pts: int, seed: int, round_robin_cls: bool, fixtures: Op
     if round_robin_cls:
         # config 5: force category b % 6, drawing without replacement inside each category
         idx = torch.empty(batch, dtype=torch.int64)
-        for c in range(len(CATEGORIES)):
+        for c in range(min(len(CATEGORIES), batch)):
             slots = torch.arange(c, batch, len(CATEGORIES))
             pool = torch.nonzero(fx.obj_cls == c).flatten()
             pick = pool[torch.randperm(pool.numel(), generator=g)[: slots.numel()]]

@@ -1,0 +1,78 @@
+"""The training-step kernel chain (catre_b200/csrc/train_kernels.cuh + train_chain.cuh), compiled for the CPU with
+CATRE_HOST_EMU (every kernel functor runs as loops over its grid), against the training oracle: checks the kernels'
+indexing and the host orchestration without a GPU.  The emulation library is test infrastructure, built into a
+temporary directory; the product library never contains it."""
+import ctypes
+import os
+import shutil
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+from catre_b200 import synth
+from oracle import catre_oracle as co
+from oracle import train_oracle as to
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+NAMES = list(np.load(synth.WEIGHTS_NPZ).files)  # checkpoint order
+
+
+@pytest.fixture(scope="module")
+def emu(tmp_path_factory):
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    out = str(tmp_path_factory.mktemp("emu") / "libtrain_emu.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-DCATRE_HOST_EMU", "-o", out,
+                           os.path.join(HERE, "emu", "train_emu.cpp")])
+    return ctypes.CDLL(out)
+
+
+def _ptr(a):
+    return a.ctypes.data_as(ctypes.c_void_p)
+
+
+def run_emu(lib, w, batch, tgt, sym_rots, pose, scale):
+    B, N = batch.pcl.shape[0], batch.pcl.shape[1]
+    wa = [np.ascontiguousarray(w[k].numpy(), dtype=np.float32) for k in NAMES]
+    ga = [np.zeros_like(a) for a in wa]
+    wp = (ctypes.c_void_p * 74)(*[_ptr(a) for a in wa])
+    gp = (ctypes.c_void_p * 74)(*[_ptr(a) for a in ga])
+    f = lambda t: np.ascontiguousarray(t.numpy(), dtype=np.float32)
+    arrs = [f(batch.pcl), f(batch.prior), f(pose), f(scale), f(batch.K), f(tgt.gt_pose), f(tgt.gt_scale)]
+    is_sym = np.ascontiguousarray(tgt.sym_y.numpy().astype(np.uint8))
+    rots = np.ascontiguousarray(sym_rots, dtype=np.float32)
+    pose_out, scale_out = np.zeros((B, 3, 4), np.float32), np.zeros((B, 3), np.float32)
+    losses, launches = np.zeros(6, np.float32), ctypes.c_long(0)
+    rc = lib.emu_train_step(wp, B, N, *[_ptr(a) for a in arrs], _ptr(is_sym), _ptr(rots), len(rots), _ptr(pose_out), _ptr(scale_out),
+                            _ptr(losses), gp, ctypes.byref(launches))
+    assert rc == 0
+    return pose_out, scale_out, losses, dict(zip(NAMES, ga)), launches.value
+
+
+LOSS_ORDER = ("loss_PM_R", "loss_rot", "loss_yaxis_rot", "loss_trans_xy", "loss_trans_z", "loss_scale")
+
+
+@pytest.mark.parametrize("B,N,seed", [(3, 64, 21), (2, 128, 22)])
+def test_emulated_chain_matches_oracle(emu, B, N, seed):
+    torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
+    w = co.resize_conv_p(synth.load_weights(), N)
+    batch, tgt = synth.make_train_batch(B, N, seed, round_robin_cls=True)  # classes 0, 1, 2: symmetric and asymmetric
+    sym_rots = to.y_symmetry_rotations()
+    sym_info = [sym_rots if s else None for s in tgt.sym_y]
+    pose, scale = batch.init_pose, batch.init_scale
+    p_ref, s_ref, l_ref, g_ref = to.train_step(w, batch.pcl, batch.prior, pose, scale, batch.K, tgt.gt_pose, tgt.gt_scale, sym_info)
+    p, s, losses, grads, launches = run_emu(emu, w, batch, tgt, sym_rots, pose, scale)
+    assert launches > 100
+    assert np.abs(p - p_ref.numpy()).max() < 2e-5 and np.abs(s - s_ref.numpy()).max() < 2e-5
+    for i, k in enumerate(LOSS_ORDER):
+        assert abs(losses[i] - l_ref.get(k, 0.0)) <= 2e-5 * max(1.0, abs(l_ref.get(k, 0.0))), (k, losses[i], l_ref.get(k))
+    for k in NAMES:
+        if k in to.UNUSED:
+            assert not grads[k].any(), k
+            continue
+        want = g_ref[k].numpy()
+        scale_k = max(np.abs(want).max(), 1e-8)
+        err = np.abs(grads[k] - want).max() / scale_k
+        assert err < 2e-4, (k, err, scale_k)
