@@ -95,9 +95,13 @@ inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base) {
 }
 
 struct TrainIn {
-  const float *pcl, *kps, *pose, *scale, *K, *gt_pose, *gt_scale;  // device (or host in the emulation)
+  // device pointers (host in the emulation).  Points: either the raw clouds (pcl = observed cloud in the camera
+  // frame, kps = normalised prior; re-posed here like batching.py:127-140), or -- when x_pm / tfd_pm are given -- the
+  // already re-posed sets the reference's forward receives (kps is then only the loss's obj_kps).
+  const float *pcl, *kps, *pose, *scale, *K, *gt_pose, *gt_scale;
   int B, n_rots, n_sym, n_nosym;                                    // is_sym / sym_rots already staged in the workspace
   float *pose_out, *scale_out;
+  const float *x_pm = nullptr, *tfd_pm = nullptr;
 };
 
 template <class Ops>
@@ -200,7 +204,8 @@ struct Chain {
   void forward(const TrainIn& in) {
     const int B = in.B, S = 2 * B, P = 2 * N;
     const long long R = (long long)S * N;
-    o.run(KUpdatePoints{in.pcl, in.kps, in.pose, in.scale, w.q, N}, cdiv(N, 256), B, 1, 256);
+    if (in.x_pm) o.run(KInterleave{in.x_pm, in.tfd_pm, w.q, N}, cdiv(3 * N, 256), B, 1, 256);
+    else o.run(KUpdatePoints{in.pcl, in.kps, in.pose, in.scale, w.q, N}, cdiv(N, 256), B, 1, 256);
     // encoder (pointnets/pointnet.py:97-116), all 2B sets at once
     tnet_fwd(w.q, 3, W_STN, 3, w.s64, w.s128, w.smax, w.sarg, w.sfc1, w.sfc2, w.t3, S);
     gemm(w.q, 3, 1, w.t3, 3, 1, w.qp, 3, 1, N, 3, 3, nullptr, 0, 0, S, (long long)N * 3, 9, (long long)N * 3);  // q' = q . T3

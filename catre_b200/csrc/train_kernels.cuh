@@ -55,6 +55,18 @@ struct KUpdatePoints {
   }
 };
 
+// the same two sets when the caller has already re-posed the points (the reference's forward takes x = pcl - t and
+// tfd_kps = R (s * kps), CATRE_disR_shared.py:40-56): q[2b] = x_pm[b], q[2b+1] = tfd_pm[b].  grid (ceil(3 N / nt), B)
+struct KInterleave {
+  const float *x_pm, *tfd_pm; float* q; int N;
+  TK_HD void operator()(const Idx& i) const {
+    const int e = i.bx * i.nt + i.tx, b = i.by;
+    if (e >= 3 * N) return;
+    q[(size_t)(2 * b) * N * 3 + e] = x_pm[(size_t)b * N * 3 + e];
+    q[(size_t)(2 * b + 1) * N * 3 + e] = tfd_pm[(size_t)b * N * 3 + e];
+  }
+};
+
 // ---- generic strided, batched GEMM: C(m,n,z) = act(sum_k A(m,k,z) B(k,n,z) + bias(n,z)) [+ C].  One thread per
 //      output element.  grid (ceil(M / (nt / 64)), ceil(N / 64), batch * splits); nt a multiple of 64.
 //      With splits > 1 (batch must be 1) block z sums k in [z * k_per, (z+1) * k_per) into partial[z][m][n].
