@@ -17,6 +17,7 @@
 #include "tc_fused.cuh"
 #include "cloud_kernels.cuh"
 #include "metrics_kernels.cuh"
+#include "train_chain.cuh"
 
 using namespace catre;
 
@@ -131,6 +132,13 @@ struct catre_engine {
   int32_t* st_cls = nullptr;
   int st_prior_rows = 0;  // rows ([N,3] each) st_prior holds: max(max_batch, 16), so a small class table always fits
   static constexpr int kMaxHostIter = 16;
+
+  // ---- training step: workspace grown on demand, weights refreshed device-to-device
+  catre_train::TrainWs tws;
+  char* tws_mem = nullptr;
+  int tws_maxB = 0;
+  std::map<std::string, bool> dw_dirty;  // tensors refreshed by catre_train_set_weight since the last pack
+  bool train_naive_gemm = false;         // CATRE_TRAIN_NAIVE_GEMM=1: one-thread-per-output GEMM (debug reference)
 
   // ---- accounting
   int64_t launches = 0;
@@ -602,6 +610,41 @@ int check_ready(catre_engine* e, int B) {
 
 }  // namespace
 
+// ---- training step: CUDA launches behind train_chain.cuh's Ops interface
+namespace {
+struct CudaTrainOps {
+  cudaStream_t s;
+  bool naive;
+  int64_t launches = 0;
+  cudaError_t err = cudaSuccess;
+  void note(cudaError_t st) { if (err == cudaSuccess && st != cudaSuccess) err = st; }
+  template <class KF>
+  void run(const KF& k, unsigned gx, unsigned gy, unsigned gz, unsigned nt) {
+    if (gx == 0 || gy == 0 || gz == 0) return;
+    catre_train::tk_run<KF><<<dim3(gx, gy, gz), nt, 0, s>>>(k);
+    ++launches;
+    note(cudaPeekAtLastError());
+  }
+  void zero(void* p, size_t bytes) { note(cudaMemsetAsync(p, 0, bytes, s)); }
+  void gemm(const catre_train::GemmP& p, int bz) {
+    if (p.M <= 0 || p.N <= 0 || bz <= 0) return;
+    if (naive) {
+      run(catre_train::KGemmNaive{p}, (unsigned)((p.M + 3) / 4), (unsigned)((p.N + 63) / 64), (unsigned)bz, 256);
+    } else {
+      catre_train::tk_gemm_tiled<<<dim3((unsigned)((p.M + 63) / 64), (unsigned)((p.N + 63) / 64), (unsigned)bz), 256, 0, s>>>(p);
+      ++launches;
+      note(cudaPeekAtLastError());
+    }
+  }
+};
+
+int weight_index(const char* name) {
+  for (int i = 0; i < kNumWeights; ++i)
+    if (strcmp(kWeights[i].name, name) == 0) return i;
+  return -1;
+}
+}  // namespace
+
 // ================================================================================================
 extern "C" {
 
@@ -730,6 +773,7 @@ void catre_destroy(catre_engine* e) {
   if (!e) return;
   cudaSetDevice(e->cfg.device);
   for (void* p : e->dev_allocs) cudaFree(p);
+  if (e->tws_mem) cudaFree(e->tws_mem);
   if (e->side) cudaStreamDestroy(e->side);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -757,6 +801,7 @@ int catre_set_weight(catre_engine* e, const char* name, const float* data, const
   std::vector<float>& h = e->hw[name];
   h.resize(n);
   CU_TRY(e, cudaMemcpy(h.data(), data, n * sizeof(float), cudaMemcpyDefault));
+  e->dw_dirty.erase(name);
   e->packed = false;
   return CATRE_OK;
 }
@@ -768,6 +813,12 @@ int catre_pack(catre_engine* e, void* stream) {
   for (int i = 0; i < kNumWeights; ++i)
     if (!e->hw.count(kWeights[i].name))
       return fail(e, CATRE_ERR_NOT_PACKED, "weight '%s' has not been set", kWeights[i].name);
+  // tensors refreshed on the device by catre_train_set_weight: pull them back so the packed copies derive from them
+  for (auto& kv : e->dw_dirty) {
+    std::vector<float>& h = e->hw.at(kv.first);
+    CU_TRY(e, cudaMemcpy(h.data(), e->dw.at(kv.first), h.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  e->dw_dirty.clear();
   // packed weights are re-created on every pack; previous device copies stay allocated until destroy
   // only when shapes change (they cannot), so reuse buffers if present
   int rc = 0;
@@ -1106,6 +1157,92 @@ int catre_pair_metrics(const double* pred_RT, const double* pred_scale, const in
                  sym_class_mask, flip_class_mask, mug_class, iou, deg_shift};
   pair_metrics_kernel<<<(n_pairs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
   CU_TRY(nullptr, cudaGetLastError());
+  return CATRE_OK;
+}
+
+// ---- training step ---------------------------------------------------------------------
+int catre_train_set_weight(catre_engine* e, const char* name, const float* src_dev, void* stream) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  if (!name || !src_dev) return fail(e, CATRE_ERR_INVALID_ARG, "catre_train_set_weight: null argument");
+  const int i = weight_index(name);
+  if (i < 0) return fail(e, CATRE_ERR_UNKNOWN_WEIGHT, "unknown weight '%s'", name);
+  auto it = e->dw.find(name);
+  if (it == e->dw.end() || !it->second)
+    return fail(e, CATRE_ERR_NOT_PACKED, "catre_train_set_weight needs one earlier catre_pack (it allocates the device copies)");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  CU_TRY(e, cudaMemcpyAsync(it->second, src_dev, catre_train::weight_numel(i, e->N) * sizeof(float), cudaMemcpyDefault,
+                            (cudaStream_t)stream));
+  e->dw_dirty[name] = true;
+  e->packed = false;
+  return CATRE_OK;
+}
+
+int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, const float* obj_kps, const float* pose,
+                     const float* scale, const float* K, const float* gt_pose, const float* gt_scale,
+                     const uint8_t* is_sym_host, const float* sym_rots_host, int32_t n_sym_rots, int32_t B, float* out_pose,
+                     float* out_scale, float* out_losses, void* stream) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  if (B == 0) return CATRE_OK;
+  if (B < 0) return fail(e, CATRE_ERR_INVALID_ARG, "negative batch %d", B);
+  if (!x_pm || !tfd_pm || !obj_kps || !pose || !scale || !K || !gt_pose || !gt_scale || !is_sym_host || !out_pose || !out_scale ||
+      !out_losses)
+    return fail(e, CATRE_ERR_INVALID_ARG, "catre_train_step: null argument");
+  if (n_sym_rots < 0 || n_sym_rots > catre_train::TrainWs::kMaxSymRots || (n_sym_rots > 0 && !sym_rots_host))
+    return fail(e, CATRE_ERR_INVALID_ARG, "catre_train_step: n_sym_rots %d outside [0, %d] or null rotations", n_sym_rots,
+                catre_train::TrainWs::kMaxSymRots);
+  if (e->dw.size() != (size_t)kNumWeights)
+    return fail(e, CATRE_ERR_NOT_PACKED, "catre_train_step needs the 74 tensors set and one catre_pack");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  if (B > e->tws_maxB) {  // (re)allocate the workspace; not on the steady-state path
+    CU_TRY(e, cudaStreamSynchronize(s));
+    if (e->tws_mem) { CU_TRY(e, cudaFree(e->tws_mem)); e->tws_mem = nullptr; e->tws_maxB = 0; }
+    catre_train::TrainWs probe;
+    const size_t bytes = catre_train::ws_layout(probe, B, e->N, nullptr);
+    void* mem = nullptr;
+    cudaError_t st = cudaMalloc(&mem, bytes);
+    if (st != cudaSuccess) {
+      cudaGetLastError();
+      return fail(e, CATRE_ERR_CUDA, "training workspace for %d objects (%.1f MB): %s", B, bytes / 1048576.0, cudaGetErrorString(st));
+    }
+    e->tws_mem = static_cast<char*>(mem);
+    catre_train::ws_layout(e->tws, B, e->N, e->tws_mem);
+    e->tws_maxB = B;
+  }
+  catre_train::TrainWs& w = e->tws;
+  int n_sym = 0;
+  for (int b = 0; b < B; ++b) n_sym += is_sym_host[b] != 0;
+  if (n_sym > 0 && n_sym_rots == 0)
+    return fail(e, CATRE_ERR_INVALID_ARG, "catre_train_step: symmetric objects but no symmetry rotations");
+  CU_TRY(e, cudaMemcpyAsync(w.is_sym, is_sym_host, (size_t)B, cudaMemcpyHostToDevice, s));
+  if (n_sym_rots) CU_TRY(e, cudaMemcpyAsync(w.sym_rots, sym_rots_host, (size_t)n_sym_rots * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
+  const float* Wp[catre_train::W_COUNT];
+  for (int i = 0; i < kNumWeights; ++i) Wp[i] = e->dw.at(kWeights[i].name);
+  const char* env = getenv("CATRE_TRAIN_NAIVE_GEMM");
+  CudaTrainOps ops{s, e->train_naive_gemm || (env && env[0] == '1')};
+  catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
+  catre_train::TrainIn in{nullptr, obj_kps, pose, scale, K, gt_pose, gt_scale, B, n_sym_rots, n_sym, B - n_sym, out_pose, out_scale};
+  in.x_pm = x_pm; in.tfd_pm = tfd_pm;
+  chain.forward(in);
+  chain.loss(in);
+  chain.backward(in);
+  ops.note(cudaMemcpyAsync(out_losses, w.losses, 6 * sizeof(float), cudaMemcpyDefault, s));
+  e->launches = ops.launches;
+  if (ops.err != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e, CATRE_ERR_CUDA, "catre_train_step: %s", cudaGetErrorString(ops.err));
+  }
+  return CATRE_OK;
+}
+
+int catre_train_grad(catre_engine* e, const char* name, float* dst, void* stream) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  if (!name || !dst) return fail(e, CATRE_ERR_INVALID_ARG, "catre_train_grad: null argument");
+  const int i = weight_index(name);
+  if (i < 0) return fail(e, CATRE_ERR_UNKNOWN_WEIGHT, "unknown weight '%s'", name);
+  if (!e->tws_mem) return fail(e, CATRE_ERR_NOT_PACKED, "catre_train_grad before any catre_train_step");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  CU_TRY(e, cudaMemcpyAsync(dst, e->tws.G[i], catre_train::weight_numel(i, e->N) * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
   return CATRE_OK;
 }
 

@@ -16,16 +16,71 @@ tensors, and a missing library or device raises.
 Additionally (not in the reference): ``CatreB200.refine(...)`` runs the evaluator's whole K-loop
 (batch_updater_test + forward, catre_evaluator.py:292-311, batch_test.py:63-97) in one call.
 
-Training (``do_loss=True``) is out of scope for this engine and raises.
+Training (``do_loss=True``): the forward runs the engine's fused training step
+(``catre_train_step``: forward with saved activations, the shipped LOSS_CFG's losses and the hand-derived backward
+of their sum, all CUDA) and returns ``(out_dict, loss_dict)`` like the reference (CATRE_disR_shared.py:125-165).
+The loss tensors are tied to the parameters through a small autograd bridge, so the reference's training loop
+(``sum(loss_dict.values()).backward(); optimizer.step()``, core/catre/engine/engine.py:318-352) works unchanged:
+``backward()`` copies the engine's gradients into ``param.grad``.  The bridge assumes what that loop does -- every
+loss enters the total with the same weight (a uniform factor such as an AMP loss scale is fine); per-term weights
+raise.  There is still no PyTorch implementation of the network in this package.
 """
 from __future__ import annotations
 
-from typing import Any, Dict, Optional, Tuple
+from typing import Any, Dict, List, Optional, Tuple
 
+import numpy as np
 import torch
 import torch.nn as nn
 
 from . import engine as _engine
+
+# tensors of the shipped config that never see a gradient (the heads' unused `norm`; the reference leaves their
+# .grad None, core/catre/models/heads/conv_out_per_rot_head.py:96-101, fc_trans_size_head.py:33-36)
+UNUSED_PARAMS = ("rot_head.rot_head_x.norm.weight", "rot_head.rot_head_x.norm.bias", "rot_head.rot_head_y.norm.weight",
+                 "rot_head.rot_head_y.norm.bias", "ts_head.norm.weight", "ts_head.norm.bias")
+
+# loss configuration the training step implements (configs/catre/NOCS_REAL/aug05_..._120e.py:115-134 over
+# configs/_base_/catre_base.py); anything else is refused
+_REQUIRED_LOSS_CFG = {
+    "PM_LOSS_SYM": True, "PM_NORM_BY_EXTENT": False, "PM_R_ONLY": True, "PM_WITH_SCALE": True, "PM_LW": 1.0,
+    "PM_LOSS_TYPE": "L1", "PM_USE_BBOX": False,
+    "ROT_LOSS_TYPE": "angular", "ROT_LW": 1.0, "ROT_YAXIS_LOSS_TYPE": "L1",
+    "TRANS_LOSS_TYPE": "L1", "TRANS_LOSS_DISENTANGLE": True, "TRANS_LW": 1.0,
+    "SCALE_LOSS_TYPE": "L1", "SCALE_LW": 1.0,
+}
+
+
+class _LossBridge(torch.autograd.Function):
+    """Ties the engine's loss values to the module's parameters: backward() hands out the gradients the fused
+    training step already computed for d(sum of losses)."""
+
+    @staticmethod
+    def forward(ctx, losses, present, model, names, *params):
+        ctx.model, ctx.names, ctx.present = model, names, present
+        ctx.step_id = model._train_step_id
+        return losses.clone()
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        model = ctx.model
+        if ctx.step_id != model._train_step_id:
+            raise RuntimeError("catre_b200: backward() of an older training forward; the engine keeps the gradients of "
+                               "the latest do_loss=True forward only (the reference's loop backpropagates each iteration "
+                               "before the next forward, core/catre/engine/engine.py:318-352)")
+        g = grad_out[ctx.present]
+        scale = g[0]
+        if not bool((g == scale).all()):
+            raise NotImplementedError("catre_b200: the fused training step backpropagates the plain sum of the losses; "
+                                      f"got per-term weights {g.tolist()}")
+        eng = model._engine
+        grads: List[Optional[torch.Tensor]] = []
+        for name, p in zip(ctx.names, model.parameters()):
+            if name in UNUSED_PARAMS or not p.requires_grad:
+                grads.append(None)
+                continue
+            grads.append(eng.train_grad(name, torch.empty_like(p, memory_format=torch.contiguous_format)) * scale)
+        return (None, None, None, None, *grads)
 
 # (name, shape); -1 = n_obs + n_prior (conv_p is tied to the point count,
 # core/catre/models/heads/conv_out_per_rot_head.py:112)
@@ -163,6 +218,8 @@ class CatreB200(nn.Module):
             node.register_parameter(parts[-1], nn.Parameter(init))
         self._engine: Optional[_engine.Engine] = None
         self._packed_key = None
+        self._train_versions: Optional[Dict[str, Tuple[int, int]]] = None  # per tensor (version, data_ptr) the engine's training copy holds
+        self._train_step_id = 0
 
     # ---- engine plumbing -----------------------------------------------------------------------
     def _weights_key(self):
@@ -184,25 +241,70 @@ class CatreB200(nn.Module):
         if key != self._packed_key:
             self._engine.load_weights({k: v for k, v in self.state_dict().items()})
             self._packed_key = key
+            self._train_versions = {n: (p._version, p.data_ptr()) for n, p in self.named_parameters()}
         return self._engine
 
+    def _engine_for_training(self, device: torch.device) -> _engine.Engine:
+        """The engine with its fp32 training copies in step with the parameters: one full load the first time, then a
+        device-to-device refresh of exactly the tensors the optimiser changed (no host round trip per step)."""
+        if device.type != "cuda":
+            raise _engine.CatreError(f"catre_b200 runs on CUDA (sm_100a) only; there is no CPU path. Got tensors on {device}.")
+        idx = device.index if device.index is not None else torch.cuda.current_device()
+        if self._engine is None or self._engine.device != idx or self._train_versions is None:
+            self.engine(device)  # create + full load (allocates the engine's device copies)
+        eng = self._engine
+        for n, p in self.named_parameters():
+            cur = (p._version, p.data_ptr())
+            if self._train_versions.get(n) != cur:
+                eng.train_set_weight(n, p.data.float())
+                self._train_versions[n] = cur
+                self._packed_key = None  # the packed inference weights are stale until the next eval-mode forward
+        return eng
+
     # ---- the reference's forward (one iteration) ---------------------------------------------------
-    @torch.no_grad()
     def forward(self, x, tfd_kps, init_pose, init_scale, K_zoom=None, obj_class=None, gt_ego_rot=None, gt_trans=None,
                 gt_scale=None, obj_kps=None, mean_scales=None, sym_info=None, do_loss=False, cur_iter=0):
         """x [B,3,N_o] and tfd_kps [B,3,N_p] as the reference passes them (permuted views of point-major
-        tensors, core/catre/engine/batch_test.py:92-95).  Returns {f"pose_{cur_iter}", f"scale_{cur_iter}"}."""
-        if do_loss:
-            raise NotImplementedError("catre_b200 is a forward-only inference engine; the training forward "
-                                      "(do_loss=True) is out of scope (SURVEY.md 8(f) N4)")
+        tensors, core/catre/engine/batch_test.py:92-95).  Returns {f"pose_{cur_iter}", f"scale_{cur_iter}"}, and with
+        do_loss=True ``(out_dict, loss_dict)`` (CATRE_disR_shared.py:125-165)."""
         if K_zoom is None:
             raise ValueError("K_zoom is required (T_TRANSFORM_K_AWARE=True)")
-        eng = self.engine(x.device)
-        x_pm = x.transpose(1, 2).contiguous().float()
-        k_pm = tfd_kps.transpose(1, 2).contiguous().float()
-        pose, scale = eng.forward_once(x_pm, k_pm, init_pose.float().contiguous(), init_scale.float().contiguous(),
-                                       K_zoom.float().contiguous())
+        if do_loss:
+            return self._forward_train(x, tfd_kps, init_pose, init_scale, K_zoom, gt_ego_rot, gt_trans, gt_scale, obj_kps,
+                                       sym_info, cur_iter)
+        with torch.no_grad():
+            eng = self.engine(x.device)
+            x_pm = x.transpose(1, 2).contiguous().float()
+            k_pm = tfd_kps.transpose(1, 2).contiguous().float()
+            pose, scale = eng.forward_once(x_pm, k_pm, init_pose.float().contiguous(), init_scale.float().contiguous(),
+                                           K_zoom.float().contiguous())
         return {f"pose_{cur_iter}": pose, f"scale_{cur_iter}": scale}
+
+    # ---- the reference's training forward (SURVEY.md 8(f) N4) ---------------------------------------
+    def _forward_train(self, x, tfd_kps, init_pose, init_scale, K_zoom, gt_ego_rot, gt_trans, gt_scale, obj_kps, sym_info,
+                       cur_iter):
+        if gt_ego_rot is None or gt_trans is None or gt_scale is None or obj_kps is None or sym_info is None:
+            raise ValueError("do_loss=True needs gt_ego_rot, gt_trans, gt_scale, obj_kps and sym_info "
+                             "(CATRE_disR_shared.py:126, 191, 224)")
+        check_loss_cfg(self.cfg)
+        is_sym, sym_rots = split_sym_info(sym_info)
+        if len(is_sym) != x.shape[0]:
+            raise ValueError(f"sym_info has {len(is_sym)} entries for a batch of {x.shape[0]}")
+        with torch.no_grad():
+            eng = self._engine_for_training(x.device)
+            f32 = lambda t: t.detach().float().contiguous()
+            gt_pose = torch.cat((f32(gt_ego_rot), f32(gt_trans).reshape(-1, 3, 1)), dim=2).contiguous()
+            pose, scale, losses = eng.train_step(x.detach().transpose(1, 2).contiguous().float(),
+                                                 tfd_kps.detach().transpose(1, 2).contiguous().float(), f32(obj_kps),
+                                                 f32(init_pose), f32(init_scale), f32(K_zoom), gt_pose, f32(gt_scale), is_sym,
+                                                 sym_rots)
+        self._train_step_id += 1
+        present = [n != "loss_rot" or not all(is_sym) for n in _engine.TRAIN_LOSS_NAMES]
+        present = [p and (n != "loss_yaxis_rot" or any(is_sym)) for p, n in zip(present, _engine.TRAIN_LOSS_NAMES)]
+        names = [n for n, _ in self.named_parameters()]
+        bridged = _LossBridge.apply(losses, torch.tensor(present, device=losses.device), self, names, *self.parameters())
+        loss_dict = {n: bridged[i] for i, n in enumerate(_engine.TRAIN_LOSS_NAMES) if present[i]}
+        return {f"pose_{cur_iter}": pose, f"scale_{cur_iter}": scale}, loss_dict
 
     # ---- fused K-loop (additive API) ------------------------------------------------------------------
     @torch.no_grad()
@@ -230,15 +332,68 @@ class CatreB200(nn.Module):
         return out
 
 
+def check_loss_cfg(cfg: Any) -> None:
+    """The training step implements the shipped LOSS_CFG only; a config object that sets something else is refused
+    (absent keys take the shipped values)."""
+    bad = []
+    for key, want in _REQUIRED_LOSS_CFG.items():
+        got = _cfg_get(cfg, "MODEL.CATRE.LOSS_CFG." + key, want)
+        if (got.lower() if isinstance(got, str) else got) != (want.lower() if isinstance(want, str) else want):
+            bad.append(f"{key}={got!r} (implemented: {want!r})")
+    if _cfg_get(cfg, "MODEL.CATRE.USE_MTL", False):
+        bad.append("USE_MTL=True (implemented: False)")
+    if bad:
+        raise NotImplementedError("catre_b200's training step implements the shipped loss config only: " + "; ".join(bad))
+
+
+def split_sym_info(sym_info) -> Tuple[List[bool], np.ndarray]:
+    """The reference's per-object list ``[K x 3 x 3 rotations or None]`` (core/catre/engine/batching.py:49-63) ->
+    (is_sym per object, the one rotation set).  Every symmetric NOCS object carries the same discretised rotations
+    about y (core/catre/datasets/data_loader.py:385-401); differing sets are refused."""
+    is_sym = [s is not None for s in sym_info]
+    rots = None
+    for s in sym_info:
+        if s is None:
+            continue
+        a = (s.detach().cpu().numpy() if isinstance(s, torch.Tensor) else np.asarray(s)).astype(np.float32).reshape(-1, 3, 3)
+        if rots is None:
+            rots = a
+        elif rots.shape != a.shape or not np.array_equal(rots, a):
+            raise NotImplementedError("catre_b200: objects with different symmetry-rotation sets in one batch")
+    return is_sym, (rots if rots is not None else np.zeros((0, 3, 3), np.float32))
+
+
+def _build_optimizer(cfg: Any, model: nn.Module):
+    """The reference builds its optimiser from cfg.SOLVER.OPTIMIZER_CFG through its own registry
+    (core/utils/solver_utils.build_optimizer_with_params; the shipped config names its `Ranger`).  Inside the
+    reference's tree that builder is used as is; elsewhere any torch.optim class of that name works."""
+    lr = float(_cfg_get(cfg, "SOLVER.BASE_LR", _cfg_get(cfg, "SOLVER.OPTIMIZER_CFG.lr", 1e-4)))
+    groups = [{"params": [p for p in model.parameters() if p.requires_grad], "lr": lr}]
+    try:
+        from core.utils.solver_utils import build_optimizer_with_params  # the reference's own builder
+    except Exception:
+        build_optimizer_with_params = None
+    if build_optimizer_with_params is not None:
+        return build_optimizer_with_params(cfg, groups)
+    opt_cfg = dict(_cfg_get(cfg, "SOLVER.OPTIMIZER_CFG", {}) or {})
+    name = opt_cfg.pop("type", None)
+    opt_cfg.pop("_delete_", None)
+    if name is None or not hasattr(torch.optim, name):
+        raise NotImplementedError(f"optimizer {name!r}: run inside the reference tree (its registry provides it) or use a "
+                                  "torch.optim class name in SOLVER.OPTIMIZER_CFG.type")
+    opt_cfg.pop("lr", None)
+    return getattr(torch.optim, name)(groups, lr=lr, **opt_cfg)
+
+
 def build_model_optimizer(cfg, is_test: bool = False, precision: str = "f16x3", max_batch: int = 256):
     """Same contract as the reference's build_model_optimizer (CATRE_disR_shared.py:291-350):
     returns (model, optimizer).  ``optimizer`` is None for is_test=True, as in the reference."""
     n_obs, n_prior = check_cfg(cfg)
-    if not is_test:
-        raise NotImplementedError("catre_b200 is an inference engine: build it with is_test=True "
-                                  "(--eval-only); training is out of scope (SURVEY.md 8(f) N4)")
     model = CatreB200(n_obs, n_prior, precision=precision, max_batch=max_batch, cfg=cfg)
     device = _cfg_get(cfg, "MODEL.DEVICE", "cuda")
     model.to(torch.device(device))
-    model.eval()
-    return model, None
+    if is_test:
+        model.eval()
+        return model, None
+    check_loss_cfg(cfg)
+    return model, _build_optimizer(cfg, model)

@@ -46,6 +46,9 @@ SYMBOLS = {
                                           ctypes.c_int32, ctypes.c_int32, _F, _P]),
     "catre_pair_metrics": (ctypes.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32,
                                           ctypes.c_int32, _F, _F, _P]),
+    "catre_train_set_weight": (ctypes.c_int, [_P, ctypes.c_char_p, _F, _P]),
+    "catre_train_step": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P, ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _P]),
+    "catre_train_grad": (ctypes.c_int, [_P, ctypes.c_char_p, _F, _P]),
     "catre_last_launch_count": (ctypes.c_int64, [_P]),
     "catre_debug_read": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_size_t]),
     "catre_profile_enable": (ctypes.c_int, [_P, ctypes.c_int32]),
@@ -82,6 +85,10 @@ def load_library(path: Optional[str] = None) -> ctypes.CDLL:
 
 class CatreError(RuntimeError):
     pass
+
+
+# order of catre_train_step's out_losses (the reference's loss_dict keys, CATRE_disR_shared.py:168-288)
+TRAIN_LOSS_NAMES = ("loss_PM_R", "loss_rot", "loss_yaxis_rot", "loss_trans_xy", "loss_trans_z", "loss_scale")
 
 
 def _ptr(t: Optional[torch.Tensor]) -> Optional[int]:
@@ -245,6 +252,49 @@ class Engine:
                                                      _ptr(init_pose), _ptr(init_scale), _ptr(K), B, n_iter, _ptr(poses),
                                                      _ptr(scales), self._stream()), "catre_refine_table_host")
         return poses, scales
+
+    # ---- training step ---------------------------------------------------------
+    def train_set_weight(self, name: str, t: torch.Tensor):
+        """Device-to-device refresh of the engine's fp32 copy of one checkpoint tensor (after an optimiser step)."""
+        if not t.is_cuda or t.device.index != self.device or t.dtype != torch.float32:
+            raise CatreError(f"{name}: expected a float32 CUDA tensor on device {self.device}")
+        t = t.detach().contiguous()
+        self._check(self.lib.catre_train_set_weight(self._h, name.encode(), t.data_ptr(), self._stream()), f"train_set_weight({name})")
+
+    def train_step(self, x_pm, tfd_pm, obj_kps, pose, scale, K, gt_pose, gt_scale, is_sym, sym_rots):
+        """Forward + shipped losses + backward of one refinement iteration.  Device fp32 tensors except
+        is_sym (B bools / 0-1 on the host) and sym_rots ([n,3,3] fp32 numpy / CPU tensor, may be empty).
+        Returns (pose [B,3,4], scale [B,3], losses [6] on the device in the order of TRAIN_LOSS_NAMES); the
+        parameter gradients stay in the engine (train_grad)."""
+        import numpy as np
+
+        B, N = x_pm.shape[0], self.n_pts
+        x_pm = self._dev(x_pm, (B, N, 3), "x")
+        tfd_pm = self._dev(tfd_pm, (B, N, 3), "tfd_kps")
+        obj_kps = self._dev(obj_kps, (B, N, 3), "obj_kps")
+        pose = self._dev(pose, (B, 3, 4), "init_pose")
+        scale = self._dev(scale, (B, 3), "init_scale")
+        K = self._dev(K, (B, 3, 3), "K")
+        gt_pose = self._dev(gt_pose, (B, 3, 4), "gt_pose")
+        gt_scale = self._dev(gt_scale, (B, 3), "gt_scale")
+        sym = np.ascontiguousarray(np.asarray(is_sym).astype(np.uint8).reshape(-1))
+        if sym.shape[0] != B:
+            raise CatreError(f"is_sym has {sym.shape[0]} entries, expected {B}")
+        rots = np.ascontiguousarray(np.asarray(sym_rots, dtype=np.float32).reshape(-1, 3, 3))
+        op = torch.empty((B, 3, 4), dtype=torch.float32, device=x_pm.device)
+        os_ = torch.empty((B, 3), dtype=torch.float32, device=x_pm.device)
+        losses = torch.empty((6,), dtype=torch.float32, device=x_pm.device)
+        self._check(self.lib.catre_train_step(self._h, _ptr(x_pm), _ptr(tfd_pm), _ptr(obj_kps), _ptr(pose), _ptr(scale), _ptr(K),
+                                              _ptr(gt_pose), _ptr(gt_scale), sym.ctypes.data, rots.ctypes.data if len(rots) else None,
+                                              len(rots), B, _ptr(op), _ptr(os_), _ptr(losses), self._stream()), "catre_train_step")
+        return op, os_, losses
+
+    def train_grad(self, name: str, out: torch.Tensor) -> torch.Tensor:
+        """Copy the gradient of checkpoint tensor `name` from the last train_step into `out` (device fp32, same numel)."""
+        if not out.is_cuda or out.dtype != torch.float32 or not out.is_contiguous():
+            raise CatreError(f"{name}: gradient destination must be a contiguous float32 CUDA tensor")
+        self._check(self.lib.catre_train_grad(self._h, name.encode(), out.data_ptr(), self._stream()), f"train_grad({name})")
+        return out
 
     # ---- accounting ------------------------------------------------------------------------------
     def last_launch_count(self) -> int:

@@ -162,7 +162,40 @@ int catre_pair_metrics(const double* pred_RT, const double* pred_scale, const in
                        const int32_t* pair_gt, int32_t n_pairs, uint32_t sym_class_mask, uint32_t flip_class_mask,
                        int32_t mug_class, float* iou, float* deg_shift, void* stream);
 
-/* Number of kernels the last forward/refine call launched (bench.py's `gpu_launches`). */
+/* ---- Training step --------------------------------------------------------------------
+ * Replaces one refinement iteration of the reference's training loop (core/catre/engine/engine.py:293-352 without the
+ * optimiser): CATRE_disR_shared.forward(..., do_loss=True) (CATRE_disR_shared.py:40-165), catre_loss with the shipped
+ * LOSS_CFG (:168-288; core/catre/losses/pm_loss.py:110-130, rot_loss.py:45-58; closest symmetric ground truth of
+ * core/utils/pose_utils.py:472-528) and `sum(loss_dict.values()).backward()`.  All fp32 on CUDA cores; the backward is
+ * hand-derived (sparse max-pool backward through the arg-max points, GroupNorm backward from two group sums, the
+ * rotation head's layer-0 split) -- about 1/6 of the multiply-adds autograd spends on the same step.
+ *
+ * catre_train_set_weight: device-to-device refresh of the engine's fp32 copy of checkpoint tensor `name` (the
+ *   optimiser owns the parameters; call after every optimiser step for the tensors it changed).  Needs one earlier
+ *   catre_pack (which allocates the copies).  Marks the packed inference weights stale: the inference entries return
+ *   CATRE_ERR_NOT_PACKED until the next catre_pack, which first pulls the refreshed tensors back from the device.
+ * catre_train_step: forward + losses + backward for B objects, stream-ordered, no host sync.
+ *   x_pm / tfd_pm [B, n, 3]  the re-posed points the reference's forward receives (as in catre_forward_once)
+ *   obj_kps [B, n, 3]        normalised category prior (batch["obj_kps"], the point-matching loss's points)
+ *   pose [B,3,4], scale [B,3], K [B,3,3]; gt_pose [B,3,4] (batch["obj_pose"]), gt_scale [B,3]   -- all device
+ *   is_sym_host [B]          host bytes: 1 = sym_info[b] is not None (symmetric about y)
+ *   sym_rots_host [n_sym_rots, 3, 3] host fp32: the symmetry rotations the data loader attaches to such objects
+ *                            (lib/pysixd/misc.py:220-231; at most 1024)
+ *   out_pose [B,3,4], out_scale [B,3] device = out_dict["pose_i"/"scale_i"]
+ *   out_losses [6] device = (loss_PM_R, loss_rot, loss_yaxis_rot, loss_trans_xy, loss_trans_z, loss_scale); the
+ *                            reference omits loss_rot / loss_yaxis_rot from its dict when no object is asymmetric /
+ *                            symmetric -- here they are 0.
+ *   The workspace (about 14 KB per point of the batch) is allocated on the first call and grown when B grows.
+ * catre_train_grad: copy d(sum of losses)/d(tensor `name`) of the last catre_train_step to dst (device or host,
+ *   stream-ordered); tensors the shipped config never uses (the heads' `norm`) have zero gradients. */
+int catre_train_set_weight(catre_engine* e, const char* name, const float* src_dev, void* stream);
+int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, const float* obj_kps, const float* pose,
+                     const float* scale, const float* K, const float* gt_pose, const float* gt_scale,
+                     const uint8_t* is_sym_host, const float* sym_rots_host, int32_t n_sym_rots, int32_t B, float* out_pose,
+                     float* out_scale, float* out_losses, void* stream);
+int catre_train_grad(catre_engine* e, const char* name, float* dst, void* stream);
+
+/* Number of kernels the last forward/refine/train call launched (bench.py's `gpu_launches`). */
 int64_t catre_last_launch_count(const catre_engine* e);
 
 /* Debug tap (tests only): synchronise and copy `bytes` of the internal workspace buffer `name`

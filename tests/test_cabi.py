@@ -74,10 +74,33 @@ def test_dropin_refuses_cpu_and_training():
     m = dropin.CatreB200(1024, 1024)
     b = synth.known_answer_inputs()
     x = b.pcl.permute(0, 2, 1)
-    with pytest.raises(NotImplementedError):
+    with pytest.raises(ValueError):  # the training forward needs the ground truth, like the reference's assert
         m(x, x, b.init_pose, b.init_scale, K_zoom=b.K, do_loss=True)
-    with pytest.raises(engine.CatreError):  # no CPU path, no silent fallback
+    with pytest.raises(engine.CatreError):  # no CPU path, no silent fallback -- inference ...
         m(x, x, b.init_pose, b.init_scale, K_zoom=b.K)
+    with pytest.raises(engine.CatreError):  # ... and training alike
+        m(x, x, b.init_pose, b.init_scale, K_zoom=b.K, gt_ego_rot=b.init_pose[:, :, :3], gt_trans=b.init_pose[:, :, 3],
+          gt_scale=b.init_scale, obj_kps=b.prior, sym_info=[None], do_loss=True)
+
+
+def test_training_cfg_and_sym_info_checks():
+    import numpy as np
+
+    dropin.check_loss_cfg({})  # absent keys = the shipped values
+    dropin.check_loss_cfg({"MODEL": {"CATRE": {"LOSS_CFG": {"PM_LOSS_TYPE": "l1", "ROT_LW": 1.0}}}})
+    with pytest.raises(NotImplementedError):
+        dropin.check_loss_cfg({"MODEL": {"CATRE": {"LOSS_CFG": {"ROT_LOSS_TYPE": "L2"}}}})
+    with pytest.raises(NotImplementedError):
+        dropin.check_loss_cfg({"MODEL": {"CATRE": {"USE_MTL": True}}})
+    r = np.stack([np.eye(3, dtype=np.float32)] * 4)
+    is_sym, rots = dropin.split_sym_info([None, r, None, torch.from_numpy(r)])
+    assert is_sym == [False, True, False, True] and rots.shape == (4, 3, 3)
+    assert dropin.split_sym_info([None])[1].shape == (0, 3, 3)
+    with pytest.raises(NotImplementedError):
+        dropin.split_sym_info([r, 2 * r])
+    model, opt = dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "SGD", "lr": 1e-3}}},
+                                              is_test=False)
+    assert isinstance(opt, torch.optim.SGD) and model.training
 
 
 def test_check_cfg():

@@ -1,0 +1,129 @@
+"""Training step on the GPU, through the C ABI: catre_train_step's poses, losses and all 68
+parameter gradients against the training oracle (fp64 run committed as tests/golden/oracle_train_fp64.npz; the oracle is
+pinned to the unmodified reference by tests/test_train_oracle.py), with both GEMM kernels, and the drop-in's
+do_loss=True forward inside the reference's loop shape (sum of losses -> backward -> optimiser step)."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from catre_b200 import dropin, engine, synth
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+FIX = os.path.join(HERE, "golden", "oracle_train_fp64.npz")
+N_SAMPLES = 256
+UNUSED = set(dropin.UNUSED_PARAMS)
+pytestmark = pytest.mark.gpu
+
+
+def sample_positions(name, numel):  # same rule as tests/golden/make_golden_train.py
+    seed = int.from_bytes(name.encode()[-8:].rjust(8, b"\0"), "little") % (2 ** 31)
+    return np.random.RandomState(seed).randint(0, numel, size=N_SAMPLES)
+
+
+def y_symmetry_rotations(step=0.01):
+    """The rotations the reference's data loader attaches to y-symmetric objects (lib/pysixd/misc.py:220-231)."""
+    n = int(np.ceil(np.pi / step))
+    a = np.arange(1, n) * 2.0 * np.pi / n
+    r = np.zeros((n - 1, 3, 3))
+    r[:, 0, 0], r[:, 0, 2], r[:, 1, 1], r[:, 2, 0], r[:, 2, 2] = np.cos(a), np.sin(a), 1.0, -np.sin(a), np.cos(a)
+    return r.astype(np.float32)
+
+
+def inputs(device="cuda"):
+    batch, tgt = synth.make_train_batch(6, 1024, 11, round_robin_cls=True)
+    d = batch.to(device)
+    x_pm = d.pcl - d.init_pose[:, :, 3].unsqueeze(1)  # batch_test.py:95
+    tfd_pm = (d.prior * d.init_scale.unsqueeze(1)) @ d.init_pose[:, :, :3].transpose(1, 2)  # misc.py:1011-1026
+    return d, tgt, x_pm.contiguous(), tfd_pm.contiguous()
+
+
+def check_grad(z, name, g, tol=3e-4):
+    g = g.detach().double().flatten().cpu().numpy()
+    if f"grad/{name}/full" in z.files:
+        want = z[f"grad/{name}/full"]
+        assert np.abs(g - want).max() <= tol * max(np.abs(want).max(), 1e-12), (name, np.abs(g - want).max(), np.abs(want).max())
+    else:
+        stats, samples = z[f"grad/{name}/stats"], z[f"grad/{name}/samples"]
+        got = np.array([g.sum(), np.abs(g).sum(), np.sqrt((g * g).sum())])
+        assert np.allclose(got[1:], stats[1:], rtol=tol), (name, got, stats)
+        assert abs(got[0] - stats[0]) <= tol * stats[1], (name, got, stats)
+        err = np.abs(g[sample_positions(name, g.size)] - samples).max()
+        assert err <= tol * max(np.abs(samples).max(), 1e-12), (name, err)
+
+
+@pytest.mark.parametrize("naive", ["0", "1"])
+def test_train_step_matches_oracle(naive, monkeypatch):
+    monkeypatch.setenv("CATRE_TRAIN_NAIVE_GEMM", naive)  # 1 = the one-thread-per-output GEMM the CPU emulation verifies
+    z = np.load(FIX)
+    d, tgt, x_pm, tfd_pm = inputs()
+    w = synth.load_weights()
+    eng = engine.Engine(1024, 8, "fp32", 0)
+    eng.load_weights(w)
+    pose, scale, losses = eng.train_step(x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, tgt.gt_pose.cuda(), tgt.gt_scale.cuda(),
+                                         tgt.sym_y.numpy(), y_symmetry_rotations())
+    torch.cuda.synchronize()
+    assert eng.last_launch_count() > 100
+    assert np.abs(pose.cpu().numpy() - z["pose"]).max() < 5e-6 and np.abs(scale.cpu().numpy() - z["scale"]).max() < 5e-6
+    got = dict(zip(engine.TRAIN_LOSS_NAMES, losses.cpu().numpy()))
+    for k, v in zip(z["loss_names"], z["loss_values"]):
+        assert abs(got[str(k)] - v) <= 2e-5 * max(1.0, abs(v)), (k, got[str(k)], v)
+    for name, t in w.items():
+        g = eng.train_grad(name, torch.empty(t.shape, device="cuda"))
+        if name in UNUSED:
+            assert not bool(g.any()), name
+        else:
+            check_grad(z, name, g)
+    # deterministic: a second step reproduces the gradients bit for bit
+    g1 = eng.train_grad("pcl_net.conv3.weight", torch.empty(512, 128, 1, device="cuda")).clone()
+    eng.train_step(x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, tgt.gt_pose.cuda(), tgt.gt_scale.cuda(), tgt.sym_y.numpy(),
+                   y_symmetry_rotations())
+    assert torch.equal(g1, eng.train_grad("pcl_net.conv3.weight", torch.empty(512, 128, 1, device="cuda")))
+    eng.close()
+
+
+def test_dropin_training_loop():
+    """The reference's loop shape (core/catre/engine/engine.py:293-352) on the drop-in model."""
+    z = np.load(FIX)
+    d, tgt, x_pm, tfd_pm = inputs()
+    model = dropin.CatreB200(1024, 1024, max_batch=8).cuda()
+    model.load_state_dict(synth.load_weights(), strict=True)
+    model.train()
+    opt = torch.optim.SGD([p for p in model.parameters()], lr=1e-3)
+    rots = y_symmetry_rotations()
+    sym_info = [rots if s else None for s in tgt.sym_y]
+    kw = dict(init_pose=d.init_pose, init_scale=d.init_scale, K_zoom=d.K, obj_class=d.obj_cls, gt_ego_rot=tgt.gt_pose[:, :, :3].cuda(),
+              gt_trans=tgt.gt_pose[:, :, 3].cuda(), gt_scale=tgt.gt_scale.cuda(), obj_kps=d.prior, sym_info=sym_info, do_loss=True)
+    x, tfd = x_pm.permute(0, 2, 1), tfd_pm.permute(0, 2, 1)  # the reference passes permuted views
+    out, loss_dict = model(x, tfd, cur_iter=1, **kw)
+    assert sorted(loss_dict) == sorted(str(k) for k in z["loss_names"])
+    total = sum(loss_dict.values())
+    assert abs(float(total) - float(z["loss_values"].sum())) < 1e-5
+    total.backward()
+    for name, p in model.named_parameters():
+        if name in UNUSED:
+            assert p.grad is None, name
+        else:
+            check_grad(z, name, p.grad)
+    before = float(total)
+    opt.step()
+    opt.zero_grad(set_to_none=True)
+    out2, loss_dict2 = model(x, tfd, cur_iter=1, **kw)  # refreshed weights reach the engine device-to-device
+    after = float(sum(loss_dict2.values()))
+    assert after != before and abs(after - before) < 0.05
+    # a uniform loss scale (AMP) is honoured, per-term weights are refused
+    (2.0 * sum(loss_dict2.values())).backward()
+    g2 = model.pcl_net.conv3.weight.grad.clone()
+    opt.zero_grad(set_to_none=True)
+    out3, loss_dict3 = model(x, tfd, cur_iter=1, **kw)
+    sum(loss_dict3.values()).backward()
+    assert torch.allclose(g2, 2.0 * model.pcl_net.conv3.weight.grad, rtol=1e-6, atol=0)
+    with pytest.raises(NotImplementedError):
+        out4, loss_dict4 = model(x, tfd, cur_iter=1, **kw)
+        (loss_dict4["loss_scale"] * 3.0 + loss_dict4["loss_PM_R"]).backward()
+    # inference after training re-packs from the refreshed device copies: same weights -> same pose (f16x3 vs fp32 chain)
+    model.eval()
+    with torch.no_grad():
+        inf = model(x, tfd, init_pose=d.init_pose, init_scale=d.init_scale, K_zoom=d.K, cur_iter=1)
+    assert (inf["pose_1"] - out3["pose_1"]).abs().max() < 1e-4 and (inf["scale_1"] - out3["scale_1"]).abs().max() < 1e-4

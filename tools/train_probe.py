@@ -1,0 +1,48 @@
+"""GPU probe of the training step: device time per step of catre_train_step with the tiled and
+the naive GEMM, at the reference's training batch sizes.  Prints one JSON line per configuration.
+Usage (GPU box):  python tools/train_probe.py [B ...]"""
+import json
+import os
+import sys
+
+import numpy as np
+import torch
+
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from catre_b200 import engine, synth  # noqa: E402
+from tests.test_train_gpu import y_symmetry_rotations  # noqa: E402
+
+
+def main():
+    sizes = [int(a) for a in sys.argv[1:]] or [16, 32]
+    w = synth.load_weights()
+    rots = y_symmetry_rotations()
+    for B in sizes:
+        batch, tgt = synth.make_train_batch(B, 1024, 3, round_robin_cls=True)
+        d = batch.to("cuda")
+        x_pm = (d.pcl - d.init_pose[:, :, 3].unsqueeze(1)).contiguous()
+        tfd_pm = ((d.prior * d.init_scale.unsqueeze(1)) @ d.init_pose[:, :, :3].transpose(1, 2)).contiguous()
+        gp, gs = tgt.gt_pose.cuda(), tgt.gt_scale.cuda()
+        for naive in ("0", "1"):
+            os.environ["CATRE_TRAIN_NAIVE_GEMM"] = naive
+            eng = engine.Engine(1024, 8, "fp32", 0)
+            eng.load_weights(w)
+            step = lambda: eng.train_step(x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, gp, gs, tgt.sym_y.numpy(), rots)
+            for _ in range(2):
+                step()
+            torch.cuda.synchronize()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n = 5 if naive == "0" else 2
+            a.record()
+            for _ in range(n):
+                step()
+            b.record()
+            torch.cuda.synchronize()
+            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": "naive" if naive == "1" else "tiled",
+                              "ms_per_step": a.elapsed_time(b) / n, "launches": eng.last_launch_count(),
+                              "objects_per_s": B / (a.elapsed_time(b) / n / 1e3)}), flush=True)
+            eng.close()
+
+
+if __name__ == "__main__":
+    main()
