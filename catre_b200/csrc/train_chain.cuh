@@ -48,12 +48,14 @@ struct TrainWs {
   float *lossp, *losses, *dpose, *d_r6, *d_dts, *tsd_u, *tsd_u0, *ts_din, *gn_m, *gnp_g, *gnp_b;
   float *dg, *dpfmax, *dpf, *e, *du, *du0, *dcset, *d512, *d128, *d64, *dh1, *dt64, *dfc2, *dfc1, *dmax, *dqp, *dt3;
   float *partial, *cs_partial;
+  double* gn_part;  // [maxB, kGnChunks, 32, 18]
   unsigned char* is_sym;
   float* sym_rots;
   float* G[W_COUNT];  // gradient arena, checkpoint order
   size_t grad_floats = 0;
   static constexpr size_t kPartialFloats = (size_t)4 << 20;
   static constexpr int kMaxSymRots = 1024;
+  static constexpr int kGnChunks = 64;
 };
 
 // Assigns every workspace pointer from `base` (256-byte aligned slices) and returns the bytes needed; with
@@ -86,6 +88,7 @@ inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base) {
   F(w.dcset, S * 256); F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
   F(w.dfc2, S * 256); F(w.dfc1, S * 512); F(w.dmax, S * 1024); F(w.dqp, R * 3); F(w.dt3, S * 9);
   F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, (size_t)64 * 4096);
+  w.gn_part = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
   w.is_sym = reinterpret_cast<unsigned char*>(take(B));
   F(w.sym_rots, (size_t)TrainWs::kMaxSymRots * 9);
   const size_t g0 = off;
@@ -156,14 +159,19 @@ struct Chain {
     if (dx) gemm(dy, ldy, 1, W[wi] + woff, ldw, 1, dx, K, 1, (int)rows, K, C, nullptr, 0, dx_acc);
   }
   void relu_mask(float* d, const float* act, long long n) { o.run(KReluMask{d, act, n}, cdiv(n, 256), 1, 1, 256); }
+  static int gn_chunks(int P) { return P >= 4 * TrainWs::kGnChunks ? TrainWs::kGnChunks : 1; }
   void gn_fwd(const float* y, float* st, const float* ga, const float* be, float* u, int B, int P) {
-    o.run(KGnStats{y, st, P}, B, 1, 1, 32);
+    const int chunks = gn_chunks(P), per = (P + chunks - 1) / chunks;
+    o.run(KGnStatsPart{y, w.gn_part, P, chunks, per}, B, chunks, 1, 32);
+    o.run(KGnStats{w.gn_part, st, P, chunks}, B, 1, 1, 32);
     const long long n = (long long)B * P * 256;
     o.run(KGnGeluFwd{y, st, ga, be, u, P, n}, cdiv(n, 256), 1, 1, 256);
   }
   // du -> dy in place; gamma / beta gradients accumulated into G[gi], G[gi + 1]
   void gn_bwd(float* du, const float* y, const float* st, int gi, int B, int P) {
-    o.run(KGnBwdSums{du, y, st, W[gi], W[gi + 1], w.gn_m, w.gnp_g, w.gnp_b, P}, B, 1, 1, 32);
+    const int chunks = gn_chunks(P), per = (P + chunks - 1) / chunks;
+    o.run(KGnBwdPart{du, y, st, W[gi], W[gi + 1], w.gn_part, P, chunks, per}, B, chunks, 1, 32);
+    o.run(KGnBwdSums{w.gn_part, w.gn_m, w.gnp_g, w.gnp_b, P, chunks}, B, 1, 1, 32);
     colsum(w.gnp_g, B, 256, 256, w.G[gi], 1);
     colsum(w.gnp_b, B, 256, 256, w.G[gi + 1], 1);
     const long long n = (long long)B * P * 256;
@@ -192,8 +200,7 @@ struct Chain {
     lin_bwd(wb + T_FC2, fc1, 512, w.dfc2, 256, 256, S, w.dfc1, 0);
     relu_mask(w.dfc1, fc1, (long long)S * 512);
     lin_bwd(wb + T_FC1, vmax, 1024, w.dfc1, 512, 512, S, w.dmax, 0);
-    o.zero(w.d128, (size_t)R * 128 * sizeof(float));
-    o.run(KMaxBwdDx{w.dmax, vmax, W[wb + T_CONV3], arg, w.d128, N, 1024, 128}, cdiv(128, 128), S, 1, 128);
+    o.run(KMaxBwdDx{w.dmax, vmax, W[wb + T_CONV3], arg, w.d128, N, 1024, 128}, cdiv(128, 128), cdiv(N, MAXBWD_PTS), S, 128);
     o.run(KMaxBwdDw{w.dmax, vmax, c128, arg, w.G[wb + T_CONV3], w.G[wb + T_CONV3 + 1], S, N, 1024, 128}, cdiv(128, 128), 1024, 1, 128);
     relu_mask(w.d128, c128, R * 128);
     lin_bwd(wb + T_CONV2, c64, 64, w.d128, 128, 128, R, w.d64, 0);
@@ -285,8 +292,7 @@ struct Chain {
     }
     // ---- encoder
     o.run(KScatterMax{w.dpfmax, w.pfarg, w.dpf, N, 64}, 1, S, 1, 64);
-    o.zero(w.d512, (size_t)R * 512 * sizeof(float));
-    o.run(KMaxBwdDx{w.dg, nullptr, W[W_CONV4], w.garg, w.d512, N, 1024, 512}, cdiv(512, 128), S, 1, 128);
+    o.run(KMaxBwdDx{w.dg, nullptr, W[W_CONV4], w.garg, w.d512, N, 1024, 512}, cdiv(512, 128), cdiv(N, MAXBWD_PTS), S, 128);
     o.run(KMaxBwdDw{w.dg, nullptr, w.a512, w.garg, w.G[W_CONV4], w.G[W_CONV4 + 1], S, N, 1024, 512}, cdiv(512, 128), 1024, 1, 128);
     relu_mask(w.d512, w.a512, R * 512);
     lin_bwd(W_CONV3, w.a128, 128, w.d512, 512, 512, R, w.d128, 0);

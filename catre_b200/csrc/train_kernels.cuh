@@ -161,20 +161,28 @@ struct KColSum {
 
 // ---- sparse backward of `max over points of [relu](x W^T + b)` (oracle: max_layer_bwd).  Only the arg-max row of
 //      each (set, channel) receives a gradient.
-// dx[(s, arg[s,c]), k] += d[s,c] W[c,k] for c = 0..C-1 in order; thread (s, k) owns column k of set s, so there are
-// no races and the order is fixed.  dx must be zero on entry.  grid (ceil(K / nt), S)
+// dx[(s, n), k] = sum over the channels c (ascending) whose arg-max point is n of d[s,c] W[c,k].  A thread owns column
+// k of MAXBWD_PTS consecutive points of one set and scans the set's C arg-max entries (warp-uniform reads), so every
+// dx element is written exactly once (no zero fill, no read-modify-write chain) in a fixed order.
+// grid (ceil(K / nt), ceil(N / MAXBWD_PTS), S)
+constexpr int MAXBWD_PTS = 8;
 struct KMaxBwdDx {
   const float *dmax, *relu_max, *W; const int* arg; float* dx; int N, C, K;
   TK_HD void operator()(const Idx& i) const {
-    const int k = i.bx * i.nt + i.tx, s = i.by;
+    const int k = i.bx * i.nt + i.tx, n0 = i.by * MAXBWD_PTS, s = i.bz;
     if (k >= K) return;
+    float acc[MAXBWD_PTS];
+    for (int j = 0; j < MAXBWD_PTS; ++j) acc[j] = 0.0f;
     for (int c = 0; c < C; ++c) {
+      const int j = arg[(size_t)s * C + c] - n0;
+      if (j < 0 || j >= MAXBWD_PTS) continue;
       float d = dmax[(size_t)s * C + c];
       if (relu_max && !(relu_max[(size_t)s * C + c] > 0.0f)) d = 0.0f;
-      if (d == 0.0f) continue;
-      float* o = dx + ((size_t)s * N + arg[(size_t)s * C + c]) * K + k;
-      *o = fmaf(d, W[(size_t)c * K + k], *o);
+      const float v = d * W[(size_t)c * K + k];
+      for (int t = 0; t < MAXBWD_PTS; ++t)
+        if (t == j) acc[t] += v;
     }
+    for (int j = 0; j < MAXBWD_PTS && n0 + j < N; ++j) dx[((size_t)s * N + n0 + j) * K + k] = acc[j];
   }
 };
 // dW[c, k] += sum_s d[s,c] x[(s, arg[s,c]), k];  db[c] += sum_s d[s,c].  grid (ceil(K / nt), C)
@@ -204,16 +212,34 @@ struct KScatterMax {
 };
 
 // ---- GroupNorm (32 groups of 8 channels over the P points of an object; P = 1 for the ts head), eps 1e-5,
-//      biased variance, fp64 accumulation.  y [B, P, 256] -> st [B, 32, 2] = (mean, rstd).  grid (B), nt = 32
+//      biased variance, fp64 accumulation in two deterministic stages: the points of an object are cut into `chunks`
+//      pieces of `per` points, thread (b, chunk, g) sums its piece into part [B, chunks, 32, 2] (doubles), then thread
+//      (b, g) adds the pieces in order.  y [B, P, 256] -> st [B, 32, 2] = (mean, rstd).
+//      stage 1: grid (B, chunks), nt = 32;  stage 2: grid (B), nt = 32
+struct KGnStatsPart {
+  const float* y; double* part; int P, chunks, per;
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx, ch = i.by, g = i.tx;
+    if (g >= 32) return;
+    const int n0 = ch * per, n1 = n0 + per < P ? n0 + per : P;
+    const float* p = y + (size_t)b * P * 256 + g * 8;
+    double s = 0.0, ss = 0.0;
+    for (int n = n0; n < n1; ++n)
+      for (int j = 0; j < 8; ++j) { const double v = p[(size_t)n * 256 + j]; s += v; ss += v * v; }
+    double* o = part + (((size_t)b * chunks + ch) * 32 + g) * 2;
+    o[0] = s; o[1] = ss;
+  }
+};
 struct KGnStats {
-  const float* y; float* st; int P;
+  const double* part; float* st; int P, chunks;
   TK_HD void operator()(const Idx& i) const {
     const int b = i.bx, g = i.tx;
     if (g >= 32) return;
-    const float* p = y + (size_t)b * P * 256 + g * 8;
     double s = 0.0, ss = 0.0;
-    for (int n = 0; n < P; ++n)
-      for (int j = 0; j < 8; ++j) { const double v = p[(size_t)n * 256 + j]; s += v; ss += v * v; }
+    for (int ch = 0; ch < chunks; ++ch) {
+      const double* o = part + (((size_t)b * chunks + ch) * 32 + g) * 2;
+      s += o[0]; ss += o[1];
+    }
     const double cnt = 8.0 * P, mu = s / cnt;
     double var = ss / cnt - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -235,17 +261,19 @@ struct KGnGeluFwd {
 };
 // backward, pass 1 (oracle: _gn_gelu_backward): with xhat = (y - mu) rstd, dn = du gelu'(gamma xhat + beta),
 // g = dn gamma:  m [B, 32, 2] = group means of (g, g xhat);  dgam [B, 256] = sum_p dn xhat, dbet [B, 256] = sum_p dn.
-// grid (B), nt = 32
-struct KGnBwdSums {
-  const float *du, *y, *st, *gamma, *beta; float *m, *dgam, *dbet; int P;
+// Two deterministic stages like the statistics: part [B, chunks, 32, 18] doubles = (sum g, sum g xhat, 8 x dgam, 8 x dbet).
+// stage 1: grid (B, chunks), nt = 32;  stage 2: grid (B), nt = 32
+struct KGnBwdPart {
+  const float *du, *y, *st, *gamma, *beta; double* part; int P, chunks, per;
   TK_HD void operator()(const Idx& i) const {
-    const int b = i.bx, g = i.tx;
+    const int b = i.bx, ch = i.by, g = i.tx;
     if (g >= 32) return;
+    const int n0 = ch * per, n1 = n0 + per < P ? n0 + per : P;
     const float mu = st[((size_t)b * 32 + g) * 2], rstd = st[((size_t)b * 32 + g) * 2 + 1];
     double s1 = 0.0, s2 = 0.0, dga[8], dbe[8];
     for (int j = 0; j < 8; ++j) dga[j] = dbe[j] = 0.0;
     const size_t base = (size_t)b * P * 256 + g * 8;
-    for (int n = 0; n < P; ++n)
+    for (int n = n0; n < n1; ++n)
       for (int j = 0; j < 8; ++j) {
         const size_t e = base + (size_t)n * 256 + j;
         const float xh = (y[e] - mu) * rstd, ga = gamma[g * 8 + j];
@@ -253,9 +281,25 @@ struct KGnBwdSums {
         s1 += (double)(dn * ga); s2 += (double)(dn * ga) * xh;
         dga[j] += (double)dn * xh; dbe[j] += dn;
       }
-    m[((size_t)b * 32 + g) * 2 + 0] = (float)(s1 / (8.0 * P));
-    m[((size_t)b * 32 + g) * 2 + 1] = (float)(s2 / (8.0 * P));
-    for (int j = 0; j < 8; ++j) { dgam[(size_t)b * 256 + g * 8 + j] = (float)dga[j]; dbet[(size_t)b * 256 + g * 8 + j] = (float)dbe[j]; }
+    double* o = part + (((size_t)b * chunks + ch) * 32 + g) * 18;
+    o[0] = s1; o[1] = s2;
+    for (int j = 0; j < 8; ++j) { o[2 + j] = dga[j]; o[10 + j] = dbe[j]; }
+  }
+};
+struct KGnBwdSums {
+  const double* part; float *m, *dgam, *dbet; int P, chunks;
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx, g = i.tx;
+    if (g >= 32) return;
+    double a[18];
+    for (int j = 0; j < 18; ++j) a[j] = 0.0;
+    for (int ch = 0; ch < chunks; ++ch) {
+      const double* o = part + (((size_t)b * chunks + ch) * 32 + g) * 18;
+      for (int j = 0; j < 18; ++j) a[j] += o[j];
+    }
+    m[((size_t)b * 32 + g) * 2 + 0] = (float)(a[0] / (8.0 * P));
+    m[((size_t)b * 32 + g) * 2 + 1] = (float)(a[1] / (8.0 * P));
+    for (int j = 0; j < 8; ++j) { dgam[(size_t)b * 256 + g * 8 + j] = (float)a[2 + j]; dbet[(size_t)b * 256 + g * 8 + j] = (float)a[10 + j]; }
   }
 };
 // pass 2: dy = rstd (g - m1 - xhat m2), written over du.  grid (ceil(B * P * 256 / nt))
