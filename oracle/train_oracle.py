@@ -58,8 +58,8 @@ def closest_sym_rot(pred_rot: torch.Tensor, gt_rot: torch.Tensor, sym_info: List
     """get_closest_rot_batch (core/utils/pose_utils.py:472-528): per object, the ground-truth rotation or the
     symmetric variant R_gt . S_i with the smallest rotation error to the (detached) prediction; strict '<', so the
     plain ground truth wins ties."""
-    out = gt_rot.detach().clone().numpy()
-    pred = pred_rot.detach().numpy()
+    out = gt_rot.detach().cpu().clone().numpy()
+    pred = pred_rot.detach().cpu().numpy()
     for b, sym in enumerate(sym_info):
         if sym is None:
             continue
@@ -71,7 +71,7 @@ def closest_sym_rot(pred_rot: torch.Tensor, gt_rot: torch.Tensor, sym_info: List
             if err < best_err:
                 best, best_err = cand, err
         out[b] = best
-    return torch.from_numpy(out).to(gt_rot.dtype)
+    return torch.from_numpy(out).to(dtype=gt_rot.dtype, device=gt_rot.device)
 
 
 def catre_loss(rot: torch.Tensor, trans: torch.Tensor, scale: torch.Tensor, gt_rot: torch.Tensor, gt_trans: torch.Tensor,
@@ -87,7 +87,7 @@ def catre_loss(rot: torch.Tensor, trans: torch.Tensor, scale: torch.Tensor, gt_r
     tgt = (kps * gt_scale.unsqueeze(1)) @ gt_sym.transpose(1, 2)
     loss["loss_PM_R"] = 3.0 * (est - tgt).abs().mean()
     # rotation (CATRE_disR_shared.py:222-250; core/catre/losses/rot_loss.py:45-58)
-    is_sym = torch.tensor([s is not None for s in sym_info])
+    is_sym = torch.tensor([s is not None for s in sym_info], device=rot.device)
     if (~is_sym).any():
         m = rot[~is_sym] @ gt_rot[~is_sym].transpose(1, 2)
         cos = (m.diagonal(dim1=1, dim2=2).sum(1) - 1.0) / 2.0
