@@ -58,6 +58,7 @@ class _LossBridge(torch.autograd.Function):
     @staticmethod
     def forward(ctx, losses, present, model, names, *params):
         ctx.model, ctx.names, ctx.present = model, names, present
+        ctx.shapes = [p.detach() for p in params]  # only their shape / dtype / device are used
         ctx.step_id = model._train_step_id
         return losses.clone()
 
@@ -75,8 +76,8 @@ class _LossBridge(torch.autograd.Function):
                                       f"got per-term weights {g.tolist()}")
         eng = model._engine
         grads: List[Optional[torch.Tensor]] = []
-        for name, p in zip(ctx.names, model.parameters()):
-            if name in UNUSED_PARAMS or not p.requires_grad:
+        for name, p, need in zip(ctx.names, ctx.shapes, ctx.needs_input_grad[4:]):
+            if not need:
                 grads.append(None)
                 continue
             grads.append(eng.train_grad(name, torch.empty_like(p, memory_format=torch.contiguous_format)) * scale)
@@ -301,8 +302,12 @@ class CatreB200(nn.Module):
         self._train_step_id += 1
         present = [n != "loss_rot" or not all(is_sym) for n in _engine.TRAIN_LOSS_NAMES]
         present = [p and (n != "loss_yaxis_rot" or any(is_sym)) for p, n in zip(present, _engine.TRAIN_LOSS_NAMES)]
-        names = [n for n, _ in self.named_parameters()]
-        bridged = _LossBridge.apply(losses, torch.tensor(present, device=losses.device), self, names, *self.parameters())
+        # only the tensors the shipped config uses enter the graph: the heads' unused `norm` stay out of it, so their .grad
+        # stays None as in the reference and DistributedDataParallel(find_unused_parameters=True) (main_catre.py:155-160)
+        # marks them unused instead of waiting for a gradient
+        used = [(n, p) for n, p in self.named_parameters() if n not in UNUSED_PARAMS]
+        bridged = _LossBridge.apply(losses, torch.tensor(present, device=losses.device), self, [n for n, _ in used],
+                                    *[p for _, p in used])
         loss_dict = {n: bridged[i] for i, n in enumerate(_engine.TRAIN_LOSS_NAMES) if present[i]}
         return {f"pose_{cur_iter}": pose, f"scale_{cur_iter}": scale}, loss_dict
 

@@ -95,3 +95,63 @@ def test_only_changed_tensors_are_refreshed(model):
     opt.step()
     call(m, [None])
     assert len(stub.refreshed) == 68 and not set(stub.refreshed) & set(dropin.UNUSED_PARAMS)
+
+
+# ---- data-parallel training: the reference wraps the model in DistributedDataParallel(find_unused_parameters=True)
+#      (core/catre/main_catre.py:154-160); world_size-2 gloo run of the drop-in under that wrapper, stub engine per rank
+def _ddp_worker(rank, world, port, q):
+    import os
+
+    import torch.distributed as dist
+    from torch.nn.parallel import DistributedDataParallel
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+
+    class RankStub(StubEngine):
+        def train_grad(self, name, out):
+            return out.fill_(float(len(name)) * (rank + 1))  # rank-dependent gradients: DDP must average them
+
+    m = dropin.CatreB200(64, 64, max_batch=4)
+    m._engine = RankStub()
+    m._train_versions = {n: (p._version, p.data_ptr()) for n, p in m.named_parameters()}
+    dropin.CatreB200._engine_for_training = lambda self, device: _refresh(self)
+    ddp = DistributedDataParallel(m, broadcast_buffers=False, find_unused_parameters=True)
+    ok = True
+    for it in range(2):  # two iterations: the second forward fails if a reduction of the first never finished
+        B = 2
+        x = torch.randn(B, 64, 3).permute(0, 2, 1)
+        pose = torch.cat((torch.eye(3).expand(B, 3, 3), torch.ones(B, 3, 1)), 2)
+        _, loss = ddp(x, x, init_pose=pose, init_scale=torch.ones(B, 3), K_zoom=torch.eye(3).expand(B, 3, 3), gt_ego_rot=pose[:, :, :3],
+                      gt_trans=pose[:, :, 3], gt_scale=torch.ones(B, 3), obj_kps=torch.randn(B, 64, 3), sym_info=[None] * B,
+                      do_loss=True, cur_iter=it + 1)
+        m.zero_grad(set_to_none=True)
+        sum(loss.values()).backward()
+        for name, p in m.named_parameters():
+            if name in dropin.UNUSED_PARAMS:
+                ok = ok and p.grad is None
+            else:
+                ok = ok and bool((p.grad == len(name) * 1.5).all())  # mean of (1, 2) x len(name)
+    q.put((rank, ok))
+    dist.destroy_process_group()
+
+
+def test_dropin_under_ddp_gloo_world2():
+    import socket
+
+    import torch.multiprocessing as mp
+
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    port = s.getsockname()[1]
+    s.close()
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    procs = [ctx.Process(target=_ddp_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted(q.get(timeout=240) for _ in procs)
+    for p in procs:
+        p.join(60)
+    assert res == [(0, True), (1, True)]
