@@ -615,6 +615,7 @@ namespace {
 struct CudaTrainOps {
   cudaStream_t s;
   bool naive;
+  bool v2;  // CATRE_TRAIN_GEMM=v2: the 128 x BN register-prefetch GEMM (opt-in until it has been measured on the GPU)
   int64_t launches = 0;
   cudaError_t err = cudaSuccess;
   void note(cudaError_t st) { if (err == cudaSuccess && st != cudaSuccess) err = st; }
@@ -630,6 +631,11 @@ struct CudaTrainOps {
     if (p.M <= 0 || p.N <= 0 || bz <= 0) return;
     if (naive) {
       run(catre_train::KGemmNaive{p}, (unsigned)((p.M + 3) / 4), (unsigned)((p.N + 63) / 64), (unsigned)bz, 256);
+    } else if (v2) {
+      if (p.N <= 64) catre_train::tk_gemm_tiled2<64><<<dim3((unsigned)((p.M + 127) / 128), (unsigned)((p.N + 63) / 64), (unsigned)bz), 256, 0, s>>>(p);
+      else catre_train::tk_gemm_tiled2<128><<<dim3((unsigned)((p.M + 127) / 128), (unsigned)((p.N + 127) / 128), (unsigned)bz), 256, 0, s>>>(p);
+      ++launches;
+      note(cudaPeekAtLastError());
     } else {
       catre_train::tk_gemm_tiled<<<dim3((unsigned)((p.M + 63) / 64), (unsigned)((p.N + 63) / 64), (unsigned)bz), 256, 0, s>>>(p);
       ++launches;
@@ -1219,7 +1225,8 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   const float* Wp[catre_train::W_COUNT];
   for (int i = 0; i < kNumWeights; ++i) Wp[i] = e->dw.at(kWeights[i].name);
   const char* env = getenv("CATRE_TRAIN_NAIVE_GEMM");
-  CudaTrainOps ops{s, e->train_naive_gemm || (env && env[0] == '1')};
+  const char* env2 = getenv("CATRE_TRAIN_GEMM");
+  CudaTrainOps ops{s, e->train_naive_gemm || (env && env[0] == '1'), env2 && strcmp(env2, "v2") == 0};
   catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
   catre_train::TrainIn in{nullptr, obj_kps, pose, scale, K, gt_pose, gt_scale, B, n_sym_rots, n_sym, B - n_sym, out_pose, out_scale};
   in.x_pm = x_pm; in.tfd_pm = tfd_pm;

@@ -21,12 +21,16 @@ using std::min;
 #define __global__
 #define __shared__ static
 #define __launch_bounds__(n)
+#define __align__(n) __attribute__((aligned(n)))
 #include "../../catre_b200/csrc/train_gemm_tiled.cuh"
 
 using namespace catre_train;
 
 extern "C" void emu_gemm(const GemmP* p, int bz, int tiled) {
-  const unsigned gx = tiled ? (p->M + 63) / 64 : (p->M + 3) / 4, gy = (p->N + 63) / 64;
+  // tiled: 0 = KGemmNaive, 1 = tk_gemm_tiled, 2 = tk_gemm_tiled2 (BN chosen like CudaTrainOps::gemm does)
+  const int bn2 = p->N <= 64 ? 64 : 128;
+  const unsigned gx = tiled == 2 ? (p->M + 127) / 128 : tiled ? (p->M + 63) / 64 : (p->M + 3) / 4;
+  const unsigned gy = tiled == 2 ? (p->N + bn2 - 1) / bn2 : (p->N + 63) / 64;
   if (!tiled) {
     KGemmNaive k{*p};
     for (unsigned z = 0; z < (unsigned)bz; ++z)
@@ -43,7 +47,8 @@ extern "C" void emu_gemm(const GemmP* p, int bz, int tiled) {
         for (unsigned t = 0; t < 256; ++t)
           th.emplace_back([=]() {
             threadIdx.x = t; blockIdx.x = x; blockIdx.y = y; blockIdx.z = z;
-            tk_gemm_tiled(*p);
+            if (tiled == 2) { if (bn2 == 64) tk_gemm_tiled2<64>(*p); else tk_gemm_tiled2<128>(*p); }
+            else tk_gemm_tiled(*p);
           });
         for (auto& h : th) h.join();
       }

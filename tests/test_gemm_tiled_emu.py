@@ -46,12 +46,12 @@ def run(lib, tiled, A, sa, B, sb, C, sc, M, N, K, bias=None, sbias_b=0, relu=0, 
 
 def both(lib, make, **kw):
     outs = []
-    for tiled in (0, 1):
+    for tiled in (0, 1, 2):  # naive, tk_gemm_tiled, tk_gemm_tiled2
         arrs = make()
         run(lib, tiled, *arrs["args"], **kw, **arrs.get("kw", {}))
         outs.append(arrs["out"]().copy())
-    assert np.allclose(outs[0], outs[1], rtol=1e-5, atol=1e-5)
-    return outs[1]
+    assert np.allclose(outs[0], outs[1], rtol=1e-5, atol=1e-5) and np.allclose(outs[0], outs[2], rtol=1e-5, atol=1e-5)
+    return outs[2]
 
 
 def test_layer_bias_relu_edges(lib):
