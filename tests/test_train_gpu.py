@@ -75,8 +75,7 @@ def teardown_module(module):
             json.dump({"tolerance": GRAD_TOL, "tensors_checked": len(REPORT), "worst_relative_errors": worst}, f, indent=1)
 
 
-@pytest.mark.parametrize("naive", ["0", "1"])
-def test_train_step_matches_oracle(naive, monkeypatch):
+def _step_vs_oracle(naive, monkeypatch):
     monkeypatch.setenv("CATRE_TRAIN_NAIVE_GEMM", naive)  # 1 = the one-thread-per-output GEMM the CPU emulation verifies
     z = np.load(FIX)
     d, tgt, x_pm, tfd_pm = inputs()
@@ -96,13 +95,18 @@ def test_train_step_matches_oracle(naive, monkeypatch):
         if name in UNUSED:
             assert not bool(g.any()), name
         else:
-            check_grad(z, name, g, tag=f"gemm_naive={naive}/")
+            check_grad(z, name, g, tag=f"gemm_naive={naive},{os.environ.get('CATRE_TRAIN_GEMM', 'v1')}/")
     # deterministic: a second step reproduces the gradients bit for bit
     g1 = eng.train_grad("pcl_net.conv3.weight", torch.empty(512, 128, 1, device="cuda")).clone()
     eng.train_step(x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, tgt.gt_pose.cuda(), tgt.gt_scale.cuda(), tgt.sym_y.numpy(),
                    y_symmetry_rotations())
     assert torch.equal(g1, eng.train_grad("pcl_net.conv3.weight", torch.empty(512, 128, 1, device="cuda")))
     eng.close()
+
+
+@pytest.mark.parametrize("naive", ["0", "1"])
+def test_train_step_matches_oracle(naive, monkeypatch):
+    _step_vs_oracle(naive, monkeypatch)
 
 
 def test_dropin_training_loop():
@@ -149,3 +153,11 @@ def test_dropin_training_loop():
     with torch.no_grad():
         inf = model(x, tfd, init_pose=d.init_pose, init_scale=d.init_scale, K_zoom=d.K, cur_iter=1)
     assert (inf["pose_1"] - out3["pose_1"]).abs().max() < 1e-4 and (inf["scale_1"] - out3["scale_1"]).abs().max() < 1e-4
+
+
+def test_train_step_with_opt_in_gemm_v2(monkeypatch):
+    """The 128 x BN register-prefetch GEMM (CATRE_TRAIN_GEMM=v2; its source is verified by tests/test_gemm_tiled_emu.py on
+    the CPU).  Last in this file on purpose: it is the only piece of the training step that had not run on a GPU when it was
+    committed."""
+    monkeypatch.setenv("CATRE_TRAIN_GEMM", "v2")
+    _step_vs_oracle("0", monkeypatch)

@@ -23,8 +23,9 @@ def main():
         x_pm = (d.pcl - d.init_pose[:, :, 3].unsqueeze(1)).contiguous()
         tfd_pm = ((d.prior * d.init_scale.unsqueeze(1)) @ d.init_pose[:, :, :3].transpose(1, 2)).contiguous()
         gp, gs = tgt.gt_pose.cuda(), tgt.gt_scale.cuda()
-        for naive in ("0", "1"):
+        for naive, ver in (("0", "v1"), ("0", "v2"), ("1", "v1")):
             os.environ["CATRE_TRAIN_NAIVE_GEMM"] = naive
+            os.environ["CATRE_TRAIN_GEMM"] = ver
             eng = engine.Engine(1024, 8, "fp32", 0)
             eng.load_weights(w)
             step = lambda: eng.train_step(x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, gp, gs, tgt.sym_y.numpy(), rots)
@@ -38,7 +39,7 @@ def main():
                 step()
             b.record()
             torch.cuda.synchronize()
-            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": "naive" if naive == "1" else "tiled",
+            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": "naive" if naive == "1" else "tiled-" + ver,
                               "ms_per_step": a.elapsed_time(b) / n, "launches": eng.last_launch_count(),
                               "objects_per_s": B / (a.elapsed_time(b) / n / 1e3)}), flush=True)
             eng.close()
