@@ -61,11 +61,16 @@ LOSS_ORDER = ("loss_PM_R", "loss_rot", "loss_yaxis_rot", "loss_trans_xy", "loss_
 
 
 # the last case has real (un-resized) weights and 4096 rows, which switches the weight-gradient GEMMs to split-K
-@pytest.mark.parametrize("B,N,seed,reposed", [(3, 64, 21, False), (2, 128, 22, True), (2, 1024, 23, False)])
-def test_emulated_chain_matches_oracle(emu, B, N, seed, reposed):
+# ... and two edge shapes: a single symmetric object with a point count that is no multiple of anything (N = 100: ragged
+# tiles everywhere, one GroupNorm chunk), and an all-asymmetric batch with N = 130 (64 GroupNorm chunks, some empty)
+@pytest.mark.parametrize("B,N,seed,reposed,sym", [(3, 64, 21, False, None), (2, 128, 22, True, None), (2, 1024, 23, False, None),
+                                                  (1, 100, 24, False, None), (2, 130, 25, True, False)])
+def test_emulated_chain_matches_oracle(emu, B, N, seed, reposed, sym):
     torch.set_num_threads(max(1, (os.cpu_count() or 2) // 2))
     w = co.resize_conv_p(synth.load_weights(), N)
     batch, tgt = synth.make_train_batch(B, N, seed, round_robin_cls=True)  # classes 0, 1, 2: symmetric and asymmetric
+    if sym is not None:
+        tgt.sym_y[:] = sym
     sym_rots = to.y_symmetry_rotations()
     sym_info = [sym_rots if s else None for s in tgt.sym_y]
     pose, scale = batch.init_pose, batch.init_scale
