@@ -108,6 +108,70 @@ def greedy_matches(overlaps, rt_overlaps, pred_class_ids, gt_class_ids, iou_3d_t
     return gt_matches, pred_matches
 
 
+def greedy_matches_batch(items, iou_3d_thresholds, degree_thesholds, shift_thesholds, score_threshold=0):
+    """greedy_matches for many images at once.  ``items`` = [(overlaps [P,G], rt_overlaps [P,G,2], pred_class_ids [P],
+    gt_class_ids [G])] over score-sorted predictions; returns [(gt_matches [D,T,S,G], pred_matches [D,T,S,P])], equal to
+    the per-image loops (test_utils.py:354-387) entry for entry.
+
+    The loops are sequential in the prediction (score order) and in its candidate list (IoU order) but independent across
+    images and across the D*T*S threshold triples, so every step runs as one array operation over [images, D, T, S]:
+    a triple of an image is `alive` while its current prediction is still looking for a ground truth; a candidate that is
+    already taken is skipped, one that fails a threshold ends the search (`break`), one of another class is skipped, the
+    first that passes is matched.  The candidate order of every row is numpy's argsort of that row, as in the reference
+    (ties keep numpy's order)."""
+    n = len(items)
+    nd, nt, ns = len(degree_thesholds), len(shift_thesholds), len(iou_3d_thresholds)
+    if n == 0:
+        return []
+    p_cnt = np.array([it[0].shape[0] for it in items])
+    g_cnt = np.array([it[0].shape[1] for it in items])
+    pmax, gmax = int(p_cnt.max()), int(g_cnt.max())
+    out_shape = (n, nd, nt, ns)
+    gt_m = -1 * np.ones(out_shape + (max(gmax, 1),))
+    pred_m = -1 * np.ones(out_shape + (max(pmax, 1),))
+    if pmax and gmax:
+        ov = np.full((n, pmax, gmax), -np.inf)
+        rt = np.full((n, pmax, gmax, 2), np.inf)
+        order = np.zeros((n, pmax, gmax), dtype=np.int64)
+        n_cand = np.zeros((n, pmax), dtype=np.int64)  # candidates of a prediction after the score_threshold cut
+        pcls = np.full((n, pmax), -1, dtype=np.int64)
+        gcls = np.full((n, gmax), -2, dtype=np.int64)
+        for k, (o, r, pc, gc) in enumerate(items):
+            P, G = o.shape
+            if P == 0 or G == 0:
+                continue
+            ov[k, :P, :G], rt[k, :P, :G] = o, r
+            pcls[k, :P], gcls[k, :G] = pc, gc
+            for i in range(P):
+                od = np.argsort(o[i])[::-1]
+                low = np.where(o[i, od] < score_threshold)[0]
+                order[k, i, :G] = od
+                n_cand[k, i] = low[0] if low.size else G
+        iou_t = np.asarray(iou_3d_thresholds, dtype=np.float64).reshape(1, 1, 1, ns)
+        deg_t = np.asarray(degree_thesholds, dtype=np.float64).reshape(1, nd, 1, 1)
+        sh_t = np.asarray(shift_thesholds, dtype=np.float64).reshape(1, 1, nt, 1)
+        rows = np.arange(n)
+        for i in range(pmax):
+            alive = np.broadcast_to((n_cand[:, i] > 0).reshape(n, 1, 1, 1), out_shape).copy()
+            for r in range(gmax):
+                alive &= (r < n_cand[:, i]).reshape(n, 1, 1, 1)
+                if not alive.any():
+                    break
+                j = order[:, i, r]
+                free = np.take_along_axis(gt_m, j.reshape(n, 1, 1, 1, 1), axis=4)[..., 0] <= -1
+                o_ij, r_ij = ov[rows, i, j], rt[rows, i, j]
+                fail = (o_ij.reshape(n, 1, 1, 1) < iou_t) | (r_ij[:, 0].reshape(n, 1, 1, 1) > deg_t) | (r_ij[:, 1].reshape(n, 1, 1, 1) > sh_t)
+                consider = alive & free
+                alive &= ~(consider & fail)
+                hit = consider & ~fail & (pcls[:, i] == gcls[rows, j]).reshape(n, 1, 1, 1)
+                if hit.any():
+                    kk, dd, tt, ss = np.nonzero(hit)
+                    gt_m[kk, dd, tt, ss, j[kk]] = i
+                    pred_m[kk, dd, tt, ss, i] = j[kk]
+                    alive &= ~hit
+    return [(gt_m[k, ..., :g_cnt[k]].copy(), pred_m[k, ..., :p_cnt[k]].copy()) for k in range(n)]
+
+
 def _sorted_image(gt_class_ids, gt_RTs, gt_scales, gt_handle_visibility, pred_class_ids, pred_scores, pred_RTs, pred_scales):
     num_pred = len(pred_class_ids)
     indices = np.zeros(0)
@@ -139,7 +203,7 @@ def match_images(results: List[Dict[str, np.ndarray]], synset_names, iou_3d_thre
                  pair_metrics_fn=None):
     """Batched form: ``results[k]`` has the keys of one entry of the reference's ``final_results`` that the matcher
     reads (gt_class_ids, gt_RTs, gt_scales, gt_handle_visibility, pred_class_ids, pred_scores, pred_RTs, pred_scales).
-    One GPU launch for all images, then the per-image host matching.  Returns [(gt_matches, pred_matches, indices)]."""
+    One GPU launch for all images, then the matching of all images at once (greedy_matches_batch).  Returns [(gt_matches, pred_matches, indices)]."""
     ims, idxs = [], []
     for r in results:
         im, ind = _sorted_image(r["gt_class_ids"], r["gt_RTs"], r["gt_scales"], r["gt_handle_visibility"], r["pred_class_ids"],
@@ -147,11 +211,9 @@ def match_images(results: List[Dict[str, np.ndarray]], synset_names, iou_3d_thre
         ims.append(im)
         idxs.append(ind)
     pm = (pair_metrics_fn or pair_metrics_batch)(ims, synset_names)
-    out = []
-    for im, ind, (ov, rt) in zip(ims, idxs, pm):
-        gt_m, pred_m = greedy_matches(ov, rt, im["pred_cls"], im["gt_cls"], iou_3d_thresholds, degree_thesholds, shift_thesholds)
-        out.append((gt_m, pred_m, ind))
-    return out
+    matched = greedy_matches_batch([(ov, rt, im["pred_cls"], im["gt_cls"]) for im, (ov, rt) in zip(ims, pm)], iou_3d_thresholds,
+                                   degree_thesholds, shift_thesholds)
+    return [(gt_m, pred_m, ind) for (gt_m, pred_m), ind in zip(matched, idxs)]
 
 
 def compute_ap_from_matches_scores(pred_match, pred_scores, gt_match) -> float:

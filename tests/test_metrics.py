@@ -112,3 +112,25 @@ def test_cuda_map_equals_reference():
     want = np.load(GOLDEN)["aps"]
     got = metrics.compute_combination_mAP(final_results(), SYNSET, MAP_DEG, MAP_SHIFT, MAP_IOU)
     assert np.array_equal(got, want)
+
+
+def test_batched_matching_equals_reference_loops_on_random_inputs():
+    """greedy_matches_batch (all images and threshold triples as array operations) == the reference's per-image loops
+    (oracle restatement), entry for entry: ragged sizes, empty images, tied and zero overlaps, an IoU threshold of 0,
+    NaN pose errors, a score threshold."""
+    g = np.random.RandomState(11)
+    items = []
+    for k in range(300):
+        P, G = g.randint(0, 9), g.randint(0, 9)
+        ov = np.round(g.rand(P, G), 1).astype(np.float32)  # one decimal: plenty of ties
+        ov[g.rand(P, G) < 0.3] = 0.0
+        rt = np.stack((g.rand(P, G) * 20, g.rand(P, G) * 8), axis=-1).astype(np.float32)
+        rt[g.rand(P, G) < 0.05] = np.nan
+        items.append((ov, rt, g.randint(1, 4, size=P), g.randint(1, 4, size=G)))
+    for iou_t, deg_t, sh_t, score_t in (([0.0, 0.25, 0.5], [5, 10, 360], [2, 5, 100], 0), ([0.3], [360], [100], 0.2)):
+        got = metrics.greedy_matches_batch(items, iou_t, deg_t, sh_t, score_t)
+        for (ov, rt, pc, gc), (gm, pm) in zip(items, got):
+            want_g, want_p = mo.greedy_matches(ov, rt, pc, gc, iou_t, deg_t, sh_t, score_t)
+            assert gm.shape == want_g.shape and pm.shape == want_p.shape and gm.dtype == want_g.dtype
+            assert np.array_equal(gm, want_g) and np.array_equal(pm, want_p)
+    assert metrics.greedy_matches_batch([], [0.5], [5], [2]) == []
