@@ -58,8 +58,8 @@ def batch_data_test(cfg: Any, data: Sequence[Dict[str, Any]], device: str = "cud
     lg = dict(dtype=torch.long, device=device, non_blocking=True)
 
     def cat(attr, kw):
-        parts = [_tensor_of(getattr(d["instances"], attr)) for d in data]
-        return torch.cat([torch.as_tensor(p) for p in parts], dim=0).to(**kw)
+        parts = [torch.as_tensor(_tensor_of(getattr(d["instances"], attr))) for d in data]
+        return (parts[0] if len(parts) == 1 else torch.cat(parts, dim=0)).to(**kw)  # one image per item is the usual case
 
     batch: Dict[str, Any] = {}
     batch["obj_cls"] = cat("obj_classes", lg)
@@ -75,13 +75,13 @@ def batch_data_test(cfg: Any, data: Sequence[Dict[str, Any]], device: str = "cud
     for i_im, d in enumerate(data):
         n_inst = len(d["instances"])
         sym_infos.extend(list(getattr(d["instances"], "obj_sym_infos", [None] * n_inst)))
-        for i_inst in range(n_inst):
-            im_ids.append(i_im)
-            inst_ids.append(i_inst)
-            k_list.append(torch.as_tensor(d["cam"]))
+        im_ids.extend([i_im] * n_inst)
+        inst_ids.extend(range(n_inst))
+        if n_inst:
+            k_list.append(torch.as_tensor(d["cam"]).reshape(1, 3, 3).expand(n_inst, 3, 3))  # one K per instance (batch_test.py:41-47)
     batch["im_id"] = torch.tensor(im_ids, dtype=dtype, device=device)  # float, like the reference (batch_test.py:45)
     batch["inst_id"] = torch.tensor(inst_ids, dtype=dtype, device=device)
-    batch["K"] = (torch.stack(k_list, dim=0) if k_list else torch.zeros(0, 3, 3)).to(**fl)
+    batch["K"] = (torch.cat(k_list, dim=0) if k_list else torch.zeros(0, 3, 3)).to(**fl).contiguous()
     batch["sym_info"] = sym_infos
     batch["pcl"] = cat("pcl", fl)
     batch["obj_kps"] = batch["obj_mean_points"]
@@ -349,7 +349,12 @@ class PosePredictionCollector:
         self.reset()
 
     def reset(self):
-        self._rows: List[torch.Tensor] = []  # each [n, META + (K+1)*15] float64
+        k1 = self.n_iter_test + 1
+        self._meta: List[List[float]] = []  # one metadata row per record
+        self._order: List[int] = []  # record -> row of the concatenated pose tensors
+        self._poses: List[List[torch.Tensor]] = [[] for _ in range(k1)]  # per iteration, one [n, 3, 4] tensor per item
+        self._scales: List[List[torch.Tensor]] = [[] for _ in range(k1)]
+        self._n_seen = 0
         self._scenes: List[str] = []
 
     def _maybe_adapt_label_cls_name(self, label):
@@ -362,13 +367,12 @@ class PosePredictionCollector:
         return self.train_objs.index(name), name
 
     def process(self, inputs, batch, outputs, out_dict):
+        """Only bookkeeping here (this runs once per loader item underneath the next launch): the per-record metadata and
+        references to the item's pose tensors; the numeric rows are assembled for all items at once in rows()."""
         k1 = self.n_iter_test + 1
-        poses = torch.stack([out_dict[f"pose_{i}"].detach().cpu() for i in range(k1)], dim=1).double()  # [n, K+1, 3, 4]
-        scales = torch.stack([out_dict[f"scale_{i}"].detach().cpu() for i in range(k1)], dim=1).double()
-        n = poses.shape[0]
-        im_ids = batch["im_id"].detach().cpu().numpy().tolist()
-        inst_ids = batch["inst_id"].detach().cpu().numpy().tolist()
-        labels = batch["obj_cls"].detach().cpu().numpy().tolist()
+        im_ids = batch["im_id"].detach().cpu().tolist()
+        inst_ids = batch["inst_id"].detach().cpu().tolist()
+        labels = batch["obj_cls"].detach().cpu().tolist()
         names = self.train_objs if self.train_objs is not None else self.obj_names
         meta_rows, order = [], []
         for im_i, (inp, output) in enumerate(zip(inputs, outputs)):  # records are emitted image by image
@@ -384,16 +388,26 @@ class PosePredictionCollector:
                 handle = float(inst.mug_handle[inst_id]) if inst is not None and hasattr(inst, "mug_handle") else 1.0
                 meta_rows.append([self._scenes.index(scene_id), int(im_id), self.obj2id[names[labels[out_i]]], score, handle,
                                   output["time"]])
-                order.append(out_i)
-        if not order:
-            return
-        idx = torch.tensor(order, dtype=torch.long)
-        body = torch.cat((poses.reshape(n, k1, 12), scales.reshape(n, k1, 3)), dim=2).reshape(n, k1 * 15)
-        self._rows.append(torch.cat((torch.tensor(meta_rows, dtype=torch.float64), body[idx]), dim=1))
+                order.append(self._n_seen + out_i)
+        self._n_seen += len(labels)
+        self._meta.extend(meta_rows)
+        self._order.extend(order)
+        for i in range(k1):
+            self._poses[i].append(out_dict[f"pose_{i}"])
+            self._scales[i].append(out_dict[f"scale_{i}"])
 
     def rows(self) -> torch.Tensor:
-        width = self._META + (self.n_iter_test + 1) * 15
-        return torch.cat(self._rows, dim=0) if self._rows else torch.zeros((0, width), dtype=torch.float64)
+        """[records, META + (K+1)*15] float64: metadata, then per iteration the 3x4 pose and the 3 scales."""
+        k1 = self.n_iter_test + 1
+        width = self._META + k1 * 15
+        if not self._order:
+            return torch.zeros((0, width), dtype=torch.float64)
+        poses = torch.stack([torch.cat([t.detach().cpu() for t in self._poses[i]], dim=0) for i in range(k1)], dim=1).double()
+        scales = torch.stack([torch.cat([t.detach().cpu() for t in self._scales[i]], dim=0) for i in range(k1)], dim=1).double()
+        n = poses.shape[0]
+        body = torch.cat((poses.reshape(n, k1, 12), scales.reshape(n, k1, 3)), dim=2).reshape(n, k1 * 15)
+        idx = torch.tensor(self._order, dtype=torch.long)
+        return torch.cat((torch.tensor(self._meta, dtype=torch.float64), body[idx]), dim=1)
 
     def evaluate(self):
         rows, scenes = self.rows(), list(self._scenes)
