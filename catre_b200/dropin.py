@@ -309,6 +309,7 @@ class CatreB200(nn.Module):
         bridged = _LossBridge.apply(losses, torch.tensor(present, device=losses.device), self, [n for n, _ in used],
                                     *[p for _, p in used])
         loss_dict = {n: bridged[i] for i, n in enumerate(_engine.TRAIN_LOSS_NAMES) if present[i]}
+        _put_vis_scalars(cur_iter, pose, init_pose, K_zoom, gt_ego_rot, gt_trans)
         return {f"pose_{cur_iter}": pose, f"scale_{cur_iter}": scale}, loss_dict
 
     # ---- fused K-loop (additive API) ------------------------------------------------------------------
@@ -335,6 +336,44 @@ class CatreB200(nn.Module):
             out[f"pose_{i}"] = poses[i]
             out[f"scale_{i}"] = scales[i]
         return out
+
+
+def vis_scalars(cur_iter: int, pose, init_pose, K, gt_rot, gt_trans) -> Dict[str, float]:
+    """The `vis/*` scalars the reference's training forward logs (CATRE_disR_shared.py:127-146): mean rotation error
+    [deg] and translation error [cm] of the batch (lib/pysixd/pose_error.py:359-374, 406-417) and, for object 0, the
+    per-axis translation error [cm], the predicted / ground-truth translation and the raw translation deltas of the head
+    (recovered from the pose update, pose_scale_from_delta_init.py:47-95).  Host work on [B, 3, 4] values."""
+    P = pose.detach().double().cpu().numpy()
+    P0 = init_pose.detach().double().cpu().numpy()
+    G, gt = gt_rot.detach().double().cpu().numpy(), gt_trans.detach().double().cpu().numpy()
+    Kh = K.detach().double().cpu().numpy()
+    tr = np.einsum("bij,bij->b", P[:, :, :3], G)  # trace(R_est R_gt^T)
+    re_deg = np.rad2deg(np.arccos(np.clip(0.5 * (np.minimum(tr, 3.0) - 1.0), -1.0, 1.0)))
+    te = np.linalg.norm(gt - P[:, :, 3], axis=1)
+    t, t0 = P[0, :, 3], P0[0, :, 3]
+    dz = t[2] / t0[2]
+    dx = (t[0] / t[2] - t0[0] / t0[2]) * Kh[0, 0, 0]
+    dy = (t[1] / t[2] - t0[1] / t0[2]) * Kh[0, 1, 1]
+    i = cur_iter
+    out = {f"vis/error_R_{i}": float(re_deg.astype(np.float32).mean()), f"vis/error_t_{i}": float(te.astype(np.float32).mean()) * 100}
+    for a, ax in enumerate("xyz"):
+        out[f"vis/error_t{ax}_{i}"] = float(abs(t[a] - gt[0, a]) * 100)
+        out[f"vis/t{ax}_pred_{i}"] = float(t[a])
+        out[f"vis/t{ax}_delta_{i}"] = float((dx, dy, dz)[a])
+        out[f"vis/t{ax}_gt_{i}"] = float(gt[0, a])
+    return out
+
+
+def _put_vis_scalars(cur_iter, pose, init_pose, K, gt_rot, gt_trans) -> None:
+    """storage.put_scalars(**vis_dict) as the reference does (CATRE_disR_shared.py:163-164) -- when detectron2's event
+    storage is there (inside the reference's training loop); silently nothing otherwise."""
+    try:
+        from detectron2.utils.events import get_event_storage
+
+        storage = get_event_storage()
+    except Exception:
+        return
+    storage.put_scalars(**vis_scalars(cur_iter, pose, init_pose, K, gt_rot, gt_trans))
 
 
 def check_loss_cfg(cfg: Any) -> None:

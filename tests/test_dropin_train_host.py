@@ -155,3 +155,24 @@ def test_dropin_under_ddp_gloo_world2():
     for p in procs:
         p.join(60)
     assert res == [(0, True), (1, True)]
+
+
+def test_vis_scalars_follow_the_reference_formulas():
+    """vis/* scalars (CATRE_disR_shared.py:127-146): checked against the oracle's pose update and plain formulas."""
+    from oracle import catre_oracle as co
+
+    g = torch.Generator().manual_seed(3)
+    b = synth.make_batch(3, 64, 5)
+    d_t = torch.tensor([[3.0, -2.0, 1.01], [0.5, 0.2, 0.99], [-1.0, 4.0, 1.0]])
+    rot, t, s = co.pose_update(torch.eye(3).expand(3, 3, 3), d_t, torch.zeros(3, 3), b.init_pose[:, :, :3], b.init_pose[:, :, 3],
+                               b.init_scale, b.K)
+    pose = torch.cat((rot, t.reshape(3, 3, 1)), dim=2)
+    gt_rot = b.init_pose[:, :, :3]  # zero rotation error
+    gt_t = b.init_pose[:, :, 3] + torch.randn(3, 3, generator=g) * 0.01
+    v = dropin.vis_scalars(2, pose, b.init_pose, b.K, gt_rot, gt_t)
+    assert len(v) == 14 and abs(v["vis/error_R_2"]) < 0.05
+    assert abs(v["vis/error_t_2"] - 100 * float((gt_t - t).norm(dim=1).mean())) < 1e-4
+    for a, ax in enumerate("xyz"):
+        assert abs(v[f"vis/t{ax}_delta_2"] - float(d_t[0, a])) < 1e-3  # the head's raw deltas, recovered
+        assert abs(v[f"vis/t{ax}_pred_2"] - float(t[0, a])) < 1e-7 and abs(v[f"vis/t{ax}_gt_2"] - float(gt_t[0, a])) < 1e-7
+        assert abs(v[f"vis/error_t{ax}_2"] - 100 * abs(float(t[0, a] - gt_t[0, a]))) < 1e-5
