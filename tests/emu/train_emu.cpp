@@ -14,6 +14,7 @@ using namespace catre_train;
 namespace {
 struct EmuOps {
   long launches = 0;
+  double gemm_macs = 0.0;  // multiply-adds of all GEMM launches (the training step's algorithmic work)
   template <class KF>
   void run(const KF& k, unsigned gx, unsigned gy, unsigned gz, unsigned nt) {
     ++launches;
@@ -24,6 +25,7 @@ struct EmuOps {
   }
   void zero(void* p, size_t bytes) { memset(p, 0, bytes); }
   void gemm(const GemmP& p, int batch_or_splits) {
+    gemm_macs += (double)p.M * p.N * p.K * (p.splits > 1 ? 1 : batch_or_splits);
     run(KGemmNaive{p}, (unsigned)((p.M + 3) / 4), (unsigned)((p.N + 63) / 64), (unsigned)batch_or_splits, 256);
   }
 };
@@ -32,7 +34,7 @@ struct EmuOps {
 extern "C" int emu_train_step(const float* const* weights, int B, int N, const float* pcl, const float* kps, const float* pose,
                               const float* scale, const float* K, const float* gt_pose, const float* gt_scale,
                               const unsigned char* is_sym, const float* sym_rots, int n_rots, float* pose_out, float* scale_out,
-                              float* losses, float* const* grads, long* launches, const float* x_pm, const float* tfd_pm) {
+                              float* losses, float* const* grads, long* launches, const float* x_pm, const float* tfd_pm, double* gemm_macs) {
   if (n_rots > TrainWs::kMaxSymRots) return -1;
   TrainWs w;
   const size_t bytes = ws_layout(w, B, N, nullptr);
@@ -53,5 +55,6 @@ extern "C" int emu_train_step(const float* const* weights, int B, int N, const f
   memcpy(losses, w.losses, 6 * sizeof(float));
   for (int i = 0; i < W_COUNT; ++i) memcpy(grads[i], w.G[i], weight_numel(i, N) * sizeof(float));
   if (launches) *launches = ops.launches;
+  if (gemm_macs) *gemm_macs = ops.gemm_macs;
   return 0;
 }
