@@ -138,6 +138,7 @@ struct catre_engine {
   char* tws_mem = nullptr;
   int tws_maxB = 0;
   std::map<std::string, bool> dw_dirty;  // tensors refreshed by catre_train_set_weight since the last pack
+  float loss_w[4] = {1.0f, 1.0f, 1.0f, 1.0f};  // PM_LW, ROT_LW, TRANS_LW, SCALE_LW
   bool train_naive_gemm = false;         // CATRE_TRAIN_NAIVE_GEMM=1: one-thread-per-output GEMM (debug reference)
 
   // ---- accounting
@@ -1183,6 +1184,17 @@ int catre_train_set_weight(catre_engine* e, const char* name, const float* src_d
   return CATRE_OK;
 }
 
+int catre_train_set_loss_weights(catre_engine* e, float pm_lw, float rot_lw, float trans_lw, float scale_lw) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  const float w[4] = {pm_lw, rot_lw, trans_lw, scale_lw};
+  for (float v : w)
+    if (!(v > 0.0f) || !isfinite(v))
+      return fail(e, CATRE_ERR_UNSUPPORTED, "loss weights must be finite and > 0 (got %g %g %g %g): a zero weight removes the term from "
+                  "the reference's loss dict, which this engine does not implement", pm_lw, rot_lw, trans_lw, scale_lw);
+  for (int i = 0; i < 4; ++i) e->loss_w[i] = w[i];
+  return CATRE_OK;
+}
+
 int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, const float* obj_kps, const float* pose,
                      const float* scale, const float* K, const float* gt_pose, const float* gt_scale,
                      const uint8_t* is_sym_host, const float* sym_rots_host, int32_t n_sym_rots, int32_t B, float* out_pose,
@@ -1230,6 +1242,7 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
   catre_train::TrainIn in{nullptr, obj_kps, pose, scale, K, gt_pose, gt_scale, B, n_sym_rots, n_sym, B - n_sym, out_pose, out_scale};
   in.x_pm = x_pm; in.tfd_pm = tfd_pm;
+  in.w_pm = e->loss_w[0]; in.w_rot = e->loss_w[1]; in.w_trans = e->loss_w[2]; in.w_scale = e->loss_w[3];
   chain.forward(in);
   chain.loss(in);
   chain.backward(in);

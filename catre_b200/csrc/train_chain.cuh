@@ -105,6 +105,7 @@ struct TrainIn {
   int B, n_rots, n_sym, n_nosym;                                    // is_sym / sym_rots already staged in the workspace
   float *pose_out, *scale_out;
   const float *x_pm = nullptr, *tfd_pm = nullptr;
+  float w_pm = 1.0f, w_rot = 1.0f, w_trans = 1.0f, w_scale = 1.0f;  // LOSS_CFG.*_LW
 };
 
 template <class Ops>
@@ -249,7 +250,7 @@ struct Chain {
 
   void loss(const TrainIn& in) {
     o.run(KLoss{in.pose_out, in.scale_out, in.gt_pose, in.gt_scale, in.kps, w.sym_rots, w.is_sym, w.lossp, w.dpose, in.B, N,
-                in.n_rots, in.n_sym, in.n_nosym}, cdiv(in.B, 32), 1, 1, 32);
+                in.n_rots, in.n_sym, in.n_nosym, in.w_pm, in.w_rot, in.w_trans, in.w_scale}, cdiv(in.B, 32), 1, 1, 32);
     o.run(KLossSum{w.lossp, w.losses, in.B}, 1, 1, 1, 32);
   }
 

@@ -464,6 +464,7 @@ struct KPoseFwd {
 struct KLoss {
   const float *pose, *scale, *gt_pose, *gt_scale, *kps, *sym_rots; const unsigned char* is_sym;
   float *lossp, *dpose; int B, N, n_rots, n_sym, n_nosym;
+  float w_pm, w_rot, w_trans, w_scale;  // LOSS_CFG.PM_LW, ROT_LW, TRANS_LW, SCALE_LW (all 1 in the shipped config)
   TK_HD void operator()(const Idx& i) const {
     const int b = i.bx * i.nt + i.tx;
     if (b >= B) return;
@@ -490,7 +491,7 @@ struct KLoss {
     const float* sg = gt_scale + (size_t)b * 3;
     float dR[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ds[3] = {0, 0, 0};
     double pm = 0.0;
-    const float inv_bn = 1.0f / ((float)B * (float)N);
+    const float inv_bn = w_pm / ((float)B * (float)N);
     for (int n = 0; n < N; ++n) {
       const float* k = kps + ((size_t)b * N + n) * 3;
       const float sk[3] = {k[0] * s[0], k[1] * s[1], k[2] * s[2]};
@@ -506,26 +507,26 @@ struct KLoss {
       for (int c = 0; c < 3; ++c) ds[c] += (R[c] * de[0] + R[3 + c] * de[1] + R[6 + c] * de[2]) * k[c];
     }
     float* L = lossp + (size_t)b * 6;
-    L[0] = (float)(pm / ((double)B * N));  // 3 * mean over B*N*3
+    L[0] = w_pm * (float)(pm / ((double)B * N));  // PM_LW * 3 * mean over B*N*3
     L[1] = L[2] = 0.0f;
     if (sym) {
       float a = 0.0f;
-      for (int r = 0; r < 3; ++r) { const float d = R[r * 3 + 1] - G[r * 3 + 1]; a += fabsf(d); dR[r * 3 + 1] += tk_sign(d) / (3.0f * n_sym); }
-      L[2] = a / (3.0f * n_sym);
+      for (int r = 0; r < 3; ++r) { const float d = R[r * 3 + 1] - G[r * 3 + 1]; a += fabsf(d); dR[r * 3 + 1] += w_rot * tk_sign(d) / (3.0f * n_sym); }
+      L[2] = w_rot * a / (3.0f * n_sym);
     } else {
       float tr = 0.0f;
-      for (int e = 0; e < 9; ++e) { tr += R[e] * G[e]; dR[e] += -G[e] / (4.0f * n_nosym); }
-      L[1] = (3.0f - tr) * 0.25f / n_nosym;
+      for (int e = 0; e < 9; ++e) { tr += R[e] * G[e]; dR[e] += -w_rot * G[e] / (4.0f * n_nosym); }
+      L[1] = w_rot * (3.0f - tr) * 0.25f / n_nosym;
     }
     float* D = dpose + (size_t)b * 15;
     for (int e = 0; e < 9; ++e) D[e] = dR[e];
     const float dx = Pp[3] - Gp[3], dy = Pp[7] - Gp[7], dz = Pp[11] - Gp[11];
-    L[3] = (fabsf(dx) + fabsf(dy)) / (2.0f * B);
-    L[4] = fabsf(dz) / (float)B;
-    D[9] = tk_sign(dx) / (2.0f * B); D[10] = tk_sign(dy) / (2.0f * B); D[11] = tk_sign(dz) / (float)B;
+    L[3] = w_trans * (fabsf(dx) + fabsf(dy)) / (2.0f * B);
+    L[4] = w_trans * fabsf(dz) / (float)B;
+    D[9] = w_trans * tk_sign(dx) / (2.0f * B); D[10] = w_trans * tk_sign(dy) / (2.0f * B); D[11] = w_trans * tk_sign(dz) / (float)B;
     float ls = 0.0f;
-    for (int c = 0; c < 3; ++c) { const float d = s[c] - sg[c]; ls += fabsf(d); D[12 + c] = ds[c] + tk_sign(d) / (3.0f * B); }
-    L[5] = ls / (3.0f * B);
+    for (int c = 0; c < 3; ++c) { const float d = s[c] - sg[c]; ls += fabsf(d); D[12 + c] = ds[c] + w_scale * tk_sign(d) / (3.0f * B); }
+    L[5] = w_scale * ls / (3.0f * B);
   }
 };
 // losses[j] = sum_b lossp[b, j] in object order.  grid (1), nt >= 6

@@ -43,12 +43,14 @@ UNUSED_PARAMS = ("rot_head.rot_head_x.norm.weight", "rot_head.rot_head_x.norm.bi
 # loss configuration the training step implements (configs/catre/NOCS_REAL/aug05_..._120e.py:115-134 over
 # configs/_base_/catre_base.py); anything else is refused
 _REQUIRED_LOSS_CFG = {
-    "PM_LOSS_SYM": True, "PM_NORM_BY_EXTENT": False, "PM_R_ONLY": True, "PM_WITH_SCALE": True, "PM_LW": 1.0,
+    "PM_LOSS_SYM": True, "PM_NORM_BY_EXTENT": False, "PM_R_ONLY": True, "PM_WITH_SCALE": True,
     "PM_LOSS_TYPE": "L1", "PM_USE_BBOX": False,
-    "ROT_LOSS_TYPE": "angular", "ROT_LW": 1.0, "ROT_YAXIS_LOSS_TYPE": "L1",
-    "TRANS_LOSS_TYPE": "L1", "TRANS_LOSS_DISENTANGLE": True, "TRANS_LW": 1.0,
-    "SCALE_LOSS_TYPE": "L1", "SCALE_LW": 1.0,
+    "ROT_LOSS_TYPE": "angular", "ROT_YAXIS_LOSS_TYPE": "L1",
+    "TRANS_LOSS_TYPE": "L1", "TRANS_LOSS_DISENTANGLE": True,
+    "SCALE_LOSS_TYPE": "L1",
 }
+# the four loss weights are free (> 0): (config key, shipped value)
+_LOSS_WEIGHTS = (("PM_LW", 1.0), ("ROT_LW", 1.0), ("TRANS_LW", 1.0), ("SCALE_LW", 1.0))
 
 
 class _LossBridge(torch.autograd.Function):
@@ -221,6 +223,7 @@ class CatreB200(nn.Module):
         self._packed_key = None
         self._train_versions: Optional[Dict[str, Tuple[int, int]]] = None  # per tensor (version, data_ptr) the engine's training copy holds
         self._train_step_id = 0
+        self._loss_w: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)  # what the engine currently holds
 
     # ---- engine plumbing -----------------------------------------------------------------------
     def _weights_key(self):
@@ -287,12 +290,15 @@ class CatreB200(nn.Module):
         if gt_ego_rot is None or gt_trans is None or gt_scale is None or obj_kps is None or sym_info is None:
             raise ValueError("do_loss=True needs gt_ego_rot, gt_trans, gt_scale, obj_kps and sym_info "
                              "(CATRE_disR_shared.py:126, 191, 224)")
-        check_loss_cfg(self.cfg)
+        loss_w = check_loss_cfg(self.cfg)
         is_sym, sym_rots = split_sym_info(sym_info)
         if len(is_sym) != x.shape[0]:
             raise ValueError(f"sym_info has {len(is_sym)} entries for a batch of {x.shape[0]}")
         with torch.no_grad():
             eng = self._engine_for_training(x.device)
+            if loss_w != self._loss_w:
+                eng.train_set_loss_weights(*loss_w)
+                self._loss_w = loss_w
             f32 = lambda t: t.detach().float().contiguous()
             gt_pose = torch.cat((f32(gt_ego_rot), f32(gt_trans).reshape(-1, 3, 1)), dim=2).contiguous()
             pose, scale, losses = eng.train_step(x.detach().transpose(1, 2).contiguous().float(),
@@ -376,10 +382,15 @@ def _put_vis_scalars(cur_iter, pose, init_pose, K, gt_rot, gt_trans) -> None:
     storage.put_scalars(**vis_scalars(cur_iter, pose, init_pose, K, gt_rot, gt_trans))
 
 
-def check_loss_cfg(cfg: Any) -> None:
-    """The training step implements the shipped LOSS_CFG only; a config object that sets something else is refused
-    (absent keys take the shipped values)."""
+def check_loss_cfg(cfg: Any) -> Tuple[float, float, float, float]:
+    """The training step implements the shipped LOSS_CFG's loss types; a config object that sets something else is refused
+    (absent keys take the shipped values).  Returns the loss weights (PM_LW, ROT_LW, TRANS_LW, SCALE_LW), which may be any
+    positive numbers; a zero weight (the reference then drops the term from its dict) is refused."""
     bad = []
+    weights = tuple(float(_cfg_get(cfg, "MODEL.CATRE.LOSS_CFG." + k, d)) for k, d in _LOSS_WEIGHTS)
+    for (k, _), v in zip(_LOSS_WEIGHTS, weights):
+        if not v > 0:
+            bad.append(f"{k}={v!r} (implemented: > 0)")
     for key, want in _REQUIRED_LOSS_CFG.items():
         got = _cfg_get(cfg, "MODEL.CATRE.LOSS_CFG." + key, want)
         if (got.lower() if isinstance(got, str) else got) != (want.lower() if isinstance(want, str) else want):
@@ -388,6 +399,7 @@ def check_loss_cfg(cfg: Any) -> None:
         bad.append("USE_MTL=True (implemented: False)")
     if bad:
         raise NotImplementedError("catre_b200's training step implements the shipped loss config only: " + "; ".join(bad))
+    return weights
 
 
 def split_sym_info(sym_info) -> Tuple[List[bool], np.ndarray]:

@@ -47,6 +47,7 @@ SYMBOLS = {
     "catre_pair_metrics": (ctypes.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32,
                                           ctypes.c_int32, _F, _F, _P]),
     "catre_train_set_weight": (ctypes.c_int, [_P, ctypes.c_char_p, _F, _P]),
+    "catre_train_set_loss_weights": (ctypes.c_int, [_P, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
     "catre_train_step": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P, ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _P]),
     "catre_train_grad": (ctypes.c_int, [_P, ctypes.c_char_p, _F, _P]),
     "catre_last_launch_count": (ctypes.c_int64, [_P]),
@@ -260,6 +261,10 @@ class Engine:
             raise CatreError(f"{name}: expected a float32 CUDA tensor on device {self.device}")
         t = t.detach().contiguous()
         self._check(self.lib.catre_train_set_weight(self._h, name.encode(), t.data_ptr(), self._stream()), f"train_set_weight({name})")
+
+    def train_set_loss_weights(self, pm_lw: float = 1.0, rot_lw: float = 1.0, trans_lw: float = 1.0, scale_lw: float = 1.0):
+        """LOSS_CFG.PM_LW / ROT_LW / TRANS_LW / SCALE_LW (all > 0)."""
+        self._check(self.lib.catre_train_set_loss_weights(self._h, pm_lw, rot_lw, trans_lw, scale_lw), "train_set_loss_weights")
 
     def train_step(self, x_pm, tfd_pm, obj_kps, pose, scale, K, gt_pose, gt_scale, is_sym, sym_rots):
         """Forward + shipped losses + backward of one refinement iteration.  Device fp32 tensors except

@@ -187,8 +187,12 @@ int catre_pair_metrics(const double* pred_RT, const double* pred_scale, const in
  *                            symmetric -- here they are 0.
  *   The workspace (about 14 KB per point of the batch) is allocated on the first call and grown when B grows.
  * catre_train_grad: copy d(sum of losses)/d(tensor `name`) of the last catre_train_step to dst (device or host,
- *   stream-ordered); tensors the shipped config never uses (the heads' `norm`) have zero gradients. */
+ *   stream-ordered); tensors the shipped config never uses (the heads' `norm`) have zero gradients.
+ * catre_train_set_loss_weights: LOSS_CFG.PM_LW, ROT_LW (rotation and y-axis terms), TRANS_LW (xy and z terms), SCALE_LW;
+ *   each scales its loss values and gradients (CATRE_disR_shared.py:217, 238, 250, 262-263, 286).  Default 1 (shipped
+ *   config); must be > 0 (the reference drops a term whose weight is 0 from its dict -- not implemented). */
 int catre_train_set_weight(catre_engine* e, const char* name, const float* src_dev, void* stream);
+int catre_train_set_loss_weights(catre_engine* e, float pm_lw, float rot_lw, float trans_lw, float scale_lw);
 int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, const float* obj_kps, const float* pose,
                      const float* scale, const float* K, const float* gt_pose, const float* gt_scale,
                      const uint8_t* is_sym_host, const float* sym_rots_host, int32_t n_sym_rots, int32_t B, float* out_pose,

@@ -75,34 +75,38 @@ def closest_sym_rot(pred_rot: torch.Tensor, gt_rot: torch.Tensor, sym_info: List
 
 
 def catre_loss(rot: torch.Tensor, trans: torch.Tensor, scale: torch.Tensor, gt_rot: torch.Tensor, gt_trans: torch.Tensor,
-               gt_scale: torch.Tensor, kps: torch.Tensor, sym_info: List[Optional[np.ndarray]]) -> Dict[str, torch.Tensor]:
+               gt_scale: torch.Tensor, kps: torch.Tensor, sym_info: List[Optional[np.ndarray]],
+               weights: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)) -> Dict[str, torch.Tensor]:
     """CATRE_disR_shared.catre_loss with the shipped LOSS_CFG (core/catre/models/CATRE_disR_shared.py:168-288;
     configs/catre/NOCS_REAL/aug05_..._120e.py:115-134: symmetric point-matching loss on R only with scale, L1;
     angular rotation loss for asymmetric objects, L1 on the y axis for symmetric ones; L1 on xy / z; L1 on scale;
-    every weight 1)."""
+    every weight 1).  ``weights`` = (PM_LW, ROT_LW, TRANS_LW, SCALE_LW), each multiplying its terms (:217, 238, 250, 262-263,
+    286)."""
+    w_pm, w_rot, w_trans, w_scale = weights
     loss: Dict[str, torch.Tensor] = {}
     # point matching (core/catre/losses/pm_loss.py:110-130): R (s * kps) vs R_gt* (s_gt * kps), L1 mean, times 3
     gt_sym = closest_sym_rot(rot, gt_rot, sym_info)
     est = (kps * scale.unsqueeze(1)) @ rot.transpose(1, 2)
     tgt = (kps * gt_scale.unsqueeze(1)) @ gt_sym.transpose(1, 2)
-    loss["loss_PM_R"] = 3.0 * (est - tgt).abs().mean()
+    loss["loss_PM_R"] = 3.0 * (est - tgt).abs().mean() * w_pm
     # rotation (CATRE_disR_shared.py:222-250; core/catre/losses/rot_loss.py:45-58)
     is_sym = torch.tensor([s is not None for s in sym_info], device=rot.device)
     if (~is_sym).any():
         m = rot[~is_sym] @ gt_rot[~is_sym].transpose(1, 2)
         cos = (m.diagonal(dim1=1, dim2=2).sum(1) - 1.0) / 2.0
-        loss["loss_rot"] = ((1.0 - cos) / 2.0).mean()
+        loss["loss_rot"] = ((1.0 - cos) / 2.0).mean() * w_rot
     if is_sym.any():
-        loss["loss_yaxis_rot"] = (rot[is_sym][:, :, 1] - gt_rot[is_sym][:, :, 1]).abs().mean()
+        loss["loss_yaxis_rot"] = (rot[is_sym][:, :, 1] - gt_rot[is_sym][:, :, 1]).abs().mean() * w_rot
     # translation, disentangled (CATRE_disR_shared.py:253-262) and scale (:277-286)
-    loss["loss_trans_xy"] = (trans[:, :2] - gt_trans[:, :2]).abs().mean()
-    loss["loss_trans_z"] = (trans[:, 2] - gt_trans[:, 2]).abs().mean()
-    loss["loss_scale"] = (scale - gt_scale).abs().mean()
+    loss["loss_trans_xy"] = (trans[:, :2] - gt_trans[:, :2]).abs().mean() * w_trans
+    loss["loss_trans_z"] = (trans[:, 2] - gt_trans[:, 2]).abs().mean() * w_trans
+    loss["loss_scale"] = (scale - gt_scale).abs().mean() * w_scale
     return loss
 
 
 def train_step(w: Weights, pcl: torch.Tensor, kps: torch.Tensor, pose: torch.Tensor, scale: torch.Tensor, K: torch.Tensor,
-               gt_pose: torch.Tensor, gt_scale: torch.Tensor, sym_info: List[Optional[np.ndarray]]):
+               gt_pose: torch.Tensor, gt_scale: torch.Tensor, sym_info: List[Optional[np.ndarray]],
+               weights: Tuple[float, float, float, float] = (1.0, 1.0, 1.0, 1.0)):
     """One refinement iteration of the training loop (core/catre/engine/engine.py:293-352 without the optimiser):
     re-pose the points with the current (detached) estimate, forward, losses, backward of their sum.
     Returns (pose', scale', loss dict of floats, {name: gradient})."""
@@ -110,7 +114,7 @@ def train_step(w: Weights, pcl: torch.Tensor, kps: torch.Tensor, pose: torch.Ten
     x, tfd = co.update_points(pcl, kps, pose, scale)
     new_pose, new_scale = co.forward_once(wg, x, tfd, pose, scale, K)
     losses = catre_loss(new_pose[:, :3, :3], new_pose[:, :3, 3], new_scale, gt_pose[:, :3, :3], gt_pose[:, :3, 3], gt_scale,
-                        kps, sym_info)
+                        kps, sym_info, weights)
     sum(losses.values()).backward()
     grads = {k: v.grad for k, v in wg.items() if v.grad is not None}
     return new_pose.detach(), new_scale.detach(), {k: float(v.detach()) for k, v in losses.items()}, grads

@@ -34,7 +34,7 @@ struct EmuOps {
 extern "C" int emu_train_step(const float* const* weights, int B, int N, const float* pcl, const float* kps, const float* pose,
                               const float* scale, const float* K, const float* gt_pose, const float* gt_scale,
                               const unsigned char* is_sym, const float* sym_rots, int n_rots, float* pose_out, float* scale_out,
-                              float* losses, float* const* grads, long* launches, const float* x_pm, const float* tfd_pm, double* gemm_macs) {
+                              float* losses, float* const* grads, long* launches, const float* x_pm, const float* tfd_pm, double* gemm_macs, const float* loss_w) {
   if (n_rots > TrainWs::kMaxSymRots) return -1;
   TrainWs w;
   const size_t bytes = ws_layout(w, B, N, nullptr);
@@ -49,6 +49,7 @@ extern "C" int emu_train_step(const float* const* weights, int B, int N, const f
   Chain<EmuOps> c{ops, w, weights, N};
   TrainIn in{pcl, kps, pose, scale, K, gt_pose, gt_scale, B, n_rots, n_sym, B - n_sym, pose_out, scale_out};
   in.x_pm = x_pm; in.tfd_pm = tfd_pm;
+  if (loss_w) { in.w_pm = loss_w[0]; in.w_rot = loss_w[1]; in.w_trans = loss_w[2]; in.w_scale = loss_w[3]; }
   c.forward(in);
   c.loss(in);
   c.backward(in);

@@ -86,8 +86,10 @@ def test_dropin_refuses_cpu_and_training():
 def test_training_cfg_and_sym_info_checks():
     import numpy as np
 
-    dropin.check_loss_cfg({})  # absent keys = the shipped values
-    dropin.check_loss_cfg({"MODEL": {"CATRE": {"LOSS_CFG": {"PM_LOSS_TYPE": "l1", "ROT_LW": 1.0}}}})
+    assert dropin.check_loss_cfg({}) == (1.0, 1.0, 1.0, 1.0)  # absent keys = the shipped values
+    assert dropin.check_loss_cfg({"MODEL": {"CATRE": {"LOSS_CFG": {"PM_LOSS_TYPE": "l1", "ROT_LW": 2.5}}}}) == (1.0, 2.5, 1.0, 1.0)
+    with pytest.raises(NotImplementedError):  # a zero weight removes the term from the reference's loss dict
+        dropin.check_loss_cfg({"MODEL": {"CATRE": {"LOSS_CFG": {"SCALE_LW": 0}}}})
     with pytest.raises(NotImplementedError):
         dropin.check_loss_cfg({"MODEL": {"CATRE": {"LOSS_CFG": {"ROT_LOSS_TYPE": "L2"}}}})
     with pytest.raises(NotImplementedError):

@@ -17,6 +17,9 @@ class StubEngine:
     def train_set_weight(self, name, t):
         self.refreshed.append(name)
 
+    def train_set_loss_weights(self, *w):
+        self.loss_w = w
+
     def train_step(self, x_pm, tfd_pm, obj_kps, pose, scale, K, gt_pose, gt_scale, is_sym, sym_rots):
         self.steps += 1
         self.last = dict(x=x_pm, gt_pose=gt_pose, is_sym=list(is_sym), n_rots=len(sym_rots))
@@ -73,6 +76,15 @@ def test_loss_dict_keys_and_gradients(model):
     only_asym = call(m, [None, None])[1]
     assert "loss_yaxis_rot" not in only_asym and "loss_rot" in only_asym
     sum(only_asym.values()).backward()  # grad_out of the absent entry is 0 and must not count as a per-term weight
+
+
+def test_loss_weights_from_the_config_reach_the_engine(model):
+    m, stub = model
+    call(m, [None])
+    assert not hasattr(stub, "loss_w")  # shipped weights: nothing to set
+    m.cfg = {"MODEL": {"CATRE": {"LOSS_CFG": {"PM_LW": 0.5, "TRANS_LW": 3.0}}}}
+    call(m, [None])
+    assert stub.loss_w == (0.5, 1.0, 3.0, 1.0)
 
 
 def test_per_term_weights_and_stale_backward_are_refused(model):
