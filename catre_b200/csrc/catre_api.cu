@@ -18,6 +18,7 @@
 #include "cloud_kernels.cuh"
 #include "metrics_kernels.cuh"
 #include "train_chain.cuh"
+#include "optim_kernels.cuh"
 
 using namespace catre;
 
@@ -1263,6 +1264,29 @@ int catre_train_grad(catre_engine* e, const char* name, float* dst, void* stream
   if (!e->tws_mem) return fail(e, CATRE_ERR_NOT_PACKED, "catre_train_grad before any catre_train_step");
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   CU_TRY(e, cudaMemcpyAsync(dst, e->tws.G[i], catre_train::weight_numel(i, e->N) * sizeof(float), cudaMemcpyDefault, (cudaStream_t)stream));
+  return CATRE_OK;
+}
+
+int catre_ranger_step(const int64_t* table, const float* lr_wd, const int64_t* elem_start, const int64_t* row_start,
+                      int32_t n_tensors, int64_t total_elems, int64_t total_rows, float* rowmean, const catre_ranger_args* a,
+                      void* stream) {
+  static_assert(sizeof(catre_train::RangerTensor) == 64 && sizeof(catre_train::RangerArgs) == sizeof(catre_ranger_args),
+                "table row / argument layout of include/catre_b200.h");
+  if (n_tensors == 0 || total_elems == 0) return CATRE_OK;
+  if (!table || !lr_wd || !elem_start || !row_start || !a || n_tensors < 0 || total_elems < 0 || total_rows < 0 ||
+      (total_rows > 0 && !rowmean))
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_ranger_step: null or negative argument");
+  cudaStream_t s = (cudaStream_t)stream;
+  const catre_train::RangerTensor* T = reinterpret_cast<const catre_train::RangerTensor*>(table);
+  catre_train::RangerArgs ra{a->beta1, a->beta2, a->eps, a->one_minus_beta1, a->one_minus_beta2, a->step_size, a->rectified, a->alpha, a->lookahead, a->nan_to_num};
+  if (total_rows > 0) {
+    catre_train::KRangerRowMean k{T, reinterpret_cast<const long long*>(row_start), n_tensors, (long long)total_rows, rowmean, a->nan_to_num};
+    catre_train::tk_run<<<(unsigned)((total_rows + 255) / 256), 256, 0, s>>>(k);
+  }
+  catre_train::KRangerUpdate k{T, reinterpret_cast<const long long*>(elem_start), reinterpret_cast<const long long*>(row_start), lr_wd,
+                               rowmean, n_tensors, (long long)total_elems, ra};
+  catre_train::tk_run<<<(unsigned)((total_elems + 255) / 256), 256, 0, s>>>(k);
+  CU_TRY(nullptr, cudaGetLastError());
   return CATRE_OK;
 }
 

@@ -425,6 +425,13 @@ def _build_optimizer(cfg: Any, model: nn.Module):
     reference's tree that builder is used as is; elsewhere any torch.optim class of that name works."""
     lr = float(_cfg_get(cfg, "SOLVER.BASE_LR", _cfg_get(cfg, "SOLVER.OPTIMIZER_CFG.lr", 1e-4)))
     groups = [{"params": [p for p in model.parameters() if p.requires_grad], "lr": lr}]
+    if str(_cfg_get(cfg, "SOLVER.OPTIMIZER_CFG.type", "")) == "Ranger":
+        # the shipped config's optimiser: same constructor and state dict as lib/torch_utils/solver/ranger.py, one fused
+        # CUDA step over all tensors instead of ~700 small launches (catre_b200/optim.py)
+        from .optim import FusedRanger
+
+        kw = {k: v for k, v in dict(_cfg_get(cfg, "SOLVER.OPTIMIZER_CFG", {})).items() if k not in ("type", "_delete_", "lr")}
+        return FusedRanger(groups, lr=lr, **kw)
     try:
         from core.utils.solver_utils import build_optimizer_with_params  # the reference's own builder
     except Exception:

@@ -50,6 +50,7 @@ SYMBOLS = {
     "catre_train_set_loss_weights": (ctypes.c_int, [_P, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
     "catre_train_step": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P, ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _P]),
     "catre_train_grad": (ctypes.c_int, [_P, ctypes.c_char_p, _F, _P]),
+    "catre_ranger_step": (ctypes.c_int, [_F, _F, _F, _F, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, _F, _P, _P]),
     "catre_last_launch_count": (ctypes.c_int64, [_P]),
     "catre_debug_read": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_size_t]),
     "catre_profile_enable": (ctypes.c_int, [_P, ctypes.c_int32]),

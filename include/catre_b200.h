@@ -199,6 +199,35 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
                      float* out_scale, float* out_losses, void* stream);
 int catre_train_grad(catre_engine* e, const char* name, float* dst, void* stream);
 
+/* ---- Fused optimiser step (core/catre/engine/engine.py:349-352) -------------------------------
+ * Replaces: `optimizer.step()` of the optimiser the shipped config trains with, Ranger = RAdam + Lookahead + gradient
+ * centralisation (lib/torch_utils/solver/ranger.py:102-200: ~10 small launches per tensor, ~700 for the model), and
+ * optionally the gradient NaN guard in front of it (engine.py:349-352), in two launches over all tensors.
+ * Engine-independent and stateless: the caller owns parameters, gradients and optimiser state (exp_avg, exp_avg_sq,
+ * slow_buffer -- the reference's state-dict entries) and passes their device addresses in a table.
+ *   table        [n_tensors, 8] int64, device: per tensor (param, grad, exp_avg, exp_avg_sq, slow_buffer, numel, row_len, 0);
+ *                row_len = numel / shape[0] for tensors whose gradient is centralised (more than 1 dimension, or more than
+ *                3 with gc_conv_only), else 0
+ *   lr_wd        [n_tensors, 2] fp32, device: the tensor's group learning rate and weight decay
+ *   elem_start   [n_tensors + 1] int64, device: prefix sums of numel;  row_start [n_tensors + 1]: prefix sums of the
+ *                centralised tensors' shape[0] (0 rows for the others)
+ *   rowmean      [total_rows] fp32 device scratch
+ *   a            host: this step's scalars; step_size / rectified are the RAdam quantities of ranger.py:160-178 for the
+ *                step count, lookahead = (step % k == 0)
+ * All tensors fp32 and contiguous.  Errors through catre_last_error(NULL). */
+typedef struct catre_ranger_args {
+  float beta1, beta2, eps;
+  float one_minus_beta1, one_minus_beta2; /* evaluated in double, rounded once (torch passes them as Python scalars) */
+  float step_size;
+  int32_t rectified;
+  float alpha;
+  int32_t lookahead;
+  int32_t nan_to_num;
+} catre_ranger_args;
+int catre_ranger_step(const int64_t* table, const float* lr_wd, const int64_t* elem_start, const int64_t* row_start,
+                      int32_t n_tensors, int64_t total_elems, int64_t total_rows, float* rowmean, const catre_ranger_args* a,
+                      void* stream);
+
 /* Number of kernels the last forward/refine/train call launched (bench.py's `gpu_launches`). */
 int64_t catre_last_launch_count(const catre_engine* e);
 

@@ -103,6 +103,11 @@ def test_training_cfg_and_sym_info_checks():
     model, opt = dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "SGD", "lr": 1e-3}}},
                                               is_test=False)
     assert isinstance(opt, torch.optim.SGD) and model.training
+    from catre_b200 import optim
+
+    _, opt = dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "Ranger", "lr": 1e-4,
+                                                                                                   "weight_decay": 0}}}, is_test=False)
+    assert isinstance(opt, optim.FusedRanger) and opt.param_groups[0]["lr"] == 1e-4  # the shipped config's optimiser
 
 
 def test_check_cfg():
