@@ -60,11 +60,13 @@ struct TrainWs {
 
 // Assigns every workspace pointer from `base` (256-byte aligned slices) and returns the bytes needed; with
 // base == nullptr only the size is computed.
-inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base) {
+// `gap` bytes are left unused after every slice (0 in the product; the sanitizer build of tests/emu poisons them so an
+// out-of-range access of any kernel is caught on the CPU).
+inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base, size_t gap = 0) {
   size_t off = 0;
   auto take = [&](size_t bytes) -> char* {
     char* p = base ? base + off : nullptr;
-    off += (bytes + 255) & ~(size_t)255;
+    off += ((bytes + 255) & ~(size_t)255) + gap;
     return p;
   };
   auto F = [&](float*& p, size_t n) { p = reinterpret_cast<float*>(take(n * sizeof(float))); };

@@ -98,3 +98,17 @@ def test_emulated_chain_matches_oracle(emu, B, N, seed, reposed, sym):
         scale_k = max(np.abs(want).max(), 1e-8)
         err = np.abs(grads[k] - want).max() / scale_k
         assert err < 2e-4, (k, err, scale_k)
+
+
+def test_emulated_chain_under_address_sanitizer(tmp_path):
+    """Every workspace slice followed by a poisoned red zone, ragged shapes: no kernel of the chain reads or writes out of range
+    (the CPU stand-in for compute-sanitizer's memcheck, which needs a GPU)."""
+    if shutil.which("g++") is None:
+        pytest.skip("g++ not available")
+    exe = str(tmp_path / "train_asan")
+    r = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=address", "-DCATRE_HOST_EMU", "-DCATRE_EMU_ASAN",
+                        os.path.join(HERE, "emu", "train_emu_asan_main.cpp"), "-o", exe], capture_output=True, text=True)
+    if r.returncode != 0:
+        pytest.skip("AddressSanitizer runtime not available: " + r.stderr[-200:])
+    r = subprocess.run([exe], capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "no out-of-range access" in r.stdout, r.stdout[-500:] + r.stderr[-1500:]
