@@ -6,7 +6,7 @@ unmodified reference optimiser produced (``tests/golden/make_golden_ranger.py``)
 from __future__ import annotations
 
 import math
-from typing import Dict, List, Tuple
+from typing import List, Tuple
 
 import numpy as np
 

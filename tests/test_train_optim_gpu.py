@@ -3,7 +3,6 @@ against the goldens of the reference's own optimiser, and one full drop-in train
 is checked on the CPU against the kernels' source in tests/test_optim.py; this file sorts late on purpose: the kernels had
 not run on a GPU when it was committed.)"""
 import pytest
-import torch
 
 from catre_b200 import dropin, optim, synth
 from tests.test_optim import run_fused

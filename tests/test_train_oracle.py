@@ -5,7 +5,6 @@ import sys
 
 import numpy as np
 import pytest
-import torch
 
 sys.path.insert(0, os.path.join(os.path.dirname(__file__), "golden"))
 

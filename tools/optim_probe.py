@@ -4,7 +4,6 @@ GC mean/sub, two moment updates, sqrt/add/addcdiv, copy, lookahead every k steps
 (core/catre/engine/engine.py:349-352), on the model's 68 trained tensors.  Measurement tool; prints one JSON line each.
 Usage (GPU box): python tools/optim_probe.py"""
 import json
-import math
 import os
 import sys
 import time
