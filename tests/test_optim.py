@@ -84,3 +84,31 @@ def test_fused_ranger_refuses_cpu_without_the_library_path():
     p.grad = torch.ones(4, 4)
     with pytest.raises(Exception):
         optim.FusedRanger([p]).step()
+
+
+def test_fused_ranger_resumes_from_a_state_dict(emu_step):
+    """Checkpoint / resume (the reference saves optimizer.state_dict() with its PeriodicCheckpointer): stop after 5 steps,
+    load the state into a fresh optimiser over fresh parameter objects, continue -- same trajectory as the uninterrupted run."""
+    z = np.load(GOLDEN)
+    params, grads = make_inputs()
+
+    def build(ps):
+        return optim.FusedRanger([{"params": ps[:3], "lr": 1e-2}, {"params": ps[3:], "lr": 3e-3, "weight_decay": 0.1}], lr=1e-2,
+                                 nan_to_num=True, step_fn=emu_step)
+
+    ps = [torch.nn.Parameter(p.clone()) for p in params]
+    opt = build(ps)
+    for k in range(5):
+        for p, g in zip(ps, grads[k]):
+            p.grad = g.clone()
+        opt.step()
+    saved = opt.state_dict()
+    ps2 = [torch.nn.Parameter(p.detach().clone()) for p in ps]
+    opt2 = build(ps2)
+    opt2.load_state_dict(saved)
+    for k in range(5, N_STEPS):
+        for p, g in zip(ps2, grads[k]):
+            p.grad = g.clone()
+        opt2.step()
+    for i, p in enumerate(ps2):
+        assert np.allclose(p.detach().numpy(), z[f"step{N_STEPS}_p{i}"], rtol=2e-6, atol=2e-7), i
