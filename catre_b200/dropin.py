@@ -424,7 +424,19 @@ def _build_optimizer(cfg: Any, model: nn.Module):
     (core/utils/solver_utils.build_optimizer_with_params; the shipped config names its `Ranger`).  Inside the
     reference's tree that builder is used as is; elsewhere any torch.optim class of that name works."""
     lr = float(_cfg_get(cfg, "SOLVER.BASE_LR", _cfg_get(cfg, "SOLVER.OPTIMIZER_CFG.lr", 1e-4)))
-    groups = [{"params": [p for p in model.parameters() if p.requires_grad], "lr": lr}]
+    # the reference's three parameter groups, in its order (CATRE_disR_shared.py:292-315, model_utils.py:66-89, 144-167):
+    # pcl_net at the base rate, the rotation and translation/size heads at base * LR_MULT; a FREEZE'd part is left out and
+    # stops requiring gradients.  Same grouping and parameter order -> optimiser checkpoints interoperate.
+    groups = []
+    for prefix, cfg_key, mult_key in (("pcl_net.", "MODEL.CATRE.PCLNET", None), ("rot_head.", "MODEL.CATRE.ROT_HEAD", "LR_MULT"),
+                                      ("ts_head.", "MODEL.CATRE.TS_HEAD", "LR_MULT")):
+        part = [p for n, p in model.named_parameters() if n.startswith(prefix)]
+        if _cfg_get(cfg, cfg_key + ".FREEZE", False):
+            for p in part:
+                p.requires_grad = False
+            continue
+        mult = float(_cfg_get(cfg, cfg_key + "." + mult_key, 1.0)) if mult_key else 1.0
+        groups.append({"params": [p for p in part if p.requires_grad], "lr": lr * mult})
     if str(_cfg_get(cfg, "SOLVER.OPTIMIZER_CFG.type", "")) == "Ranger":
         # the shipped config's optimiser: same constructor and state dict as lib/torch_utils/solver/ranger.py, one fused
         # CUDA step over all tensors instead of ~700 small launches (catre_b200/optim.py)

@@ -108,6 +108,11 @@ def test_training_cfg_and_sym_info_checks():
     _, opt = dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "Ranger", "lr": 1e-4,
                                                                                                    "weight_decay": 0}}}, is_test=False)
     assert isinstance(opt, optim.FusedRanger) and opt.param_groups[0]["lr"] == 1e-4  # the shipped config's optimiser
+    assert [len(g["params"]) for g in opt.param_groups] == [32, 28, 14]  # pcl_net, rot_head, ts_head -- the reference's groups
+    cfg = {"MODEL": {"DEVICE": "cpu", "CATRE": {"ROT_HEAD": {"LR_MULT": 0.5}, "TS_HEAD": {"FREEZE": True}}},
+           "SOLVER": {"BASE_LR": 2e-4, "OPTIMIZER_CFG": {"type": "SGD", "lr": 1e-3}}}
+    model, opt = dropin.build_model_optimizer(cfg, is_test=False)
+    assert [g["lr"] for g in opt.param_groups] == [2e-4, 1e-4] and not model.ts_head.fc_t.weight.requires_grad
 
 
 def test_check_cfg():
