@@ -226,8 +226,7 @@ def compute_ap_from_matches_scores(pred_match, pred_scores, gt_match) -> float:
     recalls = np.cumsum(hit).astype(np.float32) / len(gt_match)
     precisions = np.concatenate([[0], precisions, [0]])
     recalls = np.concatenate([[0], recalls, [1]])
-    for i in range(len(precisions) - 2, -1, -1):
-        precisions[i] = np.maximum(precisions[i], precisions[i + 1])
+    precisions = np.maximum.accumulate(precisions[::-1])[::-1]  # the reference's right-to-left running maximum (:127-128)
     steps = np.where(recalls[:-1] != recalls[1:])[0] + 1
     return np.sum((recalls[steps] - recalls[steps - 1]) * precisions[steps])
 
@@ -259,6 +258,8 @@ def compute_combination_mAP(final_results, synset_names=("BG", "bottle", "bowl",
             g = gt_class_ids == cls_id if len(gt_class_ids) else np.zeros(0, bool)
             q = pred_class_ids == cls_id if len(pred_class_ids) else np.zeros(0, bool)
             n_g = int(g.sum())
+            if n_g == 0 and not q.any():
+                continue  # neither a ground truth nor a prediction of this class: the reference's call returns empty arrays
             if synset_names[cls_id] != "mug":
                 handle = np.ones(n_g, dtype=np.int32)  # handle visibility only matters for mugs (:443-448)
             else:
@@ -274,20 +275,21 @@ def compute_combination_mAP(final_results, synset_names=("BG", "bottle", "bowl",
     matched = match_images(subs, synset_names, iou_list, deg_list, shift_list, pair_metrics_fn=pair_metrics_fn)
     pred_m = [[np.zeros((nd, nt, ns, 0))] for _ in range(num_classes)]
     gt_m = [[np.zeros((nd, nt, ns, 0))] for _ in range(num_classes)]
-    scores = [[np.zeros((nd, nt, ns, 0))] for _ in range(num_classes)]
+    scores = [[np.zeros(0)] for _ in range(num_classes)]
     for sub, cls_id, (gm, pm, ind) in zip(subs, sub_cls, matched):
         sc = np.asarray(sub["pred_scores"])
         if len(ind):
             sc = sc[ind]
         pred_m[cls_id].append(pm)
-        scores[cls_id].append(np.tile(sc, (nd, nt, ns, 1)))
+        scores[cls_id].append(sc)  # the same for every threshold triple: broadcast once per class below
         gt_m[cls_id].append(gm)
     aps = np.zeros((num_classes + 1, nd, nt, ns))
     for cls_id in range(1, num_classes):
-        pm_all, sc_all, gm_all = (np.concatenate(x[cls_id], axis=-1) for x in (pred_m, scores, gt_m))
+        pm_all, gm_all = (np.concatenate(x[cls_id], axis=-1) for x in (pred_m, gt_m))
+        sc_all = np.concatenate([np.asarray(x, dtype=np.float64).reshape(-1) for x in scores[cls_id]])  # np.tile(...) made float64 rows
         for s in range(ns):
             for d in range(nd):
                 for t in range(nt):
-                    aps[cls_id, d, t, s] = compute_ap_from_matches_scores(pm_all[d, t, s, :], sc_all[d, t, s, :], gm_all[d, t, s, :])
+                    aps[cls_id, d, t, s] = compute_ap_from_matches_scores(pm_all[d, t, s, :], sc_all, gm_all[d, t, s, :])
     aps[-1] = np.mean(aps[1:-1], axis=0)
     return aps
