@@ -7,6 +7,7 @@ timeout 300 python -m pytest tests/test_train_gpu.py tests/test_train_optim_gpu.
 echo "pytest rc=$?" >> gpurun_out/pytest_train.log; tail -15 gpurun_out/pytest_train.log
 timeout 200 python tools/train_probe.py 16 64 > gpurun_out/train_probe.log 2>&1; cat gpurun_out/train_probe.log
 timeout 100 python tools/optim_probe.py > gpurun_out/optim_probe.log 2>&1; cat gpurun_out/optim_probe.log
+timeout 200 python tools/train_loop_probe.py 16 > gpurun_out/train_loop_probe.log 2>&1; cat gpurun_out/train_loop_probe.log
 timeout 100 python tools/train_ref_probe.py 16 64 > gpurun_out/train_ref_probe.log 2>&1; cat gpurun_out/train_ref_probe.log
 # per-kernel durations of one training step (serialised under ncu: compare shares, not absolutes)
 timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none -c 700 --csv --log-file gpurun_out/train_launches.csv \
