@@ -1267,6 +1267,33 @@ int catre_train_grad(catre_engine* e, const char* name, float* dst, void* stream
   return CATRE_OK;
 }
 
+int catre_train_grad_layout(catre_engine* e, int64_t* offsets, int64_t* total_floats) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  if (!offsets || !total_floats) return fail(e, CATRE_ERR_INVALID_ARG, "catre_train_grad_layout: null argument");
+  catre_train::TrainWs probe;
+  catre_train::ws_layout(probe, 1, e->N, reinterpret_cast<char*>(4096));  // dummy base: only pointer differences are used
+  for (int i = 0; i < kNumWeights; ++i) offsets[i] = (int64_t)(probe.G[i] - probe.G[0]);
+  *total_floats = (int64_t)probe.grad_floats;
+  return CATRE_OK;
+}
+
+int catre_train_grads_flat(catre_engine* e, float* dst, float scale, void* stream) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  if (!dst) return fail(e, CATRE_ERR_INVALID_ARG, "catre_train_grads_flat: null argument");
+  if (!e->tws_mem) return fail(e, CATRE_ERR_NOT_PACKED, "catre_train_grads_flat before any catre_train_step");
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  cudaStream_t s = (cudaStream_t)stream;
+  const long long n = (long long)e->tws.grad_floats;
+  if (scale == 1.0f) {
+    CU_TRY(e, cudaMemcpyAsync(dst, e->tws.G[0], (size_t)n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  } else {
+    catre_train::KScaleCopy k{e->tws.G[0], dst, scale, n};
+    catre_train::tk_run<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(k);
+    CU_TRY(e, cudaGetLastError());
+  }
+  return CATRE_OK;
+}
+
 int catre_ranger_step(const int64_t* table, const float* lr_wd, const int64_t* elem_start, const int64_t* row_start,
                       int32_t n_tensors, int64_t total_elems, int64_t total_rows, float* rowmean, const catre_ranger_args* a,
                       void* stream) {

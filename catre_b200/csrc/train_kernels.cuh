@@ -134,6 +134,15 @@ struct KAddEye {
   }
 };
 
+// dst[e] = scale * src[e]  (gradients handed to the caller with the upstream factor applied).  grid (ceil(n / nt))
+struct KScaleCopy {
+  const float* src; float* dst; float scale; long long n;
+  TK_HD void operator()(const Idx& i) const {
+    const long long e = (long long)i.bx * i.nt + i.tx;
+    if (e < n) dst[e] = scale * src[e];
+  }
+};
+
 // d[e] = act[e] > 0 ? d[e] : 0   (ReLU backward).  grid (ceil(n / nt))
 struct KReluMask {
   float* d; const float* act; long long n;

@@ -27,6 +27,7 @@ raise.  There is still no PyTorch implementation of the network in this package.
 """
 from __future__ import annotations
 
+import os
 from typing import Any, Dict, List, Optional, Tuple
 
 import numpy as np
@@ -78,6 +79,14 @@ class _LossBridge(torch.autograd.Function):
                                       f"got per-term weights {g.tolist()}")
         eng = model._engine
         grads: List[Optional[torch.Tensor]] = []
+        if os.environ.get("CATRE_TRAIN_FLAT_GRADS", "0") == "1":
+            # opt-in (not yet measured on a GPU): one scaled copy of the engine's gradient arena, handed out as views,
+            # instead of a copy and a multiply per tensor
+            offsets, _ = eng._grad_layout()
+            flat = eng.train_grads_flat(float(scale))
+            for name, p, need in zip(ctx.names, ctx.shapes, ctx.needs_input_grad[4:]):
+                grads.append(flat[offsets[name]: offsets[name] + p.numel()].view(p.shape) if need else None)
+            return (None, None, None, None, *grads)
         for name, p, need in zip(ctx.names, ctx.shapes, ctx.needs_input_grad[4:]):
             if not need:
                 grads.append(None)

@@ -50,6 +50,8 @@ SYMBOLS = {
     "catre_train_set_loss_weights": (ctypes.c_int, [_P, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
     "catre_train_step": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P, ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _P]),
     "catre_train_grad": (ctypes.c_int, [_P, ctypes.c_char_p, _F, _P]),
+    "catre_train_grad_layout": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_int64), ctypes.POINTER(ctypes.c_int64)]),
+    "catre_train_grads_flat": (ctypes.c_int, [_P, _F, ctypes.c_float, _P]),
     "catre_ranger_step": (ctypes.c_int, [_F, _F, _F, _F, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, _F, _P, _P]),
     "catre_last_launch_count": (ctypes.c_int64, [_P]),
     "catre_debug_read": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_size_t]),
@@ -301,6 +303,25 @@ class Engine:
             raise CatreError(f"{name}: gradient destination must be a contiguous float32 CUDA tensor")
         self._check(self.lib.catre_train_grad(self._h, name.encode(), out.data_ptr(), self._stream()), f"train_grad({name})")
         return out
+
+    def train_grad_layout(self):
+        """({checkpoint name: offset in floats}, arena size in floats) of the engine's gradient arena."""
+        n = self.lib.catre_num_weights()
+        offs, total = (ctypes.c_int64 * n)(), ctypes.c_int64()
+        self._check(self.lib.catre_train_grad_layout(self._h, offs, ctypes.byref(total)), "train_grad_layout")
+        return {name: int(offs[i]) for i, name in enumerate(self.weight_names())}, int(total.value)
+
+    def train_grads_flat(self, scale: float = 1.0) -> torch.Tensor:
+        """scale * (all gradients of the last train_step) as one flat device tensor laid out like train_grad_layout()."""
+        _, total = self._grad_layout()
+        out = torch.empty((total,), dtype=torch.float32, device=torch.device("cuda", self.device))
+        self._check(self.lib.catre_train_grads_flat(self._h, out.data_ptr(), float(scale), self._stream()), "train_grads_flat")
+        return out
+
+    def _grad_layout(self):
+        if getattr(self, "_layout", None) is None:
+            self._layout = self.train_grad_layout()
+        return self._layout
 
     # ---- accounting ------------------------------------------------------------------------------
     def last_launch_count(self) -> int:

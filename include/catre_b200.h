@@ -198,6 +198,13 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
                      const uint8_t* is_sym_host, const float* sym_rots_host, int32_t n_sym_rots, int32_t B, float* out_pose,
                      float* out_scale, float* out_losses, void* stream);
 int catre_train_grad(catre_engine* e, const char* name, float* dst, void* stream);
+/* All gradients at once: the engine keeps them in one arena (checkpoint order, every tensor on a 256-byte boundary).
+ * catre_train_grad_layout: offsets[i] = position (in floats) of checkpoint tensor i inside the arena, *total_floats = arena
+ *   size; depends on the point count only, valid before the first step.
+ * catre_train_grads_flat: dst[0 .. total_floats) = scale * arena (device pointer, stream-ordered): one copy (scale == 1) or
+ *   one kernel instead of 68 per-tensor copies; a binding hands out views of dst as the parameters' gradients. */
+int catre_train_grad_layout(catre_engine* e, int64_t* offsets, int64_t* total_floats);
+int catre_train_grads_flat(catre_engine* e, float* dst, float scale, void* stream);
 
 /* ---- Fused optimiser step (core/catre/engine/engine.py:349-352) -------------------------------
  * Replaces: `optimizer.step()` of the optimiser the shipped config trains with, Ranger = RAdam + Lookahead + gradient

@@ -161,3 +161,25 @@ def test_train_step_with_opt_in_gemm_v2(monkeypatch):
     committed."""
     monkeypatch.setenv("CATRE_TRAIN_GEMM", "v2")
     _step_vs_oracle("0", monkeypatch)
+
+
+def test_flat_gradient_handoff_equals_per_tensor_copies():
+    """catre_train_grads_flat + catre_train_grad_layout (the opt-in one-copy hand-off of all gradients, CATRE_TRAIN_FLAT_GRADS=1)
+    against the per-tensor catre_train_grad copies, with and without a scale factor.  Late in the file: not yet run on a GPU
+    when committed."""
+    d, tgt, x_pm, tfd_pm = inputs()
+    w = synth.load_weights()
+    eng = engine.Engine(1024, 8, "fp32", 0)
+    eng.load_weights(w)
+    offsets, total = eng.train_grad_layout()
+    assert sorted(offsets, key=offsets.get) == list(w.keys()) and offsets["pcl_net.stn.conv1.weight"] == 0
+    assert all(o % 64 == 0 for o in offsets.values()) and total >= sum(t.numel() for t in w.values())
+    eng.train_step(x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, tgt.gt_pose.cuda(), tgt.gt_scale.cuda(), tgt.sym_y.numpy(),
+                   y_symmetry_rotations())
+    for scale in (1.0, 0.5):
+        flat = eng.train_grads_flat(scale)
+        assert flat.shape == (total,)
+        for name, t in w.items():
+            g = eng.train_grad(name, torch.empty(t.shape, device="cuda"))
+            assert torch.equal(flat[offsets[name]: offsets[name] + t.numel()].view(t.shape), scale * g), name
+    eng.close()

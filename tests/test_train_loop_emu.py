@@ -56,6 +56,20 @@ class EmuEngine:
     def train_grad(self, name, out):
         return out.copy_(torch.from_numpy(self.g[name]).reshape(out.shape))
 
+    def _grad_layout(self):  # an arena in checkpoint order with padding between the tensors, like the engine's
+        offs, o = {}, 0
+        for k in NAMES:
+            offs[k] = o
+            o += (self.g[k].size + 63) // 64 * 64
+        return offs, o
+
+    def train_grads_flat(self, scale=1.0):
+        offs, total = self._grad_layout()
+        flat = torch.full((total,), float("nan"))
+        for k in NAMES:
+            flat[offs[k]: offs[k] + self.g[k].size] = scale * torch.from_numpy(self.g[k]).flatten()
+        return flat
+
 
 def _refresh(m):
     for n, p in m.named_parameters():
@@ -66,7 +80,9 @@ def _refresh(m):
     return m._engine
 
 
-def test_three_training_iterations_match_the_reference_loop(emu, emu_step, monkeypatch):
+@pytest.mark.parametrize("flat_grads", ["0", "1"])
+def test_three_training_iterations_match_the_reference_loop(emu, emu_step, monkeypatch, flat_grads):
+    monkeypatch.setenv("CATRE_TRAIN_FLAT_GRADS", flat_grads)  # 1 = gradients as views of one copy of the arena (opt-in)
     z = np.load(GOLDEN)
     w = co.resize_conv_p(synth.load_weights(), N_PTS)
     model = dropin.CatreB200(N_PTS, N_PTS, max_batch=4)
