@@ -67,3 +67,24 @@ def test_rot_is_orthonormal(weights):
     eye = torch.eye(3, dtype=torch.float64)
     assert (r @ r.transpose(-1, -2) - eye).abs().max() < 1e-5
     assert (torch.linalg.det(r) - 1).abs().max() < 1e-5
+
+
+def test_seeded_generator_reproduces_the_golden_inputs():
+    """synth.make_batch / make_train_batch are the SURVEY.md 8(d) generator: for the seeds the golden cases were made with they
+    must keep producing the committed inputs byte for byte (bench.py, the probes and the training fixtures rely on it)."""
+    import numpy as np
+
+    from catre_b200 import synth
+    from tests import golden_util as gu
+
+    for name, meta in gu.index()["cases"].items():
+        if meta["seed"] is None:
+            continue
+        z = np.load(f"{gu.GOLDEN_DIR}/golden_{name}.npz")
+        b = synth.make_batch(meta["batch"], meta["n_pts"], meta["seed"], meta["round_robin"])
+        assert np.array_equal(b.pcl.numpy(), z["pcl"]) and np.array_equal(b.init_pose.numpy(), z["init_pose"]), name
+        assert np.array_equal(b.init_scale.numpy(), z["init_scale"]) and np.array_equal(b.obj_cls.numpy(), z["prior_cls"]), name
+    zt = np.load(f"{gu.GOLDEN_DIR}/golden_train.npz")
+    b, t = synth.make_train_batch(6, 1024, 11, round_robin_cls=True)
+    assert np.array_equal(b.pcl.numpy(), zt["pcl"]) and np.array_equal(t.gt_pose.numpy(), zt["gt_pose"])
+    assert np.array_equal(t.gt_scale.numpy(), zt["gt_scale"]) and np.array_equal(t.sym_y.numpy(), zt["sym_y"])
