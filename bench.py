@@ -148,6 +148,7 @@ def main():
     ap.add_argument("--precision", default="f16x3", choices=["fp32", "f16x3", "bf16"])
     ap.add_argument("--cpu-sample", type=int, default=16, help="objects in the bounded CPU-baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-train-leg", action="store_true", help="skip the informational training-step timing (SURVEY.md 8(f) N4)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "catre_b200" else args.warmup
 
@@ -311,6 +312,39 @@ def main():
         cpu_baseline = {"value": v, "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"{sample} objects, N={N}, K={K}, 1 pass after 1 warm-up, torch CPU fp32 oracle"}
 
+    # ---- informational (not part of the contract's metric): one training step (forward with losses +
+    #      backward, catre_train_step) of 16 objects on the same engine; measured last and never allowed to disturb the line
+    train_leg = None
+    if rank == 0 and world == 1 and N == 1024 and not args.no_train_leg:
+        try:
+            import numpy as np
+
+            tb, tt = synth.make_train_batch(16, N, seed=3, round_robin_cls=True)
+            td = tb.to(dev)
+            x_pm = (td.pcl - td.init_pose[:, :, 3].unsqueeze(1)).contiguous()
+            tfd_pm = ((td.prior * td.init_scale.unsqueeze(1)) @ td.init_pose[:, :, :3].transpose(1, 2)).contiguous()
+            n_rot_y = int(np.ceil(np.pi / 0.01))
+            ang = np.arange(1, n_rot_y) * 2.0 * np.pi / n_rot_y
+            rots = np.zeros((n_rot_y - 1, 3, 3), np.float32)
+            rots[:, 0, 0], rots[:, 0, 2], rots[:, 1, 1], rots[:, 2, 0], rots[:, 2, 2] = np.cos(ang), np.sin(ang), 1.0, -np.sin(ang), np.cos(ang)
+            gp, gs = tt.gt_pose.to(dev), tt.gt_scale.to(dev)
+            tstep = lambda: eng.train_step(x_pm, tfd_pm, td.prior, td.init_pose, td.init_scale, td.K, gp, gs, tt.sym_y.numpy(), rots)
+            for _ in range(2):
+                tstep()
+            torch.cuda.synchronize()
+            a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record()
+            for _ in range(5):
+                _, _, tl = tstep()
+            b_.record()
+            torch.cuda.synchronize()
+            tms = a.elapsed_time(b_) / 5
+            train_leg = {"what": "catre_train_step: forward + shipped losses + backward of one refinement iteration, fp32 CUDA cores",
+                         "objects": 16, "n_pts": N, "ms_per_step": tms, "objects_per_s": 16 / (tms * 1e-3),
+                         "launches": eng.last_launch_count(), "sum_of_losses": float(tl.sum().item())}
+        except Exception as exc:  # informational leg: report, never fail the bench line
+            train_leg = {"error": f"{type(exc).__name__}: {exc}"[:300]}
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
@@ -324,6 +358,8 @@ def main():
                        "object_iterations_per_s": value * K},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roofline, "cpu_baseline": cpu_baseline,
         }
+        if train_leg is not None:
+            line["train_step"] = train_leg
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
