@@ -15,6 +15,7 @@
 #include "simt_kernels.cuh"
 #include "tc_kernels.cuh"
 #include "tc_fused.cuh"
+#include "fc_chain.cuh"
 #include "cloud_kernels.cuh"
 #include "metrics_kernels.cuh"
 #include "train_chain.cuh"
@@ -117,10 +118,10 @@ struct catre_engine {
   // ---- workspace
   float *q = nullptr, *h64a = nullptr, *h64b = nullptr, *h128 = nullptr, *h512 = nullptr, *a0 = nullptr, *a1 = nullptr;
   int *gmax_all = nullptr, *gmax_stn = nullptr, *gmax_fstn = nullptr, *gmax_g = nullptr, *gmax_pf = nullptr;
-  float *fc512 = nullptr, *fc256 = nullptr, *ts0 = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
-  // tensor-core FC path of the T-Nets / rot g-feature: operands [Spad, K] (Spad = S rounded up to 128 rows)
-  TcPair g16, fc1o, fc2o, t64s_out;  // t64s_out: the t64s memory viewed as [Spad, 4096] for the FC's TMA stores
-  TcPair tw_fc1[2], tw_fc2[2], tw_fstn_fc3, tw_rot_w0g;  // [0] = stn, [1] = fstn
+  float *ts0 = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
+  // fused FC chains (fc_chain.cuh): weights packed [8 ranks][K][C/8] fp32; [0] = stn, [1] = fstn
+  float *fcc_fc1[2] = {nullptr, nullptr}, *fcc_fc2[2] = {nullptr, nullptr}, *fcc_fc3[2] = {nullptr, nullptr};
+  float *fcc_cset = nullptr, *fcc_ts0 = nullptr;
   TcPair t64s;  // tensor-core modes: bf16 hi/lo of T64^T, [S*64, 64]
   float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
   // bf16 hi/lo activations of the tensor-core path and their tensor maps
@@ -319,73 +320,56 @@ int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv,
   return check_launch(e, "front3_split");
 }
 
-// small-M fully-connected layer on a cluster of FC_KSPLIT CTAs (see fc_cluster_kernel)
-template <int AMODE>
-int run_fc(catre_engine* e, cudaStream_t s, int grp, const float* A, int lda, const float* Wt, int ldw, const float* bias,
-           int R, int C, int K, int relu, float* out32, const TcPair* out16) {
-  FcP p{};
-  p.A = A; p.lda = lda; p.W = Wt; p.ldw = ldw; p.bias = bias; p.out32 = out32;
-  p.out_hi = out16 ? reinterpret_cast<unsigned short*>(out16->hi) : nullptr;
-  p.out_lo = out16 ? reinterpret_cast<unsigned short*>(out16->lo) : nullptr;
-  p.out_f16 = e->cfg.precision == CATRE_PREC_F16X3;
-  p.R = R; p.C = C; p.K = K; p.relu = relu;
+// ---- fused FC chains (fc_chain.cuh): one cluster launch per chain, fp32, same arithmetic at every batch size
+FccLayer fcc_layer_desc(const float* wp, const float* bias, int K, int C, int NC, int relu) {
+  FccLayer l{};
+  l.wp = wp; l.bias = bias; l.K = K; l.C = C; l.NC = NC; l.relu = relu;
+  return l;
+}
+
+int run_chain(catre_engine* e, cudaStream_t s, int grp, const FccProblem& p0, const FccProblem* p1) {
+  FccBatch b{};
+  b.p[0] = p0;
+  b.clusters0 = (p0.rows + FCC_ROWS - 1) / FCC_ROWS;
+  int clusters = b.clusters0;
+  if (p1) { b.p[1] = *p1; clusters += (p1->rows + FCC_ROWS - 1) / FCC_ROWS; }
+  for (int q = 0; q < (p1 ? 2 : 1); ++q)
+    for (int l = 0; l < b.p[q].n_layers; ++l)
+      if (!fcc_layer_ok(b.p[q].L[l])) return fail(e, CATRE_ERR_UNSUPPORTED, "fc chain: unsupported layer geometry");
+  cudaError_t st;
   {
     Launch l(e, s, grp);
-    if ((long long)((C + 63) / 64) * ((R + 127) / 128) >= 32) {  // enough 128 x 64 tiles to fill the GPU with 8-CTA clusters
-      dim3 grid((C + 63) / 64, (R + 127) / 128, FC_KSPLIT);
-      launch_pdl(fc_cluster_kernel<AMODE, 128, 64, 256>, dim3(grid), dim3(256), (size_t)(0), s, p);
+    st = fcc_launch(b, clusters, s);
+  }
+  if (st != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e, CATRE_ERR_CUDA, "launch of fc chain (%s) failed: %s", kGrpNames[grp], cudaGetErrorString(st));
+  }
+  return 0;
+}
+
+// T-Net FC chain: keys [S,1024] -> 512 -> 256 -> kk (+I)  (pointnets/pointnet.py:32-40, 66-77); which = 0 stn, 1 fstn
+int tnet_fc_chain(catre_engine* e, cudaStream_t s, const int* keys, int S, int which) {
+  const std::string pf = which ? "pcl_net.fstn" : "pcl_net.stn";
+  const bool tc = e->cfg.precision != CATRE_PREC_FP32_SIMT;
+  FccProblem p{};
+  p.keys = keys; p.lda = 1024; p.rows = S; p.n_layers = 3;
+  p.L[0] = fcc_layer_desc(e->fcc_fc1[which], W(e, (pf + ".fc1.bias").c_str()), 1024, 512, 64, 1);
+  p.L[1] = fcc_layer_desc(e->fcc_fc2[which], W(e, (pf + ".fc2.bias").c_str()), 512, 256, 32, 1);
+  if (which == 0) {
+    p.L[2] = fcc_layer_desc(e->fcc_fc3[0], e->stn_fc3_bI, 256, 9, 2, 0);
+    p.out32 = e->t3;
+  } else {  // fc3's rows are permuted at pack time so the chain emits T64^T (the feature transform's N-side operand)
+    p.L[2] = fcc_layer_desc(e->fcc_fc3[1], e->fstn_fc3_bI, 256, 4096, 512, 0);
+    if (tc) {
+      p.out_hi = reinterpret_cast<unsigned short*>(e->t64s.hi);
+      p.out_lo = reinterpret_cast<unsigned short*>(e->t64s.lo);
+      p.out_f16 = e->cfg.precision == CATRE_PREC_F16X3;
     } else {
-      dim3 grid((C + 31) / 32, (R + 63) / 64, FC_KSPLIT);
-      launch_pdl(fc_cluster_kernel<AMODE, 64, 32, 128>, dim3(grid), dim3(128), (size_t)(0), s, p);
+      p.out32 = e->t64;
     }
   }
-  return check_launch(e, kGrpNames[grp]);
-}
-
-// T-Net FC chain: keys [S,1024] -> 512 -> 256 -> kk  (pointnets/pointnet.py:32-40, 66-77)
-int tnet_fc(catre_engine* e, cudaStream_t s, const int* keys, int S, const char* prefix, const float* fc3_w,
-            const float* fc3_bias_I, int kk, float* out32, const TcPair* out16) {
-  std::string pf(prefix);
-  int rc;
-  if ((rc = run_fc<A_KEY>(e, s, G_TNET_FC, reinterpret_cast<const float*>(keys), 1024, W(e, (pf + ".fc1.weight").c_str()), 1024,
-                          W(e, (pf + ".fc1.bias").c_str()), S, 512, 1024, 1, e->fc512, nullptr))) return rc;
-  if ((rc = run_fc<A_PLAIN>(e, s, G_TNET_FC, e->fc512, 512, W(e, (pf + ".fc2.weight").c_str()), 512,
-                            W(e, (pf + ".fc2.bias").c_str()), S, 256, 512, 1, e->fc256, nullptr))) return rc;
-  return run_fc<A_PLAIN>(e, s, G_TNET_FC, e->fc256, 256, fc3_w, 256, fc3_bias_I, S, kk, 256, 0, out32, out16);
-}
-
-// ---- tensor-core small-M FC layers (tensor-core modes): out[S, C] = act(in[S, K] . W[C, K]^T + b) with the
-//      sets on the TMEM lanes (one or a few 128-row tiles), weights streamed, f16x3 (or bf16) like every wide layer
-int tc_keys_split(catre_engine* e, cudaStream_t s, int grp, const int* keys, int S, const TcPair& out) {
-  const long long n4 = (long long)S * 1024 / 4;
-  {
-    Launch l(e, s, grp);
-    launch_pdl(keys_split_kernel, dim3((unsigned)((n4 + 255) / 256)), dim3(256), (size_t)0, s, keys,
-               reinterpret_cast<unsigned short*>(out.hi), reinterpret_cast<unsigned short*>(out.lo), n4,
-               (int)(e->cfg.precision == CATRE_PREC_F16X3));
-  }
-  return check_launch(e, "keys_split");
-}
-
-int tc_fc(catre_engine* e, cudaStream_t s, int grp, const TcPair& in, const TcPair& w, int S, int C, int K, const float* bias,
-          int relu, const TcPair& out16, float* out32) {
-  TcGemmP p{};
-  p.K = K; p.m_tiles = (S + 127) / 128; p.n_tiles = C / 64; p.rows_per_set = 1 << 30;
-  p.bias = bias; p.relu = relu; p.out32 = out32; p.ldo32 = C; p.rows32 = S;
-  return tc_run<PT_ON_LANES, EPI_SPLIT_STREAM, 64>(e, s, grp, in.map_hi, in.map_lo, w.map_hi, w.map_lo, p, &out16);
-}
-
-// T-Net FC chain on the tensor cores: which = 0 (stn, kk = 9: last layer stays a fp32 cluster FC) or 1 (fstn, kk = 4096)
-int tnet_fc_tc(catre_engine* e, cudaStream_t s, const int* keys, int S, int which) {
-  const char* pre = which ? "pcl_net.fstn" : "pcl_net.stn";
-  std::string pf(pre);
-  int rc;
-  if ((rc = tc_keys_split(e, s, G_TNET_FC, keys, S, e->g16))) return rc;
-  if ((rc = tc_fc(e, s, G_TNET_FC, e->g16, e->tw_fc1[which], S, 512, 1024, W(e, (pf + ".fc1.bias").c_str()), 1, e->fc1o, nullptr))) return rc;
-  if ((rc = tc_fc(e, s, G_TNET_FC, e->fc1o, e->tw_fc2[which], S, 256, 512, W(e, (pf + ".fc2.bias").c_str()), 1, e->fc2o,
-                  which ? nullptr : e->fc256))) return rc;
-  if (which) return tc_fc(e, s, G_TNET_FC, e->fc2o, e->tw_fstn_fc3, S, 4096, 256, e->fstn_fc3_bI, 0, e->t64s_out, nullptr);
-  return run_fc<A_PLAIN>(e, s, G_TNET_FC, e->fc256, 256, W(e, "pcl_net.stn.fc3.weight"), 256, e->stn_fc3_bI, S, 9, 256, 0, e->t3, nullptr);
+  return run_chain(e, s, G_TNET_FC, p, nullptr);
 }
 
 // One refinement iteration on a chunk of B objects whose points are already in e->q.
@@ -395,9 +379,6 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   const long long R = (long long)S * N;
   int rc;
   const bool tc = e->cfg.precision != CATRE_PREC_FP32_SIMT;
-  // small-M FC layers: tensor cores when there are at least two 128-row tiles of sets (measured: B=256 -0.33 ms),
-  // split-K cluster FMA kernels otherwise (with one tile only 4-8 CTAs would stream all of K: B=64 +0.05 ms)
-  const bool tc_fcs = tc && S >= 256;
 
   // column-max key buffers are laid out for the current S; the point kernel that filled e->q has reset them
   e->gmax_stn = e->gmax_all;
@@ -425,9 +406,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p.gmax = e->gmax_stn; p.rows_per_set = N;
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_STN_CONV3_MAX, p))) return rc;
   }
-  if (tc_fcs) {
-    if ((rc = tnet_fc_tc(e, s, e->gmax_stn, S, 0))) return rc;
-  } else if ((rc = tnet_fc(e, s, e->gmax_stn, S, "pcl_net.stn", W(e, "pcl_net.stn.fc3.weight"), e->stn_fc3_bI, 9, e->t3, nullptr))) return rc;
+  if ((rc = tnet_fc_chain(e, s, e->gmax_stn, S, 0))) return rc;
 
   // ---- E2: input transform + conv1 (pointnet.py:97-103)
   if (tc) {
@@ -458,10 +437,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p.gmax = e->gmax_fstn; p.rows_per_set = N;
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_FSTN_CONV3_MAX, p))) return rc;
   }
-  if (tc_fcs) {
-    if ((rc = tnet_fc_tc(e, s, e->gmax_fstn, S, 1))) return rc;
-  } else if ((rc = tnet_fc(e, s, e->gmax_fstn, S, "pcl_net.fstn", e->fstn_fc3_wT, e->fstn_fc3_bI, 4096, tc ? nullptr : e->t64,
-                           tc ? &e->t64s : nullptr))) return rc;
+  if ((rc = tnet_fc_chain(e, s, e->gmax_fstn, S, 1))) return rc;
 
   // ---- E4: feature transform pf = h1 . T64 (per set), trunk conv2-4, global max (pointnet.py:105-116)
   if (tc) {
@@ -487,9 +463,20 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV4_MAX, p))) return rc;
   }
 
-  // ---- H1 on the side stream (needs only the max-pooled features; independent of the rot head).  ts-head
-  //      layer 0 over the 1024 global-feature inputs of the OBSERVED set (row b -> set 2b) is a cluster FC;
-  //      the remaining 67 inputs (pointfeat max, init scale) are added in ts_head_kernel.
+  // ---- the two FC layers over the max-pooled global feature, one launch: cset = W0[:, :1024] . g_set + b0 for every
+  //      set (rot layer-0 split) and ts-head layer 0 over the OBSERVED sets' g (row b -> set 2b)
+  {
+    FccProblem pc{}, pt{};
+    pc.keys = e->gmax_g; pc.lda = 1024; pc.rows = S; pc.n_layers = 1;
+    pc.L[0] = fcc_layer_desc(e->fcc_cset, e->rot_b0, 1024, 512, 64, 0);
+    pc.out32 = e->cset;
+    pt.keys = e->gmax_g; pt.lda = 2048; pt.rows = B; pt.n_layers = 1;
+    pt.L[0] = fcc_layer_desc(e->fcc_ts0, W(e, "ts_head.linears.0.bias"), 1024, 256, 32, 0);
+    pt.out32 = e->ts0;
+    if ((rc = run_chain(e, s, G_ROT_GFEAT, pc, &pt))) return rc;
+  }
+  // ---- H1 on the side stream (needs only the max-pooled features; independent of the rot head): the remaining
+  //      67 inputs of ts layer 0 (pointfeat max, init scale) are added in ts_head_kernel.
   TsPoseP tsp{};
   {
     tsp.ts0 = e->ts0; tsp.gmax_pf = e->gmax_pf; tsp.dts = e->dts;
@@ -503,8 +490,6 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     tsp.cls = prior_cls; tsp.n_cls = n_cls;
     CU_TRY(e, cudaEventRecord(e->ev_fork, s));
     CU_TRY(e, cudaStreamWaitEvent(e->side, e->ev_fork, 0));
-    if ((rc = run_fc<A_KEY>(e, e->side, G_TS_POSE, reinterpret_cast<const float*>(e->gmax_g), 2048, e->ts_w0g, 1024,
-                            W(e, "ts_head.linears.0.bias"), B, 256, 1024, 0, e->ts0, nullptr))) return rc;
     {
       Launch l(e, e->side, G_TS_POSE);
       launch_pdl(ts_head_kernel, dim3(B), dim3(256), (size_t)(0), e->side, tsp);
@@ -513,15 +498,6 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     CU_TRY(e, cudaEventRecord(e->ev_join, e->side));
   }
 
-  // ---- R1: rotation heads (heads/conv_out_per_rot_head.py:62-71,126-140) with the layer-0 split:
-  //      layers.0 . [g_set | pf_p] = W0[:, :1024] . g_set (once per set) + W0[:, 1024:] . pf_p
-  {
-    if (tc_fcs) {  // cset = W0g . g_set + b0 on the tensor cores (fp32 copy is what the consumers read; fc1o is a scratch sink)
-      if ((rc = tc_keys_split(e, s, G_ROT_GFEAT, e->gmax_g, S, e->g16))) return rc;
-      if ((rc = tc_fc(e, s, G_ROT_GFEAT, e->g16, e->tw_rot_w0g, S, 512, 1024, e->rot_b0, 0, e->fc1o, e->cset))) return rc;
-    } else if ((rc = run_fc<A_KEY>(e, s, G_ROT_GFEAT, reinterpret_cast<const float*>(e->gmax_g), 1024, e->rot_w0g, 1024, e->rot_b0, S, 512,
-                                   1024, 0, e->cset, nullptr))) return rc;
-  }
   float* gn0_scale = e->gn0;
   float* gn0_shift = e->gn0 + (size_t)e->maxB * 1024;
   if (tc) {
@@ -710,8 +686,6 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   e->gmax_fstn = e->gmax_all + S * 1024;
   e->gmax_g = e->gmax_all + S * 2048;
   e->gmax_pf = e->gmax_all + S * 3072;
-  rc |= dalloc(e, &e->fc512, S * 512);
-  rc |= dalloc(e, &e->fc256, S * 256);
   rc |= dalloc(e, &e->ts0, B * 256);
   rc |= dalloc(e, &e->dts, B * 6);
   rc |= dalloc(e, &e->t3, S * 9 + 7);
@@ -748,17 +722,7 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
       rc |= dalloc(e, &e->t64s.lo, Spad * 4096);
       if (!rc && (!tc_make_map(&e->t64s.map_hi, e->t64s.hi, S * 64, 64, 64, 64) ||
                   !tc_make_map(&e->t64s.map_lo, e->t64s.lo, S * 64, 64, 64, 64))) rc |= 2;
-      e->t64s_out.hi = e->t64s.hi; e->t64s_out.lo = e->t64s.lo;
-      if (!rc && (!tc_make_map(&e->t64s_out.map_hi, e->t64s.hi, Spad, 4096, 4096, 128) ||
-                  !tc_make_map(&e->t64s_out.map_lo, e->t64s.lo, Spad, 4096, 4096, 128))) rc |= 2;
     }
-    auto pair_rows = [&](TcPair& t, size_t rows, size_t cols) {
-      rc |= dalloc(e, &t.hi, rows * cols);
-      rc |= dalloc(e, &t.lo, rows * cols);
-      if (rc) return;
-      if (!tc_make_map(&t.map_hi, t.hi, rows, cols, cols, 128) || !tc_make_map(&t.map_lo, t.lo, rows, cols, cols, 128)) rc |= 2;
-    };
-    if (!rc) { pair_rows(e->g16, Spad, 1024); pair_rows(e->fc1o, Spad, 512); pair_rows(e->fc2o, Spad, 256); }
     if (!rc) {
       bool ok = true;
       ok &= tc_make_map(&e->a128_nb[0], e->a128.hi, R, 128, 128, 256) && tc_make_map(&e->a128_nb[1], e->a128.lo, R, 128, 128, 256);
@@ -808,6 +772,8 @@ int catre_set_weight(catre_engine* e, const char* name, const float* data, const
   }
   std::vector<float>& h = e->hw[name];
   h.resize(n);
+  // `data` may be a device tensor written on any of the caller's streams: wait for the device (set-up path, not hot)
+  CU_TRY(e, cudaDeviceSynchronize());
   CU_TRY(e, cudaMemcpy(h.data(), data, n * sizeof(float), cudaMemcpyDefault));
   e->dw_dirty.erase(name);
   e->packed = false;
@@ -816,8 +782,12 @@ int catre_set_weight(catre_engine* e, const char* name, const float* data, const
 
 int catre_pack(catre_engine* e, void* stream) {
   if (!e) return CATRE_ERR_INVALID_ARG;
-  (void)stream;
   CU_TRY(e, cudaSetDevice(e->cfg.device));
+  // Ordering contract (include/catre_b200.h): pack overwrites the device weights in place with blocking copies, so
+  // everything the caller enqueued before it -- catre_train_set_weight copies on `stream`, kernels still reading the
+  // old weights on any stream, non-blocking streams included -- must have finished first.
+  (void)stream;
+  CU_TRY(e, cudaDeviceSynchronize());
   for (int i = 0; i < kNumWeights; ++i)
     if (!e->hw.count(kWeights[i].name))
       return fail(e, CATRE_ERR_NOT_PACKED, "weight '%s' has not been set", kWeights[i].name);
@@ -894,6 +864,20 @@ int catre_pack(catre_engine* e, void* stream) {
     std::vector<float> t0g(256 * 1024);
     for (int c = 0; c < 256; ++c) memcpy(&t0g[(size_t)c * 1024], &t0[(size_t)c * 1091], 1024 * sizeof(float));
     up(&e->ts_w0g, t0g);
+    // fused FC chains (fc_chain.cuh): [8 ranks][K][C/8] fp32 slices, one contiguous stream per CTA and layer
+    auto pack_chain = [&](float** dst, const std::vector<float>& w, int C, int K, int NC) {
+      std::vector<float> pk((size_t)FCC_RANKS * K * NC);
+      fcc_pack(w.data(), C, K, NC, pk.data());
+      up(dst, pk);
+    };
+    pack_chain(&e->fcc_fc1[0], H("pcl_net.stn.fc1.weight"), 512, 1024, 64);
+    pack_chain(&e->fcc_fc2[0], H("pcl_net.stn.fc2.weight"), 256, 512, 32);
+    pack_chain(&e->fcc_fc3[0], H("pcl_net.stn.fc3.weight"), 9, 256, 2);
+    pack_chain(&e->fcc_fc1[1], H("pcl_net.fstn.fc1.weight"), 512, 1024, 64);
+    pack_chain(&e->fcc_fc2[1], H("pcl_net.fstn.fc2.weight"), 256, 512, 32);
+    pack_chain(&e->fcc_fc3[1], fstn_fc3_wT_host, 4096, 256, 512);
+    pack_chain(&e->fcc_cset, w0g, 512, 1024, 64);
+    pack_chain(&e->fcc_ts0, t0g, 256, 1024, 32);
   }
   if (rc) return fail(e, CATRE_ERR_CUDA, "uploading packed weights failed: %s", cudaGetErrorString(cudaGetLastError()));
 
@@ -932,12 +916,6 @@ int catre_pack(catre_engine* e, void* stream) {
     r2 = r2 ? r2 : wpair(e->tw_conv3, H("pcl_net.conv3.weight"), 512, 128, 128);
     r2 = r2 ? r2 : wpair(e->tw_conv4, H("pcl_net.conv4.weight"), 1024, 512, 128);
     r2 = r2 ? r2 : wpair(e->tw_rot0, w0p, 512, 64, 128);
-    r2 = r2 ? r2 : wpair(e->tw_fc1[0], H("pcl_net.stn.fc1.weight"), 512, 1024, 64);
-    r2 = r2 ? r2 : wpair(e->tw_fc1[1], H("pcl_net.fstn.fc1.weight"), 512, 1024, 64);
-    r2 = r2 ? r2 : wpair(e->tw_fc2[0], H("pcl_net.stn.fc2.weight"), 256, 512, 64);
-    r2 = r2 ? r2 : wpair(e->tw_fc2[1], H("pcl_net.fstn.fc2.weight"), 256, 512, 64);
-    r2 = r2 ? r2 : wpair(e->tw_fstn_fc3, fstn_fc3_wT_host, 4096, 256, 64);
-    r2 = r2 ? r2 : wpair(e->tw_rot_w0g, w0g, 512, 1024, 64);
     if (!r2 && (!tc_make_map(&e->tw_rot0_nb[0], e->tw_rot0.hi, 512, 64, 64, 256) ||
                 !tc_make_map(&e->tw_rot0_nb[1], e->tw_rot0.lo, 512, 64, 64, 256)))
       r2 = fail(e, CATRE_ERR_CUDA, "cuTensorMapEncodeTiled failed for the rot layer-0 N-side view");
@@ -1324,8 +1302,8 @@ int catre_debug_read(catre_engine* e, const char* name, void* dst_host, size_t b
   std::map<std::string, const void*> m = {
       {"q", e->q}, {"h64a", e->h64a}, {"h64b", e->h64b}, {"h128", e->h128}, {"h512", e->h512}, {"a0", e->a0}, {"a1", e->a1},
       {"gmax_stn", e->gmax_stn}, {"gmax_fstn", e->gmax_fstn}, {"gmax_g", e->gmax_g}, {"gmax_pf", e->gmax_pf},
-      {"fc512", e->fc512}, {"fc256", e->fc256}, {"t3", e->t3}, {"t64", e->t64}, {"cset", e->cset},
-      {"t64s_hi", e->t64s.hi}, {"t64s_lo", e->t64s.lo},
+      {"t3", e->t3}, {"t64", e->t64}, {"cset", e->cset},
+      {"t64s_hi", e->t64s.hi}, {"t64s_lo", e->t64s.lo}, {"ts0", e->ts0},
       {"stats0", e->stats0}, {"stats1", e->stats1}, {"gn0", e->gn0}, {"gn1", e->gn1}, {"rot_partial", e->rot_partial}};
   m["x64_hi"] = e->x64.hi; m["x64_lo"] = e->x64.lo; m["f64_hi"] = e->f64.hi; m["f64_lo"] = e->f64.lo;
   m["a128_hi"] = e->a128.hi; m["a128_lo"] = e->a128.lo; m["pf_hi"] = e->pf16.hi; m["pf_lo"] = e->pf16.lo;

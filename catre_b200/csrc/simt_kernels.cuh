@@ -921,8 +921,21 @@ __global__ void __launch_bounds__(256) pose_update_kernel(TsPoseP p, int B) {
     So[0] = sc_in[0] + outv[3];
     So[1] = sc_in[1] + outv[4];
     So[2] = sc_in[2] + outv[5];
+    const float qnan = __int_as_float(0x7fc00000);
+    // IEEE propagation as in the reference.  A non-finite input pose poisons the re-posed points (x = pcl - t,
+    // tfd_kps = R (s * kps): batch_test.py:85-97) and torch's relu / max / GroupNorm carry the NaN to every output
+    // that depends on them, whereas fmaxf() and the ordered-int atomicMax of this chain drop NaNs.  Restore it here:
+    // t or s non-finite -> everything (the ts head sees the observed features and the scale, the rot head both sets);
+    // only R non-finite -> only R' (t', s' do not depend on the prior set: WITH_KPS_FEATURE=False).  One REAL275
+    // initial pose (of 15,374) has t = 0, for which the reference itself returns NaN from iteration 1 on.
+    bool bad_r = false, bad_ts = false;
+    for (int i = 0; i < 9; ++i) bad_r |= !isfinite(Rin[i]);
+    for (int i = 0; i < 3; ++i) bad_ts |= !isfinite(tin[i]) || !isfinite(sc_in[i]);
+    if (bad_r || bad_ts) {
+      Pout[0] = Pout[1] = Pout[2] = Pout[4] = Pout[5] = Pout[6] = Pout[8] = Pout[9] = Pout[10] = qnan;
+      if (bad_ts) { Pout[3] = Pout[7] = Pout[11] = qnan; So[0] = So[1] = So[2] = qnan; }
+    }
     if (p.cls != nullptr && (p.cls[b] < 0 || p.cls[b] >= p.n_cls)) {  // bad class id: make it visible, not plausible
-      const float qnan = __int_as_float(0x7fc00000);
       for (int i = 0; i < 12; ++i) Pout[i] = qnan;
       So[0] = So[1] = So[2] = qnan;
     }

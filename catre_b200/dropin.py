@@ -179,15 +179,29 @@ _REQUIRED_CFG = {
     "MODEL.CATRE.TS_HEAD.INIT_CFG.norm": "GN",
     "MODEL.CATRE.TS_HEAD.INIT_CFG.act": "gelu",
     "MODEL.REFINE_SCLAE": True,
+    # the remaining constructor switches the kernels assume (conv_out_per_rot_head.py:85-106, fc_trans_size_head.py:9-44)
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.point_bias": True,
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.norm_input": False,
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.dropout": False,
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.rot_dim": 3,
+    "MODEL.CATRE.ROT_HEAD.INIT_CFG.kernel_size": 1,
+    "MODEL.CATRE.TS_HEAD.INIT_CFG.num_gn_groups": 32,
+    "MODEL.CATRE.TS_HEAD.INIT_CFG.norm_input": False,
+    "MODEL.CATRE.TS_HEAD.INIT_CFG.dropout": False,
+    # the fused K-loop hard-codes x = pcl - t and tfd_kps = R (s * kps) without + t (batch_test.py:84-97)
+    "INPUT.ZERO_CENTER_INPUT": True,
 }
+# keys whose value in the reference's BASE config (configs/_base_/catre_base.py:80) differs from the shipped one and
+# silently changes the arithmetic: an absent key means the base default, which is refused
+_ABSENT_MEANS = {"INPUT.ZERO_CENTER_INPUT": False}
 
 
 def check_cfg(cfg: Any) -> Tuple[int, int]:
     """Validate a reference config against what the engine implements; returns (n_obs, n_prior)."""
     bad = []
     for path, want in _REQUIRED_CFG.items():
-        got = _cfg_get(cfg, path, want)  # absent keys take the reference's base-config defaults
-        if got != want:
+        got = _cfg_get(cfg, path, _ABSENT_MEANS.get(path, want))  # other absent keys: the shipped config's value
+        if (got.lower() if isinstance(got, str) else got) != (want.lower() if isinstance(want, str) else want):
             bad.append(f"{path}={got!r} (engine implements {want!r})")
     if bad:
         raise NotImplementedError("catre_b200 implements the shipped CATRE config only: " + "; ".join(bad))
@@ -197,6 +211,60 @@ def check_cfg(cfg: Any) -> Tuple[int, int]:
     if n_rot != n_obs + n_prior:
         raise NotImplementedError(f"ROT_HEAD num_points={n_rot} != NUM_PCL+NUM_KPS={n_obs + n_prior}")
     return n_obs, n_prior
+
+
+def reference_init(n_obs: int, n_prior: int) -> Dict[str, torch.Tensor]:
+    """Fresh parameters drawn the way the reference's constructors draw them, from the GLOBAL torch RNG and in the
+    reference's order, so ``torch.manual_seed(s); build_model_optimizer(cfg)`` starts training from the same tensors as
+    the reference does (pinned by tests/test_dropin_init.py against the unmodified reference's build):
+
+    * ``pcl_net`` keeps torch's stock Conv1d / Linear initialisation -- kaiming-uniform(a=sqrt 5) weights and
+      uniform(+-1/sqrt(fan_in)) biases -- in construction order stn, conv1..4, fstn (pointnets/pointnet.py:15-21, 46-52,
+      88-95);
+    * each head is constructed (stock init, consuming the RNG) and then re-drawn by its ``_init_weights``: Conv1d / Linear
+      weights ~ N(0, 0.001), biases 0, GroupNorm 1 / 0, in ``self.modules()`` order; ``fc_t`` / ``fc_s`` a second time with
+      std 0.01 (heads/conv_out_per_rot_head.py:93-124, heads/fc_trans_size_head.py:28-59); rot_head (x, then y) before
+      ts_head (CATRE_disR_shared.py:311-315).
+
+    Only stock torch layers are built here; they exist to consume the RNG exactly as the reference's layers do."""
+    out: Dict[str, torch.Tensor] = {}
+
+    def keep(prefix: str, layer: nn.Module) -> nn.Module:
+        out[prefix + ".weight"], out[prefix + ".bias"] = layer.weight.data, layer.bias.data
+        return layer
+
+    def tnet(prefix: str, k_in: int, k_out: int) -> None:
+        keep(prefix + ".conv1", nn.Conv1d(k_in, 64, 1)); keep(prefix + ".conv2", nn.Conv1d(64, 128, 1))
+        keep(prefix + ".conv3", nn.Conv1d(128, 1024, 1)); keep(prefix + ".fc1", nn.Linear(1024, 512))
+        keep(prefix + ".fc2", nn.Linear(512, 256)); keep(prefix + ".fc3", nn.Linear(256, k_out))
+
+    tnet("pcl_net.stn", 3, 9)
+    keep("pcl_net.conv1", nn.Conv1d(3, 64, 1)); keep("pcl_net.conv2", nn.Conv1d(64, 128, 1))
+    keep("pcl_net.conv3", nn.Conv1d(128, 512, 1)); keep("pcl_net.conv4", nn.Conv1d(512, 1024, 1))
+    tnet("pcl_net.fstn", 64, 4096)
+
+    def head_normal(layer: nn.Module, std: float) -> None:
+        nn.init.normal_(layer.weight, 0.0, std)
+        nn.init.constant_(layer.bias, 0.0)
+
+    for axis in ("x", "y"):
+        pre = f"rot_head.rot_head_{axis}."
+        for gn in ("norm", "layers.1", "layers.4"):
+            keep(pre + gn, nn.GroupNorm(32, 256))  # constructed 1 / 0 and re-set to 1 / 0: no RNG either way
+        # construction order (stock init draws), then the re-draw in modules() order: layers.0, layers.3, neck.0, conv_p
+        convs = [keep(pre + "layers.0", nn.Conv1d(1088, 256, 1)), keep(pre + "layers.3", nn.Conv1d(256, 256, 1)),
+                 keep(pre + "neck.0", nn.Conv1d(256, 3, 1)), keep(pre + "conv_p", nn.Conv1d(n_obs + n_prior, 1, 1))]
+        for c in convs:
+            head_normal(c, 0.001)
+    for gn in ("norm", "linears.1", "linears.4"):
+        keep("ts_head." + gn, nn.GroupNorm(32, 256))
+    lin = [keep("ts_head.linears.0", nn.Linear(1091, 256)), keep("ts_head.linears.3", nn.Linear(256, 256)),
+           keep("ts_head.fc_t", nn.Linear(256, 3)), keep("ts_head.fc_s", nn.Linear(256, 3))]
+    for l in lin:
+        head_normal(l, 0.001)
+    head_normal(lin[2], 0.01)
+    head_normal(lin[3], 0.01)
+    return out
 
 
 class CatreB200(nn.Module):
@@ -213,7 +281,7 @@ class CatreB200(nn.Module):
         self.n_obs, self.n_prior = int(n_obs), int(n_prior)
         self.precision = precision
         self.max_batch = int(max_batch)
-        g = torch.Generator().manual_seed(0)
+        init = reference_init(n_obs, n_prior)  # the reference's own initial distribution, from the global torch RNG
         for name, shape in param_specs(n_obs, n_prior):
             parts = name.split(".")
             node: nn.Module = self
@@ -221,13 +289,8 @@ class CatreB200(nn.Module):
                 if p not in node._modules:
                     node.add_module(p, _Holder())
                 node = node._modules[p]
-            if parts[-1] == "bias":
-                init = torch.zeros(shape)
-            elif len(shape) == 1:
-                init = torch.ones(shape)  # norm scales
-            else:
-                init = torch.randn(shape, generator=g) * 0.01
-            node.register_parameter(parts[-1], nn.Parameter(init))
+            assert tuple(init[name].shape) == tuple(shape), name
+            node.register_parameter(parts[-1], nn.Parameter(init[name].clone()))
         self._engine: Optional[_engine.Engine] = None
         self._packed_key = None
         self._train_versions: Optional[Dict[str, Tuple[int, int]]] = None  # per tensor (version, data_ptr) the engine's training copy holds
@@ -473,6 +536,12 @@ def build_model_optimizer(cfg, is_test: bool = False, precision: str = "f16x3", 
     """Same contract as the reference's build_model_optimizer (CATRE_disR_shared.py:291-350):
     returns (model, optimizer).  ``optimizer`` is None for is_test=True, as in the reference."""
     n_obs, n_prior = check_cfg(cfg)
+    pretrained = _cfg_get(cfg, "MODEL.CATRE.PCLNET.PRETRAINED", "")
+    if _cfg_get(cfg, "MODEL.WEIGHTS", "") == "" and pretrained not in ("", None):
+        # the reference loads these into pcl_net with mmcv's load_checkpoint (CATRE_disR_shared.py:327-346); the shipped
+        # config leaves it empty.  Refuse rather than silently start from random weights.
+        raise NotImplementedError(f"MODEL.CATRE.PCLNET.PRETRAINED={pretrained!r}: load the file into model.pcl_net yourself "
+                                  "(state_dict names are the reference's) and clear the key")
     model = CatreB200(n_obs, n_prior, precision=precision, max_batch=max_batch, cfg=cfg)
     device = _cfg_get(cfg, "MODEL.DEVICE", "cuda")
     model.to(torch.device(device))

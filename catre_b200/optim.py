@@ -73,7 +73,9 @@ class FusedRanger(Optimizer):
                             ("slow_buffer", st["slow_buffer"])):
                 if t.dtype != torch.float32 or not t.is_contiguous() or t.device != dev:
                     raise NotImplementedError(f"FusedRanger: {name} must be a contiguous float32 tensor on {dev}")
-            gc = self.use_gc and g.dim() > self.gc_gradient_threshold
+            # like the reference's step() (lib/torch_utils/solver/ranger.py:146-148): centralise whenever the gradient has more
+            # dims than the threshold -- use_gc only chooses that threshold in the constructor, it does not gate the step
+            gc = g.dim() > self.gc_gradient_threshold
             row_len = p.numel() // p.shape[0] if gc else 0
             rows.append(p.shape[0] if gc else 0)
             table.append([p.data_ptr(), g.data_ptr(), st["exp_avg"].data_ptr(), st["exp_avg_sq"].data_ptr(), st["slow_buffer"].data_ptr(),

@@ -73,8 +73,11 @@ int catre_set_weight(catre_engine* e, const char* name, const float* data, const
 int32_t catre_num_weights(void);
 const char* catre_weight_name(int32_t i);
 
-/* Derive the engine's packed weights (stacked heads, folded identities, bf16 hi/lo splits). Must be
- * called after the weights change and before forward/refine.  Stream-ordered. */
+/* Derive the engine's packed weights (stacked heads, folded identities, 16-bit hi/lo splits, FC-chain slices). Must
+ * be called after the weights change and before forward/refine.  Ordering: a set-up call, not a hot one -- it (and
+ * catre_set_weight) waits for the whole device (cudaDeviceSynchronize) before touching the weights, so work enqueued
+ * earlier on ANY stream (catre_train_set_weight copies, kernels still reading the old weights) is complete, and it
+ * returns with the packed weights resident.  `stream` is accepted for symmetry with the hot calls. */
 int catre_pack(catre_engine* e, void* stream);
 
 /* Bytes of device workspace the engine holds for a launch of B objects (0 <= B <= max_batch). */

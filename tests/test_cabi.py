@@ -10,6 +10,8 @@ import torch
 
 from catre_b200 import build, dropin, engine, synth
 
+ZC = {"ZERO_CENTER_INPUT": True}  # the shipped config's value; the reference's base default (False) is refused
+
 REPO = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
@@ -100,29 +102,41 @@ def test_training_cfg_and_sym_info_checks():
     assert dropin.split_sym_info([None])[1].shape == (0, 3, 3)
     with pytest.raises(NotImplementedError):
         dropin.split_sym_info([r, 2 * r])
-    model, opt = dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "SGD", "lr": 1e-3}}},
+    model, opt = dropin.build_model_optimizer({"INPUT": ZC, "MODEL": {"DEVICE": "cpu"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "SGD", "lr": 1e-3}}},
                                               is_test=False)
     assert isinstance(opt, torch.optim.SGD) and model.training
     from catre_b200 import optim
 
-    _, opt = dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "Ranger", "lr": 1e-4,
+    _, opt = dropin.build_model_optimizer({"INPUT": ZC, "MODEL": {"DEVICE": "cpu"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "Ranger", "lr": 1e-4,
                                                                                                    "weight_decay": 0}}}, is_test=False)
     assert isinstance(opt, optim.FusedRanger) and opt.param_groups[0]["lr"] == 1e-4  # the shipped config's optimiser
     assert [len(g["params"]) for g in opt.param_groups] == [32, 28, 14]  # pcl_net, rot_head, ts_head -- the reference's groups
-    cfg = {"MODEL": {"DEVICE": "cpu", "CATRE": {"ROT_HEAD": {"LR_MULT": 0.5}, "TS_HEAD": {"FREEZE": True}}},
+    cfg = {"INPUT": ZC, "MODEL": {"DEVICE": "cpu", "CATRE": {"ROT_HEAD": {"LR_MULT": 0.5}, "TS_HEAD": {"FREEZE": True}}},
            "SOLVER": {"BASE_LR": 2e-4, "OPTIMIZER_CFG": {"type": "SGD", "lr": 1e-3}}}
     model, opt = dropin.build_model_optimizer(cfg, is_test=False)
     assert [g["lr"] for g in opt.param_groups] == [2e-4, 1e-4] and not model.ts_head.fc_t.weight.requires_grad
 
 
 def test_check_cfg():
-    cfg = {"INPUT": {"NUM_PCL": 1024, "NUM_KPS": 1024},
+    cfg = {"INPUT": {"NUM_PCL": 1024, "NUM_KPS": 1024, "ZERO_CENTER_INPUT": True},
            "MODEL": {"REFINE_SCLAE": True, "CATRE": {"ROT_HEAD": {"ROT_TYPE": "ego_rot6d", "INIT_CFG": {"num_points": 2048}}}}}
     assert dropin.check_cfg(cfg) == (1024, 1024)
     cfg["MODEL"]["CATRE"]["ROT_HEAD"]["ROT_TYPE"] = "allo_rot6d"
     with pytest.raises(NotImplementedError):
         dropin.check_cfg(cfg)
     with pytest.raises(NotImplementedError):
-        dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}}, is_test=False)
-    model, opt = dropin.build_model_optimizer({"MODEL": {"DEVICE": "cpu"}}, is_test=True)
+        dropin.build_model_optimizer({"INPUT": ZC, "MODEL": {"DEVICE": "cpu"}}, is_test=False)
+    model, opt = dropin.build_model_optimizer({"INPUT": ZC, "MODEL": {"DEVICE": "cpu"}}, is_test=True)
     assert opt is None and not model.training
+    # the fused K-loop hard-codes ZERO_CENTER_INPUT=True; the reference's base default is False, so an absent
+    # key (or False) is refused; so are the constructor switches the kernels assume and a PRETRAINED pcl_net
+    for bad in ({"MODEL": {"DEVICE": "cpu"}}, {"INPUT": {"ZERO_CENTER_INPUT": False}, "MODEL": {"DEVICE": "cpu"}},
+                {"INPUT": ZC, "MODEL": {"CATRE": {"ROT_HEAD": {"INIT_CFG": {"point_bias": False}}}}},
+                {"INPUT": ZC, "MODEL": {"CATRE": {"ROT_HEAD": {"INIT_CFG": {"norm_input": True}}}}},
+                {"INPUT": ZC, "MODEL": {"CATRE": {"TS_HEAD": {"INIT_CFG": {"num_gn_groups": 16}}}}},
+                {"INPUT": ZC, "MODEL": {"CATRE": {"TS_HEAD": {"INIT_CFG": {"dropout": True}}}}}):
+        with pytest.raises(NotImplementedError):
+            dropin.check_cfg(bad)
+    with pytest.raises(NotImplementedError):
+        dropin.build_model_optimizer({"INPUT": ZC, "MODEL": {"DEVICE": "cpu", "WEIGHTS": "", "CATRE": {"PCLNET": {"PRETRAINED": "x.pth"}}}},
+                                     is_test=True)

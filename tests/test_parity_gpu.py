@@ -286,3 +286,34 @@ def test_oracle_parity_k8_symmetric_categories(weights, prec):
     poses, scales = run_refine(get_engine(weights, 1024, prec), sub, 8)
     e = gu.max_abs_err(poses, scales, ref_p, ref_s)
     assert max(e) <= TOL, e
+
+
+@pytest.mark.parametrize("prec", PRECS)
+@pytest.mark.parametrize("name", gu.full_case_names())
+def test_full_size_reference_goldens(weights, name, prec):
+    """BASELINE.json's configs at the sizes they name, against outputs of the UNMODIFIED reference
+    (tests/golden/make_golden_full.py): the north-star headline (256 objects, N=1024, K=4), config 4 (256 objects,
+    N=2048, K=8) and config 5 (384 objects = 64 per category, mixed).  Two gates: the 1e-4 contract against the
+    reference's fp32 output, and the per-mode regression threshold against the fp64 oracle on the same inputs
+    (gu.REGRESSION_TOL).  Where the reference returns NaN (the one REAL275 initial pose with t = 0) the engine must too,
+    and only there."""
+    case = gu.load_full_case(name)
+    eng = get_engine(weights, case.n_pts, prec, max_batch=256)  # 384 objects run as two chunks
+    poses, scales = run_refine(eng, case.batch, case.n_iter)
+    e = gu.max_abs_err_nan_aware(poses, scales, case.poses, case.scales)
+    assert max(e) <= TOL, (name, prec, "vs reference fp32", e)
+    e64 = gu.max_abs_err_nan_aware(poses, scales, case.poses64, case.scales64)
+    assert max(e64) <= gu.REGRESSION_TOL[(prec, case.n_iter)], (name, prec, "vs fp64 oracle", e64)
+    print(f"\n[full-size parity] {name} {prec}: vs reference fp32 {max(e):.2e}, vs fp64 oracle {max(e64):.2e}")
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_result_is_independent_of_launch_size(weights, prec):
+    """An object's result must not depend on how many objects share its launch: the same 160
+    objects refined in launches of 160, 64 (+32 tail) and 5 give identical BYTES.  (Round 1 switched the T-Net FC chain
+    to a different arithmetic from 128 objects per launch on.)"""
+    b = synth.make_batch(160, 1024, seed=71)
+    ref = run_refine(get_engine(weights, 1024, prec, max_batch=256), b, 2)
+    for mb in (64, 5):
+        got = run_refine(get_engine(weights, 1024, prec, max_batch=mb), b, 2)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), (prec, mb)

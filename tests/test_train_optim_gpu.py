@@ -8,6 +8,8 @@ from catre_b200 import dropin, optim, synth
 from tests.test_optim import run_fused
 from tests.test_train_gpu import inputs, y_symmetry_rotations
 
+ZC = {"ZERO_CENTER_INPUT": True}  # the shipped config's value; the reference's base default (False) is refused
+
 pytestmark = pytest.mark.gpu
 
 
@@ -17,7 +19,7 @@ def test_fused_ranger_matches_reference_goldens_on_cuda():
 
 def test_dropin_iteration_with_fused_ranger():
     d, tgt, x_pm, tfd_pm = inputs()
-    cfg = {"MODEL": {"DEVICE": "cuda"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "Ranger", "lr": 1e-4, "weight_decay": 0}}}
+    cfg = {"INPUT": ZC, "MODEL": {"DEVICE": "cuda"}, "SOLVER": {"OPTIMIZER_CFG": {"type": "Ranger", "lr": 1e-4, "weight_decay": 0}}}
     model, opt = dropin.build_model_optimizer(cfg, is_test=False, max_batch=8)
     assert isinstance(opt, optim.FusedRanger)
     model.load_state_dict(synth.load_weights(), strict=True)

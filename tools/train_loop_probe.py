@@ -17,6 +17,8 @@ from catre_b200 import dropin, synth  # noqa: E402
 from oracle import catre_oracle as co, train_oracle as to  # noqa: E402  (baseline leg only)
 from tools.optim_probe import torch_ranger_step  # noqa: E402
 
+ZC = {"ZERO_CENTER_INPUT": True}  # the shipped config's value; the reference's base default (False) is refused
+
 
 def timed(fn, n_warm=3, n=8):
     for i in range(n_warm):
@@ -42,7 +44,7 @@ def main():
         x, tfd = co.update_points(d.pcl, d.prior, d.init_pose, d.init_scale)
 
         # (a) drop-in + fused optimiser
-        cfg = {"MODEL": {"DEVICE": dev}, "SOLVER": {"OPTIMIZER_CFG": {"type": "Ranger", "lr": 1e-4, "weight_decay": 0}}}
+        cfg = {"INPUT": ZC, "MODEL": {"DEVICE": dev}, "SOLVER": {"OPTIMIZER_CFG": {"type": "Ranger", "lr": 1e-4, "weight_decay": 0}}}
         model, opt = dropin.build_model_optimizer(cfg, is_test=False, max_batch=max(8, B))
         model.load_state_dict(w, strict=True)
 
