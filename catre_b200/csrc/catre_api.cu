@@ -122,6 +122,7 @@ struct catre_engine {
   // fused FC chains (fc_chain.cuh): weights packed [8 ranks][K][C/8] fp32; [0] = stn, [1] = fstn
   float *fcc_fc1[2] = {nullptr, nullptr}, *fcc_fc2[2] = {nullptr, nullptr}, *fcc_fc3[2] = {nullptr, nullptr};
   float *fcc_cset = nullptr, *fcc_ts0 = nullptr;
+  int fcc_ranks = 8;  // CTAs per FC-chain cluster (16 where the device co-schedules them), fixed per engine
   TcPair t64s;  // tensor-core modes: bf16 hi/lo of T64^T, [S*64, 64]
   float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
   // bf16 hi/lo activations of the tensor-core path and their tensor maps
@@ -321,9 +322,9 @@ int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv,
 }
 
 // ---- fused FC chains (fc_chain.cuh): one cluster launch per chain, fp32, same arithmetic at every batch size
-FccLayer fcc_layer_desc(const float* wp, const float* bias, int K, int C, int NC, int relu) {
+FccLayer fcc_layer_desc(const catre_engine* e, const float* wp, const float* bias, int K, int C, int relu) {
   FccLayer l{};
-  l.wp = wp; l.bias = bias; l.K = K; l.C = C; l.NC = NC; l.relu = relu;
+  l.wp = wp; l.bias = bias; l.K = K; l.C = C; l.NC = fcc_nc(C, e->fcc_ranks); l.relu = relu;
   return l;
 }
 
@@ -335,11 +336,11 @@ int run_chain(catre_engine* e, cudaStream_t s, int grp, const FccProblem& p0, co
   if (p1) { b.p[1] = *p1; clusters += (p1->rows + FCC_ROWS - 1) / FCC_ROWS; }
   for (int q = 0; q < (p1 ? 2 : 1); ++q)
     for (int l = 0; l < b.p[q].n_layers; ++l)
-      if (!fcc_layer_ok(b.p[q].L[l])) return fail(e, CATRE_ERR_UNSUPPORTED, "fc chain: unsupported layer geometry");
+      if (!fcc_layer_ok(b.p[q].L[l], e->fcc_ranks)) return fail(e, CATRE_ERR_UNSUPPORTED, "fc chain: unsupported layer geometry");
   cudaError_t st;
   {
     Launch l(e, s, grp);
-    st = fcc_launch(b, clusters, s);
+    st = fcc_launch(b, clusters, e->fcc_ranks, s);
   }
   if (st != cudaSuccess) {
     cudaGetLastError();
@@ -354,13 +355,13 @@ int tnet_fc_chain(catre_engine* e, cudaStream_t s, const int* keys, int S, int w
   const bool tc = e->cfg.precision != CATRE_PREC_FP32_SIMT;
   FccProblem p{};
   p.keys = keys; p.lda = 1024; p.rows = S; p.n_layers = 3;
-  p.L[0] = fcc_layer_desc(e->fcc_fc1[which], W(e, (pf + ".fc1.bias").c_str()), 1024, 512, 64, 1);
-  p.L[1] = fcc_layer_desc(e->fcc_fc2[which], W(e, (pf + ".fc2.bias").c_str()), 512, 256, 32, 1);
+  p.L[0] = fcc_layer_desc(e, e->fcc_fc1[which], W(e, (pf + ".fc1.bias").c_str()), 1024, 512, 1);
+  p.L[1] = fcc_layer_desc(e, e->fcc_fc2[which], W(e, (pf + ".fc2.bias").c_str()), 512, 256, 1);
   if (which == 0) {
-    p.L[2] = fcc_layer_desc(e->fcc_fc3[0], e->stn_fc3_bI, 256, 9, 2, 0);
+    p.L[2] = fcc_layer_desc(e, e->fcc_fc3[0], e->stn_fc3_bI, 256, 9, 0);
     p.out32 = e->t3;
   } else {  // fc3's rows are permuted at pack time so the chain emits T64^T (the feature transform's N-side operand)
-    p.L[2] = fcc_layer_desc(e->fcc_fc3[1], e->fstn_fc3_bI, 256, 4096, 512, 0);
+    p.L[2] = fcc_layer_desc(e, e->fcc_fc3[1], e->fstn_fc3_bI, 256, 4096, 0);
     if (tc) {
       p.out_hi = reinterpret_cast<unsigned short*>(e->t64s.hi);
       p.out_lo = reinterpret_cast<unsigned short*>(e->t64s.lo);
@@ -468,10 +469,10 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   {
     FccProblem pc{}, pt{};
     pc.keys = e->gmax_g; pc.lda = 1024; pc.rows = S; pc.n_layers = 1;
-    pc.L[0] = fcc_layer_desc(e->fcc_cset, e->rot_b0, 1024, 512, 64, 0);
+    pc.L[0] = fcc_layer_desc(e, e->fcc_cset, e->rot_b0, 1024, 512, 0);
     pc.out32 = e->cset;
     pt.keys = e->gmax_g; pt.lda = 2048; pt.rows = B; pt.n_layers = 1;
-    pt.L[0] = fcc_layer_desc(e->fcc_ts0, W(e, "ts_head.linears.0.bias"), 1024, 256, 32, 0);
+    pt.L[0] = fcc_layer_desc(e, e->fcc_ts0, W(e, "ts_head.linears.0.bias"), 1024, 256, 0);
     pt.out32 = e->ts0;
     if ((rc = run_chain(e, s, G_ROT_GFEAT, pc, &pt))) return rc;
   }
@@ -705,6 +706,12 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   rc |= dalloc(e, &e->st_oposes, B * 12 * (catre_engine::kMaxHostIter + 1));
   rc |= dalloc(e, &e->st_oscales, B * 3 * (catre_engine::kMaxHostIter + 1));
   e->num_sms = prop.multiProcessorCount;
+  {
+    // 8-CTA clusters measured faster than 16 on B200 (profiles/r02_ncu_fc_chain.txt); CATRE_FC_RANKS=16 selects the
+    // non-portable size where the device can co-schedule it (experiments)
+    const char* env = getenv("CATRE_FC_RANKS");
+    e->fcc_ranks = (env && atoi(env) == 16) ? fcc_pick_ranks() : 8;
+  }
   if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) rc |= 1;
@@ -865,19 +872,20 @@ int catre_pack(catre_engine* e, void* stream) {
     for (int c = 0; c < 256; ++c) memcpy(&t0g[(size_t)c * 1024], &t0[(size_t)c * 1091], 1024 * sizeof(float));
     up(&e->ts_w0g, t0g);
     // fused FC chains (fc_chain.cuh): [8 ranks][K][C/8] fp32 slices, one contiguous stream per CTA and layer
-    auto pack_chain = [&](float** dst, const std::vector<float>& w, int C, int K, int NC) {
-      std::vector<float> pk((size_t)FCC_RANKS * K * NC);
-      fcc_pack(w.data(), C, K, NC, pk.data());
+    auto pack_chain = [&](float** dst, const std::vector<float>& w, int C, int K) {
+      const int NC = fcc_nc(C, e->fcc_ranks);
+      std::vector<float> pk((size_t)e->fcc_ranks * K * NC);
+      fcc_pack(w.data(), C, K, NC, e->fcc_ranks, pk.data());
       up(dst, pk);
     };
-    pack_chain(&e->fcc_fc1[0], H("pcl_net.stn.fc1.weight"), 512, 1024, 64);
-    pack_chain(&e->fcc_fc2[0], H("pcl_net.stn.fc2.weight"), 256, 512, 32);
-    pack_chain(&e->fcc_fc3[0], H("pcl_net.stn.fc3.weight"), 9, 256, 2);
-    pack_chain(&e->fcc_fc1[1], H("pcl_net.fstn.fc1.weight"), 512, 1024, 64);
-    pack_chain(&e->fcc_fc2[1], H("pcl_net.fstn.fc2.weight"), 256, 512, 32);
-    pack_chain(&e->fcc_fc3[1], fstn_fc3_wT_host, 4096, 256, 512);
-    pack_chain(&e->fcc_cset, w0g, 512, 1024, 64);
-    pack_chain(&e->fcc_ts0, t0g, 256, 1024, 32);
+    pack_chain(&e->fcc_fc1[0], H("pcl_net.stn.fc1.weight"), 512, 1024);
+    pack_chain(&e->fcc_fc2[0], H("pcl_net.stn.fc2.weight"), 256, 512);
+    pack_chain(&e->fcc_fc3[0], H("pcl_net.stn.fc3.weight"), 9, 256);
+    pack_chain(&e->fcc_fc1[1], H("pcl_net.fstn.fc1.weight"), 512, 1024);
+    pack_chain(&e->fcc_fc2[1], H("pcl_net.fstn.fc2.weight"), 256, 512);
+    pack_chain(&e->fcc_fc3[1], fstn_fc3_wT_host, 4096, 256);
+    pack_chain(&e->fcc_cset, w0g, 512, 1024);
+    pack_chain(&e->fcc_ts0, t0g, 256, 1024);
   }
   if (rc) return fail(e, CATRE_ERR_CUDA, "uploading packed weights failed: %s", cudaGetErrorString(cudaGetLastError()));
 
@@ -1131,17 +1139,48 @@ int catre_cloud_gather(const float* depth, const float* intr, const int32_t* sel
 }
 
 // ---- pairwise NOCS pose metrics (metrics_kernels.cuh): engine-independent ----
+int catre_pair_metrics_ex(const double* pred_RT, const double* pred_scale, const int32_t* pred_cls, const double* gt_RT,
+                          const double* gt_scale, const int32_t* gt_cls, const int32_t* gt_handle, const int32_t* pair_pred,
+                          const int32_t* pair_gt, int32_t n_pairs, uint32_t sym_class_mask, uint32_t flip_class_mask,
+                          int32_t mug_class, int32_t shift_mode, float* iou, float* deg_shift, double* deg_shift64, void* stream) {
+  if (n_pairs == 0) return CATRE_OK;
+  if (n_pairs < 0) return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_pair_metrics: negative n_pairs %d", n_pairs);
+  if (shift_mode != 0 && shift_mode != 1) return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_pair_metrics: shift_mode %d", shift_mode);
+  if (!pred_RT || !pred_scale || !pred_cls || !gt_RT || !gt_scale || !gt_cls || !gt_handle || !pair_pred || !pair_gt || !iou ||
+      (!deg_shift && !deg_shift64))
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_pair_metrics: null argument");
+  PairMetricsP p{pred_RT, pred_scale, pred_cls, gt_RT, gt_scale, gt_cls, gt_handle, pair_pred, pair_gt, n_pairs,
+                 sym_class_mask, flip_class_mask, mug_class, iou, deg_shift, shift_mode, deg_shift64};
+  pair_metrics_kernel<<<(n_pairs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  CU_TRY(nullptr, cudaGetLastError());
+  return CATRE_OK;
+}
+
 int catre_pair_metrics(const double* pred_RT, const double* pred_scale, const int32_t* pred_cls, const double* gt_RT,
                        const double* gt_scale, const int32_t* gt_cls, const int32_t* gt_handle, const int32_t* pair_pred,
                        const int32_t* pair_gt, int32_t n_pairs, uint32_t sym_class_mask, uint32_t flip_class_mask,
                        int32_t mug_class, float* iou, float* deg_shift, void* stream) {
-  if (n_pairs == 0) return CATRE_OK;
-  if (n_pairs < 0) return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_pair_metrics: negative n_pairs %d", n_pairs);
-  if (!pred_RT || !pred_scale || !pred_cls || !gt_RT || !gt_scale || !gt_cls || !gt_handle || !pair_pred || !pair_gt || !iou || !deg_shift)
-    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_pair_metrics: null argument");
-  PairMetricsP p{pred_RT, pred_scale, pred_cls, gt_RT, gt_scale, gt_cls, gt_handle, pair_pred, pair_gt, n_pairs,
-                 sym_class_mask, flip_class_mask, mug_class, iou, deg_shift};
-  pair_metrics_kernel<<<(n_pairs + 127) / 128, 128, 0, (cudaStream_t)stream>>>(p);
+  if (n_pairs > 0 && !deg_shift) return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_pair_metrics: null argument");
+  return catre_pair_metrics_ex(pred_RT, pred_scale, pred_cls, gt_RT, gt_scale, gt_cls, gt_handle, pair_pred, pair_gt, n_pairs,
+                               sym_class_mask, flip_class_mask, mug_class, 0, iou, deg_shift, nullptr, stream);
+}
+
+int catre_match_greedy(int32_t mode, const int32_t* sub_pred_off, const int32_t* sub_gt_off, const int32_t* sub_pair_off,
+                       int32_t n_sub, int32_t n_pred, int32_t n_gt, const float* iou, const double* deg_shift64,
+                       const int32_t* order, const int32_t* n_cand, const int32_t* pred_cls, const int32_t* gt_cls,
+                       const double* thr_a, int32_t n_a, const double* thr_b, int32_t n_b, int32_t* gt_match,
+                       int32_t* pred_match, void* stream) {
+  if (n_sub == 0 || n_a * n_b == 0) return CATRE_OK;
+  if (mode != 0 && mode != 1) return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_match_greedy: mode %d", mode);
+  if (n_sub < 0 || n_pred < 0 || n_gt < 0 || n_a < 1 || n_b < 1)
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_match_greedy: bad sizes");
+  if (!sub_pred_off || !sub_gt_off || !sub_pair_off || !thr_a || (mode == 1 && !thr_b) || !gt_match || !pred_match ||
+      (mode == 0 ? !iou : !deg_shift64) || !order || !n_cand || !pred_cls || !gt_cls)
+    return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_match_greedy: null argument");
+  MatchP p{sub_pred_off, sub_gt_off, sub_pair_off, iou, deg_shift64, order, n_cand, pred_cls, gt_cls, thr_a, n_a,
+           thr_b, n_b, gt_match, pred_match, n_sub, n_pred, n_gt, mode};
+  const long long threads = (long long)n_sub * n_a * n_b;
+  match_kernel<<<(unsigned)((threads + 127) / 128), 128, 0, (cudaStream_t)stream>>>(p);
   CU_TRY(nullptr, cudaGetLastError());
   return CATRE_OK;
 }

@@ -24,7 +24,12 @@ struct PairMetricsP {
   unsigned flip_mask;        // bit c set: class c is symmetric under a 180-degree y flip (phone, eggbox, glue)
   int mug_cls;               // class id of "mug" (-1: none): symmetric when the handle is not visible
   float* iou;                // [M]
-  float* deg_shift;          // [M, 2] theta [degrees], |T1 - T2| / cbrt(det(gt_RT[:3,:3]))
+  float* deg_shift;          // [M, 2] theta [degrees], shift (fp32 copy; may be null when deg_shift64 is given)
+  // shift definition: 0 = |T1 - T2| / cbrt(det(gt_RT[:3,:3]))  (compute_combination_RT_degree_cm_symmetry, test_utils.py:275)
+  //                   1 = |T1 - T2| * 100 [cm]                  (compute_RT_degree_cm_symmetry, test_utils.py:687: the one
+  //                       compute_independent_mAP -- the metric the NOCS evaluator calls -- is built on)
+  int shift_mode;
+  double* deg_shift64;       // [M, 2] the same in fp64 (compute_RT_overlaps keeps fp64, test_utils.py:703), or null
 };
 
 // axis-aligned hull of the box (+-s/2) under the 4x4 matrix m (row-major), with the homogeneous divide
@@ -126,8 +131,79 @@ __global__ void __launch_bounds__(128) pair_metrics_kernel(PairMetricsP p) {
   }
   theta *= 180.0 / 3.14159265358979323846;
   const double tx = m1[3] - m2[3], ty = m1[7] - m2[7], tz = m1[11] - m2[11];
-  p.deg_shift[2 * (size_t)t] = (float)theta;
-  p.deg_shift[2 * (size_t)t + 1] = (float)(sqrt(tx * tx + ty * ty + tz * tz) / d2);
+  const double dist = sqrt(tx * tx + ty * ty + tz * tz);
+  const double shift = p.shift_mode == 1 ? dist * 100.0 : dist / d2;
+  if (p.deg_shift) {
+    p.deg_shift[2 * (size_t)t] = (float)theta;
+    p.deg_shift[2 * (size_t)t + 1] = (float)shift;
+  }
+  if (p.deg_shift64) {
+    p.deg_shift64[2 * (size_t)t] = theta;
+    p.deg_shift64[2 * (size_t)t + 1] = shift;
+  }
+}
+
+// ----------------------------------------------------------------------------------------------------------------
+// Greedy prediction <-> ground-truth matching of the NOCS protocol, one thread per (sub-problem, threshold combination).
+// A sub-problem is one (image, class) pair of compute_independent_mAP (test_utils.py:793-880): P predictions in score
+// order, G ground truths, a [P, G] pair table.  The loops are sequential in the prediction and in its candidate list but
+// independent across sub-problems and thresholds -- REAL275 has ~16 k sub-problems x 4 (IoU) or 3 x 4 (pose) thresholds.
+//   mode 0 = compute_3d_matches (test_utils.py:586-614): candidates by descending IoU; a taken ground truth is skipped,
+//            IoU below the threshold ends the search, another class is skipped, IoU strictly above the threshold matches.
+//   mode 1 = compute_match_from_degree_cm (test_utils.py:734-755): candidates by ascending (degree + shift); taken or
+//            other-class ground truths are skipped, so are candidates over either threshold; the first survivor matches.
+// The candidate ORDER of every row comes from the host (numpy's argsort of that row: its tie order is what the
+// reference's results depend on, and numpy's SIMD sorts are not stable, so it cannot be re-derived here).
+// ----------------------------------------------------------------------------------------------------------------
+struct MatchP {
+  const int* sub_pred_off;  // [n_sub + 1] first prediction of each sub-problem
+  const int* sub_gt_off;    // [n_sub + 1]
+  const int* sub_pair_off;  // [n_sub + 1] first entry of the sub-problem's row-major [P, G] pair table
+  const float* ov;          // mode 0: [pairs] IoU (fp32, as the reference stores it)
+  const double* rt;         // mode 1: [pairs, 2] degree, shift (fp64)
+  const int* order;         // [pairs] candidate order of every row (indices into the sub-problem's ground truths)
+  const int* n_cand;        // [n_pred] candidates of a row (mode 0: after the score_threshold cut)
+  const int* pred_cls;      // [n_pred]
+  const int* gt_cls;        // [n_gt]
+  const double* thr_a; int n_a;  // mode 0: IoU thresholds; mode 1: degree thresholds
+  const double* thr_b; int n_b;  // mode 1: shift thresholds (mode 0: n_b = 1, unused)
+  int* gt_match;            // [n_a * n_b, n_gt]   index of the matched prediction within the sub-problem, or -1
+  int* pred_match;          // [n_a * n_b, n_pred]
+  int n_sub, n_pred, n_gt, mode;
+};
+
+__global__ void __launch_bounds__(128) match_kernel(MatchP p) {
+  const long long t = blockIdx.x * (long long)blockDim.x + threadIdx.x;
+  const int n_thr = p.n_a * p.n_b;
+  if (t >= (long long)p.n_sub * n_thr) return;
+  const int sub = (int)(t / n_thr), c = (int)(t % n_thr), ia = c / p.n_b, ib = c % p.n_b;
+  const int p0 = p.sub_pred_off[sub], P = p.sub_pred_off[sub + 1] - p0;
+  const int g0 = p.sub_gt_off[sub], G = p.sub_gt_off[sub + 1] - g0;
+  const int q0 = p.sub_pair_off[sub];
+  int* gm = p.gt_match + (size_t)c * p.n_gt + g0;
+  int* pm = p.pred_match + (size_t)c * p.n_pred + p0;
+  for (int j = 0; j < G; ++j) gm[j] = -1;
+  for (int i = 0; i < P; ++i) pm[i] = -1;
+  const double ta = p.thr_a[ia], tb = p.mode == 1 ? p.thr_b[ib] : 0.0;
+  for (int i = 0; i < P; ++i) {
+    const int nc = p.n_cand[p0 + i];
+    for (int r = 0; r < nc; ++r) {
+      const int j = p.order[q0 + i * G + r];
+      if (p.mode == 0) {
+        if (gm[j] > -1) continue;
+        const double iou = (double)p.ov[q0 + i * G + j];
+        if (iou < ta) break;
+        if (p.pred_cls[p0 + i] != p.gt_cls[g0 + j]) continue;
+        if (iou > ta) { gm[j] = i; pm[i] = j; break; }
+      } else {
+        if (gm[j] > -1 || p.pred_cls[p0 + i] != p.gt_cls[g0 + j]) continue;
+        const double* v = p.rt + 2 * (size_t)(q0 + i * G + j);
+        if (v[0] > ta || v[1] > tb) continue;  // NaN compares false, as in numpy: an unclipped acos() NaN passes
+        gm[j] = i; pm[i] = j;
+        break;
+      }
+    }
+  }
 }
 
 }  // namespace catre

@@ -46,6 +46,10 @@ SYMBOLS = {
                                           ctypes.c_int32, ctypes.c_int32, _F, _P]),
     "catre_pair_metrics": (ctypes.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32,
                                           ctypes.c_int32, _F, _F, _P]),
+    "catre_pair_metrics_ex": (ctypes.c_int, [_F, _F, _F, _F, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_uint32, ctypes.c_uint32,
+                                             ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _P]),
+    "catre_match_greedy": (ctypes.c_int, [ctypes.c_int32, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _F,
+                                          _F, _F, _F, ctypes.c_int32, _F, ctypes.c_int32, _F, _F, _P]),
     "catre_train_set_weight": (ctypes.c_int, [_P, ctypes.c_char_p, _F, _P]),
     "catre_train_set_loss_weights": (ctypes.c_int, [_P, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
     "catre_train_step": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P, ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _P]),

@@ -29,10 +29,13 @@ def class_rules(synset_names: Sequence[str]) -> Tuple[int, int, int]:
     return sym, flip, mug
 
 
-def pair_metrics_batch(images: List[Dict[str, np.ndarray]], synset_names: Sequence[str], device: str = "cuda"):
+def pair_metrics_batch(images: List[Dict[str, np.ndarray]], synset_names: Sequence[str], device: str = "cuda",
+                       shift_cm: bool = False):
     """images[k] holds pred_RTs [P,4,4], pred_scales [P,3], pred_cls [P], gt_RTs [G,4,4], gt_scales [G,3], gt_cls [G],
     gt_handle [G] (numpy).  One kernel launch for all P_k x G_k pairs of all images.  Returns per image
-    (overlaps [P,G] fp32, RT_overlaps [P,G,2] fp32) -- the arrays the reference fills at test_utils.py:329-352."""
+    (overlaps [P,G] fp32, RT_overlaps [P,G,2]) -- the arrays the reference fills at test_utils.py:329-352 (shift =
+    |dT| / scale, stored fp32) or, with ``shift_cm``, at test_utils.py:568-578 and 703-710 (compute_3d_matches'
+    overlaps and compute_RT_overlaps' fp64 [degree, |dT| * 100 cm])."""
     if len(synset_names) > 32:
         raise ValueError("class rules are passed as 32-bit masks: at most 32 classes")
     lib = _engine.load_library()
@@ -54,7 +57,7 @@ def pair_metrics_batch(images: List[Dict[str, np.ndarray]], synset_names: Sequen
         return torch.from_numpy(np.ascontiguousarray(arr)).to(device)
 
     out_iou = torch.empty((max(n_pairs, 1),), dtype=torch.float32, device=device)
-    out_rt = torch.empty((max(n_pairs, 1), 2), dtype=torch.float32, device=device)
+    out_rt = torch.empty((max(n_pairs, 1), 2), dtype=torch.float64 if shift_cm else torch.float32, device=device)
     if n_pairs:
         t = dict(pred_RT=cat("pred_RTs", (16,), np.float64), pred_scale=cat("pred_scales", (3,), np.float64),
                  pred_cls=cat("pred_cls", (), np.int32), gt_RT=cat("gt_RTs", (16,), np.float64),
@@ -64,10 +67,11 @@ def pair_metrics_batch(images: List[Dict[str, np.ndarray]], synset_names: Sequen
         pair_g = torch.from_numpy(np.concatenate(gg).astype(np.int32)).to(device)
         sym, flip, mug = class_rules(synset_names)
         stream = ctypes.c_void_p(torch.cuda.current_stream(out_iou.device).cuda_stream)
-        rc = lib.catre_pair_metrics(t["pred_RT"].data_ptr(), t["pred_scale"].data_ptr(), t["pred_cls"].data_ptr(),
-                                    t["gt_RT"].data_ptr(), t["gt_scale"].data_ptr(), t["gt_cls"].data_ptr(),
-                                    t["gt_handle"].data_ptr(), pair_p.data_ptr(), pair_g.data_ptr(), n_pairs, sym, flip, mug,
-                                    out_iou.data_ptr(), out_rt.data_ptr(), stream)
+        rc = lib.catre_pair_metrics_ex(t["pred_RT"].data_ptr(), t["pred_scale"].data_ptr(), t["pred_cls"].data_ptr(),
+                                       t["gt_RT"].data_ptr(), t["gt_scale"].data_ptr(), t["gt_cls"].data_ptr(),
+                                       t["gt_handle"].data_ptr(), pair_p.data_ptr(), pair_g.data_ptr(), n_pairs, sym, flip, mug,
+                                       1 if shift_cm else 0, out_iou.data_ptr(), None if shift_cm else out_rt.data_ptr(),
+                                       out_rt.data_ptr() if shift_cm else None, stream)
         if rc != 0:
             raise _engine.CatreError(f"catre_pair_metrics failed ({rc}): {lib.catre_last_error(None).decode()}")
     iou_h, rt_h = out_iou.cpu().numpy(), out_rt.cpu().numpy()

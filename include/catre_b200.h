@@ -165,6 +165,33 @@ int catre_pair_metrics(const double* pred_RT, const double* pred_scale, const in
                        const int32_t* pair_gt, int32_t n_pairs, uint32_t sym_class_mask, uint32_t flip_class_mask,
                        int32_t mug_class, float* iou, float* deg_shift, void* stream);
 
+/* The same pair kernel with the shift definition as an argument and an optional fp64 output:
+ *   shift_mode 0: |T1 - T2| / cbrt(det(gt_RT[:3,:3]))  (compute_combination_RT_degree_cm_symmetry, test_utils.py:275)
+ *   shift_mode 1: |T1 - T2| * 100 [cm]                 (compute_RT_degree_cm_symmetry, test_utils.py:619-690) -- with
+ *     deg_shift64 [n_pairs, 2] this fills the overlaps array of compute_RT_overlaps (test_utils.py:692-712, fp64) for the
+ *     metric the NOCS evaluator actually calls: compute_independent_mAP (core/catre/engine/catre_custom_evaluator.py:254).
+ * deg_shift (fp32) or deg_shift64 may be NULL, not both. */
+int catre_pair_metrics_ex(const double* pred_RT, const double* pred_scale, const int32_t* pred_cls, const double* gt_RT,
+                          const double* gt_scale, const int32_t* gt_cls, const int32_t* gt_handle, const int32_t* pair_pred,
+                          const int32_t* pair_gt, int32_t n_pairs, uint32_t sym_class_mask, uint32_t flip_class_mask,
+                          int32_t mug_class, int32_t shift_mode, float* iou, float* deg_shift, double* deg_shift64, void* stream);
+
+/* Greedy prediction <-> ground-truth matching for many (image, class) sub-problems and all thresholds in one launch
+ * (one thread per sub-problem and threshold combination).
+ *   mode 0 replaces the matching loops of compute_3d_matches           (test_utils.py:586-614): thr_a = IoU thresholds;
+ *   mode 1 replaces the loops of compute_match_from_degree_cm          (test_utils.py:734-755): thr_a = degree, thr_b = shift.
+ * Sub-problem k owns predictions [sub_pred_off[k], sub_pred_off[k+1]) (in score order), ground truths
+ * [sub_gt_off[k], ..) and the row-major [P_k, G_k] pair table starting at sub_pair_off[k] in `iou` (mode 0, fp32) or
+ * `deg_shift64` (mode 1, [.., 2] fp64).  order[pair] = the candidate order of each row (indices within the sub-problem;
+ * numpy's argsort of the row, supplied by the caller because the reference's tie order is numpy's), n_cand[pred] = how
+ * many of them are candidates.  Outputs: gt_match [n_a * n_b, n_gt] and pred_match [n_a * n_b, n_pred], the matched
+ * index within the sub-problem or -1.  All pointers are device pointers. */
+int catre_match_greedy(int32_t mode, const int32_t* sub_pred_off, const int32_t* sub_gt_off, const int32_t* sub_pair_off,
+                       int32_t n_sub, int32_t n_pred, int32_t n_gt, const float* iou, const double* deg_shift64,
+                       const int32_t* order, const int32_t* n_cand, const int32_t* pred_cls, const int32_t* gt_cls,
+                       const double* thr_a, int32_t n_a, const double* thr_b, int32_t n_b, int32_t* gt_match,
+                       int32_t* pred_match, void* stream);
+
 /* ---- Training step --------------------------------------------------------------------
  * Replaces one refinement iteration of the reference's training loop (core/catre/engine/engine.py:293-352 without the
  * optimiser): CATRE_disR_shared.forward(..., do_loss=True) (CATRE_disR_shared.py:40-165), catre_loss with the shipped
