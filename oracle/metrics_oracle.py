@@ -113,3 +113,72 @@ def greedy_matches(overlaps, rt, pred_cls, gt_cls, iou_thresholds, degree_thresh
                         pred_matches[d, t, s, i] = j
                         break
     return gt_matches, pred_matches
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# The chain the NOCS evaluator actually calls: compute_independent_mAP (test_utils.py:523-926).  Pinned by
+# tests/test_nocs_map.py against tests/golden/golden_mAP.npz (made by the unmodified reference functions,
+# tests/golden/make_golden_mAP.py).
+# ---------------------------------------------------------------------------------------------------------------
+def degree_cm_independent(RT_1, RT_2, class_id: int, handle_visibility, synset_names: Sequence[str]) -> np.ndarray:
+    """compute_RT_degree_cm_symmetry (test_utils.py:619-690) -> [theta in degrees, |T1 - T2| * 100]: the same rotation
+    rules as degree_cm, the translation error in centimetres instead of object-scale units."""
+    theta = degree_cm(RT_1, RT_2, 1.0, class_id, handle_visibility, synset_names)[0]
+    return np.array([theta, np.linalg.norm(RT_1[:3, 3] - RT_2[:3, 3]) * 100])
+
+
+class OracleBackend:
+    """The two device stages of catre_b200.nocs_map on the CPU, as plain loops: the per-pair tables
+    (compute_3d_iou_new fp32, compute_RT_degree_cm_symmetry fp64) and the two greedy matchers with the candidate
+    order supplied by the caller -- the same contract as nocs_map.CudaBackend."""
+
+    def pair_tables(self, ims, synset_names):
+        out = []
+        with np.errstate(invalid="ignore"):
+            for im in ims:
+                P, G = len(im["pred_cls"]), len(im["gt_cls"])
+                ov = np.zeros((P, G), dtype=np.float32)
+                rt = np.zeros((P, G, 2), dtype=np.float64)
+                for i in range(P):
+                    for j in range(G):
+                        ov[i, j] = iou_3d(im["pred_RTs"][i], im["gt_RTs"][j], im["pred_scales"][i], im["gt_scales"][j],
+                                          im["gt_handle"][j], synset_names[im["pred_cls"][i]], synset_names[im["gt_cls"][j]])
+                        rt[i, j] = degree_cm_independent(im["pred_RTs"][i], im["gt_RTs"][j], im["gt_cls"][j], im["gt_handle"][j],
+                                                         synset_names)
+                out.append((ov, rt))
+        return out
+
+    def match(self, mode, pred_off, gt_off, pair_off, table, order, n_cand, pred_cls, gt_cls, thr_a, thr_b):
+        n_sub, n_pred, n_gt = len(pred_off) - 1, int(pred_off[-1]), int(gt_off[-1])
+        n_b = max(1, len(thr_b))
+        gt_m = -np.ones((len(thr_a) * n_b, n_gt), dtype=np.int32)
+        pred_m = -np.ones((len(thr_a) * n_b, n_pred), dtype=np.int32)
+        for k in range(n_sub):
+            p0, P, g0, G, q0 = pred_off[k], pred_off[k + 1] - pred_off[k], gt_off[k], gt_off[k + 1] - gt_off[k], pair_off[k]
+            for ia, ta in enumerate(thr_a):
+                for ib in range(n_b):
+                    c = ia * n_b + ib
+                    gm, pm = gt_m[c, g0:g0 + G], pred_m[c, p0:p0 + P]
+                    for i in range(P):
+                        for r in range(int(n_cand[p0 + i])):
+                            j = int(order[q0 + i * G + r])
+                            if mode == 0:  # compute_3d_matches, test_utils.py:597-612
+                                if gm[j] > -1:
+                                    continue
+                                iou = table[q0 + i * G + j]
+                                if iou < ta:
+                                    break
+                                if pred_cls[p0 + i] != gt_cls[g0 + j]:
+                                    continue
+                                if iou > ta:
+                                    gm[j], pm[i] = i, j
+                                    break
+                            else:          # compute_match_from_degree_cm, test_utils.py:744-755
+                                if gm[j] > -1 or pred_cls[p0 + i] != gt_cls[g0 + j]:
+                                    continue
+                                v = table[q0 + i * G + j]
+                                if v[0] > ta or v[1] > thr_b[ib]:
+                                    continue
+                                gm[j], pm[i] = i, j
+                                break
+        return gt_m, pred_m
