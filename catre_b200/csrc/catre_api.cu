@@ -1023,7 +1023,7 @@ int catre_refine_table(catre_engine* e, const float* pcl, const float* prior_tab
 
 static int refine_host_impl(catre_engine* e, const float* pcl, const float* prior, const int32_t* prior_cls, int32_t n_cls,
                             const float* init_pose, const float* init_scale, const float* K, int32_t B, int32_t n_iter,
-                            float* out_poses, float* out_scales, void* stream) {
+                            float* out_poses, float* out_scales, void* stream, float* packed_dev = nullptr) {
   int rc = check_ready(e, B);
   if (rc) return rc;
   if (n_iter < 0 || n_iter > catre_engine::kMaxHostIter)
@@ -1054,6 +1054,12 @@ static int refine_host_impl(catre_engine* e, const float* pcl, const float* prio
                      e->st_oposes, e->st_oscales, s);
     if (rc) return rc;
     launches += e->launches;
+    if (packed_dev) {  // the final poses of this chunk, packed for the multi-GPU all-gather, stay on the device
+      launch_pdl(pack_poses_kernel, dim3((unsigned)((Bc * 15 + 255) / 256)), dim3(256), (size_t)0, s, (const float*)e->st_oposes,
+                 (const float*)e->st_oscales, (int)Bc, (int)n_iter, packed_dev + (size_t)b0 * 15);
+      if ((rc = check_launch(e, "pack_poses"))) return rc;
+      ++launches;
+    }
     if (Bc == B) {  // single chunk: the staging layout [n_iter+1, B, .] is the output layout
       CU_TRY(e, cudaMemcpyAsync(out_poses, e->st_oposes, (size_t)(n_iter + 1) * B * 12 * sizeof(float), cudaMemcpyDeviceToHost, s));
       CU_TRY(e, cudaMemcpyAsync(out_scales, e->st_oscales, (size_t)(n_iter + 1) * B * 3 * sizeof(float), cudaMemcpyDeviceToHost, s));
@@ -1074,6 +1080,22 @@ static int refine_host_impl(catre_engine* e, const float* pcl, const float* prio
 int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, const float* init_pose, const float* init_scale,
                       const float* K, int32_t B, int32_t n_iter, float* out_poses, float* out_scales, void* stream) {
   return refine_host_impl(e, pcl, prior, nullptr, 0, init_pose, init_scale, K, B, n_iter, out_poses, out_scales, stream);
+}
+
+int catre_refine_host_packed(catre_engine* e, const float* pcl, const float* prior, const float* init_pose, const float* init_scale,
+                             const float* K, int32_t B, int32_t n_iter, float* out_poses, float* out_scales, float* packed_dev,
+                             void* stream) {
+  if (e && !packed_dev && B > 0) return fail(e, CATRE_ERR_INVALID_ARG, "catre_refine_host_packed: null packed_dev");
+  return refine_host_impl(e, pcl, prior, nullptr, 0, init_pose, init_scale, K, B, n_iter, out_poses, out_scales, stream, packed_dev);
+}
+
+int catre_pack_poses(const float* poses, const float* scales, int32_t B, int32_t iter, float* packed, void* stream) {
+  if (B == 0) return CATRE_OK;
+  if (!poses || !scales || !packed || B < 0 || iter < 0) return fail(nullptr, CATRE_ERR_INVALID_ARG, "catre_pack_poses: bad argument");
+  launch_pdl(pack_poses_kernel, dim3((unsigned)((B * 15 + 255) / 256)), dim3(256), (size_t)0, (cudaStream_t)stream, poses, scales, (int)B,
+             (int)iter, packed);
+  CU_TRY(nullptr, cudaGetLastError());
+  return CATRE_OK;
 }
 
 int catre_refine_table_host(catre_engine* e, const float* pcl, const float* prior_table, const int32_t* prior_cls, int32_t n_cls,

@@ -122,6 +122,17 @@ __global__ void update_points_kernel(const float* __restrict__ pcl, const float*
   o[0] = o0; o[1] = o1; o[2] = o2;
 }
 
+// [K+1, B, 12] poses + [K+1, B, 3] scales -> packed [B, 15] (R|t row-major 12, then s 3) of iteration `it`: the buffer one
+// all-gather moves between the GPUs (replaces the pickled-object gather of catre_custom_evaluator.py:202-203)
+__global__ void pack_poses_kernel(const float* __restrict__ poses, const float* __restrict__ scales, int B, int it,
+                                  float* __restrict__ packed) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= B * 15) return;
+  const int b = i / 15, c = i % 15;
+  packed[i] = c < 12 ? poses[((size_t)it * B + b) * 12 + c] : scales[((size_t)it * B + b) * 3 + (c - 12)];
+}
+
 // forward_once entry: x and tfd_kps arrive already transformed; interleave them into the q layout
 __global__ void gather_points_kernel(const float* __restrict__ x_pm, const float* __restrict__ kps_pm,
                                      float* __restrict__ q, int B, int N, int* __restrict__ gmax, long long n_keys) {

@@ -37,6 +37,8 @@ SYMBOLS = {
     "catre_forward_once": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, _F, _F, _P]),
     "catre_refine": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
     "catre_refine_host": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
+    "catre_refine_host_packed": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _P]),
+    "catre_pack_poses": (ctypes.c_int, [_F, _F, ctypes.c_int32, ctypes.c_int32, _F, _P]),
     "catre_refine_table": (ctypes.c_int, [_P, _F, _F, _F, ctypes.c_int32, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
     "catre_refine_table_host": (ctypes.c_int, [_P, _F, _F, _F, ctypes.c_int32, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, _F, _F, _P]),
     "catre_cloud_scratch_bytes": (ctypes.c_size_t, [ctypes.c_int32, ctypes.c_int32, ctypes.c_int32]),
@@ -203,8 +205,22 @@ class Engine:
                                           n_iter, _ptr(poses), _ptr(scales), self._stream()), "catre_refine")
         return poses, scales
 
-    def refine_host(self, pcl, prior, init_pose, init_scale, K, n_iter: int, out=None):
-        """Host tensors in (pinned for async copies), host tensors out; copies are inside the call."""
+    def pack_poses(self, poses, scales, it: int, out=None):
+        """poses [K+1,B,3,4], scales [K+1,B,3] (device) -> packed [B,15] of iteration `it` (one kernel; the all-gather operand)."""
+        B = poses.shape[1]
+        if not poses.is_cuda or not scales.is_cuda or not poses.is_contiguous() or not scales.is_contiguous():
+            raise CatreError("pack_poses: contiguous CUDA tensors expected")
+        if out is None:
+            out = torch.empty((B, 15), dtype=torch.float32, device=poses.device)
+        rc = self.lib.catre_pack_poses(_ptr(poses), _ptr(scales), B, int(it), _ptr(out), self._stream())
+        if rc != 0:
+            raise CatreError(f"catre_pack_poses failed ({rc}): {self.lib.catre_last_error(None).decode()}")
+        return out
+
+    def refine_host(self, pcl, prior, init_pose, init_scale, K, n_iter: int, out=None, packed_dev=None):
+        """Host tensors in (pinned for async copies), host tensors out; copies are inside the call.  With ``packed_dev``
+        (a CUDA [B,15] fp32 tensor) the last iteration's packed poses additionally stay on the device for the multi-GPU
+        all-gather (catre_refine_host_packed)."""
         B, N = pcl.shape[0], self.n_pts
         for name, t, shp in (("pcl", pcl, (B, N, 3)), ("prior", prior, (B, N, 3)), ("init_pose", init_pose, (B, 3, 4)),
                              ("init_scale", init_scale, (B, 3)), ("K", K, (B, 3, 3))):
@@ -215,6 +231,13 @@ class Engine:
             scales = torch.empty((n_iter + 1, B, 3), dtype=torch.float32).pin_memory()
         else:
             poses, scales = out
+        if packed_dev is not None:
+            if not packed_dev.is_cuda or packed_dev.dtype != torch.float32 or tuple(packed_dev.shape) != (B, 15) or not packed_dev.is_contiguous():
+                raise CatreError(f"packed_dev: expected a contiguous CUDA float32 tensor of shape ({B}, 15)")
+            self._check(self.lib.catre_refine_host_packed(self._h, _ptr(pcl), _ptr(prior), _ptr(init_pose), _ptr(init_scale), _ptr(K),
+                                                          B, n_iter, _ptr(poses), _ptr(scales), _ptr(packed_dev), self._stream()),
+                        "catre_refine_host_packed")
+            return poses, scales
         self._check(self.lib.catre_refine_host(self._h, _ptr(pcl), _ptr(prior), _ptr(init_pose), _ptr(init_scale), _ptr(K),
                                                B, n_iter, _ptr(poses), _ptr(scales), self._stream()), "catre_refine_host")
         return poses, scales

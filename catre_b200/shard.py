@@ -54,6 +54,14 @@ def gather_poses(poses: torch.Tensor, scales: torch.Tensor, total: int,
     return unpack_poses(full)
 
 
+def gather_packed(local: torch.Tensor, out: torch.Tensor, group: Optional[dist.ProcessGroup] = None) -> torch.Tensor:
+    """ONE collective and nothing else on the stream: ``local`` [per, 15] (the engine's packed final poses of this rank's
+    contiguous slice, catre_pack_poses / catre_refine_host_packed) -> ``out`` [world * per, 15] in object order (rank-major =
+    slice order).  Both buffers are preallocated by the caller; a short last slice is padded by the caller's buffer."""
+    dist.all_gather_into_tensor(out, local, group=group)
+    return out
+
+
 def world_size() -> int:
     return dist.get_world_size() if dist.is_available() and dist.is_initialized() else 1
 

@@ -111,6 +111,18 @@ int catre_refine_host(catre_engine* e, const float* pcl, const float* prior, con
                       const float* init_scale, const float* K, int32_t B, int32_t n_iter, float* out_poses,
                       float* out_scales, void* stream);
 
+/* Multi-GPU result collection: the reference gathers pickled Python lists of per-object dicts
+ * (core/catre/engine/catre_custom_evaluator.py:200-203, detectron2 all_gather).  Here a rank's final poses are packed on
+ * the device as [B, 15] fp32 (R|t row-major 12, then scale 3) -- the one buffer a single ncclAllGather on the launching
+ * stream moves (catre_b200/shard.py).
+ *   catre_pack_poses:          poses [n_iter+1, B, 3, 4], scales [n_iter+1, B, 3] (device) -> packed [B, 15] of iteration `iter`.
+ *   catre_refine_host_packed:  catre_refine_host that additionally leaves the LAST iteration's packed poses in the caller's
+ *                              device buffer packed_dev [B, 15], so the end-to-end path needs no re-upload before the gather. */
+int catre_pack_poses(const float* poses, const float* scales, int32_t B, int32_t iter, float* packed, void* stream);
+int catre_refine_host_packed(catre_engine* e, const float* pcl, const float* prior, const float* init_pose,
+                             const float* init_scale, const float* K, int32_t B, int32_t n_iter, float* out_poses,
+                             float* out_scales, float* packed_dev, void* stream);
+
 /* catre_refine with the priors given as a category table instead of one copy per object: object b uses
  * prior_table[prior_cls[b]].  Replaces the same K-loop; the table is what get_normed_kps builds once per
  * dataset (core/catre/engine/engine_utils.py:17-24: batch["obj_kps"] = the category's mean shape from

@@ -317,3 +317,18 @@ def test_result_is_independent_of_launch_size(weights, prec):
     for mb in (64, 5):
         got = run_refine(get_engine(weights, 1024, prec, max_batch=mb), b, 2)
         assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), (prec, mb)
+
+
+def test_packed_final_poses_for_the_all_gather(weights):
+    """catre_pack_poses / catre_refine_host_packed: the [B, 15] buffer one all-gather moves between the GPUs equals the last
+    iteration of the ordinary outputs, from the device entry and from the (chunked) host entry."""
+    b = synth.make_batch(7, 1024, seed=81)
+    eng = get_engine(weights, 1024, "f16x3", max_batch=5)  # 7 objects -> two chunks
+    d = b.to("cuda")
+    p, s = eng.refine(d.pcl, d.prior, d.init_pose, d.init_scale, d.K, 3)
+    want = torch.cat((p[3].reshape(7, 12), s[3]), dim=1)
+    assert torch.equal(eng.pack_poses(p, s, 3), want)
+    packed = torch.zeros(7, 15, device="cuda")
+    ph, sh = eng.refine_host(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, 3, packed_dev=packed)
+    torch.cuda.synchronize()
+    assert torch.equal(packed, want) and torch.equal(ph, p.cpu()) and torch.equal(sh, s.cpu())

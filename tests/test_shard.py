@@ -36,6 +36,12 @@ def _worker(rank, world, port, total, k1, q):
     lo, hi = shard.shard_bounds(total, world, rank)
     fp, fs = shard.gather_poses(poses[:, lo:hi].contiguous(), scales[:, lo:hi].contiguous(), total)
     ok = bool(torch.equal(fp, poses) and torch.equal(fs, scales))
+    # the bench's form: the engine's packed final poses [per, 15] of each rank's slice, ONE collective into a preallocated buffer
+    per = shard.shard_size(total, world)
+    local = torch.zeros(per, 15)
+    local[: hi - lo] = shard.pack_poses(poses[-1:, lo:hi], scales[-1:, lo:hi])[0]
+    out = shard.gather_packed(local, torch.empty(world * per, 15))
+    ok &= bool(torch.equal(out[:total], shard.pack_poses(poses[-1:], scales[-1:])[0]))
     q.put((rank, ok))
     dist.destroy_process_group()
 
