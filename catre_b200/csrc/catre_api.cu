@@ -119,6 +119,9 @@ struct catre_engine {
   float *q = nullptr, *h64a = nullptr, *h64b = nullptr, *h128 = nullptr, *h512 = nullptr, *a0 = nullptr, *a1 = nullptr;
   int *gmax_all = nullptr, *gmax_stn = nullptr, *gmax_fstn = nullptr, *gmax_g = nullptr, *gmax_pf = nullptr;
   float *ts0 = nullptr, *t3 = nullptr, *t64 = nullptr, *cset = nullptr;
+  float *fc512 = nullptr, *fc256 = nullptr;  // fp32 intermediates of the tiled FC path (large batches)
+  int fct_min_rows = 1 << 30;                // sets from which ALL FC layers run as tiled GEMMs (measured slower: off)
+  int fct_fc3_min_rows = 16;                 // sets from which fstn.fc3 (256 -> 4096, 62 % of the fstn chain) leaves the chain
   // fused FC chains (fc_chain.cuh): weights packed [8 ranks][K][C/8] fp32; [0] = stn, [1] = fstn
   float *fcc_fc1[2] = {nullptr, nullptr}, *fcc_fc2[2] = {nullptr, nullptr}, *fcc_fc3[2] = {nullptr, nullptr};
   float *fcc_cset = nullptr, *fcc_ts0 = nullptr;
@@ -349,10 +352,61 @@ int run_chain(catre_engine* e, cudaStream_t s, int grp, const FccProblem& p0, co
   return 0;
 }
 
+// one FC layer as a tiled GEMM in the chain's summation order (large row counts; bit-identical to the chain)
+int run_fct(catre_engine* e, cudaStream_t s, int grp, const int* keys, long long lda_keys, const float* a32, int lda32, const float* w,
+            const float* bias, int rows, int C, int K, int relu, float* out32, unsigned short* out_hi, unsigned short* out_lo) {
+  FctP p{};
+  p.keys = keys; p.lda_keys = lda_keys; p.a32 = a32; p.lda32 = lda32; p.w = w; p.ldw = K; p.bias = bias;
+  p.rows = rows; p.C = C; p.K = K; p.relu = relu; p.out32 = out32; p.ldo = C; p.out_hi = out_hi; p.out_lo = out_lo;
+  p.out_f16 = e->cfg.precision == CATRE_PREC_F16X3;
+  fct_geometry(K, fcc_nc(C, e->fcc_ranks), &p.KS, &p.per, &p.kc);
+  if (!fct_ok(p)) return fail(e, CATRE_ERR_UNSUPPORTED, "tiled fc: unsupported layer geometry (K=%d C=%d)", K, C);
+  cudaError_t st;
+  {
+    Launch l(e, s, grp);
+    st = fct_launch(p, s);
+  }
+  if (st != cudaSuccess) {
+    cudaGetLastError();
+    return fail(e, CATRE_ERR_CUDA, "launch of tiled fc (%s) failed: %s", kGrpNames[grp], cudaGetErrorString(st));
+  }
+  return 0;
+}
+
 // T-Net FC chain: keys [S,1024] -> 512 -> 256 -> kk (+I)  (pointnets/pointnet.py:32-40, 66-77); which = 0 stn, 1 fstn
 int tnet_fc_chain(catre_engine* e, cudaStream_t s, const int* keys, int S, int which) {
   const std::string pf = which ? "pcl_net.fstn" : "pcl_net.stn";
   const bool tc = e->cfg.precision != CATRE_PREC_FP32_SIMT;
+  if (S >= e->fct_min_rows) {  // large batch: three tiled GEMM launches, same bits as the cluster chain below
+    int rc;
+    if ((rc = run_fct(e, s, G_TNET_FC, keys, 1024, nullptr, 0, W(e, (pf + ".fc1.weight").c_str()), W(e, (pf + ".fc1.bias").c_str()), S, 512,
+                      1024, 1, e->fc512, nullptr, nullptr))) return rc;
+    if ((rc = run_fct(e, s, G_TNET_FC, nullptr, 0, e->fc512, 512, W(e, (pf + ".fc2.weight").c_str()), W(e, (pf + ".fc2.bias").c_str()), S, 256,
+                      512, 1, e->fc256, nullptr, nullptr))) return rc;
+    if (which == 0) {
+      {
+        Launch l(e, s, G_TNET_FC);
+        launch_pdl(fc_small_kernel, dim3((unsigned)((S * 9 + 127) / 128)), dim3(128), (size_t)0, s, (const float*)e->fc256, 256,
+                   W(e, "pcl_net.stn.fc3.weight"), 256, (const float*)e->stn_fc3_bI, S, 9, 256, e->t3);
+      }
+      return check_launch(e, "fc_small");
+    }
+    return run_fct(e, s, G_TNET_FC, nullptr, 0, e->fc256, 256, e->fstn_fc3_wT, e->fstn_fc3_bI, S, 4096, 256, 0, tc ? nullptr : e->t64,
+                   tc ? reinterpret_cast<unsigned short*>(e->t64s.hi) : nullptr, tc ? reinterpret_cast<unsigned short*>(e->t64s.lo) : nullptr);
+  }
+  if (which == 1 && S >= e->fct_fc3_min_rows) {
+    // fstn: fc1 + fc2 in the cluster chain (few columns, long K: needs the in-CTA k-slicing to fill an SM), fc3 as a
+    // tiled GEMM (4096 columns, K = 256: a thousand independent tiles); same bits either way
+    FccProblem p2{};
+    p2.keys = keys; p2.lda = 1024; p2.rows = S; p2.n_layers = 2;
+    p2.L[0] = fcc_layer_desc(e, e->fcc_fc1[1], W(e, "pcl_net.fstn.fc1.bias"), 1024, 512, 1);
+    p2.L[1] = fcc_layer_desc(e, e->fcc_fc2[1], W(e, "pcl_net.fstn.fc2.bias"), 512, 256, 1);
+    p2.out32 = e->fc256;
+    int rc = run_chain(e, s, G_TNET_FC, p2, nullptr);
+    if (rc) return rc;
+    return run_fct(e, s, G_TNET_FC, nullptr, 0, e->fc256, 256, e->fstn_fc3_wT, e->fstn_fc3_bI, S, 4096, 256, 0, tc ? nullptr : e->t64,
+                   tc ? reinterpret_cast<unsigned short*>(e->t64s.hi) : nullptr, tc ? reinterpret_cast<unsigned short*>(e->t64s.lo) : nullptr);
+  }
   FccProblem p{};
   p.keys = keys; p.lda = 1024; p.rows = S; p.n_layers = 3;
   p.L[0] = fcc_layer_desc(e, e->fcc_fc1[which], W(e, (pf + ".fc1.bias").c_str()), 1024, 512, 1);
@@ -466,7 +520,11 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
 
   // ---- the two FC layers over the max-pooled global feature, one launch: cset = W0[:, :1024] . g_set + b0 for every
   //      set (rot layer-0 split) and ts-head layer 0 over the OBSERVED sets' g (row b -> set 2b)
-  {
+  if (S >= e->fct_min_rows) {
+    if ((rc = run_fct(e, s, G_ROT_GFEAT, e->gmax_g, 1024, nullptr, 0, e->rot_w0g, e->rot_b0, S, 512, 1024, 0, e->cset, nullptr, nullptr))) return rc;
+    if ((rc = run_fct(e, s, G_ROT_GFEAT, e->gmax_g, 2048, nullptr, 0, e->ts_w0g, W(e, "ts_head.linears.0.bias"), B, 256, 1024, 0, e->ts0,
+                      nullptr, nullptr))) return rc;
+  } else {
     FccProblem pc{}, pt{};
     pc.keys = e->gmax_g; pc.lda = 1024; pc.rows = S; pc.n_layers = 1;
     pc.L[0] = fcc_layer_desc(e, e->fcc_cset, e->rot_b0, 1024, 512, 0);
@@ -687,6 +745,8 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   e->gmax_fstn = e->gmax_all + S * 1024;
   e->gmax_g = e->gmax_all + S * 2048;
   e->gmax_pf = e->gmax_all + S * 3072;
+  rc |= dalloc(e, &e->fc512, S * 512);
+  rc |= dalloc(e, &e->fc256, S * 256);
   rc |= dalloc(e, &e->ts0, B * 256);
   rc |= dalloc(e, &e->dts, B * 6);
   rc |= dalloc(e, &e->t3, S * 9 + 7);
@@ -711,6 +771,10 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
     // non-portable size where the device can co-schedule it (experiments)
     const char* env = getenv("CATRE_FC_RANKS");
     e->fcc_ranks = (env && atoi(env) == 16) ? fcc_pick_ranks() : 8;
+    const char* env2 = getenv("CATRE_FC_TILED_MIN_ROWS");  // experiments: where the tiled-GEMM FC path takes over (same bits)
+    if (env2 && atoi(env2) > 0) e->fct_min_rows = atoi(env2);
+    const char* env3 = getenv("CATRE_FC3_TILED_MIN_ROWS");
+    if (env3 && atoi(env3) > 0) e->fct_fc3_min_rows = atoi(env3);
   }
   if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||

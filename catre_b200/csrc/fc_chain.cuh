@@ -308,6 +308,138 @@ __global__ void __launch_bounds__(FCC_CTA_THREADS, 1) fc_chain_kernel(const __gr
   }
 }
 
+// =================================================================================================================
+// The same layers as plain tiled GEMMs, for LARGE row counts (from 256 sets on): one launch per layer, 32 x 64 output
+// tiles, every SM busy, each weight element reused for 32 rows instead of 16.  The cluster chain above wins at small
+// row counts (one launch, no global intermediates); at S = 512 its 32 clusters run as two waves of 16 (one cluster needs
+// 8 free SMs inside one GPC) at ~50 % FMA issue, ~4x slower than this.  BIT-IDENTICAL to the chain by construction: every
+// output is accumulated in the chain kernel's own order -- k-slice z = 0 .. KS-1, inside a slice the chunks in ascending
+// order and `per` consecutive k's of each chunk, fmaf by fmaf from 0, then the slices added in order, then the bias --
+// so the host may pick either path per launch without changing a single bit (tests: test_result_is_independent_of_launch_size).
+// =================================================================================================================
+constexpr int FCT_BM = 32, FCT_BN = 64, FCT_THREADS = 128, FCT_BK = 16;
+
+struct FctP {
+  const int* keys; long long lda_keys;  // layer-0 input: ordered-int keys (or null)
+  const float* a32; int lda32;          // later layers: fp32 [rows][K]
+  const float* w; int ldw;              // ORIGINAL layout [C][K] row-major
+  const float* bias;
+  int rows, C, K;
+  int KS, per, kc;                      // the chain's k-slicing of this layer (fcc_kc / KS * NC == 512)
+  int relu;
+  float* out32; int ldo;
+  unsigned short* out_hi; unsigned short* out_lo; int out_f16;
+};
+
+__global__ void __launch_bounds__(FCT_THREADS) fc_tiled_kernel(const FctP p) {
+  __shared__ __align__(16) float As[2][FCT_BK][FCT_BM + 4];
+  __shared__ __align__(16) float Ws[2][FCT_BK][FCT_BN + 4];
+  pdl_wait();
+  const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;  // 16 column quads x 8 row quads
+  const int r0 = blockIdx.y * FCT_BM, c0 = blockIdx.x * FCT_BN;
+  const int n_ch = p.K / p.kc, sub = p.per / FCT_BK;          // per is a multiple of 16 here (fct_ok)
+  const int steps_per_slice = n_ch * sub, n_steps = p.KS * steps_per_slice;
+  // step s -> first k of its 16-wide tile, in the chain's order
+  auto k_of = [&](int s) {
+    const int z = s / steps_per_slice, rem = s % steps_per_slice, ch = rem / sub, q = rem % sub;
+    return ch * p.kc + z * p.per + q * FCT_BK;
+  };
+  // global -> registers: A tile 32 rows x 16 k = 128 float4 (one per thread), W tile 64 cols x 16 k = 256 float4 (two)
+  float4 ra, rw[2];
+  auto load = [&](int s) {
+    const int k0 = k_of(s);
+    {
+      const int row = tid >> 2, kq = (tid & 3) * 4;
+      ra = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (r0 + row < p.rows) {
+        if (p.keys) {
+          const int4 kv = *reinterpret_cast<const int4*>(p.keys + (long long)(r0 + row) * p.lda_keys + k0 + kq);
+          ra = make_float4(key2f(kv.x), key2f(kv.y), key2f(kv.z), key2f(kv.w));
+        } else {
+          ra = *reinterpret_cast<const float4*>(p.a32 + (long long)(r0 + row) * p.lda32 + k0 + kq);
+        }
+      }
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int e = tid + it * FCT_THREADS, col = e >> 2, kq = (e & 3) * 4;
+      rw[it] = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (c0 + col < p.C) rw[it] = *reinterpret_cast<const float4*>(p.w + (long long)(c0 + col) * p.ldw + k0 + kq);
+    }
+  };
+  auto stash = [&](int buf) {
+    {
+      const int row = tid >> 2, kq = (tid & 3) * 4;
+      As[buf][kq + 0][row] = ra.x; As[buf][kq + 1][row] = ra.y; As[buf][kq + 2][row] = ra.z; As[buf][kq + 3][row] = ra.w;
+    }
+#pragma unroll
+    for (int it = 0; it < 2; ++it) {
+      const int e = tid + it * FCT_THREADS, col = e >> 2, kq = (e & 3) * 4;
+      Ws[buf][kq + 0][col] = rw[it].x; Ws[buf][kq + 1][col] = rw[it].y; Ws[buf][kq + 2][col] = rw[it].z; Ws[buf][kq + 3][col] = rw[it].w;
+    }
+  };
+  float acc[4][4], tot[4][4];
+#pragma unroll
+  for (int i = 0; i < 4; ++i)
+#pragma unroll
+    for (int j = 0; j < 4; ++j) { acc[i][j] = 0.f; tot[i][j] = 0.f; }
+  load(0);
+  stash(0);
+  __syncthreads();
+  for (int s = 0; s < n_steps; ++s) {
+    const int buf = s & 1;
+    if (s + 1 < n_steps) load(s + 1);
+#pragma unroll
+    for (int kk = 0; kk < FCT_BK; ++kk) {
+      const float4 a4 = *reinterpret_cast<const float4*>(&As[buf][kk][ty * 4]);
+      const float4 w4 = *reinterpret_cast<const float4*>(&Ws[buf][kk][tx * 4]);
+      const float a[4] = {a4.x, a4.y, a4.z, a4.w}, w[4] = {w4.x, w4.y, w4.z, w4.w};
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], w[j], acc[i][j]);
+    }
+    if ((s + 1) % steps_per_slice == 0) {  // end of k-slice z: the chain adds the slices in order, the first one as is
+      const bool first = (s + 1 == steps_per_slice);
+#pragma unroll
+      for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) { tot[i][j] = first ? acc[i][j] : __fadd_rn(tot[i][j], acc[i][j]); acc[i][j] = 0.f; }
+    }
+    if (s + 1 < n_steps) stash(buf ^ 1);
+    __syncthreads();
+  }
+#pragma unroll
+  for (int i = 0; i < 4; ++i) {
+    const int grow = r0 + ty * 4 + i;
+    if (grow >= p.rows) continue;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int gc = c0 + tx * 4 + j;
+      if (gc >= p.C) continue;
+      float y = __fadd_rn(tot[i][j], __ldg(p.bias + gc));
+      if (p.relu) y = fmaxf(y, 0.f);
+      if (p.out32) p.out32[(size_t)grow * p.ldo + gc] = y;
+      if (p.out_hi) split16(y, p.out_f16 != 0, p.out_hi[(size_t)grow * p.C + gc], p.out_lo[(size_t)grow * p.C + gc]);
+    }
+  }
+}
+
+// the chain's order for a layer whose slices hold ONE k each (stn.fc3: 9 outputs, K = 256, KS = 256, per = 1):
+// out = ((a0 w0 + a1 w1) + a2 w2) + ... + bias with every product rounded on its own (fmaf(a, w, 0) in the chain)
+__global__ void __launch_bounds__(128) fc_small_kernel(const float* __restrict__ a32, int lda32, const float* __restrict__ w, int ldw,
+                                                       const float* __restrict__ bias, int rows, int C, int K, float* __restrict__ out32) {
+  pdl_wait();
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * C) return;
+  const int r = i / C, c = i % C;
+  const float* a = a32 + (size_t)r * lda32;
+  const float* ww = w + (size_t)c * ldw;
+  float s = __fmul_rn(a[0], ww[0]);
+  for (int k = 1; k < K; ++k) s = __fadd_rn(s, __fmul_rn(a[k], ww[k]));
+  out32[(size_t)r * C + c] = __fadd_rn(s, bias[c]);
+}
+
 // ---- host side -----------------------------------------------------------------------------------------------
 // [C][K] row-major -> [ranks][K][NC] (zero-padded columns)
 inline void fcc_pack(const float* w, int C, int K, int NC, int ranks, float* out) {
@@ -370,6 +502,19 @@ inline int fcc_pick_ranks() {
   int n = 0;
   if (cudaOccupancyMaxActiveClusters(&n, kern, &cfg) != cudaSuccess) { cudaGetLastError(); return 8; }
   return n >= 4 ? 16 : 8;
+}
+
+// the chain's k-slicing of a layer of NC columns per CTA (what fc_tiled_kernel must reproduce)
+inline void fct_geometry(int K, int NC, int* KS, int* per, int* kc) {
+  *kc = fcc_kc(K, NC);
+  *KS = (FCC_THREADS / 2) / (NC / 2);
+  *per = *kc / *KS;
+}
+inline bool fct_ok(const FctP& p) { return p.per % FCT_BK == 0 && p.K % p.kc == 0 && p.K % 4 == 0 && p.KS * p.per == p.kc; }
+inline cudaError_t fct_launch(const FctP& p, cudaStream_t s) {
+  if (p.rows < 1) return cudaSuccess;
+  dim3 grid((unsigned)((p.C + FCT_BN - 1) / FCT_BN), (unsigned)((p.rows + FCT_BM - 1) / FCT_BM));
+  return launch_pdl(fc_tiled_kernel, grid, dim3(FCT_THREADS), (size_t)0, s, p);
 }
 
 }  // namespace catre

@@ -185,16 +185,20 @@ __global__ void __launch_bounds__(128) match_kernel(MatchP p) {
   for (int j = 0; j < G; ++j) gm[j] = -1;
   for (int i = 0; i < P; ++i) pm[i] = -1;
   const double ta = p.thr_a[ia], tb = p.mode == 1 ? p.thr_b[ib] : 0.0;
+  // mode 0 compares an fp32 IoU with a Python-float threshold: under NumPy >= 2 (NEP 50; the goldens were made with 2.3) the
+  // Python float is weakly typed and the comparison runs in fp32.  (NumPy 1.x promoted to fp64; the two differ only when an
+  // IoU equals the fp32 rounding of a threshold exactly.)
+  const float taf = (float)ta;
   for (int i = 0; i < P; ++i) {
     const int nc = p.n_cand[p0 + i];
     for (int r = 0; r < nc; ++r) {
       const int j = p.order[q0 + i * G + r];
       if (p.mode == 0) {
         if (gm[j] > -1) continue;
-        const double iou = (double)p.ov[q0 + i * G + j];
-        if (iou < ta) break;
+        const float iou = p.ov[q0 + i * G + j];
+        if (iou < taf) break;
         if (p.pred_cls[p0 + i] != p.gt_cls[g0 + j]) continue;
-        if (iou > ta) { gm[j] = i; pm[i] = j; break; }
+        if (iou > taf) { gm[j] = i; pm[i] = j; break; }
       } else {
         if (gm[j] > -1 || p.pred_cls[p0 + i] != p.gt_cls[g0 + j]) continue;
         const double* v = p.rt + 2 * (size_t)(q0 + i * G + j);
