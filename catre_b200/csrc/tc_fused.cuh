@@ -25,8 +25,10 @@
 
 namespace catre {
 
-constexpr int RF_EW = 16;
+constexpr int RF_EW = 16;                       // epilogue warps of enc_fused_kernel; E0 (GELU) warps of rot_fused_kernel
+constexpr int RF_E1W = 8;                       // rot_fused_kernel: warps that drain D1 (concurrently with the E0 warps)
 constexpr int RF_THREADS = 64 + 32 * RF_EW;
+constexpr int ROT_THREADS = RF_THREADS + 32 * RF_E1W;
 constexpr int RF_SLOT = 32 * 1024;
 constexpr int RF_SLOTS = 3;
 constexpr int RF_U_BYTES = 128 * 1024;
@@ -64,11 +66,12 @@ __device__ __forceinline__ void tmem_ld_wait16(float* v) {
 // Schedule (software-pipelined over the CTA's work items j; half A = layer-0 channels 0..127 = U slabs 0-1,
 // half B = channels 128..255 = slabs 2-3; D0a / D0b = TMEM columns 0..127 / 128..255):
 //   MMA warp      L0(0,A) L0(0,B) | L1(j,A) L0(j+1,A) L1(j,B) L0(j+1,B) | ...
-//   epilogue      E0(0,s0..s3)    | E0(j+1,s0) E1(j,0) E0(j+1,s1) E1(j,1) E0(j+1,s2) E0(j+1,s3) | ...
-// so the GELU work of item j+1 runs underneath the layer-1 MMAs of item j and the CUDA cores never wait for
-// the tensor pipe.  E1(j, c) writes 32 of the item's 64 points per thread straight to global memory (fp32).
+//   E0 warps      E0(0,s0..s3)    | E0(j+1,s0) E0(j+1,s1) E0(j+1,s2) E0(j+1,s3) | ...      (8 warps: D0 -> U)
+//   E1 warps                      |            E1(j)  (whenever D1 of item j is complete) | ...      (8 warps: D1 -> a1T, stats)
+// The two epilogue groups are independent instruction streams: the GELU work of item j+1 runs underneath the layer-1
+// MMAs of item j AND underneath the drain of item j's D1; the only couplings are the TMEM / U barriers.
 template <int NPROD>
-__global__ void __launch_bounds__(RF_THREADS, 1)
+__global__ void __launch_bounds__(ROT_THREADS, 1)
 rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constant__ CUtensorMap pf_lo,
                  const __grid_constant__ CUtensorMap w0_hi, const __grid_constant__ CUtensorMap w0_lo,
                  const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo, const RotFusedP p) {
@@ -93,8 +96,9 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
     prefetch_tmap(&pf_hi); prefetch_tmap(&w0_hi); prefetch_tmap(&w1_hi);
     if (NPROD == 3) { prefetch_tmap(&pf_lo); prefetch_tmap(&w0_lo); prefetch_tmap(&w1_lo); }
     for (int i = 0; i < RF_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    // RF_EW warps write U (E0 group), RF_E1W warps drain D1 (E1 group)
     for (int i = 0; i < 2; ++i) { mbar_init(bar_d0_full + 8 * i, 1); mbar_init(bar_d0_empty + 8 * i, RF_EW); }
-    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RF_EW);
+    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RF_E1W);
     for (int i = 0; i < 4; ++i) mbar_init(bar_u_full + 8 * i, RF_EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -206,117 +210,119 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
     }
   } else {
     // ===================== epilogue warps =====================
-    const int quad = warp & 3, part = (warp - 2) >> 2;  // TMEM lanes 32*quad.., 4 parts per quadrant
+    // Two groups that run CONCURRENTLY: warps 2..17 turn D0 into the layer-1 operand U (E0: GroupNorm affine + GELU +
+    // 16-bit split, CUDA-core heavy: 4 warps per scheduler hide its TMEM / shared-memory latencies), warps 18..25 drain
+    // D1 (E1: bias, GroupNorm-1 partial sums, fp32 stores; mostly waiting, with a back-off so it does not steal issue slots).
+    // Round 1 ran E0 and E1 on the same 16 warps in sequence, so E1(j) -- which has to wait for the layer-1 MMAs of the
+    // slabs E0 has only just written -- stalled the GELU work of item j+1: 26 % of that kernel's samples were epilogue
+    // warps spinning on d1_full / d0_full (profiles/r02_ncu_rot_fused.txt) and the tensor pipe sat at 38 %.
+    const int quad = warp & 3;
     const int lane_row = quad * 32 + lane;
     const uint32_t row_off = (uint32_t)((lane_row >> 3) * 1024 + (lane_row & 7) * 128);
-    // E0(j, s): lane = point row; slab s (layer-0 channels s*64 .. +63), this warp's 16 channels
-    auto E0 = [&](int j, int ks) {
-      const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
-      const int set = (int)(((long long)tile * 128) / p.rows_per_set);
-      const int half = ks >> 1;
-      if ((ks & 1) == 0) {
-        mbar_wait(bar_d0_full + 8 * half, (uint32_t)j & 1);
-        tc_fence_after();
-      }
-      const float* scp = p.gn_scale + (long long)set * 512 + h * 256;
-      const float* shp = p.gn_shift + (long long)set * 512 + h * 256;
-      const int ch0 = ks * 64 + part * 16;
-      float v[16];
-      tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ch0, v);
-      float4 sc4[4], sh4[4];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {  // broadcast loads (same address on every lane), overlapped with the TMEM load
-        sc4[q] = __ldg(reinterpret_cast<const float4*>(scp + ch0) + q);
-        sh4[q] = __ldg(reinterpret_cast<const float4*>(shp + ch0) + q);
-      }
-      tmem_ld_wait16(v);
-      if (ks & 1) {  // this half of D0 is drained: the next item's L0 may overwrite it
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_d0_empty + 8 * half);
-      }
-      uint32_t hi[8], lo[8];
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float g0 = gelu_fast(fmaf(v[4 * q + 0], sc4[q].x, sh4[q].x));
-        const float g1 = gelu_fast(fmaf(v[4 * q + 1], sc4[q].y, sh4[q].y));
-        const float g2 = gelu_fast(fmaf(v[4 * q + 2], sc4[q].z, sh4[q].z));
-        const float g3 = gelu_fast(fmaf(v[4 * q + 3], sc4[q].w, sh4[q].w));
-        split16x2<TcOperand<NPROD>::F16>(g0, g1, hi[2 * q], lo[2 * q]);
-        split16x2<TcOperand<NPROD>::F16>(g2, g3, hi[2 * q + 1], lo[2 * q + 1]);
-      }
-      // two 16-byte chunks (8 channels each) of this row, 128B-swizzled: chunk' = chunk ^ (row & 7)
-      const uint32_t slab = u_base + ks * 32768 + row_off;
-      const uint32_t c0 = (uint32_t)(part * 2), sw = (uint32_t)(lane_row & 7);
-      st_shared_v4(slab + (((c0 + 0) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
-      st_shared_v4(slab + (((c0 + 1) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
-      if (NPROD == 3) {
-        st_shared_v4(slab + 16384 + (((c0 + 0) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
-        st_shared_v4(slab + 16384 + (((c0 + 1) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
-      }
-      fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-      __syncwarp();
-      if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
-    };
-    // E1(j): lane = output channel of m-tile mt; this warp's 64 points.  The fp32 values (+ bias) go straight from
-    // the registers to a1T [B][P/4][512][4]: 4 consecutive points of a channel are one 16-byte store, and the 32
-    // lanes (consecutive channels) of a warp write 512 contiguous bytes per instruction.  Keeping this activation
-    // in fp32 matters for parity: rounding it to fp16 was the largest single error of the tensor-core path
-    // (up to 3e-5 on R).
-    // Split in two halves of 32 points (E1(j, 0) and E1(j, 1)) that the schedule below places between E0 slabs,
-    // so each 64 KB burst of stores drains underneath the next slab's GELU work.
-    float e1_s = 0.f, e1_ss = 0.f;
-    auto E1 = [&](int j, int c) {
-      const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
-      const long long row0 = (long long)tile * 128;
-      if (c == 0) {
-        mbar_wait(bar_d1_full, (uint32_t)j & 1);
-        tc_fence_after();
-        e1_s = 0.f; e1_ss = 0.f;
-      }
-      const int mt = part >> 1, ph = part & 1;
-      const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
-      const long long r64 = row0 + ph * 64;          // first global row of this warp's 64 points
-      const float add = p.bias1[ch];
-      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128 + ph * 64);
-      float4* dst = reinterpret_cast<float4*>(p.a1t) + ((r64 >> 2) + c * 8) * 512 + ch;
-      float x[32];
-      tmem_ld32(taddr + c * 32, x);
-      tmem_ld_wait32(x);
-      if (c == 1) {  // D1 drained: the next item's layer-1 MMAs may overwrite it
-        tc_fence_before();
-        __syncwarp();
-        if (lane == 0) mbar_arrive(bar_d1_empty);
-      }
-      float s = e1_s, ss = e1_ss;
-#pragma unroll
-      for (int q = 0; q < 32; q += 2) {
-        x[q] += add; x[q + 1] += add;
-        s += x[q]; s += x[q + 1];
-        ss = fmaf(x[q], x[q], ss); ss = fmaf(x[q + 1], x[q + 1], ss);
-      }
-#pragma unroll
-      for (int q = 0; q < 8; ++q)  // streaming stores: a1T is read once, by the next kernel; keep the weights in L2
-        __stcs(dst + q * 512, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
-      if (c == 0) { e1_s = s; e1_ss = ss; return; }
-      s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-      s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-      s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-      if ((lane & 7) == 0) {
-        const long long o = ((r64 >> 6) * 64 + (ch >> 3)) * 2;
-        p.stats[o] = s;
-        p.stats[o + 1] = ss;
-      }
-    };
-    if (n_items > 0) {
-      E0(0, 0); E0(0, 1); E0(0, 2); E0(0, 3);
+    if (warp < 2 + RF_EW) {
+      const int part = (warp - 2) >> 2;  // 4 warps per TMEM lane quadrant: 16 of a slab's 64 channels each
+      // E0(j, s): lane = point row; slab s (layer-0 channels s*64 .. +63), this warp's 16 channels
       for (int j = 0; j < n_items; ++j) {
-        const bool more = j + 1 < n_items;
-        if (more) E0(j + 1, 0);
-        E1(j, 0);
-        if (more) E0(j + 1, 1);
-        E1(j, 1);
-        if (more) { E0(j + 1, 2); E0(j + 1, 3); }
+        const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
+        const int set = (int)(((long long)tile * 128) / p.rows_per_set);
+        const float* scp = p.gn_scale + (long long)set * 512 + h * 256;
+        const float* shp = p.gn_shift + (long long)set * 512 + h * 256;
+#pragma unroll 1
+        for (int ks = 0; ks < 4; ++ks) {
+          const int half = ks >> 1;
+          if ((ks & 1) == 0) {
+            mbar_wait(bar_d0_full + 8 * half, (uint32_t)j & 1);
+            tc_fence_after();
+          }
+          {
+            const int ch0 = ks * 64 + part * 16;
+            float v[16];
+            tmem_ld16(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)ch0, v);
+            float4 sc4[4], sh4[4];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {  // broadcast loads (same address on every lane), overlapped with the TMEM load
+              sc4[q] = __ldg(reinterpret_cast<const float4*>(scp + ch0) + q);
+              sh4[q] = __ldg(reinterpret_cast<const float4*>(shp + ch0) + q);
+            }
+            tmem_ld_wait16(v);
+            if (ks & 1) {  // this half of D0 is drained: the next item's L0 may overwrite it
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_d0_empty + 8 * half);
+            }
+            uint32_t hi[8], lo[8];
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+              const float g0 = gelu_fast(fmaf(v[4 * q + 0], sc4[q].x, sh4[q].x));
+              const float g1 = gelu_fast(fmaf(v[4 * q + 1], sc4[q].y, sh4[q].y));
+              const float g2 = gelu_fast(fmaf(v[4 * q + 2], sc4[q].z, sh4[q].z));
+              const float g3 = gelu_fast(fmaf(v[4 * q + 3], sc4[q].w, sh4[q].w));
+              split16x2<TcOperand<NPROD>::F16>(g0, g1, hi[2 * q], lo[2 * q]);
+              split16x2<TcOperand<NPROD>::F16>(g2, g3, hi[2 * q + 1], lo[2 * q + 1]);
+            }
+            // two 16-byte chunks (8 channels each) of this row, 128B-swizzled: chunk' = chunk ^ (row & 7)
+            const uint32_t slab = u_base + ks * 32768 + row_off;
+            const uint32_t c0 = (uint32_t)(part * 2), sw = (uint32_t)(lane_row & 7);
+            st_shared_v4(slab + (((c0 + 0) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+            st_shared_v4(slab + (((c0 + 1) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
+            if (NPROD == 3) {
+              st_shared_v4(slab + 16384 + (((c0 + 0) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+              st_shared_v4(slab + 16384 + (((c0 + 1) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
+            }
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
+        }
+      }
+    } else {
+      // E1(j): lane = output channel of m-tile mt; this warp takes all 128 points of the item in four chunks of 32.  The
+      // fp32 values (+ bias) go straight from the registers to a1T [B][P/4][512][4]: 4 consecutive points of a channel are
+      // one 16-byte store, and the 32 lanes (consecutive channels) of a warp write 512 contiguous bytes per instruction.
+      // Keeping this activation in fp32 matters for parity.
+      const int mt = (warp - 2 - RF_EW) >> 2;
+      for (int j = 0; j < n_items; ++j) {
+        const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
+        const long long row0 = (long long)tile * 128;
+        const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
+        const float add = p.bias1[ch];
+        while (!mbar_try_wait(bar_d1_full, (uint32_t)j & 1)) __nanosleep(64);  // idle most of the time: poll politely
+        tc_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128);
+        float s = 0.f, ss = 0.f;
+#pragma unroll 1
+        for (int c = 0; c < 4; ++c) {
+          float x[32];
+          tmem_ld32(taddr + c * 32, x);
+          tmem_ld_wait32(x);
+          if (c == 3) {  // D1 drained: the next item's layer-1 MMAs may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_d1_empty);
+          }
+#pragma unroll
+          for (int q = 0; q < 32; q += 2) {
+            x[q] += add; x[q + 1] += add;
+            s += x[q]; s += x[q + 1];
+            ss = fmaf(x[q], x[q], ss); ss = fmaf(x[q + 1], x[q + 1], ss);
+          }
+          const long long r64 = row0 + (c >> 1) * 64;  // first global row of this 64-point half
+          float4* dst = reinterpret_cast<float4*>(p.a1t) + ((r64 >> 2) + (c & 1) * 8) * 512 + ch;
+#pragma unroll
+          for (int q = 0; q < 8; ++q)  // streaming stores: a1T is read once, by the next kernel; keep the weights in L2
+            __stcs(dst + q * 512, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+          if (c & 1) {  // GroupNorm-1 partial sums per 64 points and 8-channel group
+            s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+            s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+            s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+            if ((lane & 7) == 0) {
+              const long long o = ((r64 >> 6) * 64 + (ch >> 3)) * 2;
+              p.stats[o] = s;
+              p.stats[o + 1] = ss;
+            }
+            s = 0.f; ss = 0.f;
+          }
+        }
       }
     }
   }
@@ -342,7 +348,7 @@ cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo,
   int items = p.tiles * 2;
   int grid = items < num_sms ? items : num_sms;
   if (grid < 1) return cudaSuccess;
-  return launch_pdl(kern, dim3(grid), dim3(RF_THREADS), (size_t)RF_SMEM, s, pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p);
+  return launch_pdl(kern, dim3(grid), dim3(ROT_THREADS), (size_t)RF_SMEM, s, pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p);
 }
 
 
