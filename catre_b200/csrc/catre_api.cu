@@ -91,7 +91,8 @@ const char* kGrpNames[G_NUM] = {
 struct catre_engine {
   catre_cfg cfg{};
   std::string err;
-  int N = 0;          // points per set
+  int N = 0;          // observed points per object (n_obs)
+  int Np = 0;         // prior points per object (n_prior); rows per object P = N + Np
   int maxB = 0;
   bool packed = false;
   std::map<std::string, std::vector<float>> hw;  // host copies of the checkpoint tensors
@@ -280,7 +281,7 @@ template <int BN>
 int tc_split_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& act, const TcPair& w, int K, int C,
                    const float* bias, const TcPair& out, long long R) {
   TcGemmP p{};
-  p.K = K; p.m_tiles = (int)(R / 128); p.n_tiles = C / BN; p.rows_per_set = e->N;
+  p.K = K; p.m_tiles = (int)(R / 128); p.n_tiles = C / BN; p.rows_per_set = e->N; p.rows_per_obj = e->N + e->Np;
   p.bias = bias; p.relu = 1;
   return tc_run<PT_ON_LANES, EPI_SPLIT, BN>(e, s, grp, act.map_hi, act.map_lo, w.map_hi, w.map_lo, p, &out);
 }
@@ -290,7 +291,7 @@ int tc_max_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& w, cons
                  const float* bias, int relu, int* gmax, long long R) {
   TcGemmP p{};
   p.K = K; p.m_tiles = C / 128; p.n_tiles = (int)(R / 256);
-  p.bias = bias; p.relu = relu; p.gmax = gmax; p.C = C; p.rows_per_set = e->N;
+  p.bias = bias; p.relu = relu; p.gmax = gmax; p.C = C; p.rows_per_set = e->N; p.rows_per_obj = e->N + e->Np;
   return tc_run<CH_ON_LANES, EPI_MAX, 256>(e, s, grp, w.map_hi, w.map_lo, act_nb[0], act_nb[1], p);
 }
 
@@ -298,7 +299,7 @@ int tc_max_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& w, cons
 int tc_tnet_trunk(catre_engine* e, cudaStream_t s, int grp, const TcPair& act, const TcPair& w2, const float* b2, const TcPair& w3,
                   const float* b3, int* gmax, long long R) {
   EncFusedP p{};
-  p.tiles = (int)(R / 256); p.rows_per_set = e->N; p.bias2 = b2; p.bias3 = b3; p.gmax = gmax;
+  p.tiles = (int)(R / 256); p.rows_per_set = e->N; p.rows_per_obj = e->N + e->Np; p.bias2 = b2; p.bias3 = b3; p.gmax = gmax;
   cudaError_t st;
   {
     Launch l(e, s, grp);
@@ -319,7 +320,7 @@ int tc_front(catre_engine* e, cudaStream_t s, const float* t3, const char* conv,
   {
     Launch l(e, s, G_FRONT3);
     launch_pdl(e->cfg.precision == CATRE_PREC_F16X3 ? front3_split_kernel<true> : front3_split_kernel<false>, dim3((unsigned)((R + FRONT_PTS - 1) / FRONT_PTS)), dim3(256), (size_t)(0), s, e->q, t3, e->dw.at(c + ".weight"), e->dw.at(c + ".bias"),
-                                                                 e->x64.hi, e->x64.lo, (int)R, e->N);
+                                                                 e->x64.hi, e->x64.lo, (int)R, e->N + e->Np, e->N);
   }
   return check_launch(e, "front3_split");
 }
@@ -430,8 +431,8 @@ int tnet_fc_chain(catre_engine* e, cudaStream_t s, const int* keys, int S, int w
 // One refinement iteration on a chunk of B objects whose points are already in e->q.
 int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, const float* scale_in, const float* K,
               float* pose_out, float* scale_out, const int* prior_cls = nullptr, int n_cls = 0) {
-  const int N = e->N, S = 2 * B, P = 2 * N;
-  const long long R = (long long)S * N;
+  const int N = e->N, S = 2 * B, P = e->N + e->Np;
+  const long long R = (long long)B * P;
   int rc;
   const bool tc = e->cfg.precision != CATRE_PREC_FP32_SIMT;
 
@@ -450,7 +451,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     {
       Launch l(e, s, G_FRONT3);
       launch_pdl(front3_kernel, dim3((unsigned)((R * 16 + 255) / 256)), dim3(256), (size_t)(0), s, e->q, nullptr, W(e, "pcl_net.stn.conv1.weight"),
-                                                                    W(e, "pcl_net.stn.conv1.bias"), e->h64a, R, N);
+                                                                    W(e, "pcl_net.stn.conv1.bias"), e->h64a, R, P, N);
     }
     if ((rc = check_launch(e, "front3"))) return rc;
     GemmP p = gemm_args(e->h64a, 64, W(e, "pcl_net.stn.conv2.weight"), 64, 128, W(e, "pcl_net.stn.conv2.bias"), e->h128,
@@ -458,7 +459,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_STN_CONV2, p))) return rc;
     p = gemm_args(e->h128, 128, W(e, "pcl_net.stn.conv3.weight"), 128, 1024, W(e, "pcl_net.stn.conv3.bias"), nullptr, 0,
                   R, 1);
-    p.gmax = e->gmax_stn; p.rows_per_set = N;
+    p.gmax = e->gmax_stn; p.rows_per_set = N; p.rows_per_obj = P;
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_STN_CONV3_MAX, p))) return rc;
   }
   if ((rc = tnet_fc_chain(e, s, e->gmax_stn, S, 0))) return rc;
@@ -470,7 +471,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     {
       Launch l(e, s, G_FRONT3);
       launch_pdl(front3_kernel, dim3((unsigned)((R * 16 + 255) / 256)), dim3(256), (size_t)(0), s, e->q, e->t3, W(e, "pcl_net.conv1.weight"),
-                                                                    W(e, "pcl_net.conv1.bias"), e->h64a, R, N);
+                                                                    W(e, "pcl_net.conv1.bias"), e->h64a, R, P, N);
     }
     if ((rc = check_launch(e, "front3"))) return rc;
   }
@@ -489,7 +490,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_FSTN_CONV2, p))) return rc;
     p = gemm_args(e->h128, 128, W(e, "pcl_net.fstn.conv3.weight"), 128, 1024, W(e, "pcl_net.fstn.conv3.bias"), nullptr,
                   0, R, 1);
-    p.gmax = e->gmax_fstn; p.rows_per_set = N;
+    p.gmax = e->gmax_fstn; p.rows_per_set = N; p.rows_per_obj = P;
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_FSTN_CONV3_MAX, p))) return rc;
   }
   if ((rc = tnet_fc_chain(e, s, e->gmax_fstn, S, 1))) return rc;
@@ -497,7 +498,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   // ---- E4: feature transform pf = h1 . T64 (per set), trunk conv2-4, global max (pointnet.py:105-116)
   if (tc) {
     TcGemmP p{};
-    p.K = 64; p.m_tiles = (int)(R / 128); p.n_tiles = 1; p.rows_per_set = N; p.nb_per_set = 1;
+    p.K = 64; p.m_tiles = (int)(R / 128); p.n_tiles = 1; p.rows_per_set = N; p.rows_per_obj = P; p.nb_per_set = 1;
     p.gmax = e->gmax_pf; p.C = 64;
     if ((rc = tc_run<PT_ON_LANES, EPI_SPLIT_MAX, 64>(e, s, G_FEAT_TRANSFORM, e->x64.map_hi, e->x64.map_lo, e->t64s.map_hi,
                                                       e->t64s.map_lo, p, &e->pf16))) return rc;
@@ -506,7 +507,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = tc_max_layer(e, s, G_CONV4_MAX, e->tw_conv4, e->a512_nb, 512, 1024, W(e, "pcl_net.conv4.bias"), 0, e->gmax_g, R))) return rc;
   } else {
     GemmP p = gemm_args(e->h64a, 64, e->t64, 64, 64, nullptr, e->h64b, 64, R, 0);
-    p.w_set_stride = 4096; p.rows_per_set = N;  // W[c][k] = T64^T[set][c][k]
+    p.w_set_stride = 4096; p.rows_per_set = N; p.rows_per_obj = P;  // W[c][k] = T64^T[set][c][k]
     p.gmax = e->gmax_pf;
     if ((rc = run_gemm<64, A_PLAIN>(e, s, G_FEAT_TRANSFORM, p))) return rc;
     p = gemm_args(e->h64b, 64, W(e, "pcl_net.conv2.weight"), 64, 128, W(e, "pcl_net.conv2.bias"), e->h128, 128, R, 1);
@@ -514,7 +515,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     p = gemm_args(e->h128, 128, W(e, "pcl_net.conv3.weight"), 128, 512, W(e, "pcl_net.conv3.bias"), e->h512, 512, R, 1);
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV3, p))) return rc;
     p = gemm_args(e->h512, 512, W(e, "pcl_net.conv4.weight"), 512, 1024, W(e, "pcl_net.conv4.bias"), nullptr, 0, R, 0);
-    p.gmax = e->gmax_g; p.rows_per_set = N;
+    p.gmax = e->gmax_g; p.rows_per_set = N; p.rows_per_obj = P;
     if ((rc = run_gemm<128, A_PLAIN>(e, s, G_CONV4_MAX, p))) return rc;
   }
 
@@ -562,7 +563,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
   if (tc) {
     // pass 1: GroupNorm statistics of a0 = W0p . pf + cset (nothing stored; K = 64 makes the recompute cheap)
     TcGemmP p{};
-    p.K = 64; p.m_tiles = 4; p.n_tiles = (int)(R / 256); p.rows_per_set = N;
+    p.K = 64; p.m_tiles = 4; p.n_tiles = (int)(R / 256); p.rows_per_set = N; p.rows_per_obj = P;
     p.rowvec = e->cset; p.ldrv = 512;
     p.stats = e->stats0; p.stats_ld = 64; p.stats_goff = 0;  // partials per 128 points (BN = 256, two column halves)
     if ((rc = tc_run<CH_ON_LANES, EPI_STATS, 256>(e, s, G_ROT_LAYER0, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->pf_nb[0], e->pf_nb[1], p))) return rc;
@@ -702,15 +703,13 @@ const char* catre_last_error(const catre_engine* e) { return e ? e->err.c_str() 
 int catre_create(catre_engine** out, const catre_cfg* cfg) {
   if (!out || !cfg) return fail(nullptr, CATRE_ERR_INVALID_ARG, "null argument");
   *out = nullptr;
-  if (cfg->n_obs <= 0 || cfg->n_obs % 128 != 0)
-    return fail(nullptr, CATRE_ERR_UNSUPPORTED, "n_obs=%d must be a positive multiple of 128", cfg->n_obs);
-  if (cfg->n_prior != cfg->n_obs)
-    return fail(nullptr, CATRE_ERR_UNSUPPORTED, "n_prior=%d must equal n_obs=%d in this version", cfg->n_prior, cfg->n_obs);
+  if (cfg->n_obs <= 0 || cfg->n_obs % 128 != 0 || cfg->n_prior <= 0 || cfg->n_prior % 128 != 0)
+    return fail(nullptr, CATRE_ERR_UNSUPPORTED, "n_obs=%d and n_prior=%d must be positive multiples of 128", cfg->n_obs, cfg->n_prior);
   if (cfg->max_batch < 1) return fail(nullptr, CATRE_ERR_INVALID_ARG, "max_batch=%d must be >= 1", cfg->max_batch);
   if (cfg->precision < CATRE_PREC_FP32_SIMT || cfg->precision > CATRE_PREC_BF16)
     return fail(nullptr, CATRE_ERR_INVALID_ARG, "unknown precision %d", cfg->precision);
-  if (cfg->precision != CATRE_PREC_FP32_SIMT && cfg->n_obs % 256 != 0)
-    return fail(nullptr, CATRE_ERR_UNSUPPORTED, "tensor-core modes need n_obs %% 256 == 0 (got %d)", cfg->n_obs);
+  if (cfg->precision != CATRE_PREC_FP32_SIMT && (cfg->n_obs % 256 != 0 || cfg->n_prior % 256 != 0))
+    return fail(nullptr, CATRE_ERR_UNSUPPORTED, "tensor-core modes need n_obs and n_prior %% 256 == 0 (got %d, %d)", cfg->n_obs, cfg->n_prior);
   int ndev = 0;
   cudaError_t st = cudaGetDeviceCount(&ndev);
   if (st != cudaSuccess || ndev == 0) {
@@ -726,8 +725,9 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   catre_engine* e = new catre_engine();
   e->cfg = *cfg;
   e->N = cfg->n_obs;
+  e->Np = cfg->n_prior;
   e->maxB = cfg->max_batch;
-  const size_t B = e->maxB, S = 2 * B, N = e->N, R = S * N, P = 2 * N;
+  const size_t B = e->maxB, S = 2 * B, N = e->N, Np = e->Np, P = N + Np, R = B * P;
   int rc = 0;
   const bool tc = cfg->precision != CATRE_PREC_FP32_SIMT;
   rc |= dalloc(e, &e->q, R * 3);
@@ -758,7 +758,7 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   rc |= dalloc(e, &e->rot_partial, B * (P / 128 > 16 ? P / 128 : 16) * 6);
   rc |= dalloc(e, &e->st_pcl, B * N * 3);
   e->st_prior_rows = e->maxB > 16 ? e->maxB : 16;
-  rc |= dalloc(e, &e->st_prior, (size_t)e->st_prior_rows * N * 3);
+  rc |= dalloc(e, &e->st_prior, (size_t)e->st_prior_rows * Np * 3);
   rc |= dalloc(e, &e->st_cls, B);
   rc |= dalloc(e, &e->st_pose, B * 12);
   rc |= dalloc(e, &e->st_scale, B * 3);
@@ -1023,11 +1023,11 @@ int catre_forward_once(catre_engine* e, const float* x_pm, const float* kps_pm, 
   const int N = e->N;
   for (int b0 = 0; b0 < B; b0 += e->maxB) {
     int Bc = (B - b0 < e->maxB) ? B - b0 : e->maxB;
-    long long total = (long long)Bc * 2 * N;
+    long long total = (long long)Bc * (N + e->Np);
     {
       Launch l(e, s, G_UPDATE_POINTS);
-      launch_pdl(gather_points_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, x_pm + (size_t)b0 * N * 3, kps_pm + (size_t)b0 * N * 3,
-                 e->q, Bc, N, e->gmax_all, (long long)(2 * Bc) * (1024 * 3 + 64));
+      launch_pdl(gather_points_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, x_pm + (size_t)b0 * N * 3, kps_pm + (size_t)b0 * e->Np * 3,
+                 e->q, Bc, N, e->Np, e->gmax_all, (long long)(2 * Bc) * (1024 * 3 + 64));
     }
     if ((rc = check_launch(e, "gather_points"))) return rc;
     if ((rc = iteration(e, s, Bc, pose + (size_t)b0 * 12, scale + (size_t)b0 * 3, K + (size_t)b0 * 9,
@@ -1053,7 +1053,7 @@ static int refine_impl(catre_engine* e, const float* pcl, const float* prior, co
   CU_TRY(e, cudaMemcpyAsync(out_scales, init_scale, (size_t)B * 3 * sizeof(float), cudaMemcpyDeviceToDevice, s));
   for (int b0 = 0; b0 < B; b0 += e->maxB) {
     int Bc = (B - b0 < e->maxB) ? B - b0 : e->maxB;
-    long long total = (long long)Bc * 2 * N;
+    long long total = (long long)Bc * (N + e->Np);
     const int* pc_chunk = prior_cls ? (const int*)prior_cls + b0 : (const int*)nullptr;
     for (int it = 1; it <= n_iter; ++it) {
       const float* pin = out_poses + ((size_t)(it - 1) * B + b0) * 12;
@@ -1062,9 +1062,9 @@ static int refine_impl(catre_engine* e, const float* pcl, const float* prior, co
       float* sout = out_scales + ((size_t)it * B + b0) * 3;
       {
         Launch l(e, s, G_UPDATE_POINTS);
-        const float* pr = prior_cls ? prior : prior + (size_t)b0 * N * 3;
+        const float* pr = prior_cls ? prior : prior + (size_t)b0 * e->Np * 3;
         launch_pdl(update_points_kernel, dim3((unsigned)((total + 255) / 256)), dim3(256), (size_t)(0), s, pcl + (size_t)b0 * N * 3, pr,
-                   pin, sin, e->q, Bc, N, e->gmax_all, (long long)(2 * Bc) * (1024 * 3 + 64), pc_chunk, (int)n_cls);
+                   pin, sin, e->q, Bc, N, e->Np, e->gmax_all, (long long)(2 * Bc) * (1024 * 3 + 64), pc_chunk, (int)n_cls);
       }
       if ((rc = check_launch(e, "update_points"))) return rc;
       if ((rc = iteration(e, s, Bc, pin, sin, K + (size_t)b0 * 9, pout, sout, pc_chunk, (int)n_cls))) return rc;
@@ -1104,13 +1104,13 @@ static int refine_host_impl(catre_engine* e, const float* pcl, const float* prio
     for (int b = 0; b < B; ++b)
       if (prior_cls[b] < 0 || prior_cls[b] >= n_cls)
         return fail(e, CATRE_ERR_INVALID_ARG, "prior_cls[%d] = %d outside [0, %d)", b, prior_cls[b], n_cls);
-    CU_TRY(e, cudaMemcpyAsync(e->st_prior, prior, (size_t)n_cls * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    CU_TRY(e, cudaMemcpyAsync(e->st_prior, prior, (size_t)n_cls * e->Np * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
   }
   for (int b0 = 0; b0 < B; b0 += e->maxB) {
     int Bc = (B - b0 < e->maxB) ? B - b0 : e->maxB;
     CU_TRY(e, cudaMemcpyAsync(e->st_pcl, pcl + (size_t)b0 * N * 3, (size_t)Bc * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     if (prior_cls) CU_TRY(e, cudaMemcpyAsync(e->st_cls, prior_cls + b0, (size_t)Bc * sizeof(int32_t), cudaMemcpyHostToDevice, s));
-    else CU_TRY(e, cudaMemcpyAsync(e->st_prior, prior + (size_t)b0 * N * 3, (size_t)Bc * N * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
+    else CU_TRY(e, cudaMemcpyAsync(e->st_prior, prior + (size_t)b0 * e->Np * 3, (size_t)Bc * e->Np * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     CU_TRY(e, cudaMemcpyAsync(e->st_pose, init_pose + (size_t)b0 * 12, (size_t)Bc * 12 * sizeof(float), cudaMemcpyHostToDevice, s));
     CU_TRY(e, cudaMemcpyAsync(e->st_scale, init_scale + (size_t)b0 * 3, (size_t)Bc * 3 * sizeof(float), cudaMemcpyHostToDevice, s));
     CU_TRY(e, cudaMemcpyAsync(e->st_K, K + (size_t)b0 * 9, (size_t)Bc * 9 * sizeof(float), cudaMemcpyHostToDevice, s));
@@ -1314,6 +1314,8 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
                 catre_train::TrainWs::kMaxSymRots);
   if (e->dw.size() != (size_t)kNumWeights)
     return fail(e, CATRE_ERR_NOT_PACKED, "catre_train_step needs the 74 tensors set and one catre_pack");
+  if (e->N != e->Np)
+    return fail(e, CATRE_ERR_UNSUPPORTED, "catre_train_step: the training chain needs n_obs == n_prior (got %d, %d)", e->N, e->Np);
   CU_TRY(e, cudaSetDevice(e->cfg.device));
   cudaStream_t s = (cudaStream_t)stream;
   if (B > e->tws_maxB) {  // (re)allocate the workspace; not on the steady-state path

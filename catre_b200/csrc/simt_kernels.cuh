@@ -78,6 +78,15 @@ __device__ __forceinline__ float gelu_fast(float x) {
   return fmaf(-fabsf(x), e, fmaxf(x, 0.0f));
 }
 
+// Row layout of every per-point buffer: object b owns rows [b * P, (b + 1) * P), P = n_obs + n_prior; its first n_obs rows
+// are set 2b (observed points), the remaining n_prior rows set 2b + 1 (prior points).  n_obs and n_prior are multiples of
+// the kernels' row tiles, so a tile never straddles two sets (NUM_PCL != NUM_KPS is allowed, as in the reference:
+// conv_out_per_rot_head.py:112 only ties conv_p to the SUM).
+__host__ __device__ __forceinline__ int set_of_row(long long row, int P, int n_obs) {
+  const int obj = (int)(row / P);
+  return 2 * obj + (((int)(row - (long long)obj * P) >= n_obs) ? 1 : 0);
+}
+
 // ----------------------------------------------------------------------------------------------
 // U1: per-iteration point update (core/catre/engine/batch_test.py:78-97,
 //     lib/pysixd/misc.py:1011-1026):  x = pcl - t ;  k = R (s * kps)
@@ -89,15 +98,15 @@ __device__ __forceinline__ float gelu_fast(float x) {
 // outside [0, n_cls) reads row 0 here and pose_update_kernel overwrites that object's result with NaN.
 __global__ void update_points_kernel(const float* __restrict__ pcl, const float* __restrict__ prior,
                                      const float* __restrict__ pose, const float* __restrict__ scale,
-                                     float* __restrict__ q, int B, int N, int* __restrict__ gmax, long long n_keys,
+                                     float* __restrict__ q, int B, int N, int Np, int* __restrict__ gmax, long long n_keys,
                                      const int* __restrict__ cls, int n_cls) {
   pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long total = (long long)B * 2 * N;
+  long long total = (long long)B * (N + Np);
   for (long long k = i; k < n_keys; k += (long long)gridDim.x * blockDim.x) gmax[k] = KEY_NEG_INF;
   if (i >= total) return;
-  int b = (int)(i / (2 * N));
-  int r = (int)(i % (2 * N));
+  int b = (int)(i / (N + Np));
+  int r = (int)(i % (N + Np));
   const float* P = pose + (long long)b * 12;
   float o0, o1, o2;
   if (r < N) {
@@ -111,7 +120,7 @@ __global__ void update_points_kernel(const float* __restrict__ pcl, const float*
       row = cls[b];
       if (row < 0 || row >= n_cls) row = 0;
     }
-    const float* p = prior + ((long long)row * N + (r - N)) * 3;
+    const float* p = prior + ((long long)row * Np + (r - N)) * 3;
     const float* s = scale + (long long)b * 3;
     float k0 = p[0] * s[0], k1 = p[1] * s[1], k2 = p[2] * s[2];
     o0 = P[0] * k0 + P[1] * k1 + P[2] * k2;
@@ -135,15 +144,15 @@ __global__ void pack_poses_kernel(const float* __restrict__ poses, const float* 
 
 // forward_once entry: x and tfd_kps arrive already transformed; interleave them into the q layout
 __global__ void gather_points_kernel(const float* __restrict__ x_pm, const float* __restrict__ kps_pm,
-                                     float* __restrict__ q, int B, int N, int* __restrict__ gmax, long long n_keys) {
+                                     float* __restrict__ q, int B, int N, int Np, int* __restrict__ gmax, long long n_keys) {
   pdl_wait();
   long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x;
-  long long total = (long long)B * 2 * N;
+  long long total = (long long)B * (N + Np);
   for (long long k = i; k < n_keys; k += (long long)gridDim.x * blockDim.x) gmax[k] = KEY_NEG_INF;
   if (i >= total) return;
-  int b = (int)(i / (2 * N));
-  int r = (int)(i % (2 * N));
-  const float* p = (r < N) ? x_pm + ((long long)b * N + r) * 3 : kps_pm + ((long long)b * N + (r - N)) * 3;
+  int b = (int)(i / (N + Np));
+  int r = (int)(i % (N + Np));
+  const float* p = (r < N) ? x_pm + ((long long)b * N + r) * 3 : kps_pm + ((long long)b * Np + (r - N)) * 3;
   float* o = q + i * 3;
   o[0] = p[0]; o[1] = p[1]; o[2] = p[2];
 }
@@ -156,7 +165,7 @@ __global__ void gather_points_kernel(const float* __restrict__ x_pm, const float
 // ----------------------------------------------------------------------------------------------
 __global__ void front3_kernel(const float* __restrict__ q, const float* __restrict__ t3 /*[S,9] or null*/,
                               const float* __restrict__ W /*[64,3]*/, const float* __restrict__ bias,
-                              float* __restrict__ out, long long R, int N) {
+                              float* __restrict__ out, long long R, int P, int N) {
   pdl_wait();
   __shared__ float sW[64 * 3];
   __shared__ float sB[64];
@@ -169,7 +178,7 @@ __global__ void front3_kernel(const float* __restrict__ q, const float* __restri
   if (r >= R) return;
   float x0 = q[r * 3 + 0], x1 = q[r * 3 + 1], x2 = q[r * 3 + 2];
   if (t3 != nullptr) {
-    const float* T = t3 + (r / N) * 9;
+    const float* T = t3 + (long long)set_of_row(r, P, N) * 9;
     float y0 = x0 * T[0] + x1 * T[3] + x2 * T[6];
     float y1 = x0 * T[1] + x1 * T[4] + x2 * T[7];
     float y2 = x0 * T[2] + x1 * T[5] + x2 * T[8];
@@ -219,7 +228,8 @@ __global__ void __launch_bounds__(256) pw_gemm_kernel(GemmP p) {
 
   const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
   const int r0 = blockIdx.y * BM, c0 = blockIdx.x * BN;
-  const int set = r0 / p.rows_per_set;
+  // rows_per_obj > 1: per-point layers (rows_per_set = n_obs of the row layout above); otherwise one row = one set
+  const int set = p.rows_per_obj > 1 ? set_of_row(r0, p.rows_per_obj, p.rows_per_set) : r0 / p.rows_per_set;
   const int obj = r0 / p.rows_per_obj;
   const float* Wb = p.W + (long long)set * p.w_set_stride;
 

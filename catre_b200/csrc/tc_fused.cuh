@@ -36,8 +36,8 @@ constexpr int RF_SMEM = 1024 + 1024 + RF_U_BYTES + RF_SLOTS * RF_SLOT;  // barri
 
 struct RotFusedP {
   int tiles;             // R / 128
-  int rows_per_set;      // N
-  int rows_per_obj;      // P = 2N
+  int rows_per_set;      // n_obs
+  int rows_per_obj;      // P = n_obs + n_prior
   const float* gn_scale; // [S][512]  GroupNorm-0 scale per (set, channel)
   const float* gn_shift; // [S][512]  shift with the per-set constant folded in
   const float* bias1;    // [512]     layers.3 bias, both heads
@@ -224,7 +224,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
       // E0(j, s): lane = point row; slab s (layer-0 channels s*64 .. +63), this warp's 16 channels
       for (int j = 0; j < n_items; ++j) {
         const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
-        const int set = (int)(((long long)tile * 128) / p.rows_per_set);
+        const int set = set_of_row((long long)tile * 128, p.rows_per_obj, p.rows_per_set);
         const float* scp = p.gn_scale + (long long)set * 512 + h * 256;
         const float* shp = p.gn_shift + (long long)set * 512 + h * 256;
 #pragma unroll 1
@@ -367,7 +367,8 @@ cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo,
 // =================================================================================================
 struct EncFusedP {
   int tiles;             // R / 256
-  int rows_per_set;      // N
+  int rows_per_set;      // n_obs
+  int rows_per_obj;      // P = n_obs + n_prior
   const float* bias2;    // [128]
   const float* bias3;    // [1024]
   int* gmax;             // [S][1024] ordered-int keys
@@ -527,7 +528,7 @@ enc_fused_kernel(const __grid_constant__ CUtensorMap x_hi, const __grid_constant
     uint32_t use[2] = {0, 0};
     EncUnit un;
     for (int k = 0; enc_unit(k, p.tiles, un); ++k) {
-      const int set = (int)(((long long)un.item * 256) / p.rows_per_set);
+      const int set = set_of_row((long long)un.item * 256, p.rows_per_obj, p.rows_per_set);
       // ---- epi0: lane = point row of sub-tile `sub`; this warp's 16 channels of slab ks
       mbar_wait(bar_d0_full, it_phase);
       tc_fence_after();

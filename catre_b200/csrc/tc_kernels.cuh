@@ -235,7 +235,8 @@ __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t
 struct TcGemmP {
   int K;                 // reduction length, multiple of 64
   int m_tiles, n_tiles;  // tiles on the M side (128 rows each) / N side (BN rows each)
-  int rows_per_set;      // points per set (a tile never straddles two sets)
+  int rows_per_set;      // n_obs: observed points per object (a tile never straddles two sets; see set_of_row)
+  int rows_per_obj;      // P = n_obs + n_prior
   int nb_per_set;        // PT_ON_LANES: the NB operand is per set (rows set*BN .. +BN): feature transform
   int res_stages;        // resident-weight layers: activation stages in the ring (set by tc_launch)
   int out_bufs;          // point-on-lanes layers: output staging buffers (1 or 2, set by tc_launch)
@@ -366,7 +367,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
       }
       for (int t = blockIdx.x; t < total_tiles; t += gridDim.x) {
         int mi, ni; tile_coords(t, mi, ni);
-        const int nb_row = (ORIENT == PT_ON_LANES && p.nb_per_set) ? ((mi * 128) / p.rows_per_set) * BN : ni * BN;
+        const int nb_row = (ORIENT == PT_ON_LANES && p.nb_per_set) ? set_of_row((long long)mi * 128, p.rows_per_obj, p.rows_per_set) * BN : ni * BN;
         for (int ks = 0; ks < k_slabs; ++ks) {
           mbar_wait(bar_empty + 8 * stage, phase ^ 1);
           const uint32_t sb = ring_base + stage * STAGE_BYTES;
@@ -436,12 +437,12 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         });
         if (p.bias) m += s_bias[ch];
         if (p.relu) m = fmaxf(m, 0.f);
-        const int set = (ni * BN) / p.rows_per_set;
+        const int set = set_of_row((long long)ni * BN, p.rows_per_obj, p.rows_per_set);
         atomicMax(p.gmax + (long long)set * p.C + ch, f2key(m));
       } else if (EPI == EPI_STATS) {
         const int ch = mi * 128 + lane_row;
         const long long p0 = (long long)ni * BN + half * HALF;
-        const int set = (int)(p0 / p.rows_per_set);
+        const int set = set_of_row(p0, p.rows_per_obj, p.rows_per_set);
         float add = p.bias ? s_bias[ch] : 0.f;
         if (p.rowvec) add += p.rowvec[(long long)set * p.ldrv + ch];
         float s = 0.f, ss = 0.f;
@@ -470,7 +471,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         const int box = (half * HALF) / 64;                // box index within the tile
         const bool issuer = (quad == 0) && ((half * HALF) % 64 == 0) && (lane == 0);
         const int n0 = half * HALF;                        // first channel of this warp within the tile
-        const int set = (mi * 128) / p.rows_per_set;
+        const int set = set_of_row((long long)mi * 128, p.rows_per_obj, p.rows_per_set);
         float x[32];
         {
           float v[32];
@@ -570,7 +571,7 @@ template <bool F16>
 __global__ void __launch_bounds__(256) front3_split_kernel(const float* __restrict__ q, const float* __restrict__ t3,
                                                            const float* __restrict__ W, const float* __restrict__ bias,
                                                            __nv_bfloat16* __restrict__ out_hi, __nv_bfloat16* __restrict__ out_lo,
-                                                           int R, int N) {
+                                                           int R, int P, int N) {
   __shared__ float sW[64 * 3];
   __shared__ float sB[64];
   __shared__ float sT[9];
@@ -579,7 +580,7 @@ __global__ void __launch_bounds__(256) front3_split_kernel(const float* __restri
   if (threadIdx.x < 192) sW[threadIdx.x] = W[threadIdx.x];
   if (threadIdx.x >= 192) sB[threadIdx.x - 192] = bias[threadIdx.x - 192];
   pdl_wait();  // weights above are constants; the transform and the points come from upstream kernels
-  if (threadIdx.x < 9) sT[threadIdx.x] = t3 ? t3[(r0 / N) * 9 + threadIdx.x] : ((threadIdx.x % 4 == 0) ? 1.0f : 0.0f);
+  if (threadIdx.x < 9) sT[threadIdx.x] = t3 ? t3[set_of_row(r0, P, N) * 9 + threadIdx.x] : ((threadIdx.x % 4 == 0) ? 1.0f : 0.0f);
   for (int i = threadIdx.x; i < FRONT_PTS * 3; i += 256) sQ[i] = (r0 * 3 + i < R * 3) ? q[(size_t)r0 * 3 + i] : 0.0f;
   __syncthreads();
   const int cg = threadIdx.x & 7;  // channel group (8 channels)

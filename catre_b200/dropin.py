@@ -79,9 +79,11 @@ class _LossBridge(torch.autograd.Function):
                                       f"got per-term weights {g.tolist()}")
         eng = model._engine
         grads: List[Optional[torch.Tensor]] = []
-        if os.environ.get("CATRE_TRAIN_FLAT_GRADS", "0") == "1":
-            # opt-in (not yet measured on a GPU): one scaled copy of the engine's gradient arena, handed out as views,
-            # instead of a copy and a multiply per tensor
+        if os.environ.get("CATRE_TRAIN_FLAT_GRADS", "1") == "1":
+            # default since round 2 (measured on B200: 16.3 ms vs 17.2 ms per 16-object training iteration,
+            # profiles/r02a_train_loop_probe.log; green in tests/test_train_gpu.py): ONE scaled copy of the engine's gradient
+            # arena, handed out as views, instead of a copy and a multiply per tensor (~136 launches + 68 allocations).
+            # CATRE_TRAIN_FLAT_GRADS=0 selects the per-tensor hand-off.
             offsets, _ = eng._grad_layout()
             flat = eng.train_grads_flat(float(scale))
             for name, p, need in zip(ctx.names, ctx.shapes, ctx.needs_input_grad[4:]):
@@ -275,8 +277,6 @@ class CatreB200(nn.Module):
     def __init__(self, n_obs: int = 1024, n_prior: int = 1024, precision: str = "f16x3", max_batch: int = 256,
                  cfg: Any = None):
         super().__init__()
-        if n_obs != n_prior:
-            raise NotImplementedError("catre_b200 needs NUM_PCL == NUM_KPS")
         self.cfg = cfg
         self.n_obs, self.n_prior = int(n_obs), int(n_prior)
         self.precision = precision
@@ -311,7 +311,7 @@ class CatreB200(nn.Module):
         if self._engine is None or self._engine.device != idx:
             if self._engine is not None:
                 self._engine.close()
-            self._engine = _engine.Engine(self.n_obs, self.max_batch, self.precision, idx)
+            self._engine = _engine.Engine(self.n_obs, self.max_batch, self.precision, idx, n_prior=self.n_prior)
             self._packed_key = None
         key = self._weights_key()
         if key != self._packed_key:

@@ -109,11 +109,14 @@ class Engine:
     """One engine per device.  All tensors fp32; device entry points take CUDA tensors on the engine's
     device and run on the current torch stream without host synchronisation."""
 
-    def __init__(self, n_pts: int, max_batch: int, precision: str = "f16x3", device: int = 0):
+    def __init__(self, n_pts: int, max_batch: int, precision: str = "f16x3", device: int = 0, n_prior: Optional[int] = None):
+        """n_pts = observed points per object (INPUT.NUM_PCL); n_prior = prior points per object (INPUT.NUM_KPS, default
+        = n_pts).  The reference only ties conv_p to the sum (conv_out_per_rot_head.py:112)."""
         self.lib = load_library()
         self.n_pts, self.max_batch, self.device = int(n_pts), int(max_batch), int(device)
+        self.n_prior = int(n_pts if n_prior is None else n_prior)
         self.precision = precision
-        cfg = CatreCfg(n_obs=n_pts, n_prior=n_pts, max_batch=max_batch, precision=PRECISIONS[precision], device=device)
+        cfg = CatreCfg(n_obs=n_pts, n_prior=self.n_prior, max_batch=max_batch, precision=PRECISIONS[precision], device=device)
         h = ctypes.c_void_p()
         rc = self.lib.catre_create(ctypes.byref(h), ctypes.byref(cfg))
         if rc != 0:
@@ -178,7 +181,7 @@ class Engine:
         """x_pm [B,N,3], kps_pm [B,N,3] point-major; returns (pose [B,3,4], scale [B,3])."""
         B, N = x_pm.shape[0], self.n_pts
         x_pm = self._dev(x_pm, (B, N, 3), "x")
-        kps_pm = self._dev(kps_pm, (B, N, 3), "tfd_kps")
+        kps_pm = self._dev(kps_pm, (B, self.n_prior, 3), "tfd_kps")
         pose = self._dev(pose, (B, 3, 4), "init_pose")
         scale = self._dev(scale, (B, 3), "init_scale")
         K = self._dev(K, (B, 3, 3), "K")
@@ -192,7 +195,7 @@ class Engine:
         """All K iterations on the device.  Returns poses [n_iter+1,B,3,4], scales [n_iter+1,B,3]."""
         B, N = pcl.shape[0], self.n_pts
         pcl = self._dev(pcl, (B, N, 3), "pcl")
-        prior = self._dev(prior, (B, N, 3), "prior")
+        prior = self._dev(prior, (B, self.n_prior, 3), "prior")
         init_pose = self._dev(init_pose, (B, 3, 4), "init_pose")
         init_scale = self._dev(init_scale, (B, 3), "init_scale")
         K = self._dev(K, (B, 3, 3), "K")
@@ -222,7 +225,7 @@ class Engine:
         (a CUDA [B,15] fp32 tensor) the last iteration's packed poses additionally stay on the device for the multi-GPU
         all-gather (catre_refine_host_packed)."""
         B, N = pcl.shape[0], self.n_pts
-        for name, t, shp in (("pcl", pcl, (B, N, 3)), ("prior", prior, (B, N, 3)), ("init_pose", init_pose, (B, 3, 4)),
+        for name, t, shp in (("pcl", pcl, (B, N, 3)), ("prior", prior, (B, self.n_prior, 3)), ("init_pose", init_pose, (B, 3, 4)),
                              ("init_scale", init_scale, (B, 3)), ("K", K, (B, 3, 3))):
             if t.is_cuda or t.dtype != torch.float32 or tuple(t.shape) != shp or not t.is_contiguous():
                 raise CatreError(f"{name}: expected contiguous float32 host tensor of shape {shp}")
@@ -248,7 +251,7 @@ class Engine:
         B, N = pcl.shape[0], self.n_pts
         C = prior_table.shape[0]
         pcl = self._dev(pcl, (B, N, 3), "pcl")
-        prior_table = self._dev(prior_table, (C, N, 3), "prior_table")
+        prior_table = self._dev(prior_table, (C, self.n_prior, 3), "prior_table")
         if not prior_cls.is_cuda or prior_cls.dtype != torch.int32 or tuple(prior_cls.shape) != (B,):
             raise CatreError(f"prior_cls must be a CUDA int32 tensor of shape ({B},)")
         prior_cls = prior_cls.contiguous()
@@ -269,7 +272,7 @@ class Engine:
         """Host-buffer form of refine_table (class ids are validated on the host)."""
         B, N = pcl.shape[0], self.n_pts
         C = prior_table.shape[0]
-        for name, t, shp, dt in (("pcl", pcl, (B, N, 3), torch.float32), ("prior_table", prior_table, (C, N, 3), torch.float32),
+        for name, t, shp, dt in (("pcl", pcl, (B, N, 3), torch.float32), ("prior_table", prior_table, (C, self.n_prior, 3), torch.float32),
                                  ("prior_cls", prior_cls, (B,), torch.int32), ("init_pose", init_pose, (B, 3, 4), torch.float32),
                                  ("init_scale", init_scale, (B, 3), torch.float32), ("K", K, (B, 3, 3), torch.float32)):
             if t.is_cuda or t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous():

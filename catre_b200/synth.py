@@ -59,7 +59,7 @@ def load_weights(path: str = WEIGHTS_NPZ) -> Dict[str, torch.Tensor]:
     return {k: torch.from_numpy(z[k]) for k in z.files}
 
 
-def resize_conv_p(w: Dict[str, torch.Tensor], n_pts: int) -> Dict[str, torch.Tensor]:
+def resize_conv_p(w: Dict[str, torch.Tensor], n_pts: int, n_prior: Optional[int] = None) -> Dict[str, torch.Tensor]:
     """Fixture-defined weights for N != 1024 (SURVEY.md 8(d) "Weights per config"): the checkpoint with the
     two conv_p.weight [1, 2*1024, 1] re-sized -- obs half and prior half each linearly re-sampled to n_pts
     and scaled by 1024 / n_pts (conv_p is tied to the point count,
@@ -70,13 +70,14 @@ def resize_conv_p(w: Dict[str, torch.Tensor], n_pts: int) -> Dict[str, torch.Ten
     for head in ("rot_head.rot_head_x", "rot_head.rot_head_y"):
         cp = w[head + ".conv_p.weight"]
         half = cp.shape[1] // 2
-        if half == n_pts:
+        n_p = n_pts if n_prior is None else n_prior  # the prior half may have its own point count (NUM_KPS != NUM_PCL)
+        if half == n_pts and half == n_p:
             continue
         parts = []
-        for seg in (cp[:, :half, 0], cp[:, half:, 0]):
-            r = F.interpolate(seg.reshape(1, 1, half).double(), size=n_pts, mode="linear", align_corners=True)
-            parts.append(r.reshape(1, n_pts) * (float(half) / float(n_pts)))
-        out[head + ".conv_p.weight"] = torch.cat(parts, dim=1).reshape(1, 2 * n_pts, 1).to(cp.dtype).contiguous()
+        for seg, n in ((cp[:, :half, 0], n_pts), (cp[:, half:, 0], n_p)):
+            r = F.interpolate(seg.reshape(1, 1, half).double(), size=n, mode="linear", align_corners=True)
+            parts.append(r.reshape(1, n) * (float(half) / float(n)))
+        out[head + ".conv_p.weight"] = torch.cat(parts, dim=1).reshape(1, n_pts + n_p, 1).to(cp.dtype).contiguous()
     return out
 
 
@@ -115,10 +116,14 @@ class Batch:
 
 
 def make_batch(batch: int, n_pts: int, seed: int, round_robin_cls: bool = False,
-               fixtures: Optional[Fixtures] = None) -> Batch:
+               fixtures: Optional[Fixtures] = None, n_prior: Optional[int] = None) -> Batch:
     """SURVEY.md 8(d) "Synthetic inputs".  Everything is drawn from one seeded CPU generator in
-    float64 and cast to fp32 at the end."""
-    return _draw(batch, n_pts, seed, round_robin_cls, fixtures)[0]
+    float64 and cast to fp32 at the end.  ``n_prior``: prior points per object when it differs from the observed count."""
+    b = _draw(batch, n_pts, seed, round_robin_cls, fixtures)[0]
+    if n_prior is not None and n_prior != n_pts:
+        fx = fixtures or load_fixtures()
+        b.prior = resample_prior(fx.priors[b.obj_cls], n_prior).float().contiguous()
+    return b
 
 
 @dataclass

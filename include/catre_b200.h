@@ -52,8 +52,10 @@ typedef enum catre_precision {
 /* Replaces: the cfg.MODEL.CATRE / cfg.INPUT values the reference reads at model build time
  * (core/catre/models/CATRE_disR_shared.py:291-350, configs/catre/NOCS_REAL/aug05_..._120e.py:29-30,73-114). */
 typedef struct catre_cfg {
-  int32_t n_obs;        /* INPUT.NUM_PCL: observed points per object (multiple of 128) */
-  int32_t n_prior;      /* INPUT.NUM_KPS: prior points per object (== n_obs in this version) */
+  int32_t n_obs;        /* INPUT.NUM_PCL: observed points per object (multiple of 128; of 256 in the tensor-core modes) */
+  int32_t n_prior;      /* INPUT.NUM_KPS: prior points per object (same multiples; may differ from n_obs: the reference
+                           only ties conv_p to the sum, core/catre/models/heads/conv_out_per_rot_head.py:112.  The training
+                           step, catre_train_step, needs n_prior == n_obs) */
   int32_t max_batch;    /* workspace is sized for this many objects per launch (>= 1) */
   int32_t precision;    /* catre_precision */
   int32_t device;       /* CUDA device ordinal */

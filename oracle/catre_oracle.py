@@ -183,7 +183,7 @@ def cast_weights(w: Weights, dtype: torch.dtype) -> Weights:
     return {k: v.to(dtype) for k, v in w.items()}
 
 
-def resize_conv_p(w: Weights, n_pts: int) -> Weights:
+def resize_conv_p(w: Weights, n_pts: int, n_prior=None) -> Weights:
     """Fixture-defined weights for N != 1024 (SURVEY.md 8(d) "Weights per config"): everything
     from the checkpoint except the two conv_p.weight [1, 2*1024, 1], whose obs half and prior half
     are each linearly re-sampled to n_pts and scaled by 1024 / n_pts."""
@@ -191,11 +191,12 @@ def resize_conv_p(w: Weights, n_pts: int) -> Weights:
     for head in ("rot_head.rot_head_x", "rot_head.rot_head_y"):
         cp = w[head + ".conv_p.weight"]
         half = cp.shape[1] // 2
-        if half == n_pts:
+        n_p = n_pts if n_prior is None else n_prior  # the prior half may have its own point count (NUM_KPS != NUM_PCL)
+        if half == n_pts and half == n_p:
             continue
         parts = []
-        for seg in (cp[:, :half, 0], cp[:, half:, 0]):
-            r = F.interpolate(seg.reshape(1, 1, half).double(), size=n_pts, mode="linear", align_corners=True)
-            parts.append(r.reshape(1, n_pts) * (float(half) / float(n_pts)))
-        out[head + ".conv_p.weight"] = torch.cat(parts, dim=1).reshape(1, 2 * n_pts, 1).to(cp.dtype).contiguous()
+        for seg, n in ((cp[:, :half, 0], n_pts), (cp[:, half:, 0], n_p)):
+            r = F.interpolate(seg.reshape(1, 1, half).double(), size=n, mode="linear", align_corners=True)
+            parts.append(r.reshape(1, n) * (float(half) / float(n)))
+        out[head + ".conv_p.weight"] = torch.cat(parts, dim=1).reshape(1, n_pts + n_p, 1).to(cp.dtype).contiguous()
     return out

