@@ -43,8 +43,8 @@ def main():
         results[name] = res
         out[name] = {"seconds": round(dt, 4), "objects_per_s": round(total / dt, 1), "images_per_s": round(a.images / dt, 1),
                      "launches": st.launches, "compute_s": round(st.compute_s, 4), "collect_s": round(st.process_s, 4)}
-    # the two groupings agree to rounding, not to the bit, once a launch holds >= 128 objects: from there the engine
-    # runs the T-Net FC chain on the tensor cores (f16x3) instead of the fp32 cluster kernels
+    # since round 2 an object's result does not depend on the launch it shares (one fp32 FC path at every size): the two
+    # groupings must agree to the BIT (expected: 0.0)
     last = f"iter{a.n_iter}"
     diff = 0.0
     for x, y in zip(results["per_image"][last], results["cross_image_256"][last]):
@@ -52,6 +52,25 @@ def main():
             diff = max(diff, max(abs(p - q) for p, q in zip(x[f], y[f])) * unit)
     out["max_abs_diff_between_groupings"] = diff
     out["speedup"] = round(out["per_image"]["seconds"] / out["cross_image_256"]["seconds"], 2)
+    # the NOCS chain end to end: cross-image refinement -> NOCS-format collector -> compute_independent_mAP on the device for
+    # every iteration (what CATRE_EvaluatorCustom does with Python loops, catre_custom_evaluator.py:121-330)
+    from catre_b200 import nocs_eval
+
+    dataset_dicts, lo = [], 0
+    for i, n in enumerate(sizes):
+        annos = [{"category_id": int(b.obj_cls[j]), "bbox": [1.0, 2.0, 30.0, 40.0], "pose": b.init_pose[j].numpy(),
+                  "scale": b.init_scale[j].numpy(), "mug_handle": j % 2} for j in range(lo, lo + n)]
+        dataset_dicts.append({"scene_im_id": f"scene_{1 + i // 4}/{i:04d}", "file_name": f"{i}.png", "annotations": annos})
+        lo += n
+    col = nocs_eval.NocsPredictionCollector(OBJ_NAMES, a.n_iter, dataset_dicts)
+    t0 = time.perf_counter()
+    model_out, st = ev.catre_inference_on_dataset(cfg, model, loader, col, objects_per_launch=256, return_stats=True)
+    dt = time.perf_counter() - t0
+    t1 = time.perf_counter()
+    col.evaluate()  # a second evaluation alone: the metric part (5 iterations x compute_independent_mAP)
+    out["nocs_chain"] = {"seconds_refine_collect_evaluate": round(dt, 4), "objects_per_s": round(total / dt, 1),
+                         "seconds_evaluate_only": round(time.perf_counter() - t1, 4), "iterations_evaluated": a.n_iter + 1,
+                         "IoU50_mean_last_iter": float(model_out[f"iter{a.n_iter}"]["iou_3d_aps"][-1, 2])}
     print(json.dumps(out))
 
 
