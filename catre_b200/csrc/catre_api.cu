@@ -126,6 +126,9 @@ struct catre_engine {
   // fused FC chains (fc_chain.cuh): weights packed [8 ranks][K][C/8] fp32; [0] = stn, [1] = fstn
   float *fcc_fc1[2] = {nullptr, nullptr}, *fcc_fc2[2] = {nullptr, nullptr}, *fcc_fc3[2] = {nullptr, nullptr};
   float *fcc_cset = nullptr, *fcc_ts0 = nullptr;
+  int trunk_group = 0;  // objects per conv3 -> conv4 group launch (0: the whole batch at once); CATRE_TRUNK_GROUP
+  int a1_policy = 1;  // CATRE_A1_POLICY bit 0: rot tail walks the objects backwards; bit 1: default (not streaming) a1T stores
+  int rot_var = 0;    // epilogue schedule of rot_fused_kernel (tc_fused.cuh RotVar; CATRE_ROT_VAR=0|1|2, same bits)
   int fcc_ranks = 8;  // CTAs per FC-chain cluster (16 where the device co-schedules them), fixed per engine
   TcPair t64s;  // tensor-core modes: bf16 hi/lo of T64^T, [S*64, 64]
   float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
@@ -279,19 +282,20 @@ int tc_run(catre_engine* e, cudaStream_t s, int grp, const CUtensorMap& ma_hi, c
 // point-wise layer, points on TMEM lanes: act [R,K] (hi/lo) x W [C,K] -> relu(. + bias) re-split to bf16 hi/lo [R,C]
 template <int BN>
 int tc_split_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& act, const TcPair& w, int K, int C,
-                   const float* bias, const TcPair& out, long long R) {
+                   const float* bias, const TcPair& out, long long R, long long in_row0 = 0) {
   TcGemmP p{};
   p.K = K; p.m_tiles = (int)(R / 128); p.n_tiles = C / BN; p.rows_per_set = e->N; p.rows_per_obj = e->N + e->Np;
-  p.bias = bias; p.relu = 1;
+  p.bias = bias; p.relu = 1; p.mi_in0 = (int)(in_row0 / 128);
   return tc_run<PT_ON_LANES, EPI_SPLIT, BN>(e, s, grp, act.map_hi, act.map_lo, w.map_hi, w.map_lo, p, &out);
 }
 
 // point-wise layer + column max over the points of each set, channels on TMEM lanes
 int tc_max_layer(catre_engine* e, cudaStream_t s, int grp, const TcPair& w, const CUtensorMap* act_nb, int K, int C,
-                 const float* bias, int relu, int* gmax, long long R) {
+                 const float* bias, int relu, int* gmax, long long R, long long set_row0 = 0) {
   TcGemmP p{};
   p.K = K; p.m_tiles = C / 128; p.n_tiles = (int)(R / 256);
   p.bias = bias; p.relu = relu; p.gmax = gmax; p.C = C; p.rows_per_set = e->N; p.rows_per_obj = e->N + e->Np;
+  p.set_row0 = set_row0;
   return tc_run<CH_ON_LANES, EPI_MAX, 256>(e, s, grp, w.map_hi, w.map_lo, act_nb[0], act_nb[1], p);
 }
 
@@ -503,8 +507,15 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     if ((rc = tc_run<PT_ON_LANES, EPI_SPLIT_MAX, 64>(e, s, G_FEAT_TRANSFORM, e->x64.map_hi, e->x64.map_lo, e->t64s.map_hi,
                                                       e->t64s.map_lo, p, &e->pf16))) return rc;
     if ((rc = tc_split_layer<128>(e, s, G_CONV2, e->pf16, e->tw_conv2, 64, 128, W(e, "pcl_net.conv2.bias"), e->a128, R))) return rc;
-    if ((rc = tc_split_layer<128>(e, s, G_CONV3, e->a128, e->tw_conv3, 128, 512, W(e, "pcl_net.conv3.bias"), e->a512, R))) return rc;
-    if ((rc = tc_max_layer(e, s, G_CONV4_MAX, e->tw_conv4, e->a512_nb, 512, 1024, W(e, "pcl_net.conv4.bias"), 0, e->gmax_g, R))) return rc;
+    // conv3 -> conv4 in groups of trunk_group objects: the group's [rows, 512] hi/lo activations (4 KB per point) are
+    // written and read back while they are still in L2 and the next group overwrites the same lines, so this
+    // intermediate -- the largest of the chain -- costs no HBM traffic and the workspace holds one group of it
+    const int G = e->trunk_group > 0 ? e->trunk_group : B;
+    for (int g0 = 0; g0 < B; g0 += G) {
+      const long long row0 = (long long)g0 * P, Rg = (long long)((B - g0 < G) ? B - g0 : G) * P;
+      if ((rc = tc_split_layer<128>(e, s, G_CONV3, e->a128, e->tw_conv3, 128, 512, W(e, "pcl_net.conv3.bias"), e->a512, Rg, row0))) return rc;
+      if ((rc = tc_max_layer(e, s, G_CONV4_MAX, e->tw_conv4, e->a512_nb, 512, 1024, W(e, "pcl_net.conv4.bias"), 0, e->gmax_g, Rg, row0))) return rc;
+    }
   } else {
     GemmP p = gemm_args(e->h64a, 64, e->t64, 64, 64, nullptr, e->h64b, 64, R, 0);
     p.w_set_stride = 4096; p.rows_per_set = N; p.rows_per_obj = P;  // W[c][k] = T64^T[set][c][k]
@@ -578,15 +589,16 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
       RotFusedP pf{};
       pf.tiles = (int)(R / 128); pf.rows_per_set = N; pf.rows_per_obj = P;
       pf.gn_scale = gn0_scale; pf.gn_shift = gn0_shift; pf.bias1 = e->rot_b1; pf.stats = e->stats1; pf.a1t = e->a1;
+      pf.a1_keep = (e->a1_policy >> 1) & 1;
       cudaError_t st;
       {
         Launch l(e, s, G_ROT_FUSED);
         if (e->cfg.precision == CATRE_PREC_BF16)
           st = rot_fused_launch<1>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
-                                   e->tw_rot1s.map_lo, pf, e->num_sms, s);
+                                   e->tw_rot1s.map_lo, pf, e->num_sms, s, e->rot_var);
         else
           st = rot_fused_launch<3>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
-                                   e->tw_rot1s.map_lo, pf, e->num_sms, s);
+                                   e->tw_rot1s.map_lo, pf, e->num_sms, s, e->rot_var);
       }
       if (st != cudaSuccess) {
         cudaGetLastError();
@@ -623,7 +635,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     Launch l(e, s, G_ROT_TAIL);
     if (tc)  // finalises the GroupNorm-1 statistics itself (partials per 64 points from the fused rot kernel)
       launch_pdl(rot_tail_t_kernel, dim3(16, B), dim3(256), (size_t)(P * sizeof(float)), s, e->a1,
-                 e->stats1, e->rot_gn1_g, e->rot_gn1_b, P / 64, e->neck_w, e->neck_b, e->wp, e->rot_partial, P);
+                 e->stats1, e->rot_gn1_g, e->rot_gn1_b, P / 64, e->neck_w, e->neck_b, e->wp, e->rot_partial, P, e->a1_policy & 1);
     else
       launch_pdl(rot_tail_kernel, dim3(P / 128, B), dim3(256), (size_t)(0), s, e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
                  e->neck_b, e->wp, e->rot_partial, P);
@@ -775,18 +787,26 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
     if (env2 && atoi(env2) > 0) e->fct_min_rows = atoi(env2);
     const char* env3 = getenv("CATRE_FC3_TILED_MIN_ROWS");
     if (env3 && atoi(env3) > 0) e->fct_fc3_min_rows = atoi(env3);
+    const char* env4 = getenv("CATRE_ROT_VAR");  // experiments: epilogue schedule of the fused rot kernel (same bits)
+    if (env4 && atoi(env4) >= 0 && atoi(env4) <= 2) e->rot_var = atoi(env4);
+    const char* env5 = getenv("CATRE_A1_POLICY");
+    if (env5) e->a1_policy = atoi(env5) & 3;
+    const char* env6 = getenv("CATRE_TRUNK_GROUP");
+    if (env6 && atoi(env6) >= 0) e->trunk_group = atoi(env6);
   }
   if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) rc |= 1;
   if (!rc && tc) {
-    auto pair = [&](TcPair& t, size_t cols) {
-      rc |= dalloc(e, &t.hi, R * cols);
-      rc |= dalloc(e, &t.lo, R * cols);
+    auto pair = [&](TcPair& t, size_t cols, size_t rows) {
+      rc |= dalloc(e, &t.hi, rows * cols);
+      rc |= dalloc(e, &t.lo, rows * cols);
       if (rc) return;
-      if (!tc_make_map(&t.map_hi, t.hi, R, cols, cols, 128) || !tc_make_map(&t.map_lo, t.lo, R, cols, cols, 128)) rc |= 2;
+      if (!tc_make_map(&t.map_hi, t.hi, rows, cols, cols, 128) || !tc_make_map(&t.map_lo, t.lo, rows, cols, cols, 128)) rc |= 2;
     };
-    pair(e->x64, 64); pair(e->f64, 64); pair(e->a128, 128); pair(e->pf16, 64); pair(e->a512, 512);
+    // conv3's output only ever holds one object group (see iteration()): trunk_group objects instead of max_batch
+    const size_t R512 = (e->trunk_group > 0 && (size_t)e->trunk_group < B) ? (size_t)e->trunk_group * P : R;
+    pair(e->x64, 64, R); pair(e->f64, 64, R); pair(e->a128, 128, R); pair(e->pf16, 64, R); pair(e->a512, 512, R512);
     const size_t Spad = (S + 127) / 128 * 128;
     if (!rc) {  // T64^T per set, the N-side operand of the feature transform: [S*64, 64], 64-row boxes
       rc |= dalloc(e, &e->t64s.hi, Spad * 4096);
@@ -798,7 +818,7 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
       bool ok = true;
       ok &= tc_make_map(&e->a128_nb[0], e->a128.hi, R, 128, 128, 256) && tc_make_map(&e->a128_nb[1], e->a128.lo, R, 128, 128, 256);
       ok &= tc_make_map(&e->pf_nb[0], e->pf16.hi, R, 64, 64, 256) && tc_make_map(&e->pf_nb[1], e->pf16.lo, R, 64, 64, 256);
-      ok &= tc_make_map(&e->a512_nb[0], e->a512.hi, R, 512, 512, 256) && tc_make_map(&e->a512_nb[1], e->a512.lo, R, 512, 512, 256);
+      ok &= tc_make_map(&e->a512_nb[0], e->a512.hi, R512, 512, 512, 256) && tc_make_map(&e->a512_nb[1], e->a512.lo, R512, 512, 512, 256);
       if (!ok) rc |= 2;
     }
     if (rc & 2) e->err = "cuTensorMapEncodeTiled failed for an activation buffer";

@@ -718,11 +718,14 @@ __global__ void __launch_bounds__(256) rot_tail_t_kernel(const float* __restrict
                                                          const float* __restrict__ neck_w /*[2][3][256]*/,
                                                          const float* __restrict__ neck_b /*[2][3]*/,
                                                          const float* __restrict__ wp /*[2][P]*/, float* __restrict__ partial,
-                                                         int P) {
+                                                         int P, int reverse) {
   extern __shared__ __align__(16) float s_wp[];  // [P]
   __shared__ float s_part[8][3];
   __shared__ float s_sc[32], s_sh[32];
-  const int b = blockIdx.y, cg = blockIdx.x, h = cg >> 3;  // 16 blocks per object, 8 per head
+  // reverse: walk the objects from the last one down -- the fused rot kernel wrote them in ascending order, so the last
+  // ones are the part of a1T that is still in L2 (-7 % on this kernel at 64 objects, nothing at 256)
+  const int b = reverse ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
+  const int cg = blockIdx.x, h = cg >> 3;  // 16 blocks per object, 8 per head
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   for (int i = threadIdx.x; i < P / 4; i += 256)  // weights: constants, staged before the dependency wait
     reinterpret_cast<float4*>(s_wp)[i] = __ldg(reinterpret_cast<const float4*>(wp + (long long)h * P) + i);

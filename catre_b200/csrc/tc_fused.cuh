@@ -28,7 +28,6 @@ namespace catre {
 constexpr int RF_EW = 16;                       // epilogue warps of enc_fused_kernel; E0 (GELU) warps of rot_fused_kernel
 constexpr int RF_E1W = 8;                       // rot_fused_kernel: warps that drain D1 (concurrently with the E0 warps)
 constexpr int RF_THREADS = 64 + 32 * RF_EW;
-constexpr int ROT_THREADS = RF_THREADS + 32 * RF_E1W;
 constexpr int RF_SLOT = 32 * 1024;
 constexpr int RF_SLOTS = 3;
 constexpr int RF_U_BYTES = 128 * 1024;
@@ -43,6 +42,8 @@ struct RotFusedP {
   const float* bias1;    // [512]     layers.3 bias, both heads
   float* stats;          // [R/64][64 groups][2]
   float* a1t;            // [B][P/4][512][4] fp32: layer-1 output (+ bias) for the rot tail (see rot_tail_t_kernel)
+  int a1_keep;           // 0: streaming (evict-first) stores of a1T; 1: default stores, so that the tail of the buffer is still
+                         //    L2-resident when the rot tail (which then walks the objects backwards) reads it
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -63,6 +64,9 @@ __device__ __forceinline__ void tmem_ld_wait16(float* v) {
                :
                : "memory");
 }
+__device__ __forceinline__ void st_a1(float4* dst, const float4 v, int keep) {
+  if (keep) *dst = v; else __stcs(dst, v);
+}
 // Schedule (software-pipelined over the CTA's work items j; half A = layer-0 channels 0..127 = U slabs 0-1,
 // half B = channels 128..255 = slabs 2-3; D0a / D0b = TMEM columns 0..127 / 128..255):
 //   MMA warp      L0(0,A) L0(0,B) | L1(j,A) L0(j+1,A) L1(j,B) L0(j+1,B) | ...
@@ -70,8 +74,16 @@ __device__ __forceinline__ void tmem_ld_wait16(float* v) {
 //   E1 warps                      |            E1(j)  (whenever D1 of item j is complete) | ...      (8 warps: D1 -> a1T, stats)
 // The two epilogue groups are independent instruction streams: the GELU work of item j+1 runs underneath the layer-1
 // MMAs of item j AND underneath the drain of item j's D1; the only couplings are the TMEM / U barriers.
-template <int NPROD>
-__global__ void __launch_bounds__(ROT_THREADS, 1)
+// VAR selects the epilogue schedule (same arithmetic, same bits):
+//   0  round-2a schedule: per slab  wait D0 -> tcgen05.ld + 8 LDG.128 (GroupNorm affine) -> GELU -> U;  8 E1 warps
+//   1  the affine of the NEXT slab is loaded right after the GELU math of the current one (its registers are dead by
+//      then), so the L2 round trip of those loads hides under the U stores, the barrier arrival and the next D0 wait
+//   2  as 1, plus: both slabs of a D0 half are read from TMEM in one go (the half is released to the MMA warp one slab
+//      earlier and the second slab pays no TMEM latency); E1 runs on 4 warps (one per lane quadrant, both channel tiles)
+//      instead of 8 mostly idle ones, which frees the registers the second slab's values need
+template <int VAR> struct RotVar { static constexpr int E1W = (VAR == 2) ? 4 : RF_E1W; static constexpr int THREADS = RF_THREADS + 32 * E1W; };
+template <int NPROD, int VAR>
+__global__ void __launch_bounds__(RotVar<VAR>::THREADS, 1)
 rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constant__ CUtensorMap pf_lo,
                  const __grid_constant__ CUtensorMap w0_hi, const __grid_constant__ CUtensorMap w0_lo,
                  const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo, const RotFusedP p) {
@@ -98,7 +110,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
     for (int i = 0; i < RF_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     // RF_EW warps write U (E0 group), RF_E1W warps drain D1 (E1 group)
     for (int i = 0; i < 2; ++i) { mbar_init(bar_d0_full + 8 * i, 1); mbar_init(bar_d0_empty + 8 * i, RF_EW); }
-    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RF_E1W);
+    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RotVar<VAR>::E1W);
     for (int i = 0; i < 4; ++i) mbar_init(bar_u_full + 8 * i, RF_EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -221,6 +233,80 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
     const uint32_t row_off = (uint32_t)((lane_row >> 3) * 1024 + (lane_row & 7) * 128);
     if (warp < 2 + RF_EW) {
       const int part = (warp - 2) >> 2;  // 4 warps per TMEM lane quadrant: 16 of a slab's 64 channels each
+      if constexpr (VAR != 0) {
+        // ---- pipelined E0: the GroupNorm affine (16 scale + 16 shift values, the same for every lane) of the slab after
+        //      the current one is in flight while the current slab is stored and the next D0 wait runs
+        float4 sc4[4], sh4[4];
+        auto load_affine = [&](int j, int ks) {
+          const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
+          const int set = set_of_row((long long)tile * 128, p.rows_per_obj, p.rows_per_set);
+          const long long o = (long long)set * 512 + h * 256 + ks * 64 + part * 16;
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            sc4[q] = __ldg(reinterpret_cast<const float4*>(p.gn_scale + o) + q);
+            sh4[q] = __ldg(reinterpret_cast<const float4*>(p.gn_shift + o) + q);
+          }
+        };
+        // GELU of 16 accumulator values with the loaded affine, split, swizzled store into U slab ks, hand-over to the MMA warp
+        auto emit = [&](const float* v, int j, int ks) {
+          uint32_t hi[8], lo[8];
+#pragma unroll
+          for (int q = 0; q < 4; ++q) {
+            const float g0 = gelu_fast(fmaf(v[4 * q + 0], sc4[q].x, sh4[q].x));
+            const float g1 = gelu_fast(fmaf(v[4 * q + 1], sc4[q].y, sh4[q].y));
+            const float g2 = gelu_fast(fmaf(v[4 * q + 2], sc4[q].z, sh4[q].z));
+            const float g3 = gelu_fast(fmaf(v[4 * q + 3], sc4[q].w, sh4[q].w));
+            split16x2<TcOperand<NPROD>::F16>(g0, g1, hi[2 * q], lo[2 * q]);
+            split16x2<TcOperand<NPROD>::F16>(g2, g3, hi[2 * q + 1], lo[2 * q + 1]);
+          }
+          // the affine registers are dead: fetch the next slab's (next item's first slab after the last one)
+          if (ks < 3) load_affine(j, ks + 1);
+          else if (j + 1 < n_items) load_affine(j + 1, 0);
+          const uint32_t slab = u_base + ks * 32768 + row_off;
+          const uint32_t c0 = (uint32_t)(part * 2), sw = (uint32_t)(lane_row & 7);
+          st_shared_v4(slab + (((c0 + 0) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
+          st_shared_v4(slab + (((c0 + 1) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
+          if (NPROD == 3) {
+            st_shared_v4(slab + 16384 + (((c0 + 0) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
+            st_shared_v4(slab + 16384 + (((c0 + 1) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
+          }
+          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
+        };
+        if (n_items > 0) load_affine(0, 0);
+        for (int j = 0; j < n_items; ++j) {
+#pragma unroll 1
+          for (int half = 0; half < 2; ++half) {
+            mbar_wait(bar_d0_full + 8 * half, (uint32_t)j & 1);
+            tc_fence_after();
+            const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128 + part * 16);
+            if constexpr (VAR == 2) {
+              float va[16], vb[16];
+              tmem_ld16(t0, va);
+              tmem_ld16(t0 + 64, vb);
+              tmem_ld_wait16(va);
+              tmem_ld_wait16(vb);
+              tc_fence_before();  // this half of D0 is in registers: the next item's L0 may overwrite it
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_d0_empty + 8 * half);
+              emit(va, j, 2 * half);
+              emit(vb, j, 2 * half + 1);
+            } else {
+              float v[16];
+              tmem_ld16(t0, v);
+              tmem_ld_wait16(v);
+              emit(v, j, 2 * half);
+              tmem_ld16(t0 + 64, v);
+              tmem_ld_wait16(v);
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_d0_empty + 8 * half);
+              emit(v, j, 2 * half + 1);
+            }
+          }
+        }
+      } else
       // E0(j, s): lane = point row; slab s (layer-0 channels s*64 .. +63), this warp's 16 channels
       for (int j = 0; j < n_items; ++j) {
         const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
@@ -280,6 +366,55 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
       // fp32 values (+ bias) go straight from the registers to a1T [B][P/4][512][4]: 4 consecutive points of a channel are
       // one 16-byte store, and the 32 lanes (consecutive channels) of a warp write 512 contiguous bytes per instruction.
       // Keeping this activation in fp32 matters for parity.
+      if constexpr (VAR == 2) {
+        // 4 warps, one per TMEM lane quadrant: each drains both channel tiles of the item, one after the other
+        for (int j = 0; j < n_items; ++j) {
+          const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
+          const long long row0 = (long long)tile * 128;
+          while (!mbar_try_wait(bar_d1_full, (uint32_t)j & 1)) __nanosleep(64);
+          tc_fence_after();
+#pragma unroll 1
+          for (int mt = 0; mt < 2; ++mt) {
+            const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
+            const float add = p.bias1[ch];
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128);
+            float s = 0.f, ss = 0.f;
+#pragma unroll 1
+            for (int c = 0; c < 4; ++c) {
+              float x[32];
+              tmem_ld32(taddr + c * 32, x);
+              tmem_ld_wait32(x);
+              if (mt == 1 && c == 3) {  // D1 drained: the next item's layer-1 MMAs may overwrite it
+                tc_fence_before();
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar_d1_empty);
+              }
+#pragma unroll
+              for (int q = 0; q < 32; q += 2) {
+                x[q] += add; x[q + 1] += add;
+                s += x[q]; s += x[q + 1];
+                ss = fmaf(x[q], x[q], ss); ss = fmaf(x[q + 1], x[q + 1], ss);
+              }
+              const long long r64 = row0 + (c >> 1) * 64;  // first global row of this 64-point half
+              float4* dst = reinterpret_cast<float4*>(p.a1t) + ((r64 >> 2) + (c & 1) * 8) * 512 + ch;
+#pragma unroll
+              for (int q = 0; q < 8; ++q)
+                st_a1(dst + q * 512, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]), p.a1_keep);
+              if (c & 1) {  // GroupNorm-1 partial sums per 64 points and 8-channel group
+                s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+                s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+                s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+                if ((lane & 7) == 0) {
+                  const long long o = ((r64 >> 6) * 64 + (ch >> 3)) * 2;
+                  p.stats[o] = s;
+                  p.stats[o + 1] = ss;
+                }
+                s = 0.f; ss = 0.f;
+              }
+            }
+          }
+        }
+      } else {
       const int mt = (warp - 2 - RF_EW) >> 2;
       for (int j = 0; j < n_items; ++j) {
         const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
@@ -310,7 +445,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
           float4* dst = reinterpret_cast<float4*>(p.a1t) + ((r64 >> 2) + (c & 1) * 8) * 512 + ch;
 #pragma unroll
           for (int q = 0; q < 8; ++q)  // streaming stores: a1T is read once, by the next kernel; keep the weights in L2
-            __stcs(dst + q * 512, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
+            st_a1(dst + q * 512, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]), p.a1_keep);
           if (c & 1) {  // GroupNorm-1 partial sums per 64 points and 8-channel group
             s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
             s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
@@ -324,6 +459,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
           }
         }
       }
+      }  // VAR != 2
     }
   }
   tc_fence_before();
@@ -334,11 +470,11 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   }
 }
 
-template <int NPROD>
-cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo, const CUtensorMap& w0_hi,
+template <int NPROD, int VAR>
+cudaError_t rot_fused_launch_v(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo, const CUtensorMap& w0_hi,
                              const CUtensorMap& w0_lo, const CUtensorMap& w1_hi, const CUtensorMap& w1_lo,
                              const RotFusedP& p, int num_sms, cudaStream_t s) {
-  auto kern = rot_fused_kernel<NPROD>;
+  auto kern = rot_fused_kernel<NPROD, VAR>;
   static bool configured = false;
   if (!configured) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SMEM);
@@ -348,7 +484,16 @@ cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo,
   int items = p.tiles * 2;
   int grid = items < num_sms ? items : num_sms;
   if (grid < 1) return cudaSuccess;
-  return launch_pdl(kern, dim3(grid), dim3(ROT_THREADS), (size_t)RF_SMEM, s, pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p);
+  return launch_pdl(kern, dim3(grid), dim3(RotVar<VAR>::THREADS), (size_t)RF_SMEM, s, pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p);
+}
+// var: epilogue schedule (see RotVar / rot_fused_kernel); every schedule produces the same bits
+template <int NPROD>
+cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo, const CUtensorMap& w0_hi,
+                             const CUtensorMap& w0_lo, const CUtensorMap& w1_hi, const CUtensorMap& w1_lo,
+                             const RotFusedP& p, int num_sms, cudaStream_t s, int var = 0) {
+  if (var == 0) return rot_fused_launch_v<NPROD, 0>(pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p, num_sms, s);
+  if (var == 1) return rot_fused_launch_v<NPROD, 1>(pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p, num_sms, s);
+  return rot_fused_launch_v<NPROD, 2>(pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p, num_sms, s);
 }
 
 

@@ -247,6 +247,9 @@ struct TcGemmP {
   const float* rowvec; int ldrv;                // EPI_STATS: per-set additive vector [S, ldrv]
   float* stats; int stats_ld, stats_goff;       // EPI_STATS: GroupNorm partials [R/(BN/2), stats_ld, 2]
   float* out32; int ldo32; int rows32;          // EPI_SPLIT_STREAM: optional fp32 copy [rows32, ldo32]
+  // object-group launches (the group's output lives in a small buffer that stays in L2 until the next layer has read it):
+  int mi_in0;            // PT_ON_LANES: first 128-row tile of the group in the INPUT (M-side loads use mi + mi_in0; stores use mi)
+  long long set_row0;    // CH_ON_LANES / EPI_MAX: global row of the group's first point (the set of N-tile ni is taken at ni * BN + set_row0)
 };
 
 template <int ORIENT, int BN, int NPROD>
@@ -377,7 +380,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
             // stage layout: [M hi][M lo (x3)] then (streamed weights only) [N hi][N lo (x3)]
             const uint32_t dst = sb + (is_nb ? Cfg::MA_BYTES * Cfg::ARR + (is_lo ? Cfg::NB_BYTES : 0) : (is_lo ? Cfg::MA_BYTES : 0));
             const CUtensorMap* map = is_nb ? (is_lo ? &nb_lo : &nb_hi) : (is_lo ? &ma_lo : &ma_hi);
-            tma_load_2d(dst, map, ks * TC_BK, is_nb ? nb_row : mi * 128, full);
+            tma_load_2d(dst, map, ks * TC_BK, is_nb ? nb_row : (mi + (ORIENT == PT_ON_LANES ? p.mi_in0 : 0)) * 128, full);
           }
           if (++stage == STAGES) { stage = 0; phase ^= 1; }
         }
@@ -437,7 +440,7 @@ tc_gemm_kernel(const __grid_constant__ CUtensorMap ma_hi, const __grid_constant_
         });
         if (p.bias) m += s_bias[ch];
         if (p.relu) m = fmaxf(m, 0.f);
-        const int set = set_of_row((long long)ni * BN, p.rows_per_obj, p.rows_per_set);
+        const int set = set_of_row((long long)ni * BN + p.set_row0, p.rows_per_obj, p.rows_per_set);
         atomicMax(p.gmax + (long long)set * p.C + ch, f2key(m));
       } else if (EPI == EPI_STATS) {
         const int ch = mi * 128 + lane_row;
