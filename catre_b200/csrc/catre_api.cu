@@ -127,8 +127,8 @@ struct catre_engine {
   float *fcc_fc1[2] = {nullptr, nullptr}, *fcc_fc2[2] = {nullptr, nullptr}, *fcc_fc3[2] = {nullptr, nullptr};
   float *fcc_cset = nullptr, *fcc_ts0 = nullptr;
   int trunk_group = 0;  // objects per conv3 -> conv4 group launch (0: the whole batch at once); CATRE_TRUNK_GROUP
-  int a1_policy = 1;  // CATRE_A1_POLICY bit 0: rot tail walks the objects backwards; bit 1: default (not streaming) a1T stores
-  int rot_var = 0;    // epilogue schedule of rot_fused_kernel (tc_fused.cuh RotVar; CATRE_ROT_VAR=0|1|2, same bits)
+  int* rot_count = nullptr;   // [B][2] publication counters of the fused rot kernel (zeroed by gn_finalize_set_kernel)
+  bool debug_taps = false;    // CATRE_DEBUG_TAPS=1: keep optional intermediate copies for catre_debug_read (tests/test_stages_gpu.py)
   int fcc_ranks = 8;  // CTAs per FC-chain cluster (16 where the device co-schedules them), fixed per engine
   TcPair t64s;  // tensor-core modes: bf16 hi/lo of T64^T, [S*64, 64]
   float *stats0 = nullptr, *stats1 = nullptr, *gn0 = nullptr, *gn1 = nullptr, *rot_partial = nullptr;
@@ -556,7 +556,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     tsp.be1 = W(e, "ts_head.linears.4.bias");
     tsp.wt = W(e, "ts_head.fc_t.weight"); tsp.bt = W(e, "ts_head.fc_t.bias");
     tsp.ws = W(e, "ts_head.fc_s.weight"); tsp.bs = W(e, "ts_head.fc_s.bias");
-    tsp.rot_partial = e->rot_partial; tsp.rot_tiles = tc ? 16 : P / 128; tsp.convp_bias = e->convp_b;
+    tsp.rot_partial = e->rot_partial; tsp.rot_tiles = P / 128; tsp.convp_bias = e->convp_b;
     tsp.pose_in = pose_in; tsp.scale_in = scale_in; tsp.K = K; tsp.pose_out = pose_out; tsp.scale_out = scale_out;
     tsp.cls = prior_cls; tsp.n_cls = n_cls;
     CU_TRY(e, cudaEventRecord(e->ev_fork, s));
@@ -581,24 +581,26 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     {
       Launch l(e, s, G_GN_FINALIZE);
       launch_pdl(gn_finalize_set_kernel, dim3((B * 64 + 127) / 128), dim3(128), (size_t)(0), s, e->stats0, e->rot_gn0_g, e->rot_gn0_b, e->cset, gn0_scale,
-                                                                 gn0_shift, B, 512, P / 128, P);
+                                                                 gn0_shift, B, 512, P / 128, P, e->rot_count);
     }
     if ((rc = check_launch(e, "gn_finalize_set"))) return rc;
     {
       // layer-0 recompute + GroupNorm + GELU + bf16 split into shared memory + layer 1, one kernel
       RotFusedP pf{};
       pf.tiles = (int)(R / 128); pf.rows_per_set = N; pf.rows_per_obj = P;
-      pf.gn_scale = gn0_scale; pf.gn_shift = gn0_shift; pf.bias1 = e->rot_b1; pf.stats = e->stats1; pf.a1t = e->a1;
-      pf.a1_keep = (e->a1_policy >> 1) & 1;
+      pf.gn_scale = gn0_scale; pf.gn_shift = gn0_shift; pf.bias1 = e->rot_b1; pf.stats = e->stats1;
+      pf.obj_count = e->rot_count; pf.gn1_gamma = e->rot_gn1_g; pf.gn1_beta = e->rot_gn1_b;
+      pf.neck_w = e->neck_w; pf.neck_b = e->neck_b; pf.wp = e->wp; pf.partial = e->rot_partial;
+      pf.a1t = e->debug_taps ? e->a1 : nullptr;
       cudaError_t st;
       {
         Launch l(e, s, G_ROT_FUSED);
         if (e->cfg.precision == CATRE_PREC_BF16)
           st = rot_fused_launch<1>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
-                                   e->tw_rot1s.map_lo, pf, e->num_sms, s, e->rot_var);
+                                   e->tw_rot1s.map_lo, pf, e->num_sms, s);
         else
           st = rot_fused_launch<3>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
-                                   e->tw_rot1s.map_lo, pf, e->num_sms, s, e->rot_var);
+                                   e->tw_rot1s.map_lo, pf, e->num_sms, s);
       }
       if (st != cudaSuccess) {
         cudaGetLastError();
@@ -631,14 +633,10 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
                e->gn1 + (size_t)e->maxB * 512, B, 512, P / 128, P);
   }
   if ((rc = check_launch(e, "gn_finalize"))) return rc;
-  {
+  if (!tc) {  // tensor-core modes: the tail runs inside the fused rot kernel, out of TMEM
     Launch l(e, s, G_ROT_TAIL);
-    if (tc)  // finalises the GroupNorm-1 statistics itself (partials per 64 points from the fused rot kernel)
-      launch_pdl(rot_tail_t_kernel, dim3(16, B), dim3(256), (size_t)(P * sizeof(float)), s, e->a1,
-                 e->stats1, e->rot_gn1_g, e->rot_gn1_b, P / 64, e->neck_w, e->neck_b, e->wp, e->rot_partial, P, e->a1_policy & 1);
-    else
-      launch_pdl(rot_tail_kernel, dim3(P / 128, B), dim3(256), (size_t)(0), s, e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
-                 e->neck_b, e->wp, e->rot_partial, P);
+    launch_pdl(rot_tail_kernel, dim3(P / 128, B), dim3(256), (size_t)(0), s, e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
+               e->neck_b, e->wp, e->rot_partial, P);
   }
   if ((rc = check_launch(e, "rot_tail"))) return rc;
 
@@ -751,7 +749,10 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
     rc |= dalloc(e, &e->a0, R * 512);
     rc |= dalloc(e, &e->t64, S * 4096);
   }
-  rc |= dalloc(e, &e->a1, R * 512);  // fp32 mode: a1 [R][512]; tensor-core modes: a1T [B][P/4][512][4], fp32 as well
+  // fp32 mode: a1 [R][512], the rot layer-1 output.  The tensor-core modes never store it (the rot tail runs out of TMEM);
+  // with CATRE_DEBUG_TAPS=1 they keep a copy a1T [B][P/4][512][4] for the per-stage test
+  if (!tc || (getenv("CATRE_DEBUG_TAPS") && atoi(getenv("CATRE_DEBUG_TAPS")) != 0)) rc |= dalloc(e, &e->a1, R * 512);
+  rc |= dalloc(e, &e->rot_count, 2 * B);
   rc |= dalloc(e, &e->gmax_all, S * (1024 * 3 + 64));
   e->gmax_stn = e->gmax_all;
   e->gmax_fstn = e->gmax_all + S * 1024;
@@ -787,10 +788,8 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
     if (env2 && atoi(env2) > 0) e->fct_min_rows = atoi(env2);
     const char* env3 = getenv("CATRE_FC3_TILED_MIN_ROWS");
     if (env3 && atoi(env3) > 0) e->fct_fc3_min_rows = atoi(env3);
-    const char* env4 = getenv("CATRE_ROT_VAR");  // experiments: epilogue schedule of the fused rot kernel (same bits)
-    if (env4 && atoi(env4) >= 0 && atoi(env4) <= 2) e->rot_var = atoi(env4);
-    const char* env5 = getenv("CATRE_A1_POLICY");
-    if (env5) e->a1_policy = atoi(env5) & 3;
+    const char* env5 = getenv("CATRE_DEBUG_TAPS");
+    e->debug_taps = env5 && atoi(env5) != 0;
     const char* env6 = getenv("CATRE_TRUNK_GROUP");
     if (env6 && atoi(env6) >= 0) e->trunk_group = atoi(env6);
   }

@@ -3,9 +3,12 @@
 //   epi0 u = gelu(D0 * sc + sh)   (GroupNorm folded into sc/sh, per set)      -> bf16 hi/lo written by the
 //        epilogue warps straight into shared memory in the 128B-swizzled K-major operand layout
 //   L1   D1[mt][128 ch x 128 pts] = W1_h[mt*128.., 256] . u^T,  mt = 0, 1      (tcgen05, channels on lanes)
-//   epi1 a1T[obj][h*256 + ch][pt] = D1 + b1 (stored as fp16, channel-major; the GroupNorm partial sums per
-//        64 points are taken from the fp32 values.  fp16 storage of this one activation moves the final
-//        (R, t, s) by ~5e-6, measured with the CPU oracle -- it halves the only large HBM stream of the head)
+//   epi1 the rest of the head, straight from the TMEM accumulator (heads/conv_out_per_rot_head.py:131-140): GroupNorm-1 +
+//        GELU + neck 256 -> 3 + the learned weighted sum over the point index.  GroupNorm-1 needs statistics over ALL points
+//        of the object, i.e. over the 16 items (tiles) of this (object, head), which other CTAs are working on at the same
+//        time: every item publishes its partial sums in global memory and bumps a per-(object, head) counter, waits until
+//        the counter shows all tiles, finalises the statistics and then reads D1 a second time.  The layer-1 output
+//        (4 KB per point in fp32: 268 MB per iteration at 64 objects) is never stored, and the separate rot-tail kernel is gone.
 // so the layer-0 activations (2 KB per point) never touch HBM.  The layer-1 MMAs of K-slab ks start as
 // soon as epi0 has written slab ks, i.e. they run underneath the GELU work of slabs ks+1.. (one U buffer).
 //
@@ -14,11 +17,12 @@
 //
 // Warp roles: warp 0 TMA producer, warp 1 MMA issuer (+ TMEM alloc), warps 2..17 epilogue (4 per lane quadrant).
 // Shared memory: barriers (1 KB) | U: 4 K-slabs x {hi, lo} x [128 rows x 128 B] = 128 KB | ring of 3 x 32 KB slots.
-// After the layer-1 MMAs of a work item have completed, U is dead until the next item's epi0, so epi1 stages
-// its 64 KB fp16 output tile in U slabs 0-1 (4 boxes of [128 ch x 64 pts], 128B-swizzled) and hands it to
-// the TMA store engine (cp.async.bulk.tensor, shared -> global): the a1T write drains in the background.
-// epi0 (and therefore the layer-1 K loop) visits the slabs in the order 2, 3, 0, 1, so the next item only
-// has to wait for that drain before its third slab.
+// Why (profiles/r02_rot_fused_timeline.txt): D1 is single-buffered (TMEM is full), so the layer-1 MMAs of the next item wait
+// for epi1.  Storing the tile (128 KB of st.global per item) held D1 for 6 k cycles of a 19.5 k period, pushed the weight
+// tiles that were queued behind the stores out by another ~5 k and slowed the GELU warps; with the stores compiled out the
+// drain took 1.6 k.  Deadlock-freedom of the cross-CTA wait: the grid is persistent with one CTA per SM (every CTA is
+// resident or becomes resident without anyone's help), an item publishes BEFORE it waits, and what it waits for are items of
+// the same object, which their CTAs reach after finishing items of earlier objects only (induction over the object index).
 // TMEM: D0 = columns 0..255, D1[mt] = columns 256 + 128 mt.
 #pragma once
 #include "tc_kernels.cuh"
@@ -32,6 +36,7 @@ constexpr int RF_SLOT = 32 * 1024;
 constexpr int RF_SLOTS = 3;
 constexpr int RF_U_BYTES = 128 * 1024;
 constexpr int RF_SMEM = 1024 + 1024 + RF_U_BYTES + RF_SLOTS * RF_SLOT;  // barriers + alignment slack + U + ring
+constexpr int ROT_SMEM = 2048 + 1024 + RF_U_BYTES + RF_SLOTS * RF_SLOT; // rot_fused_kernel: 2 KB of barriers + tail scratch (= 227 KB)
 
 struct RotFusedP {
   int tiles;             // R / 128
@@ -40,10 +45,14 @@ struct RotFusedP {
   const float* gn_scale; // [S][512]  GroupNorm-0 scale per (set, channel)
   const float* gn_shift; // [S][512]  shift with the per-set constant folded in
   const float* bias1;    // [512]     layers.3 bias, both heads
-  float* stats;          // [R/64][64 groups][2]
-  float* a1t;            // [B][P/4][512][4] fp32: layer-1 output (+ bias) for the rot tail (see rot_tail_t_kernel)
-  int a1_keep;           // 0: streaming (evict-first) stores of a1T; 1: default stores, so that the tail of the buffer is still
-                         //    L2-resident when the rot tail (which then walks the objects backwards) reads it
+  float* stats;          // [R/128][64 groups][2]  GroupNorm-1 partial sums of every item, exchanged between the CTAs
+  int* obj_count;        // [B][2]   items of (object, head) that have published their sums; zero before the launch
+  const float* gn1_gamma; const float* gn1_beta;  // [512]
+  const float* neck_w;   // [2][3][256]
+  const float* neck_b;   // [2][3]
+  const float* wp;       // [2][P]   conv_p weights per head and point index
+  float* partial;        // [B][P/128][6]  per-item contributions to the two heads' 3-vectors (summed by pose_update_kernel)
+  float* a1t;            // debug tap only (null in production): [B][P/4][512][4] fp32 layer-1 output + bias
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -64,9 +73,6 @@ __device__ __forceinline__ void tmem_ld_wait16(float* v) {
                :
                : "memory");
 }
-__device__ __forceinline__ void st_a1(float4* dst, const float4 v, int keep) {
-  if (keep) *dst = v; else __stcs(dst, v);
-}
 // Schedule (software-pipelined over the CTA's work items j; half A = layer-0 channels 0..127 = U slabs 0-1,
 // half B = channels 128..255 = slabs 2-3; D0a / D0b = TMEM columns 0..127 / 128..255):
 //   MMA warp      L0(0,A) L0(0,B) | L1(j,A) L0(j+1,A) L1(j,B) L0(j+1,B) | ...
@@ -74,30 +80,29 @@ __device__ __forceinline__ void st_a1(float4* dst, const float4 v, int keep) {
 //   E1 warps                      |            E1(j)  (whenever D1 of item j is complete) | ...      (8 warps: D1 -> a1T, stats)
 // The two epilogue groups are independent instruction streams: the GELU work of item j+1 runs underneath the layer-1
 // MMAs of item j AND underneath the drain of item j's D1; the only couplings are the TMEM / U barriers.
-// VAR selects the epilogue schedule (same arithmetic, same bits):
-//   0  round-2a schedule: per slab  wait D0 -> tcgen05.ld + 8 LDG.128 (GroupNorm affine) -> GELU -> U;  8 E1 warps
-//   1  the affine of the NEXT slab is loaded right after the GELU math of the current one (its registers are dead by
-//      then), so the L2 round trip of those loads hides under the U stores, the barrier arrival and the next D0 wait
-//   2  as 1, plus: both slabs of a D0 half are read from TMEM in one go (the half is released to the MMA warp one slab
-//      earlier and the second slab pays no TMEM latency); E1 runs on 4 warps (one per lane quadrant, both channel tiles)
-//      instead of 8 mostly idle ones, which frees the registers the second slab's values need
-template <int VAR> struct RotVar { static constexpr int E1W = (VAR == 2) ? 4 : RF_E1W; static constexpr int THREADS = RF_THREADS + 32 * E1W; };
-template <int NPROD, int VAR>
-__global__ void __launch_bounds__(RotVar<VAR>::THREADS, 1)
+constexpr int ROT_THREADS = RF_THREADS + 32 * RF_E1W;
+template <int NPROD>
+__global__ void __launch_bounds__(ROT_THREADS, 1)
 rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constant__ CUtensorMap pf_lo,
                  const __grid_constant__ CUtensorMap w0_hi, const __grid_constant__ CUtensorMap w0_lo,
                  const __grid_constant__ CUtensorMap w1_hi, const __grid_constant__ CUtensorMap w1_lo, const RotFusedP p) {
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
-  const uint32_t u_base = (smem_base + 1024 + 1023) & ~1023u;  // barriers live in the first 1 KB
+  const uint32_t u_base = (smem_base + 2048 + 1023) & ~1023u;  // barriers and the tail's scratch live in the first 2 KB
   const uint32_t ring_base = u_base + RF_U_BYTES;
-  // barriers (8 B each): full[3] empty[3] d0_full[2] d0_empty[2] d1_full d1_empty u_full[4], then the TMEM base slot
+  // barriers (8 B each): full[3] empty[3] d0_full[2] d0_empty[2] d1_full d1_empty u_full[4], TMEM base slot, stats_ready, pass2_done
   const uint32_t bar_full = smem_base, bar_empty = smem_base + 24;
   const uint32_t bar_d0_full = smem_base + 48, bar_d0_empty = smem_base + 64;
   const uint32_t bar_d1_full = smem_base + 80, bar_d1_empty = smem_base + 88;
   const uint32_t bar_u_full = smem_base + 96;  // 4 barriers
   const uint32_t tmem_slot = smem_base + 128;
+  const uint32_t bar_stats_ready = smem_base + 136, bar_pass2_done = smem_base + 144;
   volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + 128);
+  // tail scratch: conv_p weights of the item's 128 points | GroupNorm-1 (rstd, mean) of the head's 32 groups | per-warp neck
+  // partials [24][3]
+  float* s_wp = reinterpret_cast<float*>(smem_raw + 256);
+  float2* s_grp = reinterpret_cast<float2*>(smem_raw + 768);   // [32]
+  float* s_part = reinterpret_cast<float*>(smem_raw + 1024);    // [24 warps][3]
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_ht = p.tiles * 2;  // (tile, head) work items
@@ -110,7 +115,8 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
     for (int i = 0; i < RF_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     // RF_EW warps write U (E0 group), RF_E1W warps drain D1 (E1 group)
     for (int i = 0; i < 2; ++i) { mbar_init(bar_d0_full + 8 * i, 1); mbar_init(bar_d0_empty + 8 * i, RF_EW); }
-    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RotVar<VAR>::E1W);
+    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RF_EW + RF_E1W);  // D1 is released by pass 2 of the tail (all 24 warps)
+    mbar_init(bar_stats_ready, 1); mbar_init(bar_pass2_done, RF_EW + RF_E1W);
     for (int i = 0; i < 4; ++i) mbar_init(bar_u_full + 8 * i, RF_EW);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
@@ -222,100 +228,86 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
     }
   } else {
     // ===================== epilogue warps =====================
-    // Two groups that run CONCURRENTLY: warps 2..17 turn D0 into the layer-1 operand U (E0: GroupNorm affine + GELU +
-    // 16-bit split, CUDA-core heavy: 4 warps per scheduler hide its TMEM / shared-memory latencies), warps 18..25 drain
-    // D1 (E1: bias, GroupNorm-1 partial sums, fp32 stores; mostly waiting, with a back-off so it does not steal issue slots).
-    // Round 1 ran E0 and E1 on the same 16 warps in sequence, so E1(j) -- which has to wait for the layer-1 MMAs of the
-    // slabs E0 has only just written -- stalled the GELU work of item j+1: 26 % of that kernel's samples were epilogue
-    // warps spinning on d1_full / d0_full (profiles/r02_ncu_rot_fused.txt) and the tensor pipe sat at 38 %.
+    // Two groups that run CONCURRENTLY.
+    //   warps 2..17 (E0, CUDA-core heavy): turn D0 into the layer-1 operand U (GroupNorm-0 affine + GELU + 16-bit split), and
+    //     between the two halves of an item run PASS 2 of the previous item's tail out of D1 (GroupNorm-1 + GELU + conv_p
+    //     weighted sum): program order  E0(j, s0) E0(j, s1) PASS2(j-1) E0(j, s2) E0(j, s3).
+    //   warps 18..25 (E1): PASS 1 of the tail (GroupNorm-1 partial sums of D1), the exchange of those sums with the other CTAs
+    //     of the object, the finalised per-group statistics, and the neck over the E0 warps' partial results.
+    // History: round 1 ran E0 and the D1 drain on the same 16 warps in sequence (tensor pipe 38 %); round 2a made them
+    // concurrent groups and stored D1 for a separate tail kernel -- those stores held D1 and blocked the TMA queue
+    // (profiles/r02_rot_fused_timeline.txt); now nothing of layer 1 is stored.
     const int quad = warp & 3;
     const int lane_row = quad * 32 + lane;
     const uint32_t row_off = (uint32_t)((lane_row >> 3) * 1024 + (lane_row & 7) * 128);
-    if (warp < 2 + RF_EW) {
-      const int part = (warp - 2) >> 2;  // 4 warps per TMEM lane quadrant: 16 of a slab's 64 channels each
-      if constexpr (VAR != 0) {
-        // ---- pipelined E0: the GroupNorm affine (16 scale + 16 shift values, the same for every lane) of the slab after
-        //      the current one is in flight while the current slab is stored and the next D0 wait runs
-        float4 sc4[4], sh4[4];
-        auto load_affine = [&](int j, int ks) {
-          const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
-          const int set = set_of_row((long long)tile * 128, p.rows_per_obj, p.rows_per_set);
-          const long long o = (long long)set * 512 + h * 256 + ks * 64 + part * 16;
+    const int P = p.rows_per_obj, tiles_per_obj = P / 128;
+    // PASS 2 of the tail for item j on one warp: thread = channel (TMEM lane) of m-tile mt, the NCH 16-column chunks (points)
+    // from column col0 of D1[mt]:  acc = sum_p wp[p] gelu(GN1(D1 + b1)),  then this warp's share of the neck's 3 outputs
+    auto pass2_cols = [&](int j, int mt, int col0, int nch, int slot) {
+      const int ht = item_ht(j), h = ht & 1;
+      const int cl = mt * 128 + lane_row, ch = h * 256 + cl;  // channel within the head / of both heads
+      const float add = __ldg(p.bias1 + ch), gam = __ldg(p.gn1_gamma + ch), bet = __ldg(p.gn1_beta + ch);
+      const float nw0 = __ldg(p.neck_w + (h * 3 + 0) * 256 + cl), nw1 = __ldg(p.neck_w + (h * 3 + 1) * 256 + cl),
+                  nw2 = __ldg(p.neck_w + (h * 3 + 2) * 256 + cl);
+      mbar_wait(bar_stats_ready, (uint32_t)j & 1);  // the statistics of the whole object are there (and D1(j) is complete)
+      tc_fence_after();
+      const float2 rm = s_grp[cl >> 3];  // (rstd, mean) of this channel's group
+      const float sc = rm.x * gam, sh = bet - rm.y * sc;
+      const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128 + col0);
+      float acc = 0.f;
+      float xa[16], xb[16];
+      tmem_ld16(taddr, xa);
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            sc4[q] = __ldg(reinterpret_cast<const float4*>(p.gn_scale + o) + q);
-            sh4[q] = __ldg(reinterpret_cast<const float4*>(p.gn_shift + o) + q);
+      for (int c = 0; c < 3; ++c) {
+        if (c < nch) {
+          float* x = (c & 1) ? xb : xa;
+          tmem_ld_wait16(x);
+          if (c + 1 < nch) {
+            tmem_ld16(taddr + (c + 1) * 16, (c & 1) ? xa : xb);
+          } else {  // D1 is in registers for the last time: the next item's layer-1 MMAs may overwrite it
+            tc_fence_before();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(bar_d1_empty);
           }
-        };
-        // GELU of 16 accumulator values with the loaded affine, split, swizzled store into U slab ks, hand-over to the MMA warp
-        auto emit = [&](const float* v, int j, int ks) {
-          uint32_t hi[8], lo[8];
 #pragma unroll
-          for (int q = 0; q < 4; ++q) {
-            const float g0 = gelu_fast(fmaf(v[4 * q + 0], sc4[q].x, sh4[q].x));
-            const float g1 = gelu_fast(fmaf(v[4 * q + 1], sc4[q].y, sh4[q].y));
-            const float g2 = gelu_fast(fmaf(v[4 * q + 2], sc4[q].z, sh4[q].z));
-            const float g3 = gelu_fast(fmaf(v[4 * q + 3], sc4[q].w, sh4[q].w));
-            split16x2<TcOperand<NPROD>::F16>(g0, g1, hi[2 * q], lo[2 * q]);
-            split16x2<TcOperand<NPROD>::F16>(g2, g3, hi[2 * q + 1], lo[2 * q + 1]);
-          }
-          // the affine registers are dead: fetch the next slab's (next item's first slab after the last one)
-          if (ks < 3) load_affine(j, ks + 1);
-          else if (j + 1 < n_items) load_affine(j + 1, 0);
-          const uint32_t slab = u_base + ks * 32768 + row_off;
-          const uint32_t c0 = (uint32_t)(part * 2), sw = (uint32_t)(lane_row & 7);
-          st_shared_v4(slab + (((c0 + 0) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
-          st_shared_v4(slab + (((c0 + 1) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
-          if (NPROD == 3) {
-            st_shared_v4(slab + 16384 + (((c0 + 0) ^ sw) << 4), lo[0], lo[1], lo[2], lo[3]);
-            st_shared_v4(slab + 16384 + (((c0 + 1) ^ sw) << 4), lo[4], lo[5], lo[6], lo[7]);
-          }
-          fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-          __syncwarp();
-          if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
-        };
-        if (n_items > 0) load_affine(0, 0);
-        for (int j = 0; j < n_items; ++j) {
-#pragma unroll 1
-          for (int half = 0; half < 2; ++half) {
-            mbar_wait(bar_d0_full + 8 * half, (uint32_t)j & 1);
-            tc_fence_after();
-            const uint32_t t0 = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(half * 128 + part * 16);
-            if constexpr (VAR == 2) {
-              float va[16], vb[16];
-              tmem_ld16(t0, va);
-              tmem_ld16(t0 + 64, vb);
-              tmem_ld_wait16(va);
-              tmem_ld_wait16(vb);
-              tc_fence_before();  // this half of D0 is in registers: the next item's L0 may overwrite it
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_d0_empty + 8 * half);
-              emit(va, j, 2 * half);
-              emit(vb, j, 2 * half + 1);
-            } else {
-              float v[16];
-              tmem_ld16(t0, v);
-              tmem_ld_wait16(v);
-              emit(v, j, 2 * half);
-              tmem_ld16(t0 + 64, v);
-              tmem_ld_wait16(v);
-              tc_fence_before();
-              __syncwarp();
-              if (lane == 0) mbar_arrive(bar_d0_empty + 8 * half);
-              emit(v, j, 2 * half + 1);
-            }
+          for (int q = 0; q < 16; q += 4) {
+            const float4 w = *reinterpret_cast<const float4*>(s_wp + col0 + c * 16 + q);  // same address on every lane
+            acc = fmaf(w.x, gelu_fast(fmaf(x[q + 0] + add, sc, sh)), acc);
+            acc = fmaf(w.y, gelu_fast(fmaf(x[q + 1] + add, sc, sh)), acc);
+            acc = fmaf(w.z, gelu_fast(fmaf(x[q + 2] + add, sc, sh)), acc);
+            acc = fmaf(w.w, gelu_fast(fmaf(x[q + 3] + add, sc, sh)), acc);
           }
         }
-      } else
+      }
+      // neck (linearity: sum_p wp (neck . g_p + nb) = neck . S + nb sum_p wp)
+      float r0 = nw0 * acc, r1 = nw1 * acc, r2 = nw2 * acc;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+        r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+        r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+        r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+      }
+      if (lane == 0) {
+        s_part[slot * 3 + 0] = r0; s_part[slot * 3 + 1] = r1; s_part[slot * 3 + 2] = r2;
+        mbar_arrive(bar_pass2_done);  // (release: the stores above are visible to the E1 threads that wait)
+      }
+    };
+    if (warp < 2 + RF_EW) {
+      const int part = (warp - 2) >> 2;  // 4 warps per TMEM lane quadrant: 16 of a slab's 64 channels each
+      // PASS2(j) on this warp: E0 warps take 48 of the m-tile's 128 points each, the E1 warp of the same quadrant and m-tile
+      // the last 32 (see pass2_cols)
+      auto pass2 = [&](int j) { pass2_cols(j, part >> 1, (part & 1) * 48, 3, warp - 2); };
       // E0(j, s): lane = point row; slab s (layer-0 channels s*64 .. +63), this warp's 16 channels
       for (int j = 0; j < n_items; ++j) {
         const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
         const int set = set_of_row((long long)tile * 128, p.rows_per_obj, p.rows_per_set);
         const float* scp = p.gn_scale + (long long)set * 512 + h * 256;
         const float* shp = p.gn_shift + (long long)set * 512 + h * 256;
+        bool tail_done = (j == 0);  // PASS2(j-1) runs before the first slab of E0(j) whose turn finds the statistics there
 #pragma unroll 1
         for (int ks = 0; ks < 4; ++ks) {
           const int half = ks >> 1;
+          if (!tail_done && mbar_try_wait(bar_stats_ready, (uint32_t)(j - 1) & 1)) { pass2(j - 1); tail_done = true; }
           if ((ks & 1) == 0) {
             mbar_wait(bar_d0_full + 8 * half, (uint32_t)j & 1);
             tc_fence_after();
@@ -360,106 +352,102 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
         }
+        if (!tail_done) pass2(j - 1);
       }
+      if (n_items > 0) pass2(n_items - 1);
     } else {
-      // E1(j): lane = output channel of m-tile mt; this warp takes all 128 points of the item in four chunks of 32.  The
-      // fp32 values (+ bias) go straight from the registers to a1T [B][P/4][512][4]: 4 consecutive points of a channel are
-      // one 16-byte store, and the 32 lanes (consecutive channels) of a warp write 512 contiguous bytes per instruction.
-      // Keeping this activation in fp32 matters for parity.
-      if constexpr (VAR == 2) {
-        // 4 warps, one per TMEM lane quadrant: each drains both channel tiles of the item, one after the other
-        for (int j = 0; j < n_items; ++j) {
-          const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
-          const long long row0 = (long long)tile * 128;
-          while (!mbar_try_wait(bar_d1_full, (uint32_t)j & 1)) __nanosleep(64);
-          tc_fence_after();
-#pragma unroll 1
-          for (int mt = 0; mt < 2; ++mt) {
-            const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
-            const float add = p.bias1[ch];
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128);
-            float s = 0.f, ss = 0.f;
-#pragma unroll 1
-            for (int c = 0; c < 4; ++c) {
-              float x[32];
-              tmem_ld32(taddr + c * 32, x);
-              tmem_ld_wait32(x);
-              if (mt == 1 && c == 3) {  // D1 drained: the next item's layer-1 MMAs may overwrite it
-                tc_fence_before();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(bar_d1_empty);
-              }
-#pragma unroll
-              for (int q = 0; q < 32; q += 2) {
-                x[q] += add; x[q + 1] += add;
-                s += x[q]; s += x[q + 1];
-                ss = fmaf(x[q], x[q], ss); ss = fmaf(x[q + 1], x[q + 1], ss);
-              }
-              const long long r64 = row0 + (c >> 1) * 64;  // first global row of this 64-point half
-              float4* dst = reinterpret_cast<float4*>(p.a1t) + ((r64 >> 2) + (c & 1) * 8) * 512 + ch;
-#pragma unroll
-              for (int q = 0; q < 8; ++q)
-                st_a1(dst + q * 512, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]), p.a1_keep);
-              if (c & 1) {  // GroupNorm-1 partial sums per 64 points and 8-channel group
-                s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-                s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-                s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-                if ((lane & 7) == 0) {
-                  const long long o = ((r64 >> 6) * 64 + (ch >> 3)) * 2;
-                  p.stats[o] = s;
-                  p.stats[o + 1] = ss;
-                }
-                s = 0.f; ss = 0.f;
-              }
-            }
-          }
-        }
-      } else {
+      // E1(j): lane = output channel of m-tile mt (thread = channel, the item's 128 points are its TMEM columns).
       const int mt = (warp - 2 - RF_EW) >> 2;
+      const int t1 = (int)threadIdx.x - (64 + 32 * RF_EW);  // 0 .. 255 within the E1 group
       for (int j = 0; j < n_items; ++j) {
         const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
         const long long row0 = (long long)tile * 128;
+        const int b = (int)(row0 / P), tile_in_obj = (int)((row0 - (long long)b * P) >> 7);
         const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
         const float add = p.bias1[ch];
+        // (the previous item's readers of s_wp / s_grp / s_part finished before pass2_done(j-1), which this group waited for)
+        if (t1 < 128) s_wp[t1] = __ldg(p.wp + (long long)h * P + (row0 - (long long)b * P) + t1);
         while (!mbar_try_wait(bar_d1_full, (uint32_t)j & 1)) __nanosleep(64);  // idle most of the time: poll politely
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128);
-        float s = 0.f, ss = 0.f;
-#pragma unroll 1
-        for (int c = 0; c < 4; ++c) {
-          float x[32];
-          tmem_ld32(taddr + c * 32, x);
-          tmem_ld_wait32(x);
-          if (c == 3) {  // D1 drained: the next item's layer-1 MMAs may overwrite it
-            tc_fence_before();
-            __syncwarp();
-            if (lane == 0) mbar_arrive(bar_d1_empty);
-          }
+        // ---- pass 1: GroupNorm-1 partial sums of y = D1 + b1 over the item's 128 points (four independent chains per sum,
+        //      16-column chunks, the tcgen05.ld of the next chunk in flight)
+        {
+          float xa[16], xb[16];
+          float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
+          tmem_ld16(taddr, xa);
 #pragma unroll
-          for (int q = 0; q < 32; q += 2) {
-            x[q] += add; x[q + 1] += add;
-            s += x[q]; s += x[q + 1];
-            ss = fmaf(x[q], x[q], ss); ss = fmaf(x[q + 1], x[q + 1], ss);
-          }
-          const long long r64 = row0 + (c >> 1) * 64;  // first global row of this 64-point half
-          float4* dst = reinterpret_cast<float4*>(p.a1t) + ((r64 >> 2) + (c & 1) * 8) * 512 + ch;
+          for (int c = 0; c < 8; ++c) {
+            float* x = (c & 1) ? xb : xa;
+            tmem_ld_wait16(x);
+            if (c + 1 < 8) tmem_ld16(taddr + (c + 1) * 16, (c & 1) ? xa : xb);
 #pragma unroll
-          for (int q = 0; q < 8; ++q)  // streaming stores: a1T is read once, by the next kernel; keep the weights in L2
-            st_a1(dst + q * 512, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]), p.a1_keep);
-          if (c & 1) {  // GroupNorm-1 partial sums per 64 points and 8-channel group
-            s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
-            s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
-            s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
-            if ((lane & 7) == 0) {
-              const long long o = ((r64 >> 6) * 64 + (ch >> 3)) * 2;
-              p.stats[o] = s;
-              p.stats[o + 1] = ss;
+            for (int q = 0; q < 16; ++q) {
+              x[q] += add;
+              s4[q & 3] += x[q];
+              q4[q & 3] = fmaf(x[q], x[q], q4[q & 3]);
             }
-            s = 0.f; ss = 0.f;
+            if (p.a1t != nullptr) {  // debug tap (tests/test_stages_gpu.py)
+              float4* dst = reinterpret_cast<float4*>(p.a1t) + ((row0 >> 2) + c * 4) * 512 + ch;
+#pragma unroll
+              for (int q = 0; q < 4; ++q) dst[q * 512] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+            }
           }
+          float s = (s4[0] + s4[1]) + (s4[2] + s4[3]), ss = (q4[0] + q4[1]) + (q4[2] + q4[3]);
+          s += __shfl_xor_sync(0xffffffffu, s, 1); ss += __shfl_xor_sync(0xffffffffu, ss, 1);
+          s += __shfl_xor_sync(0xffffffffu, s, 2); ss += __shfl_xor_sync(0xffffffffu, ss, 2);
+          s += __shfl_xor_sync(0xffffffffu, s, 4); ss += __shfl_xor_sync(0xffffffffu, ss, 4);
+          if ((lane & 7) == 0)
+            *reinterpret_cast<float2*>(p.stats + (((long long)tile * 64 + (ch >> 3)) * 2)) = make_float2(s, ss);
         }
+        // ---- publish, then (first E1 warp) wait for the other tiles of this (object, head) and finalise the statistics of
+        //      the head's 32 groups: lane = group; fp64 sum of the object's tiles in tile order, biased variance, eps 1e-5
+        named_bar_sync(1, 32 * RF_E1W);  // every E1 thread's sums are written (and s_wp is complete)
+        if (warp == 2 + RF_EW) {
+          int* cnt = p.obj_count + b * 2 + h;
+          if (lane == 0) {
+            // release at GPU scope, cumulative over the sums the other E1 threads wrote before the barrier above
+            asm volatile("red.release.gpu.global.add.s32 [%0], 1;" ::"l"(cnt) : "memory");
+            uint32_t spins = 0;
+            int seen;
+            do {
+              asm volatile("ld.acquire.gpu.global.s32 %0, [%1];" : "=r"(seen) : "l"(cnt) : "memory");
+              if (seen >= tiles_per_obj) break;
+              __nanosleep(32);
+              if (++spins > (1u << 22)) __trap();  // a scheduling bug must fail the launch, not hang the GPU
+            } while (true);
+          }
+          __syncwarp();
+          const float2* st = reinterpret_cast<const float2*>(p.stats) + (long long)b * tiles_per_obj * 64 + h * 32 + lane;
+          double s = 0.0, ss = 0.0;
+          for (int t0 = 0; t0 < tiles_per_obj; t0 += 16) {  // one L2 round trip per 16 tiles
+            float2 v[16];
+#pragma unroll
+            for (int u = 0; u < 16; ++u)  // written by other SMs: read from L2, not L1
+              v[u] = (t0 + u < tiles_per_obj) ? __ldcg(st + (long long)(t0 + u) * 64) : make_float2(0.f, 0.f);
+#pragma unroll
+            for (int u = 0; u < 16; ++u) { s += (double)v[u].x; ss += (double)v[u].y; }
+          }
+          const double n = 8.0 * P, mean = s / n;
+          double var = ss / n - mean * mean;
+          if (var < 0.0) var = 0.0;
+          s_grp[lane] = make_float2((float)(1.0 / sqrt(var + 1e-5)), (float)mean);
+          __syncwarp();
+          if (lane == 0) mbar_arrive(bar_stats_ready);  // release: s_grp and s_wp are visible to the E0 warps that wait
+        }
+        // ---- pass 2: this warp's 32 points (the E0 warps take 48 each); then three threads sum the 24 warps' partial results
+        //      in warp order
+        pass2_cols(j, mt, 96, 2, RF_EW + (warp - 2 - RF_EW));
+        if (t1 < 3) {
+          mbar_wait(bar_pass2_done, (uint32_t)j & 1);
+          float wsum = 0.f;
+          for (int i = 0; i < 128; ++i) wsum += s_wp[i];
+          float sum = 0.f;
+          for (int w = 0; w < RF_EW + RF_E1W; ++w) sum += s_part[w * 3 + t1];
+          p.partial[((long long)b * tiles_per_obj + tile_in_obj) * 6 + h * 3 + t1] = fmaf(__ldg(p.neck_b + h * 3 + t1), wsum, sum);
+        }
+        named_bar_sync(1, 32 * RF_E1W);  // s_wp / s_part / s_grp may be rewritten for the next item
       }
-      }  // VAR != 2
     }
   }
   tc_fence_before();
@@ -470,30 +458,21 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   }
 }
 
-template <int NPROD, int VAR>
-cudaError_t rot_fused_launch_v(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo, const CUtensorMap& w0_hi,
+template <int NPROD>
+cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo, const CUtensorMap& w0_hi,
                              const CUtensorMap& w0_lo, const CUtensorMap& w1_hi, const CUtensorMap& w1_lo,
                              const RotFusedP& p, int num_sms, cudaStream_t s) {
-  auto kern = rot_fused_kernel<NPROD, VAR>;
+  auto kern = rot_fused_kernel<NPROD>;
   static bool configured = false;
   if (!configured) {
-    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SMEM);
+    cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ROT_SMEM);
     if (st != cudaSuccess) return st;
     configured = true;
   }
   int items = p.tiles * 2;
   int grid = items < num_sms ? items : num_sms;
   if (grid < 1) return cudaSuccess;
-  return launch_pdl(kern, dim3(grid), dim3(RotVar<VAR>::THREADS), (size_t)RF_SMEM, s, pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p);
-}
-// var: epilogue schedule (see RotVar / rot_fused_kernel); every schedule produces the same bits
-template <int NPROD>
-cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo, const CUtensorMap& w0_hi,
-                             const CUtensorMap& w0_lo, const CUtensorMap& w1_hi, const CUtensorMap& w1_lo,
-                             const RotFusedP& p, int num_sms, cudaStream_t s, int var = 0) {
-  if (var == 0) return rot_fused_launch_v<NPROD, 0>(pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p, num_sms, s);
-  if (var == 1) return rot_fused_launch_v<NPROD, 1>(pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p, num_sms, s);
-  return rot_fused_launch_v<NPROD, 2>(pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p, num_sms, s);
+  return launch_pdl(kern, dim3(grid), dim3(ROT_THREADS), (size_t)ROT_SMEM, s, pf_hi, pf_lo, w0_hi, w0_lo, w1_hi, w1_lo, p);
 }
 
 

@@ -5,6 +5,8 @@ behind the heads' normalisations, this test names it.
 
 Tolerance per stage: REL * max(1, max|reference stage|); REL = 1e-5 (fp32 mode) / 3e-5 (f16x3: operands carry 22
 significand bits, products are accumulated in fp32)."""
+import os
+
 import pytest
 import torch
 import torch.nn.functional as F
@@ -37,7 +39,11 @@ def test_every_stage_matches_the_oracle(prec):
     S = 2 * B
     w = synth.load_weights()
     b = synth.make_batch(B, N, seed=5)
-    eng = engine.Engine(N, B, prec, 0)
+    os.environ["CATRE_DEBUG_TAPS"] = "1"  # read at catre_create: the tensor-core modes then keep a copy of the rot layer-1 output
+    try:
+        eng = engine.Engine(N, B, prec, 0)
+    finally:
+        del os.environ["CATRE_DEBUG_TAPS"]
     eng.load_weights(w)
     d = b.to("cuda")
     poses, scales = eng.refine(d.pcl, d.prior, d.init_pose, d.init_scale, d.K, 1)

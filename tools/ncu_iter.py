@@ -16,7 +16,7 @@ ORDER = [("update_points", "update_points_kernel"), ("front3", "front3_split"), 
          ("front3", "front3_split"), ("fstn_conv1", "tc_gemm_kernel<1, 2, 64"), ("fstn_conv3_max", "enc_fused"), ("tnet_fc", "fc_chain"),
          ("tnet_fc", "fc_tiled"), ("feat_transform", "tc_gemm_kernel<1, 5, 64"), ("conv2", "tc_gemm_kernel<1, 2, 128"),
          ("conv3", "tc_gemm_kernel<1, 2, 128"), ("conv4_max", "tc_gemm_kernel<0, 0, 256"), ("rot_gfeat", "fc_chain"), ("ts_pose", "ts_head"),
-         ("rot_layer0", "tc_gemm_kernel<0, 3, 256"), ("gn_finalize", "gn_finalize_set"), ("rot_fused", "rot_fused"), ("rot_tail", "rot_tail_t"),
+         ("rot_layer0", "tc_gemm_kernel<0, 3, 256"), ("gn_finalize", "gn_finalize_set"), ("rot_fused", "rot_fused"),
          ("ts_pose", "pose_update")]
 
 rep, batch = sys.argv[1], sys.argv[2]
