@@ -15,7 +15,7 @@ No CPU fallback: needs the CUDA library and a device.
 from __future__ import annotations
 
 import ctypes
-from typing import Optional, Tuple
+from typing import List, Optional, Sequence, Tuple
 
 import torch
 
@@ -83,30 +83,51 @@ def select_ball_points(depth: torch.Tensor, K, masks: torch.Tensor, poses: torch
     return sel_pix, n_sel
 
 
-def sample_object_clouds(depth: torch.Tensor, K, masks: torch.Tensor, poses: torch.Tensor, scales: torch.Tensor,
-                         num_points: int = 1024, ratio: float = 0.6,
-                         generator: Optional[torch.Generator] = None) -> torch.Tensor:
-    """``test_insts.pcl`` for one image: [B, num_points, 3] fp32 on the GPU (data_loader.py:773-799)."""
+def sample_object_clouds_batch(items: Sequence[Tuple[torch.Tensor, object, torch.Tensor, torch.Tensor, torch.Tensor]],
+                               num_points: int = 1024, ratio: float = 0.6,
+                               generator: Optional[torch.Generator] = None) -> List[torch.Tensor]:
+    """``test_insts.pcl`` for SEVERAL images per call: ``items`` = [(depth, K, masks, poses, scales), ...] in loader order;
+    returns one [B_i, num_points, 3] fp32 CUDA tensor per image.
+
+    One call was host-bound (the kernels take a few microseconds; the device->host read of the point counts, the sample
+    upload and a dozen small torch calls per image dominate), so the per-image costs that do not depend on the image are paid
+    once per call here: every image's selection kernels are enqueued first, then ONE device->host copy brings all counts, the
+    random draws run on the host in the reference's order -- image by image, object by object, one ``torch.randperm`` each on
+    the same generator, so ``torch.manual_seed(s)`` still reproduces the reference's clouds bit for bit -- and ONE pinned
+    upload carries every object's sample indices."""
     lib = _engine.load_library()
-    sel_pix, n_sel = select_ball_points(depth, K, masks, poses, scales, ratio)
-    dev = sel_pix.device
-    B = int(n_sel.shape[0])
-    H, W = depth.shape
-    counts = n_sel.cpu().tolist()  # the one host sync: the draw below depends on the counts
-    sample = torch.empty((B, num_points), dtype=torch.int64)
-    for b, n in enumerate(counts):  # instance order, one randperm per object: the reference's RNG call sequence
+    sel = [select_ball_points(depth, K, masks, poses, scales, ratio) for depth, K, masks, poses, scales in items]
+    if not sel:
+        return []
+    dev = sel[0][0].device
+    counts = torch.cat([n for _, n in sel]).cpu().tolist()  # the one host sync: the draws below depend on the counts
+    sample = torch.empty((len(counts), num_points), dtype=torch.int64, pin_memory=True)
+    for b, n in enumerate(counts):  # loader order, instance order, one randperm per object: the reference's RNG call sequence
         if n == 0:
-            raise ValueError(f"object {b} has no valid depth pixel under its mask")
+            raise ValueError(f"object {b} of the call has no valid depth pixel under its mask")
         length = n
         while length < num_points:  # `while len(idx) < num_points: idx = cat([idx, idx])` (cat_data_utils.py:297-298)
             length *= 2
         sample[b] = torch.randperm(length, generator=generator)[:num_points]
-    sample_d = sample.pin_memory().to(dev, non_blocking=True)
-    depth_d = depth.to(dev, torch.float32).contiguous()
-    pcl = torch.empty((B, num_points, 3), dtype=torch.float32, device=dev)
+    sample_d = sample.to(dev, non_blocking=True)
     stream = ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
-    rc = lib.catre_cloud_gather(depth_d.data_ptr(), _intr(K), sel_pix.data_ptr(), n_sel.data_ptr(), sample_d.data_ptr(), B, H, W,
-                                num_points, pcl.data_ptr(), stream)
-    if rc != 0:
-        raise _engine.CatreError(f"catre_cloud_gather failed ({rc}): {lib.catre_last_error(None).decode()}")
-    return pcl
+    out, lo = [], 0
+    for (depth, K, masks, poses, scales), (sel_pix, n_sel) in zip(items, sel):
+        B = int(n_sel.shape[0])
+        H, W = depth.shape
+        depth_d = depth.to(dev, torch.float32).contiguous()
+        pcl = torch.empty((B, num_points, 3), dtype=torch.float32, device=dev)
+        rc = lib.catre_cloud_gather(depth_d.data_ptr(), _intr(K), sel_pix.data_ptr(), n_sel.data_ptr(),
+                                    sample_d[lo:lo + B].data_ptr(), B, H, W, num_points, pcl.data_ptr(), stream)
+        if rc != 0:
+            raise _engine.CatreError(f"catre_cloud_gather failed ({rc}): {lib.catre_last_error(None).decode()}")
+        out.append(pcl)
+        lo += B
+    return out
+
+
+def sample_object_clouds(depth: torch.Tensor, K, masks: torch.Tensor, poses: torch.Tensor, scales: torch.Tensor,
+                         num_points: int = 1024, ratio: float = 0.6,
+                         generator: Optional[torch.Generator] = None) -> torch.Tensor:
+    """``test_insts.pcl`` for one image: [B, num_points, 3] fp32 on the GPU (data_loader.py:773-799)."""
+    return sample_object_clouds_batch([(depth, K, masks, poses, scales)], num_points, ratio, generator)[0]

@@ -181,6 +181,11 @@ class CrossImageRefiner:
         if int(batch["obj_cls"].shape[0]) == 0 or not _filter_labels(self.evaluator, batch, "cpu"):
             return  # nothing to refine for this item (the reference `continue`s)
         n_obj = int(batch["obj_cls"].shape[0])
+        # never let a launch grow past objects_per_launch (normally the engine's max_batch): the engine would split it into a
+        # full chunk plus a few-object chunk, and a few-object K-loop is latency-bound (1 ms for 8 objects, as long as 20 of
+        # a full launch's objects) -- launch what is pending first
+        if self.pending and self.pending_objs + n_obj > self.objects_per_launch:
+            self.flush()
         self.pending.append(_Pending(inputs, batch, n_obj, time.perf_counter() - t0))
         self.pending_objs += n_obj
         if self.pending_objs >= self.objects_per_launch:

@@ -110,3 +110,23 @@ def test_cuda_producer_full_resolution_vs_oracle():
     assert torch.equal(got.cpu(), want)
     with pytest.raises(ValueError):
         cloud.sample_object_clouds(depth, K, torch.zeros_like(masks[:1]), poses[:1], scales[:1], 1024)
+
+
+@pytest.mark.gpu
+def test_batched_call_equals_the_per_image_sequence():
+    """Several images per call (one count read-back, one sample upload): the same clouds, bit for bit, as the per-image calls in
+    loader order -- the host draws stay in the reference's order on the same generator."""
+    scenes = [load_scene(0), load_scene(1), load_scene(0)]
+    items = [(d, K, m, p, s) for d, K, m, p, s, *_ in scenes]
+    torch.manual_seed(123)
+    one_by_one = [cloud.sample_object_clouds(*it, 1024) for it in items]
+    torch.manual_seed(123)
+    batched = cloud.sample_object_clouds_batch(items, 1024)
+    assert len(batched) == len(one_by_one)
+    for a, b in zip(batched, one_by_one):
+        assert torch.equal(a, b)
+    # and against the CPU oracle run image by image with the same seed
+    torch.manual_seed(123)
+    for it, got in zip(items, batched):
+        assert torch.equal(got.cpu(), co.sample_clouds(*it, 1024))
+    assert cloud.sample_object_clouds_batch([], 1024) == []

@@ -115,8 +115,9 @@ def test_cross_image_batching_feeds_evaluator_like_the_reference():
     model, rec = StubModel(), Recorder()
     res, st = ev.catre_inference_on_dataset(CFG, model, loader, rec, objects_per_launch=8, device="cpu", return_stats=True)
     assert res == {} and rec.was_reset
-    # launches: 3+5 -> 8 | 1+4+2+6=13 (crosses the threshold on the last item) ; the empty image is never queued
-    assert model.calls == [8, 13] and st.launches == 2 and st.objects == 21 and st.images == 7
+    # a launch never exceeds objects_per_launch: 3+5 -> 8 | 1+4+2 = 7 (the next image's 6 would not fit) | 6 ; the empty image
+    # is never queued
+    assert model.calls == [8, 7, 6] and st.launches == 3 and st.objects == 21 and st.images == 7
     assert len(rec.calls) == 6  # once per non-empty loader item, in loader order
     ref_p, ref_s = StubModel().refine(b.pcl, b.prior, b.init_pose, b.init_scale, b.K, N_ITER)
     lo = 0

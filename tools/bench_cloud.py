@@ -66,11 +66,24 @@ def main():
         cloud.select_ball_points(dd, K, md, poses, scales)
     b.record(); torch.cuda.synchronize()
     sel_ms = a.elapsed_time(b) / reps
+    # several images per call (one count read-back and one sample upload per call)
+    batch_ms = {}
+    for nb in (4, 16):
+        items = [(depth, K, masks, poses, scales)] * nb
+        cloud.sample_object_clouds_batch(items, 1024)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(max(2, reps // nb)):
+            cloud.sample_object_clouds_batch(items, 1024)
+        torch.cuda.synchronize()
+        batch_ms[nb] = (time.perf_counter() - t0) / (max(2, reps // nb) * nb) * 1e3
     px_bytes = n_obj * 480 * 640 * (4 + 1) * 2  # depth + mask read by the histogram and the compaction pass
     print(json.dumps({"workload": "480x640 depth, 6 objects, NUM_PCL=1024", "bit_exact_vs_cpu": exact,
                       "cpu_reference_loop_ms_per_image": round(cpu_ms, 3), "cpu_threads": torch.get_num_threads(),
                       "cuda_producer_ms_per_image_host_inputs": round(gpu_ms, 3),
                       "cuda_producer_ms_per_image_resident_inputs": round(gpu_res_ms, 3),
+                      "cuda_producer_ms_per_image_host_inputs_4_images_per_call": round(batch_ms[4], 3),
+                      "cuda_producer_ms_per_image_host_inputs_16_images_per_call": round(batch_ms[16], 3),
                       "select_call_ms_incl_host_radii": round(sel_ms, 4),
                       "select_algorithmic_bytes": px_bytes,
                       "speedup_vs_cpu_host_inputs": round(cpu_ms / gpu_ms, 2)}))
