@@ -30,13 +30,18 @@
 namespace catre {
 
 constexpr int RF_EW = 16;                       // epilogue warps of enc_fused_kernel; E0 (GELU) warps of rot_fused_kernel
-constexpr int RF_E1W = 8;                       // rot_fused_kernel: warps that drain D1 (concurrently with the E0 warps)
+constexpr int RF_E1W = 8;                       // rot_fused_kernel: E1 warps (pass 1 of the tail + the exchange between CTAs)
 constexpr int RF_THREADS = 64 + 32 * RF_EW;
 constexpr int RF_SLOT = 32 * 1024;
 constexpr int RF_SLOTS = 3;
 constexpr int RF_U_BYTES = 128 * 1024;
 constexpr int RF_SMEM = 1024 + 1024 + RF_U_BYTES + RF_SLOTS * RF_SLOT;  // barriers + alignment slack + U + ring
-constexpr int ROT_SMEM = 2048 + 1024 + RF_U_BYTES + RF_SLOTS * RF_SLOT; // rot_fused_kernel: 2 KB of barriers + tail scratch (= 227 KB)
+// rot_fused_kernel: 2 KB of barriers + tail scratch | U = a ring of two K-slab buffers (hi | lo, 32 KB each) | TMA ring of 5 slots.
+// (Round 2a kept all four slabs of an item in U and had 3 ring slots: the layer-1 phase then waited for weight tiles -- 384 KB
+// of W0 / W1 / pf per item through a ring that shallow -- for longer than its MMAs took, profiles/r02_rot_fused_timeline.txt.)
+constexpr int ROT_SLOTS = 5;
+constexpr int ROT_U_BYTES = 64 * 1024;
+constexpr int ROT_SMEM = 2048 + 1024 + ROT_U_BYTES + ROT_SLOTS * RF_SLOT;  // = 227 KB
 
 struct RotFusedP {
   int tiles;             // R / 128
@@ -89,15 +94,17 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = smem_u32(smem_raw);
   const uint32_t u_base = (smem_base + 2048 + 1023) & ~1023u;  // barriers and the tail's scratch live in the first 2 KB
-  const uint32_t ring_base = u_base + RF_U_BYTES;
-  // barriers (8 B each): full[3] empty[3] d0_full[2] d0_empty[2] d1_full d1_empty u_full[4], TMEM base slot, stats_ready, pass2_done
-  const uint32_t bar_full = smem_base, bar_empty = smem_base + 24;
-  const uint32_t bar_d0_full = smem_base + 48, bar_d0_empty = smem_base + 64;
-  const uint32_t bar_d1_full = smem_base + 80, bar_d1_empty = smem_base + 88;
-  const uint32_t bar_u_full = smem_base + 96;  // 4 barriers
-  const uint32_t tmem_slot = smem_base + 128;
-  const uint32_t bar_stats_ready = smem_base + 136, bar_pass2_done = smem_base + 144;
-  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + 128);
+  const uint32_t ring_base = u_base + ROT_U_BYTES;
+  // barriers (8 B each): full[5] empty[5] d0_full[2] d0_empty[2] d1_full d1_empty u_full[4], TMEM base slot, stats_ready,
+  // pass2_done, u_empty[2]
+  const uint32_t bar_full = smem_base, bar_empty = smem_base + 40;
+  const uint32_t bar_d0_full = smem_base + 80, bar_d0_empty = smem_base + 96;
+  const uint32_t bar_d1_full = smem_base + 112, bar_d1_empty = smem_base + 120;
+  const uint32_t bar_u_full = smem_base + 128;  // 4 barriers (one per K slab of an item)
+  const uint32_t tmem_slot = smem_base + 160;
+  const uint32_t bar_stats_ready = smem_base + 168, bar_pass2_done = smem_base + 176;
+  const uint32_t bar_u_empty = smem_base + 184;  // 2 barriers (one per U buffer)
+  volatile uint32_t* tmem_slot_ptr = reinterpret_cast<volatile uint32_t*>(smem_raw + 160);
   // tail scratch: conv_p weights of the item's 128 points | GroupNorm-1 (rstd, mean) of the head's 32 groups | per-warp neck
   // partials [24][3]
   float* s_wp = reinterpret_cast<float*>(smem_raw + 256);
@@ -112,12 +119,13 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&pf_hi); prefetch_tmap(&w0_hi); prefetch_tmap(&w1_hi);
     if (NPROD == 3) { prefetch_tmap(&pf_lo); prefetch_tmap(&w0_lo); prefetch_tmap(&w1_lo); }
-    for (int i = 0; i < RF_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
+    for (int i = 0; i < ROT_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     // RF_EW warps write U (E0 group), RF_E1W warps drain D1 (E1 group)
     for (int i = 0; i < 2; ++i) { mbar_init(bar_d0_full + 8 * i, 1); mbar_init(bar_d0_empty + 8 * i, RF_EW); }
     mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RF_EW + RF_E1W);  // D1 is released by pass 2 of the tail (all 24 warps)
     mbar_init(bar_stats_ready, 1); mbar_init(bar_pass2_done, RF_EW + RF_E1W);
     for (int i = 0; i < 4; ++i) mbar_init(bar_u_full + 8 * i, RF_EW);
+    for (int i = 0; i < 2; ++i) mbar_init(bar_u_empty + 8 * i, 1);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
   if (warp == 1) tmem_alloc(tmem_slot, 512);
@@ -138,7 +146,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
         const uint32_t sb = ring_base + slot * RF_SLOT, full = bar_full + 8 * slot;
         if (lane == 0) { mbar_expect_tx(full, SLOT_TX); tma_load_2d(sb, hi, c0, c1, full); }
         else tma_load_2d(sb + 16384, lo, c0, c1, full);
-        if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; }
+        if (++slot == ROT_SLOTS) { slot = 0; phase ^= 1; }
       };
       auto load_l0 = [&](int j, int half) {  // point features of the tile + 128 rows of W0p_h
         const int ht = item_ht(j), tile = ht >> 1, h = ht & 1;
@@ -163,7 +171,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
     if (lane == 0 && n_items > 0) {
       constexpr uint32_t idesc = umma_idesc<TcOperand<NPROD>::F16>(128, 128);
       int slot = 0; uint32_t phase = 0;
-      auto next = [&]() { if (++slot == RF_SLOTS) { slot = 0; phase ^= 1; } };
+      auto next = [&]() { if (++slot == ROT_SLOTS) { slot = 0; phase ^= 1; } };
       // L0(j, half): D0[half] = pf . W0p_h[half*128 ..]^T   (K = 64: 4 k-steps, N = 128)
       auto L0 = [&](int j, int half) {
         mbar_wait(bar_d0_empty + 8 * half, ((uint32_t)j & 1) ^ 1);  // E0(j-1) has drained this half of D0
@@ -197,7 +205,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
         for (int ks = half * 2; ks < half * 2 + 2; ++ks) {
           mbar_wait(bar_u_full + 8 * ks, par);
           tc_fence_after();
-          const uint32_t u_hi = u_base + ks * 32768, u_lo = u_hi + 16384;
+          const uint32_t u_hi = u_base + (ks & 1) * 32768, u_lo = u_hi + 16384;
           for (int mt = 0; mt < 2; ++mt) {
             mbar_wait(bar_full + 8 * slot, phase);
             tc_fence_after();
@@ -215,6 +223,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
             umma_commit(bar_empty + 8 * slot);
             next();
           }
+          umma_commit(bar_u_empty + 8 * (ks & 1));  // E0 may refill this U buffer once these MMAs have read it
         }
         if (half == 1) umma_commit(bar_d1_full);
       };
@@ -303,11 +312,13 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
         const int set = set_of_row((long long)tile * 128, p.rows_per_obj, p.rows_per_set);
         const float* scp = p.gn_scale + (long long)set * 512 + h * 256;
         const float* shp = p.gn_shift + (long long)set * 512 + h * 256;
-        bool tail_done = (j == 0);  // PASS2(j-1) runs before the first slab of E0(j) whose turn finds the statistics there
+        bool tail_done = (j == 0);
 #pragma unroll 1
         for (int ks = 0; ks < 4; ++ks) {
           const int half = ks >> 1;
-          if (!tail_done && mbar_try_wait(bar_stats_ready, (uint32_t)(j - 1) & 1)) { pass2(j - 1); tail_done = true; }
+          // PASS2(j-1): as soon as its statistics are there, and at the latest before slab 2 -- slab 2 reuses the U buffer of
+          // slab 0, i.e. it waits for the layer-1 MMAs of THIS item, which wait for D1, which PASS2(j-1) releases
+          if (!tail_done && (ks == 2 || mbar_try_wait(bar_stats_ready, (uint32_t)(j - 1) & 1))) { pass2(j - 1); tail_done = true; }
           if ((ks & 1) == 0) {
             mbar_wait(bar_d0_full + 8 * half, (uint32_t)j & 1);
             tc_fence_after();
@@ -338,8 +349,11 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
               split16x2<TcOperand<NPROD>::F16>(g0, g1, hi[2 * q], lo[2 * q]);
               split16x2<TcOperand<NPROD>::F16>(g2, g3, hi[2 * q + 1], lo[2 * q + 1]);
             }
+            // U is a ring of two slab buffers (slab ks -> buffer ks & 1): its previous occupant, two slabs ago, must have been
+            // read by the layer-1 MMAs (use m of a buffer waits for the completion of use m - 1; the first use passes)
+            mbar_wait(bar_u_empty + 8 * (ks & 1), (uint32_t)((2 * j + (ks >> 1)) & 1) ^ 1);
             // two 16-byte chunks (8 channels each) of this row, 128B-swizzled: chunk' = chunk ^ (row & 7)
-            const uint32_t slab = u_base + ks * 32768 + row_off;
+            const uint32_t slab = u_base + (ks & 1) * 32768 + row_off;
             const uint32_t c0 = (uint32_t)(part * 2), sw = (uint32_t)(lane_row & 7);
             st_shared_v4(slab + (((c0 + 0) ^ sw) << 4), hi[0], hi[1], hi[2], hi[3]);
             st_shared_v4(slab + (((c0 + 1) ^ sw) << 4), hi[4], hi[5], hi[6], hi[7]);
@@ -352,7 +366,6 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
           __syncwarp();
           if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
         }
-        if (!tail_done) pass2(j - 1);
       }
       if (n_items > 0) pass2(n_items - 1);
     } else {
