@@ -433,8 +433,11 @@ int tnet_fc_chain(catre_engine* e, cudaStream_t s, const int* keys, int S, int w
 }
 
 // One refinement iteration on a chunk of B objects whose points are already in e->q.
+// head_done: the iteration's head kernel (iter_head_kernel) has already run stn.conv1.  defer_pose != nullptr: do not launch
+// pose_update_kernel; return its arguments instead -- the next iteration's head kernel updates the pose itself.
 int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, const float* scale_in, const float* K,
-              float* pose_out, float* scale_out, const int* prior_cls = nullptr, int n_cls = 0) {
+              float* pose_out, float* scale_out, const int* prior_cls = nullptr, int n_cls = 0, bool head_done = false,
+              TsPoseP* defer_pose = nullptr) {
   const int N = e->N, S = 2 * B, P = e->N + e->Np;
   const long long R = (long long)B * P;
   int rc;
@@ -448,7 +451,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
 
   // ---- E1: STN3d (pointnets/pointnet.py:24-41)
   if (tc) {
-    if ((rc = tc_front(e, s, nullptr, "pcl_net.stn.conv1", R))) return rc;
+    if (!head_done && (rc = tc_front(e, s, nullptr, "pcl_net.stn.conv1", R))) return rc;
     if ((rc = tc_tnet_trunk(e, s, G_STN_CONV3_MAX, e->x64, e->tw_stn_c2, W(e, "pcl_net.stn.conv2.bias"), e->tw_stn_c3,
                             W(e, "pcl_net.stn.conv3.bias"), e->gmax_stn, R))) return rc;
   } else {
@@ -642,11 +645,33 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
 
   // ---- G1 + G2 after both heads: join the side stream, then rot6d Gram-Schmidt + pose update
   CU_TRY(e, cudaStreamWaitEvent(s, e->ev_join, 0));
+  if (defer_pose != nullptr) {
+    *defer_pose = tsp;
+    return 0;
+  }
   {
     Launch l(e, s, G_TS_POSE);
     launch_pdl(pose_update_kernel, dim3((B + 7) / 8), dim3(256), (size_t)(0), s, tsp, B);
   }
   return check_launch(e, "pose_update");
+}
+
+// Head of an iteration in the tensor-core modes: [previous iteration's pose update] + point update + stn.conv1, one launch.
+int iter_head(catre_engine* e, cudaStream_t s, int B, const TsPoseP* prev, const float* pose, const float* scale, const float* pcl,
+              const float* prior, const int* cls, int n_cls) {
+  IterHeadP h{};
+  if (prev) { h.prev = *prev; h.have_prev = 1; }
+  h.pose = pose; h.scale = scale; h.pcl = pcl; h.prior = prior; h.cls = cls; h.n_cls = n_cls;
+  h.q = e->q; h.gmax = e->gmax_all; h.n_keys = (long long)(2 * B) * (1024 * 3 + 64);
+  h.W = W(e, "pcl_net.stn.conv1.weight"); h.bias = W(e, "pcl_net.stn.conv1.bias");
+  h.out_hi = e->x64.hi; h.out_lo = e->x64.lo; h.B = B; h.N = e->N; h.Np = e->Np;
+  const long long R = (long long)B * (e->N + e->Np);
+  {
+    Launch l(e, s, G_FRONT3);
+    launch_pdl(e->cfg.precision == CATRE_PREC_F16X3 ? iter_head_kernel<true> : iter_head_kernel<false>, dim3((unsigned)(R / FRONT_PTS)),
+               dim3(256), (size_t)0, s, h);
+  }
+  return check_launch(e, "iter_head");
 }
 
 int check_ready(catre_engine* e, int B) {
@@ -1074,11 +1099,22 @@ static int refine_impl(catre_engine* e, const float* pcl, const float* prior, co
     int Bc = (B - b0 < e->maxB) ? B - b0 : e->maxB;
     long long total = (long long)Bc * (N + e->Np);
     const int* pc_chunk = prior_cls ? (const int*)prior_cls + b0 : (const int*)nullptr;
+    const bool fused_head = e->cfg.precision != CATRE_PREC_FP32_SIMT;
+    TsPoseP prev{};
     for (int it = 1; it <= n_iter; ++it) {
       const float* pin = out_poses + ((size_t)(it - 1) * B + b0) * 12;
       const float* sin = out_scales + ((size_t)(it - 1) * B + b0) * 3;
       float* pout = out_poses + ((size_t)it * B + b0) * 12;
       float* sout = out_scales + ((size_t)it * B + b0) * 3;
+      if (fused_head) {
+        // tensor-core modes: the previous iteration's pose update, the point update and stn.conv1 are one launch; only the
+        // last iteration ends with pose_update_kernel
+        const float* pr = prior_cls ? prior : prior + (size_t)b0 * e->Np * 3;
+        if ((rc = iter_head(e, s, Bc, it > 1 ? &prev : nullptr, pin, sin, pcl + (size_t)b0 * N * 3, pr, pc_chunk, (int)n_cls))) return rc;
+        if ((rc = iteration(e, s, Bc, pin, sin, K + (size_t)b0 * 9, pout, sout, pc_chunk, (int)n_cls, true, it < n_iter ? &prev : nullptr)))
+          return rc;
+        continue;
+      }
       {
         Launch l(e, s, G_UPDATE_POINTS);
         const float* pr = prior_cls ? prior : prior + (size_t)b0 * e->Np * 3;

@@ -802,12 +802,10 @@ __global__ void __launch_bounds__(256) ts_head_kernel(TsPoseP p) {
   if (t < 6) p.dts[(long long)b * 6 + t] = outv[t];
 }
 
-__global__ void __launch_bounds__(256) pose_update_kernel(TsPoseP p, int B) {
-  pdl_wait();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int b = blockIdx.x * 8 + warp;
-  if (b >= B) return;
-  // rot-head partial sums [tiles][6]: lanes stride over the tiles (fixed order), butterfly sum
+// G1 + G2 for object b, executed by ONE WARP: the two heads' 3-vectors from the rot partial sums (lanes stride over the tiles
+// in fixed order, butterfly sum), rot6d Gram-Schmidt, pose update.  Lane 0 ends up with the new pose in Pout[12] / So[3]
+// (registers or shared memory of the caller); nothing is written to global memory here.
+__device__ __forceinline__ void pose_update_warp(const TsPoseP& p, int b, int lane, float* Pout, float* So) {
   float r6[6];
 #pragma unroll
   for (int j = 0; j < 6; ++j) {
@@ -834,7 +832,6 @@ __global__ void __launch_bounds__(256) pose_update_kernel(TsPoseP p, int B) {
     float y2 = z0 * x1 - z1 * x0;
     float dR[9] = {x0, y0, z0, x1, y1, z1, x2, y2, z2};
     const float* Pin = p.pose_in + (long long)b * 12;
-    float* Pout = p.pose_out + (long long)b * 12;
     float Rin[9] = {Pin[0], Pin[1], Pin[2], Pin[4], Pin[5], Pin[6], Pin[8], Pin[9], Pin[10]};
     float tin[3] = {Pin[3], Pin[7], Pin[11]};
     float Ro[9];
@@ -848,7 +845,6 @@ __global__ void __launch_bounds__(256) pose_update_kernel(TsPoseP p, int B) {
     Pout[0] = Ro[0]; Pout[1] = Ro[1]; Pout[2] = Ro[2]; Pout[3] = xt;
     Pout[4] = Ro[3]; Pout[5] = Ro[4]; Pout[6] = Ro[5]; Pout[7] = yt;
     Pout[8] = Ro[6]; Pout[9] = Ro[7]; Pout[10] = Ro[8]; Pout[11] = zt;
-    float* So = p.scale_out + (long long)b * 3;
     So[0] = sc_in[0] + outv[3];
     So[1] = sc_in[1] + outv[4];
     So[2] = sc_in[2] + outv[5];
@@ -870,6 +866,22 @@ __global__ void __launch_bounds__(256) pose_update_kernel(TsPoseP p, int B) {
       for (int i = 0; i < 12; ++i) Pout[i] = qnan;
       So[0] = So[1] = So[2] = qnan;
     }
+  }
+}
+
+__global__ void __launch_bounds__(256) pose_update_kernel(TsPoseP p, int B) {
+  pdl_wait();
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int b = blockIdx.x * 8 + warp;
+  if (b >= B) return;
+  float Pn[12], Sn[3];
+  pose_update_warp(p, b, lane, Pn, Sn);
+  if (lane == 0) {
+    float* Pout = p.pose_out + (long long)b * 12;
+    float* So = p.scale_out + (long long)b * 3;
+#pragma unroll
+    for (int i = 0; i < 12; ++i) Pout[i] = Pn[i];
+    So[0] = Sn[0]; So[1] = Sn[1]; So[2] = Sn[2];
   }
 }
 

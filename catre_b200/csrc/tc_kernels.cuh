@@ -613,6 +613,108 @@ __global__ void __launch_bounds__(256) front3_split_kernel(const float* __restri
   }
 }
 
+// Head of a refinement iteration in one launch (tensor-core modes): [pose update of the previous iteration] + U1 point update +
+// stn.conv1.  The three were separate latency-bound launches on the critical path between two tensor-core kernels
+// (pose_update_kernel: 8 blocks; update_points_kernel; front3_split_kernel); here every block of 128 points recomputes the pose
+// of its object from the heads' outputs (a few hundred flops, same code as pose_update_kernel: pose_update_warp), the block
+// that holds the object's first points stores it, and the re-posed points go to q (the second front layer reads them) and
+// straight into stn.conv1.
+struct IterHeadP {
+  TsPoseP prev;        // the previous iteration's heads -> pose (used when have_prev; its pose_out / scale_out are THIS iteration's pose)
+  int have_prev;       // 0: first iteration of a call, the pose is read from pose / scale
+  const float* pose;   // [B, 12] / [B, 3] current pose when !have_prev
+  const float* scale;
+  const float* pcl; const float* prior; const int* cls; int n_cls;
+  float* q; int* gmax; long long n_keys;
+  const float* W; const float* bias;  // stn.conv1 [64, 3], [64]
+  __nv_bfloat16* out_hi; __nv_bfloat16* out_lo;
+  int B, N, Np;
+};
+template <bool F16>
+__global__ void __launch_bounds__(256) iter_head_kernel(const IterHeadP p) {
+  __shared__ float sW[64 * 3];
+  __shared__ float sB[64];
+  __shared__ float sQ[FRONT_PTS * 3];
+  __shared__ float sPose[12], sScale[3];
+  const int P = p.N + p.Np;
+  const long long r0 = (long long)blockIdx.x * FRONT_PTS;  // first point of the block (a block never straddles two sets)
+  const int b = (int)(r0 / P), rin = (int)(r0 - (long long)b * P);
+  if (threadIdx.x < 192) sW[threadIdx.x] = p.W[threadIdx.x];
+  if (threadIdx.x >= 192) sB[threadIdx.x - 192] = p.bias[threadIdx.x - 192];
+  pdl_wait();  // weights above are constants; everything below comes from upstream kernels
+  if (threadIdx.x < 32) {
+    if (p.have_prev) {
+      float Pn[12], Sn[3];
+      pose_update_warp(p.prev, b, (int)threadIdx.x, Pn, Sn);
+      if (threadIdx.x == 0) {
+#pragma unroll
+        for (int i = 0; i < 12; ++i) sPose[i] = Pn[i];
+        sScale[0] = Sn[0]; sScale[1] = Sn[1]; sScale[2] = Sn[2];
+        if (rin == 0) {  // one block per object publishes the pose of the finished iteration
+          float* Po = p.prev.pose_out + (long long)b * 12;
+          float* So = p.prev.scale_out + (long long)b * 3;
+#pragma unroll
+          for (int i = 0; i < 12; ++i) Po[i] = Pn[i];
+          So[0] = Sn[0]; So[1] = Sn[1]; So[2] = Sn[2];
+        }
+      }
+    } else {
+      if (threadIdx.x < 12) sPose[threadIdx.x] = p.pose[(long long)b * 12 + threadIdx.x];
+      if (threadIdx.x < 3) sScale[threadIdx.x] = p.scale[(long long)b * 3 + threadIdx.x];
+    }
+  }
+  // reset this iteration's column-max keys (as update_points_kernel does)
+  for (long long k = (long long)blockIdx.x * 256 + threadIdx.x; k < p.n_keys; k += (long long)gridDim.x * 256) p.gmax[k] = KEY_NEG_INF;
+  __syncthreads();
+  if (threadIdx.x < FRONT_PTS) {  // U1 (batch_test.py:78-97): x = pcl - t ; k = R (s * kps)
+    const int r = rin + (int)threadIdx.x;
+    float o0, o1, o2;
+    if (r < p.N) {
+      const float* v = p.pcl + ((long long)b * p.N + r) * 3;
+      o0 = v[0] - sPose[3]; o1 = v[1] - sPose[7]; o2 = v[2] - sPose[11];
+    } else {
+      int row = b;
+      if (p.cls != nullptr) { row = p.cls[b]; if (row < 0 || row >= p.n_cls) row = 0; }
+      const float* v = p.prior + ((long long)row * p.Np + (r - p.N)) * 3;
+      const float k0 = v[0] * sScale[0], k1 = v[1] * sScale[1], k2 = v[2] * sScale[2];
+      o0 = sPose[0] * k0 + sPose[1] * k1 + sPose[2] * k2;
+      o1 = sPose[4] * k0 + sPose[5] * k1 + sPose[6] * k2;
+      o2 = sPose[8] * k0 + sPose[9] * k1 + sPose[10] * k2;
+    }
+    float* o = p.q + (r0 + threadIdx.x) * 3;
+    o[0] = o0; o[1] = o1; o[2] = o2;
+    sQ[threadIdx.x * 3 + 0] = o0; sQ[threadIdx.x * 3 + 1] = o1; sQ[threadIdx.x * 3 + 2] = o2;
+  }
+  __syncthreads();
+  // stn.conv1 (pointnets/pointnet.py:26), no input transform: as front3_split_kernel with T3 = I
+  const int cg = threadIdx.x & 7;  // channel group (8 channels)
+  float w[8][3], bb[8];
+#pragma unroll
+  for (int j = 0; j < 8; ++j) {
+    bb[j] = sB[cg * 8 + j];
+    w[j][0] = sW[(cg * 8 + j) * 3 + 0]; w[j][1] = sW[(cg * 8 + j) * 3 + 1]; w[j][2] = sW[(cg * 8 + j) * 3 + 2];
+  }
+#pragma unroll
+  for (int it = 0; it < FRONT_PTS / 32; ++it) {
+    const int pl = it * 32 + (threadIdx.x >> 3);
+    const long long r = r0 + pl;
+    const float q0 = sQ[pl * 3 + 0], q1 = sQ[pl * 3 + 1], q2 = sQ[pl * 3 + 2];
+    // the identity transform of front3_split_kernel spelled out with the same operations: x_j = q0*T0j + q1*T1j + q2*T2j
+    const float x0 = q0 * 1.0f + q1 * 0.0f + q2 * 0.0f;
+    const float x1 = q0 * 0.0f + q1 * 1.0f + q2 * 0.0f;
+    const float x2 = q0 * 0.0f + q1 * 0.0f + q2 * 1.0f;
+    uint32_t hi[4], lo[4];
+#pragma unroll
+    for (int j = 0; j < 8; j += 2) {
+      const float v0 = fmaxf(bb[j] + w[j][0] * x0 + w[j][1] * x1 + w[j][2] * x2, 0.0f);
+      const float v1 = fmaxf(bb[j + 1] + w[j + 1][0] * x0 + w[j + 1][1] * x1 + w[j + 1][2] * x2, 0.0f);
+      split16x2<F16>(v0, v1, hi[j >> 1], lo[j >> 1]);
+    }
+    *reinterpret_cast<uint4*>(p.out_hi + (size_t)r * 64 + cg * 8) = make_uint4(hi[0], hi[1], hi[2], hi[3]);
+    *reinterpret_cast<uint4*>(p.out_lo + (size_t)r * 64 + cg * 8) = make_uint4(lo[0], lo[1], lo[2], lo[3]);
+  }
+}
+
 // ------------------------------------------------------------------------------------------------
 // host side: tensor maps and launch
 // ------------------------------------------------------------------------------------------------

@@ -361,3 +361,19 @@ def test_different_observed_and_prior_point_counts(weights, prec):
     x, tfd = catre_oracle.update_points(b.pcl, b.prior, b.init_pose, b.init_scale)
     out = model(x.cuda(), tfd.cuda(), init_pose=b.init_pose.cuda(), init_scale=b.init_scale.cuda(), K_zoom=b.K.cuda(), cur_iter=1)
     assert (out["pose_1"].cpu() - ref_p[1]).abs().max() <= TOL and (out["scale_1"].cpu() - ref_s[1]).abs().max() <= TOL
+
+
+def test_rot_tail_exchange_at_awkward_launch_sizes(weights):
+    """The fused rot kernel exchanges GroupNorm-1 statistics between the CTAs that hold the 16 tiles of an (object, head) through
+    global counters.  Launch sizes around the persistent grid's boundaries -- fewer items than CTAs, items of one
+    object split over two rounds of the grid, one object more than a multiple -- must give, object by object, exactly the bytes
+    of a launch that holds all of them (the exchange is deterministic), must agree with the fp32 CUDA-core mode (which has no
+    such exchange) and must come back at all (a wait that cannot complete traps instead of hanging)."""
+    b = synth.make_batch(150, 1024, seed=93)
+    ref = run_refine(get_engine(weights, 1024, "f16x3", max_batch=256), b, 2)
+    strict = run_refine(get_engine(weights, 1024, "fp32", max_batch=256), b, 2)
+    e = gu.max_abs_err_nan_aware(ref[0], ref[1], strict[0].cpu(), strict[1].cpu())
+    assert max(e) <= 2e-5, e
+    for mb in (1, 2, 4, 9, 37, 74, 75):  # launches of mb objects (32 items each) on the 148-CTA grid: 32 ... 2400 items per launch
+        got = run_refine(get_engine(weights, 1024, "f16x3", max_batch=mb), b, 2)
+        assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), mb
