@@ -128,6 +128,7 @@ struct catre_engine {
   float *fcc_cset = nullptr, *fcc_ts0 = nullptr;
   int trunk_group = 0;  // objects per conv3 -> conv4 group launch (0: the whole batch at once); CATRE_TRUNK_GROUP
   int* rot_count = nullptr;   // [B][2] publication counters of the fused rot kernel (zeroed by gn_finalize_set_kernel)
+  bool fused_tail = false;    // CATRE_ROT_TAIL=fused: the rot tail runs out of TMEM inside the fused rot kernel (no a1T); default: split
   bool debug_taps = false;    // CATRE_DEBUG_TAPS=1: keep optional intermediate copies for catre_debug_read (tests/test_stages_gpu.py)
   int fcc_ranks = 8;  // CTAs per FC-chain cluster (16 where the device co-schedules them), fixed per engine
   TcPair t64s;  // tensor-core modes: bf16 hi/lo of T64^T, [S*64, 64]
@@ -559,7 +560,7 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
     tsp.be1 = W(e, "ts_head.linears.4.bias");
     tsp.wt = W(e, "ts_head.fc_t.weight"); tsp.bt = W(e, "ts_head.fc_t.bias");
     tsp.ws = W(e, "ts_head.fc_s.weight"); tsp.bs = W(e, "ts_head.fc_s.bias");
-    tsp.rot_partial = e->rot_partial; tsp.rot_tiles = P / 128; tsp.convp_bias = e->convp_b;
+    tsp.rot_partial = e->rot_partial; tsp.rot_tiles = (tc && !e->fused_tail) ? 16 : P / 128; tsp.convp_bias = e->convp_b;
     tsp.pose_in = pose_in; tsp.scale_in = scale_in; tsp.K = K; tsp.pose_out = pose_out; tsp.scale_out = scale_out;
     tsp.cls = prior_cls; tsp.n_cls = n_cls;
     CU_TRY(e, cudaEventRecord(e->ev_fork, s));
@@ -594,16 +595,16 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
       pf.gn_scale = gn0_scale; pf.gn_shift = gn0_shift; pf.bias1 = e->rot_b1; pf.stats = e->stats1;
       pf.obj_count = e->rot_count; pf.gn1_gamma = e->rot_gn1_g; pf.gn1_beta = e->rot_gn1_b;
       pf.neck_w = e->neck_w; pf.neck_b = e->neck_b; pf.wp = e->wp; pf.partial = e->rot_partial;
-      pf.a1t = e->debug_taps ? e->a1 : nullptr;
+      pf.a1t = (!e->fused_tail || e->debug_taps) ? e->a1 : nullptr;
       cudaError_t st;
       {
         Launch l(e, s, G_ROT_FUSED);
-        if (e->cfg.precision == CATRE_PREC_BF16)
-          st = rot_fused_launch<1>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
-                                   e->tw_rot1s.map_lo, pf, e->num_sms, s);
-        else
-          st = rot_fused_launch<3>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi,
-                                   e->tw_rot1s.map_lo, pf, e->num_sms, s);
+#define CATRE_ROT_LAUNCH(NP, FT)                                                                                          \
+  rot_fused_launch<NP, FT>(e->pf16.map_hi, e->pf16.map_lo, e->tw_rot0.map_hi, e->tw_rot0.map_lo, e->tw_rot1s.map_hi, \
+                           e->tw_rot1s.map_lo, pf, e->num_sms, s)
+        if (e->cfg.precision == CATRE_PREC_BF16) st = e->fused_tail ? CATRE_ROT_LAUNCH(1, true) : CATRE_ROT_LAUNCH(1, false);
+        else st = e->fused_tail ? CATRE_ROT_LAUNCH(3, true) : CATRE_ROT_LAUNCH(3, false);
+#undef CATRE_ROT_LAUNCH
       }
       if (st != cudaSuccess) {
         cudaGetLastError();
@@ -636,11 +637,16 @@ int iteration(catre_engine* e, cudaStream_t s, int B, const float* pose_in, cons
                e->gn1 + (size_t)e->maxB * 512, B, 512, P / 128, P);
   }
   if ((rc = check_launch(e, "gn_finalize"))) return rc;
-  if (!tc) {  // tensor-core modes: the tail runs inside the fused rot kernel, out of TMEM
+  if (!tc) {
     Launch l(e, s, G_ROT_TAIL);
     launch_pdl(rot_tail_kernel, dim3(P / 128, B), dim3(256), (size_t)(0), s, e->a1, e->gn1, e->gn1 + (size_t)e->maxB * 512, e->neck_w,
                e->neck_b, e->wp, e->rot_partial, P);
-  }
+  } else if (!e->fused_tail) {  // split tail: finalises the GroupNorm-1 statistics itself (partials per 128 points from the fused rot
+                                // kernel) and walks the objects backwards (the last ones written are still in L2)
+    Launch l(e, s, G_ROT_TAIL);
+    launch_pdl(rot_tail_t_kernel, dim3(16, B), dim3(256), (size_t)(P * sizeof(float)), s, e->a1, e->stats1, e->rot_gn1_g, e->rot_gn1_b,
+               P / 128, e->neck_w, e->neck_b, e->wp, e->rot_partial, P, 1);
+  }  // fused tail: the tail ran inside the fused rot kernel, out of TMEM
   if ((rc = check_launch(e, "rot_tail"))) return rc;
 
   // ---- G1 + G2 after both heads: join the side stream, then rot6d Gram-Schmidt + pose update
@@ -774,9 +780,13 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
     rc |= dalloc(e, &e->a0, R * 512);
     rc |= dalloc(e, &e->t64, S * 4096);
   }
-  // fp32 mode: a1 [R][512], the rot layer-1 output.  The tensor-core modes never store it (the rot tail runs out of TMEM);
-  // with CATRE_DEBUG_TAPS=1 they keep a copy a1T [B][P/4][512][4] for the per-stage test
-  if (!tc || (getenv("CATRE_DEBUG_TAPS") && atoi(getenv("CATRE_DEBUG_TAPS")) != 0)) rc |= dalloc(e, &e->a1, R * 512);
+  // fp32 mode: a1 [R][512], the rot layer-1 output; tensor-core modes with the split rot tail (default): a1T [B][P/4][512][4].
+  // With the fused tail (CATRE_ROT_TAIL=fused) it is never stored; CATRE_DEBUG_TAPS=1 then keeps a copy for the per-stage test
+  {
+    const char* rt = getenv("CATRE_ROT_TAIL");
+    e->fused_tail = tc && rt && strcmp(rt, "fused") == 0;
+  }
+  if (!tc || !e->fused_tail || (getenv("CATRE_DEBUG_TAPS") && atoi(getenv("CATRE_DEBUG_TAPS")) != 0)) rc |= dalloc(e, &e->a1, R * 512);
   rc |= dalloc(e, &e->rot_count, 2 * B);
   rc |= dalloc(e, &e->gmax_all, S * (1024 * 3 + 64));
   e->gmax_stn = e->gmax_all;

@@ -705,6 +705,101 @@ __global__ void __launch_bounds__(256) rot_tail_kernel(const float* __restrict__
   }
 }
 
+// Split-tail variant of the tensor-core modes (CATRE_ROT_TAIL=split, the default; see rot_fused_kernel): the fused rot kernel
+// stores the rot layer-1 output in fp32 as a1T [B][P/4][512][4]: groups of 4 consecutive points,
+// channel-major inside a group, so that the fused rot kernel (lane = channel, 64 points per thread) and this
+// kernel (lane = channel too) both move 512 contiguous bytes per warp instruction.  Block = 32 channels
+// (one per lane) of one head of one object, the 8 warps split the P points;  S_c = sum_p wp[p] gelu(a1[c][p] sc_c
+// + sh_c) is accumulated per lane and the neck is applied to S_c (linearity, see above);
+// partial[b][blockIdx.x][6] (other head's 3 = 0).  The GroupNorm-1 statistics are finalised here as well (fp64
+// sum of the block's 4 groups x tiles_per_obj partials written by the fused rot kernel), so no separate finalize
+// launch is needed.
+__global__ void __launch_bounds__(256) rot_tail_t_kernel(const float* __restrict__ a1t, const float* __restrict__ stats /*[R/128][64][2]*/,
+                                                         const float* __restrict__ gamma, const float* __restrict__ beta /*[512]*/,
+                                                         int tiles_per_obj,
+                                                         const float* __restrict__ neck_w /*[2][3][256]*/,
+                                                         const float* __restrict__ neck_b /*[2][3]*/,
+                                                         const float* __restrict__ wp /*[2][P]*/, float* __restrict__ partial,
+                                                         int P, int reverse) {
+  extern __shared__ __align__(16) float s_wp[];  // [P]
+  __shared__ float s_part[8][3];
+  __shared__ float s_sc[32], s_sh[32];
+  // reverse: walk the objects from the last one down -- the fused rot kernel wrote them in ascending order, so the last
+  // ones are the part of a1T that is still in L2 (-7 % on this kernel at 64 objects, nothing at 256)
+  const int b = reverse ? (int)gridDim.y - 1 - (int)blockIdx.y : (int)blockIdx.y;
+  const int cg = blockIdx.x, h = cg >> 3;  // 16 blocks per object, 8 per head
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  for (int i = threadIdx.x; i < P / 4; i += 256)  // weights: constants, staged before the dependency wait
+    reinterpret_cast<float4*>(s_wp)[i] = __ldg(reinterpret_cast<const float4*>(wp + (long long)h * P) + i);
+  pdl_wait();
+  if (warp < 4) {  // GroupNorm(32 groups of 8 channels per head): group cg*4 + warp of the object's 64
+    const int g = cg * 4 + warp;
+    double s = 0.0, ss = 0.0;
+    for (int t = lane; t < tiles_per_obj; t += 32) {
+      const long long o = (((long long)b * tiles_per_obj + t) * 64 + g) * 2;
+      s += (double)stats[o];
+      ss += (double)stats[o + 1];
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { s += __shfl_xor_sync(0xffffffffu, s, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    const double n = 8.0 * P, mean = s / n;
+    double var = ss / n - mean * mean;
+    if (var < 0.0) var = 0.0;
+    const float rstd = (float)(1.0 / sqrt(var + 1e-5)), fmean = (float)mean;
+    if (lane < 8) {
+      const int c = g * 8 + lane;
+      const float sc = rstd * gamma[c];
+      s_sc[warp * 8 + lane] = sc;
+      s_sh[warp * 8 + lane] = beta[c] - fmean * sc;
+    }
+  }
+  __syncthreads();
+  const int c = cg * 32 + lane;  // this lane's channel in [0, 512)
+  const float sc = s_sc[lane], sh = s_sh[lane];
+  const int quads = P / 4, per_warp = quads / 8;  // P is a multiple of 256
+  const float4* src = reinterpret_cast<const float4*>(a1t) + ((long long)b * quads + warp * per_warp) * 512 + c;
+  const float4* wq = reinterpret_cast<const float4*>(s_wp) + warp * per_warp;
+  float acc = 0.f;
+#pragma unroll 4
+  for (int i = 0; i < per_warp; ++i) {
+    const float4 f = __ldcs(src + (long long)i * 512);  // read once: streaming
+    const float4 w = wq[i];  // same address on every lane: shared-memory broadcast
+    acc = fmaf(w.x, gelu_fast(fmaf(f.x, sc, sh)), acc);
+    acc = fmaf(w.y, gelu_fast(fmaf(f.y, sc, sh)), acc);
+    acc = fmaf(w.z, gelu_fast(fmaf(f.z, sc, sh)), acc);
+    acc = fmaf(w.w, gelu_fast(fmaf(f.w, sc, sh)), acc);
+  }
+  const int cl = c & 255;
+  float r0 = neck_w[(h * 3 + 0) * 256 + cl] * acc;
+  float r1 = neck_w[(h * 3 + 1) * 256 + cl] * acc;
+  float r2 = neck_w[(h * 3 + 2) * 256 + cl] * acc;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    r0 += __shfl_xor_sync(0xffffffffu, r0, o);
+    r1 += __shfl_xor_sync(0xffffffffu, r1, o);
+    r2 += __shfl_xor_sync(0xffffffffu, r2, o);
+  }
+  if (lane == 0) { s_part[warp][0] = r0; s_part[warp][1] = r1; s_part[warp][2] = r2; }
+  __syncthreads();
+  if (warp == 0) {
+    float wsum = 0.f;
+    if ((cg & 7) == 0) {  // the neck bias term  nb * sum_p wp[p]  is added once per head
+      for (int i = lane; i < P; i += 32) wsum += s_wp[i];
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) wsum += __shfl_xor_sync(0xffffffffu, wsum, o);
+    }
+    if (lane < 6) {
+      float s = 0.f;
+      if (lane / 3 == h) {
+        const int d = lane % 3;
+        for (int w = 0; w < 8; ++w) s += s_part[w][d];
+        s = fmaf(neck_b[h * 3 + d], wsum, s);
+      }
+      partial[((long long)b * gridDim.x + cg) * 6 + lane] = s;
+    }
+  }
+}
+
 // ----------------------------------------------------------------------------------------------
 // H1 + G1 + G2: per object -- translation/size head (heads/fc_trans_size_head.py:61-70), rot6d
 // Gram-Schmidt (core/utils/rot_reps.py:34-55) and the pose update

@@ -57,7 +57,7 @@ struct RotFusedP {
   const float* neck_b;   // [2][3]
   const float* wp;       // [2][P]   conv_p weights per head and point index
   float* partial;        // [B][P/128][6]  per-item contributions to the two heads' 3-vectors (summed by pose_update_kernel)
-  float* a1t;            // debug tap only (null in production): [B][P/4][512][4] fp32 layer-1 output + bias
+  float* a1t;            // split tail: [B][P/4][512][4] fp32 layer-1 output + bias; fused tail: debug tap only (else null)
 };
 
 __device__ __forceinline__ void tmem_ld16(uint32_t taddr, float* v) {
@@ -86,7 +86,13 @@ __device__ __forceinline__ void tmem_ld_wait16(float* v) {
 // The two epilogue groups are independent instruction streams: the GELU work of item j+1 runs underneath the layer-1
 // MMAs of item j AND underneath the drain of item j's D1; the only couplings are the TMEM / U barriers.
 constexpr int ROT_THREADS = RF_THREADS + 32 * RF_E1W;
-template <int NPROD>
+// FT (fused tail): true = the rot tail runs out of TMEM as described above; false = "split tail": E1 adds the bias, takes the
+// GroupNorm-1 partial sums and stores the fp32 tile as a1T [B][P/4][512][4] for rot_tail_t_kernel (the round-2a design).
+// Measured (64 / 256 objects, N = 1024; 256 objects, N = 2048, K = 8): split 3.33 / 12.9 / 49.6 ms per step, fused 3.45 / 13.1 /
+// 52.0 ms, fused 6 % faster at 8 objects -- the standalone tail kernel runs its GELU sweep at 7.3 GELU/clk/SM (48 resident warps
+// per SM, streaming), the 24 epilogue warps of this kernel at 2.5 -- so split is the default and the fused tail is the choice
+// when the 4 KB per point of a1T (1.07 GB at 256 objects, 540 MB of DRAM traffic per iteration at 64) matters more.
+template <int NPROD, bool FT>
 __global__ void __launch_bounds__(ROT_THREADS, 1)
 rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constant__ CUtensorMap pf_lo,
                  const __grid_constant__ CUtensorMap w0_hi, const __grid_constant__ CUtensorMap w0_lo,
@@ -122,7 +128,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
     for (int i = 0; i < ROT_SLOTS; ++i) { mbar_init(bar_full + 8 * i, 1); mbar_init(bar_empty + 8 * i, 1); }
     // RF_EW warps write U (E0 group), RF_E1W warps drain D1 (E1 group)
     for (int i = 0; i < 2; ++i) { mbar_init(bar_d0_full + 8 * i, 1); mbar_init(bar_d0_empty + 8 * i, RF_EW); }
-    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, RF_EW + RF_E1W);  // D1 is released by pass 2 of the tail (all 24 warps)
+    mbar_init(bar_d1_full, 1); mbar_init(bar_d1_empty, FT ? RF_EW + RF_E1W : RF_E1W);  // D1 is released by pass 2 of the tail (all 24 warps) / by the drain
     mbar_init(bar_stats_ready, 1); mbar_init(bar_pass2_done, RF_EW + RF_E1W);
     for (int i = 0; i < 4; ++i) mbar_init(bar_u_full + 8 * i, RF_EW);
     for (int i = 0; i < 2; ++i) mbar_init(bar_u_empty + 8 * i, 1);
@@ -318,7 +324,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
           const int half = ks >> 1;
           // PASS2(j-1): as soon as its statistics are there, and at the latest before slab 2 -- slab 2 reuses the U buffer of
           // slab 0, i.e. it waits for the layer-1 MMAs of THIS item, which wait for D1, which PASS2(j-1) releases
-          if (!tail_done && (ks == 2 || mbar_try_wait(bar_stats_ready, (uint32_t)(j - 1) & 1))) { pass2(j - 1); tail_done = true; }
+          if (FT && !tail_done && (ks == 2 || mbar_try_wait(bar_stats_ready, (uint32_t)(j - 1) & 1))) { pass2(j - 1); tail_done = true; }
           if ((ks & 1) == 0) {
             mbar_wait(bar_d0_full + 8 * half, (uint32_t)j & 1);
             tc_fence_after();
@@ -367,7 +373,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
           if (lane == 0) mbar_arrive(bar_u_full + 8 * ks);
         }
       }
-      if (n_items > 0) pass2(n_items - 1);
+      if (FT && n_items > 0) pass2(n_items - 1);
     } else {
       // E1(j): lane = output channel of m-tile mt (thread = channel, the item's 128 points are its TMEM columns).
       const int mt = (warp - 2 - RF_EW) >> 2;
@@ -379,12 +385,14 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
         const int ch = h * 256 + mt * 128 + lane_row;  // channel in [0, 512)
         const float add = p.bias1[ch];
         // (the previous item's readers of s_wp / s_grp / s_part finished before pass2_done(j-1), which this group waited for)
-        if (t1 < 128) s_wp[t1] = __ldg(p.wp + (long long)h * P + (row0 - (long long)b * P) + t1);
+        if (FT && t1 < 128) s_wp[t1] = __ldg(p.wp + (long long)h * P + (row0 - (long long)b * P) + t1);
         while (!mbar_try_wait(bar_d1_full, (uint32_t)j & 1)) __nanosleep(64);  // idle most of the time: poll politely
         tc_fence_after();
         const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(256 + mt * 128);
         // ---- pass 1: GroupNorm-1 partial sums of y = D1 + b1 over the item's 128 points (four independent chains per sum,
-        //      16-column chunks, the tcgen05.ld of the next chunk in flight)
+        //      16-column chunks, the tcgen05.ld of the next chunk in flight).  Split tail: this is the drain -- y goes to a1T
+        //      (4 consecutive points of a channel = one 16-byte streaming store, 512 contiguous bytes per warp instruction)
+        //      and D1 is released as soon as its last chunk is in registers.
         {
           float xa[16], xb[16];
           float s4[4] = {0.f, 0.f, 0.f, 0.f}, q4[4] = {0.f, 0.f, 0.f, 0.f};
@@ -393,17 +401,23 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
           for (int c = 0; c < 8; ++c) {
             float* x = (c & 1) ? xb : xa;
             tmem_ld_wait16(x);
-            if (c + 1 < 8) tmem_ld16(taddr + (c + 1) * 16, (c & 1) ? xa : xb);
+            if (c + 1 < 8) {
+              tmem_ld16(taddr + (c + 1) * 16, (c & 1) ? xa : xb);
+            } else if (!FT) {
+              tc_fence_before();
+              __syncwarp();
+              if (lane == 0) mbar_arrive(bar_d1_empty);
+            }
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
               x[q] += add;
               s4[q & 3] += x[q];
               q4[q & 3] = fmaf(x[q], x[q], q4[q & 3]);
             }
-            if (p.a1t != nullptr) {  // debug tap (tests/test_stages_gpu.py)
+            if (!FT || p.a1t != nullptr) {  // fused tail: debug tap only (tests/test_stages_gpu.py)
               float4* dst = reinterpret_cast<float4*>(p.a1t) + ((row0 >> 2) + c * 4) * 512 + ch;
 #pragma unroll
-              for (int q = 0; q < 4; ++q) dst[q * 512] = make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]);
+              for (int q = 0; q < 4; ++q) __stcs(dst + q * 512, make_float4(x[4 * q], x[4 * q + 1], x[4 * q + 2], x[4 * q + 3]));
             }
           }
           float s = (s4[0] + s4[1]) + (s4[2] + s4[3]), ss = (q4[0] + q4[1]) + (q4[2] + q4[3]);
@@ -413,6 +427,7 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
           if ((lane & 7) == 0)
             *reinterpret_cast<float2*>(p.stats + (((long long)tile * 64 + (ch >> 3)) * 2)) = make_float2(s, ss);
         }
+        if (!FT) continue;  // split tail: rot_tail_t_kernel finalises the statistics and does the rest
         // ---- publish, then (first E1 warp) wait for the other tiles of this (object, head) and finalise the statistics of
         //      the head's 32 groups: lane = group; fp64 sum of the object's tiles in tile order, biased variance, eps 1e-5
         named_bar_sync(1, 32 * RF_E1W);  // every E1 thread's sums are written (and s_wp is complete)
@@ -471,11 +486,11 @@ rot_fused_kernel(const __grid_constant__ CUtensorMap pf_hi, const __grid_constan
   }
 }
 
-template <int NPROD>
+template <int NPROD, bool FT>
 cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo, const CUtensorMap& w0_hi,
                              const CUtensorMap& w0_lo, const CUtensorMap& w1_hi, const CUtensorMap& w1_lo,
                              const RotFusedP& p, int num_sms, cudaStream_t s) {
-  auto kern = rot_fused_kernel<NPROD>;
+  auto kern = rot_fused_kernel<NPROD, FT>;
   static bool configured = false;
   if (!configured) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ROT_SMEM);

@@ -24,10 +24,18 @@ def weights():
 _ENGINES = {}
 
 
-def get_engine(weights, n_pts, prec, max_batch=64):
-    key = (n_pts, prec, max_batch)
+def get_engine(weights, n_pts, prec, max_batch=64, rot_tail="split"):
+    """rot_tail: "split" (default: the fused rot kernel stores its layer-1 output for rot_tail_t_kernel) or "fused" (the tail
+    runs out of TMEM inside the fused rot kernel; CATRE_ROT_TAIL is read when the engine is created)."""
+    import os
+
+    key = (n_pts, prec, max_batch, rot_tail)
     if key not in _ENGINES:
-        eng = engine.Engine(n_pts, max_batch, prec, 0)
+        os.environ["CATRE_ROT_TAIL"] = rot_tail
+        try:
+            eng = engine.Engine(n_pts, max_batch, prec, 0)
+        finally:
+            del os.environ["CATRE_ROT_TAIL"]
         eng.load_weights(catre_oracle.resize_conv_p(weights, n_pts))
         _ENGINES[key] = eng
     return _ENGINES[key]
@@ -370,10 +378,27 @@ def test_rot_tail_exchange_at_awkward_launch_sizes(weights):
     of a launch that holds all of them (the exchange is deterministic), must agree with the fp32 CUDA-core mode (which has no
     such exchange) and must come back at all (a wait that cannot complete traps instead of hanging)."""
     b = synth.make_batch(150, 1024, seed=93)
-    ref = run_refine(get_engine(weights, 1024, "f16x3", max_batch=256), b, 2)
+    ref = run_refine(get_engine(weights, 1024, "f16x3", max_batch=256, rot_tail="fused"), b, 2)
     strict = run_refine(get_engine(weights, 1024, "fp32", max_batch=256), b, 2)
     e = gu.max_abs_err_nan_aware(ref[0], ref[1], strict[0].cpu(), strict[1].cpu())
     assert max(e) <= 2e-5, e
     for mb in (1, 2, 4, 9, 37, 74, 75):  # launches of mb objects (32 items each) on the 148-CTA grid: 32 ... 2400 items per launch
-        got = run_refine(get_engine(weights, 1024, "f16x3", max_batch=mb), b, 2)
+        got = run_refine(get_engine(weights, 1024, "f16x3", max_batch=mb, rot_tail="fused"), b, 2)
         assert torch.equal(got[0], ref[0]) and torch.equal(got[1], ref[1]), mb
+
+
+@pytest.mark.parametrize("name", list(gu.full_case_names()) + ["ragged_b3_n1024_k2", "kat"])
+def test_fused_rot_tail_matches_the_reference_goldens(weights, name):
+    """CATRE_ROT_TAIL=fused (the rot tail out of TMEM, no a1T buffer) against the same goldens and gates as the default."""
+    if name in gu.full_case_names():
+        case = gu.load_full_case(name)
+        eng = get_engine(weights, case.n_pts, "f16x3", max_batch=256, rot_tail="fused")
+        poses, scales = run_refine(eng, case.batch, case.n_iter)
+        assert max(gu.max_abs_err_nan_aware(poses, scales, case.poses, case.scales)) <= TOL
+        e64 = gu.max_abs_err_nan_aware(poses, scales, case.poses64, case.scales64)
+        assert max(e64) <= gu.REGRESSION_TOL[("f16x3", case.n_iter)], (name, e64)
+    else:
+        case = gu.load_case(name)
+        eng = get_engine(weights, case.n_pts, "f16x3", rot_tail="fused")
+        poses, scales = run_refine(eng, case.batch, case.n_iter)
+        assert max(gu.max_abs_err(poses, scales, case.poses, case.scales)) <= TOL

@@ -6,7 +6,7 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-fil
     python bench.py --steps 2 --warmup 3 --no-cpu-baseline --no-train-leg --no-headline > gpurun_out/ncu_bench.log 2>&1
 # the reports are tens of MB each (gpurun_out/ is capped at 64 MiB): summarise them on the box, keep the text
 for b in 64 256; do
-  ncu --set full --clock-control none -s 19 -c 19 -o /tmp/prof_iter$b -f python tools/ncu_target.py f16x3 $b > gpurun_out/ncu_iter$b.log 2>&1
+  ncu --set full --clock-control none -s 17 -c 17 -o /tmp/prof_iter$b -f python tools/ncu_target.py f16x3 $b > gpurun_out/ncu_iter$b.log 2>&1
   python tools/ncu_iter.py /tmp/prof_iter$b.ncu-rep $b --update-traffic > gpurun_out/ncu_iteration_b$b.txt 2>&1
 done
 cp profiles/ncu_traffic.json gpurun_out/ncu_traffic.json

@@ -12,12 +12,12 @@ import os
 import subprocess
 import sys
 
-ORDER = [("update_points", "update_points_kernel"), ("front3", "front3_split"), ("stn_conv3_max", "enc_fused"), ("tnet_fc", "fc_chain"),
+ORDER = [("front3", "iter_head_kernel"), ("stn_conv3_max", "enc_fused"), ("tnet_fc", "fc_chain"),
          ("front3", "front3_split"), ("fstn_conv1", "tc_gemm_kernel<1, 2, 64"), ("fstn_conv3_max", "enc_fused"), ("tnet_fc", "fc_chain"),
          ("tnet_fc", "fc_tiled"), ("feat_transform", "tc_gemm_kernel<1, 5, 64"), ("conv2", "tc_gemm_kernel<1, 2, 128"),
          ("conv3", "tc_gemm_kernel<1, 2, 128"), ("conv4_max", "tc_gemm_kernel<0, 0, 256"), ("rot_gfeat", "fc_chain"), ("ts_pose", "ts_head"),
          ("rot_layer0", "tc_gemm_kernel<0, 3, 256"), ("gn_finalize", "gn_finalize_set"), ("rot_fused", "rot_fused"),
-         ("ts_pose", "pose_update")]
+         ("ts_pose", "pose_update"), ("update_points", "update_points_kernel")]
 
 rep, batch = sys.argv[1], sys.argv[2]
 out = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
@@ -49,6 +49,8 @@ for r, n in zip(data, names):
     for g, pat in ORDER:
         if pat in n:
             grp = g if pat not in ("tc_gemm_kernel<1, 2, 128", "fc_chain", "enc_fused", "front3_split") else None
+            if pat == "iter_head_kernel":
+                grp = "front3(pose update + points + stn.conv1)"
             break
     seq.append(grp)
 # order-dependent ones: resolve by occurrence count
@@ -57,7 +59,7 @@ for i, n in enumerate(names):
     if seq[i] is not None:
         continue
     for pat, groups in (("tc_gemm_kernel<1, 2, 128", ["conv2", "conv3"]), ("fc_chain", ["tnet_fc(stn)", "tnet_fc(fstn fc1+fc2)", "rot_gfeat(cset+ts0)"]),
-                        ("enc_fused", ["stn_conv3_max", "fstn_conv3_max"]), ("front3_split", ["front3(stn.conv1)", "front3(T3 + conv1)"])):
+                        ("enc_fused", ["stn_conv3_max", "fstn_conv3_max"]), ("front3_split", ["front3(T3 + conv1)"])):
         if pat in n:
             k = cnt.get(pat, 0)
             seq[i] = groups[k % len(groups)]
