@@ -19,6 +19,7 @@
 #include "cloud_kernels.cuh"
 #include "metrics_kernels.cuh"
 #include "train_chain.cuh"
+#include "train_gemm_tc.cuh"
 #include "optim_kernels.cuh"
 
 using namespace catre;
@@ -694,7 +695,9 @@ namespace {
 struct CudaTrainOps {
   cudaStream_t s;
   bool naive;
-  bool v2;  // CATRE_TRAIN_GEMM=v2: the 128 x BN register-prefetch GEMM (opt-in until it has been measured on the GPU)
+  bool v2;  // CATRE_TRAIN_GEMM=v2: the 128 x BN register-prefetch CUDA-core GEMM (measured slower than the 64 x 64 one)
+  bool tc;  // tcgen05 GEMM for the large shapes (default; CATRE_TRAIN_GEMM=simt / v2 / CATRE_TRAIN_NAIVE_GEMM=1 turn it off)
+  int num_sms;
   int64_t launches = 0;
   cudaError_t err = cudaSuccess;
   void note(cudaError_t st) { if (err == cudaSuccess && st != cudaSuccess) err = st; }
@@ -706,10 +709,51 @@ struct CudaTrainOps {
     note(cudaPeekAtLastError());
   }
   void zero(void* p, size_t bytes) { note(cudaMemsetAsync(p, 0, bytes, s)); }
+  // The tensor-core GEMM (train_gemm_tc.cuh) takes every GEMM with enough work for a 128 x 128 x 64 tile pipeline; the rest
+  // (K = 3 input layers, the 3- / 6- / 9-column heads, single-row products) stays on the CUDA-core tile kernel.
+  static bool tc_shape(const catre_train::GemmP& p, int bz) {
+    return p.M >= 16 && p.N >= 16 && p.K >= 16 && (double)p.M * p.N * p.K * (p.splits > 1 ? 1 : bz) >= (double)(1 << 20);
+  }
+  void gemm_tc(const catre_train::GemmP& p, int bz) {
+    note(p.f16 ? catre_train::tk_gemm_tc_launch<true>(p, bz, s) : catre_train::tk_gemm_tc_launch<false>(p, bz, s));
+    ++launches;
+  }
+  // max-pooled layer with the pooling fused into the tensor-core GEMM's epilogue (64-bit value|~row keys + atomicMax, decoded
+  // into vmax / arg afterwards); false = not available, the chain then runs the layer and the column max separately
+  bool gemm_colmax(const catre_train::GemmP& p, int rows_per_set, float* vmax, int* arg, int S, size_t partial_floats) {
+    if (!tc || rows_per_set % 128 != 0 || (size_t)S * p.N * 2 > partial_floats || !tc_shape(p, 1)) return false;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(p.partial);
+    zero(keys, (size_t)S * p.N * sizeof(unsigned long long));
+    const catre_train::TgColMax cm{keys, rows_per_set};
+    note(p.f16 ? catre_train::tk_gemm_tc_launch<true>(p, 1, s, cm) : catre_train::tk_gemm_tc_launch<false>(p, 1, s, cm));
+    ++launches;
+    const long long n = (long long)S * p.N;
+    run(catre_train::KColMaxDecode{keys, vmax, arg, n}, (unsigned)((n + 255) / 256), 1, 1, 256);
+    return true;
+  }
   void gemm(const catre_train::GemmP& p, int bz) {
     if (p.M <= 0 || p.N <= 0 || bz <= 0) return;
     if (naive) {
       run(catre_train::KGemmNaive{p}, (unsigned)((p.M + 3) / 4), (unsigned)((p.N + 63) / 64), (unsigned)bz, 256);
+    } else if (tc && tc_shape(p, bz)) {
+      // a launch of a few tiles with a long reduction (the small-M FC layers: 32 rows, K up to 1024): split K here so that
+      // the tiles x splits CTAs cover the device; the partials are summed in a fixed order (+ bias / ReLU) by KSplitReduce
+      const long long tiles = (long long)((p.M + 127) / 128) * ((p.N + 127) / 128);
+      if (p.splits == 1 && bz == 1 && tiles * 2 <= num_sms && p.K >= 256 && p.partial) {
+        int splits = (int)(num_sms / tiles);
+        if (splits > p.K / 128) splits = p.K / 128;
+        while (splits > 1 && (size_t)splits * p.M * p.N > catre_train::TrainWs::kPartialFloats) --splits;
+        if (splits > 1) {
+          catre_train::GemmP q = p;
+          q.splits = splits;
+          q.k_per = ((p.K + splits - 1) / splits + 63) & ~63;
+          gemm_tc(q, splits);
+          catre_train::KSplitReduce red{p.partial, p.C, p.scm, p.scn, p.M, p.N, splits, p.accumulate, p.bias, p.relu};
+          run(red, (unsigned)(((long long)p.M * p.N + 255) / 256), 1, 1, 256);
+          return;
+        }
+      }
+      gemm_tc(p, bz);
     } else if (v2) {
       if (p.N <= 64) catre_train::tk_gemm_tiled2<64><<<dim3((unsigned)((p.M + 127) / 128), (unsigned)((p.N + 63) / 64), (unsigned)bz), 256, 0, s>>>(p);
       else catre_train::tk_gemm_tiled2<128><<<dim3((unsigned)((p.M + 127) / 128), (unsigned)((p.N + 127) / 128), (unsigned)bz), 256, 0, s>>>(p);
@@ -1409,7 +1453,8 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   for (int i = 0; i < kNumWeights; ++i) Wp[i] = e->dw.at(kWeights[i].name);
   const char* env = getenv("CATRE_TRAIN_NAIVE_GEMM");
   const char* env2 = getenv("CATRE_TRAIN_GEMM");
-  CudaTrainOps ops{s, e->train_naive_gemm || (env && env[0] == '1'), env2 && strcmp(env2, "v2") == 0};
+  const bool naive_gemm = e->train_naive_gemm || (env && env[0] == '1'), gemm_v2 = env2 && strcmp(env2, "v2") == 0;
+  CudaTrainOps ops{s, naive_gemm, gemm_v2, !naive_gemm && !gemm_v2 && !(env2 && strcmp(env2, "simt") == 0), e->num_sms};
   catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
   catre_train::TrainIn in{nullptr, obj_kps, pose, scale, K, gt_pose, gt_scale, B, n_sym_rots, n_sym, B - n_sym, out_pose, out_scale};
   in.x_pm = x_pm; in.tfd_pm = tfd_pm;
@@ -1488,6 +1533,50 @@ int catre_ranger_step(const int64_t* table, const float* lr_wd, const int64_t* e
 }
 
 int64_t catre_last_launch_count(const catre_engine* e) { return e ? e->launches : 0; }
+
+int catre_debug_train_gemm(const float* A, const float* B, float* C, const float* bias, const int64_t* st, int32_t M, int32_t N,
+                           int32_t K, int32_t batch, int32_t relu, int32_t accumulate, int32_t splits, float* partial,
+                           int32_t kernel, int32_t rows_per_set, float* vmax, int32_t* arg, void* stream) {
+  if (!A || !B || !st || M <= 0 || N <= 0 || K <= 0 || batch <= 0 || kernel < 0 || kernel > 2) return CATRE_ERR_INVALID_ARG;
+  if (splits > 1 && (batch != 1 || !partial || bias || relu)) return CATRE_ERR_INVALID_ARG;
+  const bool colmax = vmax != nullptr;
+  if (colmax ? (!arg || !partial || kernel == 0 || splits > 1 || batch != 1 || rows_per_set <= 0 || rows_per_set % 128 != 0 || M % rows_per_set != 0)
+             : !C)
+    return CATRE_ERR_INVALID_ARG;
+  cudaStream_t s = (cudaStream_t)stream;
+  catre_train::GemmP p{};
+  p.A = A; p.sam = st[0]; p.sak = st[1]; p.sab = st[2]; p.B = B; p.sbk = st[3]; p.sbn = st[4]; p.sbb = st[5];
+  p.C = C; p.scm = st[6]; p.scn = st[7]; p.scb = st[8]; p.bias = bias; p.sbias_b = 0;
+  p.M = M; p.N = N; p.K = K; p.relu = relu; p.accumulate = accumulate; p.splits = 1; p.k_per = K; p.partial = partial;
+  p.f16 = kernel == 1;
+  int bz = batch;
+  if (splits > 1) { p.splits = splits; p.k_per = ((K + splits - 1) / splits + 63) & ~63; bz = splits; }
+  cudaError_t err;
+  if (colmax) {
+    const int sets = M / rows_per_set;
+    unsigned long long* keys = reinterpret_cast<unsigned long long*>(partial);
+    err = cudaMemsetAsync(keys, 0, (size_t)sets * N * sizeof(unsigned long long), s);
+    const catre_train::TgColMax cm{keys, rows_per_set};
+    if (err == cudaSuccess) err = p.f16 ? catre_train::tk_gemm_tc_launch<true>(p, 1, s, cm) : catre_train::tk_gemm_tc_launch<false>(p, 1, s, cm);
+    if (err == cudaSuccess) {
+      const long long n = (long long)sets * N;
+      catre_train::tk_run<<<(unsigned)((n + 255) / 256), 256, 0, s>>>(catre_train::KColMaxDecode{keys, vmax, arg, n});
+      err = cudaPeekAtLastError();
+    }
+  } else if (kernel == 0) {
+    catre_train::tk_gemm_tiled<<<dim3((unsigned)((M + 63) / 64), (unsigned)((N + 63) / 64), (unsigned)bz), 256, 0, s>>>(p);
+    err = cudaPeekAtLastError();
+  } else {
+    err = p.f16 ? catre_train::tk_gemm_tc_launch<true>(p, bz, s) : catre_train::tk_gemm_tc_launch<false>(p, bz, s);
+  }
+  if (err == cudaSuccess && splits > 1) {
+    catre_train::KSplitReduce red{partial, C, p.scm, p.scn, M, N, splits, accumulate};
+    catre_train::tk_run<<<(unsigned)(((long long)M * N + 255) / 256), 256, 0, s>>>(red);
+    err = cudaPeekAtLastError();
+  }
+  if (err != cudaSuccess) { cudaGetLastError(); return CATRE_ERR_CUDA; }
+  return CATRE_OK;
+}
 
 int catre_debug_read(catre_engine* e, const char* name, void* dst_host, size_t bytes) {
   if (!e || !name || !dst_host) return CATRE_ERR_INVALID_ARG;

@@ -47,15 +47,18 @@ struct TrainWs {
   // loss / backward
   float *lossp, *losses, *dpose, *d_r6, *d_dts, *tsd_u, *tsd_u0, *ts_din, *gn_m, *gnp_g, *gnp_b;
   float *dg, *dpfmax, *dpf, *e, *du, *du0, *dcset, *d512, *d128, *d64, *dh1, *dt64, *dfc2, *dfc1, *dmax, *dqp, *dt3;
-  float *partial, *cs_partial;
-  double* gn_part;  // [maxB, kGnChunks, 32, 18]
+  float *partial, *cs_partial, *loss_gs;
+  int *mb_start, *mb_cnt, *mb_list;  // inverse arg-max map of the sparse max-pool backward: [S, N], [S, N], [S, 1024]
+  double* gn_part;  // [maxB, kGnChunks, 32, 18]; also the point-matching partials of the loss [maxB, kLossChunks, 13]
   unsigned char* is_sym;
   float* sym_rots;
   float* G[W_COUNT];  // gradient arena, checkpoint order
   size_t grad_floats = 0;
   static constexpr size_t kPartialFloats = (size_t)4 << 20;
   static constexpr int kMaxSymRots = 1024;
-  static constexpr int kGnChunks = 64;
+  static constexpr int kGnChunks = 256;
+  static constexpr int kLossChunks = 32;
+  static constexpr size_t kCsFloats = (size_t)64 * 4096;
 };
 
 // Assigns every workspace pointer from `base` (256-byte aligned slices) and returns the bytes needed; with
@@ -89,7 +92,8 @@ inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base, size_t gap = 0)
   F(w.dg, S * 1024); F(w.dpfmax, S * 64); F(w.dpf, R * 64); F(w.e, B * 256); F(w.du, R * 256); F(w.du0, R * 256);
   F(w.dcset, S * 256); F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
   F(w.dfc2, S * 256); F(w.dfc1, S * 512); F(w.dmax, S * 1024); F(w.dqp, R * 3); F(w.dt3, S * 9);
-  F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, (size_t)64 * 4096);
+  F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, TrainWs::kCsFloats); F(w.loss_gs, B * 9);
+  I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024);
   w.gn_part = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
   w.is_sym = reinterpret_cast<unsigned char*>(take(B));
   F(w.sym_rots, (size_t)TrainWs::kMaxSymRots * 9);
@@ -116,6 +120,7 @@ struct Chain {
   TrainWs& w;
   const float* const* W;  // the 74 checkpoint tensors
   int N;
+  int gemm_f16 = 0;  // operand type of the tensor-core GEMM (GemmP::f16): 1 during forward(), 0 during backward()
 
   static unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
@@ -126,12 +131,15 @@ struct Chain {
     p.A = A; p.sam = sam; p.sak = sak; p.sab = sab; p.B = Bm; p.sbk = sbk; p.sbn = sbn; p.sbb = sbb;
     p.C = C; p.scm = scm; p.scn = scn; p.scb = scb; p.bias = bias; p.sbias_b = sbias_b;
     p.M = M; p.N = Nn; p.K = K; p.relu = relu; p.accumulate = acc; p.splits = 1; p.k_per = K; p.partial = w.partial;
+    p.f16 = gemm_f16;
     if (batch == 1 && !bias && !relu && K >= 4096) {  // weight gradients: reduce over many rows -> split K
-      int splits = K / 1024 < 32 ? K / 1024 : 32;
+      // few output tiles (at most 128 x 128 outputs): more, shorter splits so that the launch still fills the device
+      const int per = (M <= 128 && Nn <= 128) ? 256 : 1024, cap = (M <= 128 && Nn <= 128) ? 128 : 32;
+      int splits = K / per < cap ? K / per : cap;
       while (splits > 1 && (size_t)splits * M * Nn > TrainWs::kPartialFloats) --splits;
       if (splits > 1) {
         p.splits = splits;
-        p.k_per = ((K + splits - 1) / splits + 15) & ~15;
+        p.k_per = ((K + splits - 1) / splits + 63) & ~63;
         o.gemm(p, splits);
         o.run(KSplitReduce{w.partial, C, scm, scn, M, Nn, splits, acc}, cdiv((long long)M * Nn, 256), 1, 1, 256);
         return;
@@ -143,14 +151,57 @@ struct Chain {
   void layer(const float* x, int K, int wi, int C, float* out, long long rows, int relu) {
     gemm(x, K, 1, W[wi], 1, K, out, C, 1, (int)rows, C, K, W[wi + 1], relu, 0);
   }
+  // act(x W^T + b) of checkpoint layer wi, max-pooled over the N points of each of the S sets, with the arg-max.  The launcher
+  // may fuse the pooling into the GEMM (gemm_colmax: the [S N, C] activations are never stored); otherwise layer + colmax.
+  void layer_max(const float* x, int K, int wi, int C, float* vmax, int* arg, int S, int relu) {
+    GemmP p{};
+    p.A = x; p.sam = K; p.sak = 1; p.B = W[wi]; p.sbk = 1; p.sbn = K; p.C = nullptr; p.scm = C; p.scn = 1; p.bias = W[wi + 1];
+    p.M = (int)((long long)S * N); p.N = C; p.K = K; p.relu = relu; p.splits = 1; p.k_per = K; p.partial = w.partial; p.f16 = gemm_f16;
+    if (o.gemm_colmax(p, N, vmax, arg, S, TrainWs::kPartialFloats)) return;
+    layer(x, K, wi, C, w.zbuf, (long long)S * N, relu);
+    colmax(w.zbuf, vmax, arg, S, C);
+  }
   void colsum(const float* d, long long rows, int C, long long ld, float* out, int acc) {
-    if (rows > 2048) {
-      const long long per = (rows + 63) / 64;
-      o.run(KColSum{d, w.cs_partial, rows, C, per, 0, ld}, cdiv(C, 256), 64, 1, 256);
-      o.run(KColSum{w.cs_partial, out, 64, C, 64, acc, C}, cdiv(C, 256), 1, 1, 256);
+    if (rows > 256) {  // two stages; enough chunks to fill the device, few enough for a short second stage
+      long long chunks = rows >= 16384 ? 256 : (rows >= 2048 ? 64 : 16);
+      while (chunks > 1 && (size_t)chunks * C > TrainWs::kCsFloats) chunks >>= 1;
+      const long long per = (rows + chunks - 1) / chunks;
+      chunks = (rows + per - 1) / per;
+      o.run(KColSum{d, w.cs_partial, rows, C, per, 0, ld}, cdiv(C, 256), (unsigned)chunks, 1, 256);
+      o.run(KColSum{w.cs_partial, out, chunks, C, chunks, acc, C}, cdiv(C, 256), 1, 1, 256);
     } else {
       o.run(KColSum{d, out, rows, C, rows, acc, ld}, cdiv(C, 256), 1, 1, 256);
     }
+  }
+  // out[g, c] = sum over the rows of group g (groups of `per_group` consecutive rows), two stages
+  void group_colsum(const float* d, int groups, long long per_group, int C, float* out) {
+    int sub = 16;
+    while (sub > 1 && ((size_t)groups * sub * C > TrainWs::kCsFloats || per_group % sub != 0)) sub >>= 1;
+    if (sub == 1) {
+      o.run(KColSum{d, out, (long long)groups * per_group, C, per_group, 0, C}, cdiv(C, 256), groups, 1, 256);
+      return;
+    }
+    o.run(KColSum{d, w.cs_partial, (long long)groups * per_group, C, per_group / sub, 0, C}, cdiv(C, 256), groups * sub, 1, 256);
+    o.run(KColSum{w.cs_partial, out, (long long)groups * sub, C, sub, 0, C}, cdiv(C, 256), groups, 1, 256);
+  }
+  // column max + arg-max over the N points of each of S sets (first index wins ties), two stages when the scratch allows
+  void colmax(const float* z, float* vmax, int* arg, int S, int C) {
+    int chunks = 16;
+    while (chunks > 1 && ((size_t)S * chunks * C > TrainWs::kPartialFloats / 2 || N % chunks != 0)) chunks >>= 1;
+    if (chunks == 1) {
+      o.run(KColMaxArg{z, vmax, arg, N, C}, cdiv(C, 256), S, 1, C < 256 ? 64 : 256);
+      return;
+    }
+    float* pv = w.partial;
+    int* pi = reinterpret_cast<int*>(w.partial + TrainWs::kPartialFloats / 2);
+    const unsigned nt = C < 256 ? 64 : 256;
+    o.run(KColMaxArgPart{z, pv, pi, N, C, N / chunks}, cdiv(C, nt), chunks, S, nt);
+    o.run(KColMaxArgMerge{pv, pi, vmax, arg, chunks, C}, cdiv(C, nt), S, 1, nt);
+  }
+  // sparse backward of a max-pooled layer: dx[(s, n), :] from d(max) [S, C] (KMaxBwdIndex + KMaxBwdGather)
+  void max_bwd_dx(const float* dmax, const float* relu_max, const float* Wt, const int* arg, float* dx, int S, int C, int K) {
+    o.run(KMaxBwdIndex{arg, w.mb_start, w.mb_cnt, w.mb_list, N, C}, cdiv(N, 128), S, 1, 128);
+    o.run(KMaxBwdGather{dmax, relu_max, Wt, w.mb_start, w.mb_cnt, w.mb_list, dx, N, C, K}, cdiv(K, 128), N, S, 128);
   }
   // backward of y = x W^T + b for checkpoint tensor wi viewed as [C, ldw] with the K input columns at woff:
   // dW += dy^T x, db += colsum(dy) (when with_bias), dx (=|+=) dy W.
@@ -161,8 +212,20 @@ struct Chain {
     if (with_bias) colsum(dy, rows, C, ldy, w.G[wi + 1], 1);
     if (dx) gemm(dy, ldy, 1, W[wi] + woff, ldw, 1, dx, K, 1, (int)rows, K, C, nullptr, 0, dx_acc);
   }
+  // wsum[b, c] = sum_p wp[p] u1[b, p, c]: chunked over the points, then the chunks of an object in order
+  void rot_wsum(const float* u1, const float* wp, float* wsum, int B, int P) {
+    int chunks = 32;
+    while (chunks > 1 && ((size_t)B * chunks * 256 > TrainWs::kCsFloats || P % chunks != 0)) chunks >>= 1;
+    if (chunks == 1) { o.run(KRotWsum{u1, wp, wsum, P}, B, 1, 1, 256); return; }
+    o.run(KRotWsumPart{u1, wp, w.cs_partial, P, P / chunks}, 1, chunks, B, 256);
+    o.run(KColSum{w.cs_partial, wsum, (long long)B * chunks, 256, chunks, 0, 256}, 1, B, 1, 256);
+  }
   void relu_mask(float* d, const float* act, long long n) { o.run(KReluMask{d, act, n}, cdiv(n, 256), 1, 1, 256); }
-  static int gn_chunks(int P) { return P >= 4 * TrainWs::kGnChunks ? TrainWs::kGnChunks : 1; }
+  static int gn_chunks(int P) {  // at least 4 points per chunk
+    int c = TrainWs::kGnChunks;
+    while (c > 1 && P < 4 * c) c >>= 1;
+    return c;
+  }
   void gn_fwd(const float* y, float* st, const float* ga, const float* be, float* u, int B, int P) {
     const int chunks = gn_chunks(P), per = (P + chunks - 1) / chunks;
     o.run(KGnStatsPart{y, w.gn_part, P, chunks, per}, B, chunks, 1, 32);
@@ -174,7 +237,7 @@ struct Chain {
   void gn_bwd(float* du, const float* y, const float* st, int gi, int B, int P) {
     const int chunks = gn_chunks(P), per = (P + chunks - 1) / chunks;
     o.run(KGnBwdPart{du, y, st, W[gi], W[gi + 1], w.gn_part, P, chunks, per}, B, chunks, 1, 32);
-    o.run(KGnBwdSums{w.gn_part, w.gn_m, w.gnp_g, w.gnp_b, P, chunks}, B, 1, 1, 32);
+    o.run(KGnBwdSums{w.gn_part, w.gn_m, w.gnp_g, w.gnp_b, P, chunks}, B, 1, 1, 32 * 18);
     colsum(w.gnp_g, B, 256, 256, w.G[gi], 1);
     colsum(w.gnp_b, B, 256, 256, w.G[gi + 1], 1);
     const long long n = (long long)B * P * 256;
@@ -187,8 +250,7 @@ struct Chain {
     const long long R = (long long)S * N;
     layer(x, Kin, wb + T_CONV1, 64, c64, R, 1);
     layer(c64, 64, wb + T_CONV2, 128, c128, R, 1);
-    layer(c128, 128, wb + T_CONV3, 1024, w.zbuf, R, 1);
-    o.run(KColMaxArg{w.zbuf, vmax, arg, N, 1024}, cdiv(1024, 256), S, 1, 256);
+    layer_max(c128, 128, wb + T_CONV3, 1024, vmax, arg, S, 1);
     layer(vmax, 1024, wb + T_FC1, 512, fc1, S, 1);
     layer(fc1, 512, wb + T_FC2, 256, fc2, S, 1);
     layer(fc2, 256, wb + T_FC3, k * k, tout, S, 0);
@@ -203,7 +265,7 @@ struct Chain {
     lin_bwd(wb + T_FC2, fc1, 512, w.dfc2, 256, 256, S, w.dfc1, 0);
     relu_mask(w.dfc1, fc1, (long long)S * 512);
     lin_bwd(wb + T_FC1, vmax, 1024, w.dfc1, 512, 512, S, w.dmax, 0);
-    o.run(KMaxBwdDx{w.dmax, vmax, W[wb + T_CONV3], arg, w.d128, N, 1024, 128}, cdiv(128, 128), cdiv(N, MAXBWD_PTS), S, 128);
+    max_bwd_dx(w.dmax, vmax, W[wb + T_CONV3], arg, w.d128, S, 1024, 128);
     o.run(KMaxBwdDw{w.dmax, vmax, c128, arg, w.G[wb + T_CONV3], w.G[wb + T_CONV3 + 1], S, N, 1024, 128}, cdiv(128, 128), 1024, 1, 128);
     relu_mask(w.d128, c128, R * 128);
     lin_bwd(wb + T_CONV2, c64, 64, w.d128, 128, 128, R, w.d64, 0);
@@ -214,6 +276,7 @@ struct Chain {
   void forward(const TrainIn& in) {
     const int B = in.B, S = 2 * B, P = 2 * N;
     const long long R = (long long)S * N;
+    gemm_f16 = 1;
     if (in.x_pm) o.run(KInterleave{in.x_pm, in.tfd_pm, w.q, N}, cdiv(3 * N, 256), B, 1, 256);
     else o.run(KUpdatePoints{in.pcl, in.kps, in.pose, in.scale, w.q, N}, cdiv(N, 256), B, 1, 256);
     // encoder (pointnets/pointnet.py:97-116), all 2B sets at once
@@ -224,9 +287,8 @@ struct Chain {
     gemm(w.h1, 64, 1, w.t64, 64, 1, w.pf, 64, 1, N, 64, 64, nullptr, 0, 0, S, (long long)N * 64, 4096, (long long)N * 64);  // pf = h1 . T64
     layer(w.pf, 64, W_CONV2, 128, w.a128, R, 1);
     layer(w.a128, 128, W_CONV3, 512, w.a512, R, 1);
-    layer(w.a512, 512, W_CONV4, 1024, w.zbuf, R, 0);  // no ReLU after conv4 (pointnet.py:114)
-    o.run(KColMaxArg{w.zbuf, w.g, w.garg, N, 1024}, cdiv(1024, 256), S, 1, 256);
-    o.run(KColMaxArg{w.pf, w.pfmax, w.pfarg, N, 64}, 1, S, 1, 64);
+    layer_max(w.a512, 512, W_CONV4, 1024, w.g, w.garg, S, 0);  // no ReLU after conv4 (pointnet.py:114)
+    colmax(w.pf, w.pfmax, w.pfarg, S, 64);
     // translation / size head (heads/fc_trans_size_head.py:61-70)
     o.run(KTsGather{w.g, w.pfmax, in.scale, w.ts_in}, cdiv(1091, 256), B, 1, 256);
     layer(w.ts_in, 1091, W_TS + S_L0, 256, w.ts_y0, B, 0);
@@ -244,21 +306,27 @@ struct Chain {
       gn_fwd(w.ry0[h], w.rst0[h], W[rb + R_GN0], W[rb + R_GN0 + 1], w.ru0[h], B, P);
       layer(w.ru0[h], 256, rb + R_L3, 256, w.ry1[h], R, 0);
       gn_fwd(w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1, B, P);
-      o.run(KRotWsum{w.ru1, W[rb + R_CONVP], w.wsum[h], P}, B, 1, 1, 256);
+      rot_wsum(w.ru1, W[rb + R_CONVP], w.wsum[h], B, P);
       o.run(KRotOut{w.wsum[h], W[rb + R_NECK], W[rb + R_NECK + 1], W[rb + R_CONVP], W[rb + R_CONVP + 1], w.r6, P, h}, B, 1, 1, 32);
     }
     o.run(KPoseFwd{w.r6, w.dts, in.pose, in.scale, in.K, in.pose_out, in.scale_out, B}, cdiv(B, 64), 1, 1, 64);
   }
 
   void loss(const TrainIn& in) {
-    o.run(KLoss{in.pose_out, in.scale_out, in.gt_pose, in.gt_scale, in.kps, w.sym_rots, w.is_sym, w.lossp, w.dpose, in.B, N,
-                in.n_rots, in.n_sym, in.n_nosym, in.w_pm, in.w_rot, in.w_trans, in.w_scale}, cdiv(in.B, 32), 1, 1, 32);
+    int chunks = TrainWs::kLossChunks;
+    while (chunks > 1 && N % chunks != 0) chunks >>= 1;
+    o.run(KLossSel{in.pose_out, in.gt_pose, w.sym_rots, w.is_sym, w.loss_gs, in.B, in.n_rots}, cdiv(in.B, 32), 1, 1, 32);
+    o.run(KLossPm{in.pose_out, in.scale_out, in.gt_scale, in.kps, w.loss_gs, w.gn_part, in.B, N, chunks, N / chunks, in.w_pm},
+          cdiv(chunks, 32), in.B, 1, 32);
+    o.run(KLoss{in.pose_out, in.scale_out, in.gt_pose, in.gt_scale, w.gn_part, w.is_sym, w.lossp, w.dpose, in.B, N, chunks,
+                in.n_sym, in.n_nosym, in.w_pm, in.w_rot, in.w_trans, in.w_scale}, cdiv(in.B, 32), 1, 1, 32);
     o.run(KLossSum{w.lossp, w.losses, in.B}, 1, 1, 1, 32);
   }
 
   void backward(const TrainIn& in) {
     const int B = in.B, S = 2 * B, P = 2 * N;
     const long long R = (long long)S * N;
+    gemm_f16 = 0;
     o.zero(w.G[0], w.grad_floats * sizeof(float));
     o.zero(w.dg, (size_t)S * 1024 * sizeof(float));
     o.zero(w.dpfmax, (size_t)S * 64 * sizeof(float));
@@ -280,13 +348,18 @@ struct Chain {
             1, 1, 1, 256);
       const long long n = (long long)B * P * 256;
       o.run(KGnGeluFwd{w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1, P, n}, cdiv(n, 256), 1, 1, 256);  // recompute u1
-      o.run(KRotDwp{w.ru1, w.e, w.d_r6, W[rb + R_NECK + 1], w.G[rb + R_CONVP], B, P, h}, cdiv(P, 128), 1, 1, 128);
+      if ((size_t)B * P * 8 <= TrainWs::kPartialFloats) {
+        o.run(KRotDwpPart{w.ru1, w.e, w.partial, P}, cdiv(8 * P, 256), B, 1, 256);
+        o.run(KRotDwpSum{w.partial, w.d_r6, W[rb + R_NECK + 1], w.G[rb + R_CONVP], B, P, h}, cdiv(P, 128), 1, 1, 128);
+      } else {
+        o.run(KRotDwp{w.ru1, w.e, w.d_r6, W[rb + R_NECK + 1], w.G[rb + R_CONVP], B, P, h}, cdiv(P, 128), 1, 1, 128);
+      }
       o.run(KRotDu1{wp, w.e, w.du, P, n}, cdiv(n, 256), 1, 1, 256);
       gn_bwd(w.du, w.ry1[h], w.rst1[h], rb + R_GN1, B, P);
       lin_bwd(rb + R_L3, w.ru0[h], 256, w.du, 256, 256, R, w.du0, 0);
       gn_bwd(w.du0, w.ry0[h], w.rst0[h], rb + R_GN0, B, P);
       // layer 0: point-feature columns per point, global-feature columns once per set
-      o.run(KColSum{w.du0, w.dcset, R, 256, N, 0, 256}, 1, S, 1, 256);  // dcset[s] = sum over the set's points
+      group_colsum(w.du0, S, N, 256, w.dcset);  // dcset[s] = sum over the set's points
       gemm(w.dcset, 1, 256, w.g, 1024, 1, w.G[rb + R_L0], 1088, 1, 256, 1024, S, nullptr, 0, 1);
       gemm(w.du0, 1, 256, w.pf, 64, 1, w.G[rb + R_L0] + 1024, 1088, 1, 256, 64, (int)R, nullptr, 0, 1);
       colsum(w.dcset, S, 256, 256, w.G[rb + R_L0 + 1], 1);
@@ -295,7 +368,7 @@ struct Chain {
     }
     // ---- encoder
     o.run(KScatterMax{w.dpfmax, w.pfarg, w.dpf, N, 64}, 1, S, 1, 64);
-    o.run(KMaxBwdDx{w.dg, nullptr, W[W_CONV4], w.garg, w.d512, N, 1024, 512}, cdiv(512, 128), cdiv(N, MAXBWD_PTS), S, 128);
+    max_bwd_dx(w.dg, nullptr, W[W_CONV4], w.garg, w.d512, S, 1024, 512);
     o.run(KMaxBwdDw{w.dg, nullptr, w.a512, w.garg, w.G[W_CONV4], w.G[W_CONV4 + 1], S, N, 1024, 512}, cdiv(512, 128), 1024, 1, 128);
     relu_mask(w.d512, w.a512, R * 512);
     lin_bwd(W_CONV3, w.a128, 128, w.d512, 512, 512, R, w.d128, 0);
@@ -307,7 +380,12 @@ struct Chain {
     tnet_bwd(w.h1, 64, W_FSTN, 64, w.f64, w.f128, w.fmax, w.farg, w.ffc1, w.ffc2, w.dt64, w.dh1, S);
     relu_mask(w.dh1, w.h1, R * 64);
     lin_bwd(W_CONV1, w.qp, 3, w.dh1, 64, 64, R, w.dqp, 0);
-    gemm(w.q, 1, 3, w.dqp, 3, 1, w.dt3, 3, 1, 3, 3, N, nullptr, 0, 0, S, (long long)N * 3, (long long)N * 3, 9);  // dT3 = q^T . dq'
+    {  // dT3 = q^T . dq' per set (3 x 3 outputs over N points: chunked sums, then the chunks of a set in order)
+      int chunks = 32;
+      while (chunks > 1 && ((size_t)S * chunks * 9 > TrainWs::kCsFloats || N % chunks != 0)) chunks >>= 1;
+      o.run(KSet3x3Part{w.q, w.dqp, w.cs_partial, N, N / chunks}, 1, chunks, S, 32);
+      o.run(KColSum{w.cs_partial, w.dt3, (long long)S * chunks, 9, chunks, 0, 9}, 1, S, 1, 32);
+    }
     tnet_bwd(w.q, 3, W_STN, 3, w.s64, w.s128, w.smax, w.sarg, w.sfc1, w.sfc2, w.dt3, nullptr, S);
   }
 };

@@ -78,6 +78,7 @@ struct GemmP {
   int M, N, K;
   int relu, accumulate;
   int splits; int k_per; float* partial;
+  int f16;  // tensor-core GEMM only (train_gemm_tc.cuh): 1 = fp16 hi/lo operands (forward), 0 = bf16 hi/lo (backward)
 };
 struct KGemmNaive {
   GemmP p;
@@ -98,14 +99,25 @@ struct KGemmNaive {
     *c = p.accumulate ? *c + acc : acc;
   }
 };
-// fixed-order sum of the split-K partials.  grid (ceil(M * N / nt))
+// fixed-order sum of the split-K partials (+ the GEMM's bias / ReLU when the split was the launcher's choice).
+// grid (ceil(M * N / nt))
 struct KSplitReduce {
   const float* partial; float* C; long long scm, scn; int M, N, splits, accumulate;
+  const float* bias = nullptr; int relu = 0;
   TK_HD void operator()(const Idx& i) const {
     const long long e = (long long)i.bx * i.nt + i.tx;
     if (e >= (long long)M * N) return;
+    const size_t mn = (size_t)M * N;
     float acc = 0.0f;
-    for (int z = 0; z < splits; ++z) acc += partial[(size_t)z * M * N + e];
+    int z = 0;
+    for (; z + 4 <= splits; z += 4) {  // four loads in flight; the additions stay in slice order
+      const float a0 = partial[(size_t)z * mn + e], a1 = partial[(size_t)(z + 1) * mn + e];
+      const float a2 = partial[(size_t)(z + 2) * mn + e], a3 = partial[(size_t)(z + 3) * mn + e];
+      acc += a0; acc += a1; acc += a2; acc += a3;
+    }
+    for (; z < splits; ++z) acc += partial[(size_t)z * mn + e];
+    if (bias) acc += bias[e % N];
+    if (relu) acc = acc > 0.0f ? acc : 0.0f;
     float* c = C + (e / N) * scm + (e % N) * scn;
     *c = accumulate ? *c + acc : acc;
   }
@@ -121,6 +133,34 @@ struct KColMaxArg {
     const float* p = z + (size_t)s * N * C + c;
     float best = p[0]; int bi = 0;
     for (int n = 1; n < N; ++n) { const float v = p[(size_t)n * C]; if (v > best) { best = v; bi = n; } }
+    vmax[(size_t)s * C + c] = best; arg[(size_t)s * C + c] = bi;
+  }
+};
+
+// The same in two stages for more parallelism: stage 1 scans `per` consecutive points per thread, stage 2 merges the chunks in
+// order with a strict comparison, so the first index still wins ties and the result equals KColMaxArg's.
+// stage 1: grid (ceil(C / nt), chunks, S) -> pv / pi [S, chunks, C];  stage 2: grid (ceil(C / nt), S)
+struct KColMaxArgPart {
+  const float* z; float* pv; int* pi; int N, C, per;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.bx * i.nt + i.tx, ch = i.by, s = i.bz;
+    if (c >= C) return;
+    const int n0 = ch * per, n1 = n0 + per < N ? n0 + per : N;
+    const float* p = z + (size_t)s * N * C + c;
+    float best = p[(size_t)n0 * C]; int bi = n0;
+    for (int n = n0 + 1; n < n1; ++n) { const float v = p[(size_t)n * C]; if (v > best) { best = v; bi = n; } }
+    const size_t o = ((size_t)s * ((N + per - 1) / per) + ch) * C + c;
+    pv[o] = best; pi[o] = bi;
+  }
+};
+struct KColMaxArgMerge {
+  const float* pv; const int* pi; float* vmax; int* arg; int chunks, C;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.bx * i.nt + i.tx, s = i.by;
+    if (c >= C) return;
+    const size_t o = (size_t)s * chunks * C + c;
+    float best = pv[o]; int bi = pi[o];
+    for (int ch = 1; ch < chunks; ++ch) { const float v = pv[o + (size_t)ch * C]; if (v > best) { best = v; bi = pi[o + (size_t)ch * C]; } }
     vmax[(size_t)s * C + c] = best; arg[(size_t)s * C + c] = bi;
   }
 };
@@ -194,6 +234,45 @@ struct KMaxBwdDx {
     for (int j = 0; j < MAXBWD_PTS && n0 + j < N; ++j) dx[((size_t)s * N + n0 + j) * K + k] = acc[j];
   }
 };
+// The same result (same summation order: channels ascending) without the C-long scan per output element: first the
+// inverse of the arg-max map, then a gather.
+// Index: for point n of set s, start[s, n] = number of channels whose arg-max point is < n, cnt[s, n] = number whose arg-max
+// is n, and list[s, start .. start + cnt) = those channels, ascending (a counting sort, every thread scanning the set's C
+// entries twice).  grid (ceil(N / nt), S)
+struct KMaxBwdIndex {
+  const int* arg; int *start, *cnt, *list; int N, C;
+  TK_HD void operator()(const Idx& i) const {
+    const int n = i.bx * i.nt + i.tx, s = i.by;
+    if (n >= N) return;
+    const int* a = arg + (size_t)s * C;
+    int lt = 0, eq = 0;
+    for (int c = 0; c < C; ++c) { const int v = a[c]; lt += v < n; eq += v == n; }
+    start[(size_t)s * N + n] = lt; cnt[(size_t)s * N + n] = eq;
+    if (eq == 0) return;
+    int* l = list + (size_t)s * C + lt;
+    for (int c = 0; c < C; ++c)
+      if (a[c] == n) *l++ = c;
+  }
+};
+// dx[(s, n), k] = sum over the point's channels (ascending) of d[s,c] W[c,k]; every element written once.
+// grid (ceil(K / nt), N, S)
+struct KMaxBwdGather {
+  const float *dmax, *relu_max, *W; const int *start, *cnt, *list; float* dx; int N, C, K;
+  TK_HD void operator()(const Idx& i) const {
+    const int k = i.bx * i.nt + i.tx, n = i.by, s = i.bz;
+    if (k >= K) return;
+    const int m = cnt[(size_t)s * N + n];
+    const int* l = list + (size_t)s * C + start[(size_t)s * N + n];
+    float acc = 0.0f;
+    for (int j = 0; j < m; ++j) {
+      const int c = l[j];
+      float d = dmax[(size_t)s * C + c];
+      if (relu_max && !(relu_max[(size_t)s * C + c] > 0.0f)) d = 0.0f;
+      acc += d * W[(size_t)c * K + k];
+    }
+    dx[((size_t)s * N + n) * K + k] = acc;
+  }
+};
 // dW[c, k] += sum_s d[s,c] x[(s, arg[s,c]), k];  db[c] += sum_s d[s,c].  grid (ceil(K / nt), C)
 struct KMaxBwdDw {
   const float *dmax, *relu_max, *x; const int* arg; float *dW, *db; int S, N, C, K;
@@ -245,10 +324,14 @@ struct KGnStats {
     const int b = i.bx, g = i.tx;
     if (g >= 32) return;
     double s = 0.0, ss = 0.0;
-    for (int ch = 0; ch < chunks; ++ch) {
-      const double* o = part + (((size_t)b * chunks + ch) * 32 + g) * 2;
-      s += o[0]; ss += o[1];
+    const double* o = part + ((size_t)b * chunks * 32 + g) * 2;
+    int ch = 0;
+    for (; ch + 4 <= chunks; ch += 4) {  // the loads of four chunks in flight; the additions stay in chunk order
+      const double a0 = o[(size_t)ch * 64], b0 = o[(size_t)ch * 64 + 1], a1 = o[(size_t)(ch + 1) * 64], b1 = o[(size_t)(ch + 1) * 64 + 1];
+      const double a2 = o[(size_t)(ch + 2) * 64], b2 = o[(size_t)(ch + 2) * 64 + 1], a3 = o[(size_t)(ch + 3) * 64], b3 = o[(size_t)(ch + 3) * 64 + 1];
+      s += a0; ss += b0; s += a1; ss += b1; s += a2; ss += b2; s += a3; ss += b3;
     }
+    for (; ch < chunks; ++ch) { s += o[(size_t)ch * 64]; ss += o[(size_t)ch * 64 + 1]; }
     const double cnt = 8.0 * P, mu = s / cnt;
     double var = ss / cnt - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -295,20 +378,23 @@ struct KGnBwdPart {
     for (int j = 0; j < 8; ++j) { o[2 + j] = dga[j]; o[10 + j] = dbe[j]; }
   }
 };
+// stage 2: one thread per (object, group, entry of the 18): grid (B), nt = 32 * 18 (consecutive threads read consecutive doubles)
 struct KGnBwdSums {
   const double* part; float *m, *dgam, *dbet; int P, chunks;
   TK_HD void operator()(const Idx& i) const {
-    const int b = i.bx, g = i.tx;
+    const int b = i.bx, g = i.tx / 18, j = i.tx % 18;
     if (g >= 32) return;
-    double a[18];
-    for (int j = 0; j < 18; ++j) a[j] = 0.0;
-    for (int ch = 0; ch < chunks; ++ch) {
-      const double* o = part + (((size_t)b * chunks + ch) * 32 + g) * 18;
-      for (int j = 0; j < 18; ++j) a[j] += o[j];
+    double a = 0.0;
+    const double* o = part + (size_t)b * chunks * 576 + g * 18 + j;
+    int ch = 0;
+    for (; ch + 4 <= chunks; ch += 4) {
+      const double a0 = o[(size_t)ch * 576], a1 = o[(size_t)(ch + 1) * 576], a2 = o[(size_t)(ch + 2) * 576], a3 = o[(size_t)(ch + 3) * 576];
+      a += a0; a += a1; a += a2; a += a3;
     }
-    m[((size_t)b * 32 + g) * 2 + 0] = (float)(a[0] / (8.0 * P));
-    m[((size_t)b * 32 + g) * 2 + 1] = (float)(a[1] / (8.0 * P));
-    for (int j = 0; j < 8; ++j) { dgam[(size_t)b * 256 + g * 8 + j] = (float)a[2 + j]; dbet[(size_t)b * 256 + g * 8 + j] = (float)a[10 + j]; }
+    for (; ch < chunks; ++ch) a += o[(size_t)ch * 576];
+    if (j < 2) m[((size_t)b * 32 + g) * 2 + j] = (float)(a / (8.0 * P));
+    else if (j < 10) dgam[(size_t)b * 256 + g * 8 + (j - 2)] = (float)a;
+    else dbet[(size_t)b * 256 + g * 8 + (j - 10)] = (float)a;
   }
 };
 // pass 2: dy = rstd (g - m1 - xhat m2), written over du.  grid (ceil(B * P * 256 / nt))
@@ -337,6 +423,20 @@ struct KRotWsum {
     float acc = 0.0f;
     for (int p = 0; p < P; ++p) acc = fmaf(wp[p], u[(size_t)p * 256], acc);
     wsum[(size_t)b * 256 + c] = acc;
+  }
+};
+// Two stages for more parallelism: part[b, ch, c] = sum over the chunk's points (grid (1, chunks, B), nt = 256), then KColSum
+// over the chunks of an object (rows_per = chunks).
+struct KRotWsumPart {
+  const float *u1, *wp; float* part; int P, per;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.tx, ch = i.by, b = i.bz;
+    if (c >= 256) return;
+    const int p0 = ch * per, p1 = p0 + per < P ? p0 + per : P;
+    const float* u = u1 + (size_t)b * P * 256 + c;
+    float acc = 0.0f;
+    for (int p = p0; p < p1; ++p) acc = fmaf(wp[p], u[(size_t)p * 256], acc);
+    part[((size_t)b * ((P + per - 1) / per) + ch) * 256 + c] = acc;
   }
 };
 // r6[b, 3h + j] = Wn[j, :] . wsum[b, :] + bn[j] sum_p wp[p] + bp.  grid (B), nt >= 3
@@ -409,6 +509,54 @@ struct KRotDwp {
   }
 };
 
+// The same in two stages: part[b, p, q] = u1[b, p, 32 q .. 32 q + 31] . e[b, same] (one thread per 128-byte line of u1; grid
+// (ceil(8 P / nt), B)), then dwp[p] += sum_b (sum_q part[b, p, q] + dr[b, :] . bn) (grid (ceil(P / nt))).
+struct KRotDwpPart {
+  const float *u1, *e; float* part; int P;
+  TK_HD void operator()(const Idx& i) const {
+    const int x = i.bx * i.nt + i.tx, b = i.by;
+    if (x >= 8 * P) return;
+    const int p = x >> 3, q = x & 7;
+    const float* u = u1 + ((size_t)b * P + p) * 256 + q * 32;
+    const float* eb = e + (size_t)b * 256 + q * 32;
+    float a = 0.0f;
+    for (int c = 0; c < 32; ++c) a = fmaf(u[c], eb[c], a);
+    part[((size_t)b * P + p) * 8 + q] = a;
+  }
+};
+struct KRotDwpSum {
+  const float *part, *d_r6, *bn; float* dwp; int B, P, h;
+  TK_HD void operator()(const Idx& i) const {
+    const int p = i.bx * i.nt + i.tx;
+    if (p >= P) return;
+    float acc = 0.0f;
+    for (int b = 0; b < B; ++b) {
+      const float* pp = part + ((size_t)b * P + p) * 8;
+      float a = 0.0f;
+      for (int q = 0; q < 8; ++q) a += pp[q];
+      const float* dr = d_r6 + (size_t)b * 6 + 3 * h;
+      acc += a + dr[0] * bn[0] + dr[1] * bn[1] + dr[2] * bn[2];
+    }
+    dwp[p] += acc;
+  }
+};
+
+// per-set 3 x 3 products over the set's points, stage 1: part[s, ch, 3 i + j] = sum over the chunk's points n of
+// a[s, n, i] b[s, n, j]  (dT3 = q^T dq').  grid (1, chunks, S), nt >= 9; stage 2 is KColSum with rows_per = chunks.
+struct KSet3x3Part {
+  const float *a, *b; float* part; int N, per;
+  TK_HD void operator()(const Idx& i) const {
+    const int ij = i.tx, ch = i.by, s = i.bz;
+    if (ij >= 9) return;
+    const int n0 = ch * per, n1 = n0 + per < N ? n0 + per : N;
+    const float* pa = a + (size_t)s * N * 3 + ij / 3;
+    const float* pb = b + (size_t)s * N * 3 + ij % 3;
+    float acc = 0.0f;
+    for (int n = n0; n < n1; ++n) acc = fmaf(pa[(size_t)n * 3], pb[(size_t)n * 3], acc);
+    part[((size_t)s * ((N + per - 1) / per) + ch) * 9 + ij] = acc;
+  }
+};
+
 // ---- ts-head input gather / gradient scatter (CATRE_disR_shared.py:66-82): ts_in[b] = [g(2b) | pfmax(2b) | s_b]
 //      grid (ceil(1091 / nt), B)
 struct KTsGather {
@@ -470,10 +618,13 @@ struct KPoseFwd {
 //      core/utils/pose_utils.py:472-528; oracle: catre_loss / loss_backward).  One thread per object.
 //      lossp [B, 6] = this object's share of (PM_R, rot, yaxis_rot, trans_xy, trans_z, scale);
 //      dpose [B, 15] = d/d(R' row-major 9, t' 3, s' 3).  grid (ceil(B / nt))
-struct KLoss {
-  const float *pose, *scale, *gt_pose, *gt_scale, *kps, *sym_rots; const unsigned char* is_sym;
-  float *lossp, *dpose; int B, N, n_rots, n_sym, n_nosym;
-  float w_pm, w_rot, w_trans, w_scale;  // LOSS_CFG.PM_LW, ROT_LW, TRANS_LW, SCALE_LW (all 1 in the shipped config)
+// Three stages: (1) KLossSel, one thread per object: the ground-truth rotation the point-matching term compares with (for a
+// symmetric object the closest of its symmetric copies) -> gs [B, 9]; (2) KLossPm, one thread per (object, chunk of points): the
+// chunk's share of the point-matching loss and of its gradients -> pm [B, chunks, 13] doubles (|diff| sum, dR 9, ds 3);
+// (3) KLoss, one thread per object: sums the chunks in order and adds the rotation / translation / scale terms.
+// grids: (ceil(B / nt)), (chunks, B) with nt = 1 .. any (thread tx > 0 idle) -- launched as (ceil(chunks / nt), B), (ceil(B / nt))
+struct KLossSel {
+  const float *pose, *gt_pose, *sym_rots; const unsigned char* is_sym; float* gs; int B, n_rots;
   TK_HD void operator()(const Idx& i) const {
     const int b = i.bx * i.nt + i.tx;
     if (b >= B) return;
@@ -481,8 +632,7 @@ struct KLoss {
     const float* Gp = gt_pose + (size_t)b * 12;
     float R[9], G[9], Gs[9];
     for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { R[r * 3 + c] = Pp[r * 4 + c]; G[r * 3 + c] = Gp[r * 4 + c]; Gs[r * 3 + c] = G[r * 3 + c]; }
-    const bool sym = is_sym[b] != 0;
-    if (sym) {  // closest symmetric ground truth: largest clamped cosine of the rotation error, strict improvement only
+    if (is_sym[b] != 0) {  // closest symmetric ground truth: largest clamped cosine of the rotation error, strict improvement only
       float tr = 0.0f;
       for (int e = 0; e < 9; ++e) tr += R[e] * G[e];
       float best = fminf(1.0f, fmaxf(-1.0f, 0.5f * ((tr <= 3.0f ? tr : 3.0f) - 1.0f)));
@@ -496,12 +646,24 @@ struct KLoss {
         if (cs > best) { best = cs; for (int e = 0; e < 9; ++e) Gs[e] = C[e]; }
       }
     }
+    for (int e = 0; e < 9; ++e) gs[(size_t)b * 9 + e] = Gs[e];
+  }
+};
+struct KLossPm {
+  const float *pose, *scale, *gt_scale, *kps, *gs; double* pm; int B, N, chunks, per; float w_pm;
+  TK_HD void operator()(const Idx& i) const {
+    const int ch = i.bx * i.nt + i.tx, b = i.by;
+    if (ch >= chunks) return;
+    const float* Pp = pose + (size_t)b * 12;
+    float R[9], Gs[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { R[r * 3 + c] = Pp[r * 4 + c]; Gs[r * 3 + c] = gs[(size_t)b * 9 + r * 3 + c]; }
     const float* s = scale + (size_t)b * 3;
     const float* sg = gt_scale + (size_t)b * 3;
     float dR[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0}, ds[3] = {0, 0, 0};
-    double pm = 0.0;
+    double pmv = 0.0;
     const float inv_bn = w_pm / ((float)B * (float)N);
-    for (int n = 0; n < N; ++n) {
+    const int n0 = ch * per, n1 = n0 + per < N ? n0 + per : N;
+    for (int n = n0; n < n1; ++n) {
       const float* k = kps + ((size_t)b * N + n) * 3;
       const float sk[3] = {k[0] * s[0], k[1] * s[1], k[2] * s[2]};
       const float gk[3] = {k[0] * sg[0], k[1] * sg[1], k[2] * sg[2]};
@@ -509,12 +671,40 @@ struct KLoss {
       for (int r = 0; r < 3; ++r) {
         const float diff = (R[r * 3] * sk[0] + R[r * 3 + 1] * sk[1] + R[r * 3 + 2] * sk[2]) -
                            (Gs[r * 3] * gk[0] + Gs[r * 3 + 1] * gk[1] + Gs[r * 3 + 2] * gk[2]);
-        pm += fabsf(diff);
+        pmv += fabsf(diff);
         de[r] = tk_sign(diff) * inv_bn;
         for (int c = 0; c < 3; ++c) dR[r * 3 + c] += de[r] * sk[c];
       }
       for (int c = 0; c < 3; ++c) ds[c] += (R[c] * de[0] + R[3 + c] * de[1] + R[6 + c] * de[2]) * k[c];
     }
+    double* o = pm + ((size_t)b * chunks + ch) * 13;
+    o[0] = pmv;
+    for (int e = 0; e < 9; ++e) o[1 + e] = dR[e];
+    for (int c = 0; c < 3; ++c) o[10 + c] = ds[c];
+  }
+};
+struct KLoss {
+  const float *pose, *scale, *gt_pose, *gt_scale; const double* pmp; const unsigned char* is_sym;
+  float *lossp, *dpose; int B, N, chunks, n_sym, n_nosym;
+  float w_pm, w_rot, w_trans, w_scale;  // LOSS_CFG.PM_LW, ROT_LW, TRANS_LW, SCALE_LW (all 1 in the shipped config)
+  TK_HD void operator()(const Idx& i) const {
+    const int b = i.bx * i.nt + i.tx;
+    if (b >= B) return;
+    const float* Pp = pose + (size_t)b * 12;
+    const float* Gp = gt_pose + (size_t)b * 12;
+    float R[9], G[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { R[r * 3 + c] = Pp[r * 4 + c]; G[r * 3 + c] = Gp[r * 4 + c]; }
+    const bool sym = is_sym[b] != 0;
+    const float* s = scale + (size_t)b * 3;
+    const float* sg = gt_scale + (size_t)b * 3;
+    double acc[13];
+    for (int e = 0; e < 13; ++e) acc[e] = 0.0;
+    for (int ch = 0; ch < chunks; ++ch)
+      for (int e = 0; e < 13; ++e) acc[e] += pmp[((size_t)b * chunks + ch) * 13 + e];
+    float dR[9], ds[3];
+    for (int e = 0; e < 9; ++e) dR[e] = (float)acc[1 + e];
+    for (int c = 0; c < 3; ++c) ds[c] = (float)acc[10 + c];
+    const double pm = acc[0];
     float* L = lossp + (size_t)b * 6;
     L[0] = w_pm * (float)(pm / ((double)B * N));  // PM_LW * 3 * mean over B*N*3
     L[1] = L[2] = 0.0f;

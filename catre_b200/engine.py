@@ -61,6 +61,9 @@ SYMBOLS = {
     "catre_ranger_step": (ctypes.c_int, [_F, _F, _F, _F, ctypes.c_int32, ctypes.c_int64, ctypes.c_int64, _F, _P, _P]),
     "catre_last_launch_count": (ctypes.c_int64, [_P]),
     "catre_debug_read": (ctypes.c_int, [_P, ctypes.c_char_p, _P, ctypes.c_size_t]),
+    "catre_debug_train_gemm": (ctypes.c_int, [_F, _F, _F, _F, ctypes.POINTER(ctypes.c_int64), ctypes.c_int32, ctypes.c_int32, ctypes.c_int32,
+                                              ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _F, ctypes.c_int32,
+                                              ctypes.c_int32, _F, _P, _P]),
     "catre_profile_enable": (ctypes.c_int, [_P, ctypes.c_int32]),
     "catre_profile_reset": (ctypes.c_int, [_P]),
     "catre_profile_num": (ctypes.c_int32, []),

@@ -286,6 +286,19 @@ int64_t catre_last_launch_count(const catre_engine* e);
  * ("t3", "t64", "gmax_g", "cset", ...) of the last launch to host memory. */
 int catre_debug_read(catre_engine* e, const char* name, void* dst_host, size_t bytes);
 
+/* Debug entry (tests / tools only): one GEMM of the training chain, C(m,n,z) = act(sum_k A(m,k,z) B(k,n,z) + bias(n)) [+ C],
+ * with the chain's own strided / batched parameters, on device buffers.  `strides` = {sam, sak, sab, sbk, sbn, sbb, scm, scn, scb}
+ * (elements), `kernel`: 0 = CUDA-core tile kernel, 1 = tcgen05 kernel with fp16 hi/lo operands (the forward GEMMs of
+ * catre_train_step, reference modules: pointnets/pointnet.py:24-41,97-116 and the heads' Conv1d / Linear layers),
+ * 2 = tcgen05 kernel with bf16 hi/lo operands (the backward GEMMs).  `splits` > 1 (batch must be 1) sums k in `splits` slices
+ * through `partial` (>= splits * M * N floats) in a fixed order.  With `vmax` != NULL (kernel 1 or 2 only) the output is not
+ * stored: it is max-pooled over each group of `rows_per_set` consecutive rows (a multiple of 128 dividing M) inside the GEMM's
+ * epilogue -> vmax [M / rows_per_set, N] and the row index inside the group arg [.., N] (first index wins ties, like torch.max;
+ * pointnets/pointnet.py:32,65,115); `partial` then needs 2 * (M / rows_per_set) * N floats. */
+int catre_debug_train_gemm(const float* A, const float* B, float* C, const float* bias, const int64_t* strides, int32_t M, int32_t N,
+                           int32_t K, int32_t batch, int32_t relu, int32_t accumulate, int32_t splits, float* partial,
+                           int32_t kernel, int32_t rows_per_set, float* vmax, int32_t* arg, void* stream);
+
 /* Average device time (ms, CUDA events on the launching stream) of the kernel group `which` over the
  * calls since catre_profile_reset; `which` indexes catre_profile_name().  Profiling is off by default
  * (events cost launches); enable with catre_profile_enable(e, 1).  Used by bench.py's roofline leg. */

@@ -35,6 +35,7 @@ struct EmuOps {
     memset(p, 0, bytes);
 #endif
   }
+  bool gemm_colmax(const GemmP&, int, float*, int*, int, size_t) { return false; }  // no fused pooling here: layer + colmax
   void gemm(const GemmP& p, int batch_or_splits) {
     gemm_macs += (double)p.M * p.N * p.K * (p.splits > 1 ? 1 : batch_or_splits);
     run(KGemmNaive{p}, (unsigned)((p.M + 3) / 4), (unsigned)((p.N + 63) / 64), (unsigned)batch_or_splits, 256);
@@ -82,7 +83,8 @@ extern "C" int emu_train_step(const float* const* weights, int B, int N, const f
     F(w.dg, S * 1024); F(w.dpfmax, S * 64); F(w.dpf, R * 64); F(w.e, Bz * 256); F(w.du, R * 256); F(w.du0, R * 256);
     F(w.dcset, S * 256); F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
     F(w.dfc2, S * 256); F(w.dfc1, S * 512); F(w.dmax, S * 1024); F(w.dqp, R * 3); F(w.dt3, S * 9);
-    F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, (size_t)64 * 4096);
+    F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, TrainWs::kCsFloats); F(w.loss_gs, Bz * 9);
+    I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024);
     sl.push_back({reinterpret_cast<char*>(w.gn_part), Bz * TrainWs::kGnChunks * 32 * 18 * sizeof(double)});
     sl.push_back({reinterpret_cast<char*>(w.is_sym), Bz});
     F(w.sym_rots, (size_t)TrainWs::kMaxSymRots * 9);

@@ -22,7 +22,9 @@ def main():
         x_pm = (d.pcl - d.init_pose[:, :, 3].unsqueeze(1)).contiguous()
         tfd_pm = ((d.prior * d.init_scale.unsqueeze(1)) @ d.init_pose[:, :, :3].transpose(1, 2)).contiguous()
         gp, gs = tgt.gt_pose.cuda(), tgt.gt_scale.cuda()
-        for naive, ver in (("0", "v1"), ("0", "v2"), ("1", "v1")):
+        modes = os.environ.get("TRAIN_PROBE_MODES", "tc,simt").split(",")
+        for ver in modes:  # tc (default: tcgen05 GEMM for the large shapes), simt (64 x 64 CUDA-core tiles), v2, naive
+            naive = "1" if ver == "naive" else "0"
             os.environ["CATRE_TRAIN_NAIVE_GEMM"] = naive
             os.environ["CATRE_TRAIN_GEMM"] = ver
             eng = engine.Engine(1024, 8, "fp32", 0)
@@ -38,7 +40,7 @@ def main():
                 step()
             b.record()
             torch.cuda.synchronize()
-            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": "naive" if naive == "1" else "tiled-" + ver,
+            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": ver,
                               "ms_per_step": a.elapsed_time(b) / n, "launches": eng.last_launch_count(),
                               "objects_per_s": B / (a.elapsed_time(b) / n / 1e3)}), flush=True)
             eng.close()
