@@ -525,7 +525,7 @@ def main():
             b_.record()
             torch.cuda.synchronize()
             tms = a.elapsed_time(b_) / 5
-            train_leg = {"what": "catre_train_step: forward + shipped losses + backward of one refinement iteration, fp32 CUDA cores",
+            train_leg = {"what": "catre_train_step: forward + shipped losses + backward of one refinement iteration, tcgen05 GEMMs (fp32 operands split to 16-bit hi/lo pairs, 3 products) + CUDA-core reductions",
                          "objects": 16, "n_pts": N, "ms_per_step": tms, "objects_per_s": 16 / (tms * 1e-3),
                          "launches": eng.last_launch_count(), "sum_of_losses": float(tl.sum().item())}
         except Exception as exc:  # informational leg: report, never fail the bench line
