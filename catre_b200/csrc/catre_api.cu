@@ -152,6 +152,20 @@ struct catre_engine {
   std::map<std::string, bool> dw_dirty;  // tensors refreshed by catre_train_set_weight since the last pack
   float loss_w[4] = {1.0f, 1.0f, 1.0f, 1.0f};  // PM_LW, ROT_LW, TRANS_LW, SCALE_LW
   bool train_naive_gemm = false;         // CATRE_TRAIN_NAIVE_GEMM=1: one-thread-per-output GEMM (debug reference)
+  // CUDA graphs of the training chain (default; CATRE_TRAIN_GRAPH=0 launches the chain kernel by kernel).  The chain's launch
+  // geometry depends on (B, number of symmetric objects, number of symmetry rotations, loss weights, GEMM mode) only; its
+  // inputs / outputs are engine-owned static buffers (tg_io) filled / drained by plain copies around the graph launch, so a
+  // graph stays valid whatever tensors the caller passes.  The first step of a key runs kernel by kernel (it also configures
+  // the kernels' attributes), the second is captured on `cap` (torch's default stream is the legacy stream, which cannot be
+  // captured) and every later one is a single cudaGraphLaunch on the caller's stream.
+  struct TrainGraphKey {
+    int B, n_sym, n_rots, mode; float lw[4];
+    bool operator<(const TrainGraphKey& o) const { return memcmp(this, &o, sizeof(*this)) < 0; }
+  };
+  struct TrainGraph { cudaGraphExec_t exec = nullptr; int64_t launches = 0; int seen = 0; };
+  std::map<TrainGraphKey, TrainGraph> train_graphs;
+  cudaStream_t cap = nullptr;
+  float* tg_io = nullptr;                // [x_pm | tfd_pm | obj_kps | pose | scale | K | gt_pose | gt_scale | out_pose | out_scale]
 
   // ---- accounting
   int64_t launches = 0;
@@ -915,6 +929,9 @@ void catre_destroy(catre_engine* e) {
   cudaSetDevice(e->cfg.device);
   for (void* p : e->dev_allocs) cudaFree(p);
   if (e->tws_mem) cudaFree(e->tws_mem);
+  for (auto& kv : e->train_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+  if (e->tg_io) cudaFree(e->tg_io);
+  if (e->cap) cudaStreamDestroy(e->cap);
   if (e->side) cudaStreamDestroy(e->side);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
@@ -1397,6 +1414,32 @@ int catre_train_set_weight(catre_engine* e, const char* name, const float* src_d
   return CATRE_OK;
 }
 
+int catre_train_set_weights(catre_engine* e, const float* const* src_dev, void* stream) {
+  if (!e) return CATRE_ERR_INVALID_ARG;
+  if (!src_dev) return fail(e, CATRE_ERR_INVALID_ARG, "catre_train_set_weights: null argument");
+  static_assert(kNumWeights <= catre_train::KMultiCopy::kMax, "pointer table of KMultiCopy");
+  if (e->dw.size() != (size_t)kNumWeights)
+    return fail(e, CATRE_ERR_NOT_PACKED, "catre_train_set_weights needs one earlier catre_pack (it allocates the device copies)");
+  catre_train::KMultiCopy k{};
+  int n_max = 0, n_set = 0;
+  for (int i = 0; i < kNumWeights; ++i) {
+    k.src[i] = src_dev[i];
+    k.dst[i] = e->dw.at(kWeights[i].name);
+    k.n[i] = (int)catre_train::weight_numel(i, e->N);
+    if (!src_dev[i]) continue;
+    ++n_set;
+    if (k.n[i] > n_max) n_max = k.n[i];
+    e->dw_dirty[kWeights[i].name] = true;
+  }
+  if (n_set == 0) return CATRE_OK;
+  CU_TRY(e, cudaSetDevice(e->cfg.device));
+  k.per = 8192;
+  catre_train::tk_run<<<dim3((unsigned)((n_max + k.per - 1) / k.per), (unsigned)kNumWeights), 256, 0, (cudaStream_t)stream>>>(k);
+  CU_TRY(e, cudaGetLastError());
+  e->packed = false;
+  return CATRE_OK;
+}
+
 int catre_train_set_loss_weights(catre_engine* e, float pm_lw, float rot_lw, float trans_lw, float scale_lw) {
   if (!e) return CATRE_ERR_INVALID_ARG;
   const float w[4] = {pm_lw, rot_lw, trans_lw, scale_lw};
@@ -1429,7 +1472,10 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   cudaStream_t s = (cudaStream_t)stream;
   if (B > e->tws_maxB) {  // (re)allocate the workspace; not on the steady-state path
     CU_TRY(e, cudaStreamSynchronize(s));
+    for (auto& kv : e->train_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);  // they hold the old pointers
+    e->train_graphs.clear();
     if (e->tws_mem) { CU_TRY(e, cudaFree(e->tws_mem)); e->tws_mem = nullptr; e->tws_maxB = 0; }
+    if (e->tg_io) { CU_TRY(e, cudaFree(e->tg_io)); e->tg_io = nullptr; }
     catre_train::TrainWs probe;
     const size_t bytes = catre_train::ws_layout(probe, B, e->N, nullptr);
     void* mem = nullptr;
@@ -1441,6 +1487,8 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
     e->tws_mem = static_cast<char*>(mem);
     catre_train::ws_layout(e->tws, B, e->N, e->tws_mem);
     e->tws_maxB = B;
+    CU_TRY(e, cudaMalloc(&mem, ((size_t)9 * B * e->N + (size_t)64 * B) * sizeof(float)));
+    e->tg_io = static_cast<float*>(mem);
   }
   catre_train::TrainWs& w = e->tws;
   int n_sym = 0;
@@ -1453,20 +1501,76 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   for (int i = 0; i < kNumWeights; ++i) Wp[i] = e->dw.at(kWeights[i].name);
   const char* env = getenv("CATRE_TRAIN_NAIVE_GEMM");
   const char* env2 = getenv("CATRE_TRAIN_GEMM");
+  const char* env3 = getenv("CATRE_TRAIN_GRAPH");
   const bool naive_gemm = e->train_naive_gemm || (env && env[0] == '1'), gemm_v2 = env2 && strcmp(env2, "v2") == 0;
-  CudaTrainOps ops{s, naive_gemm, gemm_v2, !naive_gemm && !gemm_v2 && !(env2 && strcmp(env2, "simt") == 0), e->num_sms};
-  catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
-  catre_train::TrainIn in{nullptr, obj_kps, pose, scale, K, gt_pose, gt_scale, B, n_sym_rots, n_sym, B - n_sym, out_pose, out_scale};
-  in.x_pm = x_pm; in.tfd_pm = tfd_pm;
-  in.w_pm = e->loss_w[0]; in.w_rot = e->loss_w[1]; in.w_trans = e->loss_w[2]; in.w_scale = e->loss_w[3];
-  chain.forward(in);
-  chain.loss(in);
-  chain.backward(in);
-  ops.note(cudaMemcpyAsync(out_losses, w.losses, 6 * sizeof(float), cudaMemcpyDefault, s));
-  e->launches = ops.launches;
-  if (ops.err != cudaSuccess) {
+  const bool gemm_tc = !naive_gemm && !gemm_v2 && !(env2 && strcmp(env2, "simt") == 0);
+  auto make_in = [&](const float* x, const float* tfd, const float* kps, const float* po, const float* sc, const float* Kz,
+                     const float* gp, const float* gs, float* op, float* os) {
+    catre_train::TrainIn in{nullptr, kps, po, sc, Kz, gp, gs, B, n_sym_rots, n_sym, B - n_sym, op, os};
+    in.x_pm = x; in.tfd_pm = tfd;
+    in.w_pm = e->loss_w[0]; in.w_rot = e->loss_w[1]; in.w_trans = e->loss_w[2]; in.w_scale = e->loss_w[3];
+    return in;
+  };
+  auto run_chain = [&](cudaStream_t st, const catre_train::TrainIn& in, int64_t& n_launch) -> cudaError_t {
+    CudaTrainOps ops{st, naive_gemm, gemm_v2, gemm_tc, e->num_sms};
+    catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
+    chain.forward(in);
+    chain.loss(in);
+    chain.backward(in);
+    n_launch = ops.launches;
+    return ops.err;
+  };
+  cudaError_t cerr = cudaSuccess;
+  bool done = false;
+  if (!(env3 && env3[0] == '0')) {
+    catre_engine::TrainGraphKey key{};
+    key.B = B; key.n_sym = n_sym; key.n_rots = n_sym_rots; key.mode = naive_gemm ? 1 : (gemm_v2 ? 2 : (gemm_tc ? 0 : 3));
+    for (int i = 0; i < 4; ++i) key.lw[i] = e->loss_w[i];
+    if (e->train_graphs.size() > 64 && !e->train_graphs.count(key)) {  // bound the cache (each graph holds ~240 nodes)
+      CU_TRY(e, cudaStreamSynchronize(s));
+      for (auto& kv : e->train_graphs) if (kv.second.exec) cudaGraphExecDestroy(kv.second.exec);
+      e->train_graphs.clear();
+    }
+    catre_engine::TrainGraph& g = e->train_graphs[key];
+    if (g.seen > 0) {
+      const size_t pts = (size_t)B * e->N * 3;
+      float* io = e->tg_io;
+      float *sx = io, *st = sx + pts, *sk = st + pts, *spo = sk + pts, *ssc = spo + 12 * B, *sK = ssc + 4 * B, *sgp = sK + 12 * B,
+            *sgs = sgp + 12 * B, *sop = sgs + 4 * B, *sos = sop + 12 * B;  // every slice a multiple of 4 floats: 16-byte aligned
+      if (!g.exec) {
+        if (!e->cap) CU_TRY(e, cudaStreamCreateWithFlags(&e->cap, cudaStreamNonBlocking));
+        cudaGraph_t graph = nullptr;
+        CU_TRY(e, cudaStreamBeginCapture(e->cap, cudaStreamCaptureModeThreadLocal));
+        cerr = run_chain(e->cap, make_in(sx, st, sk, spo, ssc, sK, sgp, sgs, sop, sos), g.launches);
+        cudaError_t eend = cudaStreamEndCapture(e->cap, &graph);
+        if (cerr == cudaSuccess) cerr = eend;
+        if (cerr == cudaSuccess) cerr = cudaGraphInstantiate(&g.exec, graph, 0);
+        if (graph) cudaGraphDestroy(graph);
+        if (cerr != cudaSuccess) {
+          cudaGetLastError();
+          g.exec = nullptr;
+          return fail(e, CATRE_ERR_CUDA, "catre_train_step: capturing the chain as a CUDA graph: %s (CATRE_TRAIN_GRAPH=0 launches it "
+                      "kernel by kernel)", cudaGetErrorString(cerr));
+        }
+      }
+      const struct { float* dst; const float* src; size_t n; } cp[8] = {
+          {sx, x_pm, pts}, {st, tfd_pm, pts}, {sk, obj_kps, pts}, {spo, pose, (size_t)12 * B}, {ssc, scale, (size_t)3 * B},
+          {sK, K, (size_t)9 * B}, {sgp, gt_pose, (size_t)12 * B}, {sgs, gt_scale, (size_t)3 * B}};
+      for (const auto& c : cp) CU_TRY(e, cudaMemcpyAsync(c.dst, c.src, c.n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      CU_TRY(e, cudaGraphLaunch(g.exec, s));
+      CU_TRY(e, cudaMemcpyAsync(out_pose, sop, (size_t)12 * B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      CU_TRY(e, cudaMemcpyAsync(out_scale, sos, (size_t)3 * B * sizeof(float), cudaMemcpyDeviceToDevice, s));
+      e->launches = g.launches;
+      done = true;
+    } else {
+      g.seen = 1;  // this step runs kernel by kernel (and sets the kernels' attributes); the next one of this key is captured
+    }
+  }
+  if (!done) cerr = run_chain(s, make_in(x_pm, tfd_pm, obj_kps, pose, scale, K, gt_pose, gt_scale, out_pose, out_scale), e->launches);
+  if (cerr == cudaSuccess) cerr = cudaMemcpyAsync(out_losses, w.losses, 6 * sizeof(float), cudaMemcpyDefault, s);
+  if (cerr != cudaSuccess) {
     cudaGetLastError();
-    return fail(e, CATRE_ERR_CUDA, "catre_train_step: %s", cudaGetErrorString(ops.err));
+    return fail(e, CATRE_ERR_CUDA, "catre_train_step: %s", cudaGetErrorString(cerr));
   }
   return CATRE_OK;
 }

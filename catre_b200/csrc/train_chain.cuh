@@ -315,7 +315,15 @@ struct Chain {
   void loss(const TrainIn& in) {
     int chunks = TrainWs::kLossChunks;
     while (chunks > 1 && N % chunks != 0) chunks >>= 1;
-    o.run(KLossSel{in.pose_out, in.gt_pose, w.sym_rots, w.is_sym, w.loss_gs, in.B, in.n_rots}, cdiv(in.B, 32), 1, 1, 32);
+    // the search over the symmetric copies in chunks of 8 rotations (cs_partial is free between forward and backward)
+    int sel_per = 8;
+    while ((size_t)in.B * cdiv(in.n_rots, sel_per) * 2 > TrainWs::kCsFloats) sel_per *= 2;
+    const int sel_chunks = (int)cdiv(in.n_rots, sel_per);
+    if (sel_chunks > 0)
+      o.run(KLossSelPart{in.pose_out, in.gt_pose, w.sym_rots, w.is_sym, w.cs_partial, in.B, in.n_rots, sel_chunks, sel_per},
+            cdiv(sel_chunks, 32), in.B, 1, 32);
+    o.run(KLossSel{in.pose_out, in.gt_pose, w.sym_rots, w.is_sym, w.cs_partial, w.loss_gs, in.B, in.n_rots, sel_chunks},
+          cdiv(in.B, 32), 1, 1, 32);
     o.run(KLossPm{in.pose_out, in.scale_out, in.gt_scale, in.kps, w.loss_gs, w.gn_part, in.B, N, chunks, N / chunks, in.w_pm},
           cdiv(chunks, 32), in.B, 1, 32);
     o.run(KLoss{in.pose_out, in.scale_out, in.gt_pose, in.gt_scale, w.gn_part, w.is_sym, w.lossp, w.dpose, in.B, N, chunks,

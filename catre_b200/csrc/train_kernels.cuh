@@ -12,6 +12,7 @@
 #pragma once
 #include <math.h>
 #include <stdint.h>
+#include <string.h>
 
 #ifdef CATRE_HOST_EMU
 #define TK_HD inline
@@ -30,6 +31,8 @@ TK_HD float tk_gelu(float x) { return 0.5f * x * (1.0f + erff(x * 0.707106781186
 TK_HD float tk_gelu_grad(float x) {
   return 0.5f * (1.0f + erff(x * 0.70710678118654752f)) + x * expf(-0.5f * x * x) * 0.39894228040143268f;
 }
+TK_HD float tk_i2f(int v) { float f; memcpy(&f, &v, sizeof(f)); return f; }
+TK_HD int tk_f2i(float f) { int v; memcpy(&v, &f, sizeof(v)); return v; }
 TK_HD float tk_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
 // ---- re-posed points (core/catre/engine/batching.py:127-140 / batch_test.py:78-97): set 2b = pcl_b - t_b,
@@ -180,6 +183,20 @@ struct KScaleCopy {
   TK_HD void operator()(const Idx& i) const {
     const long long e = (long long)i.bx * i.nt + i.tx;
     if (e < n) dst[e] = scale * src[e];
+  }
+};
+
+// dst[t][e] = src[t][e] for up to kMax tensors in one launch (the optimiser's parameters -> the engine's fp32 copies); a null
+// src skips the tensor.  grid (chunks, tensors): block (bx, by) copies elements bx * per .. of tensor by.
+struct KMultiCopy {
+  static constexpr int kMax = 80;
+  const float* src[kMax]; float* dst[kMax]; int n[kMax]; int per;
+  TK_HD void operator()(const Idx& i) const {
+    const float* s = src[i.by];
+    if (!s) return;
+    float* d = dst[i.by];
+    const int lo = i.bx * per, hi = lo + per < n[i.by] ? lo + per : n[i.by];
+    for (int e = lo + i.tx; e < hi; e += i.nt) d[e] = s[e];
   }
 };
 
@@ -623,8 +640,40 @@ struct KPoseFwd {
 // chunk's share of the point-matching loss and of its gradients -> pm [B, chunks, 13] doubles (|diff| sum, dR 9, ds 3);
 // (3) KLoss, one thread per object: sums the chunks in order and adds the rotation / translation / scale terms.
 // grids: (ceil(B / nt)), (chunks, B) with nt = 1 .. any (thread tx > 0 idle) -- launched as (ceil(chunks / nt), B), (ceil(B / nt))
+// (1) runs in two launches so that the search over the symmetric copies (313 rotations with the shipped loader step) is not one
+// serial loop per object: KLossSelPart, one thread per (object, chunk of rotations): the chunk's first best clamped cosine and its
+// index -> part [B, chunks, 2]; KLossSel, one thread per object: merges the chunks in order (strict improvement only, starting
+// from the unrotated ground truth), i.e. the first maximum in rotation order -- the serial loop's choice -- and rebuilds that copy.
+TK_HD float tk_sym_cos(const float* R, const float* G, const float* S, float* C) {
+  for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C[r * 3 + c] = G[r * 3] * S[c] + G[r * 3 + 1] * S[3 + c] + G[r * 3 + 2] * S[6 + c];
+  float t2 = 0.0f;
+  for (int e = 0; e < 9; ++e) t2 += R[e] * C[e];
+  return fminf(1.0f, fmaxf(-1.0f, 0.5f * ((t2 <= 3.0f ? t2 : 3.0f) - 1.0f)));
+}
+// grid (ceil(chunks / nt), B)
+struct KLossSelPart {
+  const float *pose, *gt_pose, *sym_rots; const unsigned char* is_sym; float* part; int B, n_rots, chunks, per;
+  TK_HD void operator()(const Idx& i) const {
+    const int ch = i.bx * i.nt + i.tx, b = i.by;
+    if (ch >= chunks || is_sym[b] == 0) return;
+    const float* Pp = pose + (size_t)b * 12;
+    const float* Gp = gt_pose + (size_t)b * 12;
+    float R[9], G[9], C[9];
+    for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) { R[r * 3 + c] = Pp[r * 4 + c]; G[r * 3 + c] = Gp[r * 4 + c]; }
+    float best = -2.0f;  // below every clamped cosine
+    int bk = -1;
+    const int k0 = ch * per, k1 = k0 + per < n_rots ? k0 + per : n_rots;
+    for (int k = k0; k < k1; ++k) {
+      const float cs = tk_sym_cos(R, G, sym_rots + (size_t)k * 9, C);
+      if (cs > best) { best = cs; bk = k; }
+    }
+    part[((size_t)b * chunks + ch) * 2] = best;
+    part[((size_t)b * chunks + ch) * 2 + 1] = tk_i2f(bk);
+  }
+};
+// grid (ceil(B / nt))
 struct KLossSel {
-  const float *pose, *gt_pose, *sym_rots; const unsigned char* is_sym; float* gs; int B, n_rots;
+  const float *pose, *gt_pose, *sym_rots; const unsigned char* is_sym; const float* part; float* gs; int B, n_rots, chunks;
   TK_HD void operator()(const Idx& i) const {
     const int b = i.bx * i.nt + i.tx;
     if (b >= B) return;
@@ -636,15 +685,13 @@ struct KLossSel {
       float tr = 0.0f;
       for (int e = 0; e < 9; ++e) tr += R[e] * G[e];
       float best = fminf(1.0f, fmaxf(-1.0f, 0.5f * ((tr <= 3.0f ? tr : 3.0f) - 1.0f)));
-      for (int k = 0; k < n_rots; ++k) {
-        const float* S = sym_rots + (size_t)k * 9;
-        float C[9];
-        for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) C[r * 3 + c] = G[r * 3] * S[c] + G[r * 3 + 1] * S[3 + c] + G[r * 3 + 2] * S[6 + c];
-        float t2 = 0.0f;
-        for (int e = 0; e < 9; ++e) t2 += R[e] * C[e];
-        const float cs = fminf(1.0f, fmaxf(-1.0f, 0.5f * ((t2 <= 3.0f ? t2 : 3.0f) - 1.0f)));
-        if (cs > best) { best = cs; for (int e = 0; e < 9; ++e) Gs[e] = C[e]; }
+      int bk = -1;
+      for (int ch = 0; ch < chunks; ++ch) {
+        const float cs = part[((size_t)b * chunks + ch) * 2];
+        const int k = tk_f2i(part[((size_t)b * chunks + ch) * 2 + 1]);
+        if (k >= 0 && cs > best) { best = cs; bk = k; }
       }
+      if (bk >= 0) tk_sym_cos(R, G, sym_rots + (size_t)bk * 9, Gs);
     }
     for (int e = 0; e < 9; ++e) gs[(size_t)b * 9 + e] = Gs[e];
   }

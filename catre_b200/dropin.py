@@ -329,12 +329,15 @@ class CatreB200(nn.Module):
         if self._engine is None or self._engine.device != idx or self._train_versions is None:
             self.engine(device)  # create + full load (allocates the engine's device copies)
         eng = self._engine
+        changed = {}
         for n, p in self.named_parameters():
             cur = (p._version, p.data_ptr())
             if self._train_versions.get(n) != cur:
-                eng.train_set_weight(n, p.data.float())
+                changed[n] = p.data.float()
                 self._train_versions[n] = cur
-                self._packed_key = None  # the packed inference weights are stale until the next eval-mode forward
+        if changed:
+            eng.train_set_weights(changed)  # ONE launch for all of them (one copy per tensor before: 74 after an optimiser step)
+            self._packed_key = None  # the packed inference weights are stale until the next eval-mode forward
         return eng
 
     # ---- the reference's forward (one iteration) ---------------------------------------------------

@@ -53,6 +53,7 @@ SYMBOLS = {
     "catre_match_greedy": (ctypes.c_int, [ctypes.c_int32, _F, _F, _F, ctypes.c_int32, ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _F,
                                           _F, _F, _F, ctypes.c_int32, _F, ctypes.c_int32, _F, _F, _P]),
     "catre_train_set_weight": (ctypes.c_int, [_P, ctypes.c_char_p, _F, _P]),
+    "catre_train_set_weights": (ctypes.c_int, [_P, ctypes.POINTER(ctypes.c_void_p), _P]),
     "catre_train_set_loss_weights": (ctypes.c_int, [_P, ctypes.c_float, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
     "catre_train_step": (ctypes.c_int, [_P, _F, _F, _F, _F, _F, _F, _F, _F, _P, _P, ctypes.c_int32, ctypes.c_int32, _F, _F, _F, _P]),
     "catre_train_grad": (ctypes.c_int, [_P, ctypes.c_char_p, _F, _P]),
@@ -297,6 +298,28 @@ class Engine:
             raise CatreError(f"{name}: expected a float32 CUDA tensor on device {self.device}")
         t = t.detach().contiguous()
         self._check(self.lib.catre_train_set_weight(self._h, name.encode(), t.data_ptr(), self._stream()), f"train_set_weight({name})")
+
+    def train_set_weights(self, tensors):
+        """The same refresh for many tensors in ONE launch: {checkpoint name: contiguous float32 CUDA tensor}; names that are
+        absent keep their current values."""
+        if getattr(self, "_names", None) is None:
+            self._names = self.weight_names()
+        names = self._names
+        table = (ctypes.c_void_p * len(names))()
+        keep = []
+        for i, name in enumerate(names):
+            t = tensors.get(name)
+            if t is None:
+                continue
+            if not t.is_cuda or t.device.index != self.device or t.dtype != torch.float32:
+                raise CatreError(f"{name}: expected a float32 CUDA tensor on device {self.device}")
+            t = t.detach().contiguous()
+            keep.append(t)  # alive until the launch is enqueued (stream-ordered afterwards)
+            table[i] = t.data_ptr()
+        unknown = set(tensors) - set(names)
+        if unknown:
+            raise CatreError(f"unknown checkpoint tensors {sorted(unknown)[:3]}")
+        self._check(self.lib.catre_train_set_weights(self._h, table, self._stream()), "train_set_weights")
 
     def train_set_loss_weights(self, pm_lw: float = 1.0, rot_lw: float = 1.0, trans_lw: float = 1.0, scale_lw: float = 1.0):
         """LOSS_CFG.PM_LW / ROT_LW / TRANS_LW / SCALE_LW (all > 0)."""

@@ -255,17 +255,19 @@ class CrossImageRefiner:
         self.stats.compute_s += dt + sum(it.t_collate for it in l.items)
         t1 = time.perf_counter()
         poses_h, scales_h = l.poses_h.clone(), l.scales_h.clone()  # the pinned buffer is reused two launches later
-        o0 = 0
-        for it in l.items:
-            sl = slice(o0, o0 + it.n_obj)
-            o0 += it.n_obj
-            out_dict = {}
-            for i in range(self.n_iter + 1):
-                out_dict[f"pose_{i}"] = poses_h[i, sl]
-                out_dict[f"scale_{i}"] = scales_h[i, sl]
+        # one split per launch + one unbind per item instead of 2 (K+1) slicing calls per item (host time, not device time,
+        # bounds this loop at 256 objects per launch)
+        sizes = [it.n_obj for it in l.items]
+        pose_parts, scale_parts = poses_h.split(sizes, dim=1), scales_h.split(sizes, dim=1)
+        names_p = [f"pose_{i}" for i in range(self.n_iter + 1)]
+        names_s = [f"scale_{i}" for i in range(self.n_iter + 1)]
+        for it, pp, sp in zip(l.items, pose_parts, scale_parts):
+            pi, si = pp.unbind(0), sp.unbind(0)
+            out_dict = dict(zip(names_p, pi))
+            out_dict.update(zip(names_s, si))
             # the reference leaves the last iteration's estimate in the batch (batch_test.py:73-77)
-            it.batch["obj_pose_est"] = poses_h[self.n_iter, sl]
-            it.batch["obj_scale_est"] = scales_h[self.n_iter, sl]
+            it.batch["obj_pose_est"] = pi[self.n_iter]
+            it.batch["obj_scale_est"] = si[self.n_iter]
             share = it.t_collate + dt * (it.n_obj / float(l.n_obj))  # this item's share of the launch
             outputs = [{"time": share} for _ in range(len(it.inputs))]
             self.evaluator.process(it.inputs, it.batch, outputs, out_dict)

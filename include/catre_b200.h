@@ -218,7 +218,13 @@ int catre_match_greedy(int32_t mode, const int32_t* sub_pred_off, const int32_t*
  *   optimiser owns the parameters; call after every optimiser step for the tensors it changed).  Needs one earlier
  *   catre_pack (which allocates the copies).  Marks the packed inference weights stale: the inference entries return
  *   CATRE_ERR_NOT_PACKED until the next catre_pack, which first pulls the refreshed tensors back from the device.
- * catre_train_step: forward + losses + backward for B objects, stream-ordered, no host sync.
+ * catre_train_set_weights: the same refresh for every tensor in ONE launch: src_dev is a HOST array of
+ *   catre_num_weights() device pointers in catre_weight_name() order (contiguous fp32, the checkpoint's element counts);
+ *   a null entry leaves that tensor as it is.  What the drop-in calls after an optimiser step (74 copies -> 1 launch).
+ * catre_train_step: forward + losses + backward for B objects, stream-ordered, no host sync.  From the second step of a
+ *   (B, number of symmetric objects, n_sym_rots, loss weights) combination on, the ~240 launches of the chain are one
+ *   CUDA graph replayed on engine-owned static copies of the inputs (captured on an internal stream, launched on
+ *   `stream`; same kernels, same order, bit-identical results; CATRE_TRAIN_GRAPH=0 launches kernel by kernel).
  *   x_pm / tfd_pm [B, n, 3]  the re-posed points the reference's forward receives (as in catre_forward_once)
  *   obj_kps [B, n, 3]        normalised category prior (batch["obj_kps"], the point-matching loss's points)
  *   pose [B,3,4], scale [B,3], K [B,3,3]; gt_pose [B,3,4] (batch["obj_pose"]), gt_scale [B,3]   -- all device
@@ -236,6 +242,7 @@ int catre_match_greedy(int32_t mode, const int32_t* sub_pred_off, const int32_t*
  *   each scales its loss values and gradients (CATRE_disR_shared.py:217, 238, 250, 262-263, 286).  Default 1 (shipped
  *   config); must be > 0 (the reference drops a term whose weight is 0 from its dict -- not implemented). */
 int catre_train_set_weight(catre_engine* e, const char* name, const float* src_dev, void* stream);
+int catre_train_set_weights(catre_engine* e, const float* const* src_dev, void* stream);
 int catre_train_set_loss_weights(catre_engine* e, float pm_lw, float rot_lw, float trans_lw, float scale_lw);
 int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, const float* obj_kps, const float* pose,
                      const float* scale, const float* K, const float* gt_pose, const float* gt_scale,

@@ -183,3 +183,67 @@ def test_flat_gradient_handoff_equals_per_tensor_copies():
             g = eng.train_grad(name, torch.empty(t.shape, device="cuda"))
             assert torch.equal(flat[offsets[name]: offsets[name] + t.numel()].view(t.shape), scale * g), name
     eng.close()
+
+
+def test_train_step_cuda_graph_replay(monkeypatch):
+    """The chain as a CUDA graph (default): the first step of a (B, symmetric count) key runs kernel by kernel, the second is
+    captured, later ones replay it on engine-owned static inputs.  Replays on NEW caller tensors must equal, bit for bit, the
+    kernel-by-kernel launch (CATRE_TRAIN_GRAPH=0) of the same inputs -- poses, losses and the whole gradient arena."""
+    w = synth.load_weights()
+    rots = y_symmetry_rotations()
+
+    def make(seed, sym=None):
+        batch, tgt = synth.make_train_batch(6, 1024, seed, round_robin_cls=True)
+        d = batch.to("cuda")
+        x_pm = (d.pcl - d.init_pose[:, :, 3].unsqueeze(1)).contiguous()
+        tfd_pm = ((d.prior * d.init_scale.unsqueeze(1)) @ d.init_pose[:, :, :3].transpose(1, 2)).contiguous()
+        return (x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, tgt.gt_pose.cuda(), tgt.gt_scale.cuda(),
+                tgt.sym_y.numpy() if sym is None else np.asarray(sym), rots)
+
+    def run(eng, args):
+        pose, scale, losses = eng.train_step(*args)
+        flat = eng.train_grads_flat(1.0).clone()
+        torch.cuda.synchronize()
+        return pose.clone(), scale.clone(), losses.clone(), flat
+
+    a, b = make(11), make(12)
+    c = make(13, sym=[1, 0, 0, 0, 0, 0])  # another symmetric count: another graph
+    monkeypatch.setenv("CATRE_TRAIN_GRAPH", "0")
+    ref = engine.Engine(1024, 8, "fp32", 0)
+    ref.load_weights(w)
+    want = {k: run(ref, v) for k, v in (("a", a), ("b", b), ("c", c))}
+    monkeypatch.setenv("CATRE_TRAIN_GRAPH", "1")
+    eng = engine.Engine(1024, 8, "fp32", 0)
+    eng.load_weights(w)
+    for key, args in (("a", a), ("a", a), ("c", c), ("a", a), ("b", b), ("c", c), ("c", c), ("b", b)):
+        got = run(eng, args)
+        for x, y in zip(got, want[key]):
+            assert torch.equal(x, y), key
+    assert eng.last_launch_count() > 100  # the kernels inside the replayed graph are still counted
+    ref.close()
+    eng.close()
+
+
+def test_train_set_weights_one_launch():
+    """catre_train_set_weights (every changed tensor in one launch) leaves the engine in the state a fresh load of the same
+    tensors gives: identical training step; tensors that are not named keep their values."""
+    w = synth.load_weights()
+    d, tgt, x_pm, tfd_pm = inputs()
+    args = (x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, tgt.gt_pose.cuda(), tgt.gt_scale.cuda(), tgt.sym_y.numpy(),
+            y_symmetry_rotations())
+    g = torch.Generator().manual_seed(3)
+    changed = {n: (t + 0.01 * t.abs().mean() * torch.randn(t.shape, generator=g)).float() for i, (n, t) in enumerate(w.items()) if i % 3 != 1}
+    fresh = engine.Engine(1024, 8, "fp32", 0)
+    fresh.load_weights({**w, **changed})
+    want = [t.clone() for t in fresh.train_step(*args)] + [fresh.train_grads_flat(1.0)]
+    eng = engine.Engine(1024, 8, "fp32", 0)
+    eng.load_weights(w)
+    eng.train_set_weights({n: t.cuda() for n, t in changed.items()})
+    got = list(eng.train_step(*args)) + [eng.train_grads_flat(1.0)]
+    torch.cuda.synchronize()
+    for x, y in zip(got, want):
+        assert torch.equal(x, y)
+    with pytest.raises(engine.CatreError):
+        eng.train_set_weights({"no.such.tensor": torch.zeros(3, device="cuda")})
+    fresh.close()
+    eng.close()

@@ -65,6 +65,35 @@ def main():
             ms_a = ms if ms_a is None else min(ms_a, ms)
             print(json.dumps({"probe": "train_iteration", "impl": "catre_b200 drop-in + FusedRanger", "flat_grads": flat == "1", "B": B,
                               "N": 1024, "ms_per_iteration": ms, "objects_per_s": B / (ms / 1e3)}), flush=True)
+        os.environ["CATRE_TRAIN_FLAT_GRADS"] = "1"
+        # where the iteration goes: the same loop with a device synchronisation after every phase (the phases then cannot
+        # overlap, so their sum is an upper bound of the iteration above)
+        ph = {"forward(do_loss)": 0.0, "backward": 0.0, "nan_guard": 0.0, "optimizer.step": 0.0, "zero_grad": 0.0}
+        n_ph = 6
+        for it in range(n_ph):
+            marks = [time.perf_counter()]
+
+            def mark():
+                torch.cuda.synchronize()
+                marks.append(time.perf_counter())
+
+            _, loss_dict = model(x, tfd, init_pose=d.init_pose, init_scale=d.init_scale, K_zoom=d.K, gt_ego_rot=gt_pose[:, :, :3],
+                                 gt_trans=gt_pose[:, :, 3], gt_scale=gt_scale, obj_kps=d.prior, sym_info=sym_info, do_loss=True, cur_iter=1)
+            mark()
+            sum(loss_dict.values()).backward()
+            mark()
+            for p in model.parameters():
+                if p.grad is not None:
+                    torch.nan_to_num(p.grad, nan=0, posinf=1e5, neginf=-1e5, out=p.grad)
+            mark()
+            opt.step()
+            mark()
+            opt.zero_grad(set_to_none=True)
+            mark()
+            for k, a_, b_ in zip(ph, marks[:-1], marks[1:]):
+                ph[k] += (b_ - a_) * 1e3 / n_ph
+        print(json.dumps({"probe": "train_iteration_phases", "B": B, "ms": {k: round(v, 3) for k, v in ph.items()},
+                          "sum_ms": round(sum(ph.values()), 3)}), flush=True)
         os.environ["CATRE_TRAIN_FLAT_GRADS"] = "0"
 
         # (b) torch modules (restatement) + per-tensor Ranger ops, TF32 as PyTorch defaults it and off

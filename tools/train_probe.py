@@ -22,25 +22,28 @@ def main():
         x_pm = (d.pcl - d.init_pose[:, :, 3].unsqueeze(1)).contiguous()
         tfd_pm = ((d.prior * d.init_scale.unsqueeze(1)) @ d.init_pose[:, :, :3].transpose(1, 2)).contiguous()
         gp, gs = tgt.gt_pose.cuda(), tgt.gt_scale.cuda()
-        modes = os.environ.get("TRAIN_PROBE_MODES", "tc,simt").split(",")
-        for ver in modes:  # tc (default: tcgen05 GEMM for the large shapes), simt (64 x 64 CUDA-core tiles), v2, naive
+        modes = os.environ.get("TRAIN_PROBE_MODES", "tc,tc-nograph,simt").split(",")
+        for mode in modes:  # tc (default: tcgen05 GEMM for the large shapes), simt (64 x 64 CUDA-core tiles), v2, naive;
+            # a "-nograph" suffix launches the chain kernel by kernel (CATRE_TRAIN_GRAPH=0) instead of replaying its CUDA graph
+            ver = mode.replace("-nograph", "")
             naive = "1" if ver == "naive" else "0"
             os.environ["CATRE_TRAIN_NAIVE_GEMM"] = naive
             os.environ["CATRE_TRAIN_GEMM"] = ver
+            os.environ["CATRE_TRAIN_GRAPH"] = "0" if mode.endswith("-nograph") else "1"
             eng = engine.Engine(1024, 8, "fp32", 0)
             eng.load_weights(w)
             step = lambda: eng.train_step(x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, gp, gs, tgt.sym_y.numpy(), rots)
-            for _ in range(2):
+            for _ in range(3):
                 step()
             torch.cuda.synchronize()
             a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            n = 5 if naive == "0" else 2
+            n = 10 if naive == "0" else 2
             a.record()
             for _ in range(n):
                 step()
             b.record()
             torch.cuda.synchronize()
-            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": ver,
+            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": ver, "cuda_graph": not mode.endswith("-nograph"),
                               "ms_per_step": a.elapsed_time(b) / n, "launches": eng.last_launch_count(),
                               "objects_per_s": B / (a.elapsed_time(b) / n / 1e3)}), flush=True)
             eng.close()
