@@ -715,9 +715,23 @@ struct CudaTrainOps {
   int64_t launches = 0;
   cudaError_t err = cudaSuccess;
   void note(cudaError_t st) { if (err == cudaSuccess && st != cudaSuccess) err = st; }
+  // carve: ask for the maximum shared-memory carve-out for the small kernels too, so that the SMs do not switch their L1 /
+  // shared-memory split before and after every tensor-core GEMM (193 KB of shared memory) of the chain; set once per kernel
+  // instantiation and value (the attribute belongs to the function, not to the launch).  CATRE_TRAIN_CARVEOUT=0 turns it off.
+  bool carve = false;
+  template <class Fn>
+  void set_carve(Fn* fn, int& state) {
+    const int want = carve ? 100 : -1;
+    if (state != want) {
+      note(cudaFuncSetAttribute(fn, cudaFuncAttributePreferredSharedMemoryCarveout, want));
+      state = want;
+    }
+  }
   template <class KF>
   void run(const KF& k, unsigned gx, unsigned gy, unsigned gz, unsigned nt) {
     if (gx == 0 || gy == 0 || gz == 0) return;
+    static int carve_state = -1;  // one per instantiation
+    set_carve(catre_train::tk_run<KF>, carve_state);
     catre_train::tk_run<KF><<<dim3(gx, gy, gz), nt, 0, s>>>(k);
     ++launches;
     note(cudaPeekAtLastError());
@@ -774,6 +788,8 @@ struct CudaTrainOps {
       ++launches;
       note(cudaPeekAtLastError());
     } else {
+      static int carve_state = -1;
+      set_carve(catre_train::tk_gemm_tiled, carve_state);
       catre_train::tk_gemm_tiled<<<dim3((unsigned)((p.M + 63) / 64), (unsigned)((p.N + 63) / 64), (unsigned)bz), 256, 0, s>>>(p);
       ++launches;
       note(cudaPeekAtLastError());
@@ -1504,6 +1520,8 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   const char* env3 = getenv("CATRE_TRAIN_GRAPH");
   const bool naive_gemm = e->train_naive_gemm || (env && env[0] == '1'), gemm_v2 = env2 && strcmp(env2, "v2") == 0;
   const bool gemm_tc = !naive_gemm && !gemm_v2 && !(env2 && strcmp(env2, "simt") == 0);
+  const char* env4 = getenv("CATRE_TRAIN_CARVEOUT");
+  const bool carve = gemm_tc && env4 && env4[0] == '1';  // experiment (see CudaTrainOps::carve)
   auto make_in = [&](const float* x, const float* tfd, const float* kps, const float* po, const float* sc, const float* Kz,
                      const float* gp, const float* gs, float* op, float* os) {
     catre_train::TrainIn in{nullptr, kps, po, sc, Kz, gp, gs, B, n_sym_rots, n_sym, B - n_sym, op, os};
@@ -1513,6 +1531,7 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   };
   auto run_chain = [&](cudaStream_t st, const catre_train::TrainIn& in, int64_t& n_launch) -> cudaError_t {
     CudaTrainOps ops{st, naive_gemm, gemm_v2, gemm_tc, e->num_sms};
+    ops.carve = carve;
     catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
     chain.forward(in);
     chain.loss(in);
@@ -1524,7 +1543,7 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   bool done = false;
   if (!(env3 && env3[0] == '0')) {
     catre_engine::TrainGraphKey key{};
-    key.B = B; key.n_sym = n_sym; key.n_rots = n_sym_rots; key.mode = naive_gemm ? 1 : (gemm_v2 ? 2 : (gemm_tc ? 0 : 3));
+    key.B = B; key.n_sym = n_sym; key.n_rots = n_sym_rots; key.mode = (naive_gemm ? 1 : (gemm_v2 ? 2 : (gemm_tc ? 0 : 3))) + (carve ? 8 : 0);
     for (int i = 0; i < 4; ++i) key.lw[i] = e->loss_w[i];
     if (e->train_graphs.size() > 64 && !e->train_graphs.count(key)) {  // bound the cache (each graph holds ~240 nodes)
       CU_TRY(e, cudaStreamSynchronize(s));

@@ -43,12 +43,12 @@ struct TrainWs {
       *pfmax;
   int *sarg, *farg, *garg, *pfarg;
   float *ts_in, *ts_y0, *ts_u0, *ts_y1, *ts_u1, *ts_st0, *ts_st1, *dts;
-  float *cset[2], *ry0[2], *ru0[2], *ry1[2], *rst0[2], *rst1[2], *wsum[2], *ru1, *r6;
+  float *cset[2], *ry0[2], *ru0[2], *ry1[2], *rst0[2], *rst1[2], *wsum[2], *ru1, *r6, *swp;
   // loss / backward
   float *lossp, *losses, *dpose, *d_r6, *d_dts, *tsd_u, *tsd_u0, *ts_din, *gn_m, *gnp_g, *gnp_b;
   float *dg, *dpfmax, *dpf, *e, *du, *du0, *dcset, *d512, *d128, *d64, *dh1, *dt64, *dfc2, *dfc1, *dmax, *dqp, *dt3;
   float *partial, *cs_partial, *loss_gs;
-  int *mb_start, *mb_cnt, *mb_list;  // inverse arg-max map of the sparse max-pool backward: [S, N], [S, N], [S, 1024]
+  int *mb_start, *mb_cnt, *mb_list, *mb_key;  // inverse arg-max map of the sparse max-pool backward: [S, N], [S, N], [S, 1024] x 2
   double* gn_part;  // [maxB, kGnChunks, 32, 18]; also the point-matching partials of the loss [maxB, kLossChunks, 13]
   unsigned char* is_sym;
   float* sym_rots;
@@ -86,14 +86,14 @@ inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base, size_t gap = 0)
     F(w.cset[h], S * 256); F(w.ry0[h], R * 256); F(w.ru0[h], R * 256); F(w.ry1[h], R * 256); F(w.rst0[h], B * 64);
     F(w.rst1[h], B * 64); F(w.wsum[h], B * 256);
   }
-  F(w.ru1, R * 256); F(w.r6, B * 6);
+  F(w.ru1, R * 256); F(w.r6, B * 6); F(w.swp, 2);
   F(w.lossp, B * 6); F(w.losses, 8); F(w.dpose, B * 15); F(w.d_r6, B * 6); F(w.d_dts, B * 6); F(w.tsd_u, B * 256);
   F(w.tsd_u0, B * 256); F(w.ts_din, B * 1091); F(w.gn_m, B * 64); F(w.gnp_g, B * 256); F(w.gnp_b, B * 256);
   F(w.dg, S * 1024); F(w.dpfmax, S * 64); F(w.dpf, R * 64); F(w.e, B * 256); F(w.du, R * 256); F(w.du0, R * 256);
   F(w.dcset, S * 256); F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
   F(w.dfc2, S * 256); F(w.dfc1, S * 512); F(w.dmax, S * 1024); F(w.dqp, R * 3); F(w.dt3, S * 9);
   F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, TrainWs::kCsFloats); F(w.loss_gs, B * 9);
-  I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024);
+  I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024); I(w.mb_key, S * 1024);
   w.gn_part = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
   w.is_sym = reinterpret_cast<unsigned char*>(take(B));
   F(w.sym_rots, (size_t)TrainWs::kMaxSymRots * 9);
@@ -199,9 +199,15 @@ struct Chain {
     o.run(KColMaxArgMerge{pv, pi, vmax, arg, chunks, C}, cdiv(C, nt), S, 1, nt);
   }
   // sparse backward of a max-pooled layer: dx[(s, n), :] from d(max) [S, C] (KMaxBwdIndex + KMaxBwdGather)
-  void max_bwd_dx(const float* dmax, const float* relu_max, const float* Wt, const int* arg, float* dx, int S, int C, int K) {
-    o.run(KMaxBwdIndex{arg, w.mb_start, w.mb_cnt, w.mb_list, N, C}, cdiv(N, 128), S, 1, 128);
-    o.run(KMaxBwdGather{dmax, relu_max, Wt, w.mb_start, w.mb_cnt, w.mb_list, dx, N, C, K}, cdiv(K, 128), N, S, 128);
+  // `act`: the layer's input activation [S N, K]; dx is zeroed where it is not positive (the ReLU below the layer, folded in)
+  void max_bwd_dx(const float* dmax, const float* relu_max, const float* Wt, const int* arg, float* dx, int S, int C, int K,
+                  const float* act) {
+    o.run(KMaxBwdRank{arg, w.mb_list, w.mb_key, C}, cdiv(C, 128), S, 1, 128);
+    o.run(KMaxBwdRange{w.mb_key, w.mb_start, w.mb_cnt, N, C}, cdiv(N, 128), S, 1, 128);
+    const int kq = K / 4, nt = 128;
+    const int ppb = (kq < nt && nt % kq == 0) ? nt / kq : 1;  // points per block
+    o.run(KMaxBwdGather{dmax, relu_max, Wt, w.mb_start, w.mb_cnt, w.mb_list, dx, act, N, C, K, ppb}, ppb > 1 ? 1 : cdiv(kq, nt),
+          cdiv(N, ppb), S, nt);
   }
   // backward of y = x W^T + b for checkpoint tensor wi viewed as [C, ldw] with the K input columns at woff:
   // dW += dy^T x, db += colsum(dy) (when with_bias), dx (=|+=) dy W.
@@ -231,7 +237,7 @@ struct Chain {
     o.run(KGnStatsPart{y, w.gn_part, P, chunks, per}, B, chunks, 1, 32);
     o.run(KGnStats{w.gn_part, st, P, chunks}, B, 1, 1, 32);
     const long long n = (long long)B * P * 256;
-    o.run(KGnGeluFwd{y, st, ga, be, u, P, n}, cdiv(n, 256), 1, 1, 256);
+    o.run(KGnGeluFwd{y, st, ga, be, u, P, n}, cdiv(n / 4, 256), 1, 1, 256);
   }
   // du -> dy in place; gamma / beta gradients accumulated into G[gi], G[gi + 1]
   void gn_bwd(float* du, const float* y, const float* st, int gi, int B, int P) {
@@ -241,7 +247,7 @@ struct Chain {
     colsum(w.gnp_g, B, 256, 256, w.G[gi], 1);
     colsum(w.gnp_b, B, 256, 256, w.G[gi + 1], 1);
     const long long n = (long long)B * P * 256;
-    o.run(KGnBwdApply{du, y, st, W[gi], W[gi + 1], w.gn_m, P, n}, cdiv(n, 256), 1, 1, 256);
+    o.run(KGnBwdApply{du, y, st, W[gi], W[gi + 1], w.gn_m, P, n}, cdiv(n / 4, 256), 1, 1, 256);
   }
 
   // T-Net forward (pointnets/pointnet.py:24-41, 57-78)
@@ -265,9 +271,8 @@ struct Chain {
     lin_bwd(wb + T_FC2, fc1, 512, w.dfc2, 256, 256, S, w.dfc1, 0);
     relu_mask(w.dfc1, fc1, (long long)S * 512);
     lin_bwd(wb + T_FC1, vmax, 1024, w.dfc1, 512, 512, S, w.dmax, 0);
-    max_bwd_dx(w.dmax, vmax, W[wb + T_CONV3], arg, w.d128, S, 1024, 128);
+    max_bwd_dx(w.dmax, vmax, W[wb + T_CONV3], arg, w.d128, S, 1024, 128, c128);  // incl. the ReLU mask of conv2's output
     o.run(KMaxBwdDw{w.dmax, vmax, c128, arg, w.G[wb + T_CONV3], w.G[wb + T_CONV3 + 1], S, N, 1024, 128}, cdiv(128, 128), 1024, 1, 128);
-    relu_mask(w.d128, c128, R * 128);
     lin_bwd(wb + T_CONV2, c64, 64, w.d128, 128, 128, R, w.d64, 0);
     relu_mask(w.d64, c64, R * 64);
     lin_bwd(wb + T_CONV1, x, Kin, w.d64, 64, 64, R, dx_out, 1);
@@ -307,7 +312,8 @@ struct Chain {
       layer(w.ru0[h], 256, rb + R_L3, 256, w.ry1[h], R, 0);
       gn_fwd(w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1, B, P);
       rot_wsum(w.ru1, W[rb + R_CONVP], w.wsum[h], B, P);
-      o.run(KRotOut{w.wsum[h], W[rb + R_NECK], W[rb + R_NECK + 1], W[rb + R_CONVP], W[rb + R_CONVP + 1], w.r6, P, h}, B, 1, 1, 32);
+      colsum(W[rb + R_CONVP], P, 1, 1, w.swp + h, 0);  // sum_p wp[p], also read by the backward of this step
+      o.run(KRotOut{w.wsum[h], W[rb + R_NECK], W[rb + R_NECK + 1], w.swp, W[rb + R_CONVP + 1], w.r6, P, h}, B, 1, 1, 32);
     }
     o.run(KPoseFwd{w.r6, w.dts, in.pose, in.scale, in.K, in.pose_out, in.scale_out, B}, cdiv(B, 64), 1, 1, 64);
   }
@@ -352,10 +358,10 @@ struct Chain {
     for (int h = 0; h < 2; ++h) {
       const int rb = h ? W_ROT_Y : W_ROT_X;
       const float* wp = W[rb + R_CONVP];
-      o.run(KRotTailBwd{w.d_r6, w.wsum[h], W[rb + R_NECK], wp, w.e, w.G[rb + R_NECK], w.G[rb + R_NECK + 1], w.G[rb + R_CONVP + 1], B, P, h},
+      o.run(KRotTailBwd{w.d_r6, w.wsum[h], W[rb + R_NECK], w.swp, w.e, w.G[rb + R_NECK], w.G[rb + R_NECK + 1], w.G[rb + R_CONVP + 1], B, P, h},
             1, 1, 1, 256);
       const long long n = (long long)B * P * 256;
-      o.run(KGnGeluFwd{w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1, P, n}, cdiv(n, 256), 1, 1, 256);  // recompute u1
+      o.run(KGnGeluFwd{w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1, P, n}, cdiv(n / 4, 256), 1, 1, 256);  // recompute u1
       if ((size_t)B * P * 8 <= TrainWs::kPartialFloats) {
         o.run(KRotDwpPart{w.ru1, w.e, w.partial, P}, cdiv(8 * P, 256), B, 1, 256);
         o.run(KRotDwpSum{w.partial, w.d_r6, W[rb + R_NECK + 1], w.G[rb + R_CONVP], B, P, h}, cdiv(P, 128), 1, 1, 128);
@@ -376,9 +382,8 @@ struct Chain {
     }
     // ---- encoder
     o.run(KScatterMax{w.dpfmax, w.pfarg, w.dpf, N, 64}, 1, S, 1, 64);
-    max_bwd_dx(w.dg, nullptr, W[W_CONV4], w.garg, w.d512, S, 1024, 512);
+    max_bwd_dx(w.dg, nullptr, W[W_CONV4], w.garg, w.d512, S, 1024, 512, w.a512);  // incl. the ReLU mask of conv3's output
     o.run(KMaxBwdDw{w.dg, nullptr, w.a512, w.garg, w.G[W_CONV4], w.G[W_CONV4 + 1], S, N, 1024, 512}, cdiv(512, 128), 1024, 1, 128);
-    relu_mask(w.d512, w.a512, R * 512);
     lin_bwd(W_CONV3, w.a128, 128, w.d512, 512, 512, R, w.d128, 0);
     relu_mask(w.d128, w.a128, R * 128);
     lin_bwd(W_CONV2, w.pf, 64, w.d128, 128, 128, R, w.dpf, 1);

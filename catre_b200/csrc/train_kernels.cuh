@@ -33,6 +33,43 @@ TK_HD float tk_gelu_grad(float x) {
 }
 TK_HD float tk_i2f(int v) { float f; memcpy(&f, &v, sizeof(f)); return f; }
 TK_HD int tk_f2i(float f) { int v; memcpy(&v, &f, sizeof(v)); return v; }
+// In-order sum of n values v[0], v[stride], ...: the loads of 32 terms are issued before their additions, so a thread waits
+// for one memory round trip per 32 terms instead of one per term; the additions stay in index order (same bits as a plain loop).
+template <class T>
+TK_HD T tk_sum_inorder(const T* v, long long n, long long stride) {
+  T acc = (T)0;
+  long long k = 0;
+  for (; k + 32 <= n; k += 32) {
+    T t[32];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) t[u] = v[(k + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 32; ++u) acc += t[u];
+  }
+  for (; k < n; ++k) acc += v[k * stride];
+  return acc;
+}
+// Sum of n doubles v[0], v[stride], ... in four interleaved partial sums (term k goes to sum k mod 4), combined as
+// (s0 + s1) + (s2 + s3): a fixed order, so still deterministic, with four independent addition chains instead of one --
+// the merges of 256 chunk partials were bound by the latency of their dependent fp64 additions.
+TK_HD double tk_sum4(const double* v, long long n, long long stride) {
+  double a0 = 0.0, a1 = 0.0, a2 = 0.0, a3 = 0.0;
+  long long k = 0;
+  for (; k + 16 <= n; k += 16) {
+    double t[16];
+#pragma unroll
+    for (int u = 0; u < 16; ++u) t[u] = v[(k + u) * stride];
+#pragma unroll
+    for (int u = 0; u < 16; u += 4) { a0 += t[u]; a1 += t[u + 1]; a2 += t[u + 2]; a3 += t[u + 3]; }
+  }
+  for (; k < n; ++k) {  // the tail keeps the k mod 4 assignment (k is a multiple of 16 here)
+    const double x = v[k * stride];
+    switch ((int)(k & 3)) { case 0: a0 += x; break; case 1: a1 += x; break; case 2: a2 += x; break; default: a3 += x; }
+  }
+  return (a0 + a1) + (a2 + a3);
+}
+struct alignas(16) TkI4 { int x, y, z, w; };
+struct alignas(16) TkF4 { float x, y, z, w; };
 TK_HD float tk_sign(float x) { return x > 0.0f ? 1.0f : (x < 0.0f ? -1.0f : 0.0f); }
 
 // ---- re-posed points (core/catre/engine/batching.py:127-140 / batch_test.py:78-97): set 2b = pcl_b - t_b,
@@ -218,8 +255,7 @@ struct KColSum {
     if (c >= C) return;
     const long long r0 = (long long)i.by * rows_per;
     const long long r1 = r0 + rows_per < rows ? r0 + rows_per : rows;
-    float acc = 0.0f;
-    for (long long r = r0; r < r1; ++r) acc += d[r * ld + c];
+    const float acc = r1 > r0 ? tk_sum_inorder(d + r0 * ld + c, r1 - r0, ld) : 0.0f;
     float* o = out + (size_t)i.by * C + c;
     *o = accumulate ? *o + acc : acc;
   }
@@ -253,41 +289,119 @@ struct KMaxBwdDx {
 };
 // The same result (same summation order: channels ascending) without the C-long scan per output element: first the
 // inverse of the arg-max map, then a gather.
-// Index: for point n of set s, start[s, n] = number of channels whose arg-max point is < n, cnt[s, n] = number whose arg-max
-// is n, and list[s, start .. start + cnt) = those channels, ascending (a counting sort, every thread scanning the set's C
-// entries twice).  grid (ceil(N / nt), S)
-struct KMaxBwdIndex {
-  const int* arg; int *start, *cnt, *list; int N, C;
+// Inverse map = the set's channels sorted by (arg-max point, channel): list[s, :] with key[s, :] = the arg-max point of each
+// entry, and per point n the range start[s, n] .. + cnt[s, n] of its channels.  Two kernels without data-dependent stores:
+// KMaxBwdRank, one thread per (set, channel): position of channel c = number of channels c' with (arg[c'], c') < (arg[c], c),
+//   one scan of the set's C entries as 128-bit words (C a multiple of 4, rows 16-byte aligned; scalar otherwise).
+//   grid (ceil(C / nt), S)
+// KMaxBwdRange, one thread per (set, point): lower / upper bound of n in the sorted keys.  grid (ceil(N / nt), S)
+struct KMaxBwdRank {
+  const int* arg; int *list, *key; int C;
+  TK_HD void operator()(const Idx& i) const {
+    const int c = i.bx * i.nt + i.tx, s = i.by;
+    if (c >= C) return;
+    const int* a = arg + (size_t)s * C;
+    const int n = a[c];
+    int pos = 0;
+    if ((C & 3) == 0 && (reinterpret_cast<uintptr_t>(a) & 15) == 0) {
+      const TkI4* a4 = reinterpret_cast<const TkI4*>(a);
+      const int q = c >> 2;
+      for (int j = 0; j < q; ++j) {  // words entirely below c: ties count
+        const TkI4 v = a4[j];
+        pos += (v.x <= n) + (v.y <= n) + (v.z <= n) + (v.w <= n);
+      }
+      {
+        const TkI4 v = a4[q];
+        const int r = c & 3;
+        pos += (r > 0 ? v.x <= n : false) + (r > 1 ? v.y <= n : (r < 1 ? v.y < n : false)) +
+               (r > 2 ? v.z <= n : (r < 2 ? v.z < n : false)) + (r < 3 ? v.w < n : false);
+      }
+      for (int j = q + 1; j < C / 4; ++j) {  // words entirely above c: strict
+        const TkI4 v = a4[j];
+        pos += (v.x < n) + (v.y < n) + (v.z < n) + (v.w < n);
+      }
+    } else {
+      for (int j = 0; j < c; ++j) pos += a[j] <= n;
+      for (int j = c + 1; j < C; ++j) pos += a[j] < n;
+    }
+    list[(size_t)s * C + pos] = c;
+    key[(size_t)s * C + pos] = n;
+  }
+};
+struct KMaxBwdRange {
+  const int* key; int *start, *cnt; int N, C;
   TK_HD void operator()(const Idx& i) const {
     const int n = i.bx * i.nt + i.tx, s = i.by;
     if (n >= N) return;
-    const int* a = arg + (size_t)s * C;
-    int lt = 0, eq = 0;
-    for (int c = 0; c < C; ++c) { const int v = a[c]; lt += v < n; eq += v == n; }
-    start[(size_t)s * N + n] = lt; cnt[(size_t)s * N + n] = eq;
-    if (eq == 0) return;
-    int* l = list + (size_t)s * C + lt;
-    for (int c = 0; c < C; ++c)
-      if (a[c] == n) *l++ = c;
+    const int* k = key + (size_t)s * C;
+    int lo = 0, hi = C;  // first position with key >= n
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (k[m] < n) lo = m + 1; else hi = m; }
+    const int first = lo;
+    hi = C;              // first position with key > n
+    while (lo < hi) { const int m = (lo + hi) >> 1; if (k[m] <= n) lo = m + 1; else hi = m; }
+    start[(size_t)s * N + n] = first; cnt[(size_t)s * N + n] = lo - first;
   }
 };
-// dx[(s, n), k] = sum over the point's channels (ascending) of d[s,c] W[c,k]; every element written once.
-// grid (ceil(K / nt), N, S)
+// dx[(s, n), k .. k+3] = sum over the point's channels (ascending) of d[s,c] W[c, k .. k+3], zeroed where the layer's input
+// activation is not positive when `act` is given (the ReLU backward of the layer below, folded in: only the few rows that
+// carry a gradient read `act`); every element written once, 16 bytes per thread.  K a multiple of 4, W / dx / act 16-byte
+// aligned.  A block covers nt / (K / 4) consecutive points (ppb >= 1) so that it has nt threads for any K; the channels of a
+// point are fetched eight at a time (index, gradient and weight row of all eight in flight, then added in order): a point
+// that holds hundreds of a set's maxima is one long serial chain per thread, and its length in round trips is what the
+// kernel takes.  grid (ceil(K / 4 / nt), ceil(N / ppb), S)
 struct KMaxBwdGather {
-  const float *dmax, *relu_max, *W; const int *start, *cnt, *list; float* dx; int N, C, K;
+  const float *dmax, *relu_max, *W; const int *start, *cnt, *list; float* dx; const float* act; int N, C, K, ppb;
   TK_HD void operator()(const Idx& i) const {
-    const int k = i.bx * i.nt + i.tx, n = i.by, s = i.bz;
-    if (k >= K) return;
+    const int kq = K >> 2;
+    int k, n;
+    if (ppb > 1) { k = 4 * (i.tx % kq); n = i.by * ppb + i.tx / kq; if (i.tx >= ppb * kq) return; }
+    else { k = 4 * (i.bx * i.nt + i.tx); n = i.by; }
+    const int s = i.bz;
+    if (k >= K || n >= N) return;
     const int m = cnt[(size_t)s * N + n];
     const int* l = list + (size_t)s * C + start[(size_t)s * N + n];
-    float acc = 0.0f;
-    for (int j = 0; j < m; ++j) {
-      const int c = l[j];
-      float d = dmax[(size_t)s * C + c];
-      if (relu_max && !(relu_max[(size_t)s * C + c] > 0.0f)) d = 0.0f;
-      acc += d * W[(size_t)c * K + k];
+    const float* dm = dmax + (size_t)s * C;
+    const float* rm = relu_max ? relu_max + (size_t)s * C : nullptr;
+    TkF4 acc = {0.0f, 0.0f, 0.0f, 0.0f};
+    int j = 0;
+    int cn[8];  // the next batch's channel indices are fetched while the current batch's gradients and weight rows are in flight
+    if (m >= 8) {
+#pragma unroll
+      for (int u = 0; u < 8; ++u) cn[u] = l[u];
     }
-    dx[((size_t)s * N + n) * K + k] = acc;
+    for (; j + 8 <= m; j += 8) {
+      int c[8]; float d[8]; TkF4 w[8];
+#pragma unroll
+      for (int u = 0; u < 8; ++u) c[u] = cn[u];
+      if (j + 16 <= m) {
+#pragma unroll
+        for (int u = 0; u < 8; ++u) cn[u] = l[j + 8 + u];
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) {
+        d[u] = dm[c[u]];
+        if (rm && !(rm[c[u]] > 0.0f)) d[u] = 0.0f;
+        w[u] = *reinterpret_cast<const TkF4*>(W + (size_t)c[u] * K + k);
+      }
+#pragma unroll
+      for (int u = 0; u < 8; ++u) { acc.x += d[u] * w[u].x; acc.y += d[u] * w[u].y; acc.z += d[u] * w[u].z; acc.w += d[u] * w[u].w; }
+    }
+    for (; j < m; ++j) {
+      const int c = l[j];
+      float d = dm[c];
+      if (rm && !(rm[c] > 0.0f)) d = 0.0f;
+      const TkF4 w = *reinterpret_cast<const TkF4*>(W + (size_t)c * K + k);
+      acc.x += d * w.x; acc.y += d * w.y; acc.z += d * w.z; acc.w += d * w.w;
+    }
+    const size_t o = ((size_t)s * N + n) * K + k;
+    if (act && m > 0) {
+      const TkF4 a = *reinterpret_cast<const TkF4*>(act + o);
+      if (!(a.x > 0.0f)) acc.x = 0.0f;
+      if (!(a.y > 0.0f)) acc.y = 0.0f;
+      if (!(a.z > 0.0f)) acc.z = 0.0f;
+      if (!(a.w > 0.0f)) acc.w = 0.0f;
+    }
+    *reinterpret_cast<TkF4*>(dx + o) = acc;
   }
 };
 // dW[c, k] += sum_s d[s,c] x[(s, arg[s,c]), k];  db[c] += sum_s d[s,c].  grid (ceil(K / nt), C)
@@ -340,15 +454,8 @@ struct KGnStats {
   TK_HD void operator()(const Idx& i) const {
     const int b = i.bx, g = i.tx;
     if (g >= 32) return;
-    double s = 0.0, ss = 0.0;
     const double* o = part + ((size_t)b * chunks * 32 + g) * 2;
-    int ch = 0;
-    for (; ch + 4 <= chunks; ch += 4) {  // the loads of four chunks in flight; the additions stay in chunk order
-      const double a0 = o[(size_t)ch * 64], b0 = o[(size_t)ch * 64 + 1], a1 = o[(size_t)(ch + 1) * 64], b1 = o[(size_t)(ch + 1) * 64 + 1];
-      const double a2 = o[(size_t)(ch + 2) * 64], b2 = o[(size_t)(ch + 2) * 64 + 1], a3 = o[(size_t)(ch + 3) * 64], b3 = o[(size_t)(ch + 3) * 64 + 1];
-      s += a0; ss += b0; s += a1; ss += b1; s += a2; ss += b2; s += a3; ss += b3;
-    }
-    for (; ch < chunks; ++ch) { s += o[(size_t)ch * 64]; ss += o[(size_t)ch * 64 + 1]; }
+    const double s = tk_sum4(o, chunks, 64), ss = tk_sum4(o + 1, chunks, 64);
     const double cnt = 8.0 * P, mu = s / cnt;
     double var = ss / cnt - mu * mu;
     if (var < 0.0) var = 0.0;
@@ -357,15 +464,24 @@ struct KGnStats {
   }
 };
 // u = gelu(gamma (y - mu) rstd + beta).  grid (ceil(B * P * 256 / nt))
+// Four consecutive channels per thread (one 16-byte load and store; they share the object and the group): n a multiple of 4,
+// y / u 16-byte aligned.  grid (ceil(n / 4 / nt))
 struct KGnGeluFwd {
   const float *y, *st, *gamma, *beta; float* u; int P; long long n;
   TK_HD void operator()(const Idx& i) const {
-    const long long e = (long long)i.bx * i.nt + i.tx;
+    const long long e = 4 * ((long long)i.bx * i.nt + i.tx);
     if (e >= n) return;
     const int c = (int)(e & 255);
     const long long b = e / ((long long)P * 256);
     const float* s = st + ((size_t)b * 32 + (c >> 3)) * 2;
-    u[e] = tk_gelu(gamma[c] * ((y[e] - s[0]) * s[1]) + beta[c]);
+    const float mu = s[0], rstd = s[1];
+    const TkF4 v = *reinterpret_cast<const TkF4*>(y + e);
+    TkF4 r;
+    r.x = tk_gelu(gamma[c] * ((v.x - mu) * rstd) + beta[c]);
+    r.y = tk_gelu(gamma[c + 1] * ((v.y - mu) * rstd) + beta[c + 1]);
+    r.z = tk_gelu(gamma[c + 2] * ((v.z - mu) * rstd) + beta[c + 2]);
+    r.w = tk_gelu(gamma[c + 3] * ((v.w - mu) * rstd) + beta[c + 3]);
+    *reinterpret_cast<TkF4*>(u + e) = r;
   }
 };
 // backward, pass 1 (oracle: _gn_gelu_backward): with xhat = (y - mu) rstd, dn = du gelu'(gamma xhat + beta),
@@ -401,14 +517,7 @@ struct KGnBwdSums {
   TK_HD void operator()(const Idx& i) const {
     const int b = i.bx, g = i.tx / 18, j = i.tx % 18;
     if (g >= 32) return;
-    double a = 0.0;
-    const double* o = part + (size_t)b * chunks * 576 + g * 18 + j;
-    int ch = 0;
-    for (; ch + 4 <= chunks; ch += 4) {
-      const double a0 = o[(size_t)ch * 576], a1 = o[(size_t)(ch + 1) * 576], a2 = o[(size_t)(ch + 2) * 576], a3 = o[(size_t)(ch + 3) * 576];
-      a += a0; a += a1; a += a2; a += a3;
-    }
-    for (; ch < chunks; ++ch) a += o[(size_t)ch * 576];
+    const double a = tk_sum4(part + (size_t)b * chunks * 576 + g * 18 + j, chunks, 576);
     if (j < 2) m[((size_t)b * 32 + g) * 2 + j] = (float)(a / (8.0 * P));
     else if (j < 10) dgam[(size_t)b * 256 + g * 8 + (j - 2)] = (float)a;
     else dbet[(size_t)b * 256 + g * 8 + (j - 10)] = (float)a;
@@ -417,15 +526,25 @@ struct KGnBwdSums {
 // pass 2: dy = rstd (g - m1 - xhat m2), written over du.  grid (ceil(B * P * 256 / nt))
 struct KGnBwdApply {
   float* du; const float *y, *st, *gamma, *beta, *m; int P; long long n;
-  TK_HD void operator()(const Idx& i) const {
-    const long long e = (long long)i.bx * i.nt + i.tx;
+  TK_HD float one(float d, float yv, float mu, float rstd, float m1, float m2, int c) const {
+    const float xh = (yv - mu) * rstd;
+    const float g = d * tk_gelu_grad(gamma[c] * xh + beta[c]) * gamma[c];
+    return rstd * (g - m1 - xh * m2);
+  }
+  TK_HD void operator()(const Idx& i) const {  // four consecutive channels per thread, like KGnGeluFwd
+    const long long e = 4 * ((long long)i.bx * i.nt + i.tx);
     if (e >= n) return;
     const int c = (int)(e & 255);
     const long long b = e / ((long long)P * 256);
     const size_t gi = ((size_t)b * 32 + (c >> 3)) * 2;
-    const float xh = (y[e] - st[gi]) * st[gi + 1];
-    const float g = du[e] * tk_gelu_grad(gamma[c] * xh + beta[c]) * gamma[c];
-    du[e] = st[gi + 1] * (g - m[gi] - xh * m[gi + 1]);
+    const float mu = st[gi], rstd = st[gi + 1], m1 = m[gi], m2 = m[gi + 1];
+    const TkF4 yv = *reinterpret_cast<const TkF4*>(y + e);
+    TkF4 d = *reinterpret_cast<const TkF4*>(du + e);
+    d.x = one(d.x, yv.x, mu, rstd, m1, m2, c);
+    d.y = one(d.y, yv.y, mu, rstd, m1, m2, c + 1);
+    d.z = one(d.z, yv.z, mu, rstd, m1, m2, c + 2);
+    d.w = one(d.w, yv.w, mu, rstd, m1, m2, c + 3);
+    *reinterpret_cast<TkF4*>(du + e) = d;
   }
 };
 
@@ -456,15 +575,16 @@ struct KRotWsumPart {
     part[((size_t)b * ((P + per - 1) / per) + ch) * 256 + c] = acc;
   }
 };
-// r6[b, 3h + j] = Wn[j, :] . wsum[b, :] + bn[j] sum_p wp[p] + bp.  grid (B), nt >= 3
+// r6[b, 3h + j] = Wn[j, :] . wsum[b, :] + bn[j] sum_p wp[p] + bp; swp[h] = sum_p wp[p], computed once per step by a chunked
+// column sum (a serial sum over the P weights in every thread was 30-50 us of pure load latency).  grid (B), nt >= 3
 struct KRotOut {
-  const float *wsum, *wn, *bn, *wp, *bp; float* r6; int P, h;
+  const float *wsum, *wn, *bn, *swp, *bp; float* r6; int P, h;
   TK_HD void operator()(const Idx& i) const {
     const int b = i.bx, j = i.tx;
     if (j >= 3) return;
-    float acc = 0.0f, sw = 0.0f;
+    float acc = 0.0f;
     for (int c = 0; c < 256; ++c) acc = fmaf(wn[j * 256 + c], wsum[(size_t)b * 256 + c], acc);
-    for (int p = 0; p < P; ++p) sw += wp[p];
+    const float sw = swp[h];
     r6[(size_t)b * 6 + 3 * h + j] = acc + bn[j] * sw + bp[0];
   }
 };
@@ -472,7 +592,7 @@ struct KRotOut {
 // dWn[j, c] += sum_b dr[b, j] wsum[b, c]; dbn[j] += sum_b dr[b, j] sum_p wp; dbp += sum_{b, j} dr[b, j].
 // grid (1), nt = 256 (thread = channel c)
 struct KRotTailBwd {
-  const float *d_r6, *wsum, *wn, *wp; float *e, *dwn, *dbn, *dbp; int B, P, h;
+  const float *d_r6, *wsum, *wn, *swp; float *e, *dwn, *dbn, *dbp; int B, P, h;
   TK_HD void operator()(const Idx& i) const {
     const int c = i.tx;
     if (c >= 256) return;
@@ -484,8 +604,8 @@ struct KRotTailBwd {
     }
     for (int j = 0; j < 3; ++j) dwn[j * 256 + c] += gw[j];
     if (c < 3) {
-      float sw = 0.0f, sd = 0.0f;
-      for (int p = 0; p < P; ++p) sw += wp[p];
+      const float sw = swp[h];
+      float sd = 0.0f;
       for (int b = 0; b < B; ++b) sd += d_r6[(size_t)b * 6 + 3 * h + c];
       dbn[c] += sd * sw;
     }

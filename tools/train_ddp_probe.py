@@ -16,7 +16,7 @@ import torch.distributed as dist
 
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from catre_b200 import dropin, synth  # noqa: E402
-from oracle import catre_oracle as co, train_oracle as to  # noqa: E402  (input preparation of the probe only)
+from tests.test_train_gpu import y_symmetry_rotations  # noqa: E402
 
 
 def main():
@@ -27,12 +27,14 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device(dev))
     w = synth.load_weights()
-    rots = to.y_symmetry_rotations()
+    rots = y_symmetry_rotations()
     batch, tgt = synth.make_train_batch(B, 1024, 3 + rank, round_robin_cls=True)  # a different batch per rank
     d = batch.to(dev)
     gt_pose, gt_scale = tgt.gt_pose.to(dev), tgt.gt_scale.to(dev)
     sym_info = [rots if s else None for s in tgt.sym_y]
-    x, tfd = co.update_points(d.pcl, d.prior, d.init_pose, d.init_scale)
+    # the re-posed points the reference's forward receives (batch_test.py:92-95), channel-major views like the reference passes
+    x = (d.pcl - d.init_pose[:, :, 3].unsqueeze(1)).permute(0, 2, 1)
+    tfd = ((d.prior * d.init_scale.unsqueeze(1)) @ d.init_pose[:, :, :3].transpose(1, 2)).permute(0, 2, 1)
     cfg = {"INPUT": {"ZERO_CENTER_INPUT": True}, "MODEL": {"DEVICE": dev},
            "SOLVER": {"OPTIMIZER_CFG": {"type": "Ranger", "lr": 1e-4, "weight_decay": 0}}}
     model, opt = dropin.build_model_optimizer(cfg, is_test=False, max_batch=max(8, B))

@@ -25,11 +25,12 @@ def main():
         modes = os.environ.get("TRAIN_PROBE_MODES", "tc,tc-nograph,simt").split(",")
         for mode in modes:  # tc (default: tcgen05 GEMM for the large shapes), simt (64 x 64 CUDA-core tiles), v2, naive;
             # a "-nograph" suffix launches the chain kernel by kernel (CATRE_TRAIN_GRAPH=0) instead of replaying its CUDA graph
-            ver = mode.replace("-nograph", "")
+            ver = mode.replace("-nograph", "").replace("-carve", "")
+            os.environ["CATRE_TRAIN_CARVEOUT"] = "1" if "-carve" in mode else "0"
             naive = "1" if ver == "naive" else "0"
             os.environ["CATRE_TRAIN_NAIVE_GEMM"] = naive
             os.environ["CATRE_TRAIN_GEMM"] = ver
-            os.environ["CATRE_TRAIN_GRAPH"] = "0" if mode.endswith("-nograph") else "1"
+            os.environ["CATRE_TRAIN_GRAPH"] = "0" if "-nograph" in mode else "1"
             eng = engine.Engine(1024, 8, "fp32", 0)
             eng.load_weights(w)
             step = lambda: eng.train_step(x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, gp, gs, tgt.sym_y.numpy(), rots)
@@ -43,7 +44,7 @@ def main():
                 step()
             b.record()
             torch.cuda.synchronize()
-            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": ver, "cuda_graph": not mode.endswith("-nograph"),
+            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": ver, "cuda_graph": "-nograph" not in mode, "max_shared_carveout": "-carve" in mode,
                               "ms_per_step": a.elapsed_time(b) / n, "launches": eng.last_launch_count(),
                               "objects_per_s": B / (a.elapsed_time(b) / n / 1e3)}), flush=True)
             eng.close()
