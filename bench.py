@@ -515,7 +515,7 @@ def main():
             rots[:, 0, 0], rots[:, 0, 2], rots[:, 1, 1], rots[:, 2, 0], rots[:, 2, 2] = np.cos(ang), np.sin(ang), 1.0, -np.sin(ang), np.cos(ang)
             gp, gs = tt.gt_pose.to(dev), tt.gt_scale.to(dev)
             tstep = lambda: eng.train_step(x_pm, tfd_pm, td.prior, td.init_pose, td.init_scale, td.K, gp, gs, tt.sym_y.numpy(), rots)
-            for _ in range(2):
+            for _ in range(3):  # kernel by kernel, graph capture, first replay
                 tstep()
             torch.cuda.synchronize()
             a, b_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)

@@ -20,22 +20,35 @@ __global__ void __launch_bounds__(256) tk_gemm_tiled(GemmP p) {
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0f;
   const bool a_kfast = p.sak == 1, b_nfast = p.sbn == 1;
+  // the next slab's 4 + 4 operand values per thread are loaded into registers underneath the FMAs of the current slab: the
+  // chain's small launches (one or a few CTAs, 16 slabs each) are bound by the latency of this load, not by arithmetic
+  float ra[4], rb[4];
+  auto load_slab = [&](int kb) {
+#pragma unroll
+    for (int l = 0; l < 4; ++l) {
+      const int idx = tid + l * 256;
+      int m, k;
+      if (a_kfast) { m = idx >> 4; k = idx & 15; } else { m = idx & 63; k = idx >> 6; }
+      ra[l] = (m0 + m < p.M && kb + k < k1) ? A[(long long)(m0 + m) * p.sam + (long long)(kb + k) * p.sak] : 0.0f;
+      int n, k2;
+      if (b_nfast) { k2 = idx >> 6; n = idx & 63; } else { k2 = idx & 15; n = idx >> 4; }
+      rb[l] = (n0 + n < p.N && kb + k2 < k1) ? Bm[(long long)(kb + k2) * p.sbk + (long long)(n0 + n) * p.sbn] : 0.0f;
+    }
+  };
+  if (k0 < k1) load_slab(k0);
   for (int kb = k0; kb < k1; kb += 16) {
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       const int idx = tid + l * 256;
       int m, k;
       if (a_kfast) { m = idx >> 4; k = idx & 15; } else { m = idx & 63; k = idx >> 6; }
-      float v = 0.0f;
-      if (m0 + m < p.M && kb + k < k1) v = A[(long long)(m0 + m) * p.sam + (long long)(kb + k) * p.sak];
-      As[k][m] = v;
+      As[k][m] = ra[l];
       int n, k2;
       if (b_nfast) { k2 = idx >> 6; n = idx & 63; } else { k2 = idx & 15; n = idx >> 4; }
-      v = 0.0f;
-      if (n0 + n < p.N && kb + k2 < k1) v = Bm[(long long)(kb + k2) * p.sbk + (long long)(n0 + n) * p.sbn];
-      Bs[k2][n] = v;
+      Bs[k2][n] = rb[l];
     }
     __syncthreads();
+    if (kb + 16 < k1) load_slab(kb + 16);
 #pragma unroll
     for (int kk = 0; kk < 16; ++kk) {
       float a[4], b[4];
