@@ -175,12 +175,21 @@ class CrossImageRefiner:
 
     def add(self, inputs: Sequence[Dict[str, Any]]) -> None:
         t0 = time.perf_counter()
-        # collate on the host: the objects cross to the device once per launch (flush), not once per image
-        batch = batch_data_test(self.cfg, inputs, device="cpu")
         self.stats.images += len(inputs)
-        if int(batch["obj_cls"].shape[0]) == 0 or not _filter_labels(self.evaluator, batch, "cpu"):
-            return  # nothing to refine for this item (the reference `continue`s)
-        n_obj = int(batch["obj_cls"].shape[0])
+        if getattr(self.evaluator, "train_objs", None) is None:
+            # no label adaptation: only count the item's objects here; all items of a launch are collated by ONE
+            # batch_data_test call in flush() (a few hundred tiny torch calls per launch instead of per image -- the host, not
+            # the device, bounds this loop at 256 objects per launch)
+            batch = None
+            n_obj = sum(len(d["instances"]) for d in inputs)
+            if n_obj == 0:
+                return  # nothing to refine for this item (the reference `continue`s)
+        else:
+            # collate on the host: the objects cross to the device once per launch (flush), not once per image
+            batch = batch_data_test(self.cfg, inputs, device="cpu")
+            if int(batch["obj_cls"].shape[0]) == 0 or not _filter_labels(self.evaluator, batch, "cpu"):
+                return
+            n_obj = int(batch["obj_cls"].shape[0])
         # never let a launch grow past objects_per_launch (normally the engine's max_batch): the engine would split it into a
         # full chunk plus a few-object chunk, and a few-object K-loop is latency-bound (1 ms for 8 objects, as long as 20 of
         # a full launch's objects) -- launch what is pending first
@@ -190,6 +199,32 @@ class CrossImageRefiner:
         self.pending_objs += n_obj
         if self.pending_objs >= self.objects_per_launch:
             self.flush()
+
+    def _collate_launch(self, items: List[_Pending]) -> Dict[str, Any]:
+        """One batch_data_test over every image of the launch; the per-item batches the evaluator receives are views of it
+        (same values as a per-item collation; im_id counts the images of the item, as batch_data_test does per item)."""
+        big = batch_data_test(self.cfg, [d for it in items for d in it.inputs], device="cpu")
+        sizes = [it.n_obj for it in items]
+        n = sum(sizes)
+        parts: Dict[str, Any] = {}
+        for k, v in big.items():
+            if k == "obj_kps":
+                continue  # the same tensor as obj_mean_points
+            if isinstance(v, torch.Tensor) and v.shape[0] == n:
+                parts[k] = v.split(sizes, dim=0)
+        lo = im0 = 0
+        share = (time.perf_counter() - self._t_flush) / max(1, len(items))
+        for i, it in enumerate(items):
+            b: Dict[str, Any] = {k: p[i] for k, p in parts.items()}
+            if im0:
+                b["im_id"] = b["im_id"] - float(im0)
+            b["sym_info"] = big["sym_info"][lo: lo + it.n_obj]
+            b["obj_kps"] = b["obj_mean_points"]
+            it.batch = b
+            it.t_collate += share
+            lo += it.n_obj
+            im0 += len(it.inputs)
+        return big
 
     def _staging(self, n: int, items: List[_Pending]) -> Dict[str, torch.Tensor]:
         st = self._stage[self._cur]
@@ -209,11 +244,15 @@ class CrossImageRefiner:
         if self.pending:
             items, self.pending = self.pending, []
             n, self.pending_objs = self.pending_objs, 0
-            t0 = time.perf_counter()
+            t0 = self._t_flush = time.perf_counter()
+            big = self._collate_launch(items) if items[0].batch is None else None
             st = self._staging(n, items)
             args = []
             for key, name in self._KEYS:
-                torch.cat([it.batch[key] for it in items], dim=0, out=st[name][:n])
+                if big is not None:
+                    st[name][:n].copy_(big[key])
+                else:
+                    torch.cat([it.batch[key] for it in items], dim=0, out=st[name][:n])
                 args.append(st[name][:n].to(self.device, non_blocking=True) if self.on_gpu else st[name][:n])
             k1 = self.n_iter + 1
             poses_h = st["out_pose"][: k1 * n * 12].view(k1, n, 3, 4)
