@@ -8,7 +8,9 @@
 // both into the 128B-swizzled K-major tiles the UMMA descriptors expect (chunk' = chunk ^ (row & 7), the layout TMA's
 // SWIZZLE_128B produces).  One elected thread issues the MMAs of a 64-deep k slab; their completion (tcgen05.commit) frees the
 // slab's stage of a 3-stage ring, so the MMAs of slab s run underneath the conversions of slab s+1; the global loads of slabs
-// s+1 and s+2 are in flight (two register buffers) while slab s is converted.
+// s+1 and s+2 are in flight (two register buffers) while slab s is converted.  The issuing thread sits in a 17th warp of its
+// own: the 16 producer warps hand a stage over through a "full" mbarrier (one arrival per warp after its cross-proxy fence) and
+// never wait for the MMA issue, and there is no block-wide barrier in the k loop.
 //
 // Orientation: the GEMM's output COLUMNS n sit on the 128 TMEM lanes (UMMA M side) and its ROWS m on the TMEM columns (UMMA N
 // side): D[n][m] = sum_k B(k, n) A(m, k).  Every output of the chain is n-fast (scn == 1), so with thread = column n a warp's
@@ -31,7 +33,8 @@ constexpr int TG_STAGES = 3;
 constexpr int TG_TILE_BYTES = 128 * 128;             // 128 rows x 64 x 2 B
 constexpr int TG_STAGE_BYTES = 4 * TG_TILE_BYTES;    // [n hi][n lo][m hi][m lo]
 constexpr int TG_SMEM = 1024 + TG_STAGES * TG_STAGE_BYTES;
-constexpr int TG_THREADS = 512;
+constexpr int TG_THREADS = 512;                      // producer / epilogue threads (16 warps)
+constexpr int TG_CTA_THREADS = TG_THREADS + 32;      // + one warp whose elected lane issues the MMAs
 constexpr int TG_CHUNKS = 128 * 8 / TG_THREADS;      // 16-byte chunks per thread and operand tile
 
 // chunk i of thread tid inside a 128-row x 8-chunk operand tile.  k-fast operands: the 8 chunks of a row on 8 consecutive
@@ -99,14 +102,15 @@ struct KColMaxDecode {
   }
 };
 
-// grid (ceil(M / 128), ceil(N / 128), batch * splits), 512 threads, TG_SMEM bytes of dynamic shared memory
+// grid (ceil(M / 128), ceil(N / 128), batch * splits), 544 threads, TG_SMEM bytes of dynamic shared memory
 template <bool F16>
-__global__ void __launch_bounds__(TG_THREADS, 1) tk_gemm_tc(GemmP p, TgColMax cm) {
+__global__ void __launch_bounds__(TG_CTA_THREADS, 1) tk_gemm_tc(GemmP p, TgColMax cm) {
   using namespace catre;
   extern __shared__ __align__(1024) uint8_t tg_smem[];
   const uint32_t smem_base = smem_u32(tg_smem);
   if (smem_base & 1023u) __trap();  // the swizzled tiles need a 1 KB aligned base
-  const uint32_t bar_free = smem_base, bar_done = smem_base + 64, tmem_slot = smem_base + 128;
+  const uint32_t bar_free = smem_base, bar_full = smem_base + 32, bar_done = smem_base + 64, tmem_slot = smem_base + 128;
+  const bool producer = threadIdx.x < TG_THREADS;
   const uint32_t ring = smem_base + 1024;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const int m0 = blockIdx.x * TG_TM, n0 = blockIdx.y * TG_TN;
@@ -115,17 +119,6 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tk_gemm_tc(GemmP p, TgColMax cm
   const float* A = p.A + (long long)z * p.sab;
   const float* Bm = p.B + (long long)z * p.sbb;
   const int nslab = k1 > k0 ? (k1 - k0 + TG_BK - 1) / TG_BK : 0;  // a trailing split can be empty: its partial is zero
-
-  if (tid == 0) {
-    for (int i = 0; i < TG_STAGES; ++i) mbar_init(bar_free + 8 * i, 1);
-    mbar_init(bar_done, 1);
-    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-  }
-  if (warp == 1) tmem_alloc(tmem_slot, 128);
-  tc_fence_before();
-  __syncthreads();
-  tc_fence_after();
-  const uint32_t tmem_base = *reinterpret_cast<volatile uint32_t*>(tg_smem + 128);
 
   // operand geometry: "m" tile = rows m0.. of A (element (m, k) at A[m sam + k sak]); "n" tile = columns n0.. of B
   // (element (n, k) at B[k sbk + n sbn])
@@ -136,6 +129,7 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tk_gemm_tc(GemmP p, TgColMax cm
   const float* Bn = Bm + (long long)n0 * p.sbn;
   const int m_rows = p.M - m0, n_rows = p.N - n0;  // valid rows of the two tiles (may exceed 128)
 
+  uint32_t tmem_base = 0;  // set after the allocation below (the MMA / epilogue code only runs after it)
   // two register buffers: the loads of slabs s+1 and s+2 are in flight while slab s is converted
   float va0[TG_CHUNKS][8], vb0[TG_CHUNKS][8], va1[TG_CHUNKS][8], vb1[TG_CHUNKS][8];
   auto load_slab = [&](int s, float (&va)[TG_CHUNKS][8], float (&vb)[TG_CHUNKS][8]) {
@@ -160,16 +154,44 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tk_gemm_tc(GemmP p, TgColMax cm
     }
   };
   constexpr uint32_t idesc = umma_idesc<F16>(TG_TN, TG_TM);
+  // producer side of one slab: wait until the stage's previous occupant (slab s - STAGES) has been read by its MMAs, convert and
+  // store, make the generic-proxy writes visible to the tensor core's async-proxy reads, hand the stage over (one arrival per
+  // warp), then start the loads of slab s + 2 into the registers just emptied
   auto step = [&](int s, float (&va)[TG_CHUNKS][8], float (&vb)[TG_CHUNKS][8]) {
     const int stage = s % TG_STAGES;
     const uint32_t sb = ring + (uint32_t)stage * TG_STAGE_BYTES;
-    // the stage's previous occupant (slab s - STAGES) must have been read by its MMAs
     if (s >= TG_STAGES) mbar_wait(bar_free + 8 * stage, (uint32_t)((s / TG_STAGES) - 1) & 1);
     store_slab(sb, va, vb);
-    fence_proxy_async_smem();  // generic-proxy writes -> visible to the tensor core's async-proxy reads
-    if (s + 2 < nslab) load_slab(s + 2, va, vb);  // in flight across two barriers
-    __syncthreads();
-    if (tid == 0) {
+    fence_proxy_async_smem();
+    __syncwarp();
+    if (lane == 0) mbar_arrive(bar_full + 8 * stage);
+    if (s + 2 < nslab) load_slab(s + 2, va, vb);
+  };
+  // the global loads of the first two slabs are issued BEFORE the barrier / tensor-memory set-up: they depend on neither
+  if (producer) {
+    if (nslab > 0) load_slab(0, va0, vb0);
+    if (nslab > 1) load_slab(1, va1, vb1);
+  }
+  if (tid == 0) {
+    for (int i = 0; i < TG_STAGES; ++i) { mbar_init(bar_free + 8 * i, 1); mbar_init(bar_full + 8 * i, TG_THREADS / 32); }
+    mbar_init(bar_done, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) tmem_alloc(tmem_slot, 128);
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  tmem_base = *reinterpret_cast<volatile uint32_t*>(tg_smem + 128);
+  if (producer) {
+    for (int s = 0; s < nslab; s += 2) {
+      step(s, va0, vb0);
+      if (s + 1 < nslab) step(s + 1, va1, vb1);
+    }
+  } else if (lane == 0) {  // MMA issue: one elected thread
+    for (int s = 0; s < nslab; ++s) {
+      const int stage = s % TG_STAGES;
+      const uint32_t sb = ring + (uint32_t)stage * TG_STAGE_BYTES;
+      mbar_wait(bar_full + 8 * stage, (uint32_t)(s / TG_STAGES) & 1);
       tc_fence_after();
       const uint32_t n_hi = sb, n_lo = sb + TG_TILE_BYTES, m_hi = sb + 2 * TG_TILE_BYTES, m_lo = sb + 3 * TG_TILE_BYTES;
 #pragma unroll
@@ -182,26 +204,20 @@ __global__ void __launch_bounds__(TG_THREADS, 1) tk_gemm_tc(GemmP p, TgColMax cm
       umma_commit(bar_free + 8 * stage);
       if (s == nslab - 1) umma_commit(bar_done);
     }
-  };
-  if (nslab > 0) load_slab(0, va0, vb0);
-  if (nslab > 1) load_slab(1, va1, vb1);
-  for (int s = 0; s < nslab; s += 2) {
-    step(s, va0, vb0);
-    if (s + 1 < nslab) step(s + 1, va1, vb1);
   }
 
   // ---- epilogue: warp w reads TMEM lanes 32 (w % 4) .. +31 (column n = n0 + that lane), columns 32 (w / 4) .. +31 (rows m)
-  if (nslab > 0) {
+  if (producer && nslab > 0) {
     mbar_wait(bar_done, 0);
     tc_fence_after();
   }
-  __syncwarp();  // thread 0 issued the last MMAs on its own: the warp-collective tcgen05.ld below needs the warp converged
+  __syncwarp();
   const int quad = warp & 3, part = warp >> 2;
   const int n = n0 + quad * 32 + lane;
   const bool n_ok = n < p.N;
   const float bias = (p.bias && n_ok && p.splits == 1) ? p.bias[n + (long long)z * p.sbias_b] : 0.0f;
   const int mc = m0 + part * 32;
-  if (mc < p.M) {  // warp-uniform
+  if (producer && mc < p.M) {  // warp-uniform
     float v[32];
     if (nslab > 0) {
       tmem_ld32(tmem_base + ((uint32_t)(quad * 32) << 16) + (uint32_t)(part * 32), v);
@@ -262,7 +278,7 @@ inline cudaError_t tk_gemm_tc_launch(const GemmP& p, int bz, cudaStream_t s, TgC
     if (st != cudaSuccess) return st;
     configured = true;
   }
-  tk_gemm_tc<F16><<<dim3((unsigned)((p.M + TG_TM - 1) / TG_TM), (unsigned)((p.N + TG_TN - 1) / TG_TN), (unsigned)bz), TG_THREADS, TG_SMEM, s>>>(p, cm);
+  tk_gemm_tc<F16><<<dim3((unsigned)((p.M + TG_TM - 1) / TG_TM), (unsigned)((p.N + TG_TN - 1) / TG_TN), (unsigned)bz), TG_CTA_THREADS, TG_SMEM, s>>>(p, cm);
   return cudaPeekAtLastError();
 }
 
