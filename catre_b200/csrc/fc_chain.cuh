@@ -463,12 +463,12 @@ inline bool fcc_layer_ok(const FccLayer& L, int ranks) {
 template <int RANKS>
 inline cudaError_t fcc_launch_t(const FccBatch& b, int clusters_total, cudaStream_t s) {
   auto kern = fc_chain_kernel<RANKS>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // function attributes belong to the device: set them once per device, not once per process
+  if (configured.needed()) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FCC_SMEM);
     if (st == cudaSuccess && RANKS > 8) st = cudaFuncSetAttribute(kern, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
     if (st != cudaSuccess) return st;
-    configured = true;
+    configured.done();
   }
   if (clusters_total < 1) return cudaSuccess;
   cudaLaunchConfig_t cfg = {};

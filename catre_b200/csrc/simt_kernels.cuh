@@ -10,6 +10,19 @@
 
 namespace catre {
 
+// "Once per device" flag for one-time kernel configuration (cudaFuncSetAttribute is per device): a process that drives engines
+// on several GPUs must configure every kernel on each of them.  Not thread-safe, like the launches it guards.
+struct DeviceOnce {
+  unsigned long long mask = 0;
+  int dev = -1;
+  bool needed() {
+    if (cudaGetDevice(&dev) != cudaSuccess) { dev = -1; return true; }
+    return dev < 0 || dev >= 64 || !((mask >> dev) & 1ull);
+  }
+  void done() { if (dev >= 0 && dev < 64) mask |= 1ull << dev; }
+};
+
+
 // ----------------------------------------------------------------------------------------------
 // small helpers
 // ----------------------------------------------------------------------------------------------

@@ -491,11 +491,11 @@ cudaError_t rot_fused_launch(const CUtensorMap& pf_hi, const CUtensorMap& pf_lo,
                              const CUtensorMap& w0_lo, const CUtensorMap& w1_hi, const CUtensorMap& w1_lo,
                              const RotFusedP& p, int num_sms, cudaStream_t s) {
   auto kern = rot_fused_kernel<NPROD, FT>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // function attributes belong to the device: set them once per device, not once per process
+  if (configured.needed()) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, ROT_SMEM);
     if (st != cudaSuccess) return st;
-    configured = true;
+    configured.done();
   }
   int items = p.tiles * 2;
   int grid = items < num_sms ? items : num_sms;
@@ -756,11 +756,11 @@ template <int NPROD>
 cudaError_t enc_fused_launch(const CUtensorMap& x_hi, const CUtensorMap& x_lo, const CUtensorMap& w2_hi, const CUtensorMap& w2_lo,
                              const CUtensorMap& w3_hi, const CUtensorMap& w3_lo, const EncFusedP& p, int num_sms, cudaStream_t s) {
   auto kern = enc_fused_kernel<NPROD>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // function attributes belong to the device: set them once per device, not once per process
+  if (configured.needed()) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, RF_SMEM);
     if (st != cudaSuccess) return st;
-    configured = true;
+    configured.done();
   }
   int grid = p.tiles < num_sms ? p.tiles : num_sms;
   if (grid < 1) return cudaSuccess;

@@ -760,12 +760,12 @@ cudaError_t tc_launch(const CUtensorMap& ma_hi, const CUtensorMap& ma_lo, const 
   using Cfg = TcCfg<ORIENT, BN, NPROD>;
   constexpr bool RESW = TcRes<ORIENT, EPI>::value;
   auto kern = tc_gemm_kernel<ORIENT, EPI, BN, NPROD>;
-  static bool configured = false;
-  if (!configured) {
+  static DeviceOnce configured;  // function attributes belong to the device: set them once per device, not once per process
+  if (configured.needed()) {
     cudaError_t st = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           RESW ? Cfg::MAX_SMEM : Cfg::SMEM_BYTES);
     if (st != cudaSuccess) return st;
-    configured = true;
+    configured.done();
   }
   TcGemmP q = p;
   q.out_bufs = Cfg::OUT_BUFS;

@@ -272,11 +272,11 @@ __global__ void __launch_bounds__(TG_CTA_THREADS, 1) tk_gemm_tc(GemmP p, TgColMa
 
 template <bool F16>
 inline cudaError_t tk_gemm_tc_launch(const GemmP& p, int bz, cudaStream_t s, TgColMax cm = TgColMax{nullptr, 1}) {
-  static bool configured = false;
-  if (!configured) {
+  static catre::DeviceOnce configured;  // function attributes belong to the device: set them once per device, not once per process
+  if (configured.needed()) {
     cudaError_t st = cudaFuncSetAttribute(tk_gemm_tc<F16>, cudaFuncAttributeMaxDynamicSharedMemorySize, TG_SMEM);
     if (st != cudaSuccess) return st;
-    configured = true;
+    configured.done();
   }
   tk_gemm_tc<F16><<<dim3((unsigned)((p.M + TG_TM - 1) / TG_TM), (unsigned)((p.N + TG_TN - 1) / TG_TN), (unsigned)bz), TG_CTA_THREADS, TG_SMEM, s>>>(p, cm);
   return cudaPeekAtLastError();

@@ -402,3 +402,35 @@ def test_fused_rot_tail_matches_the_reference_goldens(weights, name):
         eng = get_engine(weights, case.n_pts, "f16x3", rot_tail="fused")
         poses, scales = run_refine(eng, case.batch, case.n_iter)
         assert max(gu.max_abs_err(poses, scales, case.poses, case.scales)) <= TOL
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs in one process")
+def test_engines_on_two_devices_in_one_process(weights):
+    """One process driving an engine on each of two GPUs (kernel attributes such as the dynamic shared-memory limit belong to
+    the device, not to the process): the second device gives the first one's bits, in inference and in the training step."""
+    import numpy as np
+
+    b = synth.make_batch(9, 1024, seed=77)
+    tb, tt = synth.make_train_batch(4, 1024, 5, round_robin_cls=True)
+    n = int(np.ceil(np.pi / 0.01))
+    a = np.arange(1, n) * 2.0 * np.pi / n
+    rots = np.zeros((n - 1, 3, 3), np.float32)
+    rots[:, 0, 0], rots[:, 0, 2], rots[:, 1, 1], rots[:, 2, 0], rots[:, 2, 2] = np.cos(a), np.sin(a), 1.0, -np.sin(a), np.cos(a)
+    outs = []
+    for dev in (0, 1):
+        with torch.cuda.device(dev):
+            eng = engine.Engine(1024, 16, "f16x3", dev)
+            eng.load_weights(weights)
+            d = b.to(f"cuda:{dev}")
+            p, s = eng.refine(d.pcl, d.prior, d.init_pose, d.init_scale, d.K, 3)
+            t = tb.to(f"cuda:{dev}")
+            x_pm = (t.pcl - t.init_pose[:, :, 3].unsqueeze(1)).contiguous()
+            tfd_pm = ((t.prior * t.init_scale.unsqueeze(1)) @ t.init_pose[:, :, :3].transpose(1, 2)).contiguous()
+            tp, ts, tl = eng.train_step(x_pm, tfd_pm, t.prior, t.init_pose, t.init_scale, t.K, tt.gt_pose.to(f"cuda:{dev}"),
+                                        tt.gt_scale.to(f"cuda:{dev}"), tt.sym_y.numpy(), rots)
+            g = eng.train_grads_flat(1.0)
+            torch.cuda.synchronize(dev)
+            outs.append([x.cpu() for x in (p, s, tp, ts, tl, g)])
+            eng.close()
+    for x, y in zip(*outs):
+        assert torch.equal(x, y)
