@@ -742,6 +742,9 @@ struct CudaTrainOps {
   static bool tc_shape(const catre_train::GemmP& p, int bz) {
     return p.M >= 16 && p.N >= 16 && p.K >= 16 && (double)p.M * p.N * p.K * (p.splits > 1 ? 1 : bz) >= (double)(1 << 20);
   }
+  // bias gradient inside a split-K weight-gradient launch (train_gemm_tc.cuh): the tensor-core path with A = dy^T (m fast)
+  bool folds_bias_grad(const catre_train::GemmP& p) const { return tc && !naive && fold_bg && p.sam == 1 && p.splits > 1 && tc_shape(p, 1); }
+  bool fold_bg = true;  // CATRE_TRAIN_FOLD_BIAS=0: column sums as separate launches
   void gemm_tc(const catre_train::GemmP& p, int bz) {
     note(p.f16 ? catre_train::tk_gemm_tc_launch<true>(p, bz, s) : catre_train::tk_gemm_tc_launch<false>(p, bz, s));
     ++launches;
@@ -1522,6 +1525,8 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   const bool gemm_tc = !naive_gemm && !gemm_v2 && !(env2 && strcmp(env2, "simt") == 0);
   const char* env4 = getenv("CATRE_TRAIN_CARVEOUT");
   const bool carve = gemm_tc && env4 && env4[0] == '1';  // experiment (see CudaTrainOps::carve)
+  const char* env5 = getenv("CATRE_TRAIN_FOLD_BIAS");
+  const bool fold_bg = !(env5 && env5[0] == '0');
   auto make_in = [&](const float* x, const float* tfd, const float* kps, const float* po, const float* sc, const float* Kz,
                      const float* gp, const float* gs, float* op, float* os) {
     catre_train::TrainIn in{nullptr, kps, po, sc, Kz, gp, gs, B, n_sym_rots, n_sym, B - n_sym, op, os};
@@ -1532,6 +1537,7 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   auto run_chain = [&](cudaStream_t st, const catre_train::TrainIn& in, int64_t& n_launch) -> cudaError_t {
     CudaTrainOps ops{st, naive_gemm, gemm_v2, gemm_tc, e->num_sms};
     ops.carve = carve;
+    ops.fold_bg = fold_bg;
     catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
     chain.forward(in);
     chain.loss(in);
@@ -1543,7 +1549,7 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   bool done = false;
   if (!(env3 && env3[0] == '0')) {
     catre_engine::TrainGraphKey key{};
-    key.B = B; key.n_sym = n_sym; key.n_rots = n_sym_rots; key.mode = (naive_gemm ? 1 : (gemm_v2 ? 2 : (gemm_tc ? 0 : 3))) + (carve ? 8 : 0);
+    key.B = B; key.n_sym = n_sym; key.n_rots = n_sym_rots; key.mode = (naive_gemm ? 1 : (gemm_v2 ? 2 : (gemm_tc ? 0 : 3))) + (carve ? 8 : 0) + (fold_bg ? 0 : 16);
     for (int i = 0; i < 4; ++i) key.lw[i] = e->loss_w[i];
     if (e->train_graphs.size() > 64 && !e->train_graphs.count(key)) {  // bound the cache (each graph holds ~240 nodes)
       CU_TRY(e, cudaStreamSynchronize(s));

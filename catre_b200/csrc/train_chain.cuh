@@ -124,9 +124,11 @@ struct Chain {
 
   static unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
-  void gemm(const float* A, long long sam, long long sak, const float* Bm, long long sbk, long long sbn, float* C, long long scm,
+  // db: for a weight-gradient product (A = dy^T), the bias gradient db[M] += column sums of dy; returns true when the launcher
+  // folded them into the GEMM (tensor-core path), false when the caller still has to compute them
+  bool gemm(const float* A, long long sam, long long sak, const float* Bm, long long sbk, long long sbn, float* C, long long scm,
             long long scn, int M, int Nn, int K, const float* bias, int relu, int acc, int batch = 1, long long sab = 0,
-            long long sbb = 0, long long scb = 0, long long sbias_b = 0) {
+            long long sbb = 0, long long scb = 0, long long sbias_b = 0, float* db = nullptr) {
     GemmP p{};
     p.A = A; p.sam = sam; p.sak = sak; p.sab = sab; p.B = Bm; p.sbk = sbk; p.sbn = sbn; p.sbb = sbb;
     p.C = C; p.scm = scm; p.scn = scn; p.scb = scb; p.bias = bias; p.sbias_b = sbias_b;
@@ -140,12 +142,17 @@ struct Chain {
       if (splits > 1) {
         p.splits = splits;
         p.k_per = ((K + splits - 1) / splits + 63) & ~63;
+        const bool fold = db && (size_t)splits * M * (Nn + 1) <= TrainWs::kPartialFloats && o.folds_bias_grad(p);
+        if (fold) p.bias_grad_partial = w.partial + (size_t)splits * M * Nn;
         o.gemm(p, splits);
-        o.run(KSplitReduce{w.partial, C, scm, scn, M, Nn, splits, acc}, cdiv((long long)M * Nn, 256), 1, 1, 256);
-        return;
+        KSplitReduce red{w.partial, C, scm, scn, M, Nn, splits, acc};
+        if (fold) { red.bg_partial = p.bias_grad_partial; red.bg_out = db; }
+        o.run(red, cdiv((long long)M * Nn, 256), 1, 1, 256);
+        return fold;
       }
     }
     o.gemm(p, batch);
+    return false;
   }
   // out[rows, C] = act(x[rows, K] W^T + b), W = checkpoint tensor wi [C, K] (+ bias wi+1)
   void layer(const float* x, int K, int wi, int C, float* out, long long rows, int relu) {
@@ -214,8 +221,9 @@ struct Chain {
   void lin_bwd(int wi, const float* x, int K, const float* dy, int C, long long ldy, long long rows, float* dx, int dx_acc,
                int ldw = 0, int woff = 0, bool with_bias = true) {
     if (ldw == 0) ldw = K;
-    gemm(dy, 1, ldy, x, K, 1, w.G[wi] + woff, ldw, 1, C, K, (int)rows, nullptr, 0, 1);
-    if (with_bias) colsum(dy, rows, C, ldy, w.G[wi + 1], 1);
+    const bool folded = gemm(dy, 1, ldy, x, K, 1, w.G[wi] + woff, ldw, 1, C, K, (int)rows, nullptr, 0, 1, 1, 0, 0, 0, 0,
+                             with_bias ? w.G[wi + 1] : nullptr);
+    if (with_bias && !folded) colsum(dy, rows, C, ldy, w.G[wi + 1], 1);
     if (dx) gemm(dy, ldy, 1, W[wi] + woff, ldw, 1, dx, K, 1, (int)rows, K, C, nullptr, 0, dx_acc);
   }
   // wsum[b, c] = sum_p wp[p] u1[b, p, c]: chunked over the points, then the chunks of an object in order

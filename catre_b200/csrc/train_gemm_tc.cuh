@@ -129,6 +129,11 @@ __global__ void __launch_bounds__(TG_CTA_THREADS, 1) tk_gemm_tc(GemmP p, TgColMa
   const float* Bn = Bm + (long long)n0 * p.sbn;
   const int m_rows = p.M - m0, n_rows = p.N - n0;  // valid rows of the two tiles (may exceed 128)
 
+  // bias gradient folded into a weight-gradient launch (GemmP::bias_grad_partial): A is dy^T with the channel m fast, so thread
+  // tid holds k values of channel m0 + (tid & 127) in every slab (tg_chunk<false>); the 4 threads of a channel are summed in a
+  // fixed order through shared memory after the k loop.  Only the first column tile does it.
+  const bool do_bg = p.bias_grad_partial != nullptr && blockIdx.y == 0 && !a_kfast && p.splits > 1;
+  float bg = 0.0f;
   uint32_t tmem_base = 0;  // set after the allocation below (the MMA / epilogue code only runs after it)
   // two register buffers: the loads of slabs s+1 and s+2 are in flight while slab s is converted
   float va0[TG_CHUNKS][8], vb0[TG_CHUNKS][8], va1[TG_CHUNKS][8], vb1[TG_CHUNKS][8];
@@ -161,6 +166,12 @@ __global__ void __launch_bounds__(TG_CTA_THREADS, 1) tk_gemm_tc(GemmP p, TgColMa
     const int stage = s % TG_STAGES;
     const uint32_t sb = ring + (uint32_t)stage * TG_STAGE_BYTES;
     if (s >= TG_STAGES) mbar_wait(bar_free + 8 * stage, (uint32_t)((s / TG_STAGES) - 1) & 1);
+    if (do_bg) {  // this thread's 2 x 8 k values of its A row (channel m0 + (tid & 127)): the bias gradient's share
+#pragma unroll
+      for (int i = 0; i < TG_CHUNKS; ++i)
+#pragma unroll
+        for (int j = 0; j < 8; ++j) bg += va[i][j];
+    }
     store_slab(sb, va, vb);
     fence_proxy_async_smem();
     __syncwarp();
@@ -261,6 +272,13 @@ __global__ void __launch_bounds__(TG_CTA_THREADS, 1) tk_gemm_tc(GemmP p, TgColMa
           if (mc + j < p.M) dst[(long long)j * p.scm] = v[j];
       }
     }
+  }
+  if (producer && do_bg) {  // the ring is free: every producer has passed bar_done (or the split is empty and nothing used it)
+    float* red = reinterpret_cast<float*>(tg_smem + 1024);
+    red[tid] = bg;
+    named_bar_sync(1, TG_THREADS);
+    if (tid < 128 && m0 + tid < p.M)
+      p.bias_grad_partial[(size_t)blockIdx.z * p.M + m0 + tid] = ((red[tid] + red[tid + 128]) + red[tid + 256]) + red[tid + 384];
   }
   tc_fence_before();
   __syncthreads();

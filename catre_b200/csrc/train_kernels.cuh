@@ -119,6 +119,9 @@ struct GemmP {
   int relu, accumulate;
   int splits; int k_per; float* partial;
   int f16;  // tensor-core GEMM only (train_gemm_tc.cuh): 1 = fp16 hi/lo operands (forward), 0 = bf16 hi/lo (backward)
+  // tensor-core GEMM only, weight-gradient launches (A(m, k) = dy[k, m], m fast, splits > 1): when set, the CTAs of the first
+  // column tile also sum their A rows over k -- the bias gradient's share of the split -- into bias_grad_partial[split][M]
+  float* bias_grad_partial;
 };
 struct KGemmNaive {
   GemmP p;
@@ -144,8 +147,14 @@ struct KGemmNaive {
 struct KSplitReduce {
   const float* partial; float* C; long long scm, scn; int M, N, splits, accumulate;
   const float* bias = nullptr; int relu = 0;
+  const float* bg_partial = nullptr; float* bg_out = nullptr;  // bias-gradient shares [splits][M] -> bg_out[M] += their sum
   TK_HD void operator()(const Idx& i) const {
     const long long e = (long long)i.bx * i.nt + i.tx;
+    if (bg_partial && e < M) {
+      float a = 0.0f;
+      for (int z = 0; z < splits; ++z) a += bg_partial[(size_t)z * M + e];
+      bg_out[e] += a;
+    }
     if (e >= (long long)M * N) return;
     const size_t mn = (size_t)M * N;
     float acc = 0.0f;

@@ -36,6 +36,7 @@ struct EmuOps {
 #endif
   }
   bool gemm_colmax(const GemmP&, int, float*, int*, int, size_t) { return false; }  // no fused pooling here: layer + colmax
+  bool folds_bias_grad(const GemmP&) { return false; }                               // nor bias gradients inside the GEMM
   void gemm(const GemmP& p, int batch_or_splits) {
     gemm_macs += (double)p.M * p.N * p.K * (p.splits > 1 ? 1 : batch_or_splits);
     run(KGemmNaive{p}, (unsigned)((p.M + 3) / 4), (unsigned)((p.N + 63) / 64), (unsigned)batch_or_splits, 256);
