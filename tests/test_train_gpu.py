@@ -249,20 +249,22 @@ def test_train_set_weights_one_launch():
     eng.close()
 
 
-@pytest.mark.parametrize("B,N,sym", [(2, 256, None), (5, 512, None), (3, 384, [0, 0, 0]), (4, 256, [1, 1, 1, 1])],
-                         ids=["b2_n256", "b5_n512_mixed", "b3_n384_no_symmetric", "b4_n256_all_symmetric"])
+@pytest.mark.parametrize("B,N,sym", [(2, 256, None), (5, 512, None), (3, 384, [0, 0, 0]), (4, 256, [1, 1, 1, 1]), (16, 1024, None)],
+                         ids=["b2_n256", "b5_n512_mixed", "b3_n384_no_symmetric", "b4_n256_all_symmetric", "b16_n1024_bench_size"])
 def test_train_step_other_sizes_against_fp64_oracle(B, N, sym, monkeypatch):
     """Point counts other than 1024 (conv_p is tied to the point count: its first 2N weights are used), batches without any /
     with only symmetric objects (a loss term is then absent in the reference and 0 here), against the training oracle run in
     float64 at test time (seconds at these sizes) -- poses, every loss, every gradient; and the step's graph replay.
 
-    Two gradient criteria.  With the CUDA-core GEMM (fp32 FMA) every entry must be within 1e-3 of its tensor's largest entry
-    (measured 4e-5).  With the tensor-core GEMM (operands split into 16-bit pairs, ~1e-6 relative) an activation that is zero to
+    Two gradient criteria.  With the CUDA-core GEMM (fp32 FMA) every entry must be within GRAD_TOL (5e-3) of its tensor's
+    largest entry (measured 4e-5 where no arg-max near-tie flips, 1.3e-3 on one T-Net tensor at 16 x 1024 points where one does
+    -- in fp32 too).  With the tensor-core GEMM (operands split into 16-bit pairs, ~1e-6 relative) an activation that is zero to
     1e-6 can land on the other side of a ReLU, or a max-pool near-tie can pick the other point, which moves one point's
     gradient -- a rank-one change that is visible entry-wise at these small sizes (measured: one conv3 channel off by 2.7e-2
     of the tensor's largest entry at 3 x 384 points, identical with the CUDA-core GEMM to 3e-5 everywhere else;
     tools/train_case_probe.py).  The reference's own default (TF32) rounds 1000 times coarser.  So the tensor-core step is
-    held to a relative L2 error of 1e-2 per tensor (measured <= 3e-3) and to the CUDA-core step's poses and losses."""
+    held to a relative L2 error of 1e-2 per tensor (measured <= 3e-3; the CUDA-core step as well) and to the same poses and
+    losses."""
     from oracle import train_oracle as to  # checker only
 
     w32 = {k: (v[:, : 2 * N].contiguous() if k.endswith("conv_p.weight") else v) for k, v in synth.load_weights().items()}
@@ -277,7 +279,7 @@ def test_train_step_other_sizes_against_fp64_oracle(B, N, sym, monkeypatch):
     tfd_pm = ((d.prior * d.init_scale.unsqueeze(1)) @ d.init_pose[:, :, :3].transpose(1, 2)).contiguous()
     for mode in ("simt", "tc"):
         monkeypatch.setenv("CATRE_TRAIN_GEMM", mode)
-        eng = engine.Engine(N, 8, "fp32", 0)
+        eng = engine.Engine(N, max(8, B), "fp32", 0)
         eng.load_weights(w32)
         call = lambda: eng.train_step(x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, tgt.gt_pose.cuda(), tgt.gt_scale.cuda(), is_sym, rots)
         pose, scale, losses = call()
@@ -296,12 +298,11 @@ def test_train_step_other_sizes_against_fp64_oracle(B, N, sym, monkeypatch):
                 assert not bool(g.any()), name
                 continue
             want = g_ref[name].flatten()
+            rel2 = (g - want).norm().item() / max(want.norm().item(), 1e-30)
+            assert rel2 <= 1e-2, (mode, name, rel2)
             if mode == "simt":
                 rel = (g - want).abs().max().item() / max(want.abs().max().item(), 1e-12)
-                assert rel <= 1e-3, (mode, name, rel)
-            else:
-                rel2 = (g - want).norm().item() / max(want.norm().item(), 1e-30)
-                assert rel2 <= 1e-2, (mode, name, rel2)
+                assert rel <= GRAD_TOL, (mode, name, rel)
             REPORT[f"other_sizes/{mode}/B{B}_N{N}/{name}"] = float((g - want).abs().max().item() / max(want.abs().max().item(), 1e-12))
         for _ in range(2):  # graph capture, then replay: same bits as the kernel-by-kernel step
             p2, s2, l2 = call()
