@@ -715,6 +715,24 @@ struct CudaTrainOps {
   int64_t launches = 0;
   cudaError_t err = cudaSuccess;
   void note(cudaError_t st) { if (err == cudaSuccess && st != cudaSuccess) err = st; }
+  // lanes (train_chain.cuh: the ts head next to the rotation heads): a second stream between fork() and join(), ordered by two
+  // events; under stream capture the same calls become parallel branches of the graph.  CATRE_TRAIN_LANES=0: one lane.
+  cudaStream_t s_main = nullptr, s_side = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool lanes = false;
+  void fork() {
+    if (!lanes) return;
+    s_main = s;
+    note(cudaEventRecord(ev_fork, s_main));
+    note(cudaStreamWaitEvent(s_side, ev_fork, 0));
+  }
+  void lane(int i) { if (lanes) s = i ? s_side : s_main; }
+  void join() {
+    if (!lanes) return;
+    note(cudaEventRecord(ev_join, s_side));
+    note(cudaStreamWaitEvent(s_main, ev_join, 0));
+    s = s_main;
+  }
   // carve: ask for the maximum shared-memory carve-out for the small kernels too, so that the SMs do not switch their L1 /
   // shared-memory split before and after every tensor-core GEMM (193 KB of shared memory) of the chain; set once per kernel
   // instantiation and value (the attribute belongs to the function, not to the launch).  CATRE_TRAIN_CARVEOUT=0 turns it off.
@@ -1527,6 +1545,8 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   const bool carve = gemm_tc && env4 && env4[0] == '1';  // experiment (see CudaTrainOps::carve)
   const char* env5 = getenv("CATRE_TRAIN_FOLD_BIAS");
   const bool fold_bg = !(env5 && env5[0] == '0');
+  const char* env6 = getenv("CATRE_TRAIN_LANES");
+  const bool lanes = !(env6 && env6[0] == '0');
   auto make_in = [&](const float* x, const float* tfd, const float* kps, const float* po, const float* sc, const float* Kz,
                      const float* gp, const float* gs, float* op, float* os) {
     catre_train::TrainIn in{nullptr, kps, po, sc, Kz, gp, gs, B, n_sym_rots, n_sym, B - n_sym, op, os};
@@ -1538,6 +1558,8 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
     CudaTrainOps ops{st, naive_gemm, gemm_v2, gemm_tc, e->num_sms};
     ops.carve = carve;
     ops.fold_bg = fold_bg;
+    ops.lanes = lanes && e->side && e->ev_fork && e->ev_join;
+    ops.s_main = st; ops.s_side = e->side; ops.ev_fork = e->ev_fork; ops.ev_join = e->ev_join;
     catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
     chain.forward(in);
     chain.loss(in);
@@ -1549,7 +1571,7 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
   bool done = false;
   if (!(env3 && env3[0] == '0')) {
     catre_engine::TrainGraphKey key{};
-    key.B = B; key.n_sym = n_sym; key.n_rots = n_sym_rots; key.mode = (naive_gemm ? 1 : (gemm_v2 ? 2 : (gemm_tc ? 0 : 3))) + (carve ? 8 : 0) + (fold_bg ? 0 : 16);
+    key.B = B; key.n_sym = n_sym; key.n_rots = n_sym_rots; key.mode = (naive_gemm ? 1 : (gemm_v2 ? 2 : (gemm_tc ? 0 : 3))) + (carve ? 8 : 0) + (fold_bg ? 0 : 16) + (lanes ? 0 : 32);
     for (int i = 0; i < 4; ++i) key.lw[i] = e->loss_w[i];
     if (e->train_graphs.size() > 64 && !e->train_graphs.count(key)) {  // bound the cache (each graph holds ~240 nodes)
       CU_TRY(e, cudaStreamSynchronize(s));

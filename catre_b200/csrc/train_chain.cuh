@@ -48,6 +48,9 @@ struct TrainWs {
   float *lossp, *losses, *dpose, *d_r6, *d_dts, *tsd_u, *tsd_u0, *ts_din, *gn_m, *gnp_g, *gnp_b;
   float *dg, *dpfmax, *dpf, *e, *du, *du0, *dcset, *d512, *d128, *d64, *dh1, *dt64, *dfc2, *dfc1, *dmax, *dqp, *dt3;
   float *partial, *cs_partial, *loss_gs;
+  // second scratch set: the ts head runs as a side lane next to the rotation heads (Chain::forward / backward)
+  float *partial_ts, *gn_m_ts, *gnp_g_ts, *gnp_b_ts;
+  double* gn_part_ts;  // [maxB, 32, 18] (one chunk: P = 1)
   int *mb_start, *mb_cnt, *mb_list, *mb_key;  // inverse arg-max map of the sparse max-pool backward: [S, N], [S, N], [S, 1024] x 2
   double* gn_part;  // [maxB, kGnChunks, 32, 18]; also the point-matching partials of the loss [maxB, kLossChunks, 13]
   unsigned char* is_sym;
@@ -93,6 +96,8 @@ inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base, size_t gap = 0)
   F(w.dcset, S * 256); F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
   F(w.dfc2, S * 256); F(w.dfc1, S * 512); F(w.dmax, S * 1024); F(w.dqp, R * 3); F(w.dt3, S * 9);
   F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, TrainWs::kCsFloats); F(w.loss_gs, B * 9);
+  F(w.partial_ts, TrainWs::kPartialFloats); F(w.gn_m_ts, B * 64); F(w.gnp_g_ts, B * 256); F(w.gnp_b_ts, B * 256);
+  w.gn_part_ts = reinterpret_cast<double*>(take(B * 32 * 18 * sizeof(double)));
   I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024); I(w.mb_key, S * 1024);
   w.gn_part = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
   w.is_sym = reinterpret_cast<unsigned char*>(take(B));
@@ -121,6 +126,20 @@ struct Chain {
   const float* const* W;  // the 74 checkpoint tensors
   int N;
   int gemm_f16 = 0;  // operand type of the tensor-core GEMM (GemmP::f16): 1 during forward(), 0 during backward()
+  // Scratch of the lane that is being recorded.  The ts head (a dozen launches forward, thirty backward, all on B rows) is
+  // independent of the two rotation heads between the encoder and the pose update, so it is issued as a side lane (Ops::fork /
+  // lane / join: a second stream on the GPU, graph branches under capture, nothing in the emulation) with its own split-K and
+  // GroupNorm scratch; everything else it touches is its own (ts_* buffers, its weights' gradients).
+  bool ts_lane = false;
+  float* sc_partial() const { return ts_lane ? w.partial_ts : w.partial; }
+  double* sc_gn_part() const { return ts_lane ? w.gn_part_ts : w.gn_part; }
+  float* sc_gn_m() const { return ts_lane ? w.gn_m_ts : w.gn_m; }
+  float* sc_gnp_g() const { return ts_lane ? w.gnp_g_ts : w.gnp_g; }
+  float* sc_gnp_b() const { return ts_lane ? w.gnp_b_ts : w.gnp_b; }
+  // two-stage column sums use cs_partial (one buffer): the side lane only exists while every sum it issues is single-stage
+  bool lanes_ok(int B) const { return B <= 256; }
+  void begin_ts_lane() { o.fork(); o.lane(1); ts_lane = true; }
+  void end_ts_lane() { ts_lane = false; o.lane(0); }
 
   static unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
@@ -132,7 +151,7 @@ struct Chain {
     GemmP p{};
     p.A = A; p.sam = sam; p.sak = sak; p.sab = sab; p.B = Bm; p.sbk = sbk; p.sbn = sbn; p.sbb = sbb;
     p.C = C; p.scm = scm; p.scn = scn; p.scb = scb; p.bias = bias; p.sbias_b = sbias_b;
-    p.M = M; p.N = Nn; p.K = K; p.relu = relu; p.accumulate = acc; p.splits = 1; p.k_per = K; p.partial = w.partial;
+    p.M = M; p.N = Nn; p.K = K; p.relu = relu; p.accumulate = acc; p.splits = 1; p.k_per = K; p.partial = sc_partial();
     p.f16 = gemm_f16;
     if (batch == 1 && !bias && !relu && K >= 4096) {  // weight gradients: reduce over many rows -> split K
       // few output tiles (at most 128 x 128 outputs): more, shorter splits so that the launch still fills the device
@@ -143,9 +162,9 @@ struct Chain {
         p.splits = splits;
         p.k_per = ((K + splits - 1) / splits + 63) & ~63;
         const bool fold = db && (size_t)splits * M * (Nn + 1) <= TrainWs::kPartialFloats && o.folds_bias_grad(p);
-        if (fold) p.bias_grad_partial = w.partial + (size_t)splits * M * Nn;
+        if (fold) p.bias_grad_partial = sc_partial() + (size_t)splits * M * Nn;
         o.gemm(p, splits);
-        KSplitReduce red{w.partial, C, scm, scn, M, Nn, splits, acc};
+        KSplitReduce red{sc_partial(), C, scm, scn, M, Nn, splits, acc};
         if (fold) { red.bg_partial = p.bias_grad_partial; red.bg_out = db; }
         o.run(red, cdiv((long long)M * Nn, 256), 1, 1, 256);
         return fold;
@@ -242,20 +261,20 @@ struct Chain {
   }
   void gn_fwd(const float* y, float* st, const float* ga, const float* be, float* u, int B, int P) {
     const int chunks = gn_chunks(P), per = (P + chunks - 1) / chunks;
-    o.run(KGnStatsPart{y, w.gn_part, P, chunks, per}, B, chunks, 1, 32);
-    o.run(KGnStats{w.gn_part, st, P, chunks}, B, 1, 1, 32);
+    o.run(KGnStatsPart{y, sc_gn_part(), P, chunks, per}, B, chunks, 1, 32);
+    o.run(KGnStats{sc_gn_part(), st, P, chunks}, B, 1, 1, 32);
     const long long n = (long long)B * P * 256;
     o.run(KGnGeluFwd{y, st, ga, be, u, P, n}, cdiv(n / 4, 256), 1, 1, 256);
   }
   // du -> dy in place; gamma / beta gradients accumulated into G[gi], G[gi + 1]
   void gn_bwd(float* du, const float* y, const float* st, int gi, int B, int P) {
     const int chunks = gn_chunks(P), per = (P + chunks - 1) / chunks;
-    o.run(KGnBwdPart{du, y, st, W[gi], W[gi + 1], w.gn_part, P, chunks, per}, B, chunks, 1, 32);
-    o.run(KGnBwdSums{w.gn_part, w.gn_m, w.gnp_g, w.gnp_b, P, chunks}, B, 1, 1, 32 * 18);
-    colsum(w.gnp_g, B, 256, 256, w.G[gi], 1);
-    colsum(w.gnp_b, B, 256, 256, w.G[gi + 1], 1);
+    o.run(KGnBwdPart{du, y, st, W[gi], W[gi + 1], sc_gn_part(), P, chunks, per}, B, chunks, 1, 32);
+    o.run(KGnBwdSums{sc_gn_part(), sc_gn_m(), sc_gnp_g(), sc_gnp_b(), P, chunks}, B, 1, 1, 32 * 18);
+    colsum(sc_gnp_g(), B, 256, 256, w.G[gi], 1);
+    colsum(sc_gnp_b(), B, 256, 256, w.G[gi + 1], 1);
     const long long n = (long long)B * P * 256;
-    o.run(KGnBwdApply{du, y, st, W[gi], W[gi + 1], w.gn_m, P, n}, cdiv(n / 4, 256), 1, 1, 256);
+    o.run(KGnBwdApply{du, y, st, W[gi], W[gi + 1], sc_gn_m(), P, n}, cdiv(n / 4, 256), 1, 1, 256);
   }
 
   // T-Net forward (pointnets/pointnet.py:24-41, 57-78)
@@ -302,7 +321,9 @@ struct Chain {
     layer(w.a128, 128, W_CONV3, 512, w.a512, R, 1);
     layer_max(w.a512, 512, W_CONV4, 1024, w.g, w.garg, S, 0);  // no ReLU after conv4 (pointnet.py:114)
     colmax(w.pf, w.pfmax, w.pfarg, S, 64);
-    // translation / size head (heads/fc_trans_size_head.py:61-70)
+    // translation / size head (heads/fc_trans_size_head.py:61-70): a side lane next to the rotation heads
+    const bool lanes = lanes_ok(B);
+    if (lanes) begin_ts_lane();
     o.run(KTsGather{w.g, w.pfmax, in.scale, w.ts_in}, cdiv(1091, 256), B, 1, 256);
     layer(w.ts_in, 1091, W_TS + S_L0, 256, w.ts_y0, B, 0);
     gn_fwd(w.ts_y0, w.ts_st0, W[W_TS + S_GN0], W[W_TS + S_GN0 + 1], w.ts_u0, B, 1);
@@ -310,6 +331,7 @@ struct Chain {
     gn_fwd(w.ts_y1, w.ts_st1, W[W_TS + S_GN1], W[W_TS + S_GN1 + 1], w.ts_u1, B, 1);
     gemm(w.ts_u1, 256, 1, W[W_TS + S_FCT], 1, 256, w.dts, 6, 1, B, 3, 256, W[W_TS + S_FCT + 1], 0, 0);
     gemm(w.ts_u1, 256, 1, W[W_TS + S_FCS], 1, 256, w.dts + 3, 6, 1, B, 3, 256, W[W_TS + S_FCS + 1], 0, 0);
+    if (lanes) end_ts_lane();
     // rotation heads (heads/conv_out_per_rot_head.py:126-140) with the layer-0 split
     for (int h = 0; h < 2; ++h) {
       const int rb = h ? W_ROT_Y : W_ROT_X;
@@ -323,6 +345,7 @@ struct Chain {
       colsum(W[rb + R_CONVP], P, 1, 1, w.swp + h, 0);  // sum_p wp[p], also read by the backward of this step
       o.run(KRotOut{w.wsum[h], W[rb + R_NECK], W[rb + R_NECK + 1], w.swp, W[rb + R_CONVP + 1], w.r6, P, h}, B, 1, 1, 32);
     }
+    if (lanes) o.join();
     o.run(KPoseFwd{w.r6, w.dts, in.pose, in.scale, in.K, in.pose_out, in.scale_out, B}, cdiv(B, 64), 1, 1, 64);
   }
 
@@ -354,14 +377,16 @@ struct Chain {
     o.zero(w.dpfmax, (size_t)S * 64 * sizeof(float));
     o.zero(w.dpf, (size_t)R * 64 * sizeof(float));
     o.run(KPoseBwd{w.dpose, w.r6, w.dts, in.pose, in.K, w.d_r6, w.d_dts, B}, cdiv(B, 64), 1, 1, 64);
-    // ---- ts head
+    // ---- ts head: side lane next to the rotation heads; its gradient w.r.t. the global feature is added after the join
+    const bool lanes = lanes_ok(B);
+    if (lanes) begin_ts_lane();
     lin_bwd(W_TS + S_FCT, w.ts_u1, 256, w.d_dts, 3, 6, B, w.tsd_u, 0);
     lin_bwd(W_TS + S_FCS, w.ts_u1, 256, w.d_dts + 3, 3, 6, B, w.tsd_u, 1);
     gn_bwd(w.tsd_u, w.ts_y1, w.ts_st1, W_TS + S_GN1, B, 1);
     lin_bwd(W_TS + S_L3, w.ts_u0, 256, w.tsd_u, 256, 256, B, w.tsd_u0, 0);
     gn_bwd(w.tsd_u0, w.ts_y0, w.ts_st0, W_TS + S_GN0, B, 1);
     lin_bwd(W_TS + S_L0, w.ts_in, 1091, w.tsd_u0, 256, 256, B, w.ts_din, 0);
-    o.run(KTsScatter{w.ts_din, w.dg, w.dpfmax}, cdiv(1088, 256), B, 1, 256);
+    if (lanes) end_ts_lane();
     // ---- rotation heads
     for (int h = 0; h < 2; ++h) {
       const int rb = h ? W_ROT_Y : W_ROT_X;
@@ -389,6 +414,8 @@ struct Chain {
       gemm(w.du0, 256, 1, W[rb + R_L0] + 1024, 1088, 1, w.dpf, 64, 1, (int)R, 64, 256, nullptr, 0, 1);
     }
     // ---- encoder
+    if (lanes) o.join();
+    o.run(KTsScatter{w.ts_din, w.dg, w.dpfmax}, cdiv(1088, 256), B, 1, 256);  // += on top of the rotation heads' share
     o.run(KScatterMax{w.dpfmax, w.pfarg, w.dpf, N, 64}, 1, S, 1, 64);
     max_bwd_dx(w.dg, nullptr, W[W_CONV4], w.garg, w.d512, S, 1024, 512, w.a512);  // incl. the ReLU mask of conv3's output
     o.run(KMaxBwdDw{w.dg, nullptr, w.a512, w.garg, w.G[W_CONV4], w.G[W_CONV4 + 1], S, N, 1024, 512}, cdiv(512, 128), 1024, 1, 128);

@@ -717,16 +717,16 @@ struct KTsGather {
     ts_in[(size_t)b * 1091 + c] = v;
   }
 };
-// dg[2b, :] = din[b, :1024], dpfmax[2b, :] = din[b, 1024:1088] (the prior sets' rows stay zero; the initial scale is
-// detached).  grid (ceil(1088 / nt), B)
+// dg[2b, :] += din[b, :1024], dpfmax[2b, :] += din[b, 1024:1088] (both zeroed at the start of the backward; dg already holds the
+// rotation heads' share; the prior sets' rows get nothing; the initial scale is detached).  grid (ceil(1088 / nt), B)
 struct KTsScatter {
   const float* din; float *dg, *dpfmax;
   TK_HD void operator()(const Idx& i) const {
     const int c = i.bx * i.nt + i.tx, b = i.by;
     if (c >= 1088) return;
     const float v = din[(size_t)b * 1091 + c];
-    if (c < 1024) dg[(size_t)(2 * b) * 1024 + c] = v;
-    else dpfmax[(size_t)(2 * b) * 64 + (c - 1024)] = v;
+    if (c < 1024) dg[(size_t)(2 * b) * 1024 + c] += v;
+    else dpfmax[(size_t)(2 * b) * 64 + (c - 1024)] += v;
   }
 };
 

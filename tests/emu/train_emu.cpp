@@ -36,6 +36,9 @@ struct EmuOps {
 #endif
   }
   bool gemm_colmax(const GemmP&, int, float*, int*, int, size_t) { return false; }  // no fused pooling here: layer + colmax
+  void fork() {}  // lanes are an execution detail of the GPU launcher: here everything runs in program order
+  void lane(int) {}
+  void join() {}
   bool folds_bias_grad(const GemmP&) { return false; }                               // nor bias gradients inside the GEMM
   void gemm(const GemmP& p, int batch_or_splits) {
     gemm_macs += (double)p.M * p.N * p.K * (p.splits > 1 ? 1 : batch_or_splits);
@@ -85,6 +88,8 @@ extern "C" int emu_train_step(const float* const* weights, int B, int N, const f
     F(w.dcset, S * 256); F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
     F(w.dfc2, S * 256); F(w.dfc1, S * 512); F(w.dmax, S * 1024); F(w.dqp, R * 3); F(w.dt3, S * 9);
     F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, TrainWs::kCsFloats); F(w.loss_gs, Bz * 9);
+    F(w.partial_ts, TrainWs::kPartialFloats); F(w.gn_m_ts, Bz * 64); F(w.gnp_g_ts, Bz * 256); F(w.gnp_b_ts, Bz * 256);
+    sl.push_back({reinterpret_cast<char*>(w.gn_part_ts), Bz * 32 * 18 * sizeof(double)});
     I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024); I(w.mb_key, S * 1024);
     sl.push_back({reinterpret_cast<char*>(w.gn_part), Bz * TrainWs::kGnChunks * 32 * 18 * sizeof(double)});
     sl.push_back({reinterpret_cast<char*>(w.is_sym), Bz});

@@ -25,7 +25,8 @@ def main():
         modes = os.environ.get("TRAIN_PROBE_MODES", "tc,tc-nograph,simt").split(",")
         for mode in modes:  # tc (default: tcgen05 GEMM for the large shapes), simt (64 x 64 CUDA-core tiles), v2, naive;
             # a "-nograph" suffix launches the chain kernel by kernel (CATRE_TRAIN_GRAPH=0) instead of replaying its CUDA graph
-            ver = mode.replace("-nograph", "").replace("-carve", "").replace("-nofold", "")
+            ver = mode.replace("-nograph", "").replace("-carve", "").replace("-nofold", "").replace("-nolanes", "")
+            os.environ["CATRE_TRAIN_LANES"] = "0" if "-nolanes" in mode else "1"
             os.environ["CATRE_TRAIN_FOLD_BIAS"] = "0" if "-nofold" in mode else "1"
             os.environ["CATRE_TRAIN_CARVEOUT"] = "1" if "-carve" in mode else "0"
             naive = "1" if ver == "naive" else "0"
@@ -45,7 +46,7 @@ def main():
                 step()
             b.record()
             torch.cuda.synchronize()
-            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": ver, "cuda_graph": "-nograph" not in mode, "max_shared_carveout": "-carve" in mode, "bias_grad_in_gemm": "-nofold" not in mode,
+            print(json.dumps({"probe": "train_step", "B": B, "N": 1024, "gemm": ver, "cuda_graph": "-nograph" not in mode, "max_shared_carveout": "-carve" in mode, "bias_grad_in_gemm": "-nofold" not in mode, "ts_head_lane": "-nolanes" not in mode,
                               "ms_per_step": a.elapsed_time(b) / n, "launches": eng.last_launch_count(),
                               "objects_per_s": B / (a.elapsed_time(b) / n / 1e3)}), flush=True)
             eng.close()
