@@ -43,14 +43,15 @@ struct TrainWs {
       *pfmax;
   int *sarg, *farg, *garg, *pfarg;
   float *ts_in, *ts_y0, *ts_u0, *ts_y1, *ts_u1, *ts_st0, *ts_st1, *dts;
-  float *cset[2], *ry0[2], *ru0[2], *ry1[2], *rst0[2], *rst1[2], *wsum[2], *ru1, *r6, *swp;
+  float *cset[2], *ry0[2], *ru0[2], *ry1[2], *rst0[2], *rst1[2], *wsum[2], *ru1[2], *r6, *swp;
   // loss / backward
   float *lossp, *losses, *dpose, *d_r6, *d_dts, *tsd_u, *tsd_u0, *ts_din, *gn_m, *gnp_g, *gnp_b;
-  float *dg, *dpfmax, *dpf, *e, *du, *du0, *dcset, *d512, *d128, *d64, *dh1, *dt64, *dfc2, *dfc1, *dmax, *dqp, *dt3;
+  float *dg, *dpfmax, *dpf, *e[2], *du[2], *du0[2], *dcset[2], *d512, *d128, *d64, *dh1, *dt64, *dfc2, *dfc1, *dmax, *dqp, *dt3;
   float *partial, *cs_partial, *loss_gs;
-  // second scratch set: the ts head runs as a side lane next to the rotation heads (Chain::forward / backward)
-  float *partial_ts, *gn_m_ts, *gnp_g_ts, *gnp_b_ts;
-  double* gn_part_ts;  // [maxB, 32, 18] (one chunk: P = 1)
+  // second scratch set: the ts head and the y rotation head run as a side lane next to the x rotation head (Chain::forward /
+  // backward); the per-head buffers above ([2]) exist for the same reason
+  float *partial_ts, *cs_partial_ts, *gn_m_ts, *gnp_g_ts, *gnp_b_ts;
+  double* gn_part_ts;
   int *mb_start, *mb_cnt, *mb_list, *mb_key;  // inverse arg-max map of the sparse max-pool backward: [S, N], [S, N], [S, 1024] x 2
   double* gn_part;  // [maxB, kGnChunks, 32, 18]; also the point-matching partials of the loss [maxB, kLossChunks, 13]
   unsigned char* is_sym;
@@ -87,17 +88,19 @@ inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base, size_t gap = 0)
   F(w.ts_st0, B * 64); F(w.ts_st1, B * 64); F(w.dts, B * 6);
   for (int h = 0; h < 2; ++h) {
     F(w.cset[h], S * 256); F(w.ry0[h], R * 256); F(w.ru0[h], R * 256); F(w.ry1[h], R * 256); F(w.rst0[h], B * 64);
-    F(w.rst1[h], B * 64); F(w.wsum[h], B * 256);
+    F(w.rst1[h], B * 64); F(w.wsum[h], B * 256); F(w.ru1[h], R * 256);
   }
-  F(w.ru1, R * 256); F(w.r6, B * 6); F(w.swp, 2);
+  F(w.r6, B * 6); F(w.swp, 2);
   F(w.lossp, B * 6); F(w.losses, 8); F(w.dpose, B * 15); F(w.d_r6, B * 6); F(w.d_dts, B * 6); F(w.tsd_u, B * 256);
   F(w.tsd_u0, B * 256); F(w.ts_din, B * 1091); F(w.gn_m, B * 64); F(w.gnp_g, B * 256); F(w.gnp_b, B * 256);
-  F(w.dg, S * 1024); F(w.dpfmax, S * 64); F(w.dpf, R * 64); F(w.e, B * 256); F(w.du, R * 256); F(w.du0, R * 256);
-  F(w.dcset, S * 256); F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
+  F(w.dg, S * 1024); F(w.dpfmax, S * 64); F(w.dpf, R * 64);
+  for (int h = 0; h < 2; ++h) { F(w.e[h], B * 256); F(w.du[h], R * 256); F(w.du0[h], R * 256); F(w.dcset[h], S * 256); }
+  F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
   F(w.dfc2, S * 256); F(w.dfc1, S * 512); F(w.dmax, S * 1024); F(w.dqp, R * 3); F(w.dt3, S * 9);
   F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, TrainWs::kCsFloats); F(w.loss_gs, B * 9);
-  F(w.partial_ts, TrainWs::kPartialFloats); F(w.gn_m_ts, B * 64); F(w.gnp_g_ts, B * 256); F(w.gnp_b_ts, B * 256);
-  w.gn_part_ts = reinterpret_cast<double*>(take(B * 32 * 18 * sizeof(double)));
+  F(w.partial_ts, TrainWs::kPartialFloats); F(w.cs_partial_ts, TrainWs::kCsFloats); F(w.gn_m_ts, B * 64); F(w.gnp_g_ts, B * 256);
+  F(w.gnp_b_ts, B * 256);
+  w.gn_part_ts = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
   I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024); I(w.mb_key, S * 1024);
   w.gn_part = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
   w.is_sym = reinterpret_cast<unsigned char*>(take(B));
@@ -126,20 +129,22 @@ struct Chain {
   const float* const* W;  // the 74 checkpoint tensors
   int N;
   int gemm_f16 = 0;  // operand type of the tensor-core GEMM (GemmP::f16): 1 during forward(), 0 during backward()
-  // Scratch of the lane that is being recorded.  The ts head (a dozen launches forward, thirty backward, all on B rows) is
-  // independent of the two rotation heads between the encoder and the pose update, so it is issued as a side lane (Ops::fork /
-  // lane / join: a second stream on the GPU, graph branches under capture, nothing in the emulation) with its own split-K and
-  // GroupNorm scratch; everything else it touches is its own (ts_* buffers, its weights' gradients).
-  bool ts_lane = false;
-  float* sc_partial() const { return ts_lane ? w.partial_ts : w.partial; }
-  double* sc_gn_part() const { return ts_lane ? w.gn_part_ts : w.gn_part; }
-  float* sc_gn_m() const { return ts_lane ? w.gn_m_ts : w.gn_m; }
-  float* sc_gnp_g() const { return ts_lane ? w.gnp_g_ts : w.gnp_g; }
-  float* sc_gnp_b() const { return ts_lane ? w.gnp_b_ts : w.gnp_b; }
-  // two-stage column sums use cs_partial (one buffer): the side lane only exists while every sum it issues is single-stage
-  bool lanes_ok(int B) const { return B <= 256; }
-  void begin_ts_lane() { o.fork(); o.lane(1); ts_lane = true; }
-  void end_ts_lane() { ts_lane = false; o.lane(0); }
+  // Scratch of the lane that is being recorded.  Between the encoder and the pose update the ts head and the two rotation heads
+  // are independent of each other; most of their launches are a few microseconds long (GroupNorm merges, column sums, the
+  // tail), so the ts head and the y head are issued as a SIDE lane next to the x head (Ops::fork / lane / join: a second stream
+  // on the GPU, parallel graph branches under capture, plain program order in the emulation).  The side lane has its own
+  // split-K / column-sum / GroupNorm scratch and the heads have their own activation and gradient buffers; the two products
+  // with which a head adds to the SHARED gradients (dg, dpf) are issued after the join for the y head, so the accumulation
+  // order -- x, y, ts -- and with it every bit of the result is the same with one lane or two.
+  bool side = false;
+  float* sc_partial() const { return side ? w.partial_ts : w.partial; }
+  float* sc_cs_partial() const { return side ? w.cs_partial_ts : w.cs_partial; }
+  double* sc_gn_part() const { return side ? w.gn_part_ts : w.gn_part; }
+  float* sc_gn_m() const { return side ? w.gn_m_ts : w.gn_m; }
+  float* sc_gnp_g() const { return side ? w.gnp_g_ts : w.gnp_g; }
+  float* sc_gnp_b() const { return side ? w.gnp_b_ts : w.gnp_b; }
+  void begin_side() { o.fork(); o.lane(1); side = true; }
+  void end_side() { side = false; o.lane(0); }
 
   static unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
@@ -193,8 +198,8 @@ struct Chain {
       while (chunks > 1 && (size_t)chunks * C > TrainWs::kCsFloats) chunks >>= 1;
       const long long per = (rows + chunks - 1) / chunks;
       chunks = (rows + per - 1) / per;
-      o.run(KColSum{d, w.cs_partial, rows, C, per, 0, ld}, cdiv(C, 256), (unsigned)chunks, 1, 256);
-      o.run(KColSum{w.cs_partial, out, chunks, C, chunks, acc, C}, cdiv(C, 256), 1, 1, 256);
+      o.run(KColSum{d, sc_cs_partial(), rows, C, per, 0, ld}, cdiv(C, 256), (unsigned)chunks, 1, 256);
+      o.run(KColSum{sc_cs_partial(), out, chunks, C, chunks, acc, C}, cdiv(C, 256), 1, 1, 256);
     } else {
       o.run(KColSum{d, out, rows, C, rows, acc, ld}, cdiv(C, 256), 1, 1, 256);
     }
@@ -207,8 +212,8 @@ struct Chain {
       o.run(KColSum{d, out, (long long)groups * per_group, C, per_group, 0, C}, cdiv(C, 256), groups, 1, 256);
       return;
     }
-    o.run(KColSum{d, w.cs_partial, (long long)groups * per_group, C, per_group / sub, 0, C}, cdiv(C, 256), groups * sub, 1, 256);
-    o.run(KColSum{w.cs_partial, out, (long long)groups * sub, C, sub, 0, C}, cdiv(C, 256), groups, 1, 256);
+    o.run(KColSum{d, sc_cs_partial(), (long long)groups * per_group, C, per_group / sub, 0, C}, cdiv(C, 256), groups * sub, 1, 256);
+    o.run(KColSum{sc_cs_partial(), out, (long long)groups * sub, C, sub, 0, C}, cdiv(C, 256), groups, 1, 256);
   }
   // column max + arg-max over the N points of each of S sets (first index wins ties), two stages when the scratch allows
   void colmax(const float* z, float* vmax, int* arg, int S, int C) {
@@ -250,8 +255,8 @@ struct Chain {
     int chunks = 32;
     while (chunks > 1 && ((size_t)B * chunks * 256 > TrainWs::kCsFloats || P % chunks != 0)) chunks >>= 1;
     if (chunks == 1) { o.run(KRotWsum{u1, wp, wsum, P}, B, 1, 1, 256); return; }
-    o.run(KRotWsumPart{u1, wp, w.cs_partial, P, P / chunks}, 1, chunks, B, 256);
-    o.run(KColSum{w.cs_partial, wsum, (long long)B * chunks, 256, chunks, 0, 256}, 1, B, 1, 256);
+    o.run(KRotWsumPart{u1, wp, sc_cs_partial(), P, P / chunks}, 1, chunks, B, 256);
+    o.run(KColSum{sc_cs_partial(), wsum, (long long)B * chunks, 256, chunks, 0, 256}, 1, B, 1, 256);
   }
   void relu_mask(float* d, const float* act, long long n) { o.run(KReluMask{d, act, n}, cdiv(n, 256), 1, 1, 256); }
   static int gn_chunks(int P) {  // at least 4 points per chunk
@@ -305,6 +310,56 @@ struct Chain {
     lin_bwd(wb + T_CONV1, x, Kin, w.d64, 64, 64, R, dx_out, 1);
   }
 
+  // one rotation head (heads/conv_out_per_rot_head.py:126-140) with the layer-0 split; h = 0: x, 1: y
+  void rot_fwd(int h, int B) {
+    const int S = 2 * B, P = 2 * N;
+    const long long R = (long long)S * N;
+    const int rb = h ? W_ROT_Y : W_ROT_X;
+    gemm(w.g, 1024, 1, W[rb + R_L0], 1, 1088, w.cset[h], 256, 1, S, 256, 1024, W[rb + R_L0 + 1], 0, 0);
+    gemm(w.pf, 64, 1, W[rb + R_L0] + 1024, 1, 1088, w.ry0[h], 256, 1, N, 256, 64, w.cset[h], 0, 0, S, (long long)N * 64, 0,
+         (long long)N * 256, 256);
+    gn_fwd(w.ry0[h], w.rst0[h], W[rb + R_GN0], W[rb + R_GN0 + 1], w.ru0[h], B, P);
+    layer(w.ru0[h], 256, rb + R_L3, 256, w.ry1[h], R, 0);
+    gn_fwd(w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1[h], B, P);
+    rot_wsum(w.ru1[h], W[rb + R_CONVP], w.wsum[h], B, P);
+    colsum(W[rb + R_CONVP], P, 1, 1, w.swp + h, 0);  // sum_p wp[p], also read by the backward of this step
+    o.run(KRotOut{w.wsum[h], W[rb + R_NECK], W[rb + R_NECK + 1], w.swp, W[rb + R_CONVP + 1], w.r6, P, h}, B, 1, 1, 32);
+  }
+  // backward of one rotation head down to its own weights' gradients and to du0 / dcset (the gradients at the layer-0 output,
+  // per point and summed per set); what it adds to the shared dg / dpf is rot_bwd_shared
+  void rot_bwd(int h, int B) {
+    const int S = 2 * B, P = 2 * N;
+    const long long R = (long long)S * N;
+    const int rb = h ? W_ROT_Y : W_ROT_X;
+    const float* wp = W[rb + R_CONVP];
+    o.run(KRotTailBwd{w.d_r6, w.wsum[h], W[rb + R_NECK], w.swp, w.e[h], w.G[rb + R_NECK], w.G[rb + R_NECK + 1], w.G[rb + R_CONVP + 1], B, P, h},
+          1, 1, 1, 256);
+    const long long n = (long long)B * P * 256;
+    o.run(KGnGeluFwd{w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1[h], P, n}, cdiv(n / 4, 256), 1, 1, 256);  // recompute u1
+    if ((size_t)B * P * 8 <= TrainWs::kPartialFloats) {
+      o.run(KRotDwpPart{w.ru1[h], w.e[h], sc_partial(), P}, cdiv(8 * P, 256), B, 1, 256);
+      o.run(KRotDwpSum{sc_partial(), w.d_r6, W[rb + R_NECK + 1], w.G[rb + R_CONVP], B, P, h}, cdiv(P, 128), 1, 1, 128);
+    } else {
+      o.run(KRotDwp{w.ru1[h], w.e[h], w.d_r6, W[rb + R_NECK + 1], w.G[rb + R_CONVP], B, P, h}, cdiv(P, 128), 1, 1, 128);
+    }
+    o.run(KRotDu1{wp, w.e[h], w.du[h], P, n}, cdiv(n, 256), 1, 1, 256);
+    gn_bwd(w.du[h], w.ry1[h], w.rst1[h], rb + R_GN1, B, P);
+    lin_bwd(rb + R_L3, w.ru0[h], 256, w.du[h], 256, 256, R, w.du0[h], 0);
+    gn_bwd(w.du0[h], w.ry0[h], w.rst0[h], rb + R_GN0, B, P);
+    // layer 0: point-feature columns per point, global-feature columns once per set
+    group_colsum(w.du0[h], S, N, 256, w.dcset[h]);  // dcset[s] = sum over the set's points
+    gemm(w.dcset[h], 1, 256, w.g, 1024, 1, w.G[rb + R_L0], 1088, 1, 256, 1024, S, nullptr, 0, 1);
+    gemm(w.du0[h], 1, 256, w.pf, 64, 1, w.G[rb + R_L0] + 1024, 1088, 1, 256, 64, (int)R, nullptr, 0, 1);
+    colsum(w.dcset[h], S, 256, 256, w.G[rb + R_L0 + 1], 1);
+  }
+  void rot_bwd_shared(int h, int B) {
+    const int S = 2 * B;
+    const long long R = (long long)S * N;
+    const int rb = h ? W_ROT_Y : W_ROT_X;
+    gemm(w.dcset[h], 256, 1, W[rb + R_L0], 1088, 1, w.dg, 1024, 1, S, 1024, 256, nullptr, 0, 1);
+    gemm(w.du0[h], 256, 1, W[rb + R_L0] + 1024, 1088, 1, w.dpf, 64, 1, (int)R, 64, 256, nullptr, 0, 1);
+  }
+
   void forward(const TrainIn& in) {
     const int B = in.B, S = 2 * B, P = 2 * N;
     const long long R = (long long)S * N;
@@ -321,9 +376,8 @@ struct Chain {
     layer(w.a128, 128, W_CONV3, 512, w.a512, R, 1);
     layer_max(w.a512, 512, W_CONV4, 1024, w.g, w.garg, S, 0);  // no ReLU after conv4 (pointnet.py:114)
     colmax(w.pf, w.pfmax, w.pfarg, S, 64);
-    // translation / size head (heads/fc_trans_size_head.py:61-70): a side lane next to the rotation heads
-    const bool lanes = lanes_ok(B);
-    if (lanes) begin_ts_lane();
+    // translation / size head (heads/fc_trans_size_head.py:61-70) and the y rotation head: the side lane
+    begin_side();
     o.run(KTsGather{w.g, w.pfmax, in.scale, w.ts_in}, cdiv(1091, 256), B, 1, 256);
     layer(w.ts_in, 1091, W_TS + S_L0, 256, w.ts_y0, B, 0);
     gn_fwd(w.ts_y0, w.ts_st0, W[W_TS + S_GN0], W[W_TS + S_GN0 + 1], w.ts_u0, B, 1);
@@ -331,21 +385,10 @@ struct Chain {
     gn_fwd(w.ts_y1, w.ts_st1, W[W_TS + S_GN1], W[W_TS + S_GN1 + 1], w.ts_u1, B, 1);
     gemm(w.ts_u1, 256, 1, W[W_TS + S_FCT], 1, 256, w.dts, 6, 1, B, 3, 256, W[W_TS + S_FCT + 1], 0, 0);
     gemm(w.ts_u1, 256, 1, W[W_TS + S_FCS], 1, 256, w.dts + 3, 6, 1, B, 3, 256, W[W_TS + S_FCS + 1], 0, 0);
-    if (lanes) end_ts_lane();
-    // rotation heads (heads/conv_out_per_rot_head.py:126-140) with the layer-0 split
-    for (int h = 0; h < 2; ++h) {
-      const int rb = h ? W_ROT_Y : W_ROT_X;
-      gemm(w.g, 1024, 1, W[rb + R_L0], 1, 1088, w.cset[h], 256, 1, S, 256, 1024, W[rb + R_L0 + 1], 0, 0);
-      gemm(w.pf, 64, 1, W[rb + R_L0] + 1024, 1, 1088, w.ry0[h], 256, 1, N, 256, 64, w.cset[h], 0, 0, S, (long long)N * 64, 0,
-           (long long)N * 256, 256);
-      gn_fwd(w.ry0[h], w.rst0[h], W[rb + R_GN0], W[rb + R_GN0 + 1], w.ru0[h], B, P);
-      layer(w.ru0[h], 256, rb + R_L3, 256, w.ry1[h], R, 0);
-      gn_fwd(w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1, B, P);
-      rot_wsum(w.ru1, W[rb + R_CONVP], w.wsum[h], B, P);
-      colsum(W[rb + R_CONVP], P, 1, 1, w.swp + h, 0);  // sum_p wp[p], also read by the backward of this step
-      o.run(KRotOut{w.wsum[h], W[rb + R_NECK], W[rb + R_NECK + 1], w.swp, W[rb + R_CONVP + 1], w.r6, P, h}, B, 1, 1, 32);
-    }
-    if (lanes) o.join();
+    rot_fwd(1, B);
+    end_side();
+    rot_fwd(0, B);
+    o.join();
     o.run(KPoseFwd{w.r6, w.dts, in.pose, in.scale, in.K, in.pose_out, in.scale_out, B}, cdiv(B, 64), 1, 1, 64);
   }
 
@@ -377,44 +420,22 @@ struct Chain {
     o.zero(w.dpfmax, (size_t)S * 64 * sizeof(float));
     o.zero(w.dpf, (size_t)R * 64 * sizeof(float));
     o.run(KPoseBwd{w.dpose, w.r6, w.dts, in.pose, in.K, w.d_r6, w.d_dts, B}, cdiv(B, 64), 1, 1, 64);
-    // ---- ts head: side lane next to the rotation heads; its gradient w.r.t. the global feature is added after the join
-    const bool lanes = lanes_ok(B);
-    if (lanes) begin_ts_lane();
+    // ---- side lane: the ts head (its gradient w.r.t. the global feature is added after the join) and the y rotation head
+    begin_side();
     lin_bwd(W_TS + S_FCT, w.ts_u1, 256, w.d_dts, 3, 6, B, w.tsd_u, 0);
     lin_bwd(W_TS + S_FCS, w.ts_u1, 256, w.d_dts + 3, 3, 6, B, w.tsd_u, 1);
     gn_bwd(w.tsd_u, w.ts_y1, w.ts_st1, W_TS + S_GN1, B, 1);
     lin_bwd(W_TS + S_L3, w.ts_u0, 256, w.tsd_u, 256, 256, B, w.tsd_u0, 0);
     gn_bwd(w.tsd_u0, w.ts_y0, w.ts_st0, W_TS + S_GN0, B, 1);
     lin_bwd(W_TS + S_L0, w.ts_in, 1091, w.tsd_u0, 256, 256, B, w.ts_din, 0);
-    if (lanes) end_ts_lane();
-    // ---- rotation heads
-    for (int h = 0; h < 2; ++h) {
-      const int rb = h ? W_ROT_Y : W_ROT_X;
-      const float* wp = W[rb + R_CONVP];
-      o.run(KRotTailBwd{w.d_r6, w.wsum[h], W[rb + R_NECK], w.swp, w.e, w.G[rb + R_NECK], w.G[rb + R_NECK + 1], w.G[rb + R_CONVP + 1], B, P, h},
-            1, 1, 1, 256);
-      const long long n = (long long)B * P * 256;
-      o.run(KGnGeluFwd{w.ry1[h], w.rst1[h], W[rb + R_GN1], W[rb + R_GN1 + 1], w.ru1, P, n}, cdiv(n / 4, 256), 1, 1, 256);  // recompute u1
-      if ((size_t)B * P * 8 <= TrainWs::kPartialFloats) {
-        o.run(KRotDwpPart{w.ru1, w.e, w.partial, P}, cdiv(8 * P, 256), B, 1, 256);
-        o.run(KRotDwpSum{w.partial, w.d_r6, W[rb + R_NECK + 1], w.G[rb + R_CONVP], B, P, h}, cdiv(P, 128), 1, 1, 128);
-      } else {
-        o.run(KRotDwp{w.ru1, w.e, w.d_r6, W[rb + R_NECK + 1], w.G[rb + R_CONVP], B, P, h}, cdiv(P, 128), 1, 1, 128);
-      }
-      o.run(KRotDu1{wp, w.e, w.du, P, n}, cdiv(n, 256), 1, 1, 256);
-      gn_bwd(w.du, w.ry1[h], w.rst1[h], rb + R_GN1, B, P);
-      lin_bwd(rb + R_L3, w.ru0[h], 256, w.du, 256, 256, R, w.du0, 0);
-      gn_bwd(w.du0, w.ry0[h], w.rst0[h], rb + R_GN0, B, P);
-      // layer 0: point-feature columns per point, global-feature columns once per set
-      group_colsum(w.du0, S, N, 256, w.dcset);  // dcset[s] = sum over the set's points
-      gemm(w.dcset, 1, 256, w.g, 1024, 1, w.G[rb + R_L0], 1088, 1, 256, 1024, S, nullptr, 0, 1);
-      gemm(w.du0, 1, 256, w.pf, 64, 1, w.G[rb + R_L0] + 1024, 1088, 1, 256, 64, (int)R, nullptr, 0, 1);
-      colsum(w.dcset, S, 256, 256, w.G[rb + R_L0 + 1], 1);
-      gemm(w.dcset, 256, 1, W[rb + R_L0], 1088, 1, w.dg, 1024, 1, S, 1024, 256, nullptr, 0, 1);
-      gemm(w.du0, 256, 1, W[rb + R_L0] + 1024, 1088, 1, w.dpf, 64, 1, (int)R, 64, 256, nullptr, 0, 1);
-    }
+    rot_bwd(1, B);
+    end_side();
+    // ---- main lane: the x rotation head, then (after the join) the shared-gradient products of both heads in the order x, y
+    rot_bwd(0, B);
+    rot_bwd_shared(0, B);
+    o.join();
+    rot_bwd_shared(1, B);
     // ---- encoder
-    if (lanes) o.join();
     o.run(KTsScatter{w.ts_din, w.dg, w.dpfmax}, cdiv(1088, 256), B, 1, 256);  // += on top of the rotation heads' share
     o.run(KScatterMax{w.dpfmax, w.pfarg, w.dpf, N, 64}, 1, S, 1, 64);
     max_bwd_dx(w.dg, nullptr, W[W_CONV4], w.garg, w.d512, S, 1024, 512, w.a512);  // incl. the ReLU mask of conv3's output

@@ -235,7 +235,7 @@ int catre_match_greedy(int32_t mode, const int32_t* sub_pred_off, const int32_t*
  *   out_losses [6] device = (loss_PM_R, loss_rot, loss_yaxis_rot, loss_trans_xy, loss_trans_z, loss_scale); the
  *                            reference omits loss_rot / loss_yaxis_rot from its dict when no object is asymmetric /
  *                            symmetric -- here they are 0.
- *   The workspace (about 43 MB per object at 1024 + 1024 points, i.e. 21 KB per point) is allocated on the first call and grown when B grows.
+ *   The workspace (about 50 MB per object at 1024 + 1024 points plus 50 MB of fixed scratch, i.e. 25 KB per point) is allocated on the first call and grown when B grows.
  * catre_train_grad: copy d(sum of losses)/d(tensor `name`) of the last catre_train_step to dst (device or host,
  *   stream-ordered); tensors the shipped config never uses (the heads' `norm`) have zero gradients.
  * catre_train_set_loss_weights: LOSS_CFG.PM_LW, ROT_LW (rotation and y-axis terms), TRANS_LW (xy and z terms), SCALE_LW;

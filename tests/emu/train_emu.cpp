@@ -79,17 +79,19 @@ extern "C" int emu_train_step(const float* const* weights, int B, int N, const f
     F(w.ts_st0, Bz * 64); F(w.ts_st1, Bz * 64); F(w.dts, Bz * 6);
     for (int h = 0; h < 2; ++h) {
       F(w.cset[h], S * 256); F(w.ry0[h], R * 256); F(w.ru0[h], R * 256); F(w.ry1[h], R * 256); F(w.rst0[h], Bz * 64);
-      F(w.rst1[h], Bz * 64); F(w.wsum[h], Bz * 256);
+      F(w.rst1[h], Bz * 64); F(w.wsum[h], Bz * 256); F(w.ru1[h], R * 256);
     }
-    F(w.ru1, R * 256); F(w.r6, Bz * 6); F(w.swp, 2);
+    F(w.r6, Bz * 6); F(w.swp, 2);
     F(w.lossp, Bz * 6); F(w.losses, 8); F(w.dpose, Bz * 15); F(w.d_r6, Bz * 6); F(w.d_dts, Bz * 6); F(w.tsd_u, Bz * 256);
     F(w.tsd_u0, Bz * 256); F(w.ts_din, Bz * 1091); F(w.gn_m, Bz * 64); F(w.gnp_g, Bz * 256); F(w.gnp_b, Bz * 256);
-    F(w.dg, S * 1024); F(w.dpfmax, S * 64); F(w.dpf, R * 64); F(w.e, Bz * 256); F(w.du, R * 256); F(w.du0, R * 256);
-    F(w.dcset, S * 256); F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
+    F(w.dg, S * 1024); F(w.dpfmax, S * 64); F(w.dpf, R * 64);
+    for (int h = 0; h < 2; ++h) { F(w.e[h], Bz * 256); F(w.du[h], R * 256); F(w.du0[h], R * 256); F(w.dcset[h], S * 256); }
+    F(w.d512, R * 512); F(w.d128, R * 128); F(w.d64, R * 64); F(w.dh1, R * 64); F(w.dt64, S * 4096);
     F(w.dfc2, S * 256); F(w.dfc1, S * 512); F(w.dmax, S * 1024); F(w.dqp, R * 3); F(w.dt3, S * 9);
     F(w.partial, TrainWs::kPartialFloats); F(w.cs_partial, TrainWs::kCsFloats); F(w.loss_gs, Bz * 9);
-    F(w.partial_ts, TrainWs::kPartialFloats); F(w.gn_m_ts, Bz * 64); F(w.gnp_g_ts, Bz * 256); F(w.gnp_b_ts, Bz * 256);
-    sl.push_back({reinterpret_cast<char*>(w.gn_part_ts), Bz * 32 * 18 * sizeof(double)});
+    F(w.partial_ts, TrainWs::kPartialFloats); F(w.cs_partial_ts, TrainWs::kCsFloats); F(w.gn_m_ts, Bz * 64); F(w.gnp_g_ts, Bz * 256);
+    F(w.gnp_b_ts, Bz * 256);
+    sl.push_back({reinterpret_cast<char*>(w.gn_part_ts), Bz * TrainWs::kGnChunks * 32 * 18 * sizeof(double)});
     I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024); I(w.mb_key, S * 1024);
     sl.push_back({reinterpret_cast<char*>(w.gn_part), Bz * TrainWs::kGnChunks * 32 * 18 * sizeof(double)});
     sl.push_back({reinterpret_cast<char*>(w.is_sym), Bz});

@@ -309,3 +309,40 @@ def test_train_step_other_sizes_against_fp64_oracle(B, N, sym, monkeypatch):
             assert torch.equal(p2, pose) and torch.equal(s2, scale) and torch.equal(l2, losses)
             assert torch.equal(eng.train_grads_flat(1.0), flat)
         eng.close()
+
+
+@pytest.mark.parametrize("B", [6, 16])
+def test_train_step_lanes_are_bit_identical_to_one_lane(B, monkeypatch):
+    """The ts head and the y rotation head run as a side lane next to the x head (second stream / graph branch, own scratch,
+    per-head buffers; shared gradients accumulated after the join in the one-lane order).  One lane (CATRE_TRAIN_LANES=0) and two
+    must give the same bits, kernel by kernel and as a replayed graph, twenty times over: any buffer the two lanes shared by
+    mistake would show up here as a difference or as run-to-run noise."""
+    w = synth.load_weights()
+    rots = y_symmetry_rotations()
+    batch, tgt = synth.make_train_batch(B, 1024, 31, round_robin_cls=True)
+    d = batch.to("cuda")
+    x_pm = (d.pcl - d.init_pose[:, :, 3].unsqueeze(1)).contiguous()
+    tfd_pm = ((d.prior * d.init_scale.unsqueeze(1)) @ d.init_pose[:, :, :3].transpose(1, 2)).contiguous()
+    args = (x_pm, tfd_pm, d.prior, d.init_pose, d.init_scale, d.K, tgt.gt_pose.cuda(), tgt.gt_scale.cuda(), tgt.sym_y.numpy(), rots)
+
+    def run(eng):
+        pose, scale, losses = eng.train_step(*args)
+        flat = eng.train_grads_flat(1.0)
+        torch.cuda.synchronize()
+        return pose.clone(), scale.clone(), losses.clone(), flat
+
+    monkeypatch.setenv("CATRE_TRAIN_LANES", "0")
+    monkeypatch.setenv("CATRE_TRAIN_GRAPH", "0")
+    one = engine.Engine(1024, 16, "fp32", 0)
+    one.load_weights(w)
+    want = run(one)
+    one.close()
+    monkeypatch.setenv("CATRE_TRAIN_LANES", "1")
+    for graph in ("0", "1"):
+        monkeypatch.setenv("CATRE_TRAIN_GRAPH", graph)
+        eng = engine.Engine(1024, 16, "fp32", 0)
+        eng.load_weights(w)
+        for _ in range(20):
+            for x, y in zip(run(eng), want):
+                assert torch.equal(x, y), graph
+        eng.close()
