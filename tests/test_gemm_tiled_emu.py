@@ -17,7 +17,7 @@ class GemmP(ctypes.Structure):  # catre_train::GemmP (train_kernels.cuh)
     _fields_ = [("A", P), ("sam", I64), ("sak", I64), ("sab", I64), ("B", P), ("sbk", I64), ("sbn", I64), ("sbb", I64),
                 ("C", P), ("scm", I64), ("scn", I64), ("scb", I64), ("bias", P), ("sbias_b", I64),
                 ("M", I32), ("N", I32), ("K", I32), ("relu", I32), ("accumulate", I32), ("splits", I32), ("k_per", I32),
-                ("partial", P), ("f16", I32)]
+                ("partial", P), ("f16", I32), ("bias_grad_partial", P)]
 
 
 @pytest.fixture(scope="module")
