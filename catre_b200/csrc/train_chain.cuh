@@ -137,6 +137,7 @@ struct Chain {
   // with which a head adds to the SHARED gradients (dg, dpf) are issued after the join for the y head, so the accumulation
   // order -- x, y, ts -- and with it every bit of the result is the same with one lane or two.
   bool side = false;
+  bool split_lin_bwd = false;  // lin_bwd may use the side lane for its parameter gradients (set while no other side lane runs)
   float* sc_partial() const { return side ? w.partial_ts : w.partial; }
   float* sc_cs_partial() const { return side ? w.cs_partial_ts : w.cs_partial; }
   double* sc_gn_part() const { return side ? w.gn_part_ts : w.gn_part; }
@@ -245,10 +246,17 @@ struct Chain {
   void lin_bwd(int wi, const float* x, int K, const float* dy, int C, long long ldy, long long rows, float* dx, int dx_acc,
                int ldw = 0, int woff = 0, bool with_bias = true) {
     if (ldw == 0) ldw = K;
+    // the parameter gradients (dW, db) and the data gradient (dx) only share their inputs: where the side lane is free (the
+    // encoder part of the backward, split_lin_bwd) the former are issued on it next to the latter and joined right here, so
+    // nothing outside this function sees a difference
+    const bool sub = split_lin_bwd && !side && dx != nullptr;
+    if (sub) begin_side();
     const bool folded = gemm(dy, 1, ldy, x, K, 1, w.G[wi] + woff, ldw, 1, C, K, (int)rows, nullptr, 0, 1, 1, 0, 0, 0, 0,
                              with_bias ? w.G[wi + 1] : nullptr);
     if (with_bias && !folded) colsum(dy, rows, C, ldy, w.G[wi + 1], 1);
+    if (sub) end_side();
     if (dx) gemm(dy, ldy, 1, W[wi] + woff, ldw, 1, dx, K, 1, (int)rows, K, C, nullptr, 0, dx_acc);
+    if (sub) o.join();
   }
   // wsum[b, c] = sum_p wp[p] u1[b, p, c]: chunked over the points, then the chunks of an object in order
   void rot_wsum(const float* u1, const float* wp, float* wsum, int B, int P) {
@@ -436,6 +444,7 @@ struct Chain {
     o.join();
     rot_bwd_shared(1, B);
     // ---- encoder
+    split_lin_bwd = true;
     o.run(KTsScatter{w.ts_din, w.dg, w.dpfmax}, cdiv(1088, 256), B, 1, 256);  // += on top of the rotation heads' share
     o.run(KScatterMax{w.dpfmax, w.pfarg, w.dpf, N, 64}, 1, S, 1, 64);
     max_bwd_dx(w.dg, nullptr, W[W_CONV4], w.garg, w.d512, S, 1024, 512, w.a512);  // incl. the ReLU mask of conv3's output
@@ -456,6 +465,7 @@ struct Chain {
       o.run(KColSum{w.cs_partial, w.dt3, (long long)S * chunks, 9, chunks, 0, 9}, 1, S, 1, 32);
     }
     tnet_bwd(w.q, 3, W_STN, 3, w.s64, w.s128, w.smax, w.sarg, w.sfc1, w.sfc2, w.dt3, nullptr, S);
+    split_lin_bwd = false;
   }
 };
 
