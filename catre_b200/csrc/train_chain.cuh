@@ -52,7 +52,8 @@ struct TrainWs {
   // backward); the per-head buffers above ([2]) exist for the same reason
   float *partial_ts, *cs_partial_ts, *gn_m_ts, *gnp_g_ts, *gnp_b_ts;
   double* gn_part_ts;
-  int *mb_start, *mb_cnt, *mb_list, *mb_key;  // inverse arg-max map of the sparse max-pool backward: [S, N], [S, N], [S, 1024] x 2
+  // inverse arg-max maps of the sparse max-pool backward, one per max-pooled layer (stn, fstn, trunk): [S, N], [S, N], [S, 1024] x 2
+  int *mb_start[3], *mb_cnt[3], *mb_list[3], *mb_key[3];
   double* gn_part;  // [maxB, kGnChunks, 32, 18]; also the point-matching partials of the loss [maxB, kLossChunks, 13]
   unsigned char* is_sym;
   float* sym_rots;
@@ -101,7 +102,7 @@ inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base, size_t gap = 0)
   F(w.partial_ts, TrainWs::kPartialFloats); F(w.cs_partial_ts, TrainWs::kCsFloats); F(w.gn_m_ts, B * 64); F(w.gnp_g_ts, B * 256);
   F(w.gnp_b_ts, B * 256);
   w.gn_part_ts = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
-  I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024); I(w.mb_key, S * 1024);
+  for (int i = 0; i < 3; ++i) { I(w.mb_start[i], S * N); I(w.mb_cnt[i], S * N); I(w.mb_list[i], S * 1024); I(w.mb_key[i], S * 1024); }
   w.gn_part = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
   w.is_sym = reinterpret_cast<unsigned char*>(take(B));
   F(w.sym_rots, (size_t)TrainWs::kMaxSymRots * 9);
@@ -224,21 +225,31 @@ struct Chain {
       o.run(KColMaxArg{z, vmax, arg, N, C}, cdiv(C, 256), S, 1, C < 256 ? 64 : 256);
       return;
     }
-    float* pv = w.partial;
-    int* pi = reinterpret_cast<int*>(w.partial + TrainWs::kPartialFloats / 2);
+    float* pv = sc_partial();
+    int* pi = reinterpret_cast<int*>(sc_partial() + TrainWs::kPartialFloats / 2);
     const unsigned nt = C < 256 ? 64 : 256;
     o.run(KColMaxArgPart{z, pv, pi, N, C, N / chunks}, cdiv(C, nt), chunks, S, nt);
     o.run(KColMaxArgMerge{pv, pi, vmax, arg, chunks, C}, cdiv(C, nt), S, 1, nt);
   }
   // sparse backward of a max-pooled layer: dx[(s, n), :] from d(max) [S, C] (KMaxBwdIndex + KMaxBwdGather)
+  // The inverse arg-max map depends on the forward pass only, so it is built there, on the side lane, right after the layer's
+  // arg-max exists (the main lane goes on with the next layers; the first join after it -- the heads' -- covers it): three
+  // rank + range launch pairs leave the backward's critical path.  One slot per max-pooled layer.
+  int mb_slot(const int* arg) const { return arg == w.sarg ? 0 : (arg == w.farg ? 1 : 2); }
+  void build_max_index(const int* arg, int S, int C) {
+    const int i = mb_slot(arg);
+    begin_side();
+    o.run(KMaxBwdRank{arg, w.mb_list[i], w.mb_key[i], C}, cdiv(C, 128), S, 1, 128);
+    o.run(KMaxBwdRange{w.mb_key[i], w.mb_start[i], w.mb_cnt[i], N, C}, cdiv(N, 128), S, 1, 128);
+    end_side();
+  }
   // `act`: the layer's input activation [S N, K]; dx is zeroed where it is not positive (the ReLU below the layer, folded in)
   void max_bwd_dx(const float* dmax, const float* relu_max, const float* Wt, const int* arg, float* dx, int S, int C, int K,
                   const float* act) {
-    o.run(KMaxBwdRank{arg, w.mb_list, w.mb_key, C}, cdiv(C, 128), S, 1, 128);
-    o.run(KMaxBwdRange{w.mb_key, w.mb_start, w.mb_cnt, N, C}, cdiv(N, 128), S, 1, 128);
+    const int i = mb_slot(arg);
     const int kq = K / 4, nt = 128;
     const int ppb = (kq < nt && nt % kq == 0) ? nt / kq : 1;  // points per block
-    o.run(KMaxBwdGather{dmax, relu_max, Wt, w.mb_start, w.mb_cnt, w.mb_list, dx, act, N, C, K, ppb}, ppb > 1 ? 1 : cdiv(kq, nt),
+    o.run(KMaxBwdGather{dmax, relu_max, Wt, w.mb_start[i], w.mb_cnt[i], w.mb_list[i], dx, act, N, C, K, ppb}, ppb > 1 ? 1 : cdiv(kq, nt),
           cdiv(N, ppb), S, nt);
   }
   // backward of y = x W^T + b for checkpoint tensor wi viewed as [C, ldw] with the K input columns at woff:
@@ -297,6 +308,7 @@ struct Chain {
     layer(x, Kin, wb + T_CONV1, 64, c64, R, 1);
     layer(c64, 64, wb + T_CONV2, 128, c128, R, 1);
     layer_max(c128, 128, wb + T_CONV3, 1024, vmax, arg, S, 1);
+    build_max_index(arg, S, 1024);
     layer(vmax, 1024, wb + T_FC1, 512, fc1, S, 1);
     layer(fc1, 512, wb + T_FC2, 256, fc2, S, 1);
     layer(fc2, 256, wb + T_FC3, k * k, tout, S, 0);
@@ -380,10 +392,13 @@ struct Chain {
     layer(w.qp, 3, W_CONV1, 64, w.h1, R, 1);
     tnet_fwd(w.h1, 64, W_FSTN, 64, w.f64, w.f128, w.fmax, w.farg, w.ffc1, w.ffc2, w.t64, S);
     gemm(w.h1, 64, 1, w.t64, 64, 1, w.pf, 64, 1, N, 64, 64, nullptr, 0, 0, S, (long long)N * 64, 4096, (long long)N * 64);  // pf = h1 . T64
+    begin_side();  // max over the points of the 64 point features (ts-head input): next to the trunk's wide layers; its
+    colmax(w.pf, w.pfmax, w.pfarg, S, 64);  // consumers are the side lane itself (ts head) and the backward
+    end_side();
     layer(w.pf, 64, W_CONV2, 128, w.a128, R, 1);
     layer(w.a128, 128, W_CONV3, 512, w.a512, R, 1);
     layer_max(w.a512, 512, W_CONV4, 1024, w.g, w.garg, S, 0);  // no ReLU after conv4 (pointnet.py:114)
-    colmax(w.pf, w.pfmax, w.pfarg, S, 64);
+    build_max_index(w.garg, S, 1024);
     // translation / size head (heads/fc_trans_size_head.py:61-70) and the y rotation head: the side lane
     begin_side();
     o.run(KTsGather{w.g, w.pfmax, in.scale, w.ts_in}, cdiv(1091, 256), B, 1, 256);

@@ -92,7 +92,7 @@ extern "C" int emu_train_step(const float* const* weights, int B, int N, const f
     F(w.partial_ts, TrainWs::kPartialFloats); F(w.cs_partial_ts, TrainWs::kCsFloats); F(w.gn_m_ts, Bz * 64); F(w.gnp_g_ts, Bz * 256);
     F(w.gnp_b_ts, Bz * 256);
     sl.push_back({reinterpret_cast<char*>(w.gn_part_ts), Bz * TrainWs::kGnChunks * 32 * 18 * sizeof(double)});
-    I(w.mb_start, S * N); I(w.mb_cnt, S * N); I(w.mb_list, S * 1024); I(w.mb_key, S * 1024);
+    for (int i = 0; i < 3; ++i) { I(w.mb_start[i], S * N); I(w.mb_cnt[i], S * N); I(w.mb_list[i], S * 1024); I(w.mb_key[i], S * 1024); }
     sl.push_back({reinterpret_cast<char*>(w.gn_part), Bz * TrainWs::kGnChunks * 32 * 18 * sizeof(double)});
     sl.push_back({reinterpret_cast<char*>(w.is_sym), Bz});
     F(w.sym_rots, (size_t)TrainWs::kMaxSymRots * 9);
