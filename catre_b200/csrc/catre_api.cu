@@ -112,6 +112,8 @@ struct catre_engine {
   TcPair tw_rot1s;            // both heads' layers.3 weights stacked [512, 256] (fused rot kernel)
   cudaStream_t side = nullptr;           // the ts head runs here, underneath the rot-head kernels
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t side2 = nullptr;          // second side lane of the training chain (the ts head's)
+  cudaEvent_t ev_join2 = nullptr;
   float* dts = nullptr;                  // [B, 6] raw ts-head outputs
   CUtensorMap tw_rot0_nb[2];  // rot layer-0 point-feature weights [512, 64] as an N-side operand (256-row boxes)
   float *fstn_fc3_wT = nullptr;  // fstn.fc3 rows permuted so the FC emits T64^T (row j = output channel j of pf = h1 . T64)
@@ -717,20 +719,21 @@ struct CudaTrainOps {
   void note(cudaError_t st) { if (err == cudaSuccess && st != cudaSuccess) err = st; }
   // lanes (train_chain.cuh: the ts head next to the rotation heads): a second stream between fork() and join(), ordered by two
   // events; under stream capture the same calls become parallel branches of the graph.  CATRE_TRAIN_LANES=0: one lane.
-  cudaStream_t s_main = nullptr, s_side = nullptr;
-  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  cudaStream_t s_main = nullptr, s_side[2] = {nullptr, nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[2] = {nullptr, nullptr};
   bool lanes = false;
   void fork() {
     if (!lanes) return;
-    s_main = s;
     note(cudaEventRecord(ev_fork, s_main));
-    note(cudaStreamWaitEvent(s_side, ev_fork, 0));
+    for (int i = 0; i < 2; ++i) note(cudaStreamWaitEvent(s_side[i], ev_fork, 0));
   }
-  void lane(int i) { if (lanes) s = i ? s_side : s_main; }
+  void lane(int i) { if (lanes) s = i ? s_side[i - 1] : s_main; }
   void join() {
     if (!lanes) return;
-    note(cudaEventRecord(ev_join, s_side));
-    note(cudaStreamWaitEvent(s_main, ev_join, 0));
+    for (int i = 0; i < 2; ++i) {
+      note(cudaEventRecord(ev_join[i], s_side[i]));
+      note(cudaStreamWaitEvent(s_main, ev_join[i], 0));
+    }
     s = s_main;
   }
   // carve: ask for the maximum shared-memory carve-out for the small kernels too, so that the SMs do not switch their L1 /
@@ -925,7 +928,9 @@ int catre_create(catre_engine** out, const catre_cfg* cfg) {
   }
   if (cudaStreamCreateWithFlags(&e->side, cudaStreamNonBlocking) != cudaSuccess ||
       cudaEventCreateWithFlags(&e->ev_fork, cudaEventDisableTiming) != cudaSuccess ||
-      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess) rc |= 1;
+      cudaEventCreateWithFlags(&e->ev_join, cudaEventDisableTiming) != cudaSuccess ||
+      cudaStreamCreateWithFlags(&e->side2, cudaStreamNonBlocking) != cudaSuccess ||
+      cudaEventCreateWithFlags(&e->ev_join2, cudaEventDisableTiming) != cudaSuccess) rc |= 1;
   if (!rc && tc) {
     auto pair = [&](TcPair& t, size_t cols, size_t rows) {
       rc |= dalloc(e, &t.hi, rows * cols);
@@ -970,6 +975,8 @@ void catre_destroy(catre_engine* e) {
   if (e->tg_io) cudaFree(e->tg_io);
   if (e->cap) cudaStreamDestroy(e->cap);
   if (e->side) cudaStreamDestroy(e->side);
+  if (e->side2) cudaStreamDestroy(e->side2);
+  if (e->ev_join2) cudaEventDestroy(e->ev_join2);
   if (e->ev_fork) cudaEventDestroy(e->ev_fork);
   if (e->ev_join) cudaEventDestroy(e->ev_join);
   for (auto& ev : e->ev_pending) { cudaEventDestroy(ev.a); cudaEventDestroy(ev.b); }
@@ -1558,8 +1565,9 @@ int catre_train_step(catre_engine* e, const float* x_pm, const float* tfd_pm, co
     CudaTrainOps ops{st, naive_gemm, gemm_v2, gemm_tc, e->num_sms};
     ops.carve = carve;
     ops.fold_bg = fold_bg;
-    ops.lanes = lanes && e->side && e->ev_fork && e->ev_join;
-    ops.s_main = st; ops.s_side = e->side; ops.ev_fork = e->ev_fork; ops.ev_join = e->ev_join;
+    ops.lanes = lanes && e->side && e->side2 && e->ev_fork && e->ev_join && e->ev_join2;
+    ops.s_main = st; ops.s_side[0] = e->side; ops.s_side[1] = e->side2; ops.ev_fork = e->ev_fork; ops.ev_join[0] = e->ev_join;
+    ops.ev_join[1] = e->ev_join2;
     catre_train::Chain<CudaTrainOps> chain{ops, w, Wp, e->N};
     chain.forward(in);
     chain.loss(in);

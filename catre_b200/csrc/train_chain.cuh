@@ -52,6 +52,9 @@ struct TrainWs {
   // backward); the per-head buffers above ([2]) exist for the same reason
   float *partial_ts, *cs_partial_ts, *gn_m_ts, *gnp_g_ts, *gnp_b_ts;
   double* gn_part_ts;
+  // third set: the ts head's own lane (GroupNorm over one "point": one chunk)
+  float *partial_l2, *cs_partial_l2, *gn_m_l2, *gnp_g_l2, *gnp_b_l2;
+  double* gn_part_l2;
   // inverse arg-max maps of the sparse max-pool backward, one per max-pooled layer (stn, fstn, trunk): [S, N], [S, N], [S, 1024] x 2
   int *mb_start[3], *mb_cnt[3], *mb_list[3], *mb_key[3];
   double* gn_part;  // [maxB, kGnChunks, 32, 18]; also the point-matching partials of the loss [maxB, kLossChunks, 13]
@@ -102,6 +105,9 @@ inline size_t ws_layout(TrainWs& w, int maxB, int N, char* base, size_t gap = 0)
   F(w.partial_ts, TrainWs::kPartialFloats); F(w.cs_partial_ts, TrainWs::kCsFloats); F(w.gn_m_ts, B * 64); F(w.gnp_g_ts, B * 256);
   F(w.gnp_b_ts, B * 256);
   w.gn_part_ts = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
+  F(w.partial_l2, TrainWs::kPartialFloats); F(w.cs_partial_l2, TrainWs::kCsFloats); F(w.gn_m_l2, B * 64); F(w.gnp_g_l2, B * 256);
+  F(w.gnp_b_l2, B * 256);
+  w.gn_part_l2 = reinterpret_cast<double*>(take(B * 32 * 18 * sizeof(double)));
   for (int i = 0; i < 3; ++i) { I(w.mb_start[i], S * N); I(w.mb_cnt[i], S * N); I(w.mb_list[i], S * 1024); I(w.mb_key[i], S * 1024); }
   w.gn_part = reinterpret_cast<double*>(take(B * TrainWs::kGnChunks * 32 * 18 * sizeof(double)));
   w.is_sym = reinterpret_cast<unsigned char*>(take(B));
@@ -137,16 +143,16 @@ struct Chain {
   // split-K / column-sum / GroupNorm scratch and the heads have their own activation and gradient buffers; the two products
   // with which a head adds to the SHARED gradients (dg, dpf) are issued after the join for the y head, so the accumulation
   // order -- x, y, ts -- and with it every bit of the result is the same with one lane or two.
-  bool side = false;
+  int lane = 0;       // lane being recorded: 0 main, 1 side (y head, per-layer parameter gradients, forward-time index builds), 2 ts head
   bool split_lin_bwd = false;  // lin_bwd may use the side lane for its parameter gradients (set while no other side lane runs)
-  float* sc_partial() const { return side ? w.partial_ts : w.partial; }
-  float* sc_cs_partial() const { return side ? w.cs_partial_ts : w.cs_partial; }
-  double* sc_gn_part() const { return side ? w.gn_part_ts : w.gn_part; }
-  float* sc_gn_m() const { return side ? w.gn_m_ts : w.gn_m; }
-  float* sc_gnp_g() const { return side ? w.gnp_g_ts : w.gnp_g; }
-  float* sc_gnp_b() const { return side ? w.gnp_b_ts : w.gnp_b; }
-  void begin_side() { o.fork(); o.lane(1); side = true; }
-  void end_side() { side = false; o.lane(0); }
+  float* sc_partial() const { return lane == 0 ? w.partial : (lane == 1 ? w.partial_ts : w.partial_l2); }
+  float* sc_cs_partial() const { return lane == 0 ? w.cs_partial : (lane == 1 ? w.cs_partial_ts : w.cs_partial_l2); }
+  double* sc_gn_part() const { return lane == 0 ? w.gn_part : (lane == 1 ? w.gn_part_ts : w.gn_part_l2); }
+  float* sc_gn_m() const { return lane == 0 ? w.gn_m : (lane == 1 ? w.gn_m_ts : w.gn_m_l2); }
+  float* sc_gnp_g() const { return lane == 0 ? w.gnp_g : (lane == 1 ? w.gnp_g_ts : w.gnp_g_l2); }
+  float* sc_gnp_b() const { return lane == 0 ? w.gnp_b : (lane == 1 ? w.gnp_b_ts : w.gnp_b_l2); }
+  void begin_side(int i = 1) { o.fork(); o.lane(i); lane = i; }
+  void end_side() { lane = 0; o.lane(0); }
 
   static unsigned cdiv(long long a, long long b) { return (unsigned)((a + b - 1) / b); }
 
@@ -260,7 +266,7 @@ struct Chain {
     // the parameter gradients (dW, db) and the data gradient (dx) only share their inputs: where the side lane is free (the
     // encoder part of the backward, split_lin_bwd) the former are issued on it next to the latter and joined right here, so
     // nothing outside this function sees a difference
-    const bool sub = split_lin_bwd && !side && dx != nullptr;
+    const bool sub = split_lin_bwd && lane == 0 && dx != nullptr;
     if (sub) begin_side();
     const bool folded = gemm(dy, 1, ldy, x, K, 1, w.G[wi] + woff, ldw, 1, C, K, (int)rows, nullptr, 0, 1, 1, 0, 0, 0, 0,
                              with_bias ? w.G[wi + 1] : nullptr);
@@ -399,8 +405,9 @@ struct Chain {
     layer(w.a128, 128, W_CONV3, 512, w.a512, R, 1);
     layer_max(w.a512, 512, W_CONV4, 1024, w.g, w.garg, S, 0);  // no ReLU after conv4 (pointnet.py:114)
     build_max_index(w.garg, S, 1024);
-    // translation / size head (heads/fc_trans_size_head.py:61-70) and the y rotation head: the side lane
-    begin_side();
+    // translation / size head (heads/fc_trans_size_head.py:61-70): its own lane; the y rotation head: the side lane
+    o.join();  // the point-feature max (side lane) feeds the ts head (another lane)
+    begin_side(2);
     o.run(KTsGather{w.g, w.pfmax, in.scale, w.ts_in}, cdiv(1091, 256), B, 1, 256);
     layer(w.ts_in, 1091, W_TS + S_L0, 256, w.ts_y0, B, 0);
     gn_fwd(w.ts_y0, w.ts_st0, W[W_TS + S_GN0], W[W_TS + S_GN0 + 1], w.ts_u0, B, 1);
@@ -408,6 +415,8 @@ struct Chain {
     gn_fwd(w.ts_y1, w.ts_st1, W[W_TS + S_GN1], W[W_TS + S_GN1 + 1], w.ts_u1, B, 1);
     gemm(w.ts_u1, 256, 1, W[W_TS + S_FCT], 1, 256, w.dts, 6, 1, B, 3, 256, W[W_TS + S_FCT + 1], 0, 0);
     gemm(w.ts_u1, 256, 1, W[W_TS + S_FCS], 1, 256, w.dts + 3, 6, 1, B, 3, 256, W[W_TS + S_FCS + 1], 0, 0);
+    end_side();
+    begin_side(1);
     rot_fwd(1, B);
     end_side();
     rot_fwd(0, B);
@@ -443,14 +452,17 @@ struct Chain {
     o.zero(w.dpfmax, (size_t)S * 64 * sizeof(float));
     o.zero(w.dpf, (size_t)R * 64 * sizeof(float));
     o.run(KPoseBwd{w.dpose, w.r6, w.dts, in.pose, in.K, w.d_r6, w.d_dts, B}, cdiv(B, 64), 1, 1, 64);
-    // ---- side lane: the ts head (its gradient w.r.t. the global feature is added after the join) and the y rotation head
-    begin_side();
+    // ---- the ts head on its own lane (its gradient w.r.t. the global feature is added after the join), the y rotation head on
+    //      the side lane
+    begin_side(2);
     lin_bwd(W_TS + S_FCT, w.ts_u1, 256, w.d_dts, 3, 6, B, w.tsd_u, 0);
     lin_bwd(W_TS + S_FCS, w.ts_u1, 256, w.d_dts + 3, 3, 6, B, w.tsd_u, 1);
     gn_bwd(w.tsd_u, w.ts_y1, w.ts_st1, W_TS + S_GN1, B, 1);
     lin_bwd(W_TS + S_L3, w.ts_u0, 256, w.tsd_u, 256, 256, B, w.tsd_u0, 0);
     gn_bwd(w.tsd_u0, w.ts_y0, w.ts_st0, W_TS + S_GN0, B, 1);
     lin_bwd(W_TS + S_L0, w.ts_in, 1091, w.tsd_u0, 256, 256, B, w.ts_din, 0);
+    end_side();
+    begin_side(1);
     rot_bwd(1, B);
     end_side();
     // ---- main lane: the x rotation head, then (after the join) the shared-gradient products of both heads in the order x, y

@@ -92,6 +92,9 @@ extern "C" int emu_train_step(const float* const* weights, int B, int N, const f
     F(w.partial_ts, TrainWs::kPartialFloats); F(w.cs_partial_ts, TrainWs::kCsFloats); F(w.gn_m_ts, Bz * 64); F(w.gnp_g_ts, Bz * 256);
     F(w.gnp_b_ts, Bz * 256);
     sl.push_back({reinterpret_cast<char*>(w.gn_part_ts), Bz * TrainWs::kGnChunks * 32 * 18 * sizeof(double)});
+    F(w.partial_l2, TrainWs::kPartialFloats); F(w.cs_partial_l2, TrainWs::kCsFloats); F(w.gn_m_l2, Bz * 64); F(w.gnp_g_l2, Bz * 256);
+    F(w.gnp_b_l2, Bz * 256);
+    sl.push_back({reinterpret_cast<char*>(w.gn_part_l2), Bz * 32 * 18 * sizeof(double)});
     for (int i = 0; i < 3; ++i) { I(w.mb_start[i], S * N); I(w.mb_cnt[i], S * N); I(w.mb_list[i], S * 1024); I(w.mb_key[i], S * 1024); }
     sl.push_back({reinterpret_cast<char*>(w.gn_part), Bz * TrainWs::kGnChunks * 32 * 18 * sizeof(double)});
     sl.push_back({reinterpret_cast<char*>(w.is_sym), Bz});
