@@ -329,8 +329,13 @@ struct Chain {
     lin_bwd(wb + T_FC2, fc1, 512, w.dfc2, 256, 256, S, w.dfc1, 0);
     relu_mask(w.dfc1, fc1, (long long)S * 512);
     lin_bwd(wb + T_FC1, vmax, 1024, w.dfc1, 512, 512, S, w.dmax, 0);
-    max_bwd_dx(w.dmax, vmax, W[wb + T_CONV3], arg, w.d128, S, 1024, 128, c128);  // incl. the ReLU mask of conv2's output
+    // the layer's parameter gradients next to its data gradient (both read d(max); joined here)
+    const bool sub = split_lin_bwd && lane == 0;
+    if (sub) begin_side();
     o.run(KMaxBwdDw{w.dmax, vmax, c128, arg, w.G[wb + T_CONV3], w.G[wb + T_CONV3 + 1], S, N, 1024, 128}, cdiv(128, 128), 1024, 1, 128);
+    if (sub) end_side();
+    max_bwd_dx(w.dmax, vmax, W[wb + T_CONV3], arg, w.d128, S, 1024, 128, c128);  // incl. the ReLU mask of conv2's output
+    if (sub) o.join();
     lin_bwd(wb + T_CONV2, c64, 64, w.d128, 128, 128, R, w.d64, 0);
     relu_mask(w.d64, c64, R * 64);
     lin_bwd(wb + T_CONV1, x, Kin, w.d64, 64, 64, R, dx_out, 1);
@@ -474,14 +479,20 @@ struct Chain {
     split_lin_bwd = true;
     o.run(KTsScatter{w.ts_din, w.dg, w.dpfmax}, cdiv(1088, 256), B, 1, 256);  // += on top of the rotation heads' share
     o.run(KScatterMax{w.dpfmax, w.pfarg, w.dpf, N, 64}, 1, S, 1, 64);
-    max_bwd_dx(w.dg, nullptr, W[W_CONV4], w.garg, w.d512, S, 1024, 512, w.a512);  // incl. the ReLU mask of conv3's output
+    begin_side();
     o.run(KMaxBwdDw{w.dg, nullptr, w.a512, w.garg, w.G[W_CONV4], w.G[W_CONV4 + 1], S, N, 1024, 512}, cdiv(512, 128), 1024, 1, 128);
+    end_side();
+    max_bwd_dx(w.dg, nullptr, W[W_CONV4], w.garg, w.d512, S, 1024, 512, w.a512);  // incl. the ReLU mask of conv3's output
+    o.join();
     lin_bwd(W_CONV3, w.a128, 128, w.d512, 512, 512, R, w.d128, 0);
     relu_mask(w.d128, w.a128, R * 128);
     lin_bwd(W_CONV2, w.pf, 64, w.d128, 128, 128, R, w.dpf, 1);
     // pf = h1 . T64 per set:  dh1 = dpf . T64^T,  dT64 = h1^T . dpf
-    gemm(w.dpf, 64, 1, w.t64, 1, 64, w.dh1, 64, 1, N, 64, 64, nullptr, 0, 0, S, (long long)N * 64, 4096, (long long)N * 64);
+    begin_side();
     gemm(w.h1, 1, 64, w.dpf, 64, 1, w.dt64, 64, 1, 64, 64, N, nullptr, 0, 0, S, (long long)N * 64, (long long)N * 64, 4096);
+    end_side();
+    gemm(w.dpf, 64, 1, w.t64, 1, 64, w.dh1, 64, 1, N, 64, 64, nullptr, 0, 0, S, (long long)N * 64, 4096, (long long)N * 64);
+    o.join();
     tnet_bwd(w.h1, 64, W_FSTN, 64, w.f64, w.f128, w.fmax, w.farg, w.ffc1, w.ffc2, w.dt64, w.dh1, S);
     relu_mask(w.dh1, w.h1, R * 64);
     lin_bwd(W_CONV1, w.qp, 3, w.dh1, 64, 64, R, w.dqp, 0);
