@@ -224,7 +224,11 @@ int catre_match_greedy(int32_t mode, const int32_t* sub_pred_off, const int32_t*
  * catre_train_step: forward + losses + backward for B objects, stream-ordered, no host sync.  From the second step of a
  *   (B, number of symmetric objects, n_sym_rots, loss weights) combination on, the ~240 launches of the chain are one
  *   CUDA graph replayed on engine-owned static copies of the inputs (captured on an internal stream, launched on
- *   `stream`; same kernels, same order, bit-identical results; CATRE_TRAIN_GRAPH=0 launches kernel by kernel).
+ *   `stream`; same kernels, same order, bit-identical results; CATRE_TRAIN_GRAPH=0 launches kernel by kernel).  Independent
+ *   parts of the chain (the x / y rotation heads and the ts head; a layer's parameter and data gradients in the encoder's
+ *   backward; index builds that depend on the forward only) are issued on two engine-owned side streams ordered by events --
+ *   parallel branches of the graph -- with per-lane scratch; accumulations into shared gradients keep the one-lane order, so
+ *   the results do not depend on it (CATRE_TRAIN_LANES=0: one lane).  The call is still stream-ordered on `stream`.
  *   x_pm / tfd_pm [B, n, 3]  the re-posed points the reference's forward receives (as in catre_forward_once)
  *   obj_kps [B, n, 3]        normalised category prior (batch["obj_kps"], the point-matching loss's points)
  *   pose [B,3,4], scale [B,3], K [B,3,3]; gt_pose [B,3,4] (batch["obj_pose"]), gt_scale [B,3]   -- all device
